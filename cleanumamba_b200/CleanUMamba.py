@@ -1,0 +1,221 @@
+"""``CleanUMamba`` nn.Module -- drop-in for /root/reference/src/network/CleanUMamba.py:30-550 on B200.
+
+The module keeps the reference's constructor signature (:33-54), module tree / ``state_dict`` keys
+(``encoder.{i}.{0,2}``, ``decoder.{j}.{0,2}``, ``tsfm_conv1/2``, ``tsfm_Mamba_layers.{l}.{mixer,norm}``, ``norm_f``),
+initialisation order (so a seeded constructor reproduces the reference's weights) and public methods
+(``forward``, ``feed``, ``flush``, ``valid_length``, ``pad_signal``, ``total_stride``, ``allocate_inference_cache``,
+``load_pruned_state_dict``).  The nn.Conv1d / nn.Linear / nn.LayerNorm children are PARAMETER HOLDERS only: the
+arithmetic of ``forward`` / ``feed`` runs in hand-written sm_100a kernels behind the C ABI of
+``libcleanumamba_sm100.so`` (see ``engine.py``).  There is no PyTorch / CPU fallback: on a non-CUDA tensor or with
+the library missing, ``forward`` raises.
+"""
+import copy
+import itertools
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from .layers import Activation
+from .mamba import InferenceParams, _init_weights, create_block
+
+
+def weight_scaling_init(layer):
+    """Demucs rescaling w, b /= sqrt(10 * std(w))  (/root/reference/src/util/util.py:174-181)."""
+    scale = torch.sqrt(10.0 * layer.weight.detach().std())
+    layer.weight.data /= scale
+    layer.bias.data /= scale
+
+
+class CleanUMamba(nn.Module):
+    def __init__(self, channels_input=1, channels_output=1, channels_H=64, max_H=768, encoder_n_layers=8,
+                 kernel_size=4, stride=2, encoder_groups=1, bypass_channels=0, glu_activation="Sigmoid",
+                 tsfm_n_layers=3, tsfm_n_head=8, tsfm_d_model=512, tsfm_d_inner=2048, fused_add_norm=False,
+                 use_fast_path=False, rms_norm=False, mamba_s4=False, LSTM=False, mamba_v2=False,
+                 residual_projection=False, norm_epsilon: float = 1e-5, normalize_input=True, device=None,
+                 dtype=None, math_mode="fp32"):
+        super().__init__()
+        assert glu_activation in ("Sigmoid", "ReLU", "SiLU", "GELU"), f"glu_activation={glu_activation} not supported"
+        for flag, name in ((mamba_s4, "mamba_s4"), (LSTM, "LSTM"), (mamba_v2, "mamba_v2"),
+                           (residual_projection, "residual_projection"), (rms_norm, "rms_norm")):
+            if flag:   # ablation variants of the reference are outside the hot path
+                raise NotImplementedError(f"cleanumamba_b200 implements the Mamba bottleneck path only ({name}=True)")
+        if encoder_groups != 1 or bypass_channels != 0:
+            raise NotImplementedError("cleanumamba_b200: encoder_groups=1 and bypass_channels=0 only (shipped configs)")
+        fk = dict(device=device, dtype=dtype)
+        self.channels_input, self.channels_output = channels_input, channels_output
+        self.channels_H, self.max_H = channels_H, max_H
+        self.encoder_n_layers, self.kernel_size, self.stride = encoder_n_layers, kernel_size, stride
+        self.tsfm_n_layers, self.tsfm_n_head = tsfm_n_layers, tsfm_n_head
+        self.tsfm_d_model, self.tsfm_d_inner = tsfm_d_model, tsfm_d_inner
+        self.residual_projection = residual_projection
+        self.normalize_input = normalize_input
+        self.glu_activation = glu_activation
+        self.norm_epsilon = norm_epsilon
+        self.dtype = dtype
+        self.math_mode = math_mode      # "fp32" (exact CUDA-core FFMA) | "tf32x3" (tcgen05, fp32-tolerance) | "tf32"
+
+        self.encoder, self.decoder = nn.ModuleList(), nn.ModuleList()
+        c_in, c_out, H = channels_input, channels_output, channels_H
+        for i in range(encoder_n_layers):
+            self.encoder.append(nn.Sequential(
+                nn.Conv1d(c_in, H, kernel_size, stride, **fk), nn.ReLU(),
+                nn.Conv1d(H, 2 * H, 1, **fk), Activation(glu_activation, 0)))
+            up = nn.Sequential(nn.Conv1d(H, 2 * H, 1, **fk), Activation(glu_activation, 0),
+                               nn.ConvTranspose1d(H, c_out, kernel_size, stride, **fk))
+            if i > 0:
+                up.append(nn.ReLU())
+            self.decoder.insert(0, up)
+            c_in = c_out = H
+            H = min(2 * H, max_H)
+
+        self.tsfm_conv1 = nn.Conv1d(c_out, tsfm_d_model, kernel_size=1, **fk)
+        ssm_cfg = dict(d_state=tsfm_d_model // tsfm_n_head, d_conv=4, expand=tsfm_d_inner // tsfm_d_model,
+                       use_fast_path=use_fast_path)
+        self.rms_norm, self.residual_in_fp32, self.fused_add_norm, self.LSTM = rms_norm, True, fused_add_norm, LSTM
+        self.tsfm_Mamba_layers = nn.ModuleList([
+            create_block(tsfm_d_model, ssm_cfg=ssm_cfg, norm_epsilon=norm_epsilon, rms_norm=rms_norm,
+                         residual_in_fp32=True, fused_add_norm=fused_add_norm, layer_idx=i, **fk)
+            for i in range(tsfm_n_layers)])
+        self.norm_f = nn.LayerNorm(tsfm_d_model, eps=norm_epsilon, **fk)
+        self.tsfm_conv2 = nn.Conv1d(tsfm_d_model, c_out, kernel_size=1, **fk)
+
+        for layer in self.modules():
+            if isinstance(layer, (nn.Conv1d, nn.ConvTranspose1d)):
+                weight_scaling_init(layer)
+        self.apply(partial(_init_weights, n_layer=tsfm_n_layers))
+
+        # streaming bookkeeping (same public fields as the reference, :208-216)
+        self.total_time = 0
+        self.frames = 0
+        self.input_std = 0
+        self.pending = torch.zeros(self.channels_input, 0, dtype=self.dtype, device=device)
+        self.frame_length = self.valid_length(1)
+        self.inference_params = None
+        self.encoder_decoder_state = {}
+        self._engine = None
+        self._stream = None
+
+    # ------------------------------------------------------------------ shape helpers (:219-250)
+    def valid_length(self, length):
+        n = length
+        for _ in range(self.encoder_n_layers):
+            n = 1 if n < self.kernel_size else 1 + math.ceil((n - self.kernel_size) / self.stride)
+        for _ in range(self.encoder_n_layers):
+            n = (n - 1) * self.stride + self.kernel_size
+        return int(n)
+
+    def pad_signal(self, input):
+        return nn.functional.pad(input, (0, self.valid_length(input.shape[-1]) - input.shape[-1]))
+
+    @property
+    def total_stride(self):
+        return self.stride ** self.encoder_n_layers
+
+    # ------------------------------------------------------------------ engine plumbing
+    def engine(self):
+        from .engine import Engine
+        if self._engine is None:
+            self._engine = Engine(self)
+        return self._engine
+
+    def forward(self, noisy_audio, return_skip_connections=False):
+        """(B, L) | (B, 1, L) -> (B, 1, L).  Like the reference (:260-262) the input tensor is normalised IN PLACE
+        when ``normalize_input`` is set."""
+        if noisy_audio.dim() == 2:
+            noisy_audio = noisy_audio.unsqueeze(1)
+        assert noisy_audio.dim() == 3 and noisy_audio.shape[1] == 1
+        if torch.is_grad_enabled() and (noisy_audio.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import forward_with_grad
+            return forward_with_grad(self, noisy_audio, return_skip_connections)
+        return self.engine().forward(noisy_audio, return_skip_connections)
+
+    # ------------------------------------------------------------------ streaming (:326-490)
+    def reset_time_per_frame(self):
+        self.total_time = 0
+        self.frames = 0
+
+    @property
+    def time_per_frame(self):
+        return 0 if self.frames == 0 else self.total_time / self.frames
+
+    def allocate_inference_cache_layer(self, layer, batch_size, dtype=None):
+        dev = layer.out_proj.weight.device
+        d = int(layer.d_model * layer.expand)
+        return (torch.zeros(batch_size, d, layer.d_conv, device=dev, dtype=dtype or layer.conv1d.weight.dtype),
+                torch.zeros(batch_size, d, layer.d_state, device=dev, dtype=dtype or layer.dt_proj.weight.dtype))
+
+    def allocate_inference_cache(self, batch_size, max_seqlen, dtype=None, **kwargs):
+        return {i: self.allocate_inference_cache_layer(blk.mixer, batch_size, dtype=dtype)
+                for i, blk in enumerate(self.tsfm_Mamba_layers)}
+
+    def stream_session(self, batch=1, compat_skip_order_bug=False):
+        """New carried-state streaming session for ``batch`` independent streams (extension: the reference's
+        ``feed`` is batch 1 and keeps its state on the module)."""
+        from .streaming import StreamSession
+        return StreamSession(self, batch=batch)
+
+    @torch.no_grad()
+    def feed(self, noisy_input):
+        """(1, n) -> (1, m): same contract as the reference's ``feed`` (:371-418).  The shipped skip indexing bug
+        (:474, crashes on every shipped checkpoint) is not reproduced: streaming == offline ``forward``."""
+        if noisy_input.dim() != 2:
+            raise ValueError("input should be two dimensional.")
+        if noisy_input.shape[0] != 1:
+            raise ValueError(f"Expected 1 channel, got {noisy_input.shape[0]}")
+        if self._stream is None:
+            self._stream = self.stream_session(batch=1)
+        out = self._stream.feed(noisy_input)
+        self.frames = self._stream.frames
+        self.pending = self._stream.pending_view()
+        return out
+
+    def flush(self):
+        if self._stream is None:
+            self._stream = self.stream_session(batch=1)
+        out = self._stream.flush()
+        self.frames = self._stream.frames
+        self.pending = self._stream.pending_view()
+        return out
+
+    # ------------------------------------------------------------------ pruned checkpoints (:492-550)
+    def load_pruned_state_dict(self, pruned_state_dict):
+        """Resize every parameter (and the bookkeeping attributes the pruning code relies on) to the shapes found in
+        ``pruned_state_dict``, then ``load_state_dict(strict=True)``."""
+        def resize(module, prefix):
+            own = itertools.chain(module._parameters.items(),
+                                  ((k, v) for k, v in module._buffers.items() if k not in module._non_persistent_buffers_set))
+            for name, tensor in own:
+                if tensor is None:
+                    continue
+                key = prefix + name
+                if key not in pruned_state_dict:
+                    print(f"Error cant find {key} in {module}")
+                    continue
+                tensor.data = copy.deepcopy(pruned_state_dict[key].data).to(tensor.device)
+            w = getattr(module, "weight", None)
+            if isinstance(module, nn.LayerNorm):
+                module.normalized_shape = tuple(w.shape)
+            elif isinstance(module, nn.ConvTranspose1d):
+                module.in_channels, module.out_channels = w.shape[0], w.shape[1]
+            elif isinstance(module, nn.Conv1d):
+                module.in_channels, module.out_channels = w.shape[1], w.shape[0]
+                if module.groups > 1:
+                    module.groups = w.shape[0]
+            elif isinstance(module, nn.Linear):
+                module.in_features, module.out_features = w.shape[1], w.shape[0]
+            for name, child in module._modules.items():
+                if child is not None:
+                    resize(child, prefix + name + ".")
+            if module.__class__.__name__ == "Mamba":
+                module.dt_rank = module.dt_proj.in_features
+                module.d_state = (module.x_proj.out_features - module.dt_rank) // 2
+                module.d_inner = module.x_proj.in_features
+                module.d_model = module.in_proj.in_features
+                module.expand = module.d_inner / module.d_model
+
+        resize(self, "")
+        self.load_state_dict(pruned_state_dict, strict=True)
+        self._engine = None
+        self._stream = None

@@ -1,0 +1,117 @@
+// extern "C" surface of libcleanumamba_sm100.so: argument validation, error reporting, dispatch.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace cum {
+
+static thread_local char g_err[512] = "";
+static int g_sm_count = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return CUM_ECUDA;
+}
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_sm_count;
+}
+
+static int validate_gemm(const cum_gemm_desc& d) {
+    CUM_REQUIRE(d.a && d.w && d.c, "gemm: null a/w/c pointer");
+    CUM_REQUIRE(d.batch > 0 && d.m > 0 && d.n > 0 && d.k > 0, "gemm: empty problem (batch=%d m=%d n=%d k=%d)", d.batch, d.m, d.n, d.k);
+    CUM_REQUIRE(d.taps == 1 || d.taps == 2, "gemm: taps=%d (must be 1 or 2)", d.taps);
+    CUM_REQUIRE(d.k % 4 == 0 && d.ldw % 4 == 0 && d.ldw >= d.k, "gemm: k=%d / ldw=%d must be multiples of 4 with ldw >= k", d.k, d.ldw);
+    CUM_REQUIRE(d.n % 8 == 0, "gemm: n=%d must be a multiple of 8", d.n);
+    CUM_REQUIRE(d.a_row_stride % 4 == 0 && d.a_batch_stride % 4 == 0 && d.a_row_stride >= 0, "gemm: a strides must be multiples of 4 elements");
+    CUM_REQUIRE(d.c_row_stride % 4 == 0 && d.c_batch_stride % 4 == 0, "gemm: c strides must be multiples of 4 elements");
+    CUM_REQUIRE(aligned16(d.a) && aligned16(d.w) && aligned16(d.c) && (!d.bias || aligned16(d.bias)), "gemm: a/w/c/bias must be 16-byte aligned");
+    CUM_REQUIRE(epi_valid(d.epilogue), "gemm: unknown epilogue %d", d.epilogue);
+    if (d.addend) {
+        CUM_REQUIRE(aligned16(d.addend) && d.add_row_stride % 4 == 0 && d.add_batch_stride % 4 == 0, "gemm: addend must be 16-byte aligned with strides multiple of 4");
+    }
+    CUM_REQUIRE(d.a_rows > 0, "gemm: a_rows=%d", d.a_rows);
+    return CUM_OK;
+}
+
+}  // namespace cum
+
+using namespace cum;
+
+extern "C" {
+
+int cum_abi_version(void) { return CUM_ABI_VERSION; }
+
+const char* cum_last_error(void) { return g_err; }
+
+int cum_init(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        set_error("cum_init: device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", device, prop.major, prop.minor);
+        return CUM_ENOTSUP;
+    }
+    g_sm_count = prop.multiProcessorCount;
+    return CUM_OK;
+}
+
+int cum_wave_normalize_fwd(float* x, float* std_out, int batch, int length, cum_stream_t stream) {
+    return wave_normalize_fwd(x, std_out, batch, length, (cudaStream_t)stream);
+}
+
+int cum_conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
+                    float* y, int rows_out, int c_pad, int kernel, int stride, cum_stream_t stream) {
+    return conv_in_fwd(x, x_stride, batch, length, w, bias, y, rows_out, c_pad, kernel, stride, (cudaStream_t)stream);
+}
+
+int cum_convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
+                      const float* scale, float* out, long long out_stride, int length, int kernel, int stride,
+                      cum_stream_t stream) {
+    return convt_out_fwd(g, batch, rows_in, c_pad, w, bias, scale, out, out_stride, length, kernel, stride,
+                         (cudaStream_t)stream);
+}
+
+int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream) {
+    if (!desc) { set_error("gemm: null descriptor"); return CUM_EINVAL; }
+    int rc = validate_gemm(*desc);
+    if (rc != CUM_OK) return rc;
+    switch (desc->math) {
+        case CUM_MATH_FP32: return gemm_simt_fwd(*desc, (cudaStream_t)stream);
+        case CUM_MATH_TF32X3:
+        case CUM_MATH_TF32: return gemm_tc_fwd(*desc, (cudaStream_t)stream);
+        default: set_error("gemm: unknown math mode %d", desc->math); return CUM_EINVAL;
+    }
+}
+
+int cum_ln_residual_fwd(const float* h, const float* residual_in, float* residual_out, float* normed,
+                        const float* gamma, const float* beta, float eps, long long rows, int c, int c_pad,
+                        cum_stream_t stream) {
+    return ln_residual_fwd(h, residual_in, residual_out, normed, gamma, beta, eps, rows, c, c_pad, (cudaStream_t)stream);
+}
+
+int cum_dwconv_silu_fwd(const float* x, long long x_batch_stride, long long x_row_stride, const float* w,
+                        const float* bias, float* y, const float* conv_state, float* conv_state_out, int batch,
+                        int len, int d_pad, int width, cum_stream_t stream) {
+    return dwconv_silu_fwd(x, x_batch_stride, x_row_stride, w, bias, y, conv_state, conv_state_out, batch, len, d_pad,
+                           width, (cudaStream_t)stream);
+}
+
+int cum_selective_scan_fwd(const cum_scan_desc* desc, cum_stream_t stream) {
+    if (!desc) { set_error("selective_scan: null descriptor"); return CUM_EINVAL; }
+    return selective_scan_fwd(*desc, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// cleanumamba_b200 -- shared device/host helpers (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/cleanumamba_b200.h"
+
+namespace cum {
+
+// thread-local last-error string (cum_last_error)
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+
+#define CUM_REQUIRE(cond, ...)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            ::cum::set_error(__VA_ARGS__);             \
+            return CUM_EINVAL;                         \
+        }                                              \
+    } while (0)
+
+#define CUM_LAUNCH_CHECK(what)                                          \
+    do {                                                                \
+        cudaError_t e__ = cudaGetLastError();                           \
+        if (e__ != cudaSuccess) return ::cum::cuda_fail(e__, what);     \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+__device__ __forceinline__ float siluf_(float v) { return v / (1.0f + expf(-v)); }
+__device__ __forceinline__ float geluf_(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+// GLU gate selected by the CUM_EPI_GLU_* code (layers.py:17-24)
+__device__ __forceinline__ float glu_gate(int epi, float b) {
+    switch (epi) {
+        case CUM_EPI_GLU_RELU: return fmaxf(b, 0.0f);
+        case CUM_EPI_GLU_SILU: return siluf_(b);
+        case CUM_EPI_GLU_GELU: return geluf_(b);
+        default:               return sigmoidf_(b);
+    }
+}
+__device__ __forceinline__ float unary_act(int epi, float v) {
+    switch (epi) {
+        case CUM_EPI_RELU: return fmaxf(v, 0.0f);
+        case CUM_EPI_SILU: return siluf_(v);
+        default:           return v;
+    }
+}
+static inline bool epi_is_glu(int epi) { return epi >= CUM_EPI_GLU_SIGMOID && epi <= CUM_EPI_GLU_GELU; }
+static inline bool epi_valid(int epi) {
+    return epi == CUM_EPI_NONE || epi == CUM_EPI_RELU || epi == CUM_EPI_SILU || epi_is_glu(epi);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// entry points implemented per translation unit (called by api.cu)
+int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStream_t st);
+int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
+                float* y, int rows_out, int c_pad, int kernel, int stride, cudaStream_t st);
+int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
+                  const float* scale, float* out, long long out_stride, int length, int kernel, int stride,
+                  cudaStream_t st);
+int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st);
+int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st);
+int ln_residual_fwd(const float* h, const float* residual_in, float* residual_out, float* normed,
+                    const float* gamma, const float* beta, float eps, long long rows, int c, int c_pad,
+                    cudaStream_t st);
+int dwconv_silu_fwd(const float* x, long long x_bs, long long x_rs, const float* w, const float* bias, float* y,
+                    const float* conv_state, float* conv_state_out, int batch, int len, int d_pad, int width,
+                    cudaStream_t st);
+int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st);
+
+int  sm_count();
+
+}  // namespace cum

@@ -1,0 +1,382 @@
+// Mamba-block operators in channels-last layout: residual add + LayerNorm, depthwise causal conv + SiLU,
+// selective scan (fwd) with optional carried state.  All HBM / MUFU-bound CUDA-core kernels.
+#include "common.cuh"
+
+namespace cum {
+
+// ---------------------------------------------------------------------------------------------------------
+// ln_residual: r = h (+ residual_in); normed = LayerNorm_c(r) * gamma + beta.   One warp per row, the row lives in
+// registers (NCH float4 per lane), two-pass mean / variance over the `c` real channels (pad lanes stay 0).
+// Reference: mamba_ssm Block.forward (non-fused add+norm, fp32 residual) and CleanUMamba.py:292-294.
+// ---------------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(256) ln_residual_kernel(const float* __restrict__ h, const float* __restrict__ rin,
+                                                           float* __restrict__ rout, float* __restrict__ normed,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, long long rows,
+                                                           int c, int c_pad) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int c4n = c_pad >> 2;
+    const float4* hp = reinterpret_cast<const float4*>(h + row * c_pad);
+    const float4* rp = rin ? reinterpret_cast<const float4*>(rin + row * c_pad) : nullptr;
+    float4 v[NCH];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c4 = lane + 32 * i;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 < c4n) {
+            v[i] = hp[c4];
+            if (rp) {
+                const float4 r = rp[c4];
+                v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+            }
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)c;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int cb = (lane + 32 * i) * 4;
+        const float dx = cb + 0 < c ? v[i].x - mean : 0.f, dy = cb + 1 < c ? v[i].y - mean : 0.f;
+        const float dz = cb + 2 < c ? v[i].z - mean : 0.f, dw = cb + 3 < c ? v[i].w - mean : 0.f;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)c + eps);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c4 = lane + 32 * i;
+        if (c4 < c4n) {
+            if (rout) reinterpret_cast<float4*>(rout + row * c_pad)[c4] = v[i];
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+            const int cb = c4 * 4;
+            float4 o;
+            o.x = cb + 0 < c ? (v[i].x - mean) * rstd * g.x + bt.x : 0.f;
+            o.y = cb + 1 < c ? (v[i].y - mean) * rstd * g.y + bt.y : 0.f;
+            o.z = cb + 2 < c ? (v[i].z - mean) * rstd * g.z + bt.z : 0.f;
+            o.w = cb + 3 < c ? (v[i].w - mean) * rstd * g.w + bt.w : 0.f;
+            reinterpret_cast<float4*>(normed + row * c_pad)[c4] = o;
+        }
+    }
+}
+
+int ln_residual_fwd(const float* h, const float* rin, float* rout, float* normed, const float* gamma,
+                    const float* beta, float eps, long long rows, int c, int c_pad, cudaStream_t st) {
+    CUM_REQUIRE(h && normed && gamma && beta, "ln_residual: null pointer");
+    CUM_REQUIRE(rows > 0 && c > 0 && c <= c_pad && c_pad % 4 == 0, "ln_residual: bad shape rows=%lld c=%d c_pad=%d", rows, c, c_pad);
+    CUM_REQUIRE(c_pad <= 1024, "ln_residual: c_pad=%d > 1024 not supported", c_pad);
+    CUM_REQUIRE(aligned16(h) && aligned16(normed) && aligned16(gamma) && aligned16(beta) && (!rin || aligned16(rin)) && (!rout || aligned16(rout)),
+                "ln_residual: pointers must be 16-byte aligned");
+    const unsigned grid = (unsigned)cdiv(rows, 8);
+    const int c4n = c_pad / 4;
+    if (c4n <= 32)        ln_residual_kernel<1><<<grid, 256, 0, st>>>(h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
+    else if (c4n <= 64)   ln_residual_kernel<2><<<grid, 256, 0, st>>>(h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
+    else if (c4n <= 128)  ln_residual_kernel<4><<<grid, 256, 0, st>>>(h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
+    else                  ln_residual_kernel<8><<<grid, 256, 0, st>>>(h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
+    CUM_LAUNCH_CHECK("ln_residual_kernel");
+    return CUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dwconv_silu: y[b,t,c] = silu(bias[c] + sum_k w[k,c] * x[b, t-(W-1)+k, c]);  inputs before t=0 come from
+// conv_state (or are 0).  Thread = 4 channels x DW_T consecutive steps with a rolling register window, so x is
+// read once (plus a W-1 halo per tile) and all accesses are coalesced float4 over channels.
+// Reference: causal_conv1d_fn(..., "silu") == act(conv1d(x)[..., :L]) in Mamba.forward; Mamba.step's roll+sum.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DW_T = 16;
+constexpr int DW_MAXW = 4;
+
+__device__ __forceinline__ float4 f4_fma(float4 w, float4 x, float4 a) {
+    return make_float4(fmaf(w.x, x.x, a.x), fmaf(w.y, x.y, a.y), fmaf(w.z, x.z, a.z), fmaf(w.w, x.w, a.w));
+}
+
+__global__ void __launch_bounds__(128) dwconv_silu_kernel(const float* __restrict__ x, long long x_bs, long long x_rs,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           float* __restrict__ y, const float* __restrict__ state,
+                                                           int len, int d_pad, int width) {
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c4 >= (d_pad >> 2)) return;
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.y * DW_T;
+    const float* xb = x + (long long)b * x_bs;
+    float4 wv[DW_MAXW];
+#pragma unroll
+    for (int k = 0; k < DW_MAXW; ++k)
+        wv[k] = k < width ? __ldg(reinterpret_cast<const float4*>(w + (long long)k * d_pad) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    // window[j] holds x[t - (W-1) + j]; slots are right-aligned in a DW_MAXW-wide window
+    float4 win[DW_MAXW];
+#pragma unroll
+    for (int j = 0; j < DW_MAXW - 1; ++j) {
+        const int back = (DW_MAXW - 1) - j;  // this slot is x[t0 - back]
+        win[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (back <= width - 1) {
+            const int t = t0 - back;
+            if (t >= 0) win[j] = *reinterpret_cast<const float4*>(xb + (long long)t * x_rs + c4 * 4);
+            else if (state) win[j] = *reinterpret_cast<const float4*>(state + ((long long)b * (width - 1) + (width - 1 + t)) * d_pad + c4 * 4);
+        }
+    }
+    const int tend = min(t0 + DW_T, len);
+    for (int t = t0; t < tend; ++t) {
+        win[DW_MAXW - 1] = *reinterpret_cast<const float4*>(xb + (long long)t * x_rs + c4 * 4);
+        float4 acc = bv;
+#pragma unroll
+        for (int k = 0; k < DW_MAXW; ++k) {
+            acc = f4_fma(wv[k], win[k], acc);  // tap k multiplies x[t - (W-1) + k]
+        }
+        float4 o = make_float4(siluf_(acc.x), siluf_(acc.y), siluf_(acc.z), siluf_(acc.w));
+        *reinterpret_cast<float4*>(y + ((long long)b * len + t) * d_pad + c4 * 4) = o;
+#pragma unroll
+        for (int j = 0; j < DW_MAXW - 1; ++j) win[j] = win[j + 1];
+    }
+}
+
+// new conv_state = last (W-1) inputs (older entries come from the previous state when len < W-1)
+__global__ void dwconv_state_kernel(const float* __restrict__ x, long long x_bs, long long x_rs,
+                                    const float* __restrict__ state, float* __restrict__ state_out, int len, int d_pad,
+                                    int width) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d_pad) return;
+    const int b = blockIdx.y;
+    float v[DW_MAXW - 1];
+#pragma unroll
+    for (int j = 0; j < DW_MAXW - 1; ++j) {
+        v[j] = 0.f;
+        if (j < width - 1) {
+            const int t = len - (width - 1) + j;
+            if (t >= 0) v[j] = x[(long long)b * x_bs + (long long)t * x_rs + c];
+            else if (state) v[j] = state[((long long)b * (width - 1) + (width - 1 + t)) * d_pad + c];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < DW_MAXW - 1; ++j)
+        if (j < width - 1) state_out[((long long)b * (width - 1) + j) * d_pad + c] = v[j];
+}
+
+int dwconv_silu_fwd(const float* x, long long x_bs, long long x_rs, const float* w, const float* bias, float* y,
+                    const float* conv_state, float* conv_state_out, int batch, int len, int d_pad, int width,
+                    cudaStream_t st) {
+    CUM_REQUIRE(x && w && bias && y, "dwconv_silu: null pointer");
+    CUM_REQUIRE(batch > 0 && len > 0 && d_pad > 0 && d_pad % 4 == 0, "dwconv_silu: bad shape");
+    CUM_REQUIRE(width >= 1 && width <= DW_MAXW, "dwconv_silu: width=%d unsupported (1..4)", width);
+    CUM_REQUIRE(x_rs % 4 == 0 && x_bs % 4 == 0 && aligned16(x) && aligned16(w) && aligned16(bias) && aligned16(y),
+                "dwconv_silu: strides/pointers must be 16-byte aligned");
+    CUM_REQUIRE(batch <= 65535, "dwconv_silu: batch too large");
+    dim3 grid((unsigned)cdiv(d_pad / 4, 128), (unsigned)cdiv(len, DW_T), (unsigned)batch);
+    CUM_REQUIRE(width == DW_MAXW, "dwconv_silu: only width 4 is instantiated (d_conv=4, CleanUMamba.py:143)");
+    dwconv_silu_kernel<<<grid, 128, 0, st>>>(x, x_bs, x_rs, w, bias, y, conv_state, len, d_pad, width);
+    CUM_LAUNCH_CHECK("dwconv_silu_kernel");
+    if (conv_state_out) {
+        dim3 g2((unsigned)cdiv(d_pad, 128), (unsigned)batch);
+        dwconv_state_kernel<<<g2, 128, 0, st>>>(x, x_bs, x_rs, conv_state, conv_state_out, len, d_pad, width);
+        CUM_LAUNCH_CHECK("dwconv_state_kernel");
+    }
+    return CUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// selective_scan (forward).  Reference arithmetic: mamba_ssm selective_scan_ref / selective_scan_fwd_kernel.
+//
+// CTA = CH channels x SL state-slices (threads = CH*SL; a warp = 32 channels of one slice, so B_t / C_t reads
+// are warp-wide shared-memory broadcasts and u / delta reads are conflict-free).  Time is processed in chunks of
+// TC steps, double-buffered through shared memory with cp.async:
+//   stage      u, delta (TC x CH) and B, C (TC x NP) tiles   (cp.async, next chunk in flight during compute)
+//   discretise delta <- softplus(delta + bias) once per (t, channel), in place
+//   recurrence every thread keeps NS states of one channel in registers: h = exp2(dl*A2) h + (dl u) B_t ;
+//              partial y = sum_i h_i C_t,i  -> ypart[slice][t][ch]         (carry h stays in registers across chunks)
+//   combine    y = (sum_slices ypart + D u) * silu(z)  -> coalesced store
+// A2 = -exp(A_log) * log2(e) is prepared at weight-pack time so the decay is a single ex2.approx.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ float softplusf_(float x) {
+    // torch softplus (beta=1, threshold=20)
+    return x > 20.0f ? x : log1pf(expf(x));
+}
+
+template <int NS, int SL, int CH, int TC>
+struct ScanSmem {
+    static constexpr int NP = NS * SL;
+    float u[2][TC][CH];
+    float dl[2][TC][CH];
+    float Bm[2][TC][NP];
+    float Cm[2][TC][NP];
+    float ypart[SL][TC][CH];
+};
+
+template <int NS, int SL, int CH, int TC>
+__global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_scan_desc p) {
+    constexpr int NP = NS * SL;
+    constexpr int NT = CH * SL;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScanSmem<NS, SL, CH, TC>& sm = *reinterpret_cast<ScanSmem<NS, SL, CH, TC>*>(smem_raw);
+
+    const int b = blockIdx.y;
+    const int c0 = blockIdx.x * CH;
+    const int tid = threadIdx.x;
+    const int ch = tid % CH, slice = tid / CH;
+    const int c = c0 + ch;
+    const bool c_ok = c < p.d;
+    const int nchunks = (p.len + TC - 1) / TC;
+
+    const float* ub = p.u + (long long)b * p.u_bs;
+    const float* db = p.delta + (long long)b * p.dl_bs;
+    const float* Bb = p.Bm + (long long)b * p.B_bs;
+    const float* Cb = p.Cm + (long long)b * p.C_bs;
+    const bool vec_ok = ((p.u_rs | p.dl_rs | p.B_rs | p.C_rs | p.u_bs | p.dl_bs | p.B_bs | p.C_bs) % 4 == 0) &&
+                        ((((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.Bm | (uintptr_t)p.Cm) & 15) == 0) &&
+                        (p.d % 4 == 0) && (p.n_state % 4 == 0);
+
+    auto stage = [&](int chunk, int buf) {
+        const int t0 = chunk * TC;
+        // u / delta tiles: TC x CH
+        for (int i = tid; i < TC * (CH / 4); i += NT) {
+            const int t = i / (CH / 4), q = i - t * (CH / 4);
+            const int tt = t0 + t, cc = c0 + q * 4;
+            float* su = &sm.u[buf][t][q * 4];
+            float* sd = &sm.dl[buf][t][q * 4];
+            if (tt < p.len && cc + 3 < p.d && vec_ok) {
+                cp_async16(su, ub + (long long)tt * p.u_rs + cc);
+                cp_async16(sd, db + (long long)tt * p.dl_rs + cc);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool ok = tt < p.len && cc + e < p.d;
+                    su[e] = ok ? ub[(long long)tt * p.u_rs + cc + e] : 0.f;
+                    sd[e] = ok ? db[(long long)tt * p.dl_rs + cc + e] : 0.f;
+                }
+            }
+        }
+        // B / C tiles: TC x NP
+        for (int i = tid; i < TC * (NP / 4); i += NT) {
+            const int t = i / (NP / 4), q = i - t * (NP / 4);
+            const int tt = t0 + t, nn = q * 4;
+            float* sb = &sm.Bm[buf][t][nn];
+            float* sc = &sm.Cm[buf][t][nn];
+            if (tt < p.len && nn + 3 < p.n_state && vec_ok) {
+                cp_async16(sb, Bb + (long long)tt * p.B_rs + nn);
+                cp_async16(sc, Cb + (long long)tt * p.C_rs + nn);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool ok = tt < p.len && nn + e < p.n_state;
+                    sb[e] = ok ? Bb[(long long)tt * p.B_rs + nn + e] : 0.f;
+                    sc[e] = ok ? Cb[(long long)tt * p.C_rs + nn + e] : 0.f;
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    // per-thread constants and carried state
+    float a2[NS], h[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const int n = slice * NS + i;
+        const bool ok = c_ok && n < p.n_state;
+        a2[i] = ok ? p.a2[(long long)c * p.n_state + n] : 0.f;
+        h[i] = (ok && p.h0) ? p.h0[((long long)b * p.d + c) * p.n_state + n] : 0.f;
+    }
+
+    stage(0, 0);
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int buf = chunk & 1;
+        const int t0 = chunk * TC;
+        const int tn = min(TC, p.len - t0);
+        cp_async_wait<0>();
+        __syncthreads();  // (A) tile `buf` landed; everybody is done with the previous chunk's combine
+        if (chunk + 1 < nchunks) stage(chunk + 1, buf ^ 1);
+        // discretise: delta <- softplus(delta + bias), once per (t, channel)
+        for (int i = tid; i < TC * CH; i += NT) {
+            const int t = i / CH, cc = i - t * CH;
+            float v = sm.dl[buf][t][cc];
+            if (p.delta_bias && c0 + cc < p.d) v += __ldg(p.delta_bias + c0 + cc);
+            if (p.delta_softplus) v = softplusf_(v);
+            sm.dl[buf][t][cc] = v;
+        }
+        __syncthreads();  // (B)
+        for (int t = 0; t < tn; ++t) {
+            const float dl = sm.dl[buf][t][ch];
+            const float du = dl * sm.u[buf][t][ch];
+            const float4* bq = reinterpret_cast<const float4*>(&sm.Bm[buf][t][slice * NS]);
+            const float4* cq = reinterpret_cast<const float4*>(&sm.Cm[buf][t][slice * NS]);
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < NS / 4; ++q) {
+                const float4 bv = bq[q], cv = cq[q];
+                h[4 * q + 0] = fmaf(ex2_approx(dl * a2[4 * q + 0]), h[4 * q + 0], du * bv.x);
+                h[4 * q + 1] = fmaf(ex2_approx(dl * a2[4 * q + 1]), h[4 * q + 1], du * bv.y);
+                h[4 * q + 2] = fmaf(ex2_approx(dl * a2[4 * q + 2]), h[4 * q + 2], du * bv.z);
+                h[4 * q + 3] = fmaf(ex2_approx(dl * a2[4 * q + 3]), h[4 * q + 3], du * bv.w);
+                acc0 = fmaf(h[4 * q + 0], cv.x, acc0);
+                acc1 = fmaf(h[4 * q + 1], cv.y, acc1);
+                acc0 = fmaf(h[4 * q + 2], cv.z, acc0);
+                acc1 = fmaf(h[4 * q + 3], cv.w, acc1);
+            }
+            sm.ypart[slice][t][ch] = acc0 + acc1;
+        }
+        __syncthreads();  // (C)
+        // combine + gate + store
+        for (int i = tid; i < tn * CH; i += NT) {
+            const int t = i / CH, cc = i - t * CH;
+            const int cg = c0 + cc;
+            if (cg >= p.d) continue;
+            float yv = 0.f;
+#pragma unroll
+            for (int s = 0; s < SL; ++s) yv += sm.ypart[s][t][cc];
+            if (p.Dskip) yv = fmaf(__ldg(p.Dskip + cg), sm.u[buf][t][cc], yv);
+            if (p.z) yv *= siluf_(p.z[(long long)b * p.z_bs + (long long)(t0 + t) * p.z_rs + cg]);
+            p.y[(long long)b * p.y_bs + (long long)(t0 + t) * p.y_rs + cg] = yv;
+        }
+    }
+    if (p.h_out) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int n = slice * NS + i;
+            if (c_ok && n < p.n_state) p.h_out[((long long)b * p.d + c) * p.n_state + n] = h[i];
+        }
+    }
+}
+
+template <int NS, int SL, int CH, int TC>
+static int launch_scan(const cum_scan_desc& d, cudaStream_t st) {
+    auto kern = selective_scan_fwd_kernel<NS, SL, CH, TC>;
+    const size_t smem = sizeof(ScanSmem<NS, SL, CH, TC>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(selective_scan_fwd_kernel)");
+        attr_done = true;
+    }
+    dim3 grid((unsigned)cdiv(d.d, CH), (unsigned)d.batch);
+    kern<<<grid, CH * SL, smem, st>>>(d);
+    CUM_LAUNCH_CHECK("selective_scan_fwd_kernel");
+    return CUM_OK;
+}
+
+int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st) {
+    CUM_REQUIRE(d.u && d.delta && d.Bm && d.Cm && d.y && d.a2, "selective_scan: null pointer");
+    CUM_REQUIRE(d.batch > 0 && d.batch <= 65535 && d.len > 0 && d.d > 0 && d.n_state > 0, "selective_scan: bad shape");
+    CUM_REQUIRE(d.n_state <= 64, "selective_scan: n_state=%d > 64 not supported", d.n_state);
+    if (d.n_state > 32) return launch_scan<16, 4, 64, 16>(d, st);
+    if (d.n_state > 16) return launch_scan<16, 2, 64, 16>(d, st);
+    if (d.n_state > 8)  return launch_scan<16, 1, 64, 16>(d, st);
+    return launch_scan<8, 1, 64, 16>(d, st);
+}
+
+}  // namespace cum

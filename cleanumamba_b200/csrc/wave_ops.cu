@@ -1,0 +1,191 @@
+// Waveform-end kernels: input normalisation, first encoder conv (Cin = 1), last decoder transposed conv (Cout = 1).
+// All three are HBM-bound streaming kernels (a few FLOP per byte); see DESIGN.md "kernels".
+#include "common.cuh"
+
+namespace cum {
+
+// ---------------------------------------------------------------------------------------------------------
+// std (unbiased) + 1e-3, in-place divide.  Reference: CleanUMamba.py:260-262.  One CTA per clip; two-pass
+// mean/variance in fp64 (torch's CPU std accumulates in double), then the divide.
+// ---------------------------------------------------------------------------------------------------------
+__device__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    if (wid == 0) {
+        t = warp_sum(t);
+        if (lane == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+}
+
+__global__ void __launch_bounds__(1024) wave_normalize_kernel(float* __restrict__ x, float* __restrict__ std_out,
+                                                               int length) {
+    __shared__ double red[32];
+    float* row = x + (long long)blockIdx.x * length;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < length; i += blockDim.x) s += (double)row[i];
+    const double mean = block_sum(s, red) / (double)length;
+    double q = 0.0;
+    for (int i = threadIdx.x; i < length; i += blockDim.x) {
+        const double d = (double)row[i] - mean;
+        q += d * d;
+    }
+    const double var = block_sum(q, red) / (double)(length > 1 ? length - 1 : 1);
+    const float sd = (float)sqrt(var) + 1e-3f;
+    if (threadIdx.x == 0) std_out[blockIdx.x] = sd;
+    for (int i = threadIdx.x; i < length; i += blockDim.x) row[i] = row[i] / sd;
+}
+
+int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStream_t st) {
+    CUM_REQUIRE(x && std_out && batch > 0 && length > 0, "wave_normalize: bad arguments");
+    wave_normalize_kernel<<<batch, 1024, 0, st>>>(x, std_out, length);
+    CUM_LAUNCH_CHECK("wave_normalize_kernel");
+    return CUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv_in: y[b,t,c] = relu(bias[c] + sum_k w[k,c] * x[b, S t + k]),  x read as 0 beyond `length` (F.pad).
+// CTA = 64 output rows; the 64*S+K input samples are staged in smem, every thread then produces float4s of
+// channels for one row so the stores are fully coalesced (the kernel is store-bound: 4*Cp bytes per row).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CI_ROWS = 64;
+constexpr int CI_MAXK = 8;
+
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, long long x_stride, int length,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ y, int rows_out, int c_pad, int kernel,
+                                                       int stride) {
+    extern __shared__ float xs[];
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * CI_ROWS;
+    const int nin = CI_ROWS * stride + kernel;
+    const float* xb = x + (long long)b * x_stride;
+    for (int i = threadIdx.x; i < nin; i += blockDim.x) {
+        const long long g = (long long)t0 * stride + i;
+        xs[i] = (g < length) ? xb[g] : 0.0f;
+    }
+    __syncthreads();
+    const int c4n = c_pad >> 2;
+    const int rows = min(CI_ROWS, rows_out - t0);
+    float* yb = y + ((long long)b * rows_out + t0) * c_pad;
+    for (int idx = threadIdx.x; idx < rows * c4n; idx += blockDim.x) {
+        const int t = idx / c4n, c4 = idx - t * c4n;
+        float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+#pragma unroll 4
+        for (int k = 0; k < kernel; ++k) {
+            const float xv = xs[t * stride + k];
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)k * c_pad) + c4);
+            acc.x = fmaf(wv.x, xv, acc.x); acc.y = fmaf(wv.y, xv, acc.y);
+            acc.z = fmaf(wv.z, xv, acc.z); acc.w = fmaf(wv.w, xv, acc.w);
+        }
+        acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+        reinterpret_cast<float4*>(yb + (long long)t * c_pad)[c4] = acc;
+    }
+}
+
+int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
+                float* y, int rows_out, int c_pad, int kernel, int stride, cudaStream_t st) {
+    CUM_REQUIRE(x && w && bias && y, "conv_in: null pointer");
+    CUM_REQUIRE(batch > 0 && length > 0 && rows_out > 0, "conv_in: empty problem");
+    CUM_REQUIRE(c_pad > 0 && c_pad % 4 == 0, "conv_in: c_pad=%d must be a positive multiple of 4", c_pad);
+    CUM_REQUIRE(kernel >= 1 && kernel <= CI_MAXK && stride >= 1 && stride <= kernel, "conv_in: kernel=%d stride=%d unsupported", kernel, stride);
+    CUM_REQUIRE(aligned16(w) && aligned16(bias) && aligned16(y), "conv_in: w/bias/y must be 16-byte aligned");
+    dim3 grid((unsigned)cdiv(rows_out, CI_ROWS), batch);
+    const size_t smem = (size_t)(CI_ROWS * stride + kernel) * sizeof(float);
+    conv_in_kernel<<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, rows_out, c_pad, kernel, stride);
+    CUM_LAUNCH_CHECK("conv_in_kernel");
+    return CUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// convt_out: out[b,m] = scale[b] * (bias + sum_{j,k: S j + k = m} <g[b,j,:], w[k,:]>)  for m < length.
+// CTA = 64 input rows (+ halo).  Phase 1: a group of LPR lanes computes the K tap-dots of one input row with
+// float4 loads (coalesced, read-once: the kernel is load-bound at 4*Cp bytes per row).  Phase 2: overlap-add
+// of the dots from smem into S*64 output samples.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CT_ROWS = 64;
+constexpr int CT_MAXK = 8;
+
+template <int LPR>
+__global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict__ g, int rows_in, int c_pad,
+                                                         const float* __restrict__ w, float bias,
+                                                         const float* __restrict__ scale, float* __restrict__ out,
+                                                         long long out_stride, int length, int kernel, int stride,
+                                                         int halo) {
+    extern __shared__ float dots[];  // [(CT_ROWS + halo)][kernel]
+    const int b = blockIdx.y;
+    const int j0 = blockIdx.x * CT_ROWS - halo;  // first staged input row (may be negative)
+    const int nrows = CT_ROWS + halo;
+    const int c4n = c_pad >> 2;
+    const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR, ngrp = blockDim.x / LPR;
+    for (int r = grp; r < nrows; r += ngrp) {
+        const int j = j0 + r;
+        float acc[CT_MAXK];
+#pragma unroll
+        for (int k = 0; k < CT_MAXK; ++k) acc[k] = 0.f;
+        if (j >= 0 && j < rows_in) {
+            const float4* row = reinterpret_cast<const float4*>(g + ((long long)b * rows_in + j) * c_pad);
+            for (int c4 = sub; c4 < c4n; c4 += LPR) {
+                const float4 v = __ldg(row + c4);
+#pragma unroll
+                for (int k = 0; k < CT_MAXK; ++k) {
+                    if (k < kernel) {
+                        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)k * c_pad) + c4);
+                        acc[k] = fmaf(v.x, wv.x, fmaf(v.y, wv.y, fmaf(v.z, wv.z, fmaf(v.w, wv.w, acc[k]))));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CT_MAXK; ++k) {
+            if (k < kernel) {
+                float v = acc[k];
+#pragma unroll
+                for (int o = LPR >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (sub == 0) dots[r * kernel + k] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const float sc = scale ? scale[b] : 1.0f;
+    const long long m0 = (long long)blockIdx.x * CT_ROWS * stride;
+    for (int i = threadIdx.x; i < CT_ROWS * stride; i += blockDim.x) {
+        const long long m = m0 + i;
+        if (m >= length) break;
+        float acc = bias;
+        for (int k = (int)(m % stride); k < kernel; k += stride) {
+            const long long j = (m - k) / stride;
+            if (m - k >= 0 && j < rows_in) acc += dots[(int)(j - j0) * kernel + k];
+        }
+        out[(long long)b * out_stride + m] = acc * sc;
+    }
+}
+
+int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
+                  const float* scale, float* out, long long out_stride, int length, int kernel, int stride,
+                  cudaStream_t st) {
+    CUM_REQUIRE(g && w && out, "convt_out: null pointer");
+    CUM_REQUIRE(batch > 0 && rows_in > 0 && length > 0, "convt_out: empty problem");
+    CUM_REQUIRE(c_pad > 0 && c_pad % 4 == 0, "convt_out: c_pad=%d must be a positive multiple of 4", c_pad);
+    CUM_REQUIRE(kernel >= 1 && kernel <= CT_MAXK && stride >= 1 && stride <= kernel, "convt_out: kernel=%d stride=%d unsupported", kernel, stride);
+    CUM_REQUIRE(aligned16(g) && aligned16(w), "convt_out: g/w must be 16-byte aligned");
+    const int halo = (kernel - 1) / stride;
+    const long long out_rows = (long long)(rows_in - 1) * stride + kernel;
+    const long long need = length < out_rows ? length : out_rows;
+    CUM_REQUIRE(length <= out_rows, "convt_out: length=%d exceeds the transposed-conv output (%lld)", length, out_rows);
+    dim3 grid((unsigned)cdiv(need, (long long)CT_ROWS * stride), batch);
+    const size_t smem = (size_t)(CT_ROWS + halo) * kernel * sizeof(float);
+    if (c_pad <= 64)
+        convt_out_kernel<16><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, out, out_stride, length, kernel, stride, halo);
+    else
+        convt_out_kernel<32><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, out, out_stride, length, kernel, stride, halo);
+    CUM_LAUNCH_CHECK("convt_out_kernel");
+    return CUM_OK;
+}
+
+}  // namespace cum

@@ -1,0 +1,327 @@
+"""Host-side engine: packs the module's parameters into kernel layouts and runs the forward plan through the C ABI.
+
+Layouts: activations are channels-last fp32 ``(batch, time, C_pad)`` with ``C_pad = ceil8(C)``; weights
+are K-contiguous ``(taps, N_pad, K_pad)`` with zero padding, so pad lanes stay exactly 0 through every layer.
+  * Conv1d(k=4, s=2)           -> 2-tap GEMM over the ``(L/2, 2 C_pad)`` view of its input, shifts {0, +1}
+  * ConvTranspose1d(k=4, s=2)  -> 2-tap GEMM writing the ``(L_in + 1, 2 C_pad)`` view of its output, shifts {0, -1}
+  * Conv1d(k=1) + GLU          -> GEMM whose weight rows are interleaved (a_c, b_c) so the gate is a register epilogue
+  * U-Net skip add (:315)      -> ``addend`` of the GEMM that produces the decoder-level input
+Reference walk: /root/reference/src/network/CleanUMamba.py:252-324.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import EPI_GLU, EPI_NONE, EPI_RELU, GemmDesc, ScanDesc, check, ptr
+
+LOG2E = 1.4426950408889634
+
+
+def p8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _pad2(t: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    out = t.new_zeros(rows, cols)
+    out[: t.shape[0], : t.shape[1]] = t
+    return out
+
+
+def _pad1(t: torch.Tensor, n: int) -> torch.Tensor:
+    out = t.new_zeros(n)
+    out[: t.shape[0]] = t
+    return out
+
+
+def _interleave_glu(w: torch.Tensor, b: torch.Tensor, k_pad: int):
+    """(2H, K) weight / (2H) bias of a 1x1 conv feeding a GLU -> rows (a_0, b_0, a_1, b_1, ...), padded to ceil8(H)."""
+    H = w.shape[0] // 2
+    Hp = p8(H)
+    wp = w.new_zeros(2 * Hp, k_pad)
+    bp = b.new_zeros(2 * Hp)
+    wp[0:2 * H:2, : w.shape[1]] = w[:H]
+    wp[1:2 * H:2, : w.shape[1]] = w[H:]
+    bp[0:2 * H:2] = b[:H]
+    bp[1:2 * H:2] = b[H:]
+    return wp, bp, Hp
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self._key = None
+        self.pk: Dict[str, torch.Tensor] = {}
+        self.meta: dict = {}
+
+    # ------------------------------------------------------------------------------------------------ packing
+    def _params_key(self):
+        return tuple((id(p), p._version, p.data_ptr(), p.device, p.dtype) for p in self.model.parameters())
+
+    def ensure_packed(self):
+        key = self._params_key()
+        if key != self._key:
+            self._pack()
+            self._key = key
+
+    @torch.no_grad()
+    def _pack(self):
+        m = self.model
+        dev = next(m.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("cleanumamba_b200 runs on CUDA (sm_100a) only: move the module with .cuda() "
+                               "(there is no CPU fallback)")
+        if m.kernel_size != 4 or m.stride != 2:
+            raise NotImplementedError("cleanumamba_b200: kernel_size=4, stride=2 only (all shipped configs)")
+        if m.channels_input != 1 or m.channels_output != 1:
+            raise NotImplementedError("cleanumamba_b200: mono in / mono out only (reference asserts C == 1, :257)")
+        f = lambda t: t.detach().to(device=dev, dtype=torch.float32)  # noqa: E731
+        D = m.encoder_n_layers
+        items: Dict[str, torch.Tensor] = {}
+        meta = dict(D=D, enc=[], dec=[], mamba=[])
+
+        c_prev_p = None
+        for i, blk in enumerate(m.encoder):
+            w0, b0, w1, b1 = f(blk[0].weight), f(blk[0].bias), f(blk[2].weight)[:, :, 0], f(blk[2].bias)
+            Hc, Cin, K = w0.shape
+            Hc_p = p8(Hc)
+            if i == 0:
+                items["enc0.w"] = _pad2(w0[:, 0, :].t().contiguous(), K, Hc_p)          # (K, Hc_p) taps-major
+            else:
+                wt = w0.new_zeros(2, Hc_p, 2 * c_prev_p)
+                for s in range(2):
+                    for j in range(2):
+                        wt[s, :Hc, j * c_prev_p: j * c_prev_p + Cin] = w0[:, :, 2 * s + j]
+                items[f"enc{i}.w"] = wt
+            items[f"enc{i}.b"] = _pad1(b0, Hc_p)
+            wg, bg, Ho_p = _interleave_glu(w1, b1, Hc_p)
+            items[f"enc{i}.wg"], items[f"enc{i}.bg"] = wg, bg
+            meta["enc"].append(dict(Hc=Hc, Hc_p=Hc_p, Ho=w1.shape[0] // 2, Ho_p=Ho_p, Cin_p=c_prev_p))
+            c_prev_p = Ho_p
+
+        w, b = f(m.tsfm_conv1.weight)[:, :, 0], f(m.tsfm_conv1.bias)
+        dm = w.shape[0]
+        dm_p = p8(dm)
+        items["t1.w"], items["t1.b"] = _pad2(w, dm_p, c_prev_p), _pad1(b, dm_p)
+        meta.update(dm=dm, dm_p=dm_p, eps=float(m.norm_f.eps))
+
+        for l, blk in enumerate(m.tsfm_Mamba_layers):
+            mx = blk.mixer
+            di, N = mx.A_log.shape
+            R = mx.dt_proj.weight.shape[1]
+            W = mx.conv1d.weight.shape[2]
+            di_p, N_p, R_p = p8(di), p8(N), p8(R)
+            win = f(mx.in_proj.weight)
+            wi = win.new_zeros(2 * di_p, dm_p)
+            wi[:di, :dm] = win[:di]
+            wi[di_p: di_p + di, :dm] = win[di:]
+            items[f"m{l}.in"] = wi
+            items[f"m{l}.cw"] = _pad2(f(mx.conv1d.weight)[:, 0, :].t().contiguous(), W, di_p)
+            items[f"m{l}.cb"] = _pad1(f(mx.conv1d.bias), di_p)
+            wx = f(mx.x_proj.weight)
+            wxp = wx.new_zeros(R_p + 2 * N_p, di_p)
+            wxp[:R, :di] = wx[:R]
+            wxp[R_p: R_p + N, :di] = wx[R: R + N]
+            wxp[R_p + N_p: R_p + N_p + N, :di] = wx[R + N:]
+            items[f"m{l}.xp"] = wxp
+            items[f"m{l}.dtw"] = _pad2(f(mx.dt_proj.weight), di_p, R_p)
+            items[f"m{l}.dtb"] = _pad1(f(mx.dt_proj.bias), di_p)
+            items[f"m{l}.a2"] = _pad2(-torch.exp(f(mx.A_log)) * LOG2E, di_p, N_p)
+            items[f"m{l}.D"] = _pad1(f(mx.D), di_p)
+            items[f"m{l}.out"] = _pad2(f(mx.out_proj.weight), dm_p, di_p)
+            items[f"m{l}.g"], items[f"m{l}.be"] = _pad1(f(blk.norm.weight), dm_p), _pad1(f(blk.norm.bias), dm_p)
+            meta["mamba"].append(dict(di=di, di_p=di_p, N=N, N_p=N_p, R=R, R_p=R_p, W=W, eps=float(blk.norm.eps)))
+        items["nf.g"], items["nf.be"] = _pad1(f(m.norm_f.weight), dm_p), _pad1(f(m.norm_f.bias), dm_p)
+
+        w, b = f(m.tsfm_conv2.weight)[:, :, 0], f(m.tsfm_conv2.bias)
+        c_p = p8(w.shape[0])
+        items["t2.w"], items["t2.b"] = _pad2(w, c_p, dm_p), _pad1(b, c_p)
+        c_prev_p = c_p
+        for j, blk in enumerate(m.decoder):
+            w0, b0, wt, bt = f(blk[0].weight)[:, :, 0], f(blk[0].bias), f(blk[2].weight), f(blk[2].bias)
+            wg, bg, Hg_p = _interleave_glu(w0, b0, c_prev_p)
+            items[f"dec{j}.wg"], items[f"dec{j}.bg"] = wg, bg
+            Hg, Co, K = wt.shape
+            Co_p = p8(Co)
+            if j == D - 1:
+                items[f"dec{j}.w"] = _pad2(wt[:, 0, :].t().contiguous(), K, Hg_p)        # (K, Hg_p)
+                meta["out_bias"] = float(bt[0].item())
+            else:
+                wp = wt.new_zeros(2, 2 * Co_p, Hg_p)
+                bp = bt.new_zeros(2 * Co_p)
+                for s in range(2):
+                    for par in range(2):
+                        wp[s, par * Co_p: par * Co_p + Co, :Hg] = wt[:, :, 2 * s + par].t()
+                for par in range(2):
+                    bp[par * Co_p: par * Co_p + Co] = bt
+                items[f"dec{j}.w"], items[f"dec{j}.b"] = wp, bp
+            meta["dec"].append(dict(Hg=Hg, Hg_p=Hg_p, Co=Co, Co_p=Co_p, Cin_p=c_prev_p))
+            c_prev_p = Co_p
+
+        # one flat device buffer, every tensor 256-byte aligned
+        offs, total = {}, 0
+        for k, t in items.items():
+            offs[k] = total
+            total += (t.numel() + 63) // 64 * 64
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.pk = {}
+        for k, t in items.items():
+            v = flat[offs[k]: offs[k] + t.numel()].view(t.shape)
+            v.copy_(t)
+            self.pk[k] = v
+        self._flat = flat
+        self.meta = meta
+        self.device = dev
+        self.math = _lib.MATH_BY_NAME[getattr(m, "math_mode", "fp32")]
+        self.lib = _lib.init(dev)
+
+    # ------------------------------------------------------------------------------------------------ op wrappers
+    def gemm(self, a, a_off, a_bs, a_rs, a_rows, k, w, bias, c, c_off, c_bs, c_rs, m, n, batch, epi,
+             taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None):
+        d = GemmDesc()
+        d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k = a.data_ptr() + 4 * a_off, a_bs, a_rs, a_rows, k
+        d.taps = taps
+        d.tap_shift[0], d.tap_shift[1] = shifts
+        d.w, d.ldw, d.bias = w.data_ptr(), w.shape[-1], ptr(bias)
+        d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch = c.data_ptr() + 4 * c_off, c_bs, c_rs, m, n, batch
+        d.epilogue = epi
+        d.addend, d.add_batch_stride, d.add_row_stride = ptr(addend), add_bs, add_rs
+        d.math = self.math if math is None else math
+        check(self.lib.cum_gemm_bias_act_fwd(C.byref(d), _lib.stream_ptr()), "cum_gemm_bias_act_fwd")
+
+    def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None):
+        """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers."""
+        n_out = n // 2 if epi >= 8 else n
+        c = out if out is not None else torch.empty(rows, n_out, dtype=torch.float32, device=a.device)
+        self.gemm(a, a_off, 0, k if a_rs is None else a_rs, rows, k, w, bias, c, 0, 0, n_out, rows, n, 1, epi,
+                  addend=addend, add_bs=0, add_rs=n_out)
+        return c
+
+    def ln(self, h, res_in, res_out, normed, g, be, eps, rows, c, c_p):
+        check(self.lib.cum_ln_residual_fwd(ptr(h), ptr(res_in), ptr(res_out), ptr(normed), ptr(g), ptr(be), eps, rows,
+                                           c, c_p, _lib.stream_ptr()), "cum_ln_residual_fwd")
+
+    def scan(self, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None):
+        di_p, N_p, R_p = mm["di_p"], mm["N_p"], mm["R_p"]
+        s = ScanDesc()
+        s.u, s.u_bs, s.u_rs = u.data_ptr(), T * di_p, di_p
+        s.delta, s.dl_bs, s.dl_rs = dt.data_ptr(), T * di_p, di_p
+        s.z, s.z_bs, s.z_rs = xz.data_ptr() + 4 * di_p, T * 2 * di_p, 2 * di_p
+        ld = R_p + 2 * N_p
+        s.Bm, s.B_bs, s.B_rs = xdbl.data_ptr() + 4 * R_p, T * ld, ld
+        s.Cm, s.C_bs, s.C_rs = xdbl.data_ptr() + 4 * (R_p + N_p), T * ld, ld
+        s.y, s.y_bs, s.y_rs = y.data_ptr(), T * di_p, di_p
+        s.a2, s.Dskip, s.delta_bias = self.pk[f"m{l}.a2"].data_ptr(), self.pk[f"m{l}.D"].data_ptr(), self.pk[f"m{l}.dtb"].data_ptr()
+        s.h0, s.h_out = ptr(h0), ptr(h_out)
+        s.batch, s.len, s.d, s.n_state, s.delta_softplus = B, T, di_p, N_p, 1
+        check(self.lib.cum_selective_scan_fwd(C.byref(s), _lib.stream_ptr()), "cum_selective_scan_fwd")
+
+    def mamba_layers(self, h, B, T, states=None):
+        """h: (B*T, dm_p) output of tsfm_conv1 -> normed (B*T, dm_p) after norm_f.  ``states``: optional list of
+        (conv_state (B, W-1, di_p), ssm_state (B, di_p, N_p)) carried in place (streaming)."""
+        pk, meta = self.pk, self.meta
+        dm, dm_p = meta["dm"], meta["dm_p"]
+        rows = B * T
+        dev = h.device
+        res = None
+        hn = torch.empty(rows, dm_p, dtype=torch.float32, device=dev)
+        for l, mm in enumerate(meta["mamba"]):
+            di_p, N_p, R_p = mm["di_p"], mm["N_p"], mm["R_p"]
+            res_out = res if res is not None else torch.empty(rows, dm_p, dtype=torch.float32, device=dev)
+            self.ln(h, res, res_out, hn, pk[f"m{l}.g"], pk[f"m{l}.be"], mm["eps"], rows, dm, dm_p)
+            res = res_out
+            xz = self.dense(hn, rows, dm_p, pk[f"m{l}.in"], None, 2 * di_p)
+            xc = torch.empty(rows, di_p, dtype=torch.float32, device=dev)
+            cs = states[l][0] if states is not None else None
+            check(self.lib.cum_dwconv_silu_fwd(xz.data_ptr(), T * 2 * di_p, 2 * di_p, pk[f"m{l}.cw"].data_ptr(),
+                                               pk[f"m{l}.cb"].data_ptr(), xc.data_ptr(), ptr(cs), ptr(cs), B, T, di_p,
+                                               mm["W"], _lib.stream_ptr()), "cum_dwconv_silu_fwd")
+            xdbl = self.dense(xc, rows, di_p, pk[f"m{l}.xp"], None, R_p + 2 * N_p)
+            dt = self.dense(xdbl, rows, R_p, pk[f"m{l}.dtw"], None, di_p, a_rs=R_p + 2 * N_p)
+            y = torch.empty(rows, di_p, dtype=torch.float32, device=dev)
+            hs = states[l][1] if states is not None else None
+            self.scan(xc, dt, xz, xdbl, y, l, mm, B, T, h0=hs, h_out=hs)
+            h = self.dense(y, rows, di_p, pk[f"m{l}.out"], None, dm_p)
+        self.ln(h, res, None, hn, pk["nf.g"], pk["nf.be"], meta["eps"], rows, dm, dm_p)
+        return hn
+
+    # ------------------------------------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, noisy: torch.Tensor, return_skip_connections: bool = False):
+        m = self.model
+        self.ensure_packed()
+        pk, meta, lib = self.pk, self.meta, self.lib
+        if noisy.device != self.device:
+            raise RuntimeError(f"input is on {noisy.device}, model on {self.device} (no CPU fallback)")
+        B, _, L = noisy.shape
+        D = meta["D"]
+        st = _lib.stream_ptr
+        act = EPI_GLU[m.glu_activation]
+
+        x = noisy
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = noisy.to(torch.float32).contiguous()
+        std = None
+        if m.normalize_input:
+            std = torch.empty(B, dtype=torch.float32, device=x.device)
+            check(lib.cum_wave_normalize_fwd(x.data_ptr(), std.data_ptr(), B, L, st()), "cum_wave_normalize_fwd")
+            if x is not noisy:
+                noisy.copy_(x)      # the reference divides the caller's tensor in place (:262)
+        Ls = [m.valid_length(L)]
+        for _ in range(D):
+            Ls.append((Ls[-1] - 4) // 2 + 1)
+
+        skips: List[torch.Tensor] = []
+        prev = None
+        for i, e in enumerate(meta["enc"]):
+            rows = B * Ls[i + 1]
+            y = torch.empty(rows, e["Hc_p"], dtype=torch.float32, device=x.device)
+            if i == 0:
+                check(lib.cum_conv_in_fwd(x.data_ptr(), L, B, L, pk["enc0.w"].data_ptr(), pk["enc0.b"].data_ptr(),
+                                          y.data_ptr(), Ls[1], e["Hc_p"], 4, 2, st()), "cum_conv_in_fwd")
+            else:
+                cp = e["Cin_p"]
+                self.gemm(prev, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2, 2 * cp, pk[f"enc{i}.w"], pk[f"enc{i}.b"],
+                          y, 0, Ls[i + 1] * e["Hc_p"], e["Hc_p"], Ls[i + 1], e["Hc_p"], B, EPI_RELU, taps=2,
+                          shifts=(0, 1))
+            prev = self.dense(y, rows, e["Hc_p"], pk[f"enc{i}.wg"], pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act)
+            skips.append(prev)
+
+        T = Ls[D]
+        rows = B * T
+        cb_p = meta["enc"][-1]["Ho_p"]
+        h = self.dense(prev, rows, cb_p, pk["t1.w"], pk["t1.b"], meta["dm_p"])
+        hn = self.mamba_layers(h, B, T)
+        xcur = self.dense(hn, rows, meta["dm_p"], pk["t2.w"], pk["t2.b"], cb_p, addend=skips[D - 1])
+
+        Tj = T
+        out = None
+        for j, d in enumerate(meta["dec"]):
+            g = self.dense(xcur, B * Tj, d["Cin_p"], pk[f"dec{j}.wg"], pk[f"dec{j}.bg"], 2 * d["Hg_p"], epi=act)
+            if j < D - 1:
+                co = d["Co_p"]
+                To = 2 * Tj + 2
+                nxt = torch.empty(B * To, co, dtype=torch.float32, device=x.device)
+                skip = skips[D - 2 - j]
+                self.gemm(g, 0, Tj * d["Hg_p"], d["Hg_p"], Tj, d["Hg_p"], pk[f"dec{j}.w"], pk[f"dec{j}.b"],
+                          nxt, 0, To * co, 2 * co, Tj + 1, 2 * co, B, EPI_RELU, taps=2, shifts=(0, -1),
+                          addend=skip, add_bs=To * co, add_rs=2 * co)
+                xcur, Tj = nxt, To
+            else:
+                length = L if m.normalize_input else Ls[0]
+                out = torch.empty(B, 1, length, dtype=torch.float32, device=x.device)
+                check(lib.cum_convt_out_fwd(g.data_ptr(), B, Tj, d["Hg_p"], pk[f"dec{j}.w"].data_ptr(),
+                                            meta["out_bias"], ptr(std), out.data_ptr(), length, length, 4, 2, st()),
+                      "cum_convt_out_fwd")
+        if not return_skip_connections:
+            return out
+        ncl = []
+        for i in reversed(range(D)):      # the reference returns the skips deepest-first (:275) in (B, C, L)
+            e = meta["enc"][i]
+            ncl.append(skips[i].view(B, Ls[i + 1], e["Ho_p"])[:, :, : e["Ho"]].permute(0, 2, 1))
+        ncl.append(hn.view(B, T, meta["dm_p"])[:, :, : meta["dm"]].permute(0, 2, 1))
+        return out, ncl

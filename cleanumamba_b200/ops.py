@@ -1,0 +1,150 @@
+"""Operator-level drop-ins with the SIGNATURES AND LAYOUTS of the third-party operators the reference calls
+(mamba-ssm==1.2.2 / causal-conv1d==1.1.0; SURVEY.md §8b "lower boundary"):
+
+    selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False)
+    causal_conv1d_fn(x, weight, bias=None, activation=None)
+    layer_norm_residual(h, residual, weight, bias, eps)
+
+They accept the reference's channel-major (b, d, l) tensors, transpose to the channels-last layout of the kernels,
+and call the C ABI.  Inside ``CleanUMamba.forward`` the engine calls the same kernels without these transposes.
+CUDA tensors only -- no fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ScanDesc, check, ptr
+
+LOG2E = 1.4426950408889634
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and t.device.type != "cuda":
+            raise RuntimeError("cleanumamba_b200.ops: CUDA tensors required (no CPU fallback)")
+
+
+def _cl(t):
+    """(b, c, l) -> contiguous channels-last (b, l, c) fp32."""
+    return t.detach().float().permute(0, 2, 1).contiguous()
+
+
+@torch.no_grad()
+def selective_scan_fn(u, delta, A, B, C_, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False, initial_state=None):
+    """u, delta, z: (b, d, l); A: (d, n); B, C: (b, n, l).  Returns y (b, d, l) [, last_state (b, d, n)].
+    ``initial_state`` (b, d, n) is an extension (the dependency's kernel always starts from h = 0)."""
+    _need_cuda(u, delta, A, B, C_, D, z, delta_bias, initial_state)
+    lib = _lib.init(u.device)
+    b, d, l = u.shape
+    n = A.shape[1]
+    ucl, dcl, Bcl, Ccl = _cl(u), _cl(delta), _cl(B), _cl(C_)
+    zcl = _cl(z) if z is not None else None
+    y = torch.empty(b, l, d, dtype=torch.float32, device=u.device)
+    a2 = (A.detach().float() * LOG2E).contiguous()
+    Df = D.detach().float().contiguous() if D is not None else None
+    bias = delta_bias.detach().float().contiguous() if delta_bias is not None else None
+    h0 = initial_state.detach().float().contiguous() if initial_state is not None else None
+    h_out = torch.empty(b, d, n, dtype=torch.float32, device=u.device) if return_last_state else None
+    s = ScanDesc()
+    s.u, s.u_bs, s.u_rs = ucl.data_ptr(), l * d, d
+    s.delta, s.dl_bs, s.dl_rs = dcl.data_ptr(), l * d, d
+    s.z, s.z_bs, s.z_rs = ptr(zcl), l * d, d
+    s.Bm, s.B_bs, s.B_rs = Bcl.data_ptr(), l * n, n
+    s.Cm, s.C_bs, s.C_rs = Ccl.data_ptr(), l * n, n
+    s.y, s.y_bs, s.y_rs = y.data_ptr(), l * d, d
+    s.a2, s.Dskip, s.delta_bias, s.h0, s.h_out = a2.data_ptr(), ptr(Df), ptr(bias), ptr(h0), ptr(h_out)
+    s.batch, s.len, s.d, s.n_state, s.delta_softplus = b, l, d, n, int(bool(delta_softplus))
+    check(lib.cum_selective_scan_fwd(C.byref(s), _lib.stream_ptr()), "cum_selective_scan_fwd")
+    out = y.permute(0, 2, 1).to(u.dtype)
+    return (out, h_out) if return_last_state else out
+
+
+@torch.no_grad()
+def causal_conv1d_fn(x, weight, bias=None, activation=None, conv_state=None):
+    """x: (b, d, l); weight: (d, width); bias: (d).  y = act(causal depthwise conv).  Only activation "silu"/"swish"
+    is fused (what Mamba uses).  ``conv_state`` (b, d, width-1), if given, supplies the inputs before t = 0 and is
+    updated in place to the last width-1 inputs (the role of causal_conv1d_update)."""
+    if activation not in ("silu", "swish"):
+        raise NotImplementedError("cleanumamba_b200.causal_conv1d_fn: activation must be 'silu' (Mamba's use)")
+    _need_cuda(x, weight, bias, conv_state)
+    lib = _lib.init(x.device)
+    b, d, l = x.shape
+    width = weight.shape[1]
+    dp = (d + 3) // 4 * 4
+    xcl = torch.zeros(b, l, dp, dtype=torch.float32, device=x.device)
+    xcl[:, :, :d] = x.detach().float().permute(0, 2, 1)
+    w = torch.zeros(width, dp, dtype=torch.float32, device=x.device)
+    w[:, :d] = weight.detach().float().t()
+    bv = torch.zeros(dp, dtype=torch.float32, device=x.device)
+    if bias is not None:
+        bv[:d] = bias.detach().float()
+    y = torch.empty(b, l, dp, dtype=torch.float32, device=x.device)
+    st = None
+    if conv_state is not None:
+        st = torch.zeros(b, width - 1, dp, dtype=torch.float32, device=x.device)
+        st[:, :, :d] = conv_state.detach().float().permute(0, 2, 1)
+    check(lib.cum_dwconv_silu_fwd(xcl.data_ptr(), l * dp, dp, w.data_ptr(), bv.data_ptr(), y.data_ptr(), ptr(st),
+                                  ptr(st), b, l, dp, width, _lib.stream_ptr()), "cum_dwconv_silu_fwd")
+    if conv_state is not None:
+        conv_state.copy_(st[:, :, :d].permute(0, 2, 1))
+    return y[:, :, :d].permute(0, 2, 1).to(x.dtype)
+
+
+@torch.no_grad()
+def layer_norm_residual(h, residual, weight, bias, eps=1e-5):
+    """(rows..., c) tensors: returns (LayerNorm(h + residual), h + residual) -- Block.forward's add + norm."""
+    _need_cuda(h, residual, weight, bias)
+    lib = _lib.init(h.device)
+    c = h.shape[-1]
+    cp = (c + 3) // 4 * 4
+    rows = h.numel() // c
+
+    def padc(t):
+        o = torch.zeros(rows, cp, dtype=torch.float32, device=h.device)
+        o[:, :c] = t.detach().float().reshape(rows, c)
+        return o
+    hp = padc(h)
+    rp = padc(residual) if residual is not None else None
+    g = torch.zeros(cp, dtype=torch.float32, device=h.device)
+    g[:c] = weight.detach().float()
+    be = torch.zeros(cp, dtype=torch.float32, device=h.device)
+    be[:c] = bias.detach().float()
+    ro = torch.empty_like(hp)
+    no = torch.empty_like(hp)
+    check(lib.cum_ln_residual_fwd(hp.data_ptr(), ptr(rp), ro.data_ptr(), no.data_ptr(), g.data_ptr(), be.data_ptr(),
+                                  float(eps), rows, c, cp, _lib.stream_ptr()), "cum_ln_residual_fwd")
+    return no[:, :c].reshape(h.shape), ro[:, :c].reshape(h.shape)
+
+
+def mamba_mixer_forward(mixer, hidden_states, inference_params=None):
+    raise NotImplementedError("stand-alone Mamba.forward is served through CleanUMamba.forward / StreamSession")
+
+
+def block_forward(block, hidden_states, residual=None, inference_params=None):
+    raise NotImplementedError("stand-alone Block.forward is served through CleanUMamba.forward / StreamSession")
+
+
+@torch.no_grad()
+def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None, addend=None, math="fp32"):
+    """Raw tap-GEMM on channels-last tensors (thin wrapper of cum_gemm_bias_act_fwd, used by tests / benchmarks).
+    a: (batch, rows, K) fp32 contiguous, K % 4 == 0;  w: (taps, N, K), N % 8 == 0;  bias: (N);  addend: (batch, m, N_out).
+    out[b, i, :] = EPI(bias + sum_s W_s . a[b, i + shifts[s], :]) + addend[b, i, :]   (rows outside a read as 0)."""
+    _need_cuda(a, w, bias, addend)
+    lib = _lib.init(a.device)
+    batch, rows, k = a.shape
+    taps, n, kw = w.shape
+    assert kw == k and a.is_contiguous() and w.is_contiguous()
+    m = rows if m is None else m
+    n_out = n // 2 if epilogue >= 8 else n
+    out = torch.empty(batch, m, n_out, dtype=torch.float32, device=a.device)
+    d = _lib.GemmDesc()
+    d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k, d.taps = a.data_ptr(), rows * k, k, rows, k, taps
+    d.tap_shift[0], d.tap_shift[1] = shifts
+    d.w, d.ldw, d.bias = w.data_ptr(), k, ptr(bias)
+    d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch, d.epilogue = out.data_ptr(), m * n_out, n_out, m, n, batch, epilogue
+    d.addend, d.add_batch_stride, d.add_row_stride = ptr(addend), m * n_out, n_out
+    d.math = _lib.MATH_BY_NAME[math]
+    check(lib.cum_gemm_bias_act_fwd(C.byref(d), _lib.stream_ptr()), "cum_gemm_bias_act_fwd")
+    return out

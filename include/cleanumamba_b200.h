@@ -1,0 +1,144 @@
+/*
+ * cleanumamba_b200 -- C ABI of libcleanumamba_sm100.so (sm_100a only).
+ *
+ * This is the drop-in boundary for the CleanUMamba hot path (forward / streaming of
+ * /root/reference/src/network/CleanUMamba.py:252-490).  The reference has NO native code: below its
+ * Python it calls ATen (cuDNN/cuBLAS) and the third-party operators of mamba-ssm==1.2.2 /
+ * causal-conv1d==1.1.0 (environment.yml:29-30).  Each entry point below names the reference-side
+ * operator(s) it replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator); the library never
+ *     allocates persistent device memory;
+ *   - every call is asynchronous and ordered on the cudaStream_t passed as `stream` (a `void*` here
+ *     so the header needs no CUDA include);
+ *   - return 0 on success, a negative CUM_E* code otherwise; never throws; cum_last_error() returns a
+ *     thread-local message for the most recent failure on the calling thread;
+ *   - callable from any host thread (the device is taken from cum_init / the current context).
+ *
+ * DATA LAYOUT.  Activations are channels-last: a (batch, time, channels) fp32 array whose channel
+ * count is padded to a multiple of 8 (pad lanes are kept at 0 by zero-padded packed weights).  The
+ * reference's NCL tensors only exist at the waveform ends, where C == 1 and both layouts coincide.
+ */
+#ifndef CLEANUMAMBA_B200_H_
+#define CLEANUMAMBA_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUM_ABI_VERSION 1
+
+/* error codes */
+#define CUM_OK            0
+#define CUM_EINVAL      (-22)   /* bad argument (shape / alignment / enum) */
+#define CUM_ENOTSUP     (-95)   /* valid request this build cannot serve */
+#define CUM_ECUDA       (-5)    /* CUDA runtime / driver error; see cum_last_error() */
+
+/* epilogues of cum_gemm_bias_act_fwd: v = acc + bias[n] */
+#define CUM_EPI_NONE         0  /* out[n]   = v[n]                                   */
+#define CUM_EPI_RELU         1  /* out[n]   = max(v[n], 0)                            */
+#define CUM_EPI_SILU         2  /* out[n]   = v[n] * sigmoid(v[n])                    */
+#define CUM_EPI_GLU_SIGMOID  8  /* out[n/2] = v[2c] * sigmoid(v[2c+1])   (layers.py:26-34; W rows interleaved) */
+#define CUM_EPI_GLU_RELU     9
+#define CUM_EPI_GLU_SILU    10
+#define CUM_EPI_GLU_GELU    11
+
+/* arithmetic of the contraction */
+#define CUM_MATH_FP32        0  /* CUDA-core FFMA, exact fp32 products (reference arithmetic) */
+#define CUM_MATH_TF32X3      1  /* tcgen05 kind::tf32, hi/lo split, 3 MMAs per product (~2^-21 rel. error) */
+#define CUM_MATH_TF32        2  /* tcgen05 kind::tf32, single pass (10-bit mantissa; NOT within the fp32 tolerance) */
+
+typedef void* cum_stream_t;    /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int         cum_abi_version(void);
+int         cum_init(int device);              /* selects + probes the device; fails unless it is sm_100 */
+const char* cum_last_error(void);
+
+/* ---- waveform ends -------------------------------------------------------------------------- */
+/* Replaces `std = x.std(dim=2, keepdim=True) + 1e-3; x /= std` (CleanUMamba.py:260-262, in place on the
+ * caller's tensor, unbiased std).  x: (batch, length) contiguous; std_out: (batch). */
+int cum_wave_normalize_fwd(float* x, float* std_out, int batch, int length, cum_stream_t stream);
+
+/* Replaces F.pad (CleanUMamba.py:219-223) + encoder[0][0] Conv1d(1,H,K,S) + ReLU (:109-110).
+ * x: (batch, length) [row stride x_stride]; samples t >= length read as 0.  w: (K, c_pad) taps-major;
+ * bias: (c_pad).  y: (batch, rows_out, c_pad) channels-last, y[b,t,c] = relu(b[c] + sum_k w[k,c] x[b,S t+k]). */
+int cum_conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w,
+                    const float* bias, float* y, int rows_out, int c_pad, int kernel, int stride,
+                    cum_stream_t stream);
+
+/* Replaces decoder[-1][2] ConvTranspose1d(H,1,K,S) (CleanUMamba.py:124) + the crop and `* std` (:318-319).
+ * g: (batch, rows_in, c_pad) channels-last; w: (K, c_pad); out: (batch, length) [row stride out_stride];
+ * out[b,m] = scale[b] * (bias + sum_{j,k: S j + k = m} <g[b,j,:], w[k,:]>), m < length.  scale may be NULL. */
+int cum_convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
+                      const float* scale, float* out, long long out_stride, int length, int kernel,
+                      int stride, cum_stream_t stream);
+
+/* ---- the tap-GEMM: every dense contraction of the path -------------------------------------- */
+/* out[b, m, :] = EPI( bias + sum_{s<taps} W_s . a[b, m + tap_shift[s], 0:k] ) (+ addend[b, m, :])
+ * Rows of `a` outside [0, a_rows) read as zero.  One descriptor covers:
+ *   - nn.Conv1d(k=1) / nn.Linear (taps=1): encoder[i][2], decoder[j][0], tsfm_conv1/2 (CleanUMamba.py:111,122,
+ *     139,194) and Mamba in_proj / x_proj / dt_proj / out_proj (mamba_ssm Mamba.forward);
+ *   - nn.Conv1d(k=4, s=2) (taps=2, shifts {0,+1} over the (L/2, 2C) view of the input; :109);
+ *   - nn.ConvTranspose1d(k=4, s=2) (taps=2, shifts {0,-1}, output seen as (Lin+1, 2Cout); :124);
+ *   with ReLU / GLU (layers.py) / U-Net skip add (:315) fused as epilogue + addend. */
+typedef struct cum_gemm_desc {
+    const float* a;  long long a_batch_stride; long long a_row_stride;  /* elements */
+    int a_rows;      /* valid rows per batch item */
+    int k;           /* contraction length per tap (multiple of 4) */
+    int taps;        /* 1 or 2 */
+    int tap_shift[2];
+    const float* w;  /* packed (taps, n, ldw), K contiguous */
+    int ldw;         /* >= k, multiple of 4 */
+    const float* bias;       /* (n) or NULL */
+    float* c;        long long c_batch_stride; long long c_row_stride;
+    int m;           /* output rows per batch item */
+    int n;           /* weight rows (multiple of 8); GLU epilogues write n/2 columns */
+    int batch;
+    int epilogue;    /* CUM_EPI_* */
+    const float* addend; long long add_batch_stride; long long add_row_stride;  /* optional */
+    int math;        /* CUM_MATH_* */
+} cum_gemm_desc;
+int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream);
+
+/* ---- Mamba block operators ------------------------------------------------------------------- */
+/* Replaces Block.forward's `residual = h + residual; h = LayerNorm(residual)` (mamba_ssm Block, non-fused
+ * branch) and the final add + norm_f (CleanUMamba.py:292-294).  All (rows, c_pad) with `c` real channels.
+ * residual_in may be NULL (first block); residual_out may alias residual_in. */
+int cum_ln_residual_fwd(const float* h, const float* residual_in, float* residual_out, float* normed,
+                        const float* gamma, const float* beta, float eps, long long rows, int c, int c_pad,
+                        cum_stream_t stream);
+
+/* Replaces causal_conv1d_fn(x, w(d,width), b, "silu") == silu(conv1d(x)[..., :L]) (Mamba.forward) and, with
+ * state pointers, causal_conv1d_update / the roll-and-sum of Mamba.step.  x: rows of stride x_row_stride inside a
+ * (batch, len, *) array; w: (width, d_pad) taps-major; y: (batch, len, d_pad).  conv_state (batch, width-1, d_pad):
+ * the inputs preceding t=0 (NULL = zeros); conv_state_out receives the last width-1 inputs (may alias). */
+int cum_dwconv_silu_fwd(const float* x, long long x_batch_stride, long long x_row_stride, const float* w,
+                        const float* bias, float* y, const float* conv_state, float* conv_state_out,
+                        int batch, int len, int d_pad, int width, cum_stream_t stream);
+
+/* Replaces selective_scan_fn(u, delta, A, B, C, D, z, delta_bias, delta_softplus=True) (mamba_ssm; oracle =
+ * selective_scan_ref) and, with h0/h_out, selective_state_update / Mamba.step's recurrence:
+ *   dl = softplus(delta + delta_bias);  h_t = exp(dl A) h_{t-1} + (dl u_t) B_t;  y_t = (<h_t, C_t> + D u_t) silu(z_t)
+ * Channels-last operands, each described by (pointer, batch stride, row stride) in elements:
+ *   u, delta, z, y: (batch, len, d);  Bm, Cm: (batch, len, n_state);  a2 = -exp(A_log) * log2(e): (d, n_state);
+ *   h0 / h_out: (batch, d, n_state) or NULL (zero initial state / state not returned; may alias). */
+typedef struct cum_scan_desc {
+    const float* u;     long long u_bs, u_rs;
+    const float* delta; long long dl_bs, dl_rs;
+    const float* z;     long long z_bs, z_rs;      /* z may be NULL (no gate) */
+    const float* Bm;    long long B_bs, B_rs;
+    const float* Cm;    long long C_bs, C_rs;
+    float* y;           long long y_bs, y_rs;
+    const float* a2;    /* (d, n_state) row-major */
+    const float* Dskip; /* (d) or NULL */
+    const float* delta_bias; /* (d) or NULL */
+    const float* h0; float* h_out;
+    int batch, len, d, n_state;
+    int delta_softplus;
+} cum_scan_desc;
+int cum_selective_scan_fwd(const cum_scan_desc* desc, cum_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLEANUMAMBA_B200_H_ */

@@ -1,0 +1,196 @@
+"""GPU parity of every C-ABI operator against the CPU oracle / plain PyTorch fp32 on the same seeded inputs.
+Tolerances are written next to each check (fp32 arithmetic, different summation order only)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cleanumamba_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel_err(a, b):
+    return ((a.double().cpu() - b.double().cpu()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("b,d,l,n,with_z,with_h0", [
+    (2, 64, 37, 64, True, False), (1, 2048, 130, 64, True, True), (3, 40, 50, 8, True, True),
+    (2, 128, 33, 16, False, False), (2, 96, 20, 24, True, False), (1, 8, 5, 8, True, True), (2, 24, 624, 64, True, False)])
+def test_selective_scan_matches_oracle(b, d, l, n, with_z, with_h0):
+    from cleanumamba_b200 import ops
+    g = torch.Generator().manual_seed(b * 1000 + d + l + n)
+    u = torch.randn(b, d, l, generator=g)
+    delta = torch.randn(b, d, l, generator=g) * 0.5
+    A = -torch.exp(torch.randn(d, n, generator=g) * 0.5 + 0.5)
+    Bm, Cm = torch.randn(b, n, l, generator=g), torch.randn(b, n, l, generator=g)
+    D = torch.randn(d, generator=g)
+    z = torch.randn(b, d, l, generator=g) if with_z else None
+    bias = torch.randn(d, generator=g) * 0.5 - 2.0
+    h0 = torch.randn(b, d, n, generator=g) if with_h0 else None
+    y_ref, h_ref = orc.selective_scan(u, delta, A, Bm, Cm, D, z, bias, True, h0=h0, return_last_state=True)
+    cu = lambda t: None if t is None else t.to(dev())  # noqa: E731
+    y, h = ops.selective_scan_fn(cu(u), cu(delta), cu(A), cu(Bm), cu(Cm), cu(D), cu(z), cu(bias), True,
+                                 return_last_state=True, initial_state=cu(h0))
+    assert y.shape == y_ref.shape and h.shape == h_ref.shape
+    assert rel_err(y, y_ref) < 2e-5      # ex2.approx + fp32 reassociation over <= 624 steps
+    assert rel_err(h, h_ref) < 2e-5
+
+
+def test_selective_scan_chunk_carry_equals_one_shot():
+    """Carried state: scanning two halves with h_out -> h0 equals one pass (streaming contract)."""
+    from cleanumamba_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    b, d, l, n = 2, 64, 48, 64
+    mk = lambda *s: torch.randn(*s, generator=g).to(dev())  # noqa: E731
+    u, delta, Bm, Cm, z = mk(b, d, l), mk(b, d, l) * 0.3, mk(b, n, l), mk(b, n, l), mk(b, d, l)
+    A, D, bias = -torch.exp(mk(d, n) * 0.3), mk(d), mk(d) * 0.1 - 1
+    y, h = ops.selective_scan_fn(u, delta, A, Bm, Cm, D, z, bias, True, return_last_state=True)
+    k = 19
+    y1, h1 = ops.selective_scan_fn(u[..., :k], delta[..., :k], A, Bm[..., :k], Cm[..., :k], D, z[..., :k], bias, True, return_last_state=True)
+    y2, h2 = ops.selective_scan_fn(u[..., k:], delta[..., k:], A, Bm[..., k:], Cm[..., k:], D, z[..., k:], bias, True, return_last_state=True, initial_state=h1)
+    assert torch.equal(torch.cat([y1, y2], -1), y) and torch.equal(h2, h)
+
+
+@pytest.mark.parametrize("b,d,l", [(2, 2048, 70), (3, 48, 5), (1, 8, 2), (2, 130, 33)])
+def test_causal_conv1d_silu(b, d, l):
+    from cleanumamba_b200 import ops
+    g = torch.Generator().manual_seed(d + l)
+    x, w, bias = torch.randn(b, d, l, generator=g), torch.randn(d, 4, generator=g), torch.randn(d, generator=g)
+    ref = F.silu(F.conv1d(x, w[:, None], bias, padding=3, groups=d)[..., :l])
+    y = ops.causal_conv1d_fn(x.to(dev()), w.to(dev()), bias.to(dev()), "silu")
+    assert rel_err(y, ref) < 2e-6
+    # carried conv state == processing the concatenation
+    st = torch.zeros(b, d, 3, device=dev())
+    k = max(1, l // 3)
+    ya = ops.causal_conv1d_fn(x[..., :k].to(dev()), w.to(dev()), bias.to(dev()), "silu", conv_state=st)
+    yb = ops.causal_conv1d_fn(x[..., k:].to(dev()), w.to(dev()), bias.to(dev()), "silu", conv_state=st) if l > k else ya[..., :0]
+    assert rel_err(torch.cat([ya, yb], -1), ref) < 2e-6
+    tail = F.pad(x, (3, 0))[..., -3:]
+    assert torch.allclose(st.cpu(), tail)
+
+
+@pytest.mark.parametrize("rows,c", [(50, 512), (7, 114), (33, 64), (5, 1000), (9, 16)])
+def test_layer_norm_residual(rows, c):
+    from cleanumamba_b200 import ops
+    g = torch.Generator().manual_seed(rows + c)
+    h, r = torch.randn(rows, c, generator=g), torch.randn(rows, c, generator=g) * 3
+    w, b = torch.randn(c, generator=g), torch.randn(c, generator=g)
+    ref = F.layer_norm(h + r, (c,), w, b, 1e-5)
+    y, res = ops.layer_norm_residual(h.to(dev()), r.to(dev()), w.to(dev()), b.to(dev()), 1e-5)
+    assert torch.allclose(res.cpu(), h + r, atol=0, rtol=0)
+    assert (y.cpu() - ref).abs().max().item() < 5e-6
+    y0, res0 = ops.layer_norm_residual(h.to(dev()), None, w.to(dev()), b.to(dev()), 1e-5)
+    assert (y0.cpu() - F.layer_norm(h, (c,), w, b, 1e-5)).abs().max().item() < 5e-6 and torch.equal(res0.cpu(), h)
+
+
+def _cl(x):  # (b, c, l) -> (b, l, c) contiguous on the GPU
+    return x.permute(0, 2, 1).contiguous().to(dev())
+
+
+@pytest.mark.parametrize("math", ["fp32"])
+@pytest.mark.parametrize("b,cin,cout,l", [(2, 64, 128, 300), (1, 768, 768, 150), (3, 56, 72, 38), (1, 8, 8, 6), (2, 104, 200, 1030)])
+def test_gemm_pointwise_and_glu(math, b, cin, cout, l):
+    from cleanumamba_b200 import _lib, ops
+    g = torch.Generator().manual_seed(cin + cout + l)
+    x = torch.randn(b, cin, l, generator=g)
+    w, bias = torch.randn(cout, cin, generator=g) / cin ** 0.5, torch.randn(cout, generator=g)
+    ref = F.conv1d(x, w[:, :, None], bias)
+    y = ops.gemm_bias_act(_cl(x), w[None].contiguous().to(dev()), bias.to(dev()), _lib.EPI_NONE, math=math)
+    assert rel_err(y.permute(0, 2, 1), ref) < 1e-5
+    yr = ops.gemm_bias_act(_cl(x), w[None].contiguous().to(dev()), bias.to(dev()), _lib.EPI_RELU, math=math)
+    assert rel_err(yr.permute(0, 2, 1), F.relu(ref)) < 1e-5
+    # GLU: interleave rows (a_c, b_c)
+    H = cout // 2
+    wi = torch.stack([w[:H], w[H:]], 1).reshape(cout, cin)
+    bi = torch.stack([bias[:H], bias[H:]], 1).reshape(cout)
+    add = torch.randn(b, l, H, generator=g)
+    yg = ops.gemm_bias_act(_cl(x), wi[None].contiguous().to(dev()), bi.to(dev()), _lib.EPI_GLU["Sigmoid"],
+                           addend=add.to(dev()), math=math)
+    refg = orc.glu(ref) + add.permute(0, 2, 1)
+    assert rel_err(yg.permute(0, 2, 1), refg) < 1e-5
+
+
+@pytest.mark.parametrize("math", ["fp32"])
+@pytest.mark.parametrize("b,cin,cout,lout", [(2, 64, 128, 200), (1, 256, 512, 77), (2, 56, 40, 129), (1, 768, 768, 130)])
+def test_gemm_as_strided_conv_and_transposed_conv(math, b, cin, cout, lout):
+    """Conv1d(k=4,s=2) and ConvTranspose1d(k=4,s=2) expressed as 2-tap GEMMs (engine.py layouts)."""
+    from cleanumamba_b200 import _lib, ops
+    g = torch.Generator().manual_seed(cin * 3 + cout + lout)
+    lin = 2 * lout + 2
+    x = torch.randn(b, cin, lin, generator=g)
+    w, bias = torch.randn(cout, cin, 4, generator=g) / (4 * cin) ** 0.5, torch.randn(cout, generator=g)
+    ref = F.relu(F.conv1d(x, w, bias, stride=2))
+    wt = torch.zeros(2, cout, 2 * cin)
+    for s in range(2):
+        for j in range(2):
+            wt[s, :, j * cin:(j + 1) * cin] = w[:, :, 2 * s + j]
+    a = _cl(x).view(b, lin // 2, 2 * cin)
+    y = ops.gemm_bias_act(a, wt.to(dev()), bias.to(dev()), _lib.EPI_RELU, shifts=(0, 1), m=lout, math=math)
+    assert rel_err(y.permute(0, 2, 1), ref) < 1e-5
+    # transposed conv: (b, cin, lout) -> (b, cout, 2 lout + 2), + skip addend, ReLU before the add
+    xt = torch.randn(b, cin, lout, generator=g)
+    wT, bT = torch.randn(cin, cout, 4, generator=g) / (2 * cin) ** 0.5, torch.randn(cout, generator=g)
+    skip = torch.randn(b, cout, lin, generator=g)
+    refT = F.relu(F.conv_transpose1d(xt, wT, bT, stride=2)) + skip
+    wp = torch.zeros(2, 2 * cout, cin)
+    for s in range(2):
+        for par in range(2):
+            wp[s, par * cout:(par + 1) * cout] = wT[:, :, 2 * s + par].t()
+    bp = torch.cat([bT, bT])
+    add = _cl(skip).view(b, lout + 1, 2 * cout)
+    yT = ops.gemm_bias_act(_cl(xt), wp.to(dev()), bp.to(dev()), _lib.EPI_RELU, shifts=(0, -1), m=lout + 1,
+                           addend=add, math=math)
+    assert rel_err(yT.reshape(b, lin, cout).permute(0, 2, 1), refT) < 1e-5
+
+
+def test_wave_ends():
+    """normalise (in place), conv_in (Cin=1 + pad), convt_out (Cout=1 + crop + scale)."""
+    from cleanumamba_b200 import _lib
+    lib = _lib.init(dev())
+    g = torch.Generator().manual_seed(5)
+    B, L, H = 3, 1000, 56
+    x = torch.randn(B, L, generator=g) * 0.3 + 0.05
+    xs = x.to(dev())
+    std = torch.empty(B, device=dev())
+    _lib.check(lib.cum_wave_normalize_fwd(xs.data_ptr(), std.data_ptr(), B, L, _lib.stream_ptr()), "norm")
+    std_ref = x.std(dim=1) + 1e-3
+    assert torch.allclose(std.cpu(), std_ref, rtol=1e-6, atol=0)
+    assert torch.allclose(xs.cpu(), x / std_ref[:, None], rtol=2e-6, atol=1e-7)
+    # conv_in with implicit right padding to 1022 -> rows_out 510
+    Lp = orc.valid_length(L, 3)
+    rows = (Lp - 4) // 2 + 1
+    w, bias = torch.randn(H, 1, 4, generator=g), torch.randn(H, generator=g)
+    ref = F.relu(F.conv1d(F.pad(x, (0, Lp - L))[:, None], w, bias, stride=2))
+    y = torch.empty(B, rows, H, device=dev())
+    xd = x.to(dev())
+    _lib.check(lib.cum_conv_in_fwd(xd.data_ptr(), L, B, L, w[:, 0].t().contiguous().to(dev()).data_ptr(),
+                                   bias.to(dev()).data_ptr(), y.data_ptr(), rows, H, 4, 2, _lib.stream_ptr()), "conv_in")
+    assert rel_err(y.permute(0, 2, 1), ref) < 1e-6
+    # convt_out
+    for Hc in (56, 64, 128):
+        gin = torch.randn(B, Hc, rows, generator=g)
+        wT, bT = torch.randn(Hc, 1, 4, generator=g), torch.randn(1, generator=g)
+        scale = torch.rand(B, generator=g) + 0.5
+        refo = F.conv_transpose1d(gin, wT, bT, stride=2)[..., :L] * scale[:, None, None]
+        out = torch.empty(B, 1, L, device=dev())
+        gcl = gin.permute(0, 2, 1).contiguous().to(dev())
+        _lib.check(lib.cum_convt_out_fwd(gcl.data_ptr(), B, rows, Hc, wT[:, 0].t().contiguous().to(dev()).data_ptr(),
+                                         float(bT), scale.to(dev()).data_ptr(), out.data_ptr(), L, L, 4, 2,
+                                         _lib.stream_ptr()), "convt_out")
+        assert rel_err(out, refo) < 2e-6
+
+
+def test_bad_arguments_fail_loudly():
+    from cleanumamba_b200 import _lib, ops
+    a = torch.randn(1, 8, 6, device=dev())      # K = 6 is not a multiple of 4
+    w = torch.randn(1, 8, 6, device=dev())
+    with pytest.raises(RuntimeError, match="multiples of 4"):
+        ops.gemm_bias_act(a, w)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.selective_scan_fn(*[torch.zeros(1, 4, 4)] * 2, torch.zeros(4, 4), torch.zeros(1, 4, 4), torch.zeros(1, 4, 4))
