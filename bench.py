@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CleanUMamba hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--seconds S] [--model e8|e6]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): CleanUMamba E8 full (41.37 M params, seeded random init -- the full checkpoints are
+not shipped), batch 64 x 10 s of 16 kHz synthetic noisy speech per GPU, offline forward, fp32 arithmetic.  A "step" is
+one forward pass over one batch.  Metric: audio-seconds denoised per wall-second, aggregate over all GPUs (utterance
+sharding, no data-path collective -> weak scaling).
+
+Own arm     : the product (cleanumamba_b200 -> libcleanumamba_sm100.so).  `value` = inputs resident in HBM, CUDA-event
+              timed, max over ranks; `e2e` = same call with pinned HOST buffers, H2D + forward + D2H inside the timing.
+Reference arm (--impl reference): the reference's CPU path (oracle port of CleanUMamba.forward + selective_scan_ref,
+              oracle/cleanumamba_oracle.py) on all host cores, each step a bounded sample (1 clip) of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "audio-sec denoised/sec (16 kHz)"
+UNIT = "audio-s/s"
+SR = 16000
+CONFIGS = {
+    "e8": dict(channels_input=1, channels_output=1, channels_H=64, max_H=768, encoder_n_layers=8, kernel_size=4,
+               stride=2, tsfm_n_layers=3, tsfm_n_head=8, tsfm_d_model=512, tsfm_d_inner=2048),
+    "e6": dict(channels_input=1, channels_output=1, channels_H=64, max_H=768, encoder_n_layers=6, kernel_size=4,
+               stride=2, tsfm_n_layers=3, tsfm_n_head=8, tsfm_d_model=512, tsfm_d_inner=2048),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def synth_noisy(batch, seconds, seed):
+    """Cheap synthetic noisy speech-like batch (harmonic stack + coloured noise), (B,1,T) fp32 on the CPU."""
+    g = torch.Generator().manual_seed(seed)
+    T = int(seconds * SR)
+    t = torch.arange(T, dtype=torch.float32) / SR
+    f0 = 80 + 220 * torch.rand(batch, 1, generator=g)
+    x = torch.zeros(batch, T)
+    for k in range(1, 9):
+        x += torch.sin(2 * torch.pi * k * f0 * t + 6.28 * torch.rand(batch, 1, generator=g)) / k
+    x *= 0.5 * (1 - torch.cos(2 * torch.pi * 4 * t))
+    x *= 0.3 / x.abs().amax(1, keepdim=True)
+    n = torch.randn(batch, T, generator=g)
+    n = 0.5 * (n + torch.roll(n, 1, 1))
+    snr = -5 + 30 * torch.rand(batch, 1, generator=g)
+    n *= x.pow(2).mean(1, keepdim=True).sqrt() / n.pow(2).mean(1, keepdim=True).sqrt() * 10 ** (-snr / 20)
+    return (x + n)[:, None].contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_pass(cfg, seconds, steps, warmup, threads):
+    """Times the oracle port of the reference's CPU path; returns (audio_s_per_s, ms_per_step, sample description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cleanumamba_oracle as orc
+    from cleanumamba_b200.network import Net
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in Net("CleanUMamba", dict(cfg)).state_dict().items()}
+    x = synth_noisy(1, seconds, 1234)
+    for _ in range(warmup):
+        orc.forward(sd, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.forward(sd, x)
+    dt = (time.perf_counter() - t0) / steps
+    return seconds / dt, dt * 1e3, f"1 clip x {seconds:g} s per step, {steps} steps after {warmup} warm-up, fp32, {threads} threads"
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    val, ms, sample = cpu_reference_pass(cfg, args.seconds, steps, warmup, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"CleanUMamba {args.model.upper()} full offline forward, reference CPU path "
+                                   f"(oracle port of CleanUMamba.forward + selective_scan_ref), {sample}"},
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="e8", choices=list(CONFIGS))
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--math", default=os.environ.get("CUM_MATH", "fp32"), choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.model]
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU fallback)"
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from cleanumamba_b200.network import Net
+    torch.manual_seed(0)
+    net = Net("CleanUMamba", dict(cfg, math_mode=args.math)).to(dev).eval()
+    eng = net.engine()
+    B, T = args.batch, int(args.seconds * SR)
+    host_in = synth_noisy(B, args.seconds, 1234 + rank).pin_memory()
+    host_out = torch.empty(B, 1, T).pin_memory()
+    x_dev = host_in.to(dev)
+    work = torch.empty_like(x_dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        work.copy_(x_dev)              # forward normalises its input in place (reference semantics): fresh copy per step
+        with torch.no_grad():
+            return net(work)
+
+    def step_e2e():
+        work.copy_(host_in, non_blocking=True)
+        with torch.no_grad():
+            y = net(work)
+        host_out.copy_(y, non_blocking=True)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    # ---- timed region 1: device-resident inputs --------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.prof, eng.launches = [], 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launches
+    prof = eng.profile_summary()
+    eng.prof = None
+
+    # ---- timed region 2: end to end through the public API with host buffers ---------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    audio_per_step = world * B * args.seconds
+    value = audio_per_step * args.steps / (ms / 1e3)
+    e2e_value = audio_per_step * args.steps / (ms_e2e / 1e3)
+    pk = peaks()
+
+    # roofline of the dominant kernel family (the tap-GEMM: all convs + projections), timed with CUDA events inside
+    # the timed region; `peak` is the measured dense bf16 tensor throughput (sustained: timed inside a long step)
+    gem = {"ms": 0.0, "launches": 0, "flops": 0}
+    for k in ("gemm", "gemm_tap2"):
+        if k in prof:
+            for f in gem:
+                gem[f] += prof[k][f]
+    total_kernel_ms = sum(v["ms"] for v in prof.values())
+    achieved = gem["flops"] / (gem["ms"] / 1e3) / 1e12 if gem["ms"] else 0.0
+    roofline = {"kernel": "tap-GEMM (conv/convT/1x1/projection contractions, %s)" % args.math, "bound": "tensor",
+                "achieved": round(achieved, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(achieved / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "share_of_step": round(gem["ms"] / total_kernel_ms, 4) if total_kernel_ms else None,
+                "launches_per_step": gem["launches"] // args.steps}
+    scan = prof.get("selective_scan")
+    scan_roof = None
+    if scan:
+        gbs = scan["bytes"] / (scan["ms"] / 1e3) / 1e9
+        scan_roof = {"kernel": "selective_scan_fwd", "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"],
+                     "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4), "traffic": None,
+                     "state_updates_per_s": round(scan["flops"] / (scan["ms"] / 1e3), 0),
+                     "share_of_step": round(scan["ms"] / total_kernel_ms, 4),
+                     "note": "d_state=64: MUFU(ex2)/FMA-bound, not HBM-bound (SURVEY.md §7); 16 ex2/clk/SM ceiling = %.3g updates/s"
+                             % (16 * 148 * 1.9e9)}
+    kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] // args.steps}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, _, sample = cpu_reference_pass(cfg, args.seconds, 3, 1, threads)
+        cpu = {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"CleanUMamba {args.model.upper()} full ({sum(p.numel() for p in net.parameters())/1e6:.2f}M, "
+                                   f"seeded random init) offline forward, batch {B} x {args.seconds:g} s @16 kHz per GPU, "
+                                   f"math={args.math}",
+                       "global_batch": world * B, "clip_seconds": args.seconds, "parallelism": f"utterance-sharded x{world}",
+                       "l2": "inputs+activations per step (>25 GB) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": B * T * 4,
+                    "d2h_bytes_per_step": B * T * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "scan_roofline": scan_roof,
+            "kernels": kernels}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,15 +73,17 @@ int cum_wave_normalize_fwd(float* x, float* std_out, int batch, int length, cum_
 }
 
 int cum_conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
-                    float* y, int rows_out, int c_pad, int kernel, int stride, cum_stream_t stream) {
-    return conv_in_fwd(x, x_stride, batch, length, w, bias, y, rows_out, c_pad, kernel, stride, (cudaStream_t)stream);
+                    float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
+                    cum_stream_t stream) {
+    return conv_in_fwd(x, x_stride, batch, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale, group_rows,
+                       (cudaStream_t)stream);
 }
 
 int cum_convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
-                      const float* scale, float* out, long long out_stride, int length, int kernel, int stride,
-                      cum_stream_t stream) {
-    return convt_out_fwd(g, batch, rows_in, c_pad, w, bias, scale, out, out_stride, length, kernel, stride,
-                         (cudaStream_t)stream);
+                      const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
+                      int kernel, int stride, cum_stream_t stream) {
+    return convt_out_fwd(g, batch, rows_in, c_pad, w, bias, scale, scale_group, out, out_stride, first, length, kernel,
+                         stride, (cudaStream_t)stream);
 }
 
 int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream) {
@@ -94,6 +96,10 @@ int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream) {
         case CUM_MATH_TF32: return gemm_tc_fwd(*desc, (cudaStream_t)stream);
         default: set_error("gemm: unknown math mode %d", desc->math); return CUM_EINVAL;
     }
+}
+
+int cum_split_tf32(const float* w, float* hi, float* lo, long long count, cum_stream_t stream) {
+    return split_tf32(w, hi, lo, count, (cudaStream_t)stream);
 }
 
 int cum_ln_residual_fwd(const float* h, const float* residual_in, float* residual_out, float* normed,

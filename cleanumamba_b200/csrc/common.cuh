@@ -69,12 +69,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // entry points implemented per translation unit (called by api.cu)
 int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStream_t st);
 int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
-                float* y, int rows_out, int c_pad, int kernel, int stride, cudaStream_t st);
+                float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
+                cudaStream_t st);
 int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
-                  const float* scale, float* out, long long out_stride, int length, int kernel, int stride,
-                  cudaStream_t st);
+                  const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
+                  int kernel, int stride, cudaStream_t st);
 int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st);
+int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t st);
 int ln_residual_fwd(const float* h, const float* residual_in, float* residual_out, float* normed,
                     const float* gamma, const float* beta, float eps, long long rows, int c, int c_pad,
                     cudaStream_t st);

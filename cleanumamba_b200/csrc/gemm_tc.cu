@@ -1,8 +1,433 @@
-// tcgen05 / TMEM / TMA tap-GEMM (CUM_MATH_TF32X3, CUM_MATH_TF32) -- placeholder until the kernel lands.
+// tcgen05 / TMEM / TMA tap-GEMM for sm_100a (CUM_MATH_TF32X3 and CUM_MATH_TF32).
+//
+//   out[b, m, :] = EPI( bias + sum_{s<taps} W_s . a[b, m + shift_s, 0:k] ) (+ addend[b, m, :])
+//
+// One persistent CTA per SM, 128 x 256 output tile (UMMA M=128, N<=256 runtime, K=8 for kind::tf32), accumulators in
+// TMEM (2 x 256 columns, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1), operands
+// staged by TMA into 128B-swizzled K-major shared-memory tiles.  The conv taps are extra K-blocks whose A-tile is the
+// same tensor map fetched at a shifted row coordinate; rows outside [0, a_rows) are zero-filled by TMA, which is
+// exactly the conv / transposed-conv boundary condition.
+//
+// Warp roles (384 threads):
+//   warp 0        TMA producer (one lane)
+//   warp 1        TMEM allocator + MMA issuer (one lane)
+//   warps 4..7    epilogue: tcgen05.ld -> bias / ReLU / GLU / skip-add -> global
+//   warps 8..11   (TF32X3 only) operand splitter: A tile -> hi = a & 0xffffe000 (in place), lo = a - hi
+//
+// TF32X3: fp32 activations cannot be fed to kind::tf32 directly within the 1e-4 waveform tolerance (10-bit mantissa,
+// 22 stacked layers), so every product is expanded a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (three MMAs, error
+// ~3*2^-22 per product).  W is split once at pack time (cum_split_tf32), A is split in shared memory by the
+// splitter warps between TMA arrival and MMA issue.
 #include "common.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 namespace cum {
-int gemm_tc_fwd(const cum_gemm_desc&, cudaStream_t) {
-    set_error("gemm: tcgen05 path not built yet");
-    return CUM_ENOTSUP;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 256;
+constexpr int TC_BK = 32;                     // fp32 elements per K-block = one 128-byte swizzle row
+constexpr int TC_UMMA_K = 8;                  // kind::tf32
+constexpr int TC_THREADS = 384;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr uint32_t TC_W_BYTES = TC_BN * TC_BK * 4;   // 32 KB
+constexpr uint32_t TC_TMEM_COLS = 512;
+
+template <bool X3> struct TcCfg {
+    static constexpr int STAGES = X3 ? 2 : 4;
+    static constexpr uint32_t STAGE_BYTES = X3 ? 2 * (TC_A_BYTES + TC_W_BYTES) : (TC_A_BYTES + TC_W_BYTES);
+    static constexpr uint32_t TX_BYTES = X3 ? (TC_A_BYTES + 2 * TC_W_BYTES) : (TC_A_BYTES + TC_W_BYTES);
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+    int m, n, k, taps, shift0, shift1, batch, epi;
+    int m_tiles, n_tiles, k_blocks;
+    const float* bias;
+    float* c; long long c_bs, c_rs;
+    const float* addend; long long add_bs, add_rs;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    // K-major, 128B swizzle: 8-row core-matrix groups are 1024 B apart (SBO); LBO unused; version 1 (sm_100)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <bool X3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
+               const __grid_constant__ CUtensorMap tmWl, const TcParams p) {
+    using Cfg = TcCfg<X3>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    // stage layout: [A | (A_lo) | W_hi | (W_lo)]
+    auto a_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES; };
+    auto alo_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + TC_A_BYTES; };
+    auto w_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + (X3 ? 2 : 1) * TC_A_BYTES; };
+    auto wlo_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + 2 * TC_A_BYTES + TC_W_BYTES; };
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto split_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
+    const int k_iters = p.k_blocks * p.taps;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmWh);
+        if (X3) tma_prefetch_desc(&tmWl);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+            mbar_init(split_bar(s), 128);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](int tile, int& b, int& m0, int& n0) {
+        const int nb = tile % p.n_tiles;
+        const int r = tile / p.n_tiles;
+        const int mb = r % p.m_tiles;
+        b = r / p.m_tiles;
+        m0 = mb * TC_BM;
+        n0 = nb * TC_BN;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================================== TMA producer
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int b, m0, n0;
+            tile_coords(tile, b, m0, n0);
+            for (int it = 0; it < k_iters; ++it) {
+                const int tap = it / p.k_blocks, kb = it - tap * p.k_blocks;
+                const int shift = tap == 0 ? p.shift0 : p.shift1;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), Cfg::TX_BYTES);
+                tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * TC_BK, m0 + shift, b);
+                tma_load_3d(smem_base + w_off(s), &tmWh, full_bar(s), kb * TC_BK, n0, tap);
+                if (X3) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), kb * TC_BK, n0, tap);
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================================================================== MMA issuer
+        int s = 0;
+        uint32_t ph = 0;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            int b, m0, n0;
+            tile_coords(tile, b, m0, n0);
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (tcount >> 1) & 1;
+            int n_rem = p.n - n0;
+            if (n_rem > TC_BN) n_rem = TC_BN;
+            const uint32_t umma_n = (uint32_t)((n_rem + 15) & ~15);
+            // c=f32 (1<<4), a=b=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_BN;
+            mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+            tc_fence_after();
+            for (int it = 0; it < k_iters; ++it) {
+                mbar_wait(X3 ? split_bar(s) : full_bar(s), ph);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_base + a_off(s));
+                const uint64_t bdesc = umma_desc_sw128(smem_base + w_off(s));
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
+                    const uint64_t koff = (uint64_t)((kk * TC_UMMA_K * 4) >> 4);
+                    umma_tf32(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
+                    if (X3) {
+                        const uint64_t alo = umma_desc_sw128(smem_base + alo_off(s));
+                        const uint64_t blo = umma_desc_sw128(smem_base + wlo_off(s));
+                        umma_tf32(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
+                        umma_tf32(tmem_d, adesc + koff, blo + koff, idesc, 1u);
+                    }
+                }
+                umma_commit(empty_bar(s));
+                if (it == k_iters - 1) umma_commit(tfull_bar(acc));
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================================================================== epilogue
+        const int q = warp & 3;
+        const bool glu = p.epi >= CUM_EPI_GLU_SIGMOID;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            int b, m0, n0;
+            tile_coords(tile, b, m0, n0);
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (tcount >> 1) & 1;
+            mbar_wait(tfull_bar(acc), acc_ph);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.m;
+            float* crow = p.c + (long long)b * p.c_bs + (long long)row * p.c_rs;
+            const float* arow = p.addend ? p.addend + (long long)b * p.add_bs + (long long)row * p.add_rs : nullptr;
+            int n_rem = p.n - n0;
+            if (n_rem > TC_BN) n_rem = TC_BN;
+            for (int c0 = 0; c0 < n_rem; c0 += 32) {
+                float v[32];
+                __syncwarp();      // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c0), v);
+                if (!row_ok) continue;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const int n = n0 + c0 + g * 4;
+                    if (n >= p.n) break;
+                    float x0 = v[g * 4 + 0], x1 = v[g * 4 + 1], x2 = v[g * 4 + 2], x3 = v[g * 4 + 3];
+                    if (p.bias) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                        x0 += bv.x; x1 += bv.y; x2 += bv.z; x3 += bv.w;
+                    }
+                    if (glu) {
+                        float2 o = make_float2(x0 * glu_gate(p.epi, x1), x2 * glu_gate(p.epi, x3));
+                        const int oc = n >> 1;
+                        if (arow) {
+                            const float2 ad = __ldg(reinterpret_cast<const float2*>(arow + oc));
+                            o.x += ad.x; o.y += ad.y;
+                        }
+                        *reinterpret_cast<float2*>(crow + oc) = o;
+                    } else {
+                        float4 o = make_float4(unary_act(p.epi, x0), unary_act(p.epi, x1), unary_act(p.epi, x2), unary_act(p.epi, x3));
+                        if (arow) {
+                            const float4 ad = __ldg(reinterpret_cast<const float4*>(arow + n));
+                            o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                        }
+                        *reinterpret_cast<float4*>(crow + n) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    } else if (X3 && warp >= 8) {
+        // ===================================================================== operand splitter (A tile)
+        const int t = threadIdx.x - 256;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int it = 0; it < k_iters; ++it) {
+                mbar_wait(full_bar(s), ph);
+                float4* hi = reinterpret_cast<float4*>(smem_gen + a_off(s));
+                float4* lo = reinterpret_cast<float4*>(smem_gen + alo_off(s));
+#pragma unroll
+                for (int j = 0; j < (int)(TC_A_BYTES / 16 / 128); ++j) {
+                    const int i = t + 128 * j;
+                    const float4 v = hi[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(split_bar(s));
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS));
+    }
+}
+
+// hi/lo split used for the weights (same bit arithmetic as the in-kernel activation split)
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = w[i];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        hi[i] = h;
+        lo[i] = v - h;
+    }
+}
+
+int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t st) {
+    CUM_REQUIRE(w && hi && lo && n > 0, "split_tf32: bad arguments");
+    split_tf32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w, hi, lo, n);
+    CUM_LAUNCH_CHECK("split_tf32_kernel");
+    return CUM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_elems,
+                    uint64_t s2_elems, uint32_t box0, uint32_t box1, const char* what) {
+    auto enc = get_encode();
+    if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return CUM_ECUDA; }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {s1_elems * 4, s2_elems * 4};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("gemm_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu strides %llu,%llu)", what,
+                  (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                  (unsigned long long)strides[0], (unsigned long long)strides[1]);
+        return CUM_ECUDA;
+    }
+    return CUM_OK;
+}
+
+template <bool X3>
+static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
+    using Cfg = TcCfg<X3>;
+    auto kern = gemm_tc_kernel<X3>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
+        attr_done = true;
+    }
+    CUtensorMap tmA, tmWh, tmWl;
+    const uint64_t a_bs = d.batch > 1 ? (uint64_t)d.a_batch_stride : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
+    int rc = make_map(&tmA, d.a, (uint64_t)d.k, (uint64_t)d.a_rows, (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs,
+                      TC_BK, TC_BM, "A");
+    if (rc) return rc;
+    const uint64_t w_ts = (uint64_t)d.n * (uint64_t)d.ldw;
+    rc = make_map(&tmWh, d.w, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, TC_BN, "W");
+    if (rc) return rc;
+    if (X3) {
+        rc = make_map(&tmWl, d.w_lo, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, TC_BN, "W_lo");
+        if (rc) return rc;
+    } else {
+        tmWl = tmWh;
+    }
+    TcParams p;
+    p.m = d.m; p.n = d.n; p.k = d.k; p.taps = d.taps; p.shift0 = d.tap_shift[0]; p.shift1 = d.tap_shift[1];
+    p.batch = d.batch; p.epi = d.epilogue;
+    p.m_tiles = (int)cdiv(d.m, TC_BM); p.n_tiles = (int)cdiv(d.n, TC_BN); p.k_blocks = (int)cdiv(d.k, TC_BK);
+    p.bias = d.bias; p.c = d.c; p.c_bs = d.c_batch_stride; p.c_rs = d.c_row_stride;
+    p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
+    const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
+    CUM_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
+    const int grid = (int)(total < sm_count() ? total : sm_count());
+    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmWh, tmWl, p);
+    CUM_LAUNCH_CHECK("gemm_tc_kernel");
+    return CUM_OK;
+}
+
+int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
+    CUM_REQUIRE(d.a_row_stride >= d.k || d.a_rows == 1, "gemm_tc: a_row_stride < k");
+    if (d.math == CUM_MATH_TF32X3) {
+        CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: TF32X3 needs w_lo (see cum_split_tf32)");
+        return launch_tc<true>(d, st);
+    }
+    return launch_tc<false>(d, st);
+}
+
 }  // namespace cum

@@ -59,7 +59,8 @@ constexpr int CI_MAXK = 8;
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, long long x_stride, int length,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        float* __restrict__ y, int rows_out, int c_pad, int kernel,
-                                                       int stride) {
+                                                       int stride, const float* __restrict__ in_scale, int scale_groups,
+                                                       int group_rows) {
     extern __shared__ float xs[];
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * CI_ROWS;
@@ -76,9 +77,11 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     for (int idx = threadIdx.x; idx < rows * c4n; idx += blockDim.x) {
         const int t = idx / c4n, c4 = idx - t * c4n;
         float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+        // streaming: the samples feeding output row t are divided by the running std of the hop that row belongs to
+        const float sdiv = in_scale ? __ldg(in_scale + (long long)b * scale_groups + (t0 + t) / group_rows) : 1.0f;
 #pragma unroll 4
         for (int k = 0; k < kernel; ++k) {
-            const float xv = xs[t * stride + k];
+            const float xv = in_scale ? xs[t * stride + k] / sdiv : xs[t * stride + k];
             const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)k * c_pad) + c4);
             acc.x = fmaf(wv.x, xv, acc.x); acc.y = fmaf(wv.y, xv, acc.y);
             acc.z = fmaf(wv.z, xv, acc.z); acc.w = fmaf(wv.w, xv, acc.w);
@@ -89,7 +92,8 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
 }
 
 int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
-                float* y, int rows_out, int c_pad, int kernel, int stride, cudaStream_t st) {
+                float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
+                cudaStream_t st) {
     CUM_REQUIRE(x && w && bias && y, "conv_in: null pointer");
     CUM_REQUIRE(batch > 0 && length > 0 && rows_out > 0, "conv_in: empty problem");
     CUM_REQUIRE(c_pad > 0 && c_pad % 4 == 0, "conv_in: c_pad=%d must be a positive multiple of 4", c_pad);
@@ -97,7 +101,10 @@ int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const
     CUM_REQUIRE(aligned16(w) && aligned16(bias) && aligned16(y), "conv_in: w/bias/y must be 16-byte aligned");
     dim3 grid((unsigned)cdiv(rows_out, CI_ROWS), batch);
     const size_t smem = (size_t)(CI_ROWS * stride + kernel) * sizeof(float);
-    conv_in_kernel<<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, rows_out, c_pad, kernel, stride);
+    CUM_REQUIRE(!in_scale || group_rows > 0, "conv_in: group_rows must be positive when in_scale is given");
+    const int groups = in_scale ? (int)cdiv(rows_out, group_rows) : 0;
+    conv_in_kernel<<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale,
+                                            groups, group_rows);
     CUM_LAUNCH_CHECK("conv_in_kernel");
     return CUM_OK;
 }
@@ -114,21 +121,25 @@ constexpr int CT_MAXK = 8;
 template <int LPR>
 __global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict__ g, int rows_in, int c_pad,
                                                          const float* __restrict__ w, float bias,
-                                                         const float* __restrict__ scale, float* __restrict__ out,
-                                                         long long out_stride, int length, int kernel, int stride,
-                                                         int halo) {
+                                                         const float* __restrict__ scale, int scale_groups,
+                                                         int scale_group, float* __restrict__ out, long long out_stride,
+                                                         int first, int length, int kernel, int stride, int halo) {
     extern __shared__ float dots[];  // [(CT_ROWS + halo)][kernel]
     const int b = blockIdx.y;
-    const int j0 = blockIdx.x * CT_ROWS - halo;  // first staged input row (may be negative)
-    const int nrows = CT_ROWS + halo;
+    const long long mbase = (long long)first + (long long)blockIdx.x * CT_ROWS * stride;  // first output of this CTA
+    const int jbase = (int)(mbase / stride);
+    const int j0 = jbase - halo;                 // first staged input row (may be negative)
+    const int nrows = CT_ROWS + halo + 1;        // +1: mbase need not be a multiple of stride
     const int c4n = c_pad >> 2;
     const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR, ngrp = blockDim.x / LPR;
-    for (int r = grp; r < nrows; r += ngrp) {
+    // NOTE: the trip count must be warp-uniform (full-mask shuffles below): iterate on r0, predicate on r
+    for (int r0 = 0; r0 < nrows; r0 += ngrp) {
+        const int r = r0 + grp;
         const int j = j0 + r;
         float acc[CT_MAXK];
 #pragma unroll
         for (int k = 0; k < CT_MAXK; ++k) acc[k] = 0.f;
-        if (j >= 0 && j < rows_in) {
+        if (r < nrows && j >= 0 && j < rows_in) {
             const float4* row = reinterpret_cast<const float4*>(g + ((long long)b * rows_in + j) * c_pad);
             for (int c4 = sub; c4 < c4n; c4 += LPR) {
                 const float4 v = __ldg(row + c4);
@@ -147,43 +158,45 @@ __global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict_
                 float v = acc[k];
 #pragma unroll
                 for (int o = LPR >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (sub == 0) dots[r * kernel + k] = v;
+                if (sub == 0 && r < nrows) dots[r * kernel + k] = v;
             }
         }
     }
     __syncthreads();
-    const float sc = scale ? scale[b] : 1.0f;
-    const long long m0 = (long long)blockIdx.x * CT_ROWS * stride;
     for (int i = threadIdx.x; i < CT_ROWS * stride; i += blockDim.x) {
-        const long long m = m0 + i;
-        if (m >= length) break;
+        const long long m = mbase + i;           // index in the full transposed-conv output
+        const long long o = m - first;           // index in `out`
+        if (o >= length) break;
         float acc = bias;
         for (int k = (int)(m % stride); k < kernel; k += stride) {
             const long long j = (m - k) / stride;
             if (m - k >= 0 && j < rows_in) acc += dots[(int)(j - j0) * kernel + k];
         }
-        out[(long long)b * out_stride + m] = acc * sc;
+        const float sc = scale ? __ldg(scale + (long long)b * scale_groups + o / scale_group) : 1.0f;
+        out[(long long)b * out_stride + o] = acc * sc;
     }
 }
 
 int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
-                  const float* scale, float* out, long long out_stride, int length, int kernel, int stride,
-                  cudaStream_t st) {
+                  const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
+                  int kernel, int stride, cudaStream_t st) {
     CUM_REQUIRE(g && w && out, "convt_out: null pointer");
-    CUM_REQUIRE(batch > 0 && rows_in > 0 && length > 0, "convt_out: empty problem");
+    CUM_REQUIRE(batch > 0 && batch <= 65535 && rows_in > 0 && length > 0 && first >= 0, "convt_out: empty problem");
     CUM_REQUIRE(c_pad > 0 && c_pad % 4 == 0, "convt_out: c_pad=%d must be a positive multiple of 4", c_pad);
     CUM_REQUIRE(kernel >= 1 && kernel <= CT_MAXK && stride >= 1 && stride <= kernel, "convt_out: kernel=%d stride=%d unsupported", kernel, stride);
     CUM_REQUIRE(aligned16(g) && aligned16(w), "convt_out: g/w must be 16-byte aligned");
+    CUM_REQUIRE(!scale || scale_group > 0, "convt_out: scale_group must be positive when scale is given");
     const int halo = (kernel - 1) / stride;
     const long long out_rows = (long long)(rows_in - 1) * stride + kernel;
-    const long long need = length < out_rows ? length : out_rows;
-    CUM_REQUIRE(length <= out_rows, "convt_out: length=%d exceeds the transposed-conv output (%lld)", length, out_rows);
-    dim3 grid((unsigned)cdiv(need, (long long)CT_ROWS * stride), batch);
-    const size_t smem = (size_t)(CT_ROWS + halo) * kernel * sizeof(float);
+    CUM_REQUIRE((long long)first + length <= out_rows, "convt_out: first+length=%lld exceeds the transposed-conv output (%lld)",
+                (long long)first + length, out_rows);
+    dim3 grid((unsigned)cdiv(length, (long long)CT_ROWS * stride), batch);
+    const size_t smem = (size_t)(CT_ROWS + halo + 1) * kernel * sizeof(float);
+    const int groups = scale ? (int)cdiv(length, scale_group) : 0;
     if (c_pad <= 64)
-        convt_out_kernel<16><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, out, out_stride, length, kernel, stride, halo);
+        convt_out_kernel<16><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, groups, scale_group, out, out_stride, first, length, kernel, stride, halo);
     else
-        convt_out_kernel<32><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, out, out_stride, length, kernel, stride, halo);
+        convt_out_kernel<32><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, groups, scale_group, out, out_stride, first, length, kernel, stride, halo);
     CUM_LAUNCH_CHECK("convt_out_kernel");
     return CUM_OK;
 }

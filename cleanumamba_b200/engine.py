@@ -57,6 +57,31 @@ class Engine:
         self._key = None
         self.pk: Dict[str, torch.Tensor] = {}
         self.meta: dict = {}
+        self.launches = 0          # kernels launched through the C ABI (bench.py's gpu_launches)
+        self.prof = None           # list of (kind, start_event, stop_event, flops, bytes) when profiling is on
+
+    def _call(self, kind, fn, *args, launches=1, flops=0, nbytes=0):
+        """One C-ABI call on the current stream; optional CUDA-event bracket for per-kernel roofline numbers."""
+        self.launches += launches
+        if self.prof is None:
+            check(fn(*args), fn.__name__)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args), fn.__name__)
+        e1.record()
+        self.prof.append((kind, e0, e1, flops, nbytes))
+
+    def profile_summary(self):
+        """{kind: dict(ms, launches, flops, bytes)} from the recorded events (call after a synchronize)."""
+        out = {}
+        for kind, e0, e1, fl, nb in self.prof or []:
+            d = out.setdefault(kind, dict(ms=0.0, launches=0, flops=0, bytes=0))
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+            d["flops"] += fl
+            d["bytes"] += nb
+        return out
 
     # ------------------------------------------------------------------------------------------------ packing
     def _params_key(self):
@@ -178,6 +203,15 @@ class Engine:
         self.device = dev
         self.math = _lib.MATH_BY_NAME[getattr(m, "math_mode", "fp32")]
         self.lib = _lib.init(dev)
+        self.pk_hi, self.pk_lo = {}, {}
+        if self.math == _lib.MATH_TF32X3:      # hi/lo copies of the whole packed buffer (only GEMM weights use them)
+            hi, lo = torch.empty_like(flat), torch.empty_like(flat)
+            check(self.lib.cum_split_tf32(flat.data_ptr(), hi.data_ptr(), lo.data_ptr(), flat.numel(),
+                                          _lib.stream_ptr()), "cum_split_tf32")
+            for k, t in items.items():
+                self.pk_hi[k] = hi[offs[k]: offs[k] + t.numel()].view(t.shape)
+                self.pk_lo[k] = lo[offs[k]: offs[k] + t.numel()].view(t.shape)
+            self._flat_split = (hi, lo)
 
     # ------------------------------------------------------------------------------------------------ op wrappers
     def gemm(self, a, a_off, a_bs, a_rs, a_rows, k, w, bias, c, c_off, c_bs, c_rs, m, n, batch, epi,
@@ -186,12 +220,19 @@ class Engine:
         d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k = a.data_ptr() + 4 * a_off, a_bs, a_rs, a_rows, k
         d.taps = taps
         d.tap_shift[0], d.tap_shift[1] = shifts
-        d.w, d.ldw, d.bias = w.data_ptr(), w.shape[-1], ptr(bias)
+        wt = self.pk[w]
+        d.math = self.math if math is None else math
+        if d.math == _lib.MATH_TF32X3:
+            d.w, d.w_lo = self.pk_hi[w].data_ptr(), self.pk_lo[w].data_ptr()
+        else:
+            d.w, d.w_lo = wt.data_ptr(), 0
+        d.ldw, d.bias = wt.shape[-1], ptr(bias)
         d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch = c.data_ptr() + 4 * c_off, c_bs, c_rs, m, n, batch
         d.epilogue = epi
         d.addend, d.add_batch_stride, d.add_row_stride = ptr(addend), add_bs, add_rs
-        d.math = self.math if math is None else math
-        check(self.lib.cum_gemm_bias_act_fwd(C.byref(d), _lib.stream_ptr()), "cum_gemm_bias_act_fwd")
+        kind = "gemm_tap2" if taps == 2 else "gemm"
+        self._call(kind, self.lib.cum_gemm_bias_act_fwd, C.byref(d), _lib.stream_ptr(),
+                   flops=2 * batch * m * n * k * taps)
 
     def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None):
         """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers."""
@@ -202,8 +243,9 @@ class Engine:
         return c
 
     def ln(self, h, res_in, res_out, normed, g, be, eps, rows, c, c_p):
-        check(self.lib.cum_ln_residual_fwd(ptr(h), ptr(res_in), ptr(res_out), ptr(normed), ptr(g), ptr(be), eps, rows,
-                                           c, c_p, _lib.stream_ptr()), "cum_ln_residual_fwd")
+        self._call("ln_residual", self.lib.cum_ln_residual_fwd, ptr(h), ptr(res_in), ptr(res_out), ptr(normed), ptr(g),
+                   ptr(be), eps, rows, c, c_p, _lib.stream_ptr(),
+                   nbytes=4 * rows * c * (2 + (res_in is not None) + (res_out is not None)))
 
     def scan(self, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None):
         di_p, N_p, R_p = mm["di_p"], mm["N_p"], mm["R_p"]
@@ -218,7 +260,9 @@ class Engine:
         s.a2, s.Dskip, s.delta_bias = self.pk[f"m{l}.a2"].data_ptr(), self.pk[f"m{l}.D"].data_ptr(), self.pk[f"m{l}.dtb"].data_ptr()
         s.h0, s.h_out = ptr(h0), ptr(h_out)
         s.batch, s.len, s.d, s.n_state, s.delta_softplus = B, T, di_p, N_p, 1
-        check(self.lib.cum_selective_scan_fwd(C.byref(s), _lib.stream_ptr()), "cum_selective_scan_fwd")
+        # algorithmic bytes: read u, delta, z + B, C, write y -- real (unpadded) widths
+        self._call("selective_scan", self.lib.cum_selective_scan_fwd, C.byref(s), _lib.stream_ptr(),
+                   nbytes=4 * B * T * (4 * mm["di"] + 2 * mm["N"]), flops=B * T * mm["di"] * mm["N"])
 
     def mamba_layers(self, h, B, T, states=None):
         """h: (B*T, dm_p) output of tsfm_conv1 -> normed (B*T, dm_p) after norm_f.  ``states``: optional list of
@@ -234,18 +278,18 @@ class Engine:
             res_out = res if res is not None else torch.empty(rows, dm_p, dtype=torch.float32, device=dev)
             self.ln(h, res, res_out, hn, pk[f"m{l}.g"], pk[f"m{l}.be"], mm["eps"], rows, dm, dm_p)
             res = res_out
-            xz = self.dense(hn, rows, dm_p, pk[f"m{l}.in"], None, 2 * di_p)
+            xz = self.dense(hn, rows, dm_p, f"m{l}.in", None, 2 * di_p)
             xc = torch.empty(rows, di_p, dtype=torch.float32, device=dev)
             cs = states[l][0] if states is not None else None
-            check(self.lib.cum_dwconv_silu_fwd(xz.data_ptr(), T * 2 * di_p, 2 * di_p, pk[f"m{l}.cw"].data_ptr(),
-                                               pk[f"m{l}.cb"].data_ptr(), xc.data_ptr(), ptr(cs), ptr(cs), B, T, di_p,
-                                               mm["W"], _lib.stream_ptr()), "cum_dwconv_silu_fwd")
-            xdbl = self.dense(xc, rows, di_p, pk[f"m{l}.xp"], None, R_p + 2 * N_p)
-            dt = self.dense(xdbl, rows, R_p, pk[f"m{l}.dtw"], None, di_p, a_rs=R_p + 2 * N_p)
+            self._call("dwconv_silu", self.lib.cum_dwconv_silu_fwd, xz.data_ptr(), T * 2 * di_p, 2 * di_p,
+                       pk[f"m{l}.cw"].data_ptr(), pk[f"m{l}.cb"].data_ptr(), xc.data_ptr(), ptr(cs), ptr(cs), B, T, di_p,
+                       mm["W"], _lib.stream_ptr(), launches=1 + (cs is not None), nbytes=8 * rows * mm["di"])
+            xdbl = self.dense(xc, rows, di_p, f"m{l}.xp", None, R_p + 2 * N_p)
+            dt = self.dense(xdbl, rows, R_p, f"m{l}.dtw", None, di_p, a_rs=R_p + 2 * N_p)
             y = torch.empty(rows, di_p, dtype=torch.float32, device=dev)
             hs = states[l][1] if states is not None else None
             self.scan(xc, dt, xz, xdbl, y, l, mm, B, T, h0=hs, h_out=hs)
-            h = self.dense(y, rows, di_p, pk[f"m{l}.out"], None, dm_p)
+            h = self.dense(y, rows, di_p, f"m{l}.out", None, dm_p)
         self.ln(h, res, None, hn, pk["nf.g"], pk["nf.be"], meta["eps"], rows, dm, dm_p)
         return hn
 
@@ -268,7 +312,8 @@ class Engine:
         std = None
         if m.normalize_input:
             std = torch.empty(B, dtype=torch.float32, device=x.device)
-            check(lib.cum_wave_normalize_fwd(x.data_ptr(), std.data_ptr(), B, L, st()), "cum_wave_normalize_fwd")
+            self._call("wave_normalize", lib.cum_wave_normalize_fwd, x.data_ptr(), std.data_ptr(), B, L, st(),
+                       nbytes=8 * B * L)
             if x is not noisy:
                 noisy.copy_(x)      # the reference divides the caller's tensor in place (:262)
         Ls = [m.valid_length(L)]
@@ -281,42 +326,43 @@ class Engine:
             rows = B * Ls[i + 1]
             y = torch.empty(rows, e["Hc_p"], dtype=torch.float32, device=x.device)
             if i == 0:
-                check(lib.cum_conv_in_fwd(x.data_ptr(), L, B, L, pk["enc0.w"].data_ptr(), pk["enc0.b"].data_ptr(),
-                                          y.data_ptr(), Ls[1], e["Hc_p"], 4, 2, st()), "cum_conv_in_fwd")
+                self._call("conv_in", lib.cum_conv_in_fwd, x.data_ptr(), L, B, L, pk["enc0.w"].data_ptr(),
+                           pk["enc0.b"].data_ptr(), y.data_ptr(), Ls[1], e["Hc_p"], 4, 2, 0, 0, st(),
+                           nbytes=4 * B * (L + Ls[1] * e["Hc"]))
             else:
                 cp = e["Cin_p"]
-                self.gemm(prev, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2, 2 * cp, pk[f"enc{i}.w"], pk[f"enc{i}.b"],
+                self.gemm(prev, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
                           y, 0, Ls[i + 1] * e["Hc_p"], e["Hc_p"], Ls[i + 1], e["Hc_p"], B, EPI_RELU, taps=2,
                           shifts=(0, 1))
-            prev = self.dense(y, rows, e["Hc_p"], pk[f"enc{i}.wg"], pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act)
+            prev = self.dense(y, rows, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act)
             skips.append(prev)
 
         T = Ls[D]
         rows = B * T
         cb_p = meta["enc"][-1]["Ho_p"]
-        h = self.dense(prev, rows, cb_p, pk["t1.w"], pk["t1.b"], meta["dm_p"])
+        h = self.dense(prev, rows, cb_p, "t1.w", pk["t1.b"], meta["dm_p"])
         hn = self.mamba_layers(h, B, T)
-        xcur = self.dense(hn, rows, meta["dm_p"], pk["t2.w"], pk["t2.b"], cb_p, addend=skips[D - 1])
+        xcur = self.dense(hn, rows, meta["dm_p"], "t2.w", pk["t2.b"], cb_p, addend=skips[D - 1])
 
         Tj = T
         out = None
         for j, d in enumerate(meta["dec"]):
-            g = self.dense(xcur, B * Tj, d["Cin_p"], pk[f"dec{j}.wg"], pk[f"dec{j}.bg"], 2 * d["Hg_p"], epi=act)
+            g = self.dense(xcur, B * Tj, d["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * d["Hg_p"], epi=act)
             if j < D - 1:
                 co = d["Co_p"]
                 To = 2 * Tj + 2
                 nxt = torch.empty(B * To, co, dtype=torch.float32, device=x.device)
                 skip = skips[D - 2 - j]
-                self.gemm(g, 0, Tj * d["Hg_p"], d["Hg_p"], Tj, d["Hg_p"], pk[f"dec{j}.w"], pk[f"dec{j}.b"],
+                self.gemm(g, 0, Tj * d["Hg_p"], d["Hg_p"], Tj, d["Hg_p"], f"dec{j}.w", pk[f"dec{j}.b"],
                           nxt, 0, To * co, 2 * co, Tj + 1, 2 * co, B, EPI_RELU, taps=2, shifts=(0, -1),
                           addend=skip, add_bs=To * co, add_rs=2 * co)
                 xcur, Tj = nxt, To
             else:
                 length = L if m.normalize_input else Ls[0]
                 out = torch.empty(B, 1, length, dtype=torch.float32, device=x.device)
-                check(lib.cum_convt_out_fwd(g.data_ptr(), B, Tj, d["Hg_p"], pk[f"dec{j}.w"].data_ptr(),
-                                            meta["out_bias"], ptr(std), out.data_ptr(), length, length, 4, 2, st()),
-                      "cum_convt_out_fwd")
+                self._call("convt_out", lib.cum_convt_out_fwd, g.data_ptr(), B, Tj, d["Hg_p"], pk[f"dec{j}.w"].data_ptr(),
+                           meta["out_bias"], ptr(std), length, out.data_ptr(), length, 0, length, 4, 2, st(),
+                           nbytes=4 * B * (Tj * d["Hg"] + length))
         if not return_skip_connections:
             return out
         ncl = []

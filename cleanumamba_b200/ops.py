@@ -142,9 +142,15 @@ def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None
     d = _lib.GemmDesc()
     d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k, d.taps = a.data_ptr(), rows * k, k, rows, k, taps
     d.tap_shift[0], d.tap_shift[1] = shifts
-    d.w, d.ldw, d.bias = w.data_ptr(), k, ptr(bias)
+    d.math = _lib.MATH_BY_NAME[math]
+    if d.math == _lib.MATH_TF32X3:
+        w_hi, w_lo = torch.empty_like(w), torch.empty_like(w)
+        check(lib.cum_split_tf32(w.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), w.numel(), _lib.stream_ptr()), "cum_split_tf32")
+        d.w, d.w_lo = w_hi.data_ptr(), w_lo.data_ptr()
+    else:
+        d.w, d.w_lo = w.data_ptr(), 0
+    d.ldw, d.bias = k, ptr(bias)
     d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch, d.epilogue = out.data_ptr(), m * n_out, n_out, m, n, batch, epilogue
     d.addend, d.add_batch_stride, d.add_row_stride = ptr(addend), m * n_out, n_out
-    d.math = _lib.MATH_BY_NAME[math]
     check(lib.cum_gemm_bias_act_fwd(C.byref(d), _lib.stream_ptr()), "cum_gemm_bias_act_fwd")
     return out

@@ -61,17 +61,23 @@ int cum_wave_normalize_fwd(float* x, float* std_out, int batch, int length, cum_
 
 /* Replaces F.pad (CleanUMamba.py:219-223) + encoder[0][0] Conv1d(1,H,K,S) + ReLU (:109-110).
  * x: (batch, length) [row stride x_stride]; samples t >= length read as 0.  w: (K, c_pad) taps-major;
- * bias: (c_pad).  y: (batch, rows_out, c_pad) channels-last, y[b,t,c] = relu(b[c] + sum_k w[k,c] x[b,S t+k]). */
+ * bias: (c_pad).  y: (batch, rows_out, c_pad) channels-last,
+ *   y[b,t,c] = relu(b[c] + sum_k w[k,c] * x[b,S t+k] / in_scale[b, t / group_rows]).
+ * in_scale (batch, ceil(rows_out / group_rows)) may be NULL (no scaling); it carries the per-hop running std of the
+ * streaming path (`frame / self.input_std`, CleanUMamba.py:399-401). */
 int cum_conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w,
                     const float* bias, float* y, int rows_out, int c_pad, int kernel, int stride,
-                    cum_stream_t stream);
+                    const float* in_scale, int group_rows, cum_stream_t stream);
 
-/* Replaces decoder[-1][2] ConvTranspose1d(H,1,K,S) (CleanUMamba.py:124) + the crop and `* std` (:318-319).
- * g: (batch, rows_in, c_pad) channels-last; w: (K, c_pad); out: (batch, length) [row stride out_stride];
- * out[b,m] = scale[b] * (bias + sum_{j,k: S j + k = m} <g[b,j,:], w[k,:]>), m < length.  scale may be NULL. */
+/* Replaces decoder[-1][2] ConvTranspose1d(H,1,K,S) (CleanUMamba.py:124) + the crop and `* std` (:318-319; per hop
+ * `out *= self.input_std` :406-407 when streaming).  g: (batch, rows_in, c_pad) channels-last; w: (K, c_pad);
+ * out: (batch, length) [row stride out_stride].  With full[m] = bias + sum_{j,k: S j + k = m} <g[b,j,:], w[k,:]>:
+ *   out[b,i] = scale[b, i / scale_group] * full[first + i],  i < length.
+ * scale (batch, ceil(length / scale_group)) may be NULL.  `first` > 0 skips the outputs already emitted when g
+ * carries one column of history (streaming overlap-add, :476-484). */
 int cum_convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
-                      const float* scale, float* out, long long out_stride, int length, int kernel,
-                      int stride, cum_stream_t stream);
+                      const float* scale, int scale_group, float* out, long long out_stride, int first,
+                      int length, int kernel, int stride, cum_stream_t stream);
 
 /* ---- the tap-GEMM: every dense contraction of the path -------------------------------------- */
 /* out[b, m, :] = EPI( bias + sum_{s<taps} W_s . a[b, m + tap_shift[s], 0:k] ) (+ addend[b, m, :])
@@ -97,8 +103,14 @@ typedef struct cum_gemm_desc {
     int epilogue;    /* CUM_EPI_* */
     const float* addend; long long add_batch_stride; long long add_row_stride;  /* optional */
     int math;        /* CUM_MATH_* */
+    const float* w_lo;       /* CUM_MATH_TF32X3 only: low halves of the weights; `w` must then hold the high halves
+                                (both produced by cum_split_tf32 from the packed fp32 weights) */
 } cum_gemm_desc;
 int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream);
+
+/* TF32 hi/lo split of a packed weight array for CUM_MATH_TF32X3: hi = w with the 13 low mantissa bits cleared,
+ * lo = w - hi (exact in fp32).  Same bit arithmetic as the in-kernel split of the activations. */
+int cum_split_tf32(const float* w, float* hi, float* lo, long long count, cum_stream_t stream);
 
 /* ---- Mamba block operators ------------------------------------------------------------------- */
 /* Replaces Block.forward's `residual = h + residual; h = LayerNorm(residual)` (mamba_ssm Block, non-fused

@@ -1,0 +1,101 @@
+"""CPU suite (no GPU): host logic of the drop-in module and the C-ABI surface."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from cleanumamba_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "cleanumamba_b200.h")).read()
+    declared = set(re.findall(r"\b(cum_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/cleanumamba_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS), "ctypes table and header disagree"
+    assert lib.cum_abi_version() == int(re.search(r"#define CUM_ABI_VERSION (\d+)", header).group(1))
+
+
+def test_struct_layouts_match_header_field_order():
+    from cleanumamba_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "cleanumamba_b200.h")).read()
+    for struct, cls in (("cum_gemm_desc", _lib.GemmDesc), ("cum_scan_desc", _lib.ScanDesc)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*\]", "", part.strip().split()[-1].lstrip("*")))
+        assert names == [f[0] for f in cls._fields_], struct
+
+
+def test_no_cpu_fallback():
+    from cleanumamba_b200.network import Net
+    fx = load_golden("tiny_equalwidth_seed0")
+    net = Net("CleanUMamba", json.loads(fx["config"])).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(fx["noisy"].clone())
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cleanumamba_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "cleanumamba_oracle" not in src and "ref_loader" not in src and "ref_shim" not in src, f
+
+
+def test_full_size_constructor_matches_reference_init_sums():
+    """Seed-0 constructor == the reference constructor (per-tensor sums recorded by oracle/make_golden.py)."""
+    from cleanumamba_b200.network import Net
+    sums = json.load(open(os.path.join(GOLDEN, "full_init_seed0_sums.json")))
+    for tag, ref in sums.items():
+        torch.manual_seed(0)
+        net = Net("CleanUMamba", ref["config"])
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(ref["tensors"].keys())
+        assert sum(p.numel() for p in net.parameters()) == ref["n_params"]
+        for k, (shape, s, a) in ref["tensors"].items():
+            assert list(sd[k].shape) == shape, k
+            assert abs(float(sd[k].double().sum()) - s) <= 1e-6 * max(1.0, abs(a)), k
+
+
+@pytest.mark.parametrize("name", ["e8_pruned_500k", "e6_pruned_200k", "mini_mamba_442k"])
+def test_shipped_checkpoints_load_unchanged(name):
+    from cleanumamba_b200.network import Net
+    fx = load_golden(name)
+    net = Net("CleanUMamba", json.loads(fx["config"]))
+    net.load_pruned_state_dict(fx["state_dict"])
+    sd = net.state_dict()
+    assert set(sd.keys()) == set(fx["state_dict"].keys())   # (the mini experiment checkpoint lists norm before mixer)
+    for k, v in fx["state_dict"].items():
+        assert sd[k].shape == v.shape and torch.equal(sd[k].to(v.dtype), v)
+    mx = net.tsfm_Mamba_layers[0].mixer
+    assert mx.d_inner == mx.A_log.shape[0] and mx.d_state == mx.A_log.shape[1]
+    assert net.encoder[1][0].in_channels == fx["state_dict"]["encoder.1.0.weight"].shape[1]
+    assert net.decoder[0][2].out_channels == fx["state_dict"]["decoder.0.2.weight"].shape[1]
+
+
+def test_shape_helpers_and_api_surface():
+    from cleanumamba_b200 import CleanUMamba
+    m = CleanUMamba(channels_H=8, max_H=16, encoder_n_layers=8, tsfm_n_layers=1, tsfm_d_model=16, tsfm_d_inner=32, tsfm_n_head=2)
+    assert m.valid_length(160000) == 160254 and m.frame_length == 766 and m.total_stride == 256
+    assert m.pad_signal(torch.zeros(1, 1, 160000)).shape[-1] == 160254
+    cache = m.allocate_inference_cache(2, 1)
+    assert cache[0][0].shape == (2, 32, 4) and cache[0][1].shape == (2, 32, 8)
+    for name in ("forward", "feed", "flush", "load_pruned_state_dict", "allocate_inference_cache_layer"):
+        assert callable(getattr(m, name))
+    with pytest.raises(NotImplementedError):
+        CleanUMamba(LSTM=True)
+    with pytest.raises(ValueError):
+        m.feed(torch.zeros(2, 3, 4))

@@ -24,10 +24,11 @@ def build(fx, **kw):
     return net.cuda().float().eval()
 
 
+@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("name", ["e8_pruned_500k", "e6_pruned_200k", "mini_mamba_442k", "tiny_equalwidth_seed0"])
-def test_forward_matches_reference_golden(name):
+def test_forward_matches_reference_golden(name, math):
     fx = load_golden(name)
-    net = build(fx)
+    net = build(fx, math_mode=math)
     x = fx["noisy"].cuda()
     with torch.no_grad():
         y = net(x)
@@ -69,13 +70,14 @@ def test_normalize_input_false_returns_padded_length():
     assert torch.equal(x.cpu(), fx["noisy"])
 
 
+@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("cfg_name,seconds", [("DNS-CleanUMamba-3N-E8", 1.0), ("DNS-CleanUMamba-3N-E6", 0.5)])
-def test_full_size_random_init_matches_oracle(cfg_name, seconds):
+def test_full_size_random_init_matches_oracle(cfg_name, seconds, math):
     """E8-full / E6-high (random init, seed 0 == reference constructor; checkpoints are not shipped)."""
     from cleanumamba_b200.network import Net
     sums = json.load(open(__import__("os").path.join(__import__("conftest").GOLDEN, "full_init_seed0_sums.json")))[cfg_name]
     torch.manual_seed(0)
-    net = Net("CleanUMamba", sums["config"])
+    net = Net("CleanUMamba", dict(sums["config"], math_mode=math))
     sd = {k: v.clone() for k, v in net.state_dict().items()}
     net = net.cuda().eval()
     clean, noisy = orc.synth_batch(2, seconds)
@@ -84,6 +86,7 @@ def test_full_size_random_init_matches_oracle(cfg_name, seconds):
         y = net(noisy.cuda())
     err = (y.cpu() - ref).abs().max().item()
     rms = ref.pow(2).mean().sqrt().item()
+    print(f"\n[{cfg_name} {math}] max-abs {err:.3e}  out-rms {rms:.3e}")
     assert err <= TOL_MAXABS, f"max-abs {err} (rms {rms})"
     d = (orc.si_sdr(y.cpu(), clean) - orc.si_sdr(ref, clean)).abs().max().item()
     assert d <= TOL_SISDR_DB
