@@ -2,17 +2,17 @@
 //
 //   out[b, m, :] = EPI( bias + sum_{s<taps} W_s . a[b, m + shift_s, 0:k] ) (+ addend[b, m, :])
 //
-// One persistent CTA per SM, 128 x 256 output tile (UMMA M=128, N<=256 runtime, K=8 for kind::tf32), accumulators in
+// One persistent CTA per SM, 128 x 256 (or 128 x 128) output tile (UMMA M=128, N runtime, K=8 for kind::tf32), accumulators in
 // TMEM (2 x 256 columns, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1), operands
 // staged by TMA into 128B-swizzled K-major shared-memory tiles.  The conv taps are extra K-blocks whose A-tile is the
 // same tensor map fetched at a shifted row coordinate; rows outside [0, a_rows) are zero-filled by TMA, which is
 // exactly the conv / transposed-conv boundary condition.
 //
-// Warp roles (384 threads):
+// Warp roles (384 threads, 512 with the splitter):
 //   warp 0        TMA producer (one lane)
 //   warp 1        TMEM allocator + MMA issuer (one lane)
-//   warps 4..7    epilogue: tcgen05.ld -> bias / ReLU / GLU / skip-add -> global
-//   warps 8..11   (TF32X3 only) operand splitter: A tile -> hi = a & 0xffffe000 (in place), lo = a - hi
+//   warps 4..11   epilogue: tcgen05.ld (16x256b fragments) -> bias / ReLU / GLU / skip-add -> 32-byte-sector stores
+//   warps 12..15  (TF32X3 only) operand splitter: A tile -> hi = a & 0xffffe000 (in place), lo = a - hi
 //
 // TF32X3: fp32 activations cannot be fed to kind::tf32 directly within the 1e-4 waveform tolerance (10-bit mantissa,
 // 22 stacked layers), so every product is expanded a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (three MMAs, error
@@ -26,19 +26,22 @@
 namespace cum {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BN = 256;
 constexpr int TC_BK = 32;                     // fp32 elements per K-block = one 128-byte swizzle row
 constexpr int TC_UMMA_K = 8;                  // kind::tf32
-constexpr int TC_THREADS = 384;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
-constexpr uint32_t TC_W_BYTES = TC_BN * TC_BK * 4;   // 32 KB
 constexpr uint32_t TC_TMEM_COLS = 512;
+constexpr int TC_EPI_WARPS = 8;               // warps 4..11: two per TMEM lane quarter (even / odd 64-column chunks)
+constexpr int TC_EPI_GENERIC_UNARY = -1;      // runtime-selected activation (SiLU ...)
+constexpr int TC_EPI_GENERIC_GLU = -2;        // runtime-selected GLU gate (ReLU / SiLU / GELU)
 
-template <bool X3> struct TcCfg {
-    static constexpr int STAGES = X3 ? 2 : 4;
-    static constexpr uint32_t STAGE_BYTES = X3 ? 2 * (TC_A_BYTES + TC_W_BYTES) : (TC_A_BYTES + TC_W_BYTES);
-    static constexpr uint32_t TX_BYTES = X3 ? (TC_A_BYTES + 2 * TC_W_BYTES) : (TC_A_BYTES + TC_W_BYTES);
+// BN = tile width (256, or 128 for narrow layers: smaller W box -> deeper pipeline for the HBM-bound layers)
+template <bool X3, int BN> struct TcCfg {
+    static constexpr uint32_t W_BYTES = BN * TC_BK * 4;
+    static constexpr uint32_t STAGE_BYTES = X3 ? 2 * (TC_A_BYTES + W_BYTES) : (TC_A_BYTES + W_BYTES);
+    static constexpr int STAGES = (int)(196608u / STAGE_BYTES);           // 2 / 3 (X3), 4 / 6 (plain)
+    static constexpr uint32_t TX_BYTES = X3 ? (TC_A_BYTES + 2 * W_BYTES) : (TC_A_BYTES + W_BYTES);
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int THREADS = X3 ? 512 : 384;                        // warps 12..15 = operand splitter (X3)
 };
 
 struct TcParams {
@@ -124,13 +127,54 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 lanes x 64 columns: thread t gets rows (t/4, t/4+8) x columns 8k + 2(t%4) + {0,1}:
+//   r[4k+0], r[4k+1] -> row t/4 ; r[4k+2], r[4k+3] -> row t/4 + 8     (CuTe SM100_TMEM_LOAD_16dp256b8x layout)
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// epilogue math.  The tensor-core path uses the fast intrinsics (ex2.approx / rcp.approx, ~2 ulp): the gate error is
+// far below the TF32X3 product error; the exact-fp32 SIMT kernel keeps expf / IEEE division.
+__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+template <int EPI>
+__device__ __forceinline__ float tc_gate(int epi, float g) {
+    if (EPI == CUM_EPI_GLU_SIGMOID) return fast_sigmoid(g);
+    switch (epi) {
+        case CUM_EPI_GLU_RELU: return fmaxf(g, 0.0f);
+        case CUM_EPI_GLU_SILU: return g * fast_sigmoid(g);
+        case CUM_EPI_GLU_GELU: return geluf_(g);
+        default:               return fast_sigmoid(g);
+    }
+}
+template <int EPI>
+__device__ __forceinline__ float tc_act(int epi, float v) {
+    if (EPI == CUM_EPI_NONE) return v;
+    if (EPI == CUM_EPI_RELU) return fmaxf(v, 0.0f);
+    switch (epi) {
+        case CUM_EPI_RELU: return fmaxf(v, 0.0f);
+        case CUM_EPI_SILU: return v * fast_sigmoid(v);
+        default:           return v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
-template <bool X3>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool X3, int BN, int EPI>
+__global__ void __launch_bounds__(TcCfg<X3, BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                const __grid_constant__ CUtensorMap tmWl, const TcParams p) {
-    using Cfg = TcCfg<X3>;
+    using Cfg = TcCfg<X3, BN>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr bool GLU = (EPI == CUM_EPI_GLU_SIGMOID || EPI == TC_EPI_GENERIC_GLU);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -138,7 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto a_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES; };
     auto alo_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + TC_A_BYTES; };
     auto w_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + (X3 ? 2 : 1) * TC_A_BYTES; };
-    auto wlo_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + 2 * TC_A_BYTES + TC_W_BYTES; };
+    auto wlo_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + 2 * TC_A_BYTES + Cfg::W_BYTES; };
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -162,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 128);
+            mbar_init(tempty_bar(a), TC_EPI_WARPS * 32);
         }
         fence_barrier_init();
     }
@@ -181,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int mb = r % p.m_tiles;
         b = r / p.m_tiles;
         m0 = mb * TC_BM;
-        n0 = nb * TC_BN;
+        n0 = nb * BN;
     };
 
     if (warp == 0 && lane == 0) {
@@ -213,11 +257,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int acc = tcount & 1;
             const uint32_t acc_ph = (tcount >> 1) & 1;
             int n_rem = p.n - n0;
-            if (n_rem > TC_BN) n_rem = TC_BN;
+            if (n_rem > BN) n_rem = BN;
             const uint32_t umma_n = (uint32_t)((n_rem + 15) & ~15);
             // c=f32 (1<<4), a=b=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_BN;
+            const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
             mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
             tc_fence_after();
             for (int it = 0; it < k_iters; ++it) {
@@ -241,10 +285,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================================================================== epilogue
-        const int q = warp & 3;
-        const bool glu = p.epi >= CUM_EPI_GLU_SIGMOID;
+    } else if (warp >= 4 && warp < 4 + TC_EPI_WARPS) {
+        // ===================================================================== epilogue (8 warps)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int chalf = (warp - 4) >> 2;      // even / odd 64-column chunks
+        const int tq = lane & 3, tr = lane >> 2;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             int b, m0, n0;
@@ -253,50 +298,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t acc_ph = (tcount >> 1) & 1;
             mbar_wait(tfull_bar(acc), acc_ph);
             tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < p.m;
-            float* crow = p.c + (long long)b * p.c_bs + (long long)row * p.c_rs;
-            const float* arow = p.addend ? p.addend + (long long)b * p.add_bs + (long long)row * p.add_rs : nullptr;
             int n_rem = p.n - n0;
-            if (n_rem > TC_BN) n_rem = TC_BN;
-            for (int c0 = 0; c0 < n_rem; c0 += 32) {
-                float v[32];
-                __syncwarp();      // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c0), v);
-                if (!row_ok) continue;
+            if (n_rem > BN) n_rem = BN;
+            float* cb = p.c + (long long)b * p.c_bs;
+            const float* ab = p.addend ? p.addend + (long long)b * p.add_bs : nullptr;
+            for (int c0 = chalf * 64; c0 < n_rem; c0 += 128) {
+                // bias for this thread's 8 column pairs
+                float2 bv[8];
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const int n = n0 + c0 + g * 4;
-                    if (n >= p.n) break;
-                    float x0 = v[g * 4 + 0], x1 = v[g * 4 + 1], x2 = v[g * 4 + 2], x3 = v[g * 4 + 3];
-                    if (p.bias) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                        x0 += bv.x; x1 += bv.y; x2 += bv.z; x3 += bv.w;
-                    }
-                    if (glu) {
-                        float2 o = make_float2(x0 * glu_gate(p.epi, x1), x2 * glu_gate(p.epi, x3));
-                        const int oc = n >> 1;
-                        if (arow) {
-                            const float2 ad = __ldg(reinterpret_cast<const float2*>(arow + oc));
-                            o.x += ad.x; o.y += ad.y;
+                for (int k = 0; k < 8; ++k) {
+                    const int n = n0 + c0 + 8 * k + 2 * tq;
+                    bv[k] = (p.bias && n < p.n) ? __ldg(reinterpret_cast<const float2*>(p.bias + n)) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    __syncwarp();       // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+                    tmem_ld_16x256b_x8(tmem_base + ((uint32_t)(q * 32 + h * 16) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh) {
+                        const int row = m0 + q * 32 + h * 16 + rh * 8 + tr;
+                        if (row >= p.m) continue;
+                        float* crow = cb + (long long)row * p.c_rs;
+                        const float* arow = ab ? ab + (long long)row * p.add_rs : nullptr;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int n = n0 + c0 + 8 * k + 2 * tq;
+                            if (n >= p.n) break;
+                            const float x0 = v[4 * k + 2 * rh + 0] + bv[k].x;
+                            const float x1 = v[4 * k + 2 * rh + 1] + bv[k].y;
+                            if (GLU) {
+                                float o = x0 * tc_gate<EPI>(p.epi, x1);
+                                const int oc = n >> 1;
+                                if (arow) o += __ldg(arow + oc);
+                                crow[oc] = o;
+                            } else {
+                                float2 o = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
+                                if (arow) {
+                                    const float2 ad = __ldg(reinterpret_cast<const float2*>(arow + n));
+                                    o.x += ad.x; o.y += ad.y;
+                                }
+                                *reinterpret_cast<float2*>(crow + n) = o;
+                            }
                         }
-                        *reinterpret_cast<float2*>(crow + oc) = o;
-                    } else {
-                        float4 o = make_float4(unary_act(p.epi, x0), unary_act(p.epi, x1), unary_act(p.epi, x2), unary_act(p.epi, x3));
-                        if (arow) {
-                            const float4 ad = __ldg(reinterpret_cast<const float4*>(arow + n));
-                            o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-                        }
-                        *reinterpret_cast<float4*>(crow + n) = o;
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
         }
-    } else if (X3 && warp >= 8) {
+    } else if (X3 && warp >= 12) {
         // ===================================================================== operand splitter (A tile)
-        const int t = threadIdx.x - 256;
+        const int t = threadIdx.x - 384;
         int s = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -383,10 +436,10 @@ static int make_map(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1
     return CUM_OK;
 }
 
-template <bool X3>
+template <bool X3, int BN, int EPI>
 static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
-    using Cfg = TcCfg<X3>;
-    auto kern = gemm_tc_kernel<X3>;
+    using Cfg = TcCfg<X3, BN>;
+    auto kern = gemm_tc_kernel<X3, BN, EPI>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -399,10 +452,10 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
                       TC_BK, TC_BM, "A");
     if (rc) return rc;
     const uint64_t w_ts = (uint64_t)d.n * (uint64_t)d.ldw;
-    rc = make_map(&tmWh, d.w, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, TC_BN, "W");
+    rc = make_map(&tmWh, d.w, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W");
     if (rc) return rc;
     if (X3) {
-        rc = make_map(&tmWl, d.w_lo, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, TC_BN, "W_lo");
+        rc = make_map(&tmWl, d.w_lo, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W_lo");
         if (rc) return rc;
     } else {
         tmWl = tmWh;
@@ -410,24 +463,37 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     TcParams p;
     p.m = d.m; p.n = d.n; p.k = d.k; p.taps = d.taps; p.shift0 = d.tap_shift[0]; p.shift1 = d.tap_shift[1];
     p.batch = d.batch; p.epi = d.epilogue;
-    p.m_tiles = (int)cdiv(d.m, TC_BM); p.n_tiles = (int)cdiv(d.n, TC_BN); p.k_blocks = (int)cdiv(d.k, TC_BK);
+    p.m_tiles = (int)cdiv(d.m, TC_BM); p.n_tiles = (int)cdiv(d.n, BN); p.k_blocks = (int)cdiv(d.k, TC_BK);
     p.bias = d.bias; p.c = d.c; p.c_bs = d.c_batch_stride; p.c_rs = d.c_row_stride;
     p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
     CUM_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmWh, tmWl, p);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmWh, tmWl, p);
     CUM_LAUNCH_CHECK("gemm_tc_kernel");
     return CUM_OK;
 }
 
+template <bool X3, int BN>
+static int dispatch_epi(const cum_gemm_desc& d, cudaStream_t st) {
+    switch (d.epilogue) {
+        case CUM_EPI_NONE:        return launch_tc<X3, BN, CUM_EPI_NONE>(d, st);
+        case CUM_EPI_RELU:        return launch_tc<X3, BN, CUM_EPI_RELU>(d, st);
+        case CUM_EPI_GLU_SIGMOID: return launch_tc<X3, BN, CUM_EPI_GLU_SIGMOID>(d, st);
+        default:
+            return epi_is_glu(d.epilogue) ? launch_tc<X3, BN, TC_EPI_GENERIC_GLU>(d, st)
+                                          : launch_tc<X3, BN, TC_EPI_GENERIC_UNARY>(d, st);
+    }
+}
+
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.a_row_stride >= d.k || d.a_rows == 1, "gemm_tc: a_row_stride < k");
+    const bool narrow = d.n <= 128;
     if (d.math == CUM_MATH_TF32X3) {
         CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: TF32X3 needs w_lo (see cum_split_tf32)");
-        return launch_tc<true>(d, st);
+        return narrow ? dispatch_epi<true, 128>(d, st) : dispatch_epi<true, 256>(d, st);
     }
-    return launch_tc<false>(d, st);
+    return narrow ? dispatch_epi<false, 128>(d, st) : dispatch_epi<false, 256>(d, st);
 }
 
 }  // namespace cum
