@@ -74,9 +74,15 @@ int cum_wave_normalize_fwd(float* x, float* std_out, int batch, int length, cum_
 
 int cum_conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
                     float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
-                    cum_stream_t stream) {
+                    int row_offset, cum_stream_t stream) {
     return conv_in_fwd(x, x_stride, batch, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale, group_rows,
-                       (cudaStream_t)stream);
+                       row_offset, (cudaStream_t)stream);
+}
+
+int cum_stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
+                       int frames_before, float* running, float* scale_out, cum_stream_t stream) {
+    return stream_std_fwd(x, x_stride, batch, frames, frame_len, hop, frames_before, running, scale_out,
+                          (cudaStream_t)stream);
 }
 
 int cum_convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,

@@ -49,6 +49,47 @@ int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStre
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// stream_std: per-frame std of the streaming path.  Reference: CleanUMamba.py:399-401
+//   s_f = std(frame_f, unbiased) + 1e-3 ;  input_std <- s_f / f + (1 - 1/f) * input_std   (running mean over frames)
+// One CTA per stream walks the `frames` frames of this call in order; frame j covers x[b, j*hop : j*hop + frame_len].
+// scale_out[b, j] = the running value after frame j; running[b] is updated in place.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stream_std_kernel(const float* __restrict__ x, long long x_stride, int frames,
+                                                          int frame_len, int hop, int frames_before,
+                                                          float* __restrict__ running, float* __restrict__ scale_out) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    const float* xb = x + (long long)b * x_stride;
+    float run = running[b];
+    for (int j = 0; j < frames; ++j) {
+        const float* fr = xb + (long long)j * hop;
+        double s = 0.0;
+        for (int i = threadIdx.x; i < frame_len; i += blockDim.x) s += (double)fr[i];
+        const double mean = block_sum(s, red) / (double)frame_len;
+        double q = 0.0;
+        for (int i = threadIdx.x; i < frame_len; i += blockDim.x) {
+            const double d = (double)fr[i] - mean;
+            q += d * d;
+        }
+        const double var = block_sum(q, red) / (double)(frame_len > 1 ? frame_len - 1 : 1);
+        const float sf = (float)sqrt(var) + 1e-3f;
+        const float f = (float)(frames_before + j + 1);
+        run = sf / f + (1.0f - 1.0f / f) * run;
+        if (threadIdx.x == 0) scale_out[(long long)b * frames + j] = run;
+    }
+    if (threadIdx.x == 0) running[b] = run;
+}
+
+int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
+                   int frames_before, float* running, float* scale_out, cudaStream_t st) {
+    CUM_REQUIRE(x && running && scale_out, "stream_std: null pointer");
+    CUM_REQUIRE(batch > 0 && frames > 0 && frame_len > 0 && hop > 0 && frames_before >= 0, "stream_std: bad shape");
+    stream_std_kernel<<<batch, 256, 0, st>>>(x, x_stride, frames, frame_len, hop, frames_before, running, scale_out);
+    CUM_LAUNCH_CHECK("stream_std_kernel");
+    return CUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // conv_in: y[b,t,c] = relu(bias[c] + sum_k w[k,c] * x[b, S t + k]),  x read as 0 beyond `length` (F.pad).
 // CTA = 64 output rows; the 64*S+K input samples are staged in smem, every thread then produces float4s of
 // channels for one row so the stores are fully coalesced (the kernel is store-bound: 4*Cp bytes per row).
@@ -60,7 +101,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        float* __restrict__ y, int rows_out, int c_pad, int kernel,
                                                        int stride, const float* __restrict__ in_scale, int scale_groups,
-                                                       int group_rows) {
+                                                       int group_rows, int row_offset) {
     extern __shared__ float xs[];
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * CI_ROWS;
@@ -78,7 +119,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
         const int t = idx / c4n, c4 = idx - t * c4n;
         float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
         // streaming: the samples feeding output row t are divided by the running std of the hop that row belongs to
-        const float sdiv = in_scale ? __ldg(in_scale + (long long)b * scale_groups + (t0 + t) / group_rows) : 1.0f;
+        const float sdiv = in_scale ? __ldg(in_scale + (long long)b * scale_groups + max(0, t0 + t + row_offset) / group_rows) : 1.0f;
 #pragma unroll 4
         for (int k = 0; k < kernel; ++k) {
             const float xv = in_scale ? xs[t * stride + k] / sdiv : xs[t * stride + k];
@@ -93,7 +134,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
 
 int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
                 float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
-                cudaStream_t st) {
+                int row_offset, cudaStream_t st) {
     CUM_REQUIRE(x && w && bias && y, "conv_in: null pointer");
     CUM_REQUIRE(batch > 0 && length > 0 && rows_out > 0, "conv_in: empty problem");
     CUM_REQUIRE(c_pad > 0 && c_pad % 4 == 0, "conv_in: c_pad=%d must be a positive multiple of 4", c_pad);
@@ -102,9 +143,9 @@ int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const
     dim3 grid((unsigned)cdiv(rows_out, CI_ROWS), batch);
     const size_t smem = (size_t)(CI_ROWS * stride + kernel) * sizeof(float);
     CUM_REQUIRE(!in_scale || group_rows > 0, "conv_in: group_rows must be positive when in_scale is given");
-    const int groups = in_scale ? (int)cdiv(rows_out, group_rows) : 0;
+    const int groups = in_scale ? (int)cdiv(max(1, rows_out + row_offset), group_rows) : 0;
     conv_in_kernel<<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale,
-                                            groups, group_rows);
+                                            groups, group_rows, row_offset);
     CUM_LAUNCH_CHECK("conv_in_kernel");
     return CUM_OK;
 }

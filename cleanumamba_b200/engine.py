@@ -327,7 +327,7 @@ class Engine:
             y = torch.empty(rows, e["Hc_p"], dtype=torch.float32, device=x.device)
             if i == 0:
                 self._call("conv_in", lib.cum_conv_in_fwd, x.data_ptr(), L, B, L, pk["enc0.w"].data_ptr(),
-                           pk["enc0.b"].data_ptr(), y.data_ptr(), Ls[1], e["Hc_p"], 4, 2, 0, 0, st(),
+                           pk["enc0.b"].data_ptr(), y.data_ptr(), Ls[1], e["Hc_p"], 4, 2, 0, 0, 0, st(),
                            nbytes=4 * B * (L + Ls[1] * e["Hc"]))
             else:
                 cp = e["Cin_p"]

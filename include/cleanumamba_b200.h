@@ -62,12 +62,20 @@ int cum_wave_normalize_fwd(float* x, float* std_out, int batch, int length, cum_
 /* Replaces F.pad (CleanUMamba.py:219-223) + encoder[0][0] Conv1d(1,H,K,S) + ReLU (:109-110).
  * x: (batch, length) [row stride x_stride]; samples t >= length read as 0.  w: (K, c_pad) taps-major;
  * bias: (c_pad).  y: (batch, rows_out, c_pad) channels-last,
- *   y[b,t,c] = relu(b[c] + sum_k w[k,c] * x[b,S t+k] / in_scale[b, t / group_rows]).
- * in_scale (batch, ceil(rows_out / group_rows)) may be NULL (no scaling); it carries the per-hop running std of the
- * streaming path (`frame / self.input_std`, CleanUMamba.py:399-401). */
+ *   y[b,t,c] = relu(b[c] + sum_k w[k,c] * x[b,S t+k] / in_scale[b, max(0, t + row_offset) / group_rows]).
+ * in_scale (batch, ceil(max(1, rows_out + row_offset) / group_rows)) may be NULL (no scaling); it carries the per-hop
+ * running std of the streaming path (`frame / self.input_std`, CleanUMamba.py:399-401); row_offset < 0 lets the
+ * first (longer) frame of a stream map to group 0. */
 int cum_conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w,
                     const float* bias, float* y, int rows_out, int c_pad, int kernel, int stride,
-                    const float* in_scale, int group_rows, cum_stream_t stream);
+                    const float* in_scale, int group_rows, int row_offset, cum_stream_t stream);
+
+/* Replaces the per-frame running std of feed() (CleanUMamba.py:399-401): for frame j of this call,
+ *   s = std(x[b, j*hop : j*hop+frame_len], unbiased) + 1e-3;  f = frames_before + j + 1;
+ *   running[b] = s / f + (1 - 1/f) * running[b];  scale_out[b, j] = running[b].
+ * x: (batch, >= (frames-1)*hop + frame_len) raw pending samples [row stride x_stride]. */
+int cum_stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
+                       int frames_before, float* running, float* scale_out, cum_stream_t stream);
 
 /* Replaces decoder[-1][2] ConvTranspose1d(H,1,K,S) (CleanUMamba.py:124) + the crop and `* std` (:318-319; per hop
  * `out *= self.input_std` :406-407 when streaming).  g: (batch, rows_in, c_pad) channels-last; w: (K, c_pad);

@@ -172,7 +172,7 @@ def test_wave_ends():
     ref = F.relu(F.conv1d(F.pad(x, (0, Lp - L))[:, None], w, bias, stride=2))
     y = torch.empty(B, rows, H, device=dev())
     xd, wd, bd = x.to(dev()), w[:, 0].t().contiguous().to(dev()), bias.to(dev())   # keep alive: raw pointers cross the ABI
-    _lib.check(lib.cum_conv_in_fwd(xd.data_ptr(), L, B, L, wd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, H, 4, 2, 0, 0,
+    _lib.check(lib.cum_conv_in_fwd(xd.data_ptr(), L, B, L, wd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, H, 4, 2, 0, 0, 0,
                                    _lib.stream_ptr()), "conv_in")
     assert rel_err(y.permute(0, 2, 1), ref) < 1e-6
     # convt_out
