@@ -1,0 +1,181 @@
+"""Carried-state streaming inference for a batch of independent streams.
+
+Reference behaviour being reproduced: ``feed / _denoise_frame / flush`` of /root/reference/src/network/CleanUMamba.py:358-490
+(one stream, one 2^D-sample hop per Python iteration, ~60 tiny kernels per hop).  Here ``batch`` streams advance in
+lock-step and every ``feed`` processes ALL complete frames of the call in one pass through the same kernels as the
+offline forward, with the state that makes chunked == offline carried between calls:
+
+  * raw ``pending`` samples (the reference's ``self.pending``)                                  (:392,410)
+  * per encoder level, the output columns the decoder has not consumed yet -- they double as the K-S = 2 input columns
+    the next strided conv still needs (the reference's ``enc{i}`` caches, :432-442)
+  * per decoder level, ONE column of the GLU output: ``convT(g)[2p+par] = Wa g[p] + Wb g[p-1]``, so carrying g[p-1]
+    replaces the reference's overlap-add tail ``x[..., -stride:] - bias`` (:476-484) exactly
+  * per Mamba layer, conv_state (B, 3, d_inner) and ssm_state (B, d_inner, d_state) updated in place by the
+    depthwise-conv / scan kernels (``Mamba.step``), any number of tokens per call
+  * the running mean of the per-frame input std and the frame counter (:399-401)
+
+Identity (normalize_input=False): the samples emitted equal offline ``forward`` on the fed signal.  With
+``normalize_input=True`` the reference's per-frame running-std rule is applied hop by hop (conv_in divides each new
+encoder column by the std of the frame that produced it; the output hop is multiplied by the same value).
+The reference's skip-index bug (:474) is NOT reproduced (it crashes on every shipped checkpoint).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import EPI_GLU, EPI_NONE, EPI_RELU, ptr
+
+
+class StreamSession:
+    def __init__(self, model, batch: int = 1):
+        self.model = model
+        self.eng = model.engine()
+        self.eng.ensure_packed()
+        self.B = batch
+        self.dev = self.eng.device
+        m, meta = model, self.eng.meta
+        self.D = meta["D"]
+        self.hop = m.total_stride
+        self.frame_length = m.frame_length
+        self.frames = 0                      # frames processed since construction (running-std denominator)
+        self.running_std = torch.zeros(batch, dtype=torch.float32, device=self.dev)
+        self.pending = torch.zeros(batch, 0, dtype=torch.float32, device=self.dev)
+        self.states = [(torch.zeros(batch, mm["W"] - 1, mm["di_p"], dtype=torch.float32, device=self.dev),
+                        torch.zeros(batch, mm["di_p"], mm["N_p"], dtype=torch.float32, device=self.dev))
+                       for mm in meta["mamba"]]
+        self._reset_conv_state()
+
+    # ------------------------------------------------------------------------------------------------------
+    def _reset_conv_state(self):
+        """Fresh encoder/decoder caches (what ``flush`` clears, :364); Mamba state and running std are kept."""
+        D, meta = self.D, self.eng.meta
+        self.enc_buf = [None] * D            # (B, cap, C_p): encoder level i outputs from absolute column enc_base[i]
+        self.enc_base = [0] * D              # columns already consumed by the decoder
+        self.enc_count = [0] * D             # columns produced so far
+        self.consumed_in = [0] * (D + 1)     # input columns (level i) fully consumed by conv i: 2 * enc_count[i]
+        self.samples_base = 0                # absolute index (since reset) of pending[:, 0]
+        self.frames_since_reset = 0
+        self.dec_carry = [torch.zeros(self.B, d["Hg_p"], dtype=torch.float32, device=self.dev) for d in meta["dec"]]
+
+    def pending_view(self):
+        return self.pending
+
+    # ------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def feed(self, chunk: torch.Tensor) -> torch.Tensor:
+        """chunk: (batch, n) -> (batch, hop * F), F = number of complete frames now available."""
+        if chunk.dim() != 2 or chunk.shape[0] != self.B:
+            raise ValueError(f"expected a (batch={self.B}, n) tensor, got {tuple(chunk.shape)}")
+        if chunk.device != self.dev:
+            raise RuntimeError(f"chunk is on {chunk.device}, model on {self.dev} (no CPU fallback)")
+        self.pending = torch.cat([self.pending, chunk.to(torch.float32)], dim=1)
+        n = self.pending.shape[1]
+        if n < self.frame_length:
+            return torch.zeros(self.B, 0, dtype=torch.float32, device=self.dev)
+        F = (n - self.frame_length) // self.hop + 1
+        out = self._process(F)
+        self.pending = self.pending[:, F * self.hop:]
+        self.samples_base += F * self.hop
+        return out
+
+    @torch.no_grad()
+    def flush(self) -> torch.Tensor:
+        """:358-368 -- clear the conv caches, feed frame_length zeros, return the first len(pending) samples."""
+        self._reset_conv_state()
+        n = self.pending.shape[1]
+        out = self.feed(torch.zeros(self.B, self.frame_length, dtype=torch.float32, device=self.dev))
+        return out[:, :n]
+
+    # ------------------------------------------------------------------------------------------------------
+    def _process(self, F: int) -> torch.Tensor:
+        eng, m, B, D, dev = self.eng, self.model, self.B, self.D, self.dev
+        pk, meta, lib = eng.pk, eng.meta, eng.lib
+        act = EPI_GLU[m.glu_activation]
+        st = _lib.stream_ptr
+        X = self.pending.contiguous()
+        self.pending = X
+        n_use = self.frame_length + (F - 1) * self.hop          # samples of X that belong to complete frames
+        first = self.frames_since_reset == 0
+
+        scale = None
+        if m.normalize_input:
+            scale = torch.empty(B, F, dtype=torch.float32, device=dev)
+            eng._call("stream_std", lib.cum_stream_std_fwd, X.data_ptr(), X.shape[1], B, F, self.frame_length, self.hop,
+                      self.frames, self.running_std.data_ptr(), scale.data_ptr(), st())
+
+        # ---------------- encoder: every level produces all columns its (frame-aligned) input allows
+        avail_in = self.samples_base + n_use                    # absolute count of level-0 inputs (samples)
+        for i, e in enumerate(meta["enc"]):
+            c_old = self.enc_count[i]
+            c_new = (avail_in - 4) // 2 + 1
+            rows_new = c_new - c_old
+            assert rows_new > 0
+            y = torch.empty(B, rows_new, e["Hc_p"], dtype=torch.float32, device=dev)
+            if i == 0:
+                off = 2 * c_old - self.samples_base             # first sample of the first new column, inside X
+                per_frame = self.hop // 2                       # new level-1 columns per frame
+                first_rows = (self.frame_length - 4) // 2 + 1   # ... of the first frame after a reset
+                row_off = -(first_rows - per_frame) if first else 0
+                eng._call("conv_in", lib.cum_conv_in_fwd, X.data_ptr() + 4 * off, X.shape[1], B, n_use - off,
+                          pk["enc0.w"].data_ptr(), pk["enc0.b"].data_ptr(), y.data_ptr(), rows_new, e["Hc_p"], 4, 2,
+                          ptr(scale), per_frame, row_off, st())
+            else:
+                src, cp = self.enc_buf[i - 1], e["Cin_p"]
+                lo = 2 * c_old - self.enc_base[i - 1]           # local column of the first input this call needs
+                have = self.enc_count[i - 1] - self.enc_base[i - 1] - lo
+                eng.gemm(src, lo * cp, src.shape[1] * cp, 2 * cp, have // 2, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
+                         y, 0, rows_new * e["Hc_p"], e["Hc_p"], rows_new, e["Hc_p"], B, EPI_RELU, taps=2, shifts=(0, 1))
+            # 1x1 + GLU, appended to this level's output FIFO
+            keep = c_old - self.enc_base[i]
+            buf = torch.empty(B, keep + rows_new, e["Ho_p"], dtype=torch.float32, device=dev)
+            if keep:
+                old = self.enc_buf[i]
+                buf[:, :keep].copy_(old[:, old.shape[1] - keep:])
+            cap = buf.shape[1]
+            eng.gemm(y, 0, rows_new * e["Hc_p"], e["Hc_p"], rows_new, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"],
+                     buf, keep * e["Ho_p"], cap * e["Ho_p"], e["Ho_p"], rows_new, 2 * e["Ho_p"], B, act)
+            self.enc_buf[i] = buf
+            self.enc_count[i] = c_new
+            avail_in = c_new
+
+        # ---------------- bottleneck: F new tokens
+        last = self.enc_buf[D - 1]
+        cbp = meta["enc"][-1]["Ho_p"]
+        assert last.shape[1] == F, (last.shape, F)
+        h = eng.dense(last, B * F, cbp, "t1.w", pk["t1.b"], meta["dm_p"])
+        hn = eng.mamba_layers(h, B, F, states=self.states)
+        xcur = eng.dense(hn, B * F, meta["dm_p"], "t2.w", pk["t2.b"], cbp, addend=last)
+        self.enc_base[D - 1] += F
+        self.enc_buf[D - 1] = last[:, F:]
+
+        # ---------------- decoder: d columns in, 2d final columns out per level
+        d_cols = F
+        out = None
+        for j, dd in enumerate(meta["dec"]):
+            hg = dd["Hg_p"]
+            G = torch.empty(B, d_cols + 1, hg, dtype=torch.float32, device=dev)
+            G[:, 0].copy_(self.dec_carry[j])
+            eng.gemm(xcur, 0, d_cols * dd["Cin_p"], dd["Cin_p"], d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"],
+                     G, hg, (d_cols + 1) * hg, hg, d_cols, 2 * hg, B, act)
+            self.dec_carry[j] = G[:, d_cols].clone()
+            if j < D - 1:
+                co = dd["Co_p"]
+                lvl = D - 2 - j
+                skip = self.enc_buf[lvl]
+                nxt = torch.empty(B, 2 * d_cols, co, dtype=torch.float32, device=dev)
+                # row p of the (d, 2 Co) output view = Wa . G[p+1] + Wb . G[p]   (G[0] is the carried column)
+                eng.gemm(G, 0, (d_cols + 1) * hg, hg, d_cols + 1, hg, f"dec{j}.w", pk[f"dec{j}.b"],
+                         nxt, 0, 2 * d_cols * co, 2 * co, d_cols, 2 * co, B, EPI_RELU, taps=2, shifts=(1, 0),
+                         addend=skip, add_bs=skip.shape[1] * co, add_rs=2 * co)
+                self.enc_base[lvl] += 2 * d_cols
+                self.enc_buf[lvl] = skip[:, 2 * d_cols:]
+                xcur, d_cols = nxt, 2 * d_cols
+            else:
+                length = 2 * d_cols
+                out = torch.empty(B, length, dtype=torch.float32, device=dev)
+                eng._call("convt_out", lib.cum_convt_out_fwd, G.data_ptr(), B, d_cols + 1, hg, pk[f"dec{j}.w"].data_ptr(),
+                          meta["out_bias"], ptr(scale), self.hop, out.data_ptr(), length, 2, length, 4, 2, st())
+        self.frames += F
+        self.frames_since_reset += F
+        return out

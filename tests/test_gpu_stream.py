@@ -1,0 +1,88 @@
+"""GPU parity of the carried-state streaming path (StreamSession / feed / flush) against the CPU streaming oracle
+(oracle.StreamOracle == the reference's feed/_denoise_frame/flush with the skip order fixed) and against offline forward."""
+import json
+
+import pytest
+import torch
+
+import cleanumamba_oracle as orc
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5      # fp32, outputs are O(0.1); chunked vs frame-by-frame differ only by summation order
+
+
+def build(fx, **kw):
+    from cleanumamba_b200.network import Net
+    net = Net("CleanUMamba", {**json.loads(fx["config"]), **kw})
+    net.load_pruned_state_dict(fx["state_dict"])
+    return net.cuda().float().eval()
+
+
+def ragged_chunks(total, seed, lo=1, hi=1500):
+    g = torch.Generator().manual_seed(seed)
+    cuts, pos = [], 0
+    while pos < total:
+        n = int(torch.randint(lo, hi, (1,), generator=g))
+        cuts.append((pos, min(total, pos + n)))
+        pos += n
+    return cuts
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("name,math", [("tiny_equalwidth_seed0", "fp32"), ("e6_pruned_200k", "fp32"),
+                                       ("e8_pruned_500k", "fp32"), ("e8_pruned_500k", "tf32x3")])
+def test_stream_matches_stream_oracle(name, math, normalize):
+    fx = load_golden(name)
+    net = build(fx, normalize_input=normalize, math_mode=math)
+    x = fx["noisy"][:1, 0]                                  # (1, T)
+    x = x[:, : min(x.shape[1], 6000)]
+    so = orc.StreamOracle(fx["state_dict"], normalize_input=normalize)
+    want = torch.cat([so.feed(x), so.flush()], 1)
+    sess = net.stream_session(batch=1)
+    outs = [sess.feed(x[:, a:b].cuda()) for a, b in ragged_chunks(x.shape[1], 3)]
+    outs.append(sess.flush())
+    got = torch.cat(outs, 1).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < TOL
+    if not normalize:       # streaming == offline forward on every sample emitted before the flush
+        off = orc.forward(fx["state_dict"], x, normalize_input=False)[:, 0]
+        n_emit = sum(o.shape[1] for o in outs[:-1])
+        assert n_emit > 0 and (got[:, :n_emit] - off[:, :n_emit]).abs().max().item() < TOL
+
+
+def test_batched_streams_multi_hop_chunks():
+    """4 independent streams, 8 hops per call: equals 4 single-stream oracles."""
+    fx = load_golden("e6_pruned_200k")
+    net = build(fx, normalize_input=True)
+    g = torch.Generator().manual_seed(11)
+    B, hop = 4, 64
+    x = torch.randn(B, 190 + hop * 8 * 5, generator=g) * 0.1 * (1 + torch.arange(B)[:, None])
+    sess = net.stream_session(batch=B)
+    outs, pos = [], 0
+    for n in [190 + hop * 7] + [hop * 8] * 4 + [hop * 1]:
+        outs.append(sess.feed(x[:, pos:pos + n].cuda()))
+        pos += n
+    got = torch.cat(outs, 1).cpu()
+    for b in range(B):
+        so = orc.StreamOracle(fx["state_dict"], normalize_input=True)
+        want = so.feed(x[b:b + 1, :pos])
+        assert got[b:b + 1].shape == want.shape
+        assert (got[b:b + 1] - want).abs().max().item() < TOL * (1 + b)
+
+
+def test_module_feed_flush_api():
+    """Same call pattern as the reference self-test (CleanUMamba.py:574-582): feed + flush ~= parallel forward."""
+    fx = load_golden("mini_mamba_442k")
+    net = build(fx, normalize_input=False)
+    x = fx["noisy"][:1, 0, :8000].cuda()
+    with torch.no_grad():
+        par = net(x.clone()).squeeze(1)[:, : x.shape[1]]     # normalize_input=False returns the padded length
+        seq = net.feed(x)
+        seq = torch.cat([seq, net.flush()], 1)
+    assert seq.shape == par.shape
+    n_exact = seq.shape[1] - 2 * net.total_stride - net.frame_length
+    assert (seq[:, :n_exact] - par[:, :n_exact]).abs().max().item() < TOL
+    assert torch.allclose(seq, par, atol=0.1)                   # the reference's own tolerance
+    with pytest.raises(ValueError):
+        net.feed(torch.zeros(2, 3, device="cuda"))

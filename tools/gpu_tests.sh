@@ -6,5 +6,5 @@ export PYTHONUNBUFFERED=1 OMP_NUM_THREADS=${OMP_NUM_THREADS:-16}
 nvidia-smi -L > gpurun_out/diag.log 2>&1
 timeout 300 python -u tools/gpu_diag.py "$@" >> gpurun_out/diag.log 2>&1; echo "diag rc=$?" >> gpurun_out/diag.log
 tail -25 gpurun_out/diag.log
-timeout ${TEST_TIMEOUT:-600} python -u -m pytest tests -m gpu -v --timeout 120 -x -p no:cacheprovider > gpurun_out/tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/tests.log
+timeout ${TEST_TIMEOUT:-600} python -u -m pytest tests -m gpu -v -rP --timeout 120 -x -p no:cacheprovider ${PYTEST_ARGS} > gpurun_out/tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/tests.log
 tail -40 gpurun_out/tests.log
