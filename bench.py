@@ -140,6 +140,68 @@ def run_reference(args, cfg, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def run_stream(args, net, eng, dev, rank, world, dist):
+    """configs[2]: `streams` concurrent streams per GPU, `hops` hops per feed() call, carried conv/SSM state.
+    A step = one feed() call over all streams; value = streamed audio-seconds per wall-second."""
+    S, H, hop = args.streams, args.hops, net.total_stride
+    g = torch.Generator().manual_seed(4321 + rank)
+    n_chunk = H * hop
+    host_chunk = (torch.randn(S, n_chunk, generator=g) * 0.1).pin_memory()
+    host_out = torch.empty(S, n_chunk).pin_memory()
+    chunk = host_chunk.to(dev)
+    sess = net.stream_session(batch=S)
+    sess.feed((torch.randn(S, net.frame_length - hop, generator=g) * 0.1).to(dev))   # prime: next feeds emit H hops each
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = sess.feed(chunk)
+        assert out.shape == (S, n_chunk), out.shape
+    barrier()
+    eng.prof, eng.launches = [], 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sess.feed(chunk)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches, prof = eng.launches, eng.profile_summary()
+    eng.prof = None
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dchunk = torch.empty_like(chunk)
+    f0.record()
+    for _ in range(args.steps):
+        dchunk.copy_(host_chunk, non_blocking=True)
+        host_out.copy_(sess.feed(dchunk), non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank == 0:
+        audio = world * S * n_chunk / SR * args.steps
+        kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] // args.steps}
+                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        print(json.dumps({"metric": METRIC + " [streaming]", "value": round(audio / (ms / 1e3), 1), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"CleanUMamba {args.model.upper()} streaming, {S} streams per GPU, {H} hops "
+                                                 f"({n_chunk} samples, {1e3 * n_chunk / SR:.0f} ms) per feed(), carried conv/SSM state, "
+                                                 f"math={args.math}", "real_time_factor_per_stream": round(n_chunk / SR / (ms / args.steps / 1e3), 2),
+                                     "chunk_latency_ms": round(ms / args.steps, 3)},
+                          "e2e": {"value": round(audio / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": S * n_chunk * 4,
+                                  "d2h_bytes_per_step": S * n_chunk * 4},
+                          "gpu_launches": launches, "kernels": kernels}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -151,6 +213,10 @@ def main():
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--math", default=os.environ.get("CUM_MATH", "fp32"), choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="offline", choices=["offline", "stream"],
+                    help="offline = headline (configs[1]); stream = configs[2]: carried-state chunked inference")
+    ap.add_argument("--streams", type=int, default=4096, help="[stream] concurrent streams per GPU")
+    ap.add_argument("--hops", type=int, default=16, help="[stream] hops (2^D samples each) per feed() call")
     args = ap.parse_args()
     cfg = CONFIGS[args.model]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -173,6 +239,9 @@ def main():
     torch.manual_seed(0)
     net = Net("CleanUMamba", dict(cfg, math_mode=args.math)).to(dev).eval()
     eng = net.engine()
+    if args.mode == "stream":
+        run_stream(args, net, eng, dev, rank, world, dist)
+        return
     B, T = args.batch, int(args.seconds * SR)
     host_in = synth_noisy(B, args.seconds, 1234 + rank).pin_memory()
     host_out = torch.empty(B, 1, T).pin_memory()

@@ -95,6 +95,7 @@ class CleanUMamba(nn.Module):
         self.inference_params = None
         self.encoder_decoder_state = {}
         self._engine = None
+        self._train_engine = None
         self._stream = None
 
     # ------------------------------------------------------------------ shape helpers (:219-250)
@@ -119,6 +120,12 @@ class CleanUMamba(nn.Module):
         if self._engine is None:
             self._engine = Engine(self)
         return self._engine
+
+    def train_engine(self):
+        from .train_engine import TrainEngine
+        if getattr(self, "_train_engine", None) is None:
+            self._train_engine = TrainEngine(self)
+        return self._train_engine
 
     def forward(self, noisy_audio, return_skip_connections=False):
         """(B, L) | (B, 1, L) -> (B, 1, L).  Like the reference (:260-262) the input tensor is normalised IN PLACE
@@ -218,4 +225,5 @@ class CleanUMamba(nn.Module):
         resize(self, "")
         self.load_state_dict(pruned_state_dict, strict=True)
         self._engine = None
+        self._train_engine = None
         self._stream = None

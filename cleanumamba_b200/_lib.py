@@ -41,7 +41,25 @@ class ScanDesc(C.Structure):
                 ("a2", C.c_void_p), ("Dskip", C.c_void_p), ("delta_bias", C.c_void_p),
                 ("h0", C.c_void_p), ("h_out", C.c_void_p),
                 ("batch", C.c_int), ("len", C.c_int), ("d", C.c_int), ("n_state", C.c_int),
-                ("delta_softplus", C.c_int)]
+                ("delta_softplus", C.c_int), ("h_ckpt", C.c_void_p)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("dz", C.c_void_p), ("dz_batch_stride", C.c_longlong), ("dz_row_stride", C.c_longlong),
+                ("a", C.c_void_p), ("a_batch_stride", C.c_longlong), ("a_row_stride", C.c_longlong), ("a_rows", C.c_int),
+                ("dw", C.c_void_p), ("ldw", C.c_int), ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("taps", C.c_int),
+                ("tap_shift", C.c_int * 2), ("batch", C.c_int)]
+
+
+class ScanBwdDesc(C.Structure):
+    _fields_ = [("fwd", ScanDesc), ("h_ckpt", C.c_void_p),
+                ("dout", C.c_void_p), ("dout_bs", C.c_longlong), ("dout_rs", C.c_longlong),
+                ("du", C.c_void_p), ("du_bs", C.c_longlong), ("du_rs", C.c_longlong),
+                ("ddelta", C.c_void_p), ("ddl_bs", C.c_longlong), ("ddl_rs", C.c_longlong),
+                ("dz", C.c_void_p), ("dz_bs", C.c_longlong), ("dz_rs", C.c_longlong),
+                ("dB", C.c_void_p), ("dB_bs", C.c_longlong), ("dB_rs", C.c_longlong),
+                ("dC", C.c_void_p), ("dC_bs", C.c_longlong), ("dC_rs", C.c_longlong),
+                ("dA_log", C.c_void_p), ("dD", C.c_void_p), ("ddelta_bias", C.c_void_p)]
 
 
 EXPORTS = {
@@ -62,6 +80,22 @@ EXPORTS = {
     "cum_dwconv_silu_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cum_selective_scan_fwd": (C.c_int, [C.POINTER(ScanDesc), C.c_void_p]),
+    "cum_glu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "cum_glu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "cum_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "cum_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "cum_add_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cum_gemm_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "cum_ln_residual_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_float, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "cum_dwconv_silu_bwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_void_p]),
+    "cum_conv_in_bwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cum_convt_out_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "cum_selective_scan_bwd": (C.c_int, [C.POINTER(ScanBwdDesc), C.c_void_p]),
 }
 
 _lib = None

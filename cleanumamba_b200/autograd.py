@@ -1,9 +1,36 @@
-"""Training-mode forward (autograd).  The backward kernels (conv dgrad/wgrad tap-GEMMs, reverse selective scan,
-LayerNorm / depthwise-conv backward) are scheduled after the forward + streaming paths; until
-they land the product refuses to silently fall back to PyTorch autograd."""
+"""Training-mode forward: one torch.autograd.Function around the whole CUDA path.
+
+The loss (L1 + multi-resolution STFT, /root/reference/src/util/util.py:215-327) stays in PyTorch and back-propagates
+into ``out``; ``backward`` then runs our kernels (train_engine.TrainEngine.backward) and hands PyTorch one gradient per
+parameter, so optimisers / GradScaler / gradient clipping / DDP-style all-reduce work unchanged.  No PyTorch autograd
+fallback exists for the model body."""
+import torch
+
+
+class _CleanUMambaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, noisy, *params):
+        eng = model.train_engine()
+        with torch.no_grad():
+            out, saved = eng.forward_train(noisy)
+        ctx.eng, ctx.saved = eng, saved
+        ctx.names = [n for n, _ in model.named_parameters()]
+        ctx.needs = [p.requires_grad for p in params]
+        ctx.dtypes = [p.dtype for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        with torch.no_grad():
+            ctx.eng.backward(ctx.saved, dout)
+            grads = ctx.eng.unpack_grads()
+        ctx.saved = None
+        outs = [grads[n].to(dt) if need else None for n, need, dt in zip(ctx.names, ctx.needs, ctx.dtypes)]
+        return (None, None, *outs)
 
 
 def forward_with_grad(model, noisy_audio, return_skip_connections=False):
-    raise NotImplementedError(
-        "cleanumamba_b200: backward kernels are not built yet -- call the model under torch.no_grad() "
-        "(inference / streaming).  No PyTorch fallback is provided on purpose.")
+    if return_skip_connections:
+        raise NotImplementedError("cleanumamba_b200: return_skip_connections is inference-only (knowledge-distillation "
+                                  "losses of the reference are outside the hot path)")
+    return _CleanUMambaFn.apply(model, noisy_audio, *list(model.parameters()))

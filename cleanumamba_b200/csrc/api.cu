@@ -126,4 +126,49 @@ int cum_selective_scan_fwd(const cum_scan_desc* desc, cum_stream_t stream) {
     return selective_scan_fwd(*desc, (cudaStream_t)stream);
 }
 
+int cum_glu_fwd(const float* z, const float* addend, float* out, long long rows, int h_pad, cum_stream_t stream) {
+    return glu_fwd(z, addend, out, rows, h_pad, (cudaStream_t)stream);
+}
+int cum_glu_bwd(const float* z, const float* dout, float* dz, float* dbias, long long rows, int h_pad, cum_stream_t stream) {
+    return rowblock_bwd(0, z, dout, dz, dbias, rows, 2 * h_pad, (cudaStream_t)stream);
+}
+int cum_relu_bwd(const float* y, const float* dy, float* dz, float* dbias, long long rows, int cols, cum_stream_t stream) {
+    return rowblock_bwd(1, y, dy, dz, dbias, rows, cols, (cudaStream_t)stream);
+}
+int cum_colsum(const float* d, float* dbias, long long rows, int cols, cum_stream_t stream) {
+    return rowblock_bwd(2, nullptr, d, nullptr, dbias, rows, cols, (cudaStream_t)stream);
+}
+int cum_add_fwd(const float* a, const float* b, float* out, long long count, cum_stream_t stream) {
+    return add_fwd(a, b, out, count, (cudaStream_t)stream);
+}
+int cum_gemm_wgrad(const cum_wgrad_desc* desc, cum_stream_t stream) {
+    if (!desc) { set_error("wgrad: null descriptor"); return CUM_EINVAL; }
+    return wgrad_fwd(*desc, (cudaStream_t)stream);
+}
+int cum_ln_residual_bwd(const float* x, const float* dy, const float* dres_in, const float* gamma, float* dx,
+                        float* dgamma, float* dbeta, float eps, long long rows, int c, int c_pad, cum_stream_t stream) {
+    return ln_bwd(x, dy, dres_in, gamma, dx, dgamma, dbeta, eps, rows, c, c_pad, (cudaStream_t)stream);
+}
+int cum_dwconv_silu_bwd(const float* x, long long x_batch_stride, long long x_row_stride, const float* w,
+                        const float* bias, const float* dy, float* dx, long long dx_batch_stride,
+                        long long dx_row_stride, float* dw, float* db, int batch, int len, int d_pad, int width,
+                        cum_stream_t stream) {
+    return dwconv_silu_bwd(x, x_batch_stride, x_row_stride, w, bias, dy, dx, dx_batch_stride, dx_row_stride, dw, db,
+                           batch, len, d_pad, width, (cudaStream_t)stream);
+}
+int cum_conv_in_bwd(const float* x, long long x_stride, int batch, int length, const float* y, const float* dy,
+                    float* dw, float* db, int rows_out, int c_pad, int kernel, int stride, cum_stream_t stream) {
+    return conv_in_bwd(x, x_stride, batch, length, y, dy, dw, db, rows_out, c_pad, kernel, stride, (cudaStream_t)stream);
+}
+int cum_convt_out_bwd(const float* g, int batch, int rows_in, int c_pad, const float* w, const float* scale,
+                      const float* dout, long long dout_stride, int length, float* dg, float* dw, float* dbias,
+                      int kernel, int stride, cum_stream_t stream) {
+    return convt_out_bwd(g, batch, rows_in, c_pad, w, scale, dout, dout_stride, length, dg, dw, dbias, kernel, stride,
+                         (cudaStream_t)stream);
+}
+int cum_selective_scan_bwd(const cum_scan_bwd_desc* desc, cum_stream_t stream) {
+    if (!desc) { set_error("selective_scan_bwd: null descriptor"); return CUM_EINVAL; }
+    return selective_scan_bwd(*desc, (cudaStream_t)stream);
+}
+
 }  // extern "C"

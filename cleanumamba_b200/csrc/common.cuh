@@ -87,6 +87,25 @@ int dwconv_silu_fwd(const float* x, long long x_bs, long long x_rs, const float*
                     cudaStream_t st);
 int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st);
 
+int glu_fwd(const float* z, const float* addend, float* out, long long rows, int h_pad, cudaStream_t st);
+int rowblock_bwd(int mode, const float* z, const float* dout, float* dz, float* dbias, long long rows, int cols, cudaStream_t st);
+int add_fwd(const float* a, const float* b, float* out, long long count, cudaStream_t st);
+int wgrad_fwd(const cum_wgrad_desc& d, cudaStream_t st);
+int ln_bwd(const float* x, const float* dy, const float* dres_in, const float* gamma, float* dx, float* dgamma,
+           float* dbeta, float eps, long long rows, int c, int c_pad, cudaStream_t st);
+int dwconv_silu_bwd(const float* x, long long x_bs, long long x_rs, const float* w, const float* bias, const float* dy,
+                    float* dx, long long dx_bs, long long dx_rs, float* dw, float* db, int batch, int len, int d_pad,
+                    int width, cudaStream_t st);
+int conv_in_bwd(const float* x, long long x_stride, int batch, int length, const float* y, const float* dy, float* dw,
+                float* db, int rows_out, int c_pad, int kernel, int stride, cudaStream_t st);
+int convt_out_bwd(const float* g, int batch, int rows_in, int c_pad, const float* w, const float* scale,
+                  const float* dout, long long dout_stride, int length, float* dg, float* dw, float* dbias, int kernel,
+                  int stride, cudaStream_t st);
+int selective_scan_bwd(const cum_scan_bwd_desc& d, cudaStream_t st);
+
+constexpr int CI_MAXK = 8;   // conv_in / conv_in_bwd
+constexpr int CT_MAXK = 8;   // convt_out / convt_out_bwd
+
 int  sm_count();
 
 }  // namespace cum

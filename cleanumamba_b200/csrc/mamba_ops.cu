@@ -298,6 +298,13 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
         const int buf = chunk & 1;
         const int t0 = chunk * TC;
         const int tn = min(TC, p.len - t0);
+        if (p.h_ckpt) {   // training: state at the start of this chunk, for the reverse scan
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const int n = slice * NS + i;
+                if (c_ok && n < p.n_state) p.h_ckpt[(((long long)b * nchunks + chunk) * p.d + c) * p.n_state + n] = h[i];
+            }
+        }
         cp_async_wait<0>();
         __syncthreads();  // (A) tile `buf` landed; everybody is done with the previous chunk's combine
         if (chunk + 1 < nchunks) stage(chunk + 1, buf ^ 1);

@@ -95,7 +95,6 @@ int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, in
 // channels for one row so the stores are fully coalesced (the kernel is store-bound: 4*Cp bytes per row).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CI_ROWS = 64;
-constexpr int CI_MAXK = 8;
 
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, long long x_stride, int length,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
@@ -157,7 +156,6 @@ int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const
 // of the dots from smem into S*64 output samples.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CT_ROWS = 64;
-constexpr int CT_MAXK = 8;
 
 template <int LPR>
 __global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict__ g, int rows_in, int c_pad,

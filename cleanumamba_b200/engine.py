@@ -187,6 +187,7 @@ class Engine:
             meta["dec"].append(dict(Hg=Hg, Hg_p=Hg_p, Co=Co, Co_p=Co_p, Cin_p=c_prev_p))
             c_prev_p = Co_p
 
+        items.update(self._extra_items(items))
         # one flat device buffer, every tensor 256-byte aligned
         offs, total = {}, 0
         for k, t in items.items():
@@ -212,6 +213,14 @@ class Engine:
                 self.pk_hi[k] = hi[offs[k]: offs[k] + t.numel()].view(t.shape)
                 self.pk_lo[k] = lo[offs[k]: offs[k] + t.numel()].view(t.shape)
             self._flat_split = (hi, lo)
+        self._post_pack(items, offs, total)
+
+    def _extra_items(self, items):
+        """Hook: additional packed tensors (TrainEngine adds the transposed weights used by the data gradients)."""
+        return {}
+
+    def _post_pack(self, items, offs, total):
+        """Hook: called once the packed buffer exists (TrainEngine allocates the gradient buffer here)."""
 
     # ------------------------------------------------------------------------------------------------ op wrappers
     def gemm(self, a, a_off, a_bs, a_rs, a_rows, k, w, bias, c, c_off, c_bs, c_rs, m, n, batch, epi,
@@ -247,19 +256,23 @@ class Engine:
                    ptr(be), eps, rows, c, c_p, _lib.stream_ptr(),
                    nbytes=4 * rows * c * (2 + (res_in is not None) + (res_out is not None)))
 
-    def scan(self, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None):
+    def fill_scan(self, s, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None, h_ckpt=None):
+        """Fill a cum_scan_desc for Mamba layer ``l`` operating on the engine's channels-last buffers."""
         di_p, N_p, R_p = mm["di_p"], mm["N_p"], mm["R_p"]
-        s = ScanDesc()
         s.u, s.u_bs, s.u_rs = u.data_ptr(), T * di_p, di_p
         s.delta, s.dl_bs, s.dl_rs = dt.data_ptr(), T * di_p, di_p
         s.z, s.z_bs, s.z_rs = xz.data_ptr() + 4 * di_p, T * 2 * di_p, 2 * di_p
         ld = R_p + 2 * N_p
         s.Bm, s.B_bs, s.B_rs = xdbl.data_ptr() + 4 * R_p, T * ld, ld
         s.Cm, s.C_bs, s.C_rs = xdbl.data_ptr() + 4 * (R_p + N_p), T * ld, ld
-        s.y, s.y_bs, s.y_rs = y.data_ptr(), T * di_p, di_p
+        s.y, s.y_bs, s.y_rs = ptr(y), T * di_p, di_p
         s.a2, s.Dskip, s.delta_bias = self.pk[f"m{l}.a2"].data_ptr(), self.pk[f"m{l}.D"].data_ptr(), self.pk[f"m{l}.dtb"].data_ptr()
-        s.h0, s.h_out = ptr(h0), ptr(h_out)
+        s.h0, s.h_out, s.h_ckpt = ptr(h0), ptr(h_out), ptr(h_ckpt)
         s.batch, s.len, s.d, s.n_state, s.delta_softplus = B, T, di_p, N_p, 1
+
+    def scan(self, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None, h_ckpt=None):
+        s = ScanDesc()
+        self.fill_scan(s, u, dt, xz, xdbl, y, l, mm, B, T, h0, h_out, h_ckpt)
         # algorithmic bytes (SURVEY.md §8d): read u, delta, z + B, C, write y -- real (unpadded) widths
         self._call("selective_scan", self.lib.cum_selective_scan_fwd, C.byref(s), _lib.stream_ptr(),
                    nbytes=4 * B * T * (4 * mm["di"] + 2 * mm["N"]), flops=B * T * mm["di"] * mm["N"])

@@ -155,8 +155,76 @@ typedef struct cum_scan_desc {
     const float* h0; float* h_out;
     int batch, len, d, n_state;
     int delta_softplus;
+    float* h_ckpt;      /* optional (training): (batch, ceil(len/16), d, n_state) -- h at the start of every 16-step chunk,
+                           consumed by cum_selective_scan_bwd */
 } cum_scan_desc;
 int cum_selective_scan_fwd(const cum_scan_desc* desc, cum_stream_t stream);
+
+/* ---- backward (training; autograd of CleanUMamba.forward, src/training/train.py:278-285) ------------------- */
+/* In training the GLU gate and the skip add run as separate kernels so the pre-activation is saved once:
+ *   glu_fwd : out[r,c] = z[r,2c] * sigmoid(z[r,2c+1]) (+ addend[r,c]);  z: (rows, 2 h_pad) interleaved
+ *   glu_bwd : dz from dout (rows, h_pad); dbias (2 h_pad) += column sums of dz (atomics; may be NULL)
+ *   relu_bwd: dz = dy * (y > 0); dbias (cols) += column sums.     colsum: dbias += column sums of d.
+ *   add     : out = a + b (count elements, multiple of 4). */
+int cum_glu_fwd(const float* z, const float* addend, float* out, long long rows, int h_pad, cum_stream_t stream);
+int cum_glu_bwd(const float* z, const float* dout, float* dz, float* dbias, long long rows, int h_pad, cum_stream_t stream);
+int cum_relu_bwd(const float* y, const float* dy, float* dz, float* dbias, long long rows, int cols, cum_stream_t stream);
+int cum_colsum(const float* d, float* dbias, long long rows, int cols, cum_stream_t stream);
+int cum_add_fwd(const float* a, const float* b, float* out, long long count, cum_stream_t stream);
+
+/* Weight gradient of the tap-GEMM:  dw[s, n, k] += sum_{b, row < m} dz[b,row,n] * a[b, row + tap_shift[s], k]
+ * (rows of `a` outside [0, a_rows) read as zero; dw is accumulated with atomics -> zero it first).  The DATA gradient
+ * of the tap-GEMM is cum_gemm_bias_act_fwd itself with transposed packed weights and negated shifts. */
+typedef struct cum_wgrad_desc {
+    const float* dz; long long dz_batch_stride; long long dz_row_stride;
+    const float* a;  long long a_batch_stride;  long long a_row_stride;
+    int a_rows;
+    float* dw; int ldw;          /* (taps, n, ldw) */
+    int m, n, k, taps;
+    int tap_shift[2];
+    int batch;
+} cum_wgrad_desc;
+int cum_gemm_wgrad(const cum_wgrad_desc* desc, cum_stream_t stream);
+
+/* LayerNorm backward + residual-stream add: x = saved LN input (rows, c_pad); dy = grad of the normalised output;
+ * dres_in (may be NULL) = gradient already in the residual stream; dx = LN_bwd(dy) + dres_in;
+ * dgamma / dbeta (c_pad) accumulated with atomics. */
+int cum_ln_residual_bwd(const float* x, const float* dy, const float* dres_in, const float* gamma, float* dx,
+                        float* dgamma, float* dbeta, float eps, long long rows, int c, int c_pad, cum_stream_t stream);
+
+/* Backward of cum_dwconv_silu_fwd (width 4, zero initial state): dx (strided like x), dw (width, d_pad) and db (d_pad)
+ * accumulated with atomics. */
+int cum_dwconv_silu_bwd(const float* x, long long x_batch_stride, long long x_row_stride, const float* w,
+                        const float* bias, const float* dy, float* dx, long long dx_batch_stride,
+                        long long dx_row_stride, float* dw, float* db, int batch, int len, int d_pad, int width,
+                        cum_stream_t stream);
+
+/* Weight / bias gradients of cum_conv_in_fwd (no data gradient: the waveform is not a parameter); y = saved output. */
+int cum_conv_in_bwd(const float* x, long long x_stride, int batch, int length, const float* y, const float* dy,
+                    float* dw, float* db, int rows_out, int c_pad, int kernel, int stride, cum_stream_t stream);
+
+/* Backward of cum_convt_out_fwd (first = 0, scale per batch item): dg (batch, rows_in, c_pad) written; dw (K, c_pad)
+ * and dbias (1) accumulated with atomics. */
+int cum_convt_out_bwd(const float* g, int batch, int rows_in, int c_pad, const float* w, const float* scale,
+                      const float* dout, long long dout_stride, int length, float* dg, float* dw, float* dbias,
+                      int kernel, int stride, cum_stream_t stream);
+
+/* Reverse selective scan.  `fwd` = the descriptor of the forward call (y / h0 / h_out ignored); h_ckpt = the
+ * checkpoints that call wrote.  du, ddelta, dz are written; dB, dC (batch, len, n_state), dA_log (d, n_state), dD (d),
+ * ddelta_bias (d) are accumulated with atomics -> zero them first.  ddelta is the gradient w.r.t. the RAW delta
+ * (before bias and softplus). */
+typedef struct cum_scan_bwd_desc {
+    cum_scan_desc fwd;
+    const float* h_ckpt;
+    const float* dout; long long dout_bs; long long dout_rs;
+    float* du;     long long du_bs;  long long du_rs;
+    float* ddelta; long long ddl_bs; long long ddl_rs;
+    float* dz;     long long dz_bs;  long long dz_rs;
+    float* dB;     long long dB_bs;  long long dB_rs;
+    float* dC;     long long dC_bs;  long long dC_rs;
+    float* dA_log; float* dD; float* ddelta_bias;
+} cum_scan_bwd_desc;
+int cum_selective_scan_bwd(const cum_scan_bwd_desc* desc, cum_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,9 @@ def glu(x: Tensor, activation: str = "Sigmoid") -> Tensor:
     return a * _GLU_ACT[activation](b)
 
 
-def _cast(sd: StateDict, dtype) -> StateDict:
+def _cast(sd: StateDict, dtype, differentiable: bool = False) -> StateDict:
+    if differentiable:      # gradient oracle: keep the autograd graph back to the caller's leaf tensors
+        return {k: v.to(device="cpu", dtype=dtype) for k, v in sd.items()}
     return {k: v.detach().to(device="cpu", dtype=dtype) for k, v in sd.items()}
 
 
@@ -93,10 +95,11 @@ def selective_scan(u: Tensor, delta: Tensor, A: Tensor, Bm: Tensor, Cm: Tensor, 
     b, d, l = u.shape
     h = torch.zeros(b, d, A.shape[1], dtype=dt) if h0 is None else h0.to(dt).clone()
     du = delta * u
-    y = torch.empty(b, d, l, dtype=dt)
+    ys = []
     for t in range(l):
         h = torch.exp(delta[:, :, t, None] * A) * h + du[:, :, t, None] * Bm[:, None, :, t]
-        y[:, :, t] = torch.einsum("bdn,bn->bd", h, Cm[:, :, t])
+        ys.append(torch.einsum("bdn,bn->bd", h, Cm[:, :, t]))
+    y = torch.stack(ys, dim=2)
     if D is not None:
         y = y + u * D.to(dt)[..., None]
     if z is not None:
@@ -170,9 +173,11 @@ def bottleneck(x: Tensor, sd: StateDict, n_mamba: int, eps: float = 1e-5, step_s
 # offline forward  (CleanUMamba.py:252-324)
 # --------------------------------------------------------------------------------------------------------------
 def forward(sd: StateDict, noisy: Tensor, *, stride: int = 2, normalize_input: bool = True, eps: float = 1e-5,
-            glu_activation: str = "Sigmoid", dtype=torch.float32, return_intermediates: bool = False):
-    """noisy: (B, L) or (B, 1, L) -> denoised (B, 1, L).  Does NOT mutate ``noisy`` (the reference does, :262)."""
-    sd = _cast(sd, dtype)
+            glu_activation: str = "Sigmoid", dtype=torch.float32, return_intermediates: bool = False,
+            differentiable: bool = False):
+    """noisy: (B, L) or (B, 1, L) -> denoised (B, 1, L).  Does NOT mutate ``noisy`` (the reference does, :262).
+    ``differentiable=True`` keeps the autograd graph to the tensors of ``sd`` (oracle for the backward kernels)."""
+    sd = _cast(sd, dtype, differentiable)
     dims = model_dims(sd)
     D, K = dims["depth"], dims["kernel"]
     x = noisy.detach().to("cpu", dtype)
