@@ -202,6 +202,73 @@ def run_stream(args, net, eng, dev, rank, world, dist):
         dist.destroy_process_group()
 
 
+def run_train(args, net, dev, rank, world, dist):
+    """configs[3]: E8-full training step (fwd + L1 + multi-resolution STFT loss + bwd + fused Adam), per-GPU batch fixed
+    (weak scaling), gradients averaged with the bucketed NCCL all-reduce overlapped with the backward."""
+    from cleanumamba_b200.distributed import apply_gradient_allreduce
+    from cleanumamba_b200.loss import DEFAULT_STFT_CONFIG, MultiResolutionSTFTLoss, loss_fn
+    B = args.batch if args.batch != 64 else 16
+    T = int(args.seconds * SR)
+    net.train()
+    if dist is not None:
+        apply_gradient_allreduce(net)
+    opt = torch.optim.Adam(net.parameters(), lr=2e-4, fused=True)
+    mr = MultiResolutionSTFTLoss(**DEFAULT_STFT_CONFIG).to(dev)
+    noisy = synth_noisy(B, args.seconds, 1234 + rank).to(dev)
+    clean = synth_noisy(B, args.seconds, 99 + rank).to(dev) * 0.5
+    work = torch.empty_like(noisy)
+    eng = net.train_engine()
+
+    def step():
+        work.copy_(noisy)
+        opt.zero_grad(set_to_none=True)
+        loss, _ = loss_fn(net, (clean, work), mrstftloss=mr)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        loss = step()
+    barrier()
+    eng.prof, eng.launches = [], 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches, prof = eng.launches, eng.profile_summary()
+    eng.prof = None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] // args.steps,
+                       "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] and v["ms"] else None}
+                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        kernel_ms = sum(v["ms"] for v in prof.values()) / args.steps
+        grad_bytes = sum(p.numel() for p in net.parameters()) * 4
+        print(json.dumps({"metric": METRIC.replace("denoised", "trained on") + " [training step]",
+                          "value": round(world * B * args.seconds * args.steps / (ms / 1e3), 1), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"CleanUMamba {args.model.upper()} full training step: fwd + L1 + MR-STFT loss (PyTorch) "
+                                                 f"+ bwd + fused Adam (PyTorch), batch {B} x {args.seconds:g} s per GPU, math={args.math}",
+                                     "global_batch": world * B, "parallelism": f"dp{world}",
+                                     "grad_allreduce": {"bytes": grad_bytes, "buckets": 3, "overlapped": True} if world > 1 else None,
+                                     "our_kernels_ms_per_step": round(kernel_ms, 3), "final_loss": round(float(loss), 5)},
+                          "gpu_launches": launches, "kernels": kernels}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -213,8 +280,9 @@ def main():
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--math", default=os.environ.get("CUM_MATH", "fp32"), choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="offline", choices=["offline", "stream"],
-                    help="offline = headline (configs[1]); stream = configs[2]: carried-state chunked inference")
+    ap.add_argument("--mode", default="offline", choices=["offline", "stream", "train"],
+                    help="offline = headline (configs[1]); stream = configs[2]: carried-state chunked inference; "
+                         "train = configs[3]: fwd + L1/MR-STFT loss + bwd + Adam, data-parallel gradient all-reduce")
     ap.add_argument("--streams", type=int, default=4096, help="[stream] concurrent streams per GPU")
     ap.add_argument("--hops", type=int, default=16, help="[stream] hops (2^D samples each) per feed() call")
     args = ap.parse_args()
@@ -241,6 +309,9 @@ def main():
     eng = net.engine()
     if args.mode == "stream":
         run_stream(args, net, eng, dev, rank, world, dist)
+        return
+    if args.mode == "train":
+        run_train(args, net, dev, rank, world, dist)
         return
     B, T = args.batch, int(args.seconds * SR)
     host_in = synth_noisy(B, args.seconds, 1234 + rank).pin_memory()

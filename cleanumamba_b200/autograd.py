@@ -22,7 +22,12 @@ class _CleanUMambaFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         with torch.no_grad():
-            ctx.eng.backward(ctx.saved, dout)
+            sync = getattr(ctx.eng.model, "_grad_sync", None)
+            ctx.eng.backward(ctx.saved, dout, sync=sync)
+            if sync is not None:
+                scale = sync.finish()           # waits for the three bucket all-reduces (stream-ordered)
+                if scale != 1.0:
+                    ctx.eng.gflat.mul_(scale)
             grads = ctx.eng.unpack_grads()
         ctx.saved = None
         outs = [grads[n].to(dt) if need else None for n, need, dt in zip(ctx.names, ctx.needs, ctx.dtypes)]

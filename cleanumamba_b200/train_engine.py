@@ -32,9 +32,16 @@ class TrainEngine(Engine):
         return extra
 
     def _post_pack(self, items, offs, total):
-        self.gflat = torch.zeros(total + 64, dtype=torch.float32, device=self.device)
-        self.gk = {k: self.gflat[offs[k]: offs[k] + t.numel()].view(t.shape) for k, t in items.items() if not k.endswith("T")}
-        self.gk["out_bias"] = self.gflat[total: total + 4]
+        # gradient buffer: same offsets as the packed weights for the base items (they precede the transposed copies),
+        # followed by a slot for the scalar bias of the last transposed conv
+        base = [k for k in items if not k.endswith("T")]
+        base_total = max(offs[k] + (items[k].numel() + 63) // 64 * 64 for k in base)
+        self.gflat = torch.zeros(base_total + 64, dtype=torch.float32, device=self.device)
+        self.gk = {k: self.gflat[offs[k]: offs[k] + items[k].numel()].view(items[k].shape) for k in base}
+        self.gk["out_bias"] = self.gflat[base_total: base_total + 4]
+        # all-reduce buckets in the order the backward completes them: decoder (+ out bias), bottleneck, encoder
+        self.buckets = dict(decoder=(offs["dec0.wg"], base_total + 64), bottleneck=(offs["t1.w"], offs["dec0.wg"]),
+                            encoder=(0, offs["t1.w"]))
 
     # ---------------------------------------------------------------------------------------------- helpers
     def new(self, *shape):
@@ -160,8 +167,13 @@ class TrainEngine(Engine):
         return out, S
 
     # ---------------------------------------------------------------------------------------------- backward
-    def backward(self, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """dout: (B, 1, length) -> flat gradient views ``self.gk`` (packed layout), also returned."""
+    def backward(self, S: dict, dout: torch.Tensor, sync=None) -> Dict[str, torch.Tensor]:
+        """dout: (B, 1, length) -> flat gradient views ``self.gk`` (packed layout), also returned.  ``sync`` (a
+        distributed.GradSync) starts an asynchronous all-reduce of each gradient bucket as soon as it is complete."""
+        def bucket_done(name):
+            if sync is not None:
+                lo, hi = self.buckets[name]
+                sync.reduce(self.gflat[lo:hi])
         m, pk, meta, lib = self.model, self.pk, self.meta, self.lib
         st = _lib.stream_ptr
         B, L, D, Ls = S["B"], S["L"], meta["D"], S["Ls"]
@@ -203,6 +215,7 @@ class TrainEngine(Engine):
                 Tj = Tp
             else:
                 dskip[D - 1] = dx                                             # x_in = tsfm_conv2(hn_f) + skip[D-1]
+        bucket_done("decoder")
         # ---- tsfm_conv2
         T = Ls[D]
         rows = B * T
@@ -259,6 +272,7 @@ class TrainEngine(Engine):
         self._call("colsum", lib.cum_colsum, dres.data_ptr(), gk["t1.b"].data_ptr(), rows, dm_p, st())
         self.wgrad(dres, 0, dm_p, S["skip"][D - 1], 0, 0, cb_p, rows, "t1.w", rows, dm_p, cb_p, 1)
         dskip[D - 1] = self.dense_T(dres, rows, dm_p, "t1.w", cb_p, addend=dskip[D - 1])
+        bucket_done("bottleneck")
         # ---- encoder levels in reverse
         for i in range(D - 1, -1, -1):
             e = meta["enc"][i]
@@ -283,6 +297,7 @@ class TrainEngine(Engine):
             else:
                 self._call("conv_in_bwd", lib.cum_conv_in_bwd, S["x"].data_ptr(), L, B, L, y.data_ptr(), dy.data_ptr(),
                            gk["enc0.w"].data_ptr(), gk["enc0.b"].data_ptr(), Ls[1], hc, 4, 2, st())
+        bucket_done("encoder")
         return gk
 
     # ---------------------------------------------------------------------------------------------- unpack

@@ -149,3 +149,20 @@ def test_product_constructor_reproduces_reference_init():
     assert list(a.keys()) == list(b.keys())
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+@needs_ref
+def test_loss_restatement_matches_live_reference():
+    """cleanumamba_b200.loss vs the reference's own MultiResolutionSTFTLoss (src/util/stft_loss.py) on the same input."""
+    import sys
+    ref_loader.import_reference()
+    from src.util.stft_loss import MultiResolutionSTFTLoss as RefLoss
+    from cleanumamba_b200.loss import DEFAULT_STFT_CONFIG, MultiResolutionSTFTLoss
+    g = torch.Generator().manual_seed(3)
+    x, y = torch.randn(2, 1, 8000, generator=g) * 0.1, torch.randn(2, 1, 8000, generator=g) * 0.1
+    for band in ("full", "high"):
+        cfg = dict(DEFAULT_STFT_CONFIG, band=band)
+        a = MultiResolutionSTFTLoss(**cfg)(x, y)
+        b = RefLoss(**cfg)(x, y)
+        assert torch.allclose(a[0], b[0], rtol=1e-5) and torch.allclose(a[1], b[1], rtol=1e-5), band
+    del sys
