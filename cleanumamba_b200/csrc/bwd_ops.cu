@@ -45,18 +45,18 @@ int glu_fwd(const float* z, const float* addend, float* out, long long rows, int
 //   MODE 1: relu_bwd  dz = dy * (y > 0)
 //   MODE 2: colsum    no elementwise output, only the column sums of `dout`
 // ---------------------------------------------------------------------------------------------------------
-constexpr int RB_ROWS = 128;
+constexpr int RB_ROWS = 128;      // minimum rows per CTA; large problems use more so the column atomics stay ~1 per SM wave
 
 template <int MODE>
 __global__ void __launch_bounds__(256) rowblock_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dout,
                                                             float* __restrict__ dz, float* __restrict__ dbias,
-                                                            long long rows, int cols /* of dz / z */) {
+                                                            long long rows, int cols /* of dz / z */, int rows_per_cta) {
     const int groups = cols >> 2;                       // float4 groups per row
     const int gpr = groups < 256 ? groups : 256;        // groups handled per pass
     const int slots = 256 / gpr;                        // row slots per pass
     const int tg = threadIdx.x % gpr, ts = threadIdx.x / gpr;
-    const long long r0 = (long long)blockIdx.x * RB_ROWS;
-    const long long r1 = r0 + RB_ROWS < rows ? r0 + RB_ROWS : rows;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
     if (ts >= slots) return;
     for (int g = tg; g < groups; g += gpr) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -89,10 +89,12 @@ int rowblock_bwd(int mode, const float* z, const float* dout, float* dz, float* 
     CUM_REQUIRE(dout && rows > 0 && cols > 0 && cols % 4 == 0, "rowblock_bwd: bad arguments");
     CUM_REQUIRE(mode == 2 || (z && dz), "rowblock_bwd: z/dz required");
     CUM_REQUIRE(mode != 0 || cols % 8 == 0, "glu_bwd: cols must be a multiple of 8");
-    const unsigned grid = (unsigned)cdiv(rows, RB_ROWS);
-    if (mode == 0) rowblock_bwd_kernel<0><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols);
-    else if (mode == 1) rowblock_bwd_kernel<1><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols);
-    else rowblock_bwd_kernel<2><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols);
+    long long rpc = cdiv(rows, 8LL * sm_count());      // ~8 CTAs per SM at most -> few thousand atomics per column
+    if (rpc < RB_ROWS) rpc = RB_ROWS;
+    const unsigned grid = (unsigned)cdiv(rows, rpc);
+    if (mode == 0) rowblock_bwd_kernel<0><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols, (int)rpc);
+    else if (mode == 1) rowblock_bwd_kernel<1><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols, (int)rpc);
+    else rowblock_bwd_kernel<2><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols, (int)rpc);
     CUM_LAUNCH_CHECK("rowblock_bwd_kernel");
     return CUM_OK;
 }
@@ -459,14 +461,14 @@ int dwconv_silu_bwd(const float* x, long long x_bs, long long x_rs, const float*
 __global__ void __launch_bounds__(256) conv_in_bwd_kernel(const float* __restrict__ x, long long x_stride, int length,
                                                            const float* __restrict__ y, const float* __restrict__ dy,
                                                            float* __restrict__ dw, float* __restrict__ db, int rows_out,
-                                                           int c_pad, int kernel, int stride) {
+                                                           int c_pad, int kernel, int stride, int rows_per_cta) {
     const int groups = c_pad >> 2;
     const int gpr = groups < 256 ? groups : 256;
     const int slots = 256 / gpr;
     const int tg = threadIdx.x % gpr, ts = threadIdx.x / gpr;
     if (ts >= slots) return;
     const int b = blockIdx.y;
-    const int t0 = blockIdx.x * 256, t1 = min(rows_out, t0 + 256);
+    const int t0 = blockIdx.x * rows_per_cta, t1 = min(rows_out, t0 + rows_per_cta);
     const float* xb = x + (long long)b * x_stride;
     for (int g = tg; g < groups; g += gpr) {
         float4 acc[CI_MAXK], accb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -504,8 +506,11 @@ int conv_in_bwd(const float* x, long long x_stride, int batch, int length, const
                 float* db, int rows_out, int c_pad, int kernel, int stride, cudaStream_t st) {
     CUM_REQUIRE(x && y && dy && dw && db, "conv_in_bwd: null pointer");
     CUM_REQUIRE(batch > 0 && batch <= 65535 && rows_out > 0 && c_pad % 4 == 0 && kernel >= 1 && kernel <= CI_MAXK, "conv_in_bwd: bad shape");
-    dim3 grid((unsigned)cdiv(rows_out, 256), (unsigned)batch);
-    conv_in_bwd_kernel<<<grid, 256, 0, st>>>(x, x_stride, length, y, dy, dw, db, rows_out, c_pad, kernel, stride);
+    long long rpc = cdiv((long long)rows_out * batch, 8LL * sm_count());
+    if (rpc < 256) rpc = 256;
+    if (rpc > rows_out) rpc = rows_out;
+    dim3 grid((unsigned)cdiv(rows_out, rpc), (unsigned)batch);
+    conv_in_bwd_kernel<<<grid, 256, 0, st>>>(x, x_stride, length, y, dy, dw, db, rows_out, c_pad, kernel, stride, (int)rpc);
     CUM_LAUNCH_CHECK("conv_in_bwd_kernel");
     return CUM_OK;
 }
@@ -520,54 +525,63 @@ __global__ void __launch_bounds__(256) convt_out_bwd_kernel(const float* __restr
                                                              const float* __restrict__ w, const float* __restrict__ scale,
                                                              const float* __restrict__ dout, long long dout_stride,
                                                              int length, float* __restrict__ dg, float* __restrict__ dw,
-                                                             float* __restrict__ dbias, int kernel, int stride) {
+                                                             float* __restrict__ dbias, int kernel, int stride,
+                                                             int blocks_per_cta) {
     extern __shared__ float es[];           // e[S*j0 .. S*(j0+64) + kernel)
     const int b = blockIdx.y;
-    const int j0 = blockIdx.x * 64, j1 = min(rows_in, j0 + 64);
     const float sc = scale ? scale[b] : 1.0f;
     const int ne = 64 * stride + kernel;
-    float esum = 0.f;
-    for (int i = threadIdx.x; i < ne; i += blockDim.x) {
-        const long long m = (long long)j0 * stride + i;
-        const float v = m < length ? sc * dout[(long long)b * dout_stride + m] : 0.f;
-        es[i] = v;
-        // every output sample belongs to exactly one CTA's first 64*S window (the last CTA also owns the K-S tail)
-        if (i < 64 * stride || blockIdx.x == gridDim.x - 1) esum += v;
-    }
-    esum = warp_sum(esum);
-    if ((threadIdx.x & 31) == 0 && dbias) atomicAdd(dbias, esum);
-    __syncthreads();
     const int groups = c_pad >> 2;
     const int gpr = groups < 256 ? groups : 256;
     const int slots = 256 / gpr;
     const int tg = threadIdx.x % gpr, ts = threadIdx.x / gpr;
-    if (ts >= slots) return;
-    for (int cg = tg; cg < groups; cg += gpr) {
-        float4 wv[CT_MAXK], acc[CT_MAXK];
+    const int nblocks = (rows_in + 63) / 64;
+    const int blk0 = blockIdx.x * blocks_per_cta, blk1 = min(nblocks, blk0 + blocks_per_cta);
+    float esum = 0.f;
+    // this kernel supports c_pad <= 1024 (one column group per thread) so the dw accumulators stay in registers
+    float4 wv[CT_MAXK], acc[CT_MAXK];
 #pragma unroll
-        for (int k = 0; k < CT_MAXK; ++k) {
-            wv[k] = k < kernel ? __ldg(reinterpret_cast<const float4*>(w + (long long)k * c_pad) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < CT_MAXK; ++k) {
+        wv[k] = (k < kernel && tg < groups && ts < slots) ? __ldg(reinterpret_cast<const float4*>(w + (long long)k * c_pad) + tg)
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int blk = blk0; blk < blk1; ++blk) {
+        const int j0 = blk * 64, j1 = min(rows_in, j0 + 64);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+            const long long m = (long long)j0 * stride + i;
+            const float v = m < length ? sc * dout[(long long)b * dout_stride + m] : 0.f;
+            es[i] = v;
+            // every output sample belongs to exactly one block's first 64*S window (the last block also owns the K-S tail)
+            if (i < 64 * stride || blk == nblocks - 1) esum += v;
         }
-        for (int j = j0 + ts; j < j1; j += slots) {
-            const long long off = ((long long)b * rows_in + j) * c_pad;
-            const float4 gv = reinterpret_cast<const float4*>(g + off)[cg];
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        if (ts < slots && tg < groups) {
+            for (int j = j0 + ts; j < j1; j += slots) {
+                const long long off = ((long long)b * rows_in + j) * c_pad;
+                const float4 gv = reinterpret_cast<const float4*>(g + off)[tg];
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < CT_MAXK; ++k) {
-                if (k < kernel) {
-                    const float e = es[(j - j0) * stride + k];
-                    o.x = fmaf(e, wv[k].x, o.x); o.y = fmaf(e, wv[k].y, o.y); o.z = fmaf(e, wv[k].z, o.z); o.w = fmaf(e, wv[k].w, o.w);
-                    acc[k].x = fmaf(e, gv.x, acc[k].x); acc[k].y = fmaf(e, gv.y, acc[k].y);
-                    acc[k].z = fmaf(e, gv.z, acc[k].z); acc[k].w = fmaf(e, gv.w, acc[k].w);
+                for (int k = 0; k < CT_MAXK; ++k) {
+                    if (k < kernel) {
+                        const float e = es[(j - j0) * stride + k];
+                        o.x = fmaf(e, wv[k].x, o.x); o.y = fmaf(e, wv[k].y, o.y); o.z = fmaf(e, wv[k].z, o.z); o.w = fmaf(e, wv[k].w, o.w);
+                        acc[k].x = fmaf(e, gv.x, acc[k].x); acc[k].y = fmaf(e, gv.y, acc[k].y);
+                        acc[k].z = fmaf(e, gv.z, acc[k].z); acc[k].w = fmaf(e, gv.w, acc[k].w);
+                    }
                 }
+                reinterpret_cast<float4*>(dg + off)[tg] = o;
             }
-            reinterpret_cast<float4*>(dg + off)[cg] = o;
         }
+    }
+    esum = warp_sum(esum);
+    if ((threadIdx.x & 31) == 0 && dbias) atomicAdd(dbias, esum);
+    if (ts < slots && tg < groups) {
 #pragma unroll
         for (int k = 0; k < CT_MAXK; ++k) {
             if (k < kernel) {
-                float* p = dw + (long long)k * c_pad + 4 * cg;
+                float* p = dw + (long long)k * c_pad + 4 * tg;
                 atomicAdd(p + 0, acc[k].x); atomicAdd(p + 1, acc[k].y); atomicAdd(p + 2, acc[k].z); atomicAdd(p + 3, acc[k].w);
             }
         }
@@ -579,9 +593,13 @@ int convt_out_bwd(const float* g, int batch, int rows_in, int c_pad, const float
                   int stride, cudaStream_t st) {
     CUM_REQUIRE(g && w && dout && dg && dw, "convt_out_bwd: null pointer");
     CUM_REQUIRE(batch > 0 && batch <= 65535 && rows_in > 0 && c_pad % 4 == 0 && kernel >= 1 && kernel <= CT_MAXK && stride >= 1, "convt_out_bwd: bad shape");
-    dim3 grid((unsigned)cdiv(rows_in, 64), (unsigned)batch);
+    CUM_REQUIRE(c_pad <= 1024, "convt_out_bwd: c_pad=%d > 1024 not supported", c_pad);
+    const int nblocks = (rows_in + 63) / 64;
+    long long bpc = cdiv((long long)nblocks * batch, 8LL * sm_count());      // 64-row blocks per CTA
+    if (bpc < 1) bpc = 1;
+    dim3 grid((unsigned)cdiv(nblocks, bpc), (unsigned)batch);
     const size_t smem = (size_t)(64 * stride + kernel) * sizeof(float);
-    convt_out_bwd_kernel<<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, scale, dout, dout_stride, length, dg, dw, dbias, kernel, stride);
+    convt_out_bwd_kernel<<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, scale, dout, dout_stride, length, dg, dw, dbias, kernel, stride, (int)bpc);
     CUM_LAUNCH_CHECK("convt_out_bwd_kernel");
     return CUM_OK;
 }

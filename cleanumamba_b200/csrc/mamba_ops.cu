@@ -285,12 +285,24 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
 
     // per-thread constants and carried state
     float a2[NS], h[NS];
+    const bool state_vec = (p.n_state % 4 == 0) && (slice * NS + NS <= p.n_state) && c_ok;   // float4 path (64 B / thread)
+    if (state_vec) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        const int n = slice * NS + i;
-        const bool ok = c_ok && n < p.n_state;
-        a2[i] = ok ? p.a2[(long long)c * p.n_state + n] : 0.f;
-        h[i] = (ok && p.h0) ? p.h0[((long long)b * p.d + c) * p.n_state + n] : 0.f;
+        for (int q = 0; q < NS / 4; ++q) {
+            const float4 av = __ldg(reinterpret_cast<const float4*>(p.a2 + (long long)c * p.n_state + slice * NS) + q);
+            a2[4 * q] = av.x; a2[4 * q + 1] = av.y; a2[4 * q + 2] = av.z; a2[4 * q + 3] = av.w;
+            float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.h0) hv = *(reinterpret_cast<const float4*>(p.h0 + ((long long)b * p.d + c) * p.n_state + slice * NS) + q);
+            h[4 * q] = hv.x; h[4 * q + 1] = hv.y; h[4 * q + 2] = hv.z; h[4 * q + 3] = hv.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int n = slice * NS + i;
+            const bool ok = c_ok && n < p.n_state;
+            a2[i] = ok ? p.a2[(long long)c * p.n_state + n] : 0.f;
+            h[i] = (ok && p.h0) ? p.h0[((long long)b * p.d + c) * p.n_state + n] : 0.f;
+        }
     }
 
     stage(0, 0);
@@ -352,10 +364,17 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
         }
     }
     if (p.h_out) {
+        if (state_vec) {
 #pragma unroll
-        for (int i = 0; i < NS; ++i) {
-            const int n = slice * NS + i;
-            if (c_ok && n < p.n_state) p.h_out[((long long)b * p.d + c) * p.n_state + n] = h[i];
+            for (int q = 0; q < NS / 4; ++q)
+                *(reinterpret_cast<float4*>(p.h_out + ((long long)b * p.d + c) * p.n_state + slice * NS) + q) =
+                    make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const int n = slice * NS + i;
+                if (c_ok && n < p.n_state) p.h_out[((long long)b * p.d + c) * p.n_state + n] = h[i];
+            }
         }
     }
 }
