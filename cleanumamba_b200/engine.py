@@ -202,7 +202,7 @@ class Engine:
         self._flat = flat
         self.meta = meta
         self.device = dev
-        self.math = _lib.MATH_BY_NAME[getattr(m, "math_mode", "fp32")]
+        self.math = _lib.MATH_BY_NAME[getattr(m, "math_mode", "tf32x3")]
         self.lib = _lib.init(dev)
         self.pk_hi, self.pk_lo = {}, {}
         if self.math == _lib.MATH_TF32X3:      # hi/lo copies of the whole packed buffer (only GEMM weights use them)
