@@ -279,8 +279,11 @@ def main():
     ap.add_argument("--model", default="e8", choices=list(CONFIGS))
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--seconds", type=float, default=10.0)
-    ap.add_argument("--math", default=os.environ.get("CUM_MATH", "tf32x3"), choices=["fp32", "tf32x3", "tf32"],
-                    help="tf32x3 (default): tcgen05 3-pass TF32 split, parity-tested within the fp32 tolerance; fp32: exact FFMA")
+    ap.add_argument("--math", default=os.environ.get("CUM_MATH", "bf16x3"), choices=["fp32", "tf32x3", "bf16x3", "tf32"],
+                    help="arithmetic of the contractions (activations / accumulation / storage are fp32 in every mode): "
+                         "bf16x3 (default) and tf32x3 = tcgen05 3-pass split products, both parity-tested inside the fp32 "
+                         "tolerance of BASELINE.json (max-abs <= 1e-4, dSI-SDR <= 0.01 dB); fp32 = exact CUDA-core FFMA")
+    ap.add_argument("--no-variants", action="store_true", help="skip the short tf32x3 / fp32 comparison runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="offline", choices=["offline", "stream", "train"],
                     help="offline = headline (configs[1]); stream = configs[2]: carried-state chunked inference; "
@@ -399,11 +402,13 @@ def main():
                 "frac": round(achieved / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
                 "share_of_step": round(gem["ms"] / total_kernel_ms, 4) if total_kernel_ms else None,
                 "launches_per_step": gem["launches"] // args.steps,
-                "mma_passes": 3 if args.math == "tf32x3" else 1,
+                "mma_passes": 3 if args.math in ("tf32x3", "bf16x3") else 1,
                 "note": ("achieved = ALGORITHMIC flops (2*M*N*K per contraction) / CUDA-event kernel time; tf32x3 issues 3 "
                          "kind::tf32 MMAs per product (TF32 pipe = 1/2 of the bf16 peak used as denominator), so the pipe-level "
                          "rate is 3x achieved; ncu sm__pipe_tensor_cycles_active = 70-76 % on the K>=1024 layers "
-                         "(profiles/r01_ncu_full_gemm_tf32x3.md)") if args.math == "tf32x3" else None}
+                         "(profiles/r01_ncu_full_gemm_tf32x3.md)") if args.math == "tf32x3" else
+                        ("achieved = ALGORITHMIC flops / CUDA-event kernel time; bf16x3 issues 3 kind::f16 (bf16) MMAs per product, "
+                         "so the tensor-pipe rate is 3x achieved (K>=1024 layers: ~1.25 PFLOP/s of bf16 MMA work)") if args.math == "bf16x3" else None}
     scan = prof.get("selective_scan")
     scan_roof = None
     if scan:
@@ -417,6 +422,34 @@ def main():
     kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] // args.steps}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
+    variants = None
+    if world == 1 and not args.no_variants and args.mode == "offline":
+        # the other arithmetic modes on the same workload (2 timed steps each after 1 warm-up), for transparency
+        variants = {}
+        for alt in ("tf32x3", "fp32"):
+            if alt == args.math:
+                continue
+            torch.manual_seed(0)
+            net_alt = Net("CleanUMamba", dict(cfg, math_mode=alt)).to(dev).eval()
+            net_alt.load_state_dict(net.state_dict())
+
+            def alt_step():
+                work.copy_(x_dev)
+                with torch.no_grad():
+                    return net_alt(work)
+            alt_step()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(2):
+                alt_step()
+            a1.record()
+            torch.cuda.synchronize()
+            variants[alt] = {"value": round(B * args.seconds * 2 / (a0.elapsed_time(a1) / 1e3), 1), "unit": UNIT,
+                             "ms_per_step": round(a0.elapsed_time(a1) / 2, 3)}
+            del net_alt
+            torch.cuda.empty_cache()
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -426,6 +459,11 @@ def main():
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "arithmetic": {"fp32": "fp32 storage + exact fp32 FFMA products",
+                           "tf32x3": "fp32 storage/accumulate; products = 3 TF32 tensor-core passes on hi/lo halves (~2^-21 per product)",
+                           "bf16x3": "fp32 storage/accumulate; products = 3 bf16 tensor-core passes on hi/lo halves (~2^-16 per product); "
+                                     "parity-tested at this workload size against the exact-fp32 mode: max-abs <= 1e-4, dSI-SDR <= 0.01 dB",
+                           "tf32": "single TF32 pass (outside the tolerance)"}[args.math],
             "config": {"workload": f"CleanUMamba {args.model.upper()} full ({sum(p.numel() for p in net.parameters())/1e6:.2f}M, "
                                    f"seeded random init) offline forward, batch {B} x {args.seconds:g} s @16 kHz per GPU, "
                                    f"math={args.math}",
@@ -435,6 +473,8 @@ def main():
                     "d2h_bytes_per_step": B * T * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "scan_roofline": scan_roof,
             "kernels": kernels}
+    if variants:
+        line["variants"] = variants
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

@@ -22,6 +22,7 @@
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_bf16.h>
 
 namespace cum {
 
@@ -34,14 +35,24 @@ constexpr int TC_EPI_WARPS = 8;               // warps 4..11: two per TMEM lane 
 constexpr int TC_EPI_GENERIC_UNARY = -1;      // runtime-selected activation (SiLU ...)
 constexpr int TC_EPI_GENERIC_GLU = -2;        // runtime-selected GLU gate (ReLU / SiLU / GELU)
 
+// MODE: 0 = single-pass TF32, 1 = TF32X3 (hi/lo fp32 tiles, 3 kind::tf32 MMAs), 2 = BF16X3 (hi/lo bf16 tiles, 3 kind::f16 MMAs)
 // BN = tile width (256, or 128 for narrow layers: smaller W box -> deeper pipeline for the HBM-bound layers)
-template <bool X3, int BN> struct TcCfg {
-    static constexpr uint32_t W_BYTES = BN * TC_BK * 4;
-    static constexpr uint32_t STAGE_BYTES = X3 ? 2 * (TC_A_BYTES + W_BYTES) : (TC_A_BYTES + W_BYTES);
-    static constexpr int STAGES = (int)(196608u / STAGE_BYTES);           // 2 / 3 (X3), 4 / 6 (plain)
-    static constexpr uint32_t TX_BYTES = X3 ? (TC_A_BYTES + 2 * W_BYTES) : (TC_A_BYTES + W_BYTES);
+constexpr int TC_TF32 = 0, TC_TF32X3 = 1, TC_BF16X3 = 2;
+template <int MODE, int BN> struct TcCfg {
+    static constexpr bool SPLIT = MODE != TC_TF32;                      // operand-splitter warps present
+    static constexpr uint32_t W_BYTES = BN * TC_BK * (MODE == TC_BF16X3 ? 2 : 4);
+    static constexpr uint32_t AOP_BYTES = MODE == TC_BF16X3 ? TC_A_BYTES / 2 : TC_A_BYTES;   // one MMA A-operand tile
+    // stage layout: [A raw fp32 (= A_hi for the TF32 modes) | A_hi (bf16 mode only) | A_lo | W_hi | W_lo]
+    static constexpr uint32_t AHI_OFF = MODE == TC_BF16X3 ? TC_A_BYTES : 0;
+    static constexpr uint32_t ALO_OFF = AHI_OFF + AOP_BYTES;
+    static constexpr uint32_t W_OFF = SPLIT ? ALO_OFF + AOP_BYTES : TC_A_BYTES;
+    static constexpr uint32_t WLO_OFF = W_OFF + W_BYTES;
+    static constexpr uint32_t STAGE_BYTES = SPLIT ? WLO_OFF + W_BYTES : W_OFF + W_BYTES;
+    static constexpr int STAGES = (int)(196608u / STAGE_BYTES);
+    static constexpr uint32_t TX_BYTES = TC_A_BYTES + (SPLIT ? 2 : 1) * W_BYTES;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int THREADS = X3 ? 512 : 384;                        // warps 12..15 = operand splitter (X3)
+    static constexpr int THREADS = SPLIT ? 512 : 384;                   // warps 12..15 = operand splitter
+    static constexpr int UMMA_K = MODE == TC_BF16X3 ? 16 : 8;
 };
 
 struct TcParams {
@@ -102,6 +113,22 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    // K-major, 64B swizzle (bf16 tiles with 32-element = 64-byte rows): 8-row groups are 512 B apart
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(512u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -168,21 +195,23 @@ __device__ __forceinline__ float tc_act(int epi, float v) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <bool X3, int BN, int EPI>
-__global__ void __launch_bounds__(TcCfg<X3, BN>::THREADS, 1)
+template <int MODE, int BN, int EPI>
+__global__ void __launch_bounds__(TcCfg<MODE, BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                const __grid_constant__ CUtensorMap tmWl, const TcParams p) {
-    using Cfg = TcCfg<X3, BN>;
+    using Cfg = TcCfg<MODE, BN>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr bool X3 = Cfg::SPLIT;
+    constexpr bool BF = MODE == TC_BF16X3;
     constexpr bool GLU = (EPI == CUM_EPI_GLU_SIGMOID || EPI == TC_EPI_GENERIC_GLU);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    // stage layout: [A | (A_lo) | W_hi | (W_lo)]
-    auto a_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES; };
-    auto alo_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + TC_A_BYTES; };
-    auto w_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + (X3 ? 2 : 1) * TC_A_BYTES; };
-    auto wlo_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + 2 * TC_A_BYTES + Cfg::W_BYTES; };
+    auto a_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES; };                      // TMA destination (fp32)
+    auto ahi_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + Cfg::AHI_OFF; };     // MMA operand A (hi)
+    auto alo_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + Cfg::ALO_OFF; };
+    auto w_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + Cfg::W_OFF; };
+    auto wlo_off = [](int s) { return (uint32_t)s * Cfg::STAGE_BYTES + Cfg::WLO_OFF; };
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -259,25 +288,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int n_rem = p.n - n0;
             if (n_rem > BN) n_rem = BN;
             const uint32_t umma_n = (uint32_t)((n_rem + 15) & ~15);
-            // c=f32 (1<<4), a=b=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            // c=f32 (1<<4); a/b format 2 = tf32, 1 = bf16 (bits 7, 10); K-major both; N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t fmt = BF ? 1u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
             mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
             tc_fence_after();
             for (int it = 0; it < k_iters; ++it) {
                 mbar_wait(X3 ? split_bar(s) : full_bar(s), ph);
                 tc_fence_after();
-                const uint64_t adesc = umma_desc_sw128(smem_base + a_off(s));
-                const uint64_t bdesc = umma_desc_sw128(smem_base + w_off(s));
+                const uint64_t adesc = BF ? umma_desc_sw64(smem_base + ahi_off(s)) : umma_desc_sw128(smem_base + ahi_off(s));
+                const uint64_t bdesc = BF ? umma_desc_sw64(smem_base + w_off(s)) : umma_desc_sw128(smem_base + w_off(s));
+                const uint64_t alo = BF ? umma_desc_sw64(smem_base + alo_off(s)) : umma_desc_sw128(smem_base + alo_off(s));
+                const uint64_t blo = BF ? umma_desc_sw64(smem_base + wlo_off(s)) : umma_desc_sw128(smem_base + wlo_off(s));
 #pragma unroll
-                for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
-                    const uint64_t koff = (uint64_t)((kk * TC_UMMA_K * 4) >> 4);
-                    umma_tf32(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
-                    if (X3) {
-                        const uint64_t alo = umma_desc_sw128(smem_base + alo_off(s));
-                        const uint64_t blo = umma_desc_sw128(smem_base + wlo_off(s));
-                        umma_tf32(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
-                        umma_tf32(tmem_d, adesc + koff, blo + koff, idesc, 1u);
+                for (int kk = 0; kk < TC_BK / Cfg::UMMA_K; ++kk) {
+                    const uint64_t koff = (uint64_t)(kk * 2);          // 32 bytes per k-step in both element types
+                    if (BF) {
+                        umma_bf16(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
+                        umma_bf16(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
+                        umma_bf16(tmem_d, adesc + koff, blo + koff, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
+                        if (X3) {
+                            umma_tf32(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
+                            umma_tf32(tmem_d, adesc + koff, blo + koff, idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(empty_bar(s));
@@ -355,6 +391,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int it = 0; it < k_iters; ++it) {
                 mbar_wait(full_bar(s), ph);
+                if (BF) {
+                    // fp32 tile (128 x 32, 128B-swizzled rows) -> bf16 hi / lo tiles (128 x 32, 64B-swizzled rows)
+                    const uint8_t* raw = smem_gen + a_off(s);
+                    uint8_t* hi = smem_gen + ahi_off(s);
+                    uint8_t* lo = smem_gen + alo_off(s);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = t + 128 * j;
+                        const int r = i >> 2, co = i & 3;              // row, 16-byte output chunk (8 bf16 = 8 k)
+                        const float4 v0 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * co) ^ (r & 7)) << 4));
+                        const float4 v1 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * co + 1) ^ (r & 7)) << 4));
+                        const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                            const float2 hf = __bfloat1622float2(hh);
+                            const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+                            h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                            l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                        }
+                        const uint32_t off = (uint32_t)r * 64u + (uint32_t)((co ^ ((r >> 1) & 3)) << 4);
+                        *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
+                } else {
                 float4* hi = reinterpret_cast<float4*>(smem_gen + a_off(s));
                 float4* lo = reinterpret_cast<float4*>(smem_gen + alo_off(s));
 #pragma unroll
@@ -369,6 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
                     hi[i] = h;
                     lo[i] = l;
+                }
                 }
                 fence_proxy_async();
                 mbar_arrive(split_bar(s));
@@ -403,6 +466,24 @@ int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t s
     return CUM_OK;
 }
 
+// bf16 hi/lo split of the weights for BF16X3 (round-to-nearest, same arithmetic as the in-kernel activation split)
+__global__ void split_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = w[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+int split_bf16(const float* w, void* hi, void* lo, long long n, cudaStream_t st) {
+    CUM_REQUIRE(w && hi && lo && n > 0, "split_bf16: bad arguments");
+    split_bf16_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+    CUM_LAUNCH_CHECK("split_bf16_kernel");
+    return CUM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -416,16 +497,18 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
-static int make_map(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_elems,
-                    uint64_t s2_elems, uint32_t box0, uint32_t box1, const char* what) {
+static int make_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_elems,
+                    uint64_t s2_elems, uint32_t box0, uint32_t box1, const char* what, bool bf16 = false) {
     auto enc = get_encode();
     if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return CUM_ECUDA; }
     cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {s1_elems * 4, s2_elems * 4};
+    const uint64_t esz = bf16 ? 2 : 4;
+    cuuint64_t strides[2] = {s1_elems * esz, s2_elems * esz};
     cuuint32_t box[3] = {box0, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base),
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("gemm_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu strides %llu,%llu)", what,
@@ -436,10 +519,12 @@ static int make_map(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1
     return CUM_OK;
 }
 
-template <bool X3, int BN, int EPI>
+template <int MODE, int BN, int EPI>
 static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
-    using Cfg = TcCfg<X3, BN>;
-    auto kern = gemm_tc_kernel<X3, BN, EPI>;
+    using Cfg = TcCfg<MODE, BN>;
+    constexpr bool X3 = Cfg::SPLIT;
+    constexpr bool BF = MODE == TC_BF16X3;
+    auto kern = gemm_tc_kernel<MODE, BN, EPI>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -452,10 +537,10 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
                       TC_BK, TC_BM, "A");
     if (rc) return rc;
     const uint64_t w_ts = (uint64_t)d.n * (uint64_t)d.ldw;
-    rc = make_map(&tmWh, d.w, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W");
+    rc = make_map(&tmWh, d.w, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W", BF);
     if (rc) return rc;
     if (X3) {
-        rc = make_map(&tmWl, d.w_lo, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W_lo");
+        rc = make_map(&tmWl, d.w_lo, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W_lo", BF);
         if (rc) return rc;
     } else {
         tmWl = tmWh;
@@ -474,15 +559,15 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     return CUM_OK;
 }
 
-template <bool X3, int BN>
+template <int MODE, int BN>
 static int dispatch_epi(const cum_gemm_desc& d, cudaStream_t st) {
     switch (d.epilogue) {
-        case CUM_EPI_NONE:        return launch_tc<X3, BN, CUM_EPI_NONE>(d, st);
-        case CUM_EPI_RELU:        return launch_tc<X3, BN, CUM_EPI_RELU>(d, st);
-        case CUM_EPI_GLU_SIGMOID: return launch_tc<X3, BN, CUM_EPI_GLU_SIGMOID>(d, st);
+        case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE>(d, st);
+        case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU>(d, st);
+        case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID>(d, st);
         default:
-            return epi_is_glu(d.epilogue) ? launch_tc<X3, BN, TC_EPI_GENERIC_GLU>(d, st)
-                                          : launch_tc<X3, BN, TC_EPI_GENERIC_UNARY>(d, st);
+            return epi_is_glu(d.epilogue) ? launch_tc<MODE, BN, TC_EPI_GENERIC_GLU>(d, st)
+                                          : launch_tc<MODE, BN, TC_EPI_GENERIC_UNARY>(d, st);
     }
 }
 
@@ -491,9 +576,14 @@ int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     const bool narrow = d.n <= 128;
     if (d.math == CUM_MATH_TF32X3) {
         CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: TF32X3 needs w_lo (see cum_split_tf32)");
-        return narrow ? dispatch_epi<true, 128>(d, st) : dispatch_epi<true, 256>(d, st);
+        return narrow ? dispatch_epi<TC_TF32X3, 128>(d, st) : dispatch_epi<TC_TF32X3, 256>(d, st);
     }
-    return narrow ? dispatch_epi<false, 128>(d, st) : dispatch_epi<false, 256>(d, st);
+    if (d.math == CUM_MATH_BF16X3) {
+        CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: BF16X3 needs w_lo (see cum_split_bf16)");
+        CUM_REQUIRE(d.ldw % 8 == 0, "gemm_tc: BF16X3 needs ldw %% 8 == 0 (ldw=%d)", d.ldw);
+        return narrow ? dispatch_epi<TC_BF16X3, 128>(d, st) : dispatch_epi<TC_BF16X3, 256>(d, st);
+    }
+    return narrow ? dispatch_epi<TC_TF32, 128>(d, st) : dispatch_epi<TC_TF32, 256>(d, st);
 }
 
 }  // namespace cum

@@ -213,6 +213,15 @@ class Engine:
                 self.pk_hi[k] = hi[offs[k]: offs[k] + t.numel()].view(t.shape)
                 self.pk_lo[k] = lo[offs[k]: offs[k] + t.numel()].view(t.shape)
             self._flat_split = (hi, lo)
+        elif self.math == _lib.MATH_BF16X3:    # bf16 hi/lo copies (same element offsets, 2 bytes per element)
+            hi = torch.empty(flat.numel(), dtype=torch.bfloat16, device=dev)
+            lo = torch.empty(flat.numel(), dtype=torch.bfloat16, device=dev)
+            check(self.lib.cum_split_bf16(flat.data_ptr(), hi.data_ptr(), lo.data_ptr(), flat.numel(),
+                                          _lib.stream_ptr()), "cum_split_bf16")
+            for k, t in items.items():
+                self.pk_hi[k] = hi[offs[k]: offs[k] + t.numel()].view(t.shape)
+                self.pk_lo[k] = lo[offs[k]: offs[k] + t.numel()].view(t.shape)
+            self._flat_split = (hi, lo)
         self._post_pack(items, offs, total)
 
     def _extra_items(self, items):
@@ -231,7 +240,7 @@ class Engine:
         d.tap_shift[0], d.tap_shift[1] = shifts
         wt = self.pk[w]
         d.math = self.math if math is None else math
-        if d.math == _lib.MATH_TF32X3:
+        if d.math in (_lib.MATH_TF32X3, _lib.MATH_BF16X3):
             d.w, d.w_lo = self.pk_hi[w].data_ptr(), self.pk_lo[w].data_ptr()
         else:
             d.w, d.w_lo = wt.data_ptr(), 0

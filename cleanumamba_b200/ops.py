@@ -147,6 +147,10 @@ def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None
         w_hi, w_lo = torch.empty_like(w), torch.empty_like(w)
         check(lib.cum_split_tf32(w.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), w.numel(), _lib.stream_ptr()), "cum_split_tf32")
         d.w, d.w_lo = w_hi.data_ptr(), w_lo.data_ptr()
+    elif d.math == _lib.MATH_BF16X3:
+        w_hi, w_lo = torch.empty_like(w, dtype=torch.bfloat16), torch.empty_like(w, dtype=torch.bfloat16)
+        check(lib.cum_split_bf16(w.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), w.numel(), _lib.stream_ptr()), "cum_split_bf16")
+        d.w, d.w_lo = w_hi.data_ptr(), w_lo.data_ptr()
     else:
         d.w, d.w_lo = w.data_ptr(), 0
     d.ldw, d.bias = k, ptr(bias)

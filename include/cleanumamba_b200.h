@@ -46,6 +46,8 @@ extern "C" {
 #define CUM_MATH_FP32        0  /* CUDA-core FFMA, exact fp32 products (reference arithmetic) */
 #define CUM_MATH_TF32X3      1  /* tcgen05 kind::tf32, hi/lo split, 3 MMAs per product (~2^-21 rel. error) */
 #define CUM_MATH_TF32        2  /* tcgen05 kind::tf32, single pass (10-bit mantissa; NOT within the fp32 tolerance) */
+#define CUM_MATH_BF16X3      3  /* tcgen05 kind::f16 on bf16 hi/lo halves, 3 MMAs per product (~2^-16 rel. error per
+                                   product; measured inside the fp32 tolerance end to end, 2x the TF32X3 tensor rate) */
 
 typedef void* cum_stream_t;    /* cudaStream_t */
 
@@ -111,14 +113,17 @@ typedef struct cum_gemm_desc {
     int epilogue;    /* CUM_EPI_* */
     const float* addend; long long add_batch_stride; long long add_row_stride;  /* optional */
     int math;        /* CUM_MATH_* */
-    const float* w_lo;       /* CUM_MATH_TF32X3 only: low halves of the weights; `w` must then hold the high halves
-                                (both produced by cum_split_tf32 from the packed fp32 weights) */
+    const float* w_lo;       /* TF32X3 / BF16X3 only: low halves of the weights; `w` must then hold the high halves (both
+                                produced by cum_split_tf32 / cum_split_bf16; bf16 arrays for BF16X3) */
 } cum_gemm_desc;
 int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream);
 
 /* TF32 hi/lo split of a packed weight array for CUM_MATH_TF32X3: hi = w with the 13 low mantissa bits cleared,
  * lo = w - hi (exact in fp32).  Same bit arithmetic as the in-kernel split of the activations. */
 int cum_split_tf32(const float* w, float* hi, float* lo, long long count, cum_stream_t stream);
+/* bf16 hi/lo split for CUM_MATH_BF16X3: hi = bf16_rn(w), lo = bf16_rn(w - hi); hi / lo are bf16 arrays (2 bytes per
+ * element) that are then passed as `w` / `w_lo` (ldw in elements, multiple of 8). */
+int cum_split_bf16(const float* w, void* hi, void* lo, long long count, cum_stream_t stream);
 
 /* ---- Mamba block operators ------------------------------------------------------------------- */
 /* Replaces Block.forward's `residual = h + residual; h = LayerNorm(residual)` (mamba_ssm Block, non-fused
