@@ -279,10 +279,11 @@ def main():
     ap.add_argument("--model", default="e8", choices=list(CONFIGS))
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--seconds", type=float, default=10.0)
-    ap.add_argument("--math", default=os.environ.get("CUM_MATH", "bf16x3"), choices=["fp32", "tf32x3", "bf16x3", "tf32"],
+    ap.add_argument("--math", default=os.environ.get("CUM_MATH", "f16x3"), choices=["fp32", "tf32x3", "bf16x3", "f16x3", "tf32"],
                     help="arithmetic of the contractions (activations / accumulation / storage are fp32 in every mode): "
-                         "bf16x3 (default) and tf32x3 = tcgen05 3-pass split products, both parity-tested inside the fp32 "
-                         "tolerance of BASELINE.json (max-abs <= 1e-4, dSI-SDR <= 0.01 dB); fp32 = exact CUDA-core FFMA")
+                         "f16x3 (default) / tf32x3 = tcgen05 3-pass split products with 22 mantissa bits, parity-tested inside the "
+                         "fp32 tolerance of BASELINE.json (max-abs <= 1e-4, dSI-SDR <= 0.01 dB); bf16x3 = 16-17 bits (marginal at "
+                         "full-scale amplitude); fp32 = exact CUDA-core FFMA")
     ap.add_argument("--no-variants", action="store_true", help="skip the short tf32x3 / fp32 comparison runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="offline", choices=["offline", "stream", "train"],
@@ -402,13 +403,13 @@ def main():
                 "frac": round(achieved / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
                 "share_of_step": round(gem["ms"] / total_kernel_ms, 4) if total_kernel_ms else None,
                 "launches_per_step": gem["launches"] // args.steps,
-                "mma_passes": 3 if args.math in ("tf32x3", "bf16x3") else 1,
+                "mma_passes": 3 if args.math in ("tf32x3", "bf16x3", "f16x3") else 1,
                 "note": ("achieved = ALGORITHMIC flops (2*M*N*K per contraction) / CUDA-event kernel time; tf32x3 issues 3 "
                          "kind::tf32 MMAs per product (TF32 pipe = 1/2 of the bf16 peak used as denominator), so the pipe-level "
                          "rate is 3x achieved; ncu sm__pipe_tensor_cycles_active = 70-76 % on the K>=1024 layers "
                          "(profiles/r01_ncu_full_gemm_tf32x3.md)") if args.math == "tf32x3" else
                         ("achieved = ALGORITHMIC flops / CUDA-event kernel time; bf16x3 issues 3 kind::f16 (bf16) MMAs per product, "
-                         "so the tensor-pipe rate is 3x achieved (K>=1024 layers: ~1.25 PFLOP/s of bf16 MMA work)") if args.math == "bf16x3" else None}
+                         "so the tensor-pipe rate is 3x achieved (K>=1024 layers: ~1.25 PFLOP/s of 16-bit MMA work)") if args.math in ("bf16x3", "f16x3") else None}
     scan = prof.get("selective_scan")
     scan_roof = None
     if scan:
@@ -426,7 +427,7 @@ def main():
     if world == 1 and not args.no_variants and args.mode == "offline":
         # the other arithmetic modes on the same workload (2 timed steps each after 1 warm-up), for transparency
         variants = {}
-        for alt in ("tf32x3", "fp32"):
+        for alt in ("tf32x3", "bf16x3", "fp32"):
             if alt == args.math:
                 continue
             torch.manual_seed(0)
@@ -463,6 +464,9 @@ def main():
                            "tf32x3": "fp32 storage/accumulate; products = 3 TF32 tensor-core passes on hi/lo halves (~2^-21 per product)",
                            "bf16x3": "fp32 storage/accumulate; products = 3 bf16 tensor-core passes on hi/lo halves (~2^-16 per product); "
                                      "parity-tested at this workload size against the exact-fp32 mode: max-abs <= 1e-4, dSI-SDR <= 0.01 dB",
+                           "f16x3": "fp32 storage/accumulate; products = 3 fp16 tensor-core passes on hi/lo halves (11+11 bits, ~2^-21 per "
+                                    "product, same accuracy class as tf32x3 at the bf16 tensor rate; weights carry a power-of-two scale, "
+                                    "activations convert with saturation); parity-tested at this workload size against the exact-fp32 mode",
                            "tf32": "single TF32 pass (outside the tolerance)"}[args.math],
             "config": {"workload": f"CleanUMamba {args.model.upper()} full ({sum(p.numel() for p in net.parameters())/1e6:.2f}M, "
                                    f"seeded random init) offline forward, batch {B} x {args.seconds:g} s @16 kHz per GPU, "

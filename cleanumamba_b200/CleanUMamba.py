@@ -34,7 +34,7 @@ class CleanUMamba(nn.Module):
                  tsfm_n_layers=3, tsfm_n_head=8, tsfm_d_model=512, tsfm_d_inner=2048, fused_add_norm=False,
                  use_fast_path=False, rms_norm=False, mamba_s4=False, LSTM=False, mamba_v2=False,
                  residual_projection=False, norm_epsilon: float = 1e-5, normalize_input=True, device=None,
-                 dtype=None, math_mode="tf32x3"):
+                 dtype=None, math_mode="f16x3"):
         super().__init__()
         assert glu_activation in ("Sigmoid", "ReLU", "SiLU", "GELU"), f"glu_activation={glu_activation} not supported"
         for flag, name in ((mamba_s4, "mamba_s4"), (LSTM, "LSTM"), (mamba_v2, "mamba_v2"),
@@ -54,8 +54,12 @@ class CleanUMamba(nn.Module):
         self.glu_activation = glu_activation
         self.norm_epsilon = norm_epsilon
         self.dtype = dtype
-        # arithmetic of the dense contractions: "tf32x3" (default: tcgen05 tensor cores, 3-pass TF32 split, inside the
-        # fp32 tolerance of BASELINE.json) | "fp32" (exact CUDA-core FFMA) | "tf32" (single pass, NOT inside the tolerance)
+        # arithmetic of the dense contractions (activations / accumulators / storage are fp32 in every mode):
+        #   "f16x3"  (default) tcgen05 tensor cores, 3 fp16 passes on hi/lo halves: 22-bit products at the bf16 tensor rate;
+        #            inside the fp32 tolerance of BASELINE.json; training maps it to "tf32x3" (gradients underflow fp16)
+        #   "tf32x3" 3 TF32 passes: same accuracy class with fp32 exponent range, half the tensor rate
+        #   "bf16x3" 3 bf16 passes: 16-17-bit products (marginal: 1.1e-4 at full-scale amplitude)
+        #   "fp32"   exact CUDA-core FFMA;  "tf32" single pass (NOT inside the tolerance)
         self.math_mode = math_mode
 
         self.encoder, self.decoder = nn.ModuleList(), nn.ModuleList()

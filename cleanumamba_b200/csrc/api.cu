@@ -100,6 +100,7 @@ int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream) {
         case CUM_MATH_FP32: return gemm_simt_fwd(*desc, (cudaStream_t)stream);
         case CUM_MATH_TF32X3:
         case CUM_MATH_BF16X3:
+        case CUM_MATH_F16X3:
         case CUM_MATH_TF32: return gemm_tc_fwd(*desc, (cudaStream_t)stream);
         default: set_error("gemm: unknown math mode %d", desc->math); return CUM_EINVAL;
     }
@@ -111,6 +112,10 @@ int cum_split_tf32(const float* w, float* hi, float* lo, long long count, cum_st
 
 int cum_split_bf16(const float* w, void* hi, void* lo, long long count, cum_stream_t stream) {
     return split_bf16(w, hi, lo, count, (cudaStream_t)stream);
+}
+
+int cum_split_f16(const float* w, void* hi, void* lo, long long count, float scale, cum_stream_t stream) {
+    return split_f16(w, hi, lo, count, scale, (cudaStream_t)stream);
 }
 
 int cum_ln_residual_fwd(const float* h, const float* residual_in, float* residual_out, float* normed,

@@ -80,6 +80,7 @@ int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t st);
 int split_bf16(const float* w, void* hi, void* lo, long long n, cudaStream_t st);
+int split_f16(const float* w, void* hi, void* lo, long long n, float scale, cudaStream_t st);
 int ln_residual_fwd(const float* h, const float* residual_in, float* residual_out, float* normed,
                     const float* gamma, const float* beta, float eps, long long rows, int c, int c_pad,
                     cudaStream_t st);

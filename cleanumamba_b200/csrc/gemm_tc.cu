@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace cum {
 
@@ -35,15 +36,17 @@ constexpr int TC_EPI_WARPS = 8;               // warps 4..11: two per TMEM lane 
 constexpr int TC_EPI_GENERIC_UNARY = -1;      // runtime-selected activation (SiLU ...)
 constexpr int TC_EPI_GENERIC_GLU = -2;        // runtime-selected GLU gate (ReLU / SiLU / GELU)
 
-// MODE: 0 = single-pass TF32, 1 = TF32X3 (hi/lo fp32 tiles, 3 kind::tf32 MMAs), 2 = BF16X3 (hi/lo bf16 tiles, 3 kind::f16 MMAs)
+// MODE: 0 = single-pass TF32, 1 = TF32X3 (hi/lo fp32 tiles, 3 kind::tf32 MMAs), 2 / 3 = BF16X3 / F16X3 (hi/lo 16-bit tiles,
+// 3 kind::f16 MMAs at twice the TF32 rate; F16X3 keeps 22 mantissa bits, its weights carry a power-of-two scale undone in the epilogue)
 // BN = tile width (256, or 128 for narrow layers: smaller W box -> deeper pipeline for the HBM-bound layers)
-constexpr int TC_TF32 = 0, TC_TF32X3 = 1, TC_BF16X3 = 2;
+constexpr int TC_TF32 = 0, TC_TF32X3 = 1, TC_BF16X3 = 2, TC_F16X3 = 3;   // F16X3: like BF16X3 with fp16 halves (11+11 bits)
 template <int MODE, int BN> struct TcCfg {
     static constexpr bool SPLIT = MODE != TC_TF32;                      // operand-splitter warps present
-    static constexpr uint32_t W_BYTES = BN * TC_BK * (MODE == TC_BF16X3 ? 2 : 4);
-    static constexpr uint32_t AOP_BYTES = MODE == TC_BF16X3 ? TC_A_BYTES / 2 : TC_A_BYTES;   // one MMA A-operand tile
+    static constexpr bool HALF = (MODE == TC_BF16X3 || MODE == TC_F16X3);    // 16-bit MMA operands
+    static constexpr uint32_t W_BYTES = BN * TC_BK * (HALF ? 2 : 4);
+    static constexpr uint32_t AOP_BYTES = HALF ? TC_A_BYTES / 2 : TC_A_BYTES;   // one MMA A-operand tile
     // stage layout: [A raw fp32 (= A_hi for the TF32 modes) | A_hi (bf16 mode only) | A_lo | W_hi | W_lo]
-    static constexpr uint32_t AHI_OFF = MODE == TC_BF16X3 ? TC_A_BYTES : 0;
+    static constexpr uint32_t AHI_OFF = HALF ? TC_A_BYTES : 0;
     static constexpr uint32_t ALO_OFF = AHI_OFF + AOP_BYTES;
     static constexpr uint32_t W_OFF = SPLIT ? ALO_OFF + AOP_BYTES : TC_A_BYTES;
     static constexpr uint32_t WLO_OFF = W_OFF + W_BYTES;
@@ -52,7 +55,7 @@ template <int MODE, int BN> struct TcCfg {
     static constexpr uint32_t TX_BYTES = TC_A_BYTES + (SPLIT ? 2 : 1) * W_BYTES;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int THREADS = SPLIT ? 512 : 384;                   // warps 12..15 = operand splitter
-    static constexpr int UMMA_K = MODE == TC_BF16X3 ? 16 : 8;
+    static constexpr int UMMA_K = HALF ? 16 : 8;
 };
 
 struct TcParams {
@@ -61,6 +64,7 @@ struct TcParams {
     const float* bias;
     float* c; long long c_bs, c_rs;
     const float* addend; long long add_bs, add_rs;
+    float acc_scale;          // F16X3: 2^-k undoing the weight pre-scale (1 otherwise)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -154,6 +158,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// packed fp32 -> fp16x2 with saturation to +-65504 (first argument lands in the low half, like __floats2half2_rn)
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+
 // 16 lanes x 64 columns: thread t gets rows (t/4, t/4+8) x columns 8k + 2(t%4) + {0,1}:
 //   r[4k+0], r[4k+1] -> row t/4 ; r[4k+2], r[4k+3] -> row t/4 + 8     (CuTe SM100_TMEM_LOAD_16dp256b8x layout)
 __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float* v) {
@@ -202,7 +213,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     using Cfg = TcCfg<MODE, BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool X3 = Cfg::SPLIT;
-    constexpr bool BF = MODE == TC_BF16X3;
+    constexpr bool BF = Cfg::HALF;               // 16-bit operand tiles (bf16 or fp16)
+    constexpr bool F16 = MODE == TC_F16X3;
     constexpr bool GLU = (EPI == CUM_EPI_GLU_SIGMOID || EPI == TC_EPI_GENERIC_GLU);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -289,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n_rem > BN) n_rem = BN;
             const uint32_t umma_n = (uint32_t)((n_rem + 15) & ~15);
             // c=f32 (1<<4); a/b format 2 = tf32, 1 = bf16 (bits 7, 10); K-major both; N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t fmt = BF ? 1u : 2u;
+            const uint32_t fmt = F16 ? 0u : (BF ? 1u : 2u);       // 0 = f16, 1 = bf16, 2 = tf32
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
             mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
@@ -361,8 +373,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int k = 0; k < 8; ++k) {
                             const int n = n0 + c0 + 8 * k + 2 * tq;
                             if (n >= p.n) break;
-                            const float x0 = v[4 * k + 2 * rh + 0] + bv[k].x;
-                            const float x1 = v[4 * k + 2 * rh + 1] + bv[k].y;
+                            const float x0 = F16 ? fmaf(v[4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[4 * k + 2 * rh + 0] + bv[k].x;
+                            const float x1 = F16 ? fmaf(v[4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[4 * k + 2 * rh + 1] + bv[k].y;
                             if (GLU) {
                                 float o = x0 * tc_gate<EPI>(p.epi, x1);
                                 const int oc = n >> 1;
@@ -406,11 +418,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint32_t h[4], l[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                            const float2 hf = __bfloat1622float2(hh);
-                            const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
-                            h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-                            l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                            if (F16) {
+                                // saturating conversion (cvt.rn.satfinite): |a| > 65504 clamps instead of becoming inf, and the
+                                // low half then absorbs up to another 65504 of the remainder
+                                h[e] = cvt_f16x2_sat(f[2 * e], f[2 * e + 1]);
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
+                                l[e] = cvt_f16x2_sat(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+                            } else {
+                                const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                                const float2 hf = __bfloat1622float2(hh);
+                                const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+                                h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                                l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                            }
                         }
                         const uint32_t off = (uint32_t)r * 64u + (uint32_t)((co ^ ((r >> 1) & 3)) << 4);
                         *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -484,6 +504,24 @@ int split_bf16(const float* w, void* hi, void* lo, long long n, cudaStream_t st)
     return CUM_OK;
 }
 
+// fp16 hi/lo split of (scale * w) for F16X3; scale is a power of two chosen by the caller so that max|scale*w| ~ 8..16
+__global__ void split_f16_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, long long n, float scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = fminf(fmaxf(w[i] * scale, -65504.f), 65504.f);
+        const __half h = __float2half_rn(v);
+        hi[i] = h;
+        lo[i] = __float2half_rn(v - __half2float(h));
+    }
+}
+
+int split_f16(const float* w, void* hi, void* lo, long long n, float scale, cudaStream_t st) {
+    CUM_REQUIRE(w && hi && lo && n > 0 && scale > 0.f, "split_f16: bad arguments");
+    split_f16_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w, (__half*)hi, (__half*)lo, n, scale);
+    CUM_LAUNCH_CHECK("split_f16_kernel");
+    return CUM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -523,7 +561,7 @@ template <int MODE, int BN, int EPI>
 static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     using Cfg = TcCfg<MODE, BN>;
     constexpr bool X3 = Cfg::SPLIT;
-    constexpr bool BF = MODE == TC_BF16X3;
+    constexpr bool BF = Cfg::HALF;
     auto kern = gemm_tc_kernel<MODE, BN, EPI>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -551,6 +589,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.m_tiles = (int)cdiv(d.m, TC_BM); p.n_tiles = (int)cdiv(d.n, BN); p.k_blocks = (int)cdiv(d.k, TC_BK);
     p.bias = d.bias; p.c = d.c; p.c_bs = d.c_batch_stride; p.c_rs = d.c_row_stride;
     p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
+    p.acc_scale = (MODE == TC_F16X3) ? d.acc_scale : 1.0f;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
     CUM_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());
@@ -582,6 +621,12 @@ int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
         CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: BF16X3 needs w_lo (see cum_split_bf16)");
         CUM_REQUIRE(d.ldw % 8 == 0, "gemm_tc: BF16X3 needs ldw %% 8 == 0 (ldw=%d)", d.ldw);
         return narrow ? dispatch_epi<TC_BF16X3, 128>(d, st) : dispatch_epi<TC_BF16X3, 256>(d, st);
+    }
+    if (d.math == CUM_MATH_F16X3) {
+        CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: F16X3 needs w_lo (see cum_split_f16)");
+        CUM_REQUIRE(d.ldw % 8 == 0, "gemm_tc: F16X3 needs ldw %% 8 == 0 (ldw=%d)", d.ldw);
+        CUM_REQUIRE(d.acc_scale > 0.f, "gemm_tc: F16X3 needs acc_scale = 1 / (weight scale passed to cum_split_f16)");
+        return narrow ? dispatch_epi<TC_F16X3, 128>(d, st) : dispatch_epi<TC_F16X3, 256>(d, st);
     }
     return narrow ? dispatch_epi<TC_TF32, 128>(d, st) : dispatch_epi<TC_TF32, 256>(d, st);
 }

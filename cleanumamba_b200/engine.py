@@ -202,14 +202,29 @@ class Engine:
         self._flat = flat
         self.meta = meta
         self.device = dev
-        self.math = _lib.MATH_BY_NAME[getattr(m, "math_mode", "tf32x3")]
+        self.math = _lib.MATH_BY_NAME[getattr(self, "model_math_override", None) or getattr(m, "math_mode", "f16x3")]
         self.lib = _lib.init(dev)
-        self.pk_hi, self.pk_lo = {}, {}
+        self.pk_hi, self.pk_lo, self.w_scale_inv = {}, {}, {}
         if self.math == _lib.MATH_TF32X3:      # hi/lo copies of the whole packed buffer (only GEMM weights use them)
             hi, lo = torch.empty_like(flat), torch.empty_like(flat)
             check(self.lib.cum_split_tf32(flat.data_ptr(), hi.data_ptr(), lo.data_ptr(), flat.numel(),
                                           _lib.stream_ptr()), "cum_split_tf32")
             for k, t in items.items():
+                self.pk_hi[k] = hi[offs[k]: offs[k] + t.numel()].view(t.shape)
+                self.pk_lo[k] = lo[offs[k]: offs[k] + t.numel()].view(t.shape)
+            self._flat_split = (hi, lo)
+        elif self.math == _lib.MATH_F16X3:     # fp16 hi/lo copies of 2^k * w, k per weight tensor so that max|2^k w| is in [8, 16)
+            hi = torch.empty(flat.numel(), dtype=torch.float16, device=dev)
+            lo = torch.empty(flat.numel(), dtype=torch.float16, device=dev)
+            gemm_keys = [k for k, t in items.items() if t.dim() == 3 or k.endswith((".wg", ".in", ".xp", ".dtw", ".out", "T")) or k in ("t1.w", "t2.w")]
+            amax = torch.stack([items[k].abs().max() for k in gemm_keys]).tolist()          # one host sync at pack time
+            for k, a in zip(gemm_keys, amax):
+                t = items[k]
+                e = int(math.floor(math.log2(8.0 / a))) if a > 0 else 0
+                e = max(-14, min(14, e))
+                self.w_scale_inv[k] = float(2.0 ** -e)
+                check(self.lib.cum_split_f16(flat.data_ptr() + 4 * offs[k], hi.data_ptr() + 2 * offs[k], lo.data_ptr() + 2 * offs[k],
+                                             t.numel(), float(2.0 ** e), _lib.stream_ptr()), "cum_split_f16")
                 self.pk_hi[k] = hi[offs[k]: offs[k] + t.numel()].view(t.shape)
                 self.pk_lo[k] = lo[offs[k]: offs[k] + t.numel()].view(t.shape)
             self._flat_split = (hi, lo)
@@ -240,8 +255,9 @@ class Engine:
         d.tap_shift[0], d.tap_shift[1] = shifts
         wt = self.pk[w]
         d.math = self.math if math is None else math
-        if d.math in (_lib.MATH_TF32X3, _lib.MATH_BF16X3):
+        if d.math in (_lib.MATH_TF32X3, _lib.MATH_BF16X3, _lib.MATH_F16X3):
             d.w, d.w_lo = self.pk_hi[w].data_ptr(), self.pk_lo[w].data_ptr()
+            d.acc_scale = self.w_scale_inv.get(w, 1.0)
         else:
             d.w, d.w_lo = wt.data_ptr(), 0
         d.ldw, d.bias = wt.shape[-1], ptr(bias)

@@ -147,6 +147,13 @@ def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None
         w_hi, w_lo = torch.empty_like(w), torch.empty_like(w)
         check(lib.cum_split_tf32(w.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), w.numel(), _lib.stream_ptr()), "cum_split_tf32")
         d.w, d.w_lo = w_hi.data_ptr(), w_lo.data_ptr()
+    elif d.math == _lib.MATH_F16X3:
+        import math as _m
+        amax = float(w.abs().max())
+        e = max(-14, min(14, int(_m.floor(_m.log2(8.0 / amax))))) if amax > 0 else 0
+        w_hi, w_lo = torch.empty_like(w, dtype=torch.float16), torch.empty_like(w, dtype=torch.float16)
+        check(lib.cum_split_f16(w.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), w.numel(), float(2.0 ** e), _lib.stream_ptr()), "cum_split_f16")
+        d.w, d.w_lo, d.acc_scale = w_hi.data_ptr(), w_lo.data_ptr(), float(2.0 ** -e)
     elif d.math == _lib.MATH_BF16X3:
         w_hi, w_lo = torch.empty_like(w, dtype=torch.bfloat16), torch.empty_like(w, dtype=torch.bfloat16)
         check(lib.cum_split_bf16(w.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), w.numel(), _lib.stream_ptr()), "cum_split_bf16")

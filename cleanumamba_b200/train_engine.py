@@ -20,7 +20,15 @@ from .engine import Engine
 
 
 class TrainEngine(Engine):
-    """Engine with transposed weight copies (for dgrad) and a gradient buffer."""
+    """Engine with transposed weight copies (for dgrad) and a gradient buffer.
+
+    Training never uses the fp16 split ("f16x3"): back-propagated gradients routinely fall below fp16's 6e-5 normal
+    range, so that mode is mapped to "tf32x3" (same 22-bit products, fp32 exponent range)."""
+
+    def _pack(self):
+        if getattr(self.model, "math_mode", None) == "f16x3":
+            self.model_math_override = "tf32x3"
+        super()._pack()
 
     def _extra_items(self, items: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         extra = {}

@@ -47,7 +47,10 @@ extern "C" {
 #define CUM_MATH_TF32X3      1  /* tcgen05 kind::tf32, hi/lo split, 3 MMAs per product (~2^-21 rel. error) */
 #define CUM_MATH_TF32        2  /* tcgen05 kind::tf32, single pass (10-bit mantissa; NOT within the fp32 tolerance) */
 #define CUM_MATH_BF16X3      3  /* tcgen05 kind::f16 on bf16 hi/lo halves, 3 MMAs per product (~2^-16 rel. error per
-                                   product; measured inside the fp32 tolerance end to end, 2x the TF32X3 tensor rate) */
+                                   product; 2x the TF32X3 tensor rate; marginal (1.1e-4) at full-scale amplitude) */
+#define CUM_MATH_F16X3       4  /* tcgen05 kind::f16 on fp16 hi/lo halves (11+11 bits, ~2^-21 per product like TF32X3)
+                                   at the bf16 tensor rate; weights pre-scaled by a power of two (cum_split_f16),
+                                   undone by acc_scale; activations converted with saturation at +-65504 */
 
 typedef void* cum_stream_t;    /* cudaStream_t */
 
@@ -114,7 +117,8 @@ typedef struct cum_gemm_desc {
     const float* addend; long long add_batch_stride; long long add_row_stride;  /* optional */
     int math;        /* CUM_MATH_* */
     const float* w_lo;       /* TF32X3 / BF16X3 only: low halves of the weights; `w` must then hold the high halves (both
-                                produced by cum_split_tf32 / cum_split_bf16; bf16 arrays for BF16X3) */
+                                produced by cum_split_tf32 / cum_split_bf16 / cum_split_f16; 16-bit arrays for *16X3) */
+    float acc_scale;         /* CUM_MATH_F16X3 only: accumulators are multiplied by this before the bias (1 / weight scale) */
 } cum_gemm_desc;
 int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream);
 
@@ -124,6 +128,9 @@ int cum_split_tf32(const float* w, float* hi, float* lo, long long count, cum_st
 /* bf16 hi/lo split for CUM_MATH_BF16X3: hi = bf16_rn(w), lo = bf16_rn(w - hi); hi / lo are bf16 arrays (2 bytes per
  * element) that are then passed as `w` / `w_lo` (ldw in elements, multiple of 8). */
 int cum_split_bf16(const float* w, void* hi, void* lo, long long count, cum_stream_t stream);
+/* fp16 hi/lo split of scale*w for CUM_MATH_F16X3 (scale = a power of two, typically 2^floor(log2(8/max|w|))); pass
+ * acc_scale = 1/scale in the descriptor. */
+int cum_split_f16(const float* w, void* hi, void* lo, long long count, float scale, cum_stream_t stream);
 
 /* ---- Mamba block operators ------------------------------------------------------------------- */
 /* Replaces Block.forward's `residual = h + residual; h = LayerNorm(residual)` (mamba_ssm Block, non-fused

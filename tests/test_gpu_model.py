@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 TOL_MAXABS = 1e-4
 TOL_SISDR_DB = 0.01
 # max-abs / rms(output): fp32 = summation order only; tf32x3 ~ 2^-21 per product; bf16x3 ~ 2^-16 per product
-REL_TO_RMS = {"fp32": 2e-5, "tf32x3": 1e-4, "bf16x3": 3e-4}
+REL_TO_RMS = {"fp32": 2e-5, "tf32x3": 1e-4, "bf16x3": 3e-4, "f16x3": 1e-4}
 
 
 def build(fx, **kw):
@@ -26,7 +26,7 @@ def build(fx, **kw):
     return net.cuda().float().eval()
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3"])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3", "f16x3"])
 @pytest.mark.parametrize("name", ["e8_pruned_500k", "e6_pruned_200k", "mini_mamba_442k", "tiny_equalwidth_seed0"])
 def test_forward_matches_reference_golden(name, math):
     fx = load_golden(name)
@@ -74,7 +74,7 @@ def test_normalize_input_false_returns_padded_length():
     assert torch.equal(x.cpu(), fx["noisy"])
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3"])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3", "f16x3"])
 @pytest.mark.parametrize("cfg_name,seconds", [("DNS-CleanUMamba-3N-E8", 1.0), ("DNS-CleanUMamba-3N-E6", 0.5)])
 def test_full_size_random_init_matches_oracle(cfg_name, seconds, math):
     """E8-full / E6-high (random init, seed 0 == reference constructor; checkpoints are not shipped)."""
@@ -96,7 +96,7 @@ def test_full_size_random_init_matches_oracle(cfg_name, seconds, math):
     assert d <= TOL_SISDR_DB
 
 
-@pytest.mark.parametrize("math,batch,seconds", [("bf16x3", 64, 10.0), ("tf32x3", 16, 10.0)])
+@pytest.mark.parametrize("math,batch,seconds", [("f16x3", 64, 10.0), ("tf32x3", 16, 10.0), ("bf16x3", 16, 10.0)])
 def test_full_size_tensor_core_modes_vs_exact_fp32_on_device(math, batch, seconds):
     """BASELINE.json configs[1] size (E8 full, 64 x 10 s): the CPU oracle cannot run this, so the tensor-core modes are
     checked on the device against the exact-fp32 CUDA-core mode (itself pinned to the oracle / reference above).
@@ -120,8 +120,8 @@ def test_full_size_tensor_core_modes_vs_exact_fp32_on_device(math, batch, second
     assert err <= TOL_MAXABS and d <= TOL_SISDR_DB
 
 
-@pytest.mark.parametrize("math", ["tf32x3", "bf16x3"])
-@pytest.mark.parametrize("name", ["e8_pruned_500k", "mini_mamba_442k"])
+@pytest.mark.parametrize("math", ["tf32x3", "f16x3"])
+@pytest.mark.parametrize("name", ["e8_pruned_500k", "mini_mamba_442k", "e6_pruned_200k"])
 def test_trained_checkpoint_at_full_scale_amplitude(name, math):
     """Trained checkpoints output at input scale, so a peak-1.0 input is the worst case for the ABSOLUTE 1e-4 bound."""
     fx = load_golden(name)

@@ -15,7 +15,7 @@ def dev():
     return torch.device("cuda:0")
 
 
-GEMM_TOL = {"fp32": 1e-5, "tf32x3": 6e-5, "bf16x3": 1.5e-4}   # x3 modes: split error per product + truncating TMEM accumulation
+GEMM_TOL = {"fp32": 1e-5, "tf32x3": 6e-5, "bf16x3": 1.5e-4, "f16x3": 6e-5}   # x3 modes: split error per product + truncating TMEM accumulation
 
 
 def rel_err(a, b):
@@ -96,7 +96,7 @@ def _cl(x):  # (b, c, l) -> (b, l, c) contiguous on the GPU
     return x.permute(0, 2, 1).contiguous().to(dev())
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3"])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3", "f16x3"])
 @pytest.mark.parametrize("b,cin,cout,l", [(2, 64, 128, 300), (1, 768, 768, 150), (3, 56, 72, 38), (1, 8, 8, 6), (2, 104, 200, 1030)])
 def test_gemm_pointwise_and_glu(math, b, cin, cout, l):
     from cleanumamba_b200 import _lib, ops
@@ -119,7 +119,7 @@ def test_gemm_pointwise_and_glu(math, b, cin, cout, l):
     assert rel_err(yg.permute(0, 2, 1), refg) < GEMM_TOL[math]
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3"])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3", "f16x3"])
 @pytest.mark.parametrize("b,cin,cout,lout", [(2, 64, 128, 200), (1, 256, 512, 77), (2, 56, 40, 129), (1, 768, 768, 130)])
 def test_gemm_as_strided_conv_and_transposed_conv(math, b, cin, cout, lout):
     """Conv1d(k=4,s=2) and ConvTranspose1d(k=4,s=2) expressed as 2-tap GEMMs (engine.py layouts)."""

@@ -31,7 +31,7 @@ def ragged_chunks(total, seed, lo=1, hi=1500):
 
 @pytest.mark.parametrize("normalize", [False, True])
 @pytest.mark.parametrize("name,math", [("tiny_equalwidth_seed0", "fp32"), ("e6_pruned_200k", "fp32"),
-                                       ("e8_pruned_500k", "fp32"), ("e8_pruned_500k", "tf32x3"), ("e8_pruned_500k", "bf16x3")])
+                                       ("e8_pruned_500k", "fp32"), ("e8_pruned_500k", "tf32x3"), ("e8_pruned_500k", "bf16x3"), ("e8_pruned_500k", "f16x3")])
 def test_stream_matches_stream_oracle(name, math, normalize):
     fx = load_golden(name)
     net = build(fx, normalize_input=normalize, math_mode=math)

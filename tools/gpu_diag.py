@@ -78,7 +78,7 @@ with torch.no_grad():
 torch.cuda.synchronize()
 say("model forward ok, max-abs vs reference golden", float((yv.cpu() - fx["denoised"]).abs().max()), "rms", float(fx["denoised"].pow(2).mean().sqrt()))
 if "--tc" in sys.argv:
-    for math in ("tf32", "tf32x3", "bf16x3"):
+    for math in ("tf32", "tf32x3", "bf16x3", "f16x3"):
         for (bt, rows, k, n_) in ((1, 300, 64, 128), (2, 1000, 768, 768), (3, 130, 104, 200)):
             a = torch.randn(bt, rows, k, generator=g); wt = torch.randn(1, n_, k, generator=g) / k ** .5
             c = ops.gemm_bias_act(a.to(dev), wt.to(dev), math=math)
