@@ -2,6 +2,11 @@
 // selective scan (fwd) with optional carried state.  All HBM / MUFU-bound CUDA-core kernels.
 #include "common.cuh"
 
+#ifndef SCAN_T_UNROLL
+#define SCAN_T_UNROLL 1   // time-loop unroll of the scan recurrence (2 trades occupancy for ILP)
+#endif
+constexpr int kScanUnroll = SCAN_T_UNROLL;
+
 namespace cum {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -205,8 +210,12 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 __device__ __forceinline__ float softplusf_(float x) {
-    // torch softplus (beta=1, threshold=20)
-    return x > 20.0f ? x : log1pf(expf(x));
+    // torch softplus (beta=1, threshold=20) = max(x,0) + log1p(exp(-|x|)), evaluated with the fast intrinsics:
+    // for e = exp(-|x|) < 1/16 a 5-term series of log1p (|rel err| < 2e-7), else log(1 + e) where 1 + e is exact enough
+    if (x > 20.0f) return x;
+    const float e = __expf(-fabsf(x));
+    const float l = e < 0.0625f ? e * (1.0f - e * (0.5f - e * (0.33333333f - e * (0.25f - e * 0.2f)))) : __logf(1.0f + e);
+    return fmaxf(x, 0.0f) + l;
 }
 
 template <int NS, int SL, int CH, int TC>
@@ -214,13 +223,14 @@ struct ScanSmem {
     static constexpr int NP = NS * SL;
     float u[2][TC][CH];
     float dl[2][TC][CH];
+    float z[2][TC][CH];           // staged with u / delta so the combine phase never waits on a global load
     float Bm[2][TC][NP];
     float Cm[2][TC][NP];
     float ypart[SL][TC][CH];
 };
 
 template <int NS, int SL, int CH, int TC>
-__global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_scan_desc p) {
+__global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_scan_fwd_kernel(const cum_scan_desc p) {
     constexpr int NP = NS * SL;
     constexpr int NT = CH * SL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -238,7 +248,9 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
     const float* db = p.delta + (long long)b * p.dl_bs;
     const float* Bb = p.Bm + (long long)b * p.B_bs;
     const float* Cb = p.Cm + (long long)b * p.C_bs;
+    const float* zb = p.z ? p.z + (long long)b * p.z_bs : nullptr;
     const bool vec_ok = ((p.u_rs | p.dl_rs | p.B_rs | p.C_rs | p.u_bs | p.dl_bs | p.B_bs | p.C_bs) % 4 == 0) &&
+                        (!p.z || ((p.z_rs | p.z_bs) % 4 == 0 && ((uintptr_t)p.z & 15) == 0)) &&
                         ((((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.Bm | (uintptr_t)p.Cm) & 15) == 0) &&
                         (p.d % 4 == 0) && (p.n_state % 4 == 0);
 
@@ -250,15 +262,18 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
             const int tt = t0 + t, cc = c0 + q * 4;
             float* su = &sm.u[buf][t][q * 4];
             float* sd = &sm.dl[buf][t][q * 4];
+            float* sz = &sm.z[buf][t][q * 4];
             if (tt < p.len && cc + 3 < p.d && vec_ok) {
                 cp_async16(su, ub + (long long)tt * p.u_rs + cc);
                 cp_async16(sd, db + (long long)tt * p.dl_rs + cc);
+                if (zb) cp_async16(sz, zb + (long long)tt * p.z_rs + cc);
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const bool ok = tt < p.len && cc + e < p.d;
                     su[e] = ok ? ub[(long long)tt * p.u_rs + cc + e] : 0.f;
                     sd[e] = ok ? db[(long long)tt * p.dl_rs + cc + e] : 0.f;
+                    if (zb) sz[e] = ok ? zb[(long long)tt * p.z_rs + cc + e] : 0.f;
                 }
             }
         }
@@ -284,24 +299,25 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
     };
 
     // per-thread constants and carried state
-    float a2[NS], h[NS];
+    float2 a2p[NS / 2], h2[NS / 2];          // (state 2j, state 2j+1) pairs
     const bool state_vec = (p.n_state % 4 == 0) && (slice * NS + NS <= p.n_state) && c_ok;   // float4 path (64 B / thread)
     if (state_vec) {
 #pragma unroll
         for (int q = 0; q < NS / 4; ++q) {
             const float4 av = __ldg(reinterpret_cast<const float4*>(p.a2 + (long long)c * p.n_state + slice * NS) + q);
-            a2[4 * q] = av.x; a2[4 * q + 1] = av.y; a2[4 * q + 2] = av.z; a2[4 * q + 3] = av.w;
+            a2p[2 * q] = make_float2(av.x, av.y); a2p[2 * q + 1] = make_float2(av.z, av.w);
             float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.h0) hv = *(reinterpret_cast<const float4*>(p.h0 + ((long long)b * p.d + c) * p.n_state + slice * NS) + q);
-            h[4 * q] = hv.x; h[4 * q + 1] = hv.y; h[4 * q + 2] = hv.z; h[4 * q + 3] = hv.w;
+            h2[2 * q] = make_float2(hv.x, hv.y); h2[2 * q + 1] = make_float2(hv.z, hv.w);
         }
     } else {
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int n = slice * NS + i;
             const bool ok = c_ok && n < p.n_state;
-            a2[i] = ok ? p.a2[(long long)c * p.n_state + n] : 0.f;
-            h[i] = (ok && p.h0) ? p.h0[((long long)b * p.d + c) * p.n_state + n] : 0.f;
+            const float av = ok ? p.a2[(long long)c * p.n_state + n] : 0.f;
+            const float hv = (ok && p.h0) ? p.h0[((long long)b * p.d + c) * p.n_state + n] : 0.f;
+            if (i & 1) { a2p[i >> 1].y = av; h2[i >> 1].y = hv; } else { a2p[i >> 1].x = av; h2[i >> 1].x = hv; }
         }
     }
 
@@ -314,7 +330,8 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
                 const int n = slice * NS + i;
-                if (c_ok && n < p.n_state) p.h_ckpt[(((long long)b * nchunks + chunk) * p.d + c) * p.n_state + n] = h[i];
+                if (c_ok && n < p.n_state)
+                    p.h_ckpt[(((long long)b * nchunks + chunk) * p.d + c) * p.n_state + n] = (i & 1) ? h2[i >> 1].y : h2[i >> 1].x;
             }
         }
         cp_async_wait<0>();
@@ -329,25 +346,29 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
             sm.dl[buf][t][cc] = v;
         }
         __syncthreads();  // (B)
+        // recurrence: packed 2-wide fp32 math (FMUL2 / FFMA2, sm_100) halves the FMA-pipe issue slots per state update, so the
+        // loop is bounded by the MUFU ex2 rate alone (1 ex2 per update)
+#pragma unroll kScanUnroll
         for (int t = 0; t < tn; ++t) {
             const float dl = sm.dl[buf][t][ch];
             const float du = dl * sm.u[buf][t][ch];
+            const float2 dl2 = make_float2(dl, dl), du2 = make_float2(du, du);
             const float4* bq = reinterpret_cast<const float4*>(&sm.Bm[buf][t][slice * NS]);
             const float4* cq = reinterpret_cast<const float4*>(&sm.Cm[buf][t][slice * NS]);
-            float acc0 = 0.f, acc1 = 0.f;
+            float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < NS / 4; ++q) {
                 const float4 bv = bq[q], cv = cq[q];
-                h[4 * q + 0] = fmaf(ex2_approx(dl * a2[4 * q + 0]), h[4 * q + 0], du * bv.x);
-                h[4 * q + 1] = fmaf(ex2_approx(dl * a2[4 * q + 1]), h[4 * q + 1], du * bv.y);
-                h[4 * q + 2] = fmaf(ex2_approx(dl * a2[4 * q + 2]), h[4 * q + 2], du * bv.z);
-                h[4 * q + 3] = fmaf(ex2_approx(dl * a2[4 * q + 3]), h[4 * q + 3], du * bv.w);
-                acc0 = fmaf(h[4 * q + 0], cv.x, acc0);
-                acc1 = fmaf(h[4 * q + 1], cv.y, acc1);
-                acc0 = fmaf(h[4 * q + 2], cv.z, acc0);
-                acc1 = fmaf(h[4 * q + 3], cv.w, acc1);
+                float2 x0 = __fmul2_rn(dl2, a2p[2 * q]), x1 = __fmul2_rn(dl2, a2p[2 * q + 1]);
+                x0.x = ex2_approx(x0.x); x0.y = ex2_approx(x0.y);
+                x1.x = ex2_approx(x1.x); x1.y = ex2_approx(x1.y);
+                h2[2 * q] = __ffma2_rn(x0, h2[2 * q], __fmul2_rn(du2, make_float2(bv.x, bv.y)));
+                h2[2 * q + 1] = __ffma2_rn(x1, h2[2 * q + 1], __fmul2_rn(du2, make_float2(bv.z, bv.w)));
+                acc0 = __ffma2_rn(h2[2 * q], make_float2(cv.x, cv.y), acc0);
+                acc1 = __ffma2_rn(h2[2 * q + 1], make_float2(cv.z, cv.w), acc1);
             }
-            sm.ypart[slice][t][ch] = acc0 + acc1;
+            const float2 a = __fadd2_rn(acc0, acc1);
+            sm.ypart[slice][t][ch] = a.x + a.y;
         }
         __syncthreads();  // (C)
         // combine + gate + store
@@ -359,7 +380,10 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
 #pragma unroll
             for (int s = 0; s < SL; ++s) yv += sm.ypart[s][t][cc];
             if (p.Dskip) yv = fmaf(__ldg(p.Dskip + cg), sm.u[buf][t][cc], yv);
-            if (p.z) yv *= siluf_(p.z[(long long)b * p.z_bs + (long long)(t0 + t) * p.z_rs + cg]);
+            if (p.z) {
+                const float zz = sm.z[buf][t][cc];
+                yv *= __fdividef(zz, 1.0f + __expf(-zz));
+            }
             p.y[(long long)b * p.y_bs + (long long)(t0 + t) * p.y_rs + cg] = yv;
         }
     }
@@ -368,12 +392,12 @@ __global__ void __launch_bounds__(CH* SL) selective_scan_fwd_kernel(const cum_sc
 #pragma unroll
             for (int q = 0; q < NS / 4; ++q)
                 *(reinterpret_cast<float4*>(p.h_out + ((long long)b * p.d + c) * p.n_state + slice * NS) + q) =
-                    make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+                    make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
         } else {
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
                 const int n = slice * NS + i;
-                if (c_ok && n < p.n_state) p.h_out[((long long)b * p.d + c) * p.n_state + n] = h[i];
+                if (c_ok && n < p.n_state) p.h_out[((long long)b * p.d + c) * p.n_state + n] = (i & 1) ? h2[i >> 1].y : h2[i >> 1].x;
             }
         }
     }
