@@ -427,12 +427,16 @@ def main():
     if world == 1 and not args.no_variants and args.mode == "offline":
         # the other arithmetic modes on the same workload (2 timed steps each after 1 warm-up), for transparency
         variants = {}
-        for alt in ("tf32x3", "bf16x3", "fp32"):
+        for alt in ("f16x3+fp16-stored-weights", "tf32x3", "bf16x3", "fp32"):
             if alt == args.math:
                 continue
             torch.manual_seed(0)
-            net_alt = Net("CleanUMamba", dict(cfg, math_mode=alt)).to(dev).eval()
+            net_alt = Net("CleanUMamba", dict(cfg, math_mode=alt.split("+")[0])).to(dev).eval()
             net_alt.load_state_dict(net.state_dict())
+            if "+" in alt:      # weights rounded to fp16 exactly as the reference's released checkpoints store them:
+                with torch.no_grad():       # the low weight halves vanish and the engine runs 2 MMA passes per product
+                    for p_ in net_alt.parameters():
+                        p_.copy_(p_.half().float())
 
             def alt_step():
                 work.copy_(x_dev)

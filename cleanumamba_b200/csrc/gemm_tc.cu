@@ -65,6 +65,7 @@ struct TcParams {
     float* c; long long c_bs, c_rs;
     const float* addend; long long add_bs, add_rs;
     float acc_scale;          // F16X3: 2^-k undoing the weight pre-scale (1 otherwise)
+    int skip_wlo;             // split modes: the low half of the weights is exactly zero -> skip its load and its MMA pass
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -280,10 +281,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int tap = it / p.k_blocks, kb = it - tap * p.k_blocks;
                 const int shift = tap == 0 ? p.shift0 : p.shift1;
                 mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_arrive_expect_tx(full_bar(s), Cfg::TX_BYTES);
+                const bool load_lo = X3 && !p.skip_wlo;
+                mbar_arrive_expect_tx(full_bar(s), load_lo ? Cfg::TX_BYTES : Cfg::TX_BYTES - Cfg::W_BYTES);
                 tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * TC_BK, m0 + shift, b);
                 tma_load_3d(smem_base + w_off(s), &tmWh, full_bar(s), kb * TC_BK, n0, tap);
-                if (X3) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), kb * TC_BK, n0, tap);
+                if (load_lo) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), kb * TC_BK, n0, tap);
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
@@ -319,12 +321,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (BF) {
                         umma_bf16(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
                         umma_bf16(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
-                        umma_bf16(tmem_d, adesc + koff, blo + koff, idesc, 1u);
+                        if (!p.skip_wlo) umma_bf16(tmem_d, adesc + koff, blo + koff, idesc, 1u);
                     } else {
                         umma_tf32(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
                         if (X3) {
                             umma_tf32(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
-                            umma_tf32(tmem_d, adesc + koff, blo + koff, idesc, 1u);
+                            if (!p.skip_wlo) umma_tf32(tmem_d, adesc + koff, blo + koff, idesc, 1u);
                         }
                     }
                 }
@@ -590,6 +592,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.bias = d.bias; p.c = d.c; p.c_bs = d.c_batch_stride; p.c_rs = d.c_row_stride;
     p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
     p.acc_scale = (MODE == TC_F16X3) ? d.acc_scale : 1.0f;
+    p.skip_wlo = (X3 && d.w_lo_is_zero) ? 1 : 0;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
     CUM_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());

@@ -52,6 +52,8 @@ def _interleave_glu(w: torch.Tensor, b: torch.Tensor, k_pad: int):
 
 
 class Engine:
+    skip_zero_lo = True      # skip the a_hi*w_lo pass for weights whose low half is exactly zero (tests may turn it off)
+
     def __init__(self, model):
         self.model = model
         self._key = None
@@ -204,7 +206,7 @@ class Engine:
         self.device = dev
         self.math = _lib.MATH_BY_NAME[getattr(self, "model_math_override", None) or getattr(m, "math_mode", "f16x3")]
         self.lib = _lib.init(dev)
-        self.pk_hi, self.pk_lo, self.w_scale_inv = {}, {}, {}
+        self.pk_hi, self.pk_lo, self.w_scale_inv, self.w_lo_zero = {}, {}, {}, set()
         if self.math == _lib.MATH_TF32X3:      # hi/lo copies of the whole packed buffer (only GEMM weights use them)
             hi, lo = torch.empty_like(flat), torch.empty_like(flat)
             check(self.lib.cum_split_tf32(flat.data_ptr(), hi.data_ptr(), lo.data_ptr(), flat.numel(),
@@ -237,6 +239,12 @@ class Engine:
                 self.pk_hi[k] = hi[offs[k]: offs[k] + t.numel()].view(t.shape)
                 self.pk_lo[k] = lo[offs[k]: offs[k] + t.numel()].view(t.shape)
             self._flat_split = (hi, lo)
+        if self.pk_lo:
+            # weights that are exactly representable by their high half (e.g. a checkpoint shipped in fp16, loaded with
+            # .float(), under f16x3): the third MMA pass multiplies by zeros and is skipped (identical result)
+            keys = [k for k in self.pk_lo if self.pk_lo[k].numel() > 0]
+            nz = torch.stack([self.pk_lo[k].float().abs().max() for k in keys]).tolist()     # one host sync at pack time
+            self.w_lo_zero = {k for k, v in zip(keys, nz) if v == 0.0}
         self._post_pack(items, offs, total)
 
     def _extra_items(self, items):
@@ -258,6 +266,7 @@ class Engine:
         if d.math in (_lib.MATH_TF32X3, _lib.MATH_BF16X3, _lib.MATH_F16X3):
             d.w, d.w_lo = self.pk_hi[w].data_ptr(), self.pk_lo[w].data_ptr()
             d.acc_scale = self.w_scale_inv.get(w, 1.0)
+            d.w_lo_is_zero = 1 if (self.skip_zero_lo and w in self.w_lo_zero) else 0
         else:
             d.w, d.w_lo = wt.data_ptr(), 0
         d.ldw, d.bias = wt.shape[-1], ptr(bias)

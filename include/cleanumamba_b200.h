@@ -119,6 +119,8 @@ typedef struct cum_gemm_desc {
     const float* w_lo;       /* TF32X3 / BF16X3 only: low halves of the weights; `w` must then hold the high halves (both
                                 produced by cum_split_tf32 / cum_split_bf16 / cum_split_f16; 16-bit arrays for *16X3) */
     float acc_scale;         /* CUM_MATH_F16X3 only: accumulators are multiplied by this before the bias (1 / weight scale) */
+    int w_lo_is_zero;        /* split modes: caller asserts every element of w_lo is exactly 0 (e.g. weights of a checkpoint
+                                shipped in fp16 under F16X3): the a_hi*w_lo pass is skipped -- identical result, 2 MMAs / product */
 } cum_gemm_desc;
 int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream);
 

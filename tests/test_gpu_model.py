@@ -135,3 +135,30 @@ def test_trained_checkpoint_at_full_scale_amplitude(name, math):
     d = (orc.si_sdr(y, clean) - orc.si_sdr(ref, clean)).abs().max().item()
     print(f"\n[{name} {math} full-scale] max-abs {err:.3e}  out-rms {ref.pow(2).mean().sqrt().item():.3e}  dSI-SDR {d:.2e} dB")
     assert err <= TOL_MAXABS and d <= TOL_SISDR_DB
+
+
+@pytest.mark.parametrize("math", ["f16x3", "tf32x3"])
+def test_two_pass_shortcut_for_fp16_stored_weights_is_bit_identical(math):
+    """Released checkpoints are stored in fp16: under f16x3 their low halves are exactly zero and the a_hi*w_lo MMA pass
+    is skipped.  The shortcut must not change a single bit (and must not trigger for weights that need the low half)."""
+    fx = load_golden("e8_pruned_500k")
+    net = build(fx, math_mode=math)
+    x = fx["noisy"].cuda()
+    eng = net.engine()
+    with torch.no_grad():
+        y_fast = net(x.clone())
+        if math == "f16x3":
+            assert len(eng.w_lo_zero) > 20, "fp16-stored weights should be recognised"
+        eng.skip_zero_lo = False
+        y_full = net(x.clone())
+        eng.skip_zero_lo = True
+    assert torch.equal(y_fast, y_full)
+    # a model with genuinely fp32 weights must keep all three passes
+    from cleanumamba_b200.network import Net
+    torch.manual_seed(1)
+    rnd = Net("CleanUMamba", dict(channels_H=16, max_H=32, encoder_n_layers=4, tsfm_n_layers=1, tsfm_d_model=32, tsfm_d_inner=64,
+                                  tsfm_n_head=2, math_mode=math)).cuda().eval()
+    with torch.no_grad():
+        rnd(torch.randn(1, 1, 4000, device="cuda"))
+    gemm_keys = {k for k in rnd.engine().w_lo_zero if k.endswith((".w", ".wg", ".in", ".xp", ".dtw", ".out"))}
+    assert not gemm_keys, gemm_keys       # (all-ones / all-zeros vectors like LayerNorm gamma / beta are not GEMM weights)
