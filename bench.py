@@ -398,9 +398,16 @@ def main():
                 gem[f] += prof[k][f]
     total_kernel_ms = sum(v["ms"] for v in prof.values())
     achieved = gem["flops"] / (gem["ms"] / 1e3) / 1e12 if gem["ms"] else 0.0
+    traffic = None       # dram__bytes of the 44 GEMM launches of one step, from the committed ncu capture of this workload
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic_f16x3.json")
+    if os.path.exists(tpath) and args.math == "f16x3" and B == 64 and args.seconds == 10.0 and args.model == "e8":
+        traffic = json.load(open(tpath))["dram_bytes_per_step_gemm_launches"]
     roofline = {"kernel": "tap-GEMM (conv/convT/1x1/projection contractions, %s)" % args.math, "bound": "tensor",
                 "achieved": round(achieved, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic,
+                "traffic_note": "bytes per STEP over the 44 launches of this kernel family (ncu dram__bytes, profiles/r01_ncu_gemm_all44_f16x3.md); "
+                                "algorithmic activation traffic is 64-66 GB, i.e. no re-reads" if traffic else None,
+                "peak_source": pk["src"] + " bf16 sustained",
                 "share_of_step": round(gem["ms"] / total_kernel_ms, 4) if total_kernel_ms else None,
                 "launches_per_step": gem["launches"] // args.steps,
                 "mma_passes": 3 if args.math in ("tf32x3", "bf16x3", "f16x3") else 1,

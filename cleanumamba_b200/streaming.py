@@ -104,15 +104,20 @@ class StreamSession:
             eng._call("stream_std", lib.cum_stream_std_fwd, X.data_ptr(), X.shape[1], B, F, self.frame_length, self.hop,
                       self.frames, self.running_std.data_ptr(), scale.data_ptr(), st())
 
-        # ---------------- encoder: every level produces all columns its (frame-aligned) input allows
+        # ---------------- encoder: every level produces all columns its (frame-aligned) input allows.
+        # All streams are flattened into the GEMM M dimension (full 128-row MMA tiles even when a stream contributes only
+        # a few rows): the strided conv reads a compact per-stream window of P = rows_new + 1 two-column rows, so row
+        # b*P + t of the flat problem is output t of stream b and the one junk row per stream (t = rows_new, whose second
+        # tap would reach into the next stream) is dropped when the output FIFO is assembled.
         avail_in = self.samples_base + n_use                    # absolute count of level-0 inputs (samples)
         for i, e in enumerate(meta["enc"]):
             c_old = self.enc_count[i]
             c_new = (avail_in - 4) // 2 + 1
             rows_new = c_new - c_old
             assert rows_new > 0
-            y = torch.empty(B, rows_new, e["Hc_p"], dtype=torch.float32, device=dev)
             if i == 0:
+                P = rows_new
+                y = torch.empty(B * P, e["Hc_p"], dtype=torch.float32, device=dev)
                 off = 2 * c_old - self.samples_base             # first sample of the first new column, inside X
                 per_frame = self.hop // 2                       # new level-1 columns per frame
                 first_rows = (self.frame_length - 4) // 2 + 1   # ... of the first frame after a reset
@@ -121,20 +126,21 @@ class StreamSession:
                           pk["enc0.w"].data_ptr(), pk["enc0.b"].data_ptr(), y.data_ptr(), rows_new, e["Hc_p"], 4, 2,
                           ptr(scale), per_frame, row_off, st())
             else:
+                P = rows_new + 1
                 src, cp = self.enc_buf[i - 1], e["Cin_p"]
                 lo = 2 * c_old - self.enc_base[i - 1]           # local column of the first input this call needs
-                have = self.enc_count[i - 1] - self.enc_base[i - 1] - lo
-                eng.gemm(src, lo * cp, src.shape[1] * cp, 2 * cp, have // 2, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
-                         y, 0, rows_new * e["Hc_p"], e["Hc_p"], rows_new, e["Hc_p"], B, EPI_RELU, taps=2, shifts=(0, 1))
-            # 1x1 + GLU, appended to this level's output FIFO
+                cin = src[:, lo: lo + 2 * P].contiguous()       # (B, 2P, cp) == B*P rows of 2*cp
+                y = torch.empty(B * P, e["Hc_p"], dtype=torch.float32, device=dev)
+                eng.gemm(cin, 0, 0, 2 * cp, B * P, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
+                         y, 0, 0, e["Hc_p"], B * P, e["Hc_p"], 1, EPI_RELU, taps=2, shifts=(0, 1))
+            newc = eng.dense(y, B * P, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act)
+            # output FIFO of this level: [columns the decoder has not consumed yet | new columns]
             keep = c_old - self.enc_base[i]
             buf = torch.empty(B, keep + rows_new, e["Ho_p"], dtype=torch.float32, device=dev)
             if keep:
                 old = self.enc_buf[i]
                 buf[:, :keep].copy_(old[:, old.shape[1] - keep:])
-            cap = buf.shape[1]
-            eng.gemm(y, 0, rows_new * e["Hc_p"], e["Hc_p"], rows_new, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"],
-                     buf, keep * e["Ho_p"], cap * e["Ho_p"], e["Ho_p"], rows_new, 2 * e["Ho_p"], B, act)
+            buf[:, keep:].copy_(newc.view(B, P, e["Ho_p"])[:, :rows_new])
             self.enc_buf[i] = buf
             self.enc_count[i] = c_new
             avail_in = c_new
@@ -149,28 +155,31 @@ class StreamSession:
         self.enc_base[D - 1] += F
         self.enc_buf[D - 1] = last[:, F:]
 
-        # ---------------- decoder: d columns in, 2d final columns out per level
+        # ---------------- decoder: d columns in, 2d final columns out per level (same flattening, pitch d + 1)
         d_cols = F
         out = None
         for j, dd in enumerate(meta["dec"]):
             hg = dd["Hg_p"]
+            gnew = eng.dense(xcur, B * d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * hg, epi=act)
             G = torch.empty(B, d_cols + 1, hg, dtype=torch.float32, device=dev)
-            G[:, 0].copy_(self.dec_carry[j])
-            eng.gemm(xcur, 0, d_cols * dd["Cin_p"], dd["Cin_p"], d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"],
-                     G, hg, (d_cols + 1) * hg, hg, d_cols, 2 * hg, B, act)
+            G[:, 0].copy_(self.dec_carry[j])                    # carried g[-1]: replaces the overlap-add tail (:476-484)
+            G[:, 1:].copy_(gnew.view(B, d_cols, hg))
             self.dec_carry[j] = G[:, d_cols].clone()
             if j < D - 1:
                 co = dd["Co_p"]
                 lvl = D - 2 - j
                 skip = self.enc_buf[lvl]
-                nxt = torch.empty(B, 2 * d_cols, co, dtype=torch.float32, device=dev)
-                # row p of the (d, 2 Co) output view = Wa . G[p+1] + Wb . G[p]   (G[0] is the carried column)
-                eng.gemm(G, 0, (d_cols + 1) * hg, hg, d_cols + 1, hg, f"dec{j}.w", pk[f"dec{j}.b"],
-                         nxt, 0, 2 * d_cols * co, 2 * co, d_cols, 2 * co, B, EPI_RELU, taps=2, shifts=(1, 0),
-                         addend=skip, add_bs=skip.shape[1] * co, add_rs=2 * co)
+                Pd = d_cols + 1
+                skipc = torch.empty(B, Pd, 2 * co, dtype=torch.float32, device=dev)
+                skipc[:, :d_cols].copy_(skip[:, : 2 * d_cols].reshape(B, d_cols, 2 * co))
+                nxt = torch.empty(B * Pd, 2 * co, dtype=torch.float32, device=dev)
+                # flat row b*Pd + p = Wa . G[b, p+1] + Wb . G[b, p]; p = d_cols is the junk row of stream b
+                eng.gemm(G, 0, 0, hg, B * Pd, hg, f"dec{j}.w", pk[f"dec{j}.b"], nxt, 0, 0, 2 * co, B * Pd, 2 * co, 1,
+                         EPI_RELU, taps=2, shifts=(1, 0), addend=skipc, add_bs=0, add_rs=2 * co)
                 self.enc_base[lvl] += 2 * d_cols
                 self.enc_buf[lvl] = skip[:, 2 * d_cols:]
-                xcur, d_cols = nxt, 2 * d_cols
+                xcur = nxt.view(B, Pd, 2 * co)[:, :d_cols].reshape(B * 2 * d_cols, co)
+                d_cols = 2 * d_cols
             else:
                 length = 2 * d_cols
                 out = torch.empty(B, length, dtype=torch.float32, device=dev)
