@@ -153,7 +153,12 @@ int cum_add_fwd(const float* a, const float* b, float* out, long long count, cum
 }
 int cum_gemm_wgrad(const cum_wgrad_desc* desc, cum_stream_t stream) {
     if (!desc) { set_error("wgrad: null descriptor"); return CUM_EINVAL; }
-    return wgrad_fwd(*desc, (cudaStream_t)stream);
+    if (desc->math == CUM_MATH_FP32) return wgrad_fwd(*desc, (cudaStream_t)stream);
+    return wgrad_tc_fwd(*desc, (cudaStream_t)stream);
+}
+long long cum_gemm_wgrad_workspace_bytes(const cum_wgrad_desc* desc) {
+    if (!desc || desc->math == CUM_MATH_FP32) return 0;
+    return wgrad_tc_workspace_bytes(*desc);
 }
 int cum_ln_residual_bwd(const float* x, const float* dy, const float* dres_in, const float* gamma, float* dx,
                         float* dgamma, float* dbeta, float eps, long long rows, int c, int c_pad, cum_stream_t stream) {

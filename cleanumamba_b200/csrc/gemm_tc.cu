@@ -24,6 +24,7 @@
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <string.h>
 
 namespace cum {
 
@@ -35,6 +36,7 @@ constexpr uint32_t TC_TMEM_COLS = 512;
 constexpr int TC_EPI_WARPS = 8;               // warps 4..11: two per TMEM lane quarter (even / odd 64-column chunks)
 constexpr int TC_EPI_GENERIC_UNARY = -1;      // runtime-selected activation (SiLU ...)
 constexpr int TC_EPI_GENERIC_GLU = -2;        // runtime-selected GLU gate (ReLU / SiLU / GELU)
+constexpr int TC_EPI_ATOMIC_ADD = -3;         // wgrad split-K: accumulate the tile into C with atomics (no bias / activation)
 
 // MODE: 0 = single-pass TF32, 1 = TF32X3 (hi/lo fp32 tiles, 3 kind::tf32 MMAs), 2 / 3 = BF16X3 / F16X3 (hi/lo 16-bit tiles,
 // 3 kind::f16 MMAs at twice the TF32 rate; F16X3 keeps 22 mantissa bits, its weights carry a power-of-two scale undone in the epilogue)
@@ -66,6 +68,8 @@ struct TcParams {
     const float* addend; long long add_bs, add_rs;
     float acc_scale;          // F16X3: 2^-k undoing the weight pre-scale (1 otherwise)
     int skip_wlo;             // split modes: the low half of the weights is exactly zero -> skip its load and its MMA pass
+    int w_k_batch_stride;     // wgrad (split-K over rows): W k-coordinate += batch * this + w_k_off
+    int w_k_off;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -283,9 +287,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 const bool load_lo = X3 && !p.skip_wlo;
                 mbar_arrive_expect_tx(full_bar(s), load_lo ? Cfg::TX_BYTES : Cfg::TX_BYTES - Cfg::W_BYTES);
-                tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * TC_BK, m0 + shift, b);
-                tma_load_3d(smem_base + w_off(s), &tmWh, full_bar(s), kb * TC_BK, n0, tap);
-                if (load_lo) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), kb * TC_BK, n0, tap);
+                // wgrad (split-K over rows): the split index selects a column range of ONE 2-D operand instead of a batch plane
+                if (p.w_k_batch_stride) tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * TC_BK + b * p.w_k_batch_stride, m0, 0);
+                else tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * TC_BK, m0 + shift, b);
+                const int wk = kb * TC_BK + b * p.w_k_batch_stride + p.w_k_off;
+                tma_load_3d(smem_base + w_off(s), &tmWh, full_bar(s), wk, n0, tap);
+                if (load_lo) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), wk, n0, tap);
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
@@ -377,7 +384,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (n >= p.n) break;
                             const float x0 = F16 ? fmaf(v[4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[4 * k + 2 * rh + 0] + bv[k].x;
                             const float x1 = F16 ? fmaf(v[4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[4 * k + 2 * rh + 1] + bv[k].y;
-                            if (GLU) {
+                            if (EPI == TC_EPI_ATOMIC_ADD) {
+                                atomicAdd(crow + n, x0);
+                                atomicAdd(crow + n + 1, x1);
+                            } else if (GLU) {
                                 float o = x0 * tc_gate<EPI>(p.epi, x1);
                                 const int oc = n >> 1;
                                 if (arow) o += __ldg(arow + oc);
@@ -559,6 +569,9 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1,
     return CUM_OK;
 }
 
+// split-K (wgrad) launch context: set by wgrad_tc_fwd around its launches (host-side, per calling thread)
+static thread_local int g_wgrad_kbs = 0, g_wgrad_koff = 0;
+
 template <int MODE, int BN, int EPI>
 static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     using Cfg = TcCfg<MODE, BN>;
@@ -572,15 +585,16 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
         attr_done = true;
     }
     CUtensorMap tmA, tmWh, tmWl;
-    const uint64_t a_bs = d.batch > 1 ? (uint64_t)d.a_batch_stride : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
-    int rc = make_map(&tmA, d.a, (uint64_t)d.k, (uint64_t)d.a_rows, (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs,
-                      TC_BK, TC_BM, "A");
+    const uint64_t a_bs = (d.batch > 1 && !g_wgrad_kbs) ? (uint64_t)d.a_batch_stride : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
+    int rc = make_map(&tmA, d.a, g_wgrad_kbs ? (uint64_t)d.a_row_stride : (uint64_t)d.k, (uint64_t)d.a_rows,
+                      g_wgrad_kbs ? 1 : (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs, TC_BK, TC_BM, "A");
     if (rc) return rc;
     const uint64_t w_ts = (uint64_t)d.n * (uint64_t)d.ldw;
-    rc = make_map(&tmWh, d.w, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W", BF);
+    const uint64_t w_k_extent = g_wgrad_kbs ? (uint64_t)d.ldw : (uint64_t)d.k;     // wgrad: W columns span every split
+    rc = make_map(&tmWh, d.w, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W", BF);
     if (rc) return rc;
     if (X3) {
-        rc = make_map(&tmWl, d.w_lo, (uint64_t)d.k, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W_lo", BF);
+        rc = make_map(&tmWl, d.w_lo, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W_lo", BF);
         if (rc) return rc;
     } else {
         tmWl = tmWh;
@@ -593,6 +607,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
     p.acc_scale = (MODE == TC_F16X3) ? d.acc_scale : 1.0f;
     p.skip_wlo = (X3 && d.w_lo_is_zero) ? 1 : 0;
+    p.w_k_batch_stride = g_wgrad_kbs; p.w_k_off = g_wgrad_koff;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
     CUM_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());
@@ -611,6 +626,112 @@ static int dispatch_epi(const cum_gemm_desc& d, cudaStream_t st) {
             return epi_is_glu(d.epilogue) ? launch_tc<MODE, BN, TC_EPI_GENERIC_GLU>(d, st)
                                           : launch_tc<MODE, BN, TC_EPI_GENERIC_UNARY>(d, st);
     }
+}
+
+// ------------------------------------------------------------------------------------------------ tensor-core wgrad
+// dW_s[n, k] = sum_r dZ[r, n] * A[r + shift_s, k] as a split-K GEMM over the ROW dimension: both operands are first
+// transposed into (channels, rows) matrices whose columns are laid out with a per-clip pitch P (one zero column per clip
+// where a tap would otherwise reach into the neighbouring clip); the activation side is TF32-split while it is transposed.
+// Then C'[n, k] += dZ^T[n, rows] . A^T[k, rows + shift] runs on the forward kernel (TF32X3: gradients need fp32 range),
+// `splits` CTAs per output tile, atomic accumulation into the zero-initialised gradient.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) transpose_pitch_kernel(const float* __restrict__ x, long long x_bs, long long x_rs,
+                                                               int rows_src, int cols, int batch, int pitch, long long r_pad,
+                                                               int shift, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+    __shared__ float tile[32][33];
+    const long long j0 = (long long)blockIdx.x * 32;      // output column (= flattened row index with pitch)
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long j = j0 + ty + 8 * i;
+        const int b = (int)(j / pitch), t = (int)(j % pitch) + shift;     // the tap shift is baked in here: a TMA box start must
+        const int c = c0 + tx;                                           // stay 16-byte aligned, so it cannot be a +-1 coordinate
+        float v = 0.f;
+        if (j < r_pad && b < batch && t >= 0 && t < rows_src && c < cols) v = x[(long long)b * x_bs + (long long)t * x_rs + c];
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i;
+        const long long j = j0 + tx;
+        if (c < cols && j < r_pad) {
+            const float v = tile[tx][ty + 8 * i];
+            if (SPLIT) {
+                const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                out_hi[(long long)c * r_pad + j] = h;
+                out_lo[(long long)c * r_pad + j] = v - h;
+            } else {
+                out_hi[(long long)c * r_pad + j] = v;
+            }
+        }
+    }
+}
+
+struct WgradPlan { long long R, r_pad, rps; int splits, pitch; size_t ws_bytes; };
+
+static WgradPlan plan_wgrad(const cum_wgrad_desc& d) {
+    WgradPlan w;
+    w.pitch = d.taps == 1 ? d.m : (d.m > d.a_rows ? d.m : d.a_rows);
+    w.R = (long long)d.batch * w.pitch;
+    const long long tiles = cdiv(d.n, TC_BM) * cdiv(d.k, 256);
+    long long s = (3LL * sm_count() + tiles - 1) / tiles;
+    const long long max_s = cdiv(w.R, 1024);              // at least 1024 rows (32 K-blocks) per split
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    if (s > 65535) s = 65535;
+    w.rps = cdiv(cdiv(w.R, s), 32) * 32;
+    w.splits = (int)cdiv(w.R, w.rps);
+    w.r_pad = w.rps * w.splits;
+    w.ws_bytes = (size_t)w.r_pad * ((size_t)d.n + 2 * (size_t)d.k) * sizeof(float);
+    return w;
+}
+
+long long wgrad_tc_workspace_bytes(const cum_wgrad_desc& d) { return (long long)plan_wgrad(d).ws_bytes; }
+
+template <int BN> static int launch_wgrad_gemm(const cum_gemm_desc& g, cudaStream_t st) {
+    return launch_tc<TC_TF32X3, BN, TC_EPI_ATOMIC_ADD>(g, st);
+}
+
+int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
+    CUM_REQUIRE(d.workspace, "wgrad: tensor-core mode needs a workspace (cum_gemm_wgrad_workspace_bytes)");
+    CUM_REQUIRE(aligned16(d.workspace), "wgrad: workspace must be 16-byte aligned");
+    CUM_REQUIRE(d.n % 8 == 0 && d.k % 8 == 0, "wgrad: n and k must be multiples of 8");
+    const WgradPlan w = plan_wgrad(d);
+    float* zt = reinterpret_cast<float*>(d.workspace);            // dZ^T   (n, r_pad)
+    float* at_hi = zt + (size_t)d.n * w.r_pad;                     // A^T hi (k, r_pad)
+    float* at_lo = at_hi + (size_t)d.k * w.r_pad;
+    const int cb = d.taps == 1 ? 1 : d.batch;                      // taps == 1: rows of all clips are one flat run
+    const long long rows_z = d.taps == 1 ? (long long)d.batch * d.m : d.m;
+    const long long rows_a = d.taps == 1 ? (long long)d.batch * d.m : d.a_rows;
+    const int pitch = d.taps == 1 ? (int)(rows_z > 2147483647LL ? 0 : rows_z) : w.pitch;
+    CUM_REQUIRE(pitch > 0, "wgrad: too many rows");
+    if (d.taps == 1)
+        CUM_REQUIRE(d.batch == 1 || (d.dz_batch_stride == (long long)d.m * d.dz_row_stride && d.a_batch_stride == (long long)d.m * d.a_row_stride),
+                    "wgrad: taps=1 with batch>1 needs batch-contiguous operands");
+    dim3 gz((unsigned)cdiv(w.r_pad, 32), (unsigned)cdiv(d.n, 32)), ga((unsigned)cdiv(w.r_pad, 32), (unsigned)cdiv(d.k, 32));
+    transpose_pitch_kernel<false><<<gz, 256, 0, st>>>(d.dz, d.dz_batch_stride, d.dz_row_stride, (int)rows_z, d.n, cb, pitch, w.r_pad, 0, zt, nullptr);
+    CUM_LAUNCH_CHECK("transpose_pitch_kernel(dz)");
+    for (int s = 0; s < d.taps; ++s) {
+        // A^T for this tap: column (b, t) <- A[b, t + shift_s] (zero outside the clip), TF32 hi / lo halves
+        transpose_pitch_kernel<true><<<ga, 256, 0, st>>>(d.a, d.a_batch_stride, d.a_row_stride, (int)rows_a, d.k, cb, pitch, w.r_pad,
+                                                         d.tap_shift[s], at_hi, at_lo);
+        CUM_LAUNCH_CHECK("transpose_pitch_kernel(a)");
+        cum_gemm_desc g;
+        memset(&g, 0, sizeof(g));
+        g.a = zt; g.a_batch_stride = w.rps; g.a_row_stride = w.r_pad; g.a_rows = d.n; g.k = (int)w.rps; g.taps = 1;
+        g.w = at_hi; g.w_lo = at_lo; g.ldw = (int)w.r_pad; g.bias = nullptr;
+        g.c = d.dw + (size_t)s * d.n * d.ldw; g.c_batch_stride = 0; g.c_row_stride = d.ldw;
+        g.m = d.n; g.n = d.k; g.batch = w.splits; g.epilogue = CUM_EPI_NONE; g.math = CUM_MATH_TF32X3;
+        CUM_REQUIRE(w.r_pad < 2147483647LL, "wgrad: padded row count exceeds the TMA coordinate range");
+        g_wgrad_kbs = (int)w.rps;
+        g_wgrad_koff = 0;
+        const int rc = d.k <= 128 ? launch_wgrad_gemm<128>(g, st) : launch_wgrad_gemm<256>(g, st);
+        g_wgrad_kbs = 0; g_wgrad_koff = 0;
+        if (rc) return rc;
+    }
+    return CUM_OK;
 }
 
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {

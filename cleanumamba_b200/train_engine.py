@@ -25,6 +25,8 @@ class TrainEngine(Engine):
     Training never uses the fp16 split ("f16x3"): back-propagated gradients routinely fall below fp16's 6e-5 normal
     range, so that mode is mapped to "tf32x3" (same 22-bit products, fp32 exponent range)."""
 
+    tc_wgrad = True      # tensor-core weight gradients (tests may switch to the fp32 CUDA-core kernel)
+
     def _pack(self):
         if getattr(self.model, "math_mode", None) == "f16x3":
             self.model_math_override = "tf32x3"
@@ -66,7 +68,14 @@ class TrainEngine(Engine):
         d.dw, d.ldw = g.data_ptr(), g.shape[-1]
         d.m, d.n, d.k, d.taps, d.batch = m, n, k, taps, batch
         d.tap_shift[0], d.tap_shift[1] = shifts
-        self._call("wgrad", self.lib.cum_gemm_wgrad, C.byref(d), _lib.stream_ptr(), flops=2 * batch * m * n * k * taps)
+        d.math = _lib.MATH_FP32 if (self.math == _lib.MATH_FP32 or not self.tc_wgrad) else _lib.MATH_TF32X3
+        ws = None
+        if d.math != _lib.MATH_FP32:
+            nbytes = self.lib.cum_gemm_wgrad_workspace_bytes(C.byref(d))
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            d.workspace = ws.data_ptr()
+        self._call("wgrad", self.lib.cum_gemm_wgrad, C.byref(d), _lib.stream_ptr(), flops=2 * batch * m * n * k * taps,
+                   launches=1 if ws is None else 1 + 2 * taps)
 
     def dense_T(self, dz, rows, n_fwd, key, k_fwd, addend=None, out=None, c_rs=None):
         """Data gradient of a flat dense layer: (rows, n_fwd) x W (n_fwd, k_fwd) -> (rows, k_fwd)."""

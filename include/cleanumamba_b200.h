@@ -197,8 +197,12 @@ typedef struct cum_wgrad_desc {
     int m, n, k, taps;
     int tap_shift[2];
     int batch;
+    int math;            /* CUM_MATH_FP32: CUDA-core FFMA (no workspace).  Any tensor-core mode: tcgen05 split-K GEMM over the
+                            rows in TF32X3 arithmetic (gradients need the fp32 exponent range) */
+    void* workspace;     /* tensor-core mode: >= cum_gemm_wgrad_workspace_bytes(desc) bytes of device scratch */
 } cum_wgrad_desc;
-int cum_gemm_wgrad(const cum_wgrad_desc* desc, cum_stream_t stream);
+int       cum_gemm_wgrad(const cum_wgrad_desc* desc, cum_stream_t stream);
+long long cum_gemm_wgrad_workspace_bytes(const cum_wgrad_desc* desc);
 
 /* LayerNorm backward + residual-stream add: x = saved LN input (rows, c_pad); dy = grad of the normalised output;
  * dres_in (may be NULL) = gradient already in the residual stream; dx = LN_bwd(dy) + dres_in;

@@ -18,29 +18,34 @@ def rel(a, b):
     return ((a.detach().double().cpu() - b.detach().double().cpu()).abs().max() / b.detach().double().abs().max().clamp_min(1e-30)).item()
 
 
-def test_wgrad_taps():
+@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
+def test_wgrad_taps(math):
+    """fp32 CUDA-core wgrad and the tensor-core split-K wgrad (transpose + tcgen05, atomic accumulate)."""
     from cleanumamba_b200 import _lib
     lib = _lib.init(torch.device(DEV))
     g = torch.Generator().manual_seed(0)
     for (B, m, n, k, taps, shifts, a_rows) in [(2, 300, 128, 64, 1, (0, 0), 300), (3, 77, 72, 112, 2, (0, 1), 78),
-                                                (2, 130, 200, 40, 2, (0, -1), 129), (1, 1000, 1536, 768, 1, (0, 0), 1000)]:
+                                                (2, 130, 200, 40, 2, (0, -1), 129), (1, 1000, 1536, 768, 1, (0, 0), 1000),
+                                                (4, 5006, 768, 1024, 2, (0, 1), 5007), (2, 20000, 128, 64, 1, (0, 0), 20000)]:
         dz = torch.randn(B, m, n, generator=g)
         a = torch.randn(B, a_rows, k, generator=g)
         want = torch.zeros(taps, n, k)
         for s in range(taps):
             ash = torch.zeros(B, m, k)
-            for r in range(m):
-                if 0 <= r + shifts[s] < a_rows:
-                    ash[:, r] = a[:, r + shifts[s]]
-            want[s] = torch.einsum("bmn,bmk->nk", dz, ash)
+            lo, hi = max(0, -shifts[s]), min(m, a_rows - shifts[s])
+            ash[:, lo:hi] = a[:, lo + shifts[s]: hi + shifts[s]]
+            want[s] = torch.einsum("bmn,bmk->nk", dz.double(), ash.double()).float()
         dzd, ad, dw = dz.to(DEV), a.to(DEV), torch.zeros(taps, n, k, device=DEV)
         d = _lib.WgradDesc()
         d.dz, d.dz_batch_stride, d.dz_row_stride = dzd.data_ptr(), m * n, n
         d.a, d.a_batch_stride, d.a_row_stride, d.a_rows = ad.data_ptr(), a_rows * k, k, a_rows
         d.dw, d.ldw, d.m, d.n, d.k, d.taps, d.batch = dw.data_ptr(), k, m, n, k, taps, B
         d.tap_shift[0], d.tap_shift[1] = shifts
+        d.math = _lib.MATH_BY_NAME[math]
+        ws = torch.empty(max(1, lib.cum_gemm_wgrad_workspace_bytes(C.byref(d)) // 4 + 1), device=DEV)
+        d.workspace = ws.data_ptr()
         _lib.check(lib.cum_gemm_wgrad(C.byref(d), _lib.stream_ptr()), "wgrad")
-        assert rel(dw, want) < 2e-5
+        assert rel(dw, want) < (2e-5 if math == "fp32" else 1e-4), (B, m, n, k, taps, rel(dw, want))
 
 
 def test_elementwise_backward_and_colsum():
