@@ -28,6 +28,32 @@ __device__ __forceinline__ float ex2_approx_b(float x) {
 }
 __device__ __forceinline__ float softplus_b(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 
+// Sum 8 per-lane values over the 32 lanes of a warp with 9 shuffles instead of 8 x 5: each xor step halves the number of
+// values a lane still owns.  On return lane L holds the warp total of value index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1)
+// (replicated over the 4 lanes that share those bits).
+__device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane) {
+    float w4[4], w2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b4 ? v[i] : v[i + 4];
+        const float keep = b4 ? v[i + 4] : v[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b3 ? w4[i] : w4[i + 2];
+        const float keep = b3 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = b2 ? w2[0] : w2[1];
+    const float keep = b2 ? w2[1] : w2[0];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
 template <int SL>
 struct ScanBwdSmem {
     static constexpr int NP = 4 * SL;
@@ -64,29 +90,58 @@ __global__ void __launch_bounds__(32 * SL) selective_scan_bwd_kernel(const cum_s
     float accD = 0.f, accBias = 0.f;     // per (tid & 31) channel partials of the combine threads
     const float Dv = (f.Dskip && c_ok) ? f.Dskip[c] : 0.f;
 
-    for (int chunk = nchunks - 1; chunk >= 0; --chunk) {
+    // register prefetch buffers: every thread owns a fixed share of each tile
+    constexpr int PF_E = (SB_TC * SB_CH + NT - 1) / NT;      // u / delta / z / dout elements per thread
+    constexpr int PF_N = (SB_TC * NP + NT - 1) / NT;         // B / C elements per thread
+    float pf_u[PF_E], pf_d[PF_E], pf_z[PF_E], pf_o[PF_E], pf_B[PF_N], pf_C[PF_N];
+    auto prefetch = [&](int chunk) {
         const int t0 = chunk * SB_TC;
         const int tn = min(SB_TC, f.len - t0);
-        // ---- load tiles
-        for (int i = tid; i < SB_TC * SB_CH; i += NT) {
+        int e = 0;
+        for (int i = tid; i < SB_TC * SB_CH; i += NT, ++e) {
             const int t = i >> 5, cc = i & 31;
             const int tt = t0 + t, cg = c0 + cc;
             const bool ok = t < tn && cg < f.d;
-            const float uv = ok ? f.u[(long long)b * f.u_bs + (long long)tt * f.u_rs + cg] : 0.f;
-            float dr = ok ? f.delta[(long long)b * f.dl_bs + (long long)tt * f.dl_rs + cg] : 0.f;
-            if (f.delta_bias && cg < f.d) dr += f.delta_bias[cg];
-            sm.u[t][cc] = uv;
-            sm.draw[t][cc] = dr;
-            sm.dl[t][cc] = f.delta_softplus ? softplus_b(dr) : dr;
-            sm.z[t][cc] = (ok && f.z) ? f.z[(long long)b * f.z_bs + (long long)tt * f.z_rs + cg] : 0.f;
-            sm.dout[t][cc] = ok ? p.dout[(long long)b * p.dout_bs + (long long)tt * p.dout_rs + cg] : 0.f;
+            pf_u[e] = ok ? f.u[(long long)b * f.u_bs + (long long)tt * f.u_rs + cg] : 0.f;
+            pf_d[e] = ok ? f.delta[(long long)b * f.dl_bs + (long long)tt * f.dl_rs + cg] : 0.f;
+            pf_z[e] = (ok && f.z) ? f.z[(long long)b * f.z_bs + (long long)tt * f.z_rs + cg] : 0.f;
+            pf_o[e] = ok ? p.dout[(long long)b * p.dout_bs + (long long)tt * p.dout_rs + cg] : 0.f;
         }
-        for (int i = tid; i < SB_TC * NP; i += NT) {
+        e = 0;
+        for (int i = tid; i < SB_TC * NP; i += NT, ++e) {
             const int t = i / NP, n = i - t * NP;
             const bool ok = t < tn && n < f.n_state;
-            sm.Bm[t][n] = ok ? f.Bm[(long long)b * f.B_bs + (long long)(t0 + t) * f.B_rs + n] : 0.f;
-            sm.Cm[t][n] = ok ? f.Cm[(long long)b * f.C_bs + (long long)(t0 + t) * f.C_rs + n] : 0.f;
+            pf_B[e] = ok ? f.Bm[(long long)b * f.B_bs + (long long)(t0 + t) * f.B_rs + n] : 0.f;
+            pf_C[e] = ok ? f.Cm[(long long)b * f.C_bs + (long long)(t0 + t) * f.C_rs + n] : 0.f;
         }
+    };
+    prefetch(nchunks - 1);
+
+    for (int chunk = nchunks - 1; chunk >= 0; --chunk) {
+        const int t0 = chunk * SB_TC;
+        const int tn = min(SB_TC, f.len - t0);
+        // ---- tiles of this chunk were fetched into registers while the previous chunk was being processed
+        {
+            int e = 0;
+            for (int i = tid; i < SB_TC * SB_CH; i += NT, ++e) {
+                const int t = i >> 5, cc = i & 31;
+                const int cg = c0 + cc;
+                float dr = pf_d[e];
+                if (f.delta_bias && cg < f.d) dr += f.delta_bias[cg];
+                sm.u[t][cc] = pf_u[e];
+                sm.draw[t][cc] = dr;
+                sm.dl[t][cc] = f.delta_softplus ? softplus_b(dr) : dr;
+                sm.z[t][cc] = pf_z[e];
+                sm.dout[t][cc] = pf_o[e];
+            }
+            e = 0;
+            for (int i = tid; i < SB_TC * NP; i += NT, ++e) {
+                const int t = i / NP, n = i - t * NP;
+                sm.Bm[t][n] = pf_B[e];
+                sm.Cm[t][n] = pf_C[e];
+            }
+        }
+        if (chunk > 0) prefetch(chunk - 1);       // global latency of the next (earlier) chunk overlaps this chunk's math
         __syncthreads();
         // ---- forward recompute with history in registers
         float hs[4], hist[SB_TC][4];
@@ -159,15 +214,16 @@ __global__ void __launch_bounds__(32 * SL) selective_scan_bwd_kernel(const cum_s
             }
             sm.part0[slice][t][ch] = sgB;
             sm.part1[slice][t][ch] = sdl;
-            // d-reductions of dB / dC over the warp's 32 channels
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float sc = warp_sum(dCp[i]);
-                const float sb = warp_sum(dBp[i]);
-                const int n = slice * 4 + i;
-                if (ch == 0 && t < tn && n < f.n_state) {
-                    atomicAdd(p.dC + (long long)b * p.dC_bs + (long long)(t0 + t) * p.dC_rs + n, sc);
-                    atomicAdd(p.dB + (long long)b * p.dB_bs + (long long)(t0 + t) * p.dB_rs + n, sb);
+            // d-reductions of dB / dC over the warp's 32 channels: 8 values, 9 shuffles (warp_sum8)
+            {
+                const float v8[8] = {dCp[0], dCp[1], dCp[2], dCp[3], dBp[0], dBp[1], dBp[2], dBp[3]};
+                const float tot = warp_sum8(v8, ch);
+                const int idx = ((ch >> 4) & 1) * 4 + ((ch >> 3) & 1) * 2 + ((ch >> 2) & 1);    // value this lane holds
+                const int n = slice * 4 + (idx & 3);
+                if ((ch & 3) == 0 && t < tn && n < f.n_state) {
+                    float* dst = idx < 4 ? p.dC + (long long)b * p.dC_bs + (long long)(t0 + t) * p.dC_rs
+                                         : p.dB + (long long)b * p.dB_bs + (long long)(t0 + t) * p.dB_rs;
+                    atomicAdd(dst + n, tot);
                 }
             }
         }
