@@ -8,11 +8,11 @@
 // same tensor map fetched at a shifted row coordinate; rows outside [0, a_rows) are zero-filled by TMA, which is
 // exactly the conv / transposed-conv boundary condition.
 //
-// Warp roles (384 threads, 512 with the splitter):
+// Warp roles (640 threads, 768 with the splitter):
 //   warp 0        TMA producer (one lane)
 //   warp 1        TMEM allocator + MMA issuer (one lane)
-//   warps 4..11   epilogue: tcgen05.ld (16x256b fragments) -> bias / ReLU / GLU / skip-add -> 32-byte-sector stores
-//   warps 12..15  (TF32X3 only) operand splitter: A tile -> hi = a & 0xffffe000 (in place), lo = a - hi
+//   warps 4..19   epilogue: tcgen05.ld (16x256b fragments) -> bias / ReLU / GLU / skip-add -> 32-byte-sector stores
+//   warps 20..23  (split modes) operand splitter: A tile -> hi = a & 0xffffe000 (in place), lo = a - hi
 //
 // TF32X3: fp32 activations cannot be fed to kind::tf32 directly within the 1e-4 waveform tolerance (10-bit mantissa,
 // 22 stacked layers), so every product is expanded a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (three MMAs, error
@@ -33,7 +33,8 @@ constexpr int TC_BK = 32;                     // fp32 elements per K-block = one
 constexpr int TC_UMMA_K = 8;                  // kind::tf32
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr uint32_t TC_TMEM_COLS = 512;
-constexpr int TC_EPI_WARPS = 8;               // warps 4..11: two per TMEM lane quarter (even / odd 64-column chunks)
+constexpr int TC_EPI_WARPS = 16;              // warps 4..19: four per TMEM lane quarter, 32-column chunks interleaved.  The epilogue is
+                                              // serial-issue-bound per warp (~0.25 IPC), so its speed scales with the warp count
 constexpr int TC_EPI_GENERIC_UNARY = -1;      // runtime-selected activation (SiLU ...)
 constexpr int TC_EPI_GENERIC_GLU = -2;        // runtime-selected GLU gate (ReLU / SiLU / GELU)
 constexpr int TC_EPI_ATOMIC_ADD = -3;         // wgrad split-K: accumulate the tile into C with atomics (no bias / activation)
@@ -56,7 +57,7 @@ template <int MODE, int BN> struct TcCfg {
     static constexpr int STAGES = (int)(196608u / STAGE_BYTES);
     static constexpr uint32_t TX_BYTES = TC_A_BYTES + (SPLIT ? 2 : 1) * W_BYTES;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int THREADS = SPLIT ? 512 : 384;                   // warps 12..15 = operand splitter
+    static constexpr int THREADS = (4 + TC_EPI_WARPS + (SPLIT ? 4 : 0)) * 32;   // last 4 warps = operand splitter
     static constexpr int UMMA_K = HALF ? 16 : 8;
 };
 
@@ -184,6 +185,17 @@ __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float* v) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 16 lanes x 32 columns: r[4k+0..1] -> row t/4, r[4k+2..3] -> row t/4 + 8, columns 8k + 2(t%4) + {0,1}, k = 0..3
+__device__ __forceinline__ void tmem_ld_16x256b_x4_nowait(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
 }
 
 // epilogue math.  The tensor-core path uses the fast intrinsics (ex2.approx / rcp.approx, ~2 ulp): the gate error is
@@ -343,9 +355,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= 4 && warp < 4 + TC_EPI_WARPS) {
-        // ===================================================================== epilogue (8 warps)
+        // ===================================================================== epilogue (16 warps)
         const int q = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int chalf = (warp - 4) >> 2;      // even / odd 64-column chunks
+        const int sub = (warp - 4) >> 2;        // which of every four 32-column chunks
         const int tq = lane & 3, tr = lane >> 2;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -359,19 +371,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n_rem > BN) n_rem = BN;
             float* cb = p.c + (long long)b * p.c_bs;
             const float* ab = p.addend ? p.addend + (long long)b * p.add_bs : nullptr;
-            for (int c0 = chalf * 64; c0 < n_rem; c0 += 128) {
-                // bias for this thread's 8 column pairs
-                float2 bv[8];
+            for (int c0 = sub * 32; c0 < n_rem; c0 += 128) {
+                float2 bv[4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 4; ++k) {
                     const int n = n0 + c0 + 8 * k + 2 * tq;
                     bv[k] = (p.bias && n < p.n) ? __ldg(reinterpret_cast<const float2*>(p.bias + n)) : make_float2(0.f, 0.f);
                 }
+                float v[2][16];
+                __syncwarp();       // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+                tmem_ld_16x256b_x4_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v[0]);
+                tmem_ld_16x256b_x4_nowait(tmem_base + ((uint32_t)(q * 32 + 16) << 16) + (uint32_t)(acc * BN + c0), v[1]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    float v[32];
-                    __syncwarp();       // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
-                    tmem_ld_16x256b_x8(tmem_base + ((uint32_t)(q * 32 + h * 16) << 16) + (uint32_t)(acc * BN + c0), v);
 #pragma unroll
                     for (int rh = 0; rh < 2; ++rh) {
                         const int row = m0 + q * 32 + h * 16 + rh * 8 + tr;
@@ -379,11 +392,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float* crow = cb + (long long)row * p.c_rs;
                         const float* arow = ab ? ab + (long long)row * p.add_rs : nullptr;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
+                        for (int k = 0; k < 4; ++k) {
                             const int n = n0 + c0 + 8 * k + 2 * tq;
                             if (n >= p.n) break;
-                            const float x0 = F16 ? fmaf(v[4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[4 * k + 2 * rh + 0] + bv[k].x;
-                            const float x1 = F16 ? fmaf(v[4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[4 * k + 2 * rh + 1] + bv[k].y;
+                            const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
+                            const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
                             if (EPI == TC_EPI_ATOMIC_ADD) {
                                 atomicAdd(crow + n, x0);
                                 atomicAdd(crow + n + 1, x1);
@@ -407,9 +420,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
         }
-    } else if (X3 && warp >= 12) {
+    } else if (X3 && warp >= 4 + TC_EPI_WARPS) {
         // ===================================================================== operand splitter (A tile)
-        const int t = threadIdx.x - 384;
+        const int t = threadIdx.x - (4 + TC_EPI_WARPS) * 32;
         int s = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
