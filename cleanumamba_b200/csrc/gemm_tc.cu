@@ -655,14 +655,21 @@ __global__ void __launch_bounds__(256) transpose_pitch_kernel(const float* __res
     const long long j0 = (long long)blockIdx.x * 32;      // output column (= flattened row index with pitch)
     const int c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    // (clip, row) of column j0: ONE 32-bit division per thread, the 4 columns this thread reads are found incrementally
+    // (a 64-bit divide / modulo per element made this kernel integer-bound at ~1.5 TB/s)
+    const unsigned j0u = (unsigned)j0, pu = (unsigned)pitch;
+    int b = (int)(j0u / pu), t = (int)(j0u - (unsigned)b * pu) + ty;
+    while (t >= pitch) { t -= pitch; ++b; }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const long long j = j0 + ty + 8 * i;
-        const int b = (int)(j / pitch), t = (int)(j % pitch) + shift;     // the tap shift is baked in here: a TMA box start must
-        const int c = c0 + tx;                                           // stay 16-byte aligned, so it cannot be a +-1 coordinate
+        const int ts = t + shift;                          // the tap shift is baked in here: a TMA box start must stay
+        const int c = c0 + tx;                             // 16-byte aligned, so it cannot be a +-1 coordinate
         float v = 0.f;
-        if (j < r_pad && b < batch && t >= 0 && t < rows_src && c < cols) v = x[(long long)b * x_bs + (long long)t * x_rs + c];
+        if (j < r_pad && b < batch && ts >= 0 && ts < rows_src && c < cols) v = x[(long long)b * x_bs + (long long)ts * x_rs + c];
         tile[ty + 8 * i][tx] = v;
+        t += 8;
+        while (t >= pitch) { t -= pitch; ++b; }
     }
     __syncthreads();
 #pragma unroll
