@@ -162,3 +162,51 @@ def test_two_pass_shortcut_for_fp16_stored_weights_is_bit_identical(math):
         rnd(torch.randn(1, 1, 4000, device="cuda"))
     gemm_keys = {k for k in rnd.engine().w_lo_zero if k.endswith((".w", ".wg", ".in", ".xp", ".dtw", ".out"))}
     assert not gemm_keys, gemm_keys       # (all-ones / all-zeros vectors like LayerNorm gamma / beta are not GEMM weights)
+
+
+@pytest.mark.parametrize("length", [1, 3, 255, 766, 767, 1000, 12345])
+def test_ragged_and_tiny_lengths(length):
+    """Edge cases of pad_signal / valid_length (CleanUMamba.py:219-246): inputs shorter than one frame, odd lengths."""
+    fx = load_golden("mini_mamba_442k")
+    net = build(fx, math_mode="fp32")
+    g = torch.Generator().manual_seed(length)
+    x = torch.randn(2, 1, length, generator=g) * 0.1 + (0.01 if length < 4 else 0.0)
+    if length == 1:
+        net.normalize_input = False          # std of a single sample is NaN in the reference too
+    ref = orc.forward(fx["state_dict"], x, normalize_input=net.normalize_input)
+    with torch.no_grad():
+        y = net(x.clone().cuda()).cpu()
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= TOL_MAXABS
+
+
+def test_input_variants_batch1_noncontiguous_half():
+    fx = load_golden("e6_pruned_200k")
+    net = build(fx)
+    base = fx["noisy"][:1, :, :5000]
+    ref = orc.forward(fx["state_dict"], base)
+    with torch.no_grad():
+        # batch 1
+        assert (net(base.clone().cuda()).cpu() - ref).abs().max().item() <= TOL_MAXABS
+        # non-contiguous view (every other sample of a longer buffer)
+        wide = torch.zeros(1, 1, 10000)
+        wide[..., ::2] = base
+        nc = wide.cuda()[..., ::2]
+        assert not nc.is_contiguous()
+        y = net(nc)
+        assert (y.cpu() - ref).abs().max().item() <= TOL_MAXABS
+        # the reference normalises its argument in place -- also through a non-contiguous view
+        std = base.std(dim=2, keepdim=True) + 1e-3
+        assert torch.allclose(nc.cpu(), base / std, rtol=1e-5, atol=1e-7)
+        # fp16 input tensor (the reference's autocast callers): computed in fp32 storage, returned as fp32
+        yh = net(base.half().cuda())
+        ref_h = orc.forward(fx["state_dict"], base.half().float())
+        assert (yh.float().cpu() - ref_h).abs().max().item() <= 2e-3        # the in-place fp16 normalisation rounds the input
+    # weights in half precision (checkpoint loaded without .float()): packed to fp32, same result
+    from cleanumamba_b200.network import Net
+    net_h = Net("CleanUMamba", json.loads(fx["config"]))
+    net_h.load_pruned_state_dict(fx["state_dict"])
+    net_h = net_h.cuda().half().eval()
+    with torch.no_grad():
+        y2 = net_h(base.clone().cuda())
+    assert (y2.float().cpu() - ref).abs().max().item() <= TOL_MAXABS

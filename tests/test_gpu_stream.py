@@ -86,3 +86,22 @@ def test_module_feed_flush_api():
     assert torch.allclose(seq, par, atol=0.1)                   # the reference's own tolerance
     with pytest.raises(ValueError):
         net.feed(torch.zeros(2, 3, device="cuda"))
+
+
+def test_stream_edge_cases_empty_and_tiny_feeds():
+    """feed() with fewer samples than a frame returns (B, 0); one sample at a time still converges to the same output."""
+    fx = load_golden("tiny_equalwidth_seed0")
+    net = build(fx, normalize_input=False)
+    x = fx["noisy"][:1, 0, :400]
+    so = orc.StreamOracle(fx["state_dict"], normalize_input=False)
+    want = so.feed(x)
+    sess = net.stream_session(batch=1)
+    assert sess.feed(x[:, :10].cuda()).shape == (1, 0)
+    outs = [sess.feed(x[:, 10:11].cuda())]
+    outs += [sess.feed(x[:, i:i + 7].cuda()) for i in range(11, x.shape[1], 7)]
+    got = torch.cat(outs, 1).cpu()
+    assert got.shape == want.shape and (got - want).abs().max().item() < TOL
+    with pytest.raises(ValueError):
+        sess.feed(torch.zeros(2, 5, device="cuda"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sess.feed(torch.zeros(1, 5))
