@@ -198,6 +198,14 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4_nowait(uint32_t taddr, float*
         : "r"(taddr) : "memory");
 }
 
+// 16 lanes x 16 columns: r[4k+0..1] -> row t/4, r[4k+2..3] -> row t/4 + 8, columns 8k + 2(t%4) + {0,1}, k = 0..1
+__device__ __forceinline__ void tmem_ld_16x256b_x2_nowait(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+
 // epilogue math.  The tensor-core path uses the fast intrinsics (ex2.approx / rcp.approx, ~2 ulp): the gate error is
 // far below the TF32X3 product error; the exact-fp32 SIMT kernel keeps expf / IEEE division.
 __device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
@@ -371,17 +379,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n_rem > BN) n_rem = BN;
             float* cb = p.c + (long long)b * p.c_bs;
             const float* ab = p.addend ? p.addend + (long long)b * p.add_bs : nullptr;
-            for (int c0 = sub * 32; c0 < n_rem; c0 += 128) {
-                float2 bv[4];
+            // 16-column chunks (4 warps of a lane quarter interleave them): small enough that the accumulators, the bias and
+            // the prefetched skip values all stay in registers under the 85-register cap of a 768-thread CTA
+            for (int c0 = sub * 16; c0 < n_rem; c0 += 64) {
+                float2 bv[2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 2; ++k) {
                     const int n = n0 + c0 + 8 * k + 2 * tq;
                     bv[k] = (p.bias && n < p.n) ? __ldg(reinterpret_cast<const float2*>(p.bias + n)) : make_float2(0.f, 0.f);
                 }
-                float v[2][16];
+                float v[2][8];
                 __syncwarp();       // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
-                tmem_ld_16x256b_x4_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v[0]);
-                tmem_ld_16x256b_x4_nowait(tmem_base + ((uint32_t)(q * 32 + 16) << 16) + (uint32_t)(acc * BN + c0), v[1]);
+                tmem_ld_16x256b_x2_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v[0]);
+                tmem_ld_16x256b_x2_nowait(tmem_base + ((uint32_t)(q * 32 + 16) << 16) + (uint32_t)(acc * BN + c0), v[1]);
+                // the U-Net skip tile (addend) comes from DRAM: all of this thread's addend values are requested BEFORE
+                // waiting on the TMEM loads so their latency overlaps (they used to be loaded one by one right before use)
+                float2 ad[2][2][2];
+                if (ab && EPI != TC_EPI_ATOMIC_ADD) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int rh = 0; rh < 2; ++rh) {
+                            const int row = m0 + q * 32 + h * 16 + rh * 8 + tr;
+                            const float* arow = ab + (long long)row * p.add_rs;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const int n = n0 + c0 + 8 * k + 2 * tq;
+                                ad[h][rh][k] = make_float2(0.f, 0.f);
+                                if (row < p.m && n < p.n) {
+                                    if (GLU) ad[h][rh][k].x = __ldg(arow + (n >> 1));
+                                    else ad[h][rh][k] = __ldg(reinterpret_cast<const float2*>(arow + n));
+                                }
+                            }
+                        }
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -390,9 +421,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int row = m0 + q * 32 + h * 16 + rh * 8 + tr;
                         if (row >= p.m) continue;
                         float* crow = cb + (long long)row * p.c_rs;
-                        const float* arow = ab ? ab + (long long)row * p.add_rs : nullptr;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < 2; ++k) {
                             const int n = n0 + c0 + 8 * k + 2 * tq;
                             if (n >= p.n) break;
                             const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
@@ -402,15 +432,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 atomicAdd(crow + n + 1, x1);
                             } else if (GLU) {
                                 float o = x0 * tc_gate<EPI>(p.epi, x1);
-                                const int oc = n >> 1;
-                                if (arow) o += __ldg(arow + oc);
-                                crow[oc] = o;
+                                if (ab) o += ad[h][rh][k].x;
+                                crow[n >> 1] = o;
                             } else {
                                 float2 o = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
-                                if (arow) {
-                                    const float2 ad = __ldg(reinterpret_cast<const float2*>(arow + n));
-                                    o.x += ad.x; o.y += ad.y;
-                                }
+                                if (ab) { o.x += ad[h][rh][k].x; o.y += ad[h][rh][k].y; }
                                 *reinterpret_cast<float2*>(crow + n) = o;
                             }
                         }
