@@ -24,7 +24,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import EPI_GLU, EPI_NONE, EPI_RELU, ptr
+from ._lib import EPI_GLU, EPI_RELU, ptr
 
 
 class StreamSession:
@@ -53,7 +53,6 @@ class StreamSession:
         self.enc_buf = [None] * D            # (B, cap, C_p): encoder level i outputs from absolute column enc_base[i]
         self.enc_base = [0] * D              # columns already consumed by the decoder
         self.enc_count = [0] * D             # columns produced so far
-        self.consumed_in = [0] * (D + 1)     # input columns (level i) fully consumed by conv i: 2 * enc_count[i]
         self.samples_base = 0                # absolute index (since reset) of pending[:, 0]
         self.frames_since_reset = 0
         self.dec_carry = [torch.zeros(self.B, d["Hg_p"], dtype=torch.float32, device=self.dev) for d in meta["dec"]]
