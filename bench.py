@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--model", default="e8", choices=list(CONFIGS))
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--seconds", type=float, default=10.0)
-    ap.add_argument("--math", default=os.environ.get("CUM_MATH", "f16x3"), choices=["fp32", "tf32x3", "bf16x3", "f16x3", "tf32"],
+    ap.add_argument("--math", default=os.environ.get("CUM_MATH", "f16x3"), choices=["fp32", "tf32x3", "bf16x3", "f16x3", "bf16", "tf32"],
                     help="arithmetic of the contractions (activations / accumulation / storage are fp32 in every mode): "
                          "f16x3 (default) / tf32x3 = tcgen05 3-pass split products with 22 mantissa bits, parity-tested inside the "
                          "fp32 tolerance of BASELINE.json (max-abs <= 1e-4, dSI-SDR <= 0.01 dB); bf16x3 = 16-17 bits (marginal at "
@@ -411,6 +411,7 @@ def main():
                 "share_of_step": round(gem["ms"] / total_kernel_ms, 4) if total_kernel_ms else None,
                 "launches_per_step": gem["launches"] // args.steps,
                 "mma_passes": 3 if args.math in ("tf32x3", "bf16x3", "f16x3") else 1,
+                "dtype_note": "bf16 storage + bf16 products (reduced precision)" if args.math == "bf16" else None,
                 "note": ("achieved = ALGORITHMIC flops (2*M*N*K per contraction) / CUDA-event kernel time; tf32x3 issues 3 "
                          "kind::tf32 MMAs per product (TF32 pipe = 1/2 of the bf16 peak used as denominator), so the pipe-level "
                          "rate is 3x achieved; ncu sm__pipe_tensor_cycles_active = 70-76 % on the K>=1024 layers "
@@ -434,7 +435,7 @@ def main():
     if world == 1 and not args.no_variants and args.mode == "offline":
         # the other arithmetic modes on the same workload (2 timed steps each after 1 warm-up), for transparency
         variants = {}
-        for alt in ("f16x3+fp16-stored-weights", "tf32x3", "bf16x3", "fp32"):
+        for alt in ("f16x3+fp16-stored-weights", "bf16", "tf32x3", "bf16x3", "fp32"):
             if alt == args.math:
                 continue
             torch.manual_seed(0)
@@ -478,6 +479,8 @@ def main():
                            "f16x3": "fp32 storage/accumulate; products = 3 fp16 tensor-core passes on hi/lo halves (11+11 bits, ~2^-21 per "
                                     "product, same accuracy class as tf32x3 at the bf16 tensor rate; weights carry a power-of-two scale, "
                                     "activations convert with saturation); parity-tested at this workload size against the exact-fp32 mode",
+                           "bf16": "REDUCED PRECISION variant (reported separately, outside the fp32 tolerance): bf16 activation storage and "
+                                   "single-pass bf16 tensor-core products in the encoder / decoder stacks, fp32 accumulate",
                            "tf32": "single TF32 pass (outside the tolerance)"}[args.math],
             "config": {"workload": f"CleanUMamba {args.model.upper()} full ({sum(p.numel() for p in net.parameters())/1e6:.2f}M, "
                                    f"seeded random init) offline forward, batch {B} x {args.seconds:g} s @16 kHz per GPU, "

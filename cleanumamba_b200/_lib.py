@@ -17,8 +17,9 @@ LIB_PATH = os.path.join(_PKG, "libcleanumamba_sm100.so")
 # enums (mirror include/cleanumamba_b200.h)
 EPI_NONE, EPI_RELU, EPI_SILU = 0, 1, 2
 EPI_GLU = {"Sigmoid": 8, "ReLU": 9, "SiLU": 10, "GELU": 11}
-MATH_FP32, MATH_TF32X3, MATH_TF32, MATH_BF16X3, MATH_F16X3 = 0, 1, 2, 3, 4
-MATH_BY_NAME = {"fp32": MATH_FP32, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32, "bf16x3": MATH_BF16X3, "f16x3": MATH_F16X3}
+MATH_FP32, MATH_TF32X3, MATH_TF32, MATH_BF16X3, MATH_F16X3, MATH_BF16 = 0, 1, 2, 3, 4, 5
+MATH_BY_NAME = {"fp32": MATH_FP32, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32, "bf16x3": MATH_BF16X3, "f16x3": MATH_F16X3,
+                "bf16": MATH_BF16}
 
 
 class GemmDesc(C.Structure):
@@ -28,7 +29,7 @@ class GemmDesc(C.Structure):
                 ("c", C.c_void_p), ("c_batch_stride", C.c_longlong), ("c_row_stride", C.c_longlong),
                 ("m", C.c_int), ("n", C.c_int), ("batch", C.c_int), ("epilogue", C.c_int),
                 ("addend", C.c_void_p), ("add_batch_stride", C.c_longlong), ("add_row_stride", C.c_longlong),
-                ("math", C.c_int), ("w_lo", C.c_void_p), ("acc_scale", C.c_float), ("w_lo_is_zero", C.c_int)]
+                ("math", C.c_int), ("w_lo", C.c_void_p), ("acc_scale", C.c_float), ("out_bf16", C.c_int), ("w_lo_is_zero", C.c_int)]
 
 
 class ScanDesc(C.Structure):
@@ -69,6 +70,10 @@ EXPORTS = {
     "cum_wave_normalize_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cum_conv_in_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "cum_conv_in_bf16_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cum_convt_out_bf16_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cum_stream_std_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "cum_convt_out_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int,

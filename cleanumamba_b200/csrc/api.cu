@@ -79,6 +79,19 @@ int cum_conv_in_fwd(const float* x, long long x_stride, int batch, int length, c
                        row_offset, (cudaStream_t)stream);
 }
 
+int cum_conv_in_bf16_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
+                         void* y_bf16, int rows_out, int c_pad, int kernel, int stride, cum_stream_t stream) {
+    return conv_in_fwd(x, x_stride, batch, length, w, bias, reinterpret_cast<float*>(y_bf16), rows_out, c_pad, kernel, stride,
+                       nullptr, 0, 0, (cudaStream_t)stream, true);
+}
+
+int cum_convt_out_bf16_fwd(const void* g_bf16, int batch, int rows_in, int c_pad, const float* w, float bias,
+                           const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
+                           int kernel, int stride, cum_stream_t stream) {
+    return convt_out_fwd(reinterpret_cast<const float*>(g_bf16), batch, rows_in, c_pad, w, bias, scale, scale_group, out,
+                         out_stride, first, length, kernel, stride, (cudaStream_t)stream, true);
+}
+
 int cum_stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
                        int frames_before, float* running, float* scale_out, cum_stream_t stream) {
     return stream_std_fwd(x, x_stride, batch, frames, frame_len, hop, frames_before, running, scale_out,
@@ -101,6 +114,7 @@ int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream) {
         case CUM_MATH_TF32X3:
         case CUM_MATH_BF16X3:
         case CUM_MATH_F16X3:
+        case CUM_MATH_BF16:
         case CUM_MATH_TF32: return gemm_tc_fwd(*desc, (cudaStream_t)stream);
         default: set_error("gemm: unknown math mode %d", desc->math); return CUM_EINVAL;
     }

@@ -70,12 +70,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStream_t st);
 int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
                 float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
-                int row_offset, cudaStream_t st);
+                int row_offset, cudaStream_t st, bool out_bf16 = false);
 int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
                    int frames_before, float* running, float* scale_out, cudaStream_t st);
 int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
                   const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
-                  int kernel, int stride, cudaStream_t st);
+                  int kernel, int stride, cudaStream_t st, bool in_bf16 = false);
 int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t st);

@@ -43,8 +43,11 @@ constexpr int TC_EPI_ATOMIC_ADD = -3;         // wgrad split-K: accumulate the t
 // 3 kind::f16 MMAs at twice the TF32 rate; F16X3 keeps 22 mantissa bits, its weights carry a power-of-two scale undone in the epilogue)
 // BN = tile width (256, or 128 for narrow layers: smaller W box -> deeper pipeline for the HBM-bound layers)
 constexpr int TC_TF32 = 0, TC_TF32X3 = 1, TC_BF16X3 = 2, TC_F16X3 = 3;   // F16X3: like BF16X3 with fp16 halves (11+11 bits)
+constexpr int TC_BF16 = 4;   // bf16 activations straight from HBM (no splitter), one kind::f16 pass -- the reduced-precision variant
 template <int MODE, int BN> struct TcCfg {
-    static constexpr bool SPLIT = MODE != TC_TF32;                      // operand-splitter warps present
+    static constexpr bool SPLIT = MODE != TC_TF32 && MODE != TC_BF16;   // operand-splitter warps present
+    static constexpr bool PLAIN16 = MODE == TC_BF16;                    // 16-bit operands, 128-byte rows = 64 elements per K-block
+    static constexpr int BK = PLAIN16 ? 64 : TC_BK;                     // elements per K-block (always 128 B of A per row)
     static constexpr bool HALF = (MODE == TC_BF16X3 || MODE == TC_F16X3);    // 16-bit MMA operands
     static constexpr uint32_t W_BYTES = BN * TC_BK * (HALF ? 2 : 4);
     static constexpr uint32_t AOP_BYTES = HALF ? TC_A_BYTES / 2 : TC_A_BYTES;   // one MMA A-operand tile
@@ -58,7 +61,7 @@ template <int MODE, int BN> struct TcCfg {
     static constexpr uint32_t TX_BYTES = TC_A_BYTES + (SPLIT ? 2 : 1) * W_BYTES;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int THREADS = (4 + TC_EPI_WARPS + (SPLIT ? 4 : 0)) * 32;   // last 4 warps = operand splitter
-    static constexpr int UMMA_K = HALF ? 16 : 8;
+    static constexpr int UMMA_K = (HALF || PLAIN16) ? 16 : 8;
 };
 
 struct TcParams {
@@ -231,15 +234,16 @@ __device__ __forceinline__ float tc_act(int epi, float v) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int MODE, int BN, int EPI>
+template <int MODE, int BN, int EPI, bool OUT16>
 __global__ void __launch_bounds__(TcCfg<MODE, BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                const __grid_constant__ CUtensorMap tmWl, const TcParams p) {
     using Cfg = TcCfg<MODE, BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool X3 = Cfg::SPLIT;
-    constexpr bool BF = Cfg::HALF;               // 16-bit operand tiles (bf16 or fp16)
+    constexpr bool BF = Cfg::HALF;               // 16-bit SPLIT operand tiles (bf16 or fp16, 64-byte swizzle)
     constexpr bool F16 = MODE == TC_F16X3;
+    constexpr bool P16 = Cfg::PLAIN16;           // plain bf16 operands (128-byte swizzle)
     constexpr bool GLU = (EPI == CUM_EPI_GLU_SIGMOID || EPI == TC_EPI_GENERIC_GLU);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -306,11 +310,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int shift = tap == 0 ? p.shift0 : p.shift1;
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 const bool load_lo = X3 && !p.skip_wlo;
-                mbar_arrive_expect_tx(full_bar(s), load_lo ? Cfg::TX_BYTES : Cfg::TX_BYTES - Cfg::W_BYTES);
+                // bytes this stage will receive: A + W_hi (+ W_lo unless it is skipped); non-split modes have no W_lo at all
+                mbar_arrive_expect_tx(full_bar(s), (X3 && !load_lo) ? Cfg::TX_BYTES - Cfg::W_BYTES : Cfg::TX_BYTES);
                 // wgrad (split-K over rows): the split index selects a column range of ONE 2-D operand instead of a batch plane
-                if (p.w_k_batch_stride) tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * TC_BK + b * p.w_k_batch_stride, m0, 0);
-                else tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * TC_BK, m0 + shift, b);
-                const int wk = kb * TC_BK + b * p.w_k_batch_stride + p.w_k_off;
+                if (p.w_k_batch_stride) tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK + b * p.w_k_batch_stride, m0, 0);
+                else tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK, m0 + shift, b);
+                const int wk = kb * Cfg::BK + b * p.w_k_batch_stride + p.w_k_off;
                 tma_load_3d(smem_base + w_off(s), &tmWh, full_bar(s), wk, n0, tap);
                 if (load_lo) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), wk, n0, tap);
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -330,7 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n_rem > BN) n_rem = BN;
             const uint32_t umma_n = (uint32_t)((n_rem + 15) & ~15);
             // c=f32 (1<<4); a/b format 2 = tf32, 1 = bf16 (bits 7, 10); K-major both; N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t fmt = F16 ? 0u : (BF ? 1u : 2u);       // 0 = f16, 1 = bf16, 2 = tf32
+            const uint32_t fmt = F16 ? 0u : ((BF || P16) ? 1u : 2u);       // 0 = f16, 1 = bf16, 2 = tf32
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
             mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
@@ -343,9 +348,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint64_t alo = BF ? umma_desc_sw64(smem_base + alo_off(s)) : umma_desc_sw128(smem_base + alo_off(s));
                 const uint64_t blo = BF ? umma_desc_sw64(smem_base + wlo_off(s)) : umma_desc_sw128(smem_base + wlo_off(s));
 #pragma unroll
-                for (int kk = 0; kk < TC_BK / Cfg::UMMA_K; ++kk) {
+                for (int kk = 0; kk < Cfg::BK / Cfg::UMMA_K; ++kk) {
                     const uint64_t koff = (uint64_t)(kk * 2);          // 32 bytes per k-step in both element types
-                    if (BF) {
+                    if (P16) {
+                        umma_bf16(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
+                    } else if (BF) {
                         umma_bf16(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
                         umma_bf16(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
                         if (!p.skip_wlo) umma_bf16(tmem_d, adesc + koff, blo + koff, idesc, 1u);
@@ -377,8 +384,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             int n_rem = p.n - n0;
             if (n_rem > BN) n_rem = BN;
-            float* cb = p.c + (long long)b * p.c_bs;
-            const float* ab = p.addend ? p.addend + (long long)b * p.add_bs : nullptr;
+            // OUT16: the output and the addend are bf16 arrays (strides in elements)
+            float* cb = OUT16 ? reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(p.c) + (long long)b * p.c_bs) : p.c + (long long)b * p.c_bs;
+            const float* ab = !p.addend ? nullptr
+                              : OUT16 ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(p.addend) + (long long)b * p.add_bs)
+                                      : p.addend + (long long)b * p.add_bs;
             // 16-column chunks (4 warps of a lane quarter interleave them): small enough that the accumulators, the bias and
             // the prefetched skip values all stay in registers under the 85-register cap of a 768-thread CTA
             for (int c0 = sub * 16; c0 < n_rem; c0 += 64) {
@@ -402,12 +412,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int rh = 0; rh < 2; ++rh) {
                             const int row = m0 + q * 32 + h * 16 + rh * 8 + tr;
                             const float* arow = ab + (long long)row * p.add_rs;
+                            const __nv_bfloat16* arow16 = reinterpret_cast<const __nv_bfloat16*>(ab) + (long long)row * p.add_rs;
 #pragma unroll
                             for (int k = 0; k < 2; ++k) {
                                 const int n = n0 + c0 + 8 * k + 2 * tq;
                                 ad[h][rh][k] = make_float2(0.f, 0.f);
                                 if (row < p.m && n < p.n) {
-                                    if (GLU) ad[h][rh][k].x = __ldg(arow + (n >> 1));
+                                    if (OUT16) {
+                                        if (GLU) ad[h][rh][k].x = __bfloat162float(arow16[n >> 1]);
+                                        else ad[h][rh][k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(arow16 + n));
+                                    } else if (GLU) ad[h][rh][k].x = __ldg(arow + (n >> 1));
                                     else ad[h][rh][k] = __ldg(reinterpret_cast<const float2*>(arow + n));
                                 }
                             }
@@ -421,6 +435,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int row = m0 + q * 32 + h * 16 + rh * 8 + tr;
                         if (row >= p.m) continue;
                         float* crow = cb + (long long)row * p.c_rs;
+                        __nv_bfloat16* crow16 = reinterpret_cast<__nv_bfloat16*>(cb) + (long long)row * p.c_rs;
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
                             const int n = n0 + c0 + 8 * k + 2 * tq;
@@ -433,11 +448,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             } else if (GLU) {
                                 float o = x0 * tc_gate<EPI>(p.epi, x1);
                                 if (ab) o += ad[h][rh][k].x;
-                                crow[n >> 1] = o;
+                                if (OUT16) crow16[n >> 1] = __float2bfloat16_rn(o);
+                                else crow[n >> 1] = o;
                             } else {
                                 float2 o = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
                                 if (ab) { o.x += ad[h][rh][k].x; o.y += ad[h][rh][k].y; }
-                                *reinterpret_cast<float2*>(crow + n) = o;
+                                if (OUT16) *reinterpret_cast<__nv_bfloat162*>(crow16 + n) = __floats2bfloat162_rn(o.x, o.y);
+                                else *reinterpret_cast<float2*>(crow + n) = o;
                             }
                         }
                     }
@@ -587,7 +604,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 static int make_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_elems,
-                    uint64_t s2_elems, uint32_t box0, uint32_t box1, const char* what, bool bf16 = false) {
+                    uint64_t s2_elems, uint32_t box0, uint32_t box1, const char* what, bool bf16 = false, bool sw128_16 = false) {
     auto enc = get_encode();
     if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return CUM_ECUDA; }
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -597,7 +614,7 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1,
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base),
                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     (bf16 && !sw128_16) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("gemm_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu strides %llu,%llu)", what,
@@ -611,12 +628,13 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1,
 // split-K (wgrad) launch context: set by wgrad_tc_fwd around its launches (host-side, per calling thread)
 static thread_local int g_wgrad_kbs = 0, g_wgrad_koff = 0;
 
-template <int MODE, int BN, int EPI>
+template <int MODE, int BN, int EPI, bool OUT16 = false>
 static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     using Cfg = TcCfg<MODE, BN>;
     constexpr bool X3 = Cfg::SPLIT;
     constexpr bool BF = Cfg::HALF;
-    auto kern = gemm_tc_kernel<MODE, BN, EPI>;
+    constexpr bool P16 = Cfg::PLAIN16;
+    auto kern = gemm_tc_kernel<MODE, BN, EPI, OUT16>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -626,11 +644,11 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     CUtensorMap tmA, tmWh, tmWl;
     const uint64_t a_bs = (d.batch > 1 && !g_wgrad_kbs) ? (uint64_t)d.a_batch_stride : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
     int rc = make_map(&tmA, d.a, g_wgrad_kbs ? (uint64_t)d.a_row_stride : (uint64_t)d.k, (uint64_t)d.a_rows,
-                      g_wgrad_kbs ? 1 : (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs, TC_BK, TC_BM, "A");
+                      g_wgrad_kbs ? 1 : (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs, Cfg::BK, TC_BM, "A", P16, P16);
     if (rc) return rc;
     const uint64_t w_ts = (uint64_t)d.n * (uint64_t)d.ldw;
     const uint64_t w_k_extent = g_wgrad_kbs ? (uint64_t)d.ldw : (uint64_t)d.k;     // wgrad: W columns span every split
-    rc = make_map(&tmWh, d.w, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W", BF);
+    rc = make_map(&tmWh, d.w, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, Cfg::BK, BN, "W", BF || P16, P16);
     if (rc) return rc;
     if (X3) {
         rc = make_map(&tmWl, d.w_lo, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W_lo", BF);
@@ -641,7 +659,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     TcParams p;
     p.m = d.m; p.n = d.n; p.k = d.k; p.taps = d.taps; p.shift0 = d.tap_shift[0]; p.shift1 = d.tap_shift[1];
     p.batch = d.batch; p.epi = d.epilogue;
-    p.m_tiles = (int)cdiv(d.m, TC_BM); p.n_tiles = (int)cdiv(d.n, BN); p.k_blocks = (int)cdiv(d.k, TC_BK);
+    p.m_tiles = (int)cdiv(d.m, TC_BM); p.n_tiles = (int)cdiv(d.n, BN); p.k_blocks = (int)cdiv(d.k, Cfg::BK);
     p.bias = d.bias; p.c = d.c; p.c_bs = d.c_batch_stride; p.c_rs = d.c_row_stride;
     p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
     p.acc_scale = (MODE == TC_F16X3) ? d.acc_scale : 1.0f;
@@ -657,6 +675,14 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
 
 template <int MODE, int BN>
 static int dispatch_epi(const cum_gemm_desc& d, cudaStream_t st) {
+    if (d.out_bf16) {       // bf16 output / addend: only the epilogues the bf16 variant of the model uses
+        switch (d.epilogue) {
+            case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, true>(d, st);
+            case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, true>(d, st);
+            case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, true>(d, st);
+            default: set_error("gemm_tc: bf16 output supports NONE / RELU / GLU_SIGMOID epilogues"); return CUM_ENOTSUP;
+        }
+    }
     switch (d.epilogue) {
         case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE>(d, st);
         case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU>(d, st);
@@ -737,7 +763,7 @@ static WgradPlan plan_wgrad(const cum_wgrad_desc& d) {
 long long wgrad_tc_workspace_bytes(const cum_wgrad_desc& d) { return (long long)plan_wgrad(d).ws_bytes; }
 
 template <int BN> static int launch_wgrad_gemm(const cum_gemm_desc& g, cudaStream_t st) {
-    return launch_tc<TC_TF32X3, BN, TC_EPI_ATOMIC_ADD>(g, st);
+    return launch_tc<TC_TF32X3, BN, TC_EPI_ATOMIC_ADD, false>(g, st);
 }
 
 int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
@@ -792,6 +818,12 @@ int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
         CUM_REQUIRE(d.ldw % 8 == 0, "gemm_tc: BF16X3 needs ldw %% 8 == 0 (ldw=%d)", d.ldw);
         return narrow ? dispatch_epi<TC_BF16X3, 128>(d, st) : dispatch_epi<TC_BF16X3, 256>(d, st);
     }
+    if (d.math == CUM_MATH_BF16) {
+        CUM_REQUIRE(d.k % 8 == 0 && d.ldw % 8 == 0 && d.a_row_stride % 8 == 0 && d.a_batch_stride % 8 == 0,
+                    "gemm_tc: BF16 needs k, ldw and the a strides to be multiples of 8 elements");
+        return narrow ? dispatch_epi<TC_BF16, 128>(d, st) : dispatch_epi<TC_BF16, 256>(d, st);
+    }
+    CUM_REQUIRE(!d.out_bf16 || d.math == CUM_MATH_F16X3, "gemm_tc: bf16 output is available for the BF16 and F16X3 modes");
     if (d.math == CUM_MATH_F16X3) {
         CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: F16X3 needs w_lo (see cum_split_f16)");
         CUM_REQUIRE(d.ldw % 8 == 0, "gemm_tc: F16X3 needs ldw %% 8 == 0 (ldw=%d)", d.ldw);

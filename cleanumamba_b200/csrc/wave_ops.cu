@@ -2,6 +2,8 @@
 // All three are HBM-bound streaming kernels (a few FLOP per byte); see DESIGN.md "kernels".
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace cum {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -96,6 +98,7 @@ int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, in
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CI_ROWS = 64;
 
+template <bool OUT16>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, long long x_stride, int length,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        float* __restrict__ y, int rows_out, int c_pad, int kernel,
@@ -127,13 +130,19 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
             acc.z = fmaf(wv.z, xv, acc.z); acc.w = fmaf(wv.w, xv, acc.w);
         }
         acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-        reinterpret_cast<float4*>(yb + (long long)t * c_pad)[c4] = acc;
+        if (OUT16) {       // bf16 activation storage (reduced-precision variant): y is a bf16 array
+            __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y) + ((long long)b * rows_out + t0 + t) * c_pad + 4 * c4;
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+            *reinterpret_cast<uint2*>(y16) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        } else {
+            reinterpret_cast<float4*>(yb + (long long)t * c_pad)[c4] = acc;
+        }
     }
 }
 
 int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
                 float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
-                int row_offset, cudaStream_t st) {
+                int row_offset, cudaStream_t st, bool out_bf16) {
     CUM_REQUIRE(x && w && bias && y, "conv_in: null pointer");
     CUM_REQUIRE(batch > 0 && length > 0 && rows_out > 0, "conv_in: empty problem");
     CUM_REQUIRE(c_pad > 0 && c_pad % 4 == 0, "conv_in: c_pad=%d must be a positive multiple of 4", c_pad);
@@ -143,8 +152,12 @@ int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const
     const size_t smem = (size_t)(CI_ROWS * stride + kernel) * sizeof(float);
     CUM_REQUIRE(!in_scale || group_rows > 0, "conv_in: group_rows must be positive when in_scale is given");
     const int groups = in_scale ? (int)cdiv(max(1, rows_out + row_offset), group_rows) : 0;
-    conv_in_kernel<<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale,
-                                            groups, group_rows, row_offset);
+    if (out_bf16)
+        conv_in_kernel<true><<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale,
+                                                      groups, group_rows, row_offset);
+    else
+        conv_in_kernel<false><<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale,
+                                                       groups, group_rows, row_offset);
     CUM_LAUNCH_CHECK("conv_in_kernel");
     return CUM_OK;
 }
@@ -157,7 +170,7 @@ int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CT_ROWS = 64;
 
-template <int LPR>
+template <int LPR, bool IN16>
 __global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict__ g, int rows_in, int c_pad,
                                                          const float* __restrict__ w, float bias,
                                                          const float* __restrict__ scale, int scale_groups,
@@ -180,8 +193,17 @@ __global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict_
         for (int k = 0; k < CT_MAXK; ++k) acc[k] = 0.f;
         if (r < nrows && j >= 0 && j < rows_in) {
             const float4* row = reinterpret_cast<const float4*>(g + ((long long)b * rows_in + j) * c_pad);
+            const uint2* row16 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g) + ((long long)b * rows_in + j) * c_pad);
             for (int c4 = sub; c4 < c4n; c4 += LPR) {
-                const float4 v = __ldg(row + c4);
+                float4 v;
+                if (IN16) {
+                    const uint2 raw = __ldg(row16 + c4);
+                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+                    const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+                    v = make_float4(a.x, a.y, c.x, c.y);
+                } else {
+                    v = __ldg(row + c4);
+                }
 #pragma unroll
                 for (int k = 0; k < CT_MAXK; ++k) {
                     if (k < kernel) {
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict_
 
 int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
                   const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
-                  int kernel, int stride, cudaStream_t st) {
+                  int kernel, int stride, cudaStream_t st, bool in_bf16) {
     CUM_REQUIRE(g && w && out, "convt_out: null pointer");
     CUM_REQUIRE(batch > 0 && batch <= 65535 && rows_in > 0 && length > 0 && first >= 0, "convt_out: empty problem");
     CUM_REQUIRE(c_pad > 0 && c_pad % 4 == 0, "convt_out: c_pad=%d must be a positive multiple of 4", c_pad);
@@ -232,10 +254,10 @@ int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float
     dim3 grid((unsigned)cdiv(length, (long long)CT_ROWS * stride), batch);
     const size_t smem = (size_t)(CT_ROWS + halo + 1) * kernel * sizeof(float);
     const int groups = scale ? (int)cdiv(length, scale_group) : 0;
-    if (c_pad <= 64)
-        convt_out_kernel<16><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, groups, scale_group, out, out_stride, first, length, kernel, stride, halo);
-    else
-        convt_out_kernel<32><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, groups, scale_group, out, out_stride, first, length, kernel, stride, halo);
+#define CT_LAUNCH(L, I) convt_out_kernel<L, I><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, groups, scale_group, out, out_stride, first, length, kernel, stride, halo)
+    if (c_pad <= 64) { if (in_bf16) CT_LAUNCH(16, true); else CT_LAUNCH(16, false); }
+    else             { if (in_bf16) CT_LAUNCH(32, true); else CT_LAUNCH(32, false); }
+#undef CT_LAUNCH
     CUM_LAUNCH_CHECK("convt_out_kernel");
     return CUM_OK;
 }

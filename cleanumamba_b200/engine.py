@@ -204,7 +204,10 @@ class Engine:
         self._flat = flat
         self.meta = meta
         self.device = dev
-        self.math = _lib.MATH_BY_NAME[getattr(self, "model_math_override", None) or getattr(m, "math_mode", "f16x3")]
+        mode = getattr(self, "model_math_override", None) or getattr(m, "math_mode", "f16x3")
+        self.bf16_io = mode == "bf16"          # reduced-precision variant: bf16 activation storage in the conv stacks
+        self.math = _lib.MATH_BY_NAME["f16x3" if self.bf16_io else mode]
+        self.pk16 = {k: t.to(torch.bfloat16) for k, t in items.items() if t.dim() >= 2} if self.bf16_io else {}
         self.lib = _lib.init(dev)
         self.pk_hi, self.pk_lo, self.w_scale_inv, self.w_lo_zero = {}, {}, {}, set()
         if self.math == _lib.MATH_TF32X3:      # hi/lo copies of the whole packed buffer (only GEMM weights use them)
@@ -258,29 +261,33 @@ class Engine:
     def gemm(self, a, a_off, a_bs, a_rs, a_rows, k, w, bias, c, c_off, c_bs, c_rs, m, n, batch, epi,
              taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None):
         d = GemmDesc()
-        d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k = a.data_ptr() + 4 * a_off, a_bs, a_rs, a_rows, k
+        d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k = a.data_ptr() + a.element_size() * a_off, a_bs, a_rs, a_rows, k
         d.taps = taps
         d.tap_shift[0], d.tap_shift[1] = shifts
         wt = self.pk[w]
         d.math = self.math if math is None else math
-        if d.math in (_lib.MATH_TF32X3, _lib.MATH_BF16X3, _lib.MATH_F16X3):
+        d.out_bf16 = 1 if c.dtype == torch.bfloat16 else 0
+        if a.dtype == torch.bfloat16:          # reduced-precision variant: bf16 activations x bf16 weights, one MMA pass
+            d.math = _lib.MATH_BF16
+            d.w, d.w_lo = self.pk16[w].data_ptr(), 0
+        elif d.math in (_lib.MATH_TF32X3, _lib.MATH_BF16X3, _lib.MATH_F16X3):
             d.w, d.w_lo = self.pk_hi[w].data_ptr(), self.pk_lo[w].data_ptr()
             d.acc_scale = self.w_scale_inv.get(w, 1.0)
             d.w_lo_is_zero = 1 if (self.skip_zero_lo and w in self.w_lo_zero) else 0
         else:
             d.w, d.w_lo = wt.data_ptr(), 0
         d.ldw, d.bias = wt.shape[-1], ptr(bias)
-        d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch = c.data_ptr() + 4 * c_off, c_bs, c_rs, m, n, batch
+        d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch = c.data_ptr() + c.element_size() * c_off, c_bs, c_rs, m, n, batch
         d.epilogue = epi
         d.addend, d.add_batch_stride, d.add_row_stride = ptr(addend), add_bs, add_rs
         kind = "gemm_tap2" if taps == 2 else "gemm"
         self._call(kind, self.lib.cum_gemm_bias_act_fwd, C.byref(d), _lib.stream_ptr(),
                    flops=2 * batch * m * n * k * taps)
 
-    def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None):
+    def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None, out_dtype=torch.float32):
         """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers."""
         n_out = n // 2 if epi >= 8 else n
-        c = out if out is not None else torch.empty(rows, n_out, dtype=torch.float32, device=a.device)
+        c = out if out is not None else torch.empty(rows, n_out, dtype=out_dtype, device=a.device)
         self.gemm(a, a_off, 0, k if a_rs is None else a_rs, rows, k, w, bias, c, 0, 0, n_out, rows, n, 1, epi,
                   addend=addend, add_bs=0, add_rs=n_out)
         return c
@@ -367,12 +374,17 @@ class Engine:
         for _ in range(D):
             Ls.append((Ls[-1] - 4) // 2 + 1)
 
+        adt = torch.bfloat16 if self.bf16_io else torch.float32      # storage type of the encoder / decoder activations
         skips: List[torch.Tensor] = []
         prev = None
         for i, e in enumerate(meta["enc"]):
             rows = B * Ls[i + 1]
-            y = torch.empty(rows, e["Hc_p"], dtype=torch.float32, device=x.device)
-            if i == 0:
+            y = torch.empty(rows, e["Hc_p"], dtype=adt, device=x.device)
+            if i == 0 and self.bf16_io:
+                self._call("conv_in", lib.cum_conv_in_bf16_fwd, x.data_ptr(), L, B, L, pk["enc0.w"].data_ptr(),
+                           pk["enc0.b"].data_ptr(), y.data_ptr(), Ls[1], e["Hc_p"], 4, 2, st(),
+                           nbytes=B * (4 * L + 2 * Ls[1] * e["Hc"]))
+            elif i == 0:
                 self._call("conv_in", lib.cum_conv_in_fwd, x.data_ptr(), L, B, L, pk["enc0.w"].data_ptr(),
                            pk["enc0.b"].data_ptr(), y.data_ptr(), Ls[1], e["Hc_p"], 4, 2, 0, 0, 0, st(),
                            nbytes=4 * B * (L + Ls[1] * e["Hc"]))
@@ -381,7 +393,7 @@ class Engine:
                 self.gemm(prev, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
                           y, 0, Ls[i + 1] * e["Hc_p"], e["Hc_p"], Ls[i + 1], e["Hc_p"], B, EPI_RELU, taps=2,
                           shifts=(0, 1))
-            prev = self.dense(y, rows, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act)
+            prev = self.dense(y, rows, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act, out_dtype=adt)
             skips.append(prev)
 
         T = Ls[D]
@@ -389,16 +401,16 @@ class Engine:
         cb_p = meta["enc"][-1]["Ho_p"]
         h = self.dense(prev, rows, cb_p, "t1.w", pk["t1.b"], meta["dm_p"])
         hn = self.mamba_layers(h, B, T)
-        xcur = self.dense(hn, rows, meta["dm_p"], "t2.w", pk["t2.b"], cb_p, addend=skips[D - 1])
+        xcur = self.dense(hn, rows, meta["dm_p"], "t2.w", pk["t2.b"], cb_p, addend=skips[D - 1], out_dtype=adt)
 
         Tj = T
         out = None
         for j, d in enumerate(meta["dec"]):
-            g = self.dense(xcur, B * Tj, d["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * d["Hg_p"], epi=act)
+            g = self.dense(xcur, B * Tj, d["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * d["Hg_p"], epi=act, out_dtype=adt)
             if j < D - 1:
                 co = d["Co_p"]
                 To = 2 * Tj + 2
-                nxt = torch.empty(B * To, co, dtype=torch.float32, device=x.device)
+                nxt = torch.empty(B * To, co, dtype=adt, device=x.device)
                 skip = skips[D - 2 - j]
                 self.gemm(g, 0, Tj * d["Hg_p"], d["Hg_p"], Tj, d["Hg_p"], f"dec{j}.w", pk[f"dec{j}.b"],
                           nxt, 0, To * co, 2 * co, Tj + 1, 2 * co, B, EPI_RELU, taps=2, shifts=(0, -1),
@@ -407,7 +419,8 @@ class Engine:
             else:
                 length = L if m.normalize_input else Ls[0]
                 out = torch.empty(B, 1, length, dtype=torch.float32, device=x.device)
-                self._call("convt_out", lib.cum_convt_out_fwd, g.data_ptr(), B, Tj, d["Hg_p"], pk[f"dec{j}.w"].data_ptr(),
+                self._call("convt_out", lib.cum_convt_out_bf16_fwd if self.bf16_io else lib.cum_convt_out_fwd,
+                           g.data_ptr(), B, Tj, d["Hg_p"], pk[f"dec{j}.w"].data_ptr(),
                            meta["out_bias"], ptr(std), length, out.data_ptr(), length, 0, length, 4, 2, st(),
                            nbytes=4 * B * (Tj * d["Hg"] + length))
         if not return_skip_connections:
@@ -415,6 +428,6 @@ class Engine:
         ncl = []
         for i in reversed(range(D)):      # the reference returns the skips deepest-first (:275) in (B, C, L)
             e = meta["enc"][i]
-            ncl.append(skips[i].view(B, Ls[i + 1], e["Ho_p"])[:, :, : e["Ho"]].permute(0, 2, 1))
+            ncl.append(skips[i].view(B, Ls[i + 1], e["Ho_p"])[:, :, : e["Ho"]].permute(0, 2, 1).float())
         ncl.append(hn.view(B, T, meta["dm_p"])[:, :, : meta["dm"]].permute(0, 2, 1))
         return out, ncl

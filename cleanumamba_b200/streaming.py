@@ -32,6 +32,8 @@ class StreamSession:
         self.model = model
         self.eng = model.engine()
         self.eng.ensure_packed()
+        if self.eng.bf16_io:
+            raise NotImplementedError("cleanumamba_b200: math_mode='bf16' (reduced-precision variant) is offline-forward only")
         self.B = batch
         self.dev = self.eng.device
         m, meta = model, self.eng.meta

@@ -28,7 +28,7 @@ class TrainEngine(Engine):
     tc_wgrad = True      # tensor-core weight gradients (tests may switch to the fp32 CUDA-core kernel)
 
     def _pack(self):
-        if getattr(self.model, "math_mode", None) == "f16x3":
+        if getattr(self.model, "math_mode", None) in ("f16x3", "bf16"):
             self.model_math_override = "tf32x3"
         super()._pack()
 

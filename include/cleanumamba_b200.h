@@ -48,6 +48,8 @@ extern "C" {
 #define CUM_MATH_TF32        2  /* tcgen05 kind::tf32, single pass (10-bit mantissa; NOT within the fp32 tolerance) */
 #define CUM_MATH_BF16X3      3  /* tcgen05 kind::f16 on bf16 hi/lo halves, 3 MMAs per product (~2^-16 rel. error per
                                    product; 2x the TF32X3 tensor rate; marginal (1.1e-4) at full-scale amplitude) */
+#define CUM_MATH_BF16        5  /* REDUCED PRECISION variant (reported separately): `a` and `w` are bf16 arrays, one
+                                   kind::f16 MMA pass, fp32 accumulate; ~3e-3 relative error per layer */
 #define CUM_MATH_F16X3       4  /* tcgen05 kind::f16 on fp16 hi/lo halves (11+11 bits, ~2^-21 per product like TF32X3)
                                    at the bf16 tensor rate; weights pre-scaled by a power of two (cum_split_f16),
                                    undone by acc_scale; activations converted with saturation at +-65504 */
@@ -92,6 +94,15 @@ int cum_convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const f
                       const float* scale, int scale_group, float* out, long long out_stride, int first,
                       int length, int kernel, int stride, cum_stream_t stream);
 
+/* bf16-storage variants of the two kernels above for the reduced-precision model variant (BASELINE.json configs[1]
+ * "fp32 and bf16"): cum_conv_in_bf16_fwd writes y as bf16, cum_convt_out_bf16_fwd reads g as bf16; fp32 arithmetic. */
+int cum_conv_in_bf16_fwd(const float* x, long long x_stride, int batch, int length, const float* w,
+                         const float* bias, void* y_bf16, int rows_out, int c_pad, int kernel, int stride,
+                         cum_stream_t stream);
+int cum_convt_out_bf16_fwd(const void* g_bf16, int batch, int rows_in, int c_pad, const float* w, float bias,
+                           const float* scale, int scale_group, float* out, long long out_stride, int first,
+                           int length, int kernel, int stride, cum_stream_t stream);
+
 /* ---- the tap-GEMM: every dense contraction of the path -------------------------------------- */
 /* out[b, m, :] = EPI( bias + sum_{s<taps} W_s . a[b, m + tap_shift[s], 0:k] ) (+ addend[b, m, :])
  * Rows of `a` outside [0, a_rows) read as zero.  One descriptor covers:
@@ -119,6 +130,7 @@ typedef struct cum_gemm_desc {
     const float* w_lo;       /* TF32X3 / BF16X3 only: low halves of the weights; `w` must then hold the high halves (both
                                 produced by cum_split_tf32 / cum_split_bf16 / cum_split_f16; 16-bit arrays for *16X3) */
     float acc_scale;         /* CUM_MATH_F16X3 only: accumulators are multiplied by this before the bias (1 / weight scale) */
+    int out_bf16;            /* BF16 / F16X3 only: `c` and `addend` are bf16 arrays (strides still in elements) */
     int w_lo_is_zero;        /* split modes: caller asserts every element of w_lo is exactly 0 (e.g. weights of a checkpoint
                                 shipped in fp16 under F16X3): the a_hi*w_lo pass is skipped -- identical result, 2 MMAs / product */
 } cum_gemm_desc;

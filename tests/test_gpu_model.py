@@ -210,3 +210,21 @@ def test_input_variants_batch1_noncontiguous_half():
     with torch.no_grad():
         y2 = net_h(base.clone().cuda())
     assert (y2.float().cpu() - ref).abs().max().item() <= TOL_MAXABS
+
+
+@pytest.mark.parametrize("name", ["e8_pruned_500k", "mini_mamba_442k", "e6_pruned_200k"])
+def test_bf16_storage_variant_reported_separately(name):
+    """math_mode="bf16": bf16 activation storage + single-pass bf16 tensor-core products in the encoder / decoder stacks
+    (BASELINE.json configs[1] "fp32 and bf16").  This variant is NOT inside the fp32 tolerance; it is held to a bf16-class
+    bound instead: relative rms error < 2 % and SI-SDR within 0.2 dB of the reference's."""
+    fx = load_golden(name)
+    net = build(fx, math_mode="bf16")
+    with torch.no_grad():
+        y = net(fx["noisy"].clone().cuda()).cpu()
+    ref = fx["denoised"]
+    rel = ((y - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    d = (orc.si_sdr(y, fx["clean"]) - orc.si_sdr(ref, fx["clean"])).abs().max().item()
+    print(f"\n[{name} bf16 variant] rel-rms error {rel:.3e}  max-abs {(y - ref).abs().max().item():.3e}  dSI-SDR {d:.3f} dB")
+    assert rel < 2e-2 and d < 0.2
+    with pytest.raises(NotImplementedError):
+        net.stream_session(batch=1)

@@ -15,7 +15,8 @@ def dev():
     return torch.device("cuda:0")
 
 
-GEMM_TOL = {"fp32": 1e-5, "tf32x3": 6e-5, "bf16x3": 1.5e-4, "f16x3": 6e-5}   # x3 modes: split error per product + truncating TMEM accumulation
+GEMM_TOL = {"fp32": 1e-5, "tf32x3": 6e-5, "bf16x3": 1.5e-4, "f16x3": 6e-5,
+            "tf32": 1e-2}          # single-pass TF32: offered, never default, outside the model tolerance   # x3 modes: split error per product + truncating TMEM accumulation
 
 
 def rel_err(a, b):
@@ -96,7 +97,7 @@ def _cl(x):  # (b, c, l) -> (b, l, c) contiguous on the GPU
     return x.permute(0, 2, 1).contiguous().to(dev())
 
 
-@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3", "f16x3"])
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3", "f16x3", "tf32"])
 @pytest.mark.parametrize("b,cin,cout,l", [(2, 64, 128, 300), (1, 768, 768, 150), (3, 56, 72, 38), (1, 8, 8, 6), (2, 104, 200, 1030)])
 def test_gemm_pointwise_and_glu(math, b, cin, cout, l):
     from cleanumamba_b200 import _lib, ops
@@ -205,3 +206,24 @@ def test_bad_arguments_fail_loudly():
         ops.gemm_bias_act(a, w)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.selective_scan_fn(*[torch.zeros(1, 4, 4)] * 2, torch.zeros(4, 4), torch.zeros(1, 4, 4), torch.zeros(1, 4, 4))
+
+
+@pytest.mark.parametrize("b,cin,cout,l", [(2, 64, 128, 300), (1, 768, 768, 150), (2, 104, 200, 1030)])
+def test_gemm_bf16_storage_mode(b, cin, cout, l):
+    """CUM_MATH_BF16: bf16 activations / weights from HBM, fp32 accumulate, bf16 or fp32 output (reduced-precision variant)."""
+    from cleanumamba_b200 import _lib
+    lib = _lib.init(dev())
+    g = torch.Generator().manual_seed(cin + l)
+    x = torch.randn(b, l, cin, generator=g).to(dev()).to(torch.bfloat16).contiguous()
+    w = (torch.randn(1, cout, cin, generator=g) / cin ** 0.5).to(dev()).to(torch.bfloat16).contiguous()
+    bias = torch.randn(cout, generator=g).to(dev())
+    ref = torch.relu(x.float() @ w[0].float().t() + bias)
+    for out_dt in (torch.float32, torch.bfloat16):
+        out = torch.empty(b, l, cout, dtype=out_dt, device=dev())
+        d = _lib.GemmDesc()
+        d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k, d.taps = x.data_ptr(), l * cin, cin, l, cin, 1
+        d.w, d.ldw, d.bias = w.data_ptr(), cin, bias.data_ptr()
+        d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch, d.epilogue = out.data_ptr(), l * cout, cout, l, cout, b, _lib.EPI_RELU
+        d.math, d.out_bf16 = _lib.MATH_BF16, int(out_dt == torch.bfloat16)
+        _lib.check(lib.cum_gemm_bias_act_fwd(C.byref(d), _lib.stream_ptr()), "gemm bf16")
+        assert rel_err(out.float(), ref) < (2e-5 if out_dt == torch.float32 else 6e-3), out_dt
