@@ -24,6 +24,7 @@
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace cum {
@@ -44,20 +45,26 @@ constexpr int TC_EPI_ATOMIC_ADD = -3;         // wgrad split-K: accumulate the t
 // BN = tile width (256, or 128 for narrow layers: smaller W box -> deeper pipeline for the HBM-bound layers)
 constexpr int TC_TF32 = 0, TC_TF32X3 = 1, TC_BF16X3 = 2, TC_F16X3 = 3;   // F16X3: like BF16X3 with fp16 halves (11+11 bits)
 constexpr int TC_BF16 = 4;   // bf16 activations straight from HBM (no splitter), one kind::f16 pass -- the reduced-precision variant
-template <int MODE, int BN> struct TcCfg {
+// CTA2: two CTAs of a cluster (an SM pair) work on ONE 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages its own 128
+// rows of A and only HALF of the W tile (the MMA reads the other half from the peer's shared memory), which cuts the
+// L2 -> SM operand traffic per flop by a third (f16x3) to a half (bf16) -- the measured bound of the K >= 512 layers.
+template <int MODE, int BN, bool CTA2 = false> struct TcCfg {
     static constexpr bool SPLIT = MODE != TC_TF32 && MODE != TC_BF16;   // operand-splitter warps present
     static constexpr bool PLAIN16 = MODE == TC_BF16;                    // 16-bit operands, 128-byte rows = 64 elements per K-block
     static constexpr int BK = PLAIN16 ? 64 : TC_BK;                     // elements per K-block (always 128 B of A per row)
     static constexpr bool HALF = (MODE == TC_BF16X3 || MODE == TC_F16X3);    // 16-bit MMA operands
-    static constexpr uint32_t W_BYTES = BN * TC_BK * (HALF ? 2 : 4);
+    static constexpr int W_ROWS = CTA2 ? BN / 2 : BN;                   // W rows (output columns) staged by one CTA
+    static constexpr uint32_t W_BYTES = W_ROWS * TC_BK * (HALF ? 2 : 4);
     static constexpr uint32_t AOP_BYTES = HALF ? TC_A_BYTES / 2 : TC_A_BYTES;   // one MMA A-operand tile
-    // stage layout: [A raw fp32 (= A_hi for the TF32 modes) | A_hi (bf16 mode only) | A_lo | W_hi | W_lo]
-    static constexpr uint32_t AHI_OFF = HALF ? TC_A_BYTES : 0;
-    static constexpr uint32_t ALO_OFF = AHI_OFF + AOP_BYTES;
-    static constexpr uint32_t W_OFF = SPLIT ? ALO_OFF + AOP_BYTES : TC_A_BYTES;
+    // stage layout: [A raw fp32 | A_lo (TF32X3) | W_hi | W_lo].  Both kinds of split are done IN PLACE: TF32X3 masks the raw tile
+    // into A_hi; the 16-bit modes overwrite the 16 KB raw tile with its 8 KB hi + 8 KB lo tiles (all reads, a named barrier,
+    // then the writes).  Smaller stages = a deeper TMA ring: the main loop is bound by bytes in flight, not by the MMA rate
+    static constexpr uint32_t AHI_OFF = 0;
+    static constexpr uint32_t ALO_OFF = HALF ? AOP_BYTES : TC_A_BYTES;
+    static constexpr uint32_t W_OFF = (SPLIT && !HALF) ? 2 * TC_A_BYTES : TC_A_BYTES;
     static constexpr uint32_t WLO_OFF = W_OFF + W_BYTES;
     static constexpr uint32_t STAGE_BYTES = SPLIT ? WLO_OFF + W_BYTES : W_OFF + W_BYTES;
-    static constexpr int STAGES = (int)(196608u / STAGE_BYTES);
+    static constexpr int STAGES = (int)(229376u / STAGE_BYTES);          // 224 KB ring (+ 1.25 KB of barriers / alignment slack <= 227 KB)
     static constexpr uint32_t TX_BYTES = TC_A_BYTES + (SPLIT ? 2 : 1) * W_BYTES;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int THREADS = (4 + TC_EPI_WARPS + (SPLIT ? 4 : 0)) * 32;   // last 4 warps = operand splitter
@@ -153,6 +160,72 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// wait on a barrier of THIS CTA that peers arrive on remotely
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+// TMA load issued by either CTA of a pair; the bytes are accounted on `bar`, a shared::cluster barrier address (the leader's)
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on `bar` (same offset) in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <bool CTA2> __device__ __forceinline__ void umma_f16_any(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) {
+    if (CTA2) umma_bf16_2sm(d, a, b, i, acc); else umma_bf16(d, a, b, i, acc);
+}
+template <bool CTA2> __device__ __forceinline__ void umma_tf32_any(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) {
+    if (CTA2) umma_tf32_2sm(d, a, b, i, acc); else umma_tf32(d, a, b, i, acc);
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
@@ -234,11 +307,11 @@ __device__ __forceinline__ float tc_act(int epi, float v) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int MODE, int BN, int EPI, bool OUT16>
-__global__ void __launch_bounds__(TcCfg<MODE, BN>::THREADS, 1)
+template <int MODE, int BN, int EPI, bool OUT16, bool CTA2>
+__global__ void __launch_bounds__(TcCfg<MODE, BN, CTA2>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                const __grid_constant__ CUtensorMap tmWl, const TcParams p) {
-    using Cfg = TcCfg<MODE, BN>;
+    using Cfg = TcCfg<MODE, BN, CTA2>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool X3 = Cfg::SPLIT;
     constexpr bool BF = Cfg::HALF;               // 16-bit SPLIT operand tiles (bf16 or fp16, 64-byte swizzle)
@@ -262,8 +335,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
+    const int total_tiles = p.batch * p.m_tiles * p.n_tiles;      // CTA2: tiles are 256 rows tall (p.m_tiles counts those)
     const int k_iters = p.k_blocks * p.taps;
+    // CTA pair: rank 0 (the leader) issues the MMAs for both; every barrier the MMA thread waits on lives in the leader
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+    const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tstep = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -272,20 +349,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
-            mbar_init(split_bar(s), 128);
+            mbar_init(split_bar(s), CTA2 ? 8 : 128);               // CTA2: one arrival per splitter warp of both CTAs
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), TC_EPI_WARPS * 32);
+            mbar_init(tempty_bar(a), CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS * 32);   // CTA2: one per epilogue warp of both CTAs
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (CTA2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();     // CTA2: the peer's barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -294,54 +376,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = tile / p.n_tiles;
         const int mb = r % p.m_tiles;
         b = r / p.m_tiles;
-        m0 = mb * TC_BM;
+        m0 = CTA2 ? mb * (2 * TC_BM) + (int)rank * TC_BM : mb * TC_BM;      // this CTA's 128 rows
         n0 = nb * BN;
+    };
+    auto tile_umma_n = [&](int n0) {
+        int n_rem = p.n - n0;
+        if (n_rem > BN) n_rem = BN;
+        return (uint32_t)((n_rem + 15) & ~15);
     };
 
     if (warp == 0 && lane == 0) {
         // ===================================================================== TMA producer
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < total_tiles; tile += tstep) {
             int b, m0, n0;
             tile_coords(tile, b, m0, n0);
+            // CTA2: this CTA stages the W rows of ITS half of the tile's columns (the MMA splits N across the pair)
+            const int wn = CTA2 ? n0 + (int)rank * (int)(tile_umma_n(n0) >> 1) : n0;
             for (int it = 0; it < k_iters; ++it) {
                 const int tap = it / p.k_blocks, kb = it - tap * p.k_blocks;
                 const int shift = tap == 0 ? p.shift0 : p.shift1;
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 const bool load_lo = X3 && !p.skip_wlo;
                 // bytes this stage will receive: A + W_hi (+ W_lo unless it is skipped); non-split modes have no W_lo at all
-                mbar_arrive_expect_tx(full_bar(s), (X3 && !load_lo) ? Cfg::TX_BYTES - Cfg::W_BYTES : Cfg::TX_BYTES);
-                // wgrad (split-K over rows): the split index selects a column range of ONE 2-D operand instead of a batch plane
-                if (p.w_k_batch_stride) tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK + b * p.w_k_batch_stride, m0, 0);
-                else tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK, m0 + shift, b);
+                const uint32_t tx = (X3 && !load_lo) ? Cfg::TX_BYTES - Cfg::W_BYTES : Cfg::TX_BYTES;
                 const int wk = kb * Cfg::BK + b * p.w_k_batch_stride + p.w_k_off;
-                tma_load_3d(smem_base + w_off(s), &tmWh, full_bar(s), wk, n0, tap);
-                if (load_lo) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), wk, n0, tap);
+                if (CTA2 && !X3) {
+                    // no splitter in between: the leader's MMA thread waits for the bytes of BOTH CTAs on its own barrier
+                    const uint32_t lbar = mapa_rank(full_bar(s), 0);
+                    if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * tx);
+                    tma_load_3d_2sm(smem_base + a_off(s), &tmA, lbar, kb * Cfg::BK, m0 + shift, b);
+                    tma_load_3d_2sm(smem_base + w_off(s), &tmWh, lbar, wk, wn, tap);
+                } else {
+                    mbar_arrive_expect_tx(full_bar(s), tx);
+                    // wgrad (split-K over rows): the split index selects a column range of ONE 2-D operand instead of a batch plane
+                    if (p.w_k_batch_stride) tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK + b * p.w_k_batch_stride, m0, 0);
+                    else tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK, m0 + shift, b);
+                    tma_load_3d(smem_base + w_off(s), &tmWh, full_bar(s), wk, wn, tap);
+                    if (load_lo) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), wk, wn, tap);
+                }
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================================================================== MMA issuer
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===================================================================== MMA issuer (CTA2: the leader, for both CTAs)
         int s = 0;
         uint32_t ph = 0;
         int tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        for (int tile = tile0; tile < total_tiles; tile += tstep, ++tcount) {
             int b, m0, n0;
             tile_coords(tile, b, m0, n0);
             const int acc = tcount & 1;
             const uint32_t acc_ph = (tcount >> 1) & 1;
-            int n_rem = p.n - n0;
-            if (n_rem > BN) n_rem = BN;
-            const uint32_t umma_n = (uint32_t)((n_rem + 15) & ~15);
+            const uint32_t umma_n = tile_umma_n(n0);
             // c=f32 (1<<4); a/b format 2 = tf32, 1 = bf16 (bits 7, 10); K-major both; N>>3 at bit 17, M>>4 at bit 24
             const uint32_t fmt = F16 ? 0u : ((BF || P16) ? 1u : 2u);       // 0 = f16, 1 = bf16, 2 = tf32
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((umma_n >> 3) << 17) |
+                                   ((uint32_t)((CTA2 ? 2 * TC_BM : TC_BM) >> 4) << 24);
             const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
-            mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+            if (CTA2) mbar_wait_cluster(tempty_bar(acc), acc_ph ^ 1u); else mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
             tc_fence_after();
             for (int it = 0; it < k_iters; ++it) {
-                mbar_wait(X3 ? split_bar(s) : full_bar(s), ph);
+                if (CTA2) mbar_wait_cluster(X3 ? split_bar(s) : full_bar(s), ph); else mbar_wait(X3 ? split_bar(s) : full_bar(s), ph);
                 tc_fence_after();
                 const uint64_t adesc = BF ? umma_desc_sw64(smem_base + ahi_off(s)) : umma_desc_sw128(smem_base + ahi_off(s));
                 const uint64_t bdesc = BF ? umma_desc_sw64(smem_base + w_off(s)) : umma_desc_sw128(smem_base + w_off(s));
@@ -351,21 +448,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kk = 0; kk < Cfg::BK / Cfg::UMMA_K; ++kk) {
                     const uint64_t koff = (uint64_t)(kk * 2);          // 32 bytes per k-step in both element types
                     if (P16) {
-                        umma_bf16(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
+                        umma_f16_any<CTA2>(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
                     } else if (BF) {
-                        umma_bf16(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
-                        umma_bf16(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
-                        if (!p.skip_wlo) umma_bf16(tmem_d, adesc + koff, blo + koff, idesc, 1u);
+                        umma_f16_any<CTA2>(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
+                        umma_f16_any<CTA2>(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
+                        if (!p.skip_wlo) umma_f16_any<CTA2>(tmem_d, adesc + koff, blo + koff, idesc, 1u);
                     } else {
-                        umma_tf32(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
+                        umma_tf32_any<CTA2>(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
                         if (X3) {
-                            umma_tf32(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
-                            if (!p.skip_wlo) umma_tf32(tmem_d, adesc + koff, blo + koff, idesc, 1u);
+                            umma_tf32_any<CTA2>(tmem_d, alo + koff, bdesc + koff, idesc, 1u);
+                            if (!p.skip_wlo) umma_tf32_any<CTA2>(tmem_d, adesc + koff, blo + koff, idesc, 1u);
                         }
                     }
                 }
-                umma_commit(empty_bar(s));
-                if (it == k_iters - 1) umma_commit(tfull_bar(acc));
+                // the stage is free / the accumulator is complete in BOTH CTAs once these MMAs retire
+                if (CTA2) umma_commit_2sm(empty_bar(s)); else umma_commit(empty_bar(s));
+                if (it == k_iters - 1) { if (CTA2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc)); }
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
@@ -375,7 +473,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int sub = (warp - 4) >> 2;        // which of every four 32-column chunks
         const int tq = lane & 3, tr = lane >> 2;
         int tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t tempty_leader = CTA2 ? mapa_rank(tempty_bar(0), 0) : 0u;
+        for (int tile = tile0; tile < total_tiles; tile += tstep, ++tcount) {
             int b, m0, n0;
             tile_coords(tile, b, m0, n0);
             const int acc = tcount & 1;
@@ -461,14 +560,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            if (CTA2) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader + 8u * acc);
+            } else {
+                mbar_arrive(tempty_bar(acc));
+            }
         }
     } else if (X3 && warp >= 4 + TC_EPI_WARPS) {
         // ===================================================================== operand splitter (A tile)
         const int t = threadIdx.x - (4 + TC_EPI_WARPS) * 32;
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const uint32_t split_leader = CTA2 ? mapa_rank(split_bar(0), 0) : 0u;
+        for (int tile = tile0; tile < total_tiles; tile += tstep) {
             for (int it = 0; it < k_iters; ++it) {
                 mbar_wait(full_bar(s), ph);
                 if (BF) {
@@ -476,12 +581,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint8_t* raw = smem_gen + a_off(s);
                     uint8_t* hi = smem_gen + ahi_off(s);
                     uint8_t* lo = smem_gen + alo_off(s);
+                    // hi / lo overwrite the raw tile: every splitter thread first pulls its 4 x 32 bytes into registers
+                    float4 va[4], vb[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int i = t + 128 * j;
                         const int r = i >> 2, co = i & 3;              // row, 16-byte output chunk (8 bf16 = 8 k)
-                        const float4 v0 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * co) ^ (r & 7)) << 4));
-                        const float4 v1 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * co + 1) ^ (r & 7)) << 4));
+                        va[j] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * co) ^ (r & 7)) << 4));
+                        vb[j] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * co + 1) ^ (r & 7)) << 4));
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");     // the four splitter warps only
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = t + 128 * j;
+                        const int r = i >> 2, co = i & 3;
+                        const float4 v0 = va[j], v1 = vb[j];
                         const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                         uint32_t h[4], l[4];
 #pragma unroll
@@ -522,17 +636,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 }
                 fence_proxy_async();
-                mbar_arrive(split_bar(s));
+                if (CTA2) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(split_leader + 8u * s);
+                } else {
+                    mbar_arrive(split_bar(s));
+                }
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
     }
 
+    __syncwarp();
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();     // CTA2: neither CTA may exit while its peer still reads its smem / TMEM
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS));
+        if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS));
     }
 }
 
@@ -628,13 +749,13 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1,
 // split-K (wgrad) launch context: set by wgrad_tc_fwd around its launches (host-side, per calling thread)
 static thread_local int g_wgrad_kbs = 0, g_wgrad_koff = 0;
 
-template <int MODE, int BN, int EPI, bool OUT16 = false>
+template <int MODE, int BN, int EPI, bool OUT16 = false, bool CTA2 = false>
 static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
-    using Cfg = TcCfg<MODE, BN>;
+    using Cfg = TcCfg<MODE, BN, CTA2>;
     constexpr bool X3 = Cfg::SPLIT;
     constexpr bool BF = Cfg::HALF;
     constexpr bool P16 = Cfg::PLAIN16;
-    auto kern = gemm_tc_kernel<MODE, BN, EPI, OUT16>;
+    auto kern = gemm_tc_kernel<MODE, BN, EPI, OUT16, CTA2>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -648,10 +769,10 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     if (rc) return rc;
     const uint64_t w_ts = (uint64_t)d.n * (uint64_t)d.ldw;
     const uint64_t w_k_extent = g_wgrad_kbs ? (uint64_t)d.ldw : (uint64_t)d.k;     // wgrad: W columns span every split
-    rc = make_map(&tmWh, d.w, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, Cfg::BK, BN, "W", BF || P16, P16);
+    rc = make_map(&tmWh, d.w, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, Cfg::BK, Cfg::W_ROWS, "W", BF || P16, P16);
     if (rc) return rc;
     if (X3) {
-        rc = make_map(&tmWl, d.w_lo, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, BN, "W_lo", BF);
+        rc = make_map(&tmWl, d.w_lo, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, Cfg::W_ROWS, "W_lo", BF);
         if (rc) return rc;
     } else {
         tmWl = tmWh;
@@ -659,7 +780,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     TcParams p;
     p.m = d.m; p.n = d.n; p.k = d.k; p.taps = d.taps; p.shift0 = d.tap_shift[0]; p.shift1 = d.tap_shift[1];
     p.batch = d.batch; p.epi = d.epilogue;
-    p.m_tiles = (int)cdiv(d.m, TC_BM); p.n_tiles = (int)cdiv(d.n, BN); p.k_blocks = (int)cdiv(d.k, Cfg::BK);
+    p.m_tiles = (int)cdiv(d.m, CTA2 ? 2 * TC_BM : TC_BM); p.n_tiles = (int)cdiv(d.n, BN); p.k_blocks = (int)cdiv(d.k, Cfg::BK);
     p.bias = d.bias; p.c = d.c; p.c_bs = d.c_batch_stride; p.c_rs = d.c_row_stride;
     p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
     p.acc_scale = (MODE == TC_F16X3) ? d.acc_scale : 1.0f;
@@ -667,30 +788,77 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.w_k_batch_stride = g_wgrad_kbs; p.w_k_off = g_wgrad_koff;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
     CUM_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
+    if (CTA2) {
+        // one cluster of two CTAs (an SM pair of one TPC) per 256-row tile
+        const int pairs = sm_count() / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs)));
+        cfg.blockDim = dim3(Cfg::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmWh, tmWl, p);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tc_kernel, cluster 2)");
+        return CUM_OK;
+    }
     const int grid = (int)(total < sm_count() ? total : sm_count());
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmWh, tmWl, p);
     CUM_LAUNCH_CHECK("gemm_tc_kernel");
     return CUM_OK;
 }
 
-template <int MODE, int BN>
-static int dispatch_epi(const cum_gemm_desc& d, cudaStream_t st) {
+// CTA-pair policy for the 256-wide tiles.  Measured on B200 (E8 layer shapes, batch 64 x 10 s): the pair kernel is 8 % faster
+// than the single-CTA kernel in the TF32 modes (128-byte-swizzled operand rows), no faster with plain bf16 operands and
+// ~1.7x SLOWER with the 64-byte-swizzled 16-bit hi/lo tiles of BF16X3 / F16X3 -- so "auto" pairs only the TF32 modes.
+// CUM_GEMM_CTA2=0 disables pairs, =1 forces them for every mode (A/B measurements); cum_gemm_desc.cta_pair overrides per call.
+static int cta2_policy() {
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("CUM_GEMM_CTA2");
+        v = !e ? 0 : (e[0] == '0' ? -1 : 1);
+    }
+    return v;
+}
+
+template <int MODE, int BN, bool CTA2>
+static int dispatch_epi2(const cum_gemm_desc& d, cudaStream_t st) {
     if (d.out_bf16) {       // bf16 output / addend: only the epilogues the bf16 variant of the model uses
-        switch (d.epilogue) {
-            case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, true>(d, st);
-            case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, true>(d, st);
-            case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, true>(d, st);
-            default: set_error("gemm_tc: bf16 output supports NONE / RELU / GLU_SIGMOID epilogues"); return CUM_ENOTSUP;
+        if constexpr (MODE == TC_BF16 || MODE == TC_F16X3) {
+            switch (d.epilogue) {
+                case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, true, CTA2>(d, st);
+                case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, true, CTA2>(d, st);
+                case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, true, CTA2>(d, st);
+                default: set_error("gemm_tc: bf16 output supports NONE / RELU / GLU_SIGMOID epilogues"); return CUM_ENOTSUP;
+            }
+        } else {
+            set_error("gemm_tc: bf16 output is available for the BF16 and F16X3 modes");
+            return CUM_ENOTSUP;
         }
     }
     switch (d.epilogue) {
-        case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE>(d, st);
-        case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU>(d, st);
-        case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID>(d, st);
+        case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, false, CTA2>(d, st);
+        case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, false, CTA2>(d, st);
+        case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, false, CTA2>(d, st);
         default:
-            return epi_is_glu(d.epilogue) ? launch_tc<MODE, BN, TC_EPI_GENERIC_GLU>(d, st)
-                                          : launch_tc<MODE, BN, TC_EPI_GENERIC_UNARY>(d, st);
+            return epi_is_glu(d.epilogue) ? launch_tc<MODE, BN, TC_EPI_GENERIC_GLU, false, CTA2>(d, st)
+                                          : launch_tc<MODE, BN, TC_EPI_GENERIC_UNARY, false, CTA2>(d, st);
     }
+}
+
+template <int MODE, int BN>
+static int dispatch_epi(const cum_gemm_desc& d, cudaStream_t st) {
+    if constexpr (BN == 256) {
+        // a CTA pair per 256 x 256 tile when there are enough rows to fill whole pairs
+        const int pol = d.cta_pair != 0 ? d.cta_pair : cta2_policy();
+        const bool want = pol > 0 || (pol == 0 && (MODE == TC_TF32X3 || MODE == TC_TF32));
+        if (want && d.m > TC_BM && (sm_count() & 1) == 0) return dispatch_epi2<MODE, BN, true>(d, st);
+    }
+    return dispatch_epi2<MODE, BN, false>(d, st);
 }
 
 // ------------------------------------------------------------------------------------------------ tensor-core wgrad

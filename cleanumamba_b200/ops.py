@@ -127,7 +127,7 @@ def block_forward(block, hidden_states, residual=None, inference_params=None):
 
 
 @torch.no_grad()
-def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None, addend=None, math="fp32"):
+def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None, addend=None, math="fp32", cta_pair=0):
     """Raw tap-GEMM on channels-last tensors (thin wrapper of cum_gemm_bias_act_fwd, used by tests / benchmarks).
     a: (batch, rows, K) fp32 contiguous, K % 4 == 0;  w: (taps, N, K), N % 8 == 0;  bias: (N);  addend: (batch, m, N_out).
     out[b, i, :] = EPI(bias + sum_s W_s . a[b, i + shifts[s], :]) + addend[b, i, :]   (rows outside a read as 0)."""
@@ -163,5 +163,6 @@ def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None
     d.ldw, d.bias = k, ptr(bias)
     d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch, d.epilogue = out.data_ptr(), m * n_out, n_out, m, n, batch, epilogue
     d.addend, d.add_batch_stride, d.add_row_stride = ptr(addend), m * n_out, n_out
+    d.cta_pair = cta_pair
     check(lib.cum_gemm_bias_act_fwd(C.byref(d), _lib.stream_ptr()), "cum_gemm_bias_act_fwd")
     return out

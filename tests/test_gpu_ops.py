@@ -169,13 +169,14 @@ def test_wave_ends():
     # conv_in with implicit right padding to 1022 -> rows_out 510
     Lp = orc.valid_length(L, 3)
     rows = (Lp - 4) // 2 + 1
-    w, bias = torch.randn(H, 1, 4, generator=g), torch.randn(H, generator=g)
-    ref = F.relu(F.conv1d(F.pad(x, (0, Lp - L))[:, None], w, bias, stride=2))
-    y = torch.empty(B, rows, H, device=dev())
-    xd, wd, bd = x.to(dev()), w[:, 0].t().contiguous().to(dev()), bias.to(dev())   # keep alive: raw pointers cross the ABI
-    _lib.check(lib.cum_conv_in_fwd(xd.data_ptr(), L, B, L, wd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, H, 4, 2, 0, 0, 0,
-                                   _lib.stream_ptr()), "conv_in")
-    assert rel_err(y.permute(0, 2, 1), ref) < 1e-6
+    for H in (56, 64):      # 64 channels: the specialised kernel of the shipped geometry
+        w, bias = torch.randn(H, 1, 4, generator=g), torch.randn(H, generator=g)
+        ref = F.relu(F.conv1d(F.pad(x, (0, Lp - L))[:, None], w, bias, stride=2))
+        y = torch.empty(B, rows, H, device=dev())
+        xd, wd, bd = x.to(dev()), w[:, 0].t().contiguous().to(dev()), bias.to(dev())   # keep alive: raw pointers cross the ABI
+        _lib.check(lib.cum_conv_in_fwd(xd.data_ptr(), L, B, L, wd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, H, 4, 2, 0, 0, 0,
+                                       _lib.stream_ptr()), "conv_in")
+        assert rel_err(y.permute(0, 2, 1), ref) < 1e-6
     # convt_out
     for Hc in (56, 64, 128):
         gin = torch.randn(B, Hc, rows, generator=g)
@@ -227,3 +228,27 @@ def test_gemm_bf16_storage_mode(b, cin, cout, l):
         d.math, d.out_bf16 = _lib.MATH_BF16, int(out_dt == torch.bfloat16)
         _lib.check(lib.cum_gemm_bias_act_fwd(C.byref(d), _lib.stream_ptr()), "gemm bf16")
         assert rel_err(out.float(), ref) < (2e-5 if out_dt == torch.float32 else 6e-3), out_dt
+
+
+@pytest.mark.parametrize("math", ["f16x3", "tf32x3", "bf16x3", "tf32"])
+@pytest.mark.parametrize("b,k,n,m,taps", [(1, 64, 256, 129, 1), (2, 128, 768, 700, 1), (1, 96, 160, 300, 1), (3, 256, 512, 257, 2),
+                                          (1, 1536, 768, 1000, 2), (2, 64, 264, 256, 1), (1, 512, 1536, 5000, 1)])
+def test_gemm_cta_pair_is_bit_identical_to_single_cta(math, b, k, n, m, taps):
+    """Tiles wider than 128 columns run on CTA pairs (tcgen05 cta_group::2, 256-row tiles, half a weight tile per CTA).  Same
+    products, same accumulation order: the result must equal the single-CTA kernel's bit for bit -- ragged row counts (a
+    peer CTA with no rows), ragged column counts (N split unevenly over the pair), taps, batches, GLU + addend."""
+    from cleanumamba_b200 import _lib, ops
+    g = torch.Generator().manual_seed(k + n + m)
+    rows = m + 1 if taps == 2 else m
+    a = torch.randn(b, rows, k, generator=g).to(dev())
+    w = (torch.randn(taps, n, k, generator=g) / (taps * k) ** 0.5).to(dev())
+    bias = torch.randn(n, generator=g).to(dev())
+    add = torch.randn(b, m, n // 2, generator=g).to(dev())
+    shifts = (0, 1) if taps == 2 else (0, 0)
+    for epi, ad in ((_lib.EPI_RELU, None), (_lib.EPI_GLU["Sigmoid"], add)):
+        pair = ops.gemm_bias_act(a, w, bias, epi, shifts=shifts, m=m, addend=ad, math=math, cta_pair=1)
+        single = ops.gemm_bias_act(a, w, bias, epi, shifts=shifts, m=m, addend=ad, math=math, cta_pair=-1)
+        assert torch.equal(pair, single), (pair - single).abs().max().item()
+    ref = torch.relu(sum(F.pad(a, (0, 0, 0, 1))[:, s:s + m].double().cpu() @ w[t].double().cpu().t()
+                         for t, s in enumerate(shifts[:taps])) + bias.double().cpu())
+    assert rel_err(ops.gemm_bias_act(a, w, bias, _lib.EPI_RELU, shifts=shifts, m=m, math=math), ref) < GEMM_TOL[math]
