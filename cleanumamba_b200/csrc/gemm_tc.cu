@@ -175,14 +175,18 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
     return r;
 }
+// Remote arrive with the default .release.cta semantics (what CUTLASS' ClusterBarrier::arrive(cta_id) issues).  A
+// .release.cluster arrive compiles to ERRBAR (a full memory barrier, ~1 us) + SYNCS.ARRIVE and sat on the per-K-block critical
+// path; everything the leader consumes after this signal is shared memory already made visible to the async proxy by
+// fence.proxy.async + a cta-scope release/acquire inside the peer, or TMEM ordered by tcgen05.fence.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
@@ -349,7 +353,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
-            mbar_init(split_bar(s), CTA2 ? 8 : 128);               // CTA2: one arrival per splitter warp of both CTAs
+            // CTA2: one arrival per local splitter warp; the leader's barrier also takes one from the peer's forwarder thread
+            mbar_init(split_bar(s), CTA2 ? (rank == 0 ? 5 : 4) : 128);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -467,6 +472,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
+    } else if (CTA2 && X3 && warp == 1 && lane == 0 && rank == 1) {
+        // ===================================================================== peer CTA: forward "my A tile is split" to the leader
+        // A release at cluster scope costs a full memory barrier (ERRBAR); issued by the splitter warps themselves it sat on the
+        // split -> MMA critical path of every K-block (pair kernel 1.7x slower than single).  The splitters now signal a local
+        // barrier (cta scope) and this otherwise idle thread relays it: wait (acquire.cta) -> arrive on the leader (release.cluster)
+        int s = 0;
+        uint32_t ph = 0;
+        const uint32_t split_leader = mapa_rank(split_bar(0), 0);
+        for (int tile = tile0; tile < total_tiles; tile += tstep) {
+            for (int it = 0; it < k_iters; ++it) {
+                mbar_wait(split_bar(s), ph);
+                mbar_arrive_cluster(split_leader + 8u * s);
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
     } else if (warp >= 4 && warp < 4 + TC_EPI_WARPS) {
         // ===================================================================== epilogue (16 warps)
         const int q = warp & 3;                 // TMEM lane quarter this warp may touch
@@ -572,7 +592,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int t = threadIdx.x - (4 + TC_EPI_WARPS) * 32;
         int s = 0;
         uint32_t ph = 0;
-        const uint32_t split_leader = CTA2 ? mapa_rank(split_bar(0), 0) : 0u;
         for (int tile = tile0; tile < total_tiles; tile += tstep) {
             for (int it = 0; it < k_iters; ++it) {
                 mbar_wait(full_bar(s), ph);
@@ -638,7 +657,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 fence_proxy_async();
                 if (CTA2) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(split_leader + 8u * s);
+                    if (lane == 0) mbar_arrive(split_bar(s));          // local; the peer's forwarder relays it to the leader
                 } else {
                     mbar_arrive(split_bar(s));
                 }
@@ -812,10 +831,10 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     return CUM_OK;
 }
 
-// CTA-pair policy for the 256-wide tiles.  Measured on B200 (E8 layer shapes, batch 64 x 10 s): the pair kernel is 8 % faster
-// than the single-CTA kernel in the TF32 modes (128-byte-swizzled operand rows), no faster with plain bf16 operands and
-// ~1.7x SLOWER with the 64-byte-swizzled 16-bit hi/lo tiles of BF16X3 / F16X3 -- so "auto" pairs only the TF32 modes.
-// CUM_GEMM_CTA2=0 disables pairs, =1 forces them for every mode (A/B measurements); cum_gemm_desc.cta_pair overrides per call.
+// CTA-pair policy for the 256-wide tiles.  Measured on B200 (E8 full, batch 64 x 10 s, whole forward): pairs are faster in every
+// mode -- f16x3 46.2 vs 48.9 ms, tf32x3 62.1 vs 71.2, bf16x3 43.0 vs 45.3, bf16 24.5 vs 25.5 -- once no cluster-scope fence is
+// left on the per-K-block path (with .release.cluster arrives the pair kernel was 1.7x SLOWER; see mbar_arrive_cluster).
+// CUM_GEMM_CTA2=0 disables pairs (A/B measurements); cum_gemm_desc.cta_pair overrides per call.
 static int cta2_policy() {
     static int v = -2;
     if (v == -2) {
@@ -855,7 +874,7 @@ static int dispatch_epi(const cum_gemm_desc& d, cudaStream_t st) {
     if constexpr (BN == 256) {
         // a CTA pair per 256 x 256 tile when there are enough rows to fill whole pairs
         const int pol = d.cta_pair != 0 ? d.cta_pair : cta2_policy();
-        const bool want = pol > 0 || (pol == 0 && (MODE == TC_TF32X3 || MODE == TC_TF32));
+        const bool want = pol >= 0;
         if (want && d.m > TC_BM && (sm_count() & 1) == 0) return dispatch_epi2<MODE, BN, true>(d, st);
     }
     return dispatch_epi2<MODE, BN, false>(d, st);

@@ -134,8 +134,8 @@ typedef struct cum_gemm_desc {
     int w_lo_is_zero;        /* split modes: caller asserts every element of w_lo is exactly 0 (e.g. weights of a checkpoint
                                 shipped in fp16 under F16X3): the a_hi*w_lo pass is skipped -- identical result, 2 MMAs / product */
     int cta_pair;            /* tiles wider than 128 columns can run on CTA pairs (tcgen05 cta_group::2: 256-row tiles, each CTA
-                                stages half of the weight tile).  0 = automatic (pairs where they measured faster: the TF32 modes),
-                                1 = always, -1 = never.  Same products, same accumulation order: bit-identical results */
+                                stages half of the weight tile).  0 = automatic (pairs whenever a problem has more than 128 rows),
+                                1 = same, -1 = never.  Same products, same accumulation order: bit-identical results */
 } cum_gemm_desc;
 int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream);
 
