@@ -82,7 +82,13 @@ int cum_conv_in_fwd(const float* x, long long x_stride, int batch, int length, c
 int cum_conv_in_bf16_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
                          void* y_bf16, int rows_out, int c_pad, int kernel, int stride, cum_stream_t stream) {
     return conv_in_fwd(x, x_stride, batch, length, w, bias, reinterpret_cast<float*>(y_bf16), rows_out, c_pad, kernel, stride,
-                       nullptr, 0, 0, (cudaStream_t)stream, true);
+                       nullptr, 0, 0, (cudaStream_t)stream, 1);
+}
+
+int cum_conv_in_hl16_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
+                         void* y_hi, void* y_lo, int rows_out, int c_pad, int kernel, int stride, cum_stream_t stream) {
+    return conv_in_fwd(x, x_stride, batch, length, w, bias, reinterpret_cast<float*>(y_hi), rows_out, c_pad, kernel, stride,
+                       nullptr, 0, 0, (cudaStream_t)stream, 2, y_lo);
 }
 
 int cum_convt_out_bf16_fwd(const void* g_bf16, int batch, int rows_in, int c_pad, const float* w, float bias,

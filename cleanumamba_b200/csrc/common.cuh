@@ -70,7 +70,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStream_t st);
 int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
                 float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
-                int row_offset, cudaStream_t st, bool out_bf16 = false);
+                int row_offset, cudaStream_t st, int out_fmt = 0 /* 0 fp32, 1 bf16, 2 fp16 hi/lo planes */, void* y_lo = nullptr);
 int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
                    int frames_before, float* running, float* scale_out, cudaStream_t st);
 int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,

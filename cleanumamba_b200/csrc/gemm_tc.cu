@@ -45,14 +45,20 @@ constexpr int TC_EPI_ATOMIC_ADD = -3;         // wgrad split-K: accumulate the t
 // BN = tile width (256, or 128 for narrow layers: smaller W box -> deeper pipeline for the HBM-bound layers)
 constexpr int TC_TF32 = 0, TC_TF32X3 = 1, TC_BF16X3 = 2, TC_F16X3 = 3;   // F16X3: like BF16X3 with fp16 halves (11+11 bits)
 constexpr int TC_BF16 = 4;   // bf16 activations straight from HBM (no splitter), one kind::f16 pass -- the reduced-precision variant
+constexpr int TC_F16PS = 5;  // F16X3 arithmetic on activations that are ALREADY stored as fp16 hi / lo planes (written by the producing
+                             // layer's epilogue): both halves arrive by TMA in MMA-ready form, no splitter warps, no raw fp32 tile.  In-kernel
+                             // splitting re-did the conversion once per N-tile (3-6x per element) and sat on the TMA -> MMA critical path:
+                             // with the splitter's work removed the K >= 256 layers ran 8-21 % faster
 // CTA2: two CTAs of a cluster (an SM pair) work on ONE 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages its own 128
 // rows of A and only HALF of the W tile (the MMA reads the other half from the peer's shared memory), which cuts the
 // L2 -> SM operand traffic per flop by a third (f16x3) to a half (bf16) -- the measured bound of the K >= 512 layers.
 template <int MODE, int BN, bool CTA2 = false> struct TcCfg {
-    static constexpr bool SPLIT = MODE != TC_TF32 && MODE != TC_BF16;   // operand-splitter warps present
+    static constexpr bool PASS3 = MODE != TC_TF32 && MODE != TC_BF16;   // hi/lo operands, three MMA passes per product
+    static constexpr bool PRES = MODE == TC_F16PS;                      // A comes pre-split from HBM
+    static constexpr bool SPLIT = PASS3 && !PRES;                       // operand-splitter warps present
     static constexpr bool PLAIN16 = MODE == TC_BF16;                    // 16-bit operands, 128-byte rows = 64 elements per K-block
     static constexpr int BK = PLAIN16 ? 64 : TC_BK;                     // elements per K-block (always 128 B of A per row)
-    static constexpr bool HALF = (MODE == TC_BF16X3 || MODE == TC_F16X3);    // 16-bit MMA operands
+    static constexpr bool HALF = (MODE == TC_BF16X3 || MODE == TC_F16X3 || MODE == TC_F16PS);    // 16-bit hi/lo MMA operands
     static constexpr int W_ROWS = CTA2 ? BN / 2 : BN;                   // W rows (output columns) staged by one CTA
     static constexpr uint32_t W_BYTES = W_ROWS * TC_BK * (HALF ? 2 : 4);
     static constexpr uint32_t AOP_BYTES = HALF ? TC_A_BYTES / 2 : TC_A_BYTES;   // one MMA A-operand tile
@@ -63,9 +69,9 @@ template <int MODE, int BN, bool CTA2 = false> struct TcCfg {
     static constexpr uint32_t ALO_OFF = HALF ? AOP_BYTES : TC_A_BYTES;
     static constexpr uint32_t W_OFF = (SPLIT && !HALF) ? 2 * TC_A_BYTES : TC_A_BYTES;
     static constexpr uint32_t WLO_OFF = W_OFF + W_BYTES;
-    static constexpr uint32_t STAGE_BYTES = SPLIT ? WLO_OFF + W_BYTES : W_OFF + W_BYTES;
+    static constexpr uint32_t STAGE_BYTES = PASS3 ? WLO_OFF + W_BYTES : W_OFF + W_BYTES;
     static constexpr int STAGES = (int)(229376u / STAGE_BYTES);          // 224 KB ring (+ 1.25 KB of barriers / alignment slack <= 227 KB)
-    static constexpr uint32_t TX_BYTES = TC_A_BYTES + (SPLIT ? 2 : 1) * W_BYTES;
+    static constexpr uint32_t TX_BYTES = TC_A_BYTES + (PASS3 ? 2 : 1) * W_BYTES;     // PRES: A_hi + A_lo = 16 KB as well
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int THREADS = (4 + TC_EPI_WARPS + (SPLIT ? 4 : 0)) * 32;   // last 4 warps = operand splitter
     static constexpr int UMMA_K = (HALF || PLAIN16) ? 16 : 8;
@@ -81,6 +87,8 @@ struct TcParams {
     int skip_wlo;             // split modes: the low half of the weights is exactly zero -> skip its load and its MMA pass
     int w_k_batch_stride;     // wgrad (split-K over rows): W k-coordinate += batch * this + w_k_off
     int w_k_off;
+    void* c_lo;               // OUTF == 2: low-half plane of the output (c is the high-half plane), fp16
+    const void* addend_lo;    // OUTF == 2: low-half plane of the addend
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -311,15 +319,20 @@ __device__ __forceinline__ float tc_act(int epi, float v) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int MODE, int BN, int EPI, bool OUT16, bool CTA2>
+// OUTF: output (and addend) format -- 0 fp32, 1 bf16, 2 fp16 hi / lo planes ("hl16": what TC_F16PS consumes)
+template <int MODE, int BN, int EPI, int OUTF, bool CTA2>
 __global__ void __launch_bounds__(TcCfg<MODE, BN, CTA2>::THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
-               const __grid_constant__ CUtensorMap tmWl, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const TcParams p) {
     using Cfg = TcCfg<MODE, BN, CTA2>;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr bool X3 = Cfg::SPLIT;
+    constexpr bool X3 = Cfg::PASS3;              // three MMA passes, W_lo exists
+    constexpr bool SPL = Cfg::SPLIT;             // splitter warps between TMA and MMA
+    constexpr bool PRES = Cfg::PRES;             // A_hi / A_lo come from HBM
+    constexpr bool OUT16 = OUTF == 1;
+    constexpr bool OUTS = OUTF == 2;
     constexpr bool BF = Cfg::HALF;               // 16-bit SPLIT operand tiles (bf16 or fp16, 64-byte swizzle)
-    constexpr bool F16 = MODE == TC_F16X3;
+    constexpr bool F16 = MODE == TC_F16X3 || MODE == TC_F16PS;
     constexpr bool P16 = Cfg::PLAIN16;           // plain bf16 operands (128-byte swizzle)
     constexpr bool GLU = (EPI == CUM_EPI_GLU_SIGMOID || EPI == TC_EPI_GENERIC_GLU);
     extern __shared__ uint8_t smem_raw[];
@@ -348,6 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
+        if (PRES) tma_prefetch_desc(&tmAl);
         tma_prefetch_desc(&tmWh);
         if (X3) tma_prefetch_desc(&tmWl);
         for (int s = 0; s < STAGES; ++s) {
@@ -407,17 +421,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // bytes this stage will receive: A + W_hi (+ W_lo unless it is skipped); non-split modes have no W_lo at all
                 const uint32_t tx = (X3 && !load_lo) ? Cfg::TX_BYTES - Cfg::W_BYTES : Cfg::TX_BYTES;
                 const int wk = kb * Cfg::BK + b * p.w_k_batch_stride + p.w_k_off;
-                if (CTA2 && !X3) {
+                if (CTA2 && !SPL) {
                     // no splitter in between: the leader's MMA thread waits for the bytes of BOTH CTAs on its own barrier
                     const uint32_t lbar = mapa_rank(full_bar(s), 0);
                     if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * tx);
                     tma_load_3d_2sm(smem_base + a_off(s), &tmA, lbar, kb * Cfg::BK, m0 + shift, b);
+                    if (PRES) tma_load_3d_2sm(smem_base + alo_off(s), &tmAl, lbar, kb * Cfg::BK, m0 + shift, b);
                     tma_load_3d_2sm(smem_base + w_off(s), &tmWh, lbar, wk, wn, tap);
+                    if (load_lo) tma_load_3d_2sm(smem_base + wlo_off(s), &tmWl, lbar, wk, wn, tap);
                 } else {
                     mbar_arrive_expect_tx(full_bar(s), tx);
                     // wgrad (split-K over rows): the split index selects a column range of ONE 2-D operand instead of a batch plane
                     if (p.w_k_batch_stride) tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK + b * p.w_k_batch_stride, m0, 0);
                     else tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK, m0 + shift, b);
+                    if (PRES) tma_load_3d(smem_base + alo_off(s), &tmAl, full_bar(s), kb * Cfg::BK, m0 + shift, b);
                     tma_load_3d(smem_base + w_off(s), &tmWh, full_bar(s), wk, wn, tap);
                     if (load_lo) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), wk, wn, tap);
                 }
@@ -443,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (CTA2) mbar_wait_cluster(tempty_bar(acc), acc_ph ^ 1u); else mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
             tc_fence_after();
             for (int it = 0; it < k_iters; ++it) {
-                if (CTA2) mbar_wait_cluster(X3 ? split_bar(s) : full_bar(s), ph); else mbar_wait(X3 ? split_bar(s) : full_bar(s), ph);
+                if (CTA2) mbar_wait_cluster(SPL ? split_bar(s) : full_bar(s), ph); else mbar_wait(SPL ? split_bar(s) : full_bar(s), ph);
                 tc_fence_after();
                 const uint64_t adesc = BF ? umma_desc_sw64(smem_base + ahi_off(s)) : umma_desc_sw128(smem_base + ahi_off(s));
                 const uint64_t bdesc = BF ? umma_desc_sw64(smem_base + w_off(s)) : umma_desc_sw128(smem_base + w_off(s));
@@ -472,7 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (CTA2 && X3 && warp == 1 && lane == 0 && rank == 1) {
+    } else if (CTA2 && SPL && warp == 1 && lane == 0 && rank == 1) {
         // ===================================================================== peer CTA: forward "my A tile is split" to the leader
         // A release at cluster scope costs a full memory barrier (ERRBAR); issued by the splitter warps themselves it sat on the
         // split -> MMA critical path of every K-block (pair kernel 1.7x slower than single).  The splitters now signal a local
@@ -503,11 +520,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             int n_rem = p.n - n0;
             if (n_rem > BN) n_rem = BN;
-            // OUT16: the output and the addend are bf16 arrays (strides in elements)
-            float* cb = OUT16 ? reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(p.c) + (long long)b * p.c_bs) : p.c + (long long)b * p.c_bs;
+            // OUT16 / OUTS: the output and the addend are 16-bit arrays (strides in elements); OUTS has a second (low-half) plane
+            constexpr bool O16 = OUT16 || OUTS;
+            float* cb = O16 ? reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(p.c) + (long long)b * p.c_bs) : p.c + (long long)b * p.c_bs;
+            // the addend's format is independent of the output's (a U-Net skip keeps the format its encoder layer wrote):
+            // bf16 with bf16 outputs, else hl16 planes when addend_lo is set (warp-uniform runtime switch), else fp32
+            const bool ADDS = !OUT16 && p.addend_lo != nullptr;
             const float* ab = !p.addend ? nullptr
-                              : OUT16 ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(p.addend) + (long long)b * p.add_bs)
-                                      : p.addend + (long long)b * p.add_bs;
+                              : (OUT16 || ADDS) ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(p.addend) + (long long)b * p.add_bs)
+                                                : p.addend + (long long)b * p.add_bs;
+            __half* cl = OUTS ? reinterpret_cast<__half*>(p.c_lo) + (long long)b * p.c_bs : nullptr;
+            const __half* al = ADDS ? reinterpret_cast<const __half*>(p.addend_lo) + (long long)b * p.add_bs : nullptr;
             // 16-column chunks (4 warps of a lane quarter interleave them): small enough that the accumulators, the bias and
             // the prefetched skip values all stay in registers under the 85-register cap of a 768-thread CTA
             for (int c0 = sub * 16; c0 < n_rem; c0 += 64) {
@@ -537,7 +560,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const int n = n0 + c0 + 8 * k + 2 * tq;
                                 ad[h][rh][k] = make_float2(0.f, 0.f);
                                 if (row < p.m && n < p.n) {
-                                    if (OUT16) {
+                                    if (ADDS) {     // hl16 addend: value = hi + lo
+                                        const __half* ah = reinterpret_cast<const __half*>(ab) + (long long)row * p.add_rs;
+                                        const __half* alr = al + (long long)row * p.add_rs;
+                                        if (GLU) ad[h][rh][k].x = __half2float(ah[n >> 1]) + __half2float(alr[n >> 1]);
+                                        else {
+                                            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(ah + n));
+                                            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(alr + n));
+                                            ad[h][rh][k] = make_float2(fh.x + fl.x, fh.y + fl.y);
+                                        }
+                                    } else if (OUT16) {
                                         if (GLU) ad[h][rh][k].x = __bfloat162float(arow16[n >> 1]);
                                         else ad[h][rh][k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(arow16 + n));
                                     } else if (GLU) ad[h][rh][k].x = __ldg(arow + (n >> 1));
@@ -552,6 +584,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int rh = 0; rh < 2; ++rh) {
                         const int row = m0 + q * 32 + h * 16 + rh * 8 + tr;
+                        if constexpr (OUTS && GLU) {
+                            // hl16 GLU output: every lane computes its two gated values, neighbouring lanes swap one so that each
+                            // stores ONE packed pair (even lane: columns of k = 0, odd lane: k = 1) to the hi and the lo plane.
+                            // No early exit before the shuffle: all 32 lanes take part
+                            float o[2];
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const float x0 = fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x);
+                                const float x1 = fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y);
+                                o[k] = x0 * tc_gate<EPI>(p.epi, x1);
+                                if (ab) o[k] += ad[h][rh][k].x;
+                            }
+                            const bool odd = tq & 1;
+                            const float got = __shfl_xor_sync(0xffffffffu, odd ? o[0] : o[1], 1);
+                            const float p0 = odd ? got : o[0], p1 = odd ? o[1] : got;
+                            const int kk = odd ? 1 : 0;
+                            const int col = ((n0 + c0) >> 1) + 4 * kk + (tq & ~1);
+                            if (row < p.m && n0 + c0 + 8 * kk < p.n) {
+                                const uint32_t hi2 = cvt_f16x2_sat(p0, p1);
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+                                const uint32_t lo2 = cvt_f16x2_sat(p0 - hf.x, p1 - hf.y);
+                                *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(cb) + (long long)row * p.c_rs + col) = hi2;
+                                *reinterpret_cast<uint32_t*>(cl + (long long)row * p.c_rs + col) = lo2;
+                            }
+                            continue;
+                        }
                         if (row >= p.m) continue;
                         float* crow = cb + (long long)row * p.c_rs;
                         __nv_bfloat16* crow16 = reinterpret_cast<__nv_bfloat16*>(cb) + (long long)row * p.c_rs;
@@ -572,6 +630,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             } else {
                                 float2 o = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
                                 if (ab) { o.x += ad[h][rh][k].x; o.y += ad[h][rh][k].y; }
+                                if (OUTS) {
+                                    const uint32_t hi2 = cvt_f16x2_sat(o.x, o.y);
+                                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+                                    const uint32_t lo2 = cvt_f16x2_sat(o.x - hf.x, o.y - hf.y);
+                                    *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(cb) + (long long)row * p.c_rs + n) = hi2;
+                                    *reinterpret_cast<uint32_t*>(cl + (long long)row * p.c_rs + n) = lo2;
+                                } else
                                 if (OUT16) *reinterpret_cast<__nv_bfloat162*>(crow16 + n) = __floats2bfloat162_rn(o.x, o.y);
                                 else *reinterpret_cast<float2*>(crow + n) = o;
                             }
@@ -587,7 +652,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_arrive(tempty_bar(acc));
             }
         }
-    } else if (X3 && warp >= 4 + TC_EPI_WARPS) {
+    } else if (SPL && warp >= 4 + TC_EPI_WARPS) {
         // ===================================================================== operand splitter (A tile)
         const int t = threadIdx.x - (4 + TC_EPI_WARPS) * 32;
         int s = 0;
@@ -768,24 +833,32 @@ static int make_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1,
 // split-K (wgrad) launch context: set by wgrad_tc_fwd around its launches (host-side, per calling thread)
 static thread_local int g_wgrad_kbs = 0, g_wgrad_koff = 0;
 
-template <int MODE, int BN, int EPI, bool OUT16 = false, bool CTA2 = false>
+template <int MODE, int BN, int EPI, int OUTF = 0, bool CTA2 = false>
 static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     using Cfg = TcCfg<MODE, BN, CTA2>;
-    constexpr bool X3 = Cfg::SPLIT;
+    constexpr bool X3 = Cfg::PASS3;
     constexpr bool BF = Cfg::HALF;
     constexpr bool P16 = Cfg::PLAIN16;
-    auto kern = gemm_tc_kernel<MODE, BN, EPI, OUT16, CTA2>;
+    constexpr bool PRES = Cfg::PRES;
+    auto kern = gemm_tc_kernel<MODE, BN, EPI, OUTF, CTA2>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
         attr_done = true;
     }
-    CUtensorMap tmA, tmWh, tmWl;
+    CUtensorMap tmA, tmAl, tmWh, tmWl;
     const uint64_t a_bs = (d.batch > 1 && !g_wgrad_kbs) ? (uint64_t)d.a_batch_stride : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
     int rc = make_map(&tmA, d.a, g_wgrad_kbs ? (uint64_t)d.a_row_stride : (uint64_t)d.k, (uint64_t)d.a_rows,
-                      g_wgrad_kbs ? 1 : (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs, Cfg::BK, TC_BM, "A", P16, P16);
+                      g_wgrad_kbs ? 1 : (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs, Cfg::BK, TC_BM, "A", P16 || PRES, P16);
     if (rc) return rc;
+    if (PRES) {     // low-half plane of the activations: same geometry
+        rc = make_map(&tmAl, d.a_lo, (uint64_t)d.k, (uint64_t)d.a_rows, (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs, Cfg::BK, TC_BM,
+                      "A_lo", true, false);
+        if (rc) return rc;
+    } else {
+        tmAl = tmA;
+    }
     const uint64_t w_ts = (uint64_t)d.n * (uint64_t)d.ldw;
     const uint64_t w_k_extent = g_wgrad_kbs ? (uint64_t)d.ldw : (uint64_t)d.k;     // wgrad: W columns span every split
     rc = make_map(&tmWh, d.w, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, Cfg::BK, Cfg::W_ROWS, "W", BF || P16, P16);
@@ -802,7 +875,8 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.m_tiles = (int)cdiv(d.m, CTA2 ? 2 * TC_BM : TC_BM); p.n_tiles = (int)cdiv(d.n, BN); p.k_blocks = (int)cdiv(d.k, Cfg::BK);
     p.bias = d.bias; p.c = d.c; p.c_bs = d.c_batch_stride; p.c_rs = d.c_row_stride;
     p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
-    p.acc_scale = (MODE == TC_F16X3) ? d.acc_scale : 1.0f;
+    p.acc_scale = (MODE == TC_F16X3 || MODE == TC_F16PS) ? d.acc_scale : 1.0f;
+    p.c_lo = d.c_lo; p.addend_lo = d.addend_lo;
     p.skip_wlo = (X3 && d.w_lo_is_zero) ? 1 : 0;
     p.w_k_batch_stride = g_wgrad_kbs; p.w_k_off = g_wgrad_koff;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
@@ -821,12 +895,12 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmWh, tmWl, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmAl, tmWh, tmWl, p);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tc_kernel, cluster 2)");
         return CUM_OK;
     }
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmWh, tmWl, p);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmAl, tmWh, tmWl, p);
     CUM_LAUNCH_CHECK("gemm_tc_kernel");
     return CUM_OK;
 }
@@ -846,12 +920,25 @@ static int cta2_policy() {
 
 template <int MODE, int BN, bool CTA2>
 static int dispatch_epi2(const cum_gemm_desc& d, cudaStream_t st) {
+    if (d.c_lo) {           // fp16 hi / lo output planes (and addend): the activation format TC_F16PS consumes
+        if constexpr (MODE == TC_F16PS || MODE == TC_F16X3) {
+            switch (d.epilogue) {
+                case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, 2, CTA2>(d, st);
+                case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, 2, CTA2>(d, st);
+                case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, 2, CTA2>(d, st);
+                default: set_error("gemm_tc: hi/lo output supports NONE / RELU / GLU_SIGMOID epilogues"); return CUM_ENOTSUP;
+            }
+        } else {
+            set_error("gemm_tc: hi/lo output planes are available for the F16X3 mode");
+            return CUM_ENOTSUP;
+        }
+    }
     if (d.out_bf16) {       // bf16 output / addend: only the epilogues the bf16 variant of the model uses
         if constexpr (MODE == TC_BF16 || MODE == TC_F16X3) {
             switch (d.epilogue) {
-                case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, true, CTA2>(d, st);
-                case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, true, CTA2>(d, st);
-                case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, true, CTA2>(d, st);
+                case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, 1, CTA2>(d, st);
+                case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, 1, CTA2>(d, st);
+                case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, 1, CTA2>(d, st);
                 default: set_error("gemm_tc: bf16 output supports NONE / RELU / GLU_SIGMOID epilogues"); return CUM_ENOTSUP;
             }
         } else {
@@ -860,12 +947,12 @@ static int dispatch_epi2(const cum_gemm_desc& d, cudaStream_t st) {
         }
     }
     switch (d.epilogue) {
-        case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, false, CTA2>(d, st);
-        case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, false, CTA2>(d, st);
-        case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, false, CTA2>(d, st);
+        case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, 0, CTA2>(d, st);
+        case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, 0, CTA2>(d, st);
+        case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, 0, CTA2>(d, st);
         default:
-            return epi_is_glu(d.epilogue) ? launch_tc<MODE, BN, TC_EPI_GENERIC_GLU, false, CTA2>(d, st)
-                                          : launch_tc<MODE, BN, TC_EPI_GENERIC_UNARY, false, CTA2>(d, st);
+            return epi_is_glu(d.epilogue) ? launch_tc<MODE, BN, TC_EPI_GENERIC_GLU, 0, CTA2>(d, st)
+                                          : launch_tc<MODE, BN, TC_EPI_GENERIC_UNARY, 0, CTA2>(d, st);
     }
 }
 
@@ -950,7 +1037,7 @@ static WgradPlan plan_wgrad(const cum_wgrad_desc& d) {
 long long wgrad_tc_workspace_bytes(const cum_wgrad_desc& d) { return (long long)plan_wgrad(d).ws_bytes; }
 
 template <int BN> static int launch_wgrad_gemm(const cum_gemm_desc& g, cudaStream_t st) {
-    return launch_tc<TC_TF32X3, BN, TC_EPI_ATOMIC_ADD, false>(g, st);
+    return launch_tc<TC_TF32X3, BN, TC_EPI_ATOMIC_ADD, 0>(g, st);
 }
 
 int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
@@ -1011,6 +1098,16 @@ int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
         return narrow ? dispatch_epi<TC_BF16, 128>(d, st) : dispatch_epi<TC_BF16, 256>(d, st);
     }
     CUM_REQUIRE(!d.out_bf16 || d.math == CUM_MATH_F16X3, "gemm_tc: bf16 output is available for the BF16 and F16X3 modes");
+    CUM_REQUIRE((!d.a_lo && !d.c_lo && !d.addend_lo) || d.math == CUM_MATH_F16X3, "gemm_tc: hi/lo activation planes need CUM_MATH_F16X3");
+    CUM_REQUIRE(!(d.addend_lo && d.out_bf16), "gemm_tc: a bf16 output takes a bf16 addend");
+    CUM_REQUIRE(!(d.c_lo && d.out_bf16), "gemm_tc: c_lo and out_bf16 are mutually exclusive");
+    if (d.math == CUM_MATH_F16X3 && d.a_lo) {
+        CUM_REQUIRE(d.w_lo && aligned16(d.w_lo) && aligned16(d.a_lo), "gemm_tc: F16X3 needs w_lo; a_lo must be 16-byte aligned");
+        CUM_REQUIRE(d.ldw % 8 == 0 && d.k % 8 == 0 && d.a_row_stride % 8 == 0 && d.a_batch_stride % 8 == 0,
+                    "gemm_tc: hi/lo activation planes need k, ldw and the a strides to be multiples of 8 elements");
+        CUM_REQUIRE(d.acc_scale > 0.f, "gemm_tc: F16X3 needs acc_scale = 1 / (weight scale passed to cum_split_f16)");
+        return narrow ? dispatch_epi<TC_F16PS, 128>(d, st) : dispatch_epi<TC_F16PS, 256>(d, st);
+    }
     if (d.math == CUM_MATH_F16X3) {
         CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: F16X3 needs w_lo (see cum_split_f16)");
         CUM_REQUIRE(d.ldw % 8 == 0, "gemm_tc: F16X3 needs ldw %% 8 == 0 (ldw=%d)", d.ldw);

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace cum {
 
@@ -98,10 +99,34 @@ int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, in
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CI_ROWS = 64;
 
-template <bool OUT16>
+// fp32 -> fp16 hi / lo ("hl16", see cum_gemm_desc): hi = fp16(x) saturated, lo = fp16(x - hi)
+__device__ __forceinline__ uint32_t cvt_h2_sat(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+// store 4 consecutive channels at element offset `o`: OUTF 0 = fp32 (y), 1 = bf16 (y), 2 = hl16 (y = hi plane, y_lo = lo plane)
+template <int OUTF>
+__device__ __forceinline__ void store4(float* __restrict__ y, void* __restrict__ y_lo, long long o, float4 acc) {
+    if (OUTF == 1) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + o) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    } else if (OUTF == 2) {
+        const uint32_t h0 = cvt_h2_sat(acc.x, acc.y), h1 = cvt_h2_sat(acc.z, acc.w);
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+        const uint32_t l0 = cvt_h2_sat(acc.x - f0.x, acc.y - f0.y), l1 = cvt_h2_sat(acc.z - f1.x, acc.w - f1.y);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(y) + o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(y_lo) + o) = make_uint2(l0, l1);
+    } else {
+        *reinterpret_cast<float4*>(y + o) = acc;
+    }
+}
+
+template <int OUTF>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, long long x_stride, int length,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                       float* __restrict__ y, int rows_out, int c_pad, int kernel,
+                                                       float* __restrict__ y, void* __restrict__ y_lo, int rows_out, int c_pad, int kernel,
                                                        int stride, const float* __restrict__ in_scale, int scale_groups,
                                                        int group_rows, int row_offset) {
     extern __shared__ float xs[];
@@ -116,7 +141,6 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     __syncthreads();
     const int c4n = c_pad >> 2;
     const int rows = min(CI_ROWS, rows_out - t0);
-    float* yb = y + ((long long)b * rows_out + t0) * c_pad;
     for (int idx = threadIdx.x; idx < rows * c4n; idx += blockDim.x) {
         const int t = idx / c4n, c4 = idx - t * c4n;
         float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
@@ -130,23 +154,17 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
             acc.z = fmaf(wv.z, xv, acc.z); acc.w = fmaf(wv.w, xv, acc.w);
         }
         acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-        if (OUT16) {       // bf16 activation storage (reduced-precision variant): y is a bf16 array
-            __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y) + ((long long)b * rows_out + t0 + t) * c_pad + 4 * c4;
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
-            *reinterpret_cast<uint2*>(y16) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-        } else {
-            reinterpret_cast<float4*>(yb + (long long)t * c_pad)[c4] = acc;
-        }
+        store4<OUTF>(y, y_lo, ((long long)b * rows_out + t0 + t) * c_pad + 4 * c4, acc);
     }
 }
 
 // Fast path for the shipped geometry (64 channels, K = 4, S = 2, no per-hop scale): 256 rows per CTA, each thread owns one
 // float4 of channels for 16 rows, weights and bias live in registers, every pass stores 16 rows x 256 B = 4 KB contiguous.
 constexpr int CIF_ROWS = 256;
-template <bool OUT16>
+template <int OUTF>
 __global__ void __launch_bounds__(256) conv_in_c64_kernel(const float* __restrict__ x, long long x_stride, int length,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
-                                                           float* __restrict__ y, int rows_out) {
+                                                           float* __restrict__ y, void* __restrict__ y_lo, int rows_out) {
     __shared__ __align__(16) float xs[CIF_ROWS * 2 + 4];
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * CIF_ROWS;
@@ -173,20 +191,14 @@ __global__ void __launch_bounds__(256) conv_in_c64_kernel(const float* __restric
             acc.z = fmaf(wv[k].z, xv[k], acc.z); acc.w = fmaf(wv[k].w, xv[k], acc.w);
         }
         acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-        const long long o = ((long long)b * rows_out + t0 + t) * 64 + 4 * c4;
-        if (OUT16) {
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + o) =
-                make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-        } else {
-            *reinterpret_cast<float4*>(y + o) = acc;
-        }
+        store4<OUTF>(y, y_lo, ((long long)b * rows_out + t0 + t) * 64 + 4 * c4, acc);
     }
 }
 
 int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
                 float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
-                int row_offset, cudaStream_t st, bool out_bf16) {
+                int row_offset, cudaStream_t st, int out_fmt, void* y_lo) {
+    CUM_REQUIRE(out_fmt != 2 || (y_lo && aligned16(y_lo)), "conv_in: hi/lo output needs a 16-byte aligned y_lo");
     CUM_REQUIRE(x && w && bias && y, "conv_in: null pointer");
     CUM_REQUIRE(batch > 0 && length > 0 && rows_out > 0, "conv_in: empty problem");
     CUM_REQUIRE(c_pad > 0 && c_pad % 4 == 0, "conv_in: c_pad=%d must be a positive multiple of 4", c_pad);
@@ -195,20 +207,18 @@ int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const
     CUM_REQUIRE(!in_scale || group_rows > 0, "conv_in: group_rows must be positive when in_scale is given");
     if (c_pad == 64 && kernel == 4 && stride == 2 && !in_scale && batch <= 65535) {
         dim3 gridf((unsigned)cdiv(rows_out, CIF_ROWS), batch);
-        if (out_bf16) conv_in_c64_kernel<true><<<gridf, 256, 0, st>>>(x, x_stride, length, w, bias, y, rows_out);
-        else conv_in_c64_kernel<false><<<gridf, 256, 0, st>>>(x, x_stride, length, w, bias, y, rows_out);
+        if (out_fmt == 2) conv_in_c64_kernel<2><<<gridf, 256, 0, st>>>(x, x_stride, length, w, bias, y, y_lo, rows_out);
+        else if (out_fmt == 1) conv_in_c64_kernel<1><<<gridf, 256, 0, st>>>(x, x_stride, length, w, bias, y, y_lo, rows_out);
+        else conv_in_c64_kernel<0><<<gridf, 256, 0, st>>>(x, x_stride, length, w, bias, y, y_lo, rows_out);
         CUM_LAUNCH_CHECK("conv_in_c64_kernel");
         return CUM_OK;
     }
     dim3 grid((unsigned)cdiv(rows_out, CI_ROWS), batch);
     const size_t smem = (size_t)(CI_ROWS * stride + kernel) * sizeof(float);
     const int groups = in_scale ? (int)cdiv(max(1, rows_out + row_offset), group_rows) : 0;
-    if (out_bf16)
-        conv_in_kernel<true><<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale,
-                                                      groups, group_rows, row_offset);
-    else
-        conv_in_kernel<false><<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale,
-                                                       groups, group_rows, row_offset);
+#define CI_LAUNCH(F) conv_in_kernel<F><<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, y_lo, rows_out, c_pad, kernel, stride, in_scale, groups, group_rows, row_offset)
+    if (out_fmt == 2) CI_LAUNCH(2); else if (out_fmt == 1) CI_LAUNCH(1); else CI_LAUNCH(0);
+#undef CI_LAUNCH
     CUM_LAUNCH_CHECK("conv_in_kernel");
     return CUM_OK;
 }

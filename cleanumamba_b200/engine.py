@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -53,6 +54,7 @@ def _interleave_glu(w: torch.Tensor, b: torch.Tensor, k_pad: int):
 
 class Engine:
     skip_zero_lo = True      # skip the a_hi*w_lo pass for weights whose low half is exactly zero (tests may turn it off)
+    hl16 = os.environ.get("CUM_HL16", "1") != "0"    # f16x3: store the conv-stack activations as fp16 hi/lo planes (A/B switch)
 
     def __init__(self, model):
         self.model = model
@@ -262,6 +264,13 @@ class Engine:
              taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None):
         d = GemmDesc()
         d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k = a.data_ptr() + a.element_size() * a_off, a_bs, a_rs, a_rows, k
+        # "hl16" tensors (dtype float16, leading dimension 2 = [hi plane, lo plane], see cum_gemm_desc.a_lo): pre-split activations
+        if a.dtype == torch.float16:
+            d.a_lo = a[1].data_ptr() + 2 * a_off
+        if c.dtype == torch.float16:
+            d.c_lo = c[1].data_ptr() + 2 * c_off
+        if addend is not None and addend.dtype == torch.float16:
+            d.addend_lo = addend[1].data_ptr()
         d.taps = taps
         d.tap_shift[0], d.tap_shift[1] = shifts
         wt = self.pk[w]
@@ -287,10 +296,17 @@ class Engine:
     def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None, out_dtype=torch.float32):
         """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers."""
         n_out = n // 2 if epi >= 8 else n
-        c = out if out is not None else torch.empty(rows, n_out, dtype=out_dtype, device=a.device)
+        c = out if out is not None else self.act_buffer(rows, n_out, out_dtype, a.device)
         self.gemm(a, a_off, 0, k if a_rs is None else a_rs, rows, k, w, bias, c, 0, 0, n_out, rows, n, 1, epi,
                   addend=addend, add_bs=0, add_rs=n_out)
         return c
+
+    @staticmethod
+    def act_buffer(rows, c, dtype, device):
+        """Activation storage: fp32 / bf16 (rows, c), or for float16 the two-plane hl16 format (2, rows, c)."""
+        if dtype == torch.float16:
+            return torch.empty(2, rows, c, dtype=dtype, device=device)
+        return torch.empty(rows, c, dtype=dtype, device=device)
 
     def ln(self, h, res_in, res_out, normed, g, be, eps, rows, c, c_p):
         self._call("ln_residual", self.lib.cum_ln_residual_fwd, ptr(h), ptr(res_in), ptr(res_out), ptr(normed), ptr(g),
@@ -374,13 +390,25 @@ class Engine:
         for _ in range(D):
             Ls.append((Ls[-1] - 4) // 2 + 1)
 
-        adt = torch.bfloat16 if self.bf16_io else torch.float32      # storage type of the encoder / decoder activations
+        # storage of the encoder / decoder activations: bf16 (reduced-precision variant); fp16 hi/lo planes under f16x3 (each
+        # GEMM epilogue splits its output once, the consumer needs no operand splitter -- same products as fp32 storage); else fp32
+        hl16 = (not self.bf16_io) and self.math == _lib.MATH_F16X3 and self.hl16
+        adt = torch.bfloat16 if self.bf16_io else torch.float32
+
+        def fmt(consumer_k, producer_k):
+            """Per tensor: hl16 pays when the consuming GEMM is compute-bound (it loses its splitter: -6..13 % at K >= 512) and
+            the producing GEMM is not epilogue-bound (the split store costs it +3..5 % at K >= 256, +25 % on the 128-wide layers)"""
+            return torch.float16 if (hl16 and consumer_k >= 512 and producer_k >= 256) else adt
         skips: List[torch.Tensor] = []
         prev = None
         for i, e in enumerate(meta["enc"]):
             rows = B * Ls[i + 1]
-            y = torch.empty(rows, e["Hc_p"], dtype=adt, device=x.device)
-            if i == 0 and self.bf16_io:
+            y = self.act_buffer(rows, e["Hc_p"], fmt(e["Hc_p"], 2 * e["Cin_p"] if i else 0), x.device)
+            if i == 0 and y.dtype == torch.float16:
+                self._call("conv_in", lib.cum_conv_in_hl16_fwd, x.data_ptr(), L, B, L, pk["enc0.w"].data_ptr(),
+                           pk["enc0.b"].data_ptr(), y[0].data_ptr(), y[1].data_ptr(), Ls[1], e["Hc_p"], 4, 2, st(),
+                           nbytes=4 * B * (L + Ls[1] * e["Hc"]))
+            elif i == 0 and self.bf16_io:
                 self._call("conv_in", lib.cum_conv_in_bf16_fwd, x.data_ptr(), L, B, L, pk["enc0.w"].data_ptr(),
                            pk["enc0.b"].data_ptr(), y.data_ptr(), Ls[1], e["Hc_p"], 4, 2, st(),
                            nbytes=B * (4 * L + 2 * Ls[1] * e["Hc"]))
@@ -393,7 +421,8 @@ class Engine:
                 self.gemm(prev, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
                           y, 0, Ls[i + 1] * e["Hc_p"], e["Hc_p"], Ls[i + 1], e["Hc_p"], B, EPI_RELU, taps=2,
                           shifts=(0, 1))
-            prev = self.dense(y, rows, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act, out_dtype=adt)
+            prev = self.dense(y, rows, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act,
+                              out_dtype=fmt(2 * e["Ho_p"] if i < D - 1 else e["Ho_p"], e["Hc_p"]))
             skips.append(prev)
 
         T = Ls[D]
@@ -401,16 +430,18 @@ class Engine:
         cb_p = meta["enc"][-1]["Ho_p"]
         h = self.dense(prev, rows, cb_p, "t1.w", pk["t1.b"], meta["dm_p"])
         hn = self.mamba_layers(h, B, T)
-        xcur = self.dense(hn, rows, meta["dm_p"], "t2.w", pk["t2.b"], cb_p, addend=skips[D - 1], out_dtype=adt)
+        xcur = self.dense(hn, rows, meta["dm_p"], "t2.w", pk["t2.b"], cb_p, addend=skips[D - 1], out_dtype=fmt(cb_p, meta["dm_p"]))
 
         Tj = T
         out = None
         for j, d in enumerate(meta["dec"]):
-            g = self.dense(xcur, B * Tj, d["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * d["Hg_p"], epi=act, out_dtype=adt)
+            # (the waveform-end kernel reads plain fp32 / bf16 rows: the last GLU output is never written as hi/lo planes)
+            g = self.dense(xcur, B * Tj, d["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * d["Hg_p"], epi=act,
+                           out_dtype=fmt(2 * d["Hg_p"], d["Cin_p"]) if j < D - 1 else adt)
             if j < D - 1:
                 co = d["Co_p"]
                 To = 2 * Tj + 2
-                nxt = torch.empty(B * To, co, dtype=adt, device=x.device)
+                nxt = self.act_buffer(B * To, co, fmt(co, 2 * d["Hg_p"]), x.device)
                 skip = skips[D - 2 - j]
                 self.gemm(g, 0, Tj * d["Hg_p"], d["Hg_p"], Tj, d["Hg_p"], f"dec{j}.w", pk[f"dec{j}.b"],
                           nxt, 0, To * co, 2 * co, Tj + 1, 2 * co, B, EPI_RELU, taps=2, shifts=(0, -1),
@@ -428,6 +459,7 @@ class Engine:
         ncl = []
         for i in reversed(range(D)):      # the reference returns the skips deepest-first (:275) in (B, C, L)
             e = meta["enc"][i]
-            ncl.append(skips[i].view(B, Ls[i + 1], e["Ho_p"])[:, :, : e["Ho"]].permute(0, 2, 1).float())
+            sk = (skips[i][0].float() + skips[i][1].float()) if skips[i].dtype == torch.float16 else skips[i]
+            ncl.append(sk.view(B, Ls[i + 1], e["Ho_p"])[:, :, : e["Ho"]].permute(0, 2, 1).float())
         ncl.append(hn.view(B, T, meta["dm_p"])[:, :, : meta["dm"]].permute(0, 2, 1))
         return out, ncl

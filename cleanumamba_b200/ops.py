@@ -127,20 +127,38 @@ def block_forward(block, hidden_states, residual=None, inference_params=None):
 
 
 @torch.no_grad()
-def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None, addend=None, math="fp32", cta_pair=0):
+def split_hl16(x):
+    """fp32 -> the two-plane fp16 "hl16" format (2, *x.shape): hi = fp16(x), lo = fp16(x - hi)  (see cum_gemm_desc.a_lo)."""
+    hi = x.clamp(-65504.0, 65504.0).to(torch.float16)
+    lo = (x - hi.float()).clamp(-65504.0, 65504.0).to(torch.float16)
+    return torch.stack([hi, lo])
+
+
+def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None, addend=None, math="fp32", cta_pair=0,
+                  out_hl16=False):
     """Raw tap-GEMM on channels-last tensors (thin wrapper of cum_gemm_bias_act_fwd, used by tests / benchmarks).
     a: (batch, rows, K) fp32 contiguous, K % 4 == 0;  w: (taps, N, K), N % 8 == 0;  bias: (N);  addend: (batch, m, N_out).
-    out[b, i, :] = EPI(bias + sum_s W_s . a[b, i + shifts[s], :]) + addend[b, i, :]   (rows outside a read as 0)."""
+    out[b, i, :] = EPI(bias + sum_s W_s . a[b, i + shifts[s], :]) + addend[b, i, :]   (rows outside a read as 0).
+    f16x3 only: ``a`` may be an hl16 tensor (2, batch, rows, K) float16 (``split_hl16``); ``out_hl16`` returns the result in
+    that format, and the addend must then be hl16 as well."""
     _need_cuda(a, w, bias, addend)
     lib = _lib.init(a.device)
-    batch, rows, k = a.shape
+    a_planes = a if a.dtype == torch.float16 else None
+    batch, rows, k = a.shape[-3:]
     taps, n, kw = w.shape
     assert kw == k and a.is_contiguous() and w.is_contiguous()
     m = rows if m is None else m
     n_out = n // 2 if epilogue >= 8 else n
-    out = torch.empty(batch, m, n_out, dtype=torch.float32, device=a.device)
+    out = (torch.empty(2, batch, m, n_out, dtype=torch.float16, device=a.device) if out_hl16
+           else torch.empty(batch, m, n_out, dtype=torch.float32, device=a.device))
     d = _lib.GemmDesc()
     d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k, d.taps = a.data_ptr(), rows * k, k, rows, k, taps
+    if a_planes is not None:
+        d.a_lo = a_planes[1].data_ptr()
+    if out_hl16:
+        d.c_lo = out[1].data_ptr()
+    if addend is not None and addend.dtype == torch.float16:
+        d.addend_lo = addend[1].data_ptr()
     d.tap_shift[0], d.tap_shift[1] = shifts
     d.math = _lib.MATH_BY_NAME[math]
     if d.math == _lib.MATH_TF32X3:

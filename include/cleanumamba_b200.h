@@ -102,6 +102,11 @@ int cum_conv_in_bf16_fwd(const float* x, long long x_stride, int batch, int leng
 int cum_convt_out_bf16_fwd(const void* g_bf16, int batch, int rows_in, int c_pad, const float* w, float bias,
                            const float* scale, int scale_group, float* out, long long out_stride, int first,
                            int length, int kernel, int stride, cum_stream_t stream);
+/* cum_conv_in_fwd writing its output as fp16 hi / lo planes ("hl16", see cum_gemm_desc.a_lo): the first encoder GEMM then needs
+ * no operand splitter.  Same arithmetic as cum_conv_in_fwd; y_hi[i] + y_lo[i] carries 22 bits of the fp32 result. */
+int cum_conv_in_hl16_fwd(const float* x, long long x_stride, int batch, int length, const float* w,
+                         const float* bias, void* y_hi, void* y_lo, int rows_out, int c_pad, int kernel, int stride,
+                         cum_stream_t stream);
 
 /* ---- the tap-GEMM: every dense contraction of the path -------------------------------------- */
 /* out[b, m, :] = EPI( bias + sum_{s<taps} W_s . a[b, m + tap_shift[s], 0:k] ) (+ addend[b, m, :])
@@ -133,6 +138,13 @@ typedef struct cum_gemm_desc {
     int out_bf16;            /* BF16 / F16X3 only: `c` and `addend` are bf16 arrays (strides still in elements) */
     int w_lo_is_zero;        /* split modes: caller asserts every element of w_lo is exactly 0 (e.g. weights of a checkpoint
                                 shipped in fp16 under F16X3): the a_hi*w_lo pass is skipped -- identical result, 2 MMAs / product */
+    /* CUM_MATH_F16X3 only -- "hl16" activations: a tensor stored as TWO fp16 planes, value = hi + lo with hi = fp16(x) and
+     * lo = fp16(x - hi) (what the kernel's operand splitter computes from fp32 on the fly).  A layer that writes hl16 (c_lo set)
+     * splits each output ONCE in its epilogue; the next layer (a_lo set) then feeds both planes to the tensor cores straight from
+     * TMA: same products as with fp32 activations, no in-kernel splitter.  Strides are in elements and shared by both planes. */
+    const void* a_lo;        /* NULL, or the low-half plane of `a` (then `a` is the high-half plane, both fp16) */
+    void* c_lo;              /* NULL, or the low-half plane of `c` (then `c` is the high-half plane, both fp16) */
+    const void* addend_lo;   /* NULL, or the low-half plane of `addend` (then `addend` is the high-half plane, both fp16) */
     int cta_pair;            /* tiles wider than 128 columns can run on CTA pairs (tcgen05 cta_group::2: 256-row tiles, each CTA
                                 stages half of the weight tile).  0 = automatic (pairs whenever a problem has more than 128 rows),
                                 1 = same, -1 = never.  Same products, same accumulation order: bit-identical results */

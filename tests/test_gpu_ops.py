@@ -252,3 +252,53 @@ def test_gemm_cta_pair_is_bit_identical_to_single_cta(math, b, k, n, m, taps):
     ref = torch.relu(sum(F.pad(a, (0, 0, 0, 1))[:, s:s + m].double().cpu() @ w[t].double().cpu().t()
                          for t, s in enumerate(shifts[:taps])) + bias.double().cpu())
     assert rel_err(ops.gemm_bias_act(a, w, bias, _lib.EPI_RELU, shifts=shifts, m=m, math=math), ref) < GEMM_TOL[math]
+
+
+@pytest.mark.parametrize("cta_pair", [0, -1])
+@pytest.mark.parametrize("b,k,n,m,taps", [(1, 64, 128, 300, 1), (2, 128, 768, 700, 1), (1, 96, 160, 300, 1), (3, 256, 512, 257, 2),
+                                          (1, 1536, 768, 1000, 2), (2, 64, 264, 256, 1), (2, 56, 72, 77, 1)])
+def test_gemm_hl16_activation_planes(b, k, n, m, taps, cta_pair):
+    """f16x3 with activations stored as fp16 hi/lo planes (cum_gemm_desc.a_lo / c_lo / addend_lo): the operands that reach the
+    tensor cores are the ones the in-kernel splitter would have produced, so (1) pre-split input + fp32 output is bit-identical
+    to the fp32-input kernel, (2) a split output is exactly the hi/lo split of that fp32 result, also with a split addend."""
+    from cleanumamba_b200 import _lib, ops
+    g = torch.Generator().manual_seed(k * 7 + n + m)
+    rows = m + 1 if taps == 2 else m
+    a = (torch.randn(b, rows, k, generator=g) * torch.exp(torch.randn(b, rows, 1, generator=g) * 3)).to(dev())   # wide dynamic range
+    w = (torch.randn(taps, n, k, generator=g) / (taps * k) ** 0.5).to(dev())
+    bias = torch.randn(n, generator=g).to(dev())
+    shifts = (0, 1) if taps == 2 else (0, 0)
+    ah = ops.split_hl16(a)
+    for epi in (_lib.EPI_RELU, _lib.EPI_GLU["Sigmoid"]):
+        n_out = n // 2 if epi >= 8 else n
+        ref = ops.gemm_bias_act(a, w, bias, epi, shifts=shifts, m=m, math="f16x3", cta_pair=cta_pair)
+        got = ops.gemm_bias_act(ah, w, bias, epi, shifts=shifts, m=m, math="f16x3", cta_pair=cta_pair)
+        assert torch.equal(got, ref), (got - ref).abs().max().item()
+        add = torch.randn(b, m, n_out, generator=g).to(dev())
+        addh = ops.split_hl16(add)
+        add_q = addh[0].float() + addh[1].float()
+        ref2 = ops.gemm_bias_act(a, w, bias, epi, shifts=shifts, m=m, addend=add_q, math="f16x3", cta_pair=cta_pair)
+        out = ops.gemm_bias_act(ah, w, bias, epi, shifts=shifts, m=m, addend=addh, math="f16x3", cta_pair=cta_pair, out_hl16=True)
+        assert torch.equal(out, ops.split_hl16(ref2))
+        # the addend's format is independent of the output's (a skip tensor keeps the format its encoder layer wrote)
+        assert torch.equal(ops.gemm_bias_act(a, w, bias, epi, shifts=shifts, m=m, addend=addh, math="f16x3", cta_pair=cta_pair), ref2)
+        assert torch.equal(ops.gemm_bias_act(ah, w, bias, epi, shifts=shifts, m=m, addend=add_q, math="f16x3", cta_pair=cta_pair,
+                                             out_hl16=True), ops.split_hl16(ref2))
+
+
+def test_conv_in_hl16_matches_fp32_kernel():
+    from cleanumamba_b200 import _lib, ops
+    lib = _lib.init(dev())
+    g = torch.Generator().manual_seed(11)
+    B, L = 3, 1000
+    x = (torch.randn(B, L, generator=g) * 0.3).to(dev())
+    rows = (L - 4) // 2 + 1
+    for H in (56, 64):
+        w, bias = torch.randn(4, H, generator=g).to(dev()), torch.randn(H, generator=g).to(dev())
+        y = torch.empty(B, rows, H, device=dev())
+        _lib.check(lib.cum_conv_in_fwd(x.data_ptr(), L, B, L, w.data_ptr(), bias.data_ptr(), y.data_ptr(), rows, H, 4, 2, 0, 0, 0,
+                                       _lib.stream_ptr()), "conv_in")
+        yh = torch.empty(2, B, rows, H, dtype=torch.float16, device=dev())
+        _lib.check(lib.cum_conv_in_hl16_fwd(x.data_ptr(), L, B, L, w.data_ptr(), bias.data_ptr(), yh[0].data_ptr(), yh[1].data_ptr(),
+                                            rows, H, 4, 2, _lib.stream_ptr()), "conv_in_hl16")
+        assert torch.equal(yh, ops.split_hl16(y))
