@@ -25,6 +25,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <type_traits>
 #include <string.h>
 
 namespace cum {
@@ -296,7 +297,14 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2_nowait(uint32_t taddr, float*
 
 // epilogue math.  The tensor-core path uses the fast intrinsics (ex2.approx / rcp.approx, ~2 ulp): the gate error is
 // far below the TF32X3 product error; the exact-fp32 SIMT kernel keeps expf / IEEE division.
-__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+// 1 / (1 + 2^(-v log2 e)) with bare ex2.approx / rcp.approx: +inf -> rcp -> 0 and flushed underflow -> 1 are the right limits, so the
+// range guards of __expf / __fdividef (3 more instructions per output) are not needed
+__device__ __forceinline__ float fast_sigmoid(float v) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
 template <int EPI>
 __device__ __forceinline__ float tc_gate(int epi, float g) {
     if (EPI == CUM_EPI_GLU_SIGMOID) return fast_sigmoid(g);
@@ -520,130 +528,152 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             int n_rem = p.n - n0;
             if (n_rem > BN) n_rem = BN;
-            // OUT16 / OUTS: the output and the addend are 16-bit arrays (strides in elements); OUTS has a second (low-half) plane
-            constexpr bool O16 = OUT16 || OUTS;
-            float* cb = O16 ? reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(p.c) + (long long)b * p.c_bs) : p.c + (long long)b * p.c_bs;
-            // the addend's format is independent of the output's (a U-Net skip keeps the format its encoder layer wrote):
-            // bf16 with bf16 outputs, else hl16 planes when addend_lo is set (warp-uniform runtime switch), else fp32
+            // Output / addend formats: OUTF 0 fp32, 1 bf16 (addend bf16 too), 2 fp16 hi/lo planes.  The addend's format is otherwise
+            // independent of the output's (a U-Net skip keeps the format its encoder layer wrote): hl16 planes when addend_lo is
+            // set (warp-uniform runtime switch), else fp32.  All element offsets inside one batch plane fit 32 bits (host check).
             const bool ADDS = !OUT16 && p.addend_lo != nullptr;
-            const float* ab = !p.addend ? nullptr
-                              : (OUT16 || ADDS) ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(p.addend) + (long long)b * p.add_bs)
-                                                : p.addend + (long long)b * p.add_bs;
-            __half* cl = OUTS ? reinterpret_cast<__half*>(p.c_lo) + (long long)b * p.c_bs : nullptr;
-            const __half* al = ADDS ? reinterpret_cast<const __half*>(p.addend_lo) + (long long)b * p.add_bs : nullptr;
-            // 16-column chunks (4 warps of a lane quarter interleave them): small enough that the accumulators, the bias and
-            // the prefetched skip values all stay in registers under the 85-register cap of a 768-thread CTA
-            for (int c0 = sub * 16; c0 < n_rem; c0 += 64) {
-                float2 bv[2];
+            const bool has_add = p.addend != nullptr && EPI != TC_EPI_ATOMIC_ADD;
+            const long long cbo = (long long)b * p.c_bs, abo = (long long)b * p.add_bs;
+            // The epilogue is instruction-issue-bound on the narrow layers (~45 SASS instructions per output before this layout):
+            // row offsets are computed once per tile, interior tiles take a predicate-free path, addresses are base + 32-bit offset
+            auto run = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                // byte pointers of this thread's four rows at its first column of the first chunk; bumped by one chunk stride per
+                // iteration, the k-dependent part of an address is a compile-time immediate
+                constexpr int CES = OUTF == 0 ? 4 : 2;                          // output element size
+                const int aes = (OUT16 || ADDS) ? 2 : 4;                        // addend element size
+                // this thread's four rows are 8 rows apart: ONE pointer / offset + a stride (the 80-register cap of the 768-thread
+                // kernels does not leave room for four of each)
+                const char* const abase = reinterpret_cast<const char*>(p.addend) + abo * aes;
+                bool rok[2][2];
+                const int c00 = sub * 16;
+                const int row0 = m0 + q * 32 + tr;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int n = n0 + c0 + 8 * k + 2 * tq;
-                    bv[k] = (p.bias && n < p.n) ? __ldg(reinterpret_cast<const float2*>(p.bias + n)) : make_float2(0.f, 0.f);
-                }
-                float v[2][8];
-                __syncwarp();       // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
-                tmem_ld_16x256b_x2_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v[0]);
-                tmem_ld_16x256b_x2_nowait(tmem_base + ((uint32_t)(q * 32 + 16) << 16) + (uint32_t)(acc * BN + c0), v[1]);
-                // the U-Net skip tile (addend) comes from DRAM: all of this thread's addend values are requested BEFORE
-                // waiting on the TMEM loads so their latency overlaps (they used to be loaded one by one right before use)
-                float2 ad[2][2][2];
-                if (ab && EPI != TC_EPI_ATOMIC_ADD) {
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int rh = 0; rh < 2; ++rh) rok[h][rh] = FULL || row0 + h * 16 + rh * 8 < p.m;
+                const int col = GLU ? ((n0 + c00) >> 1) + (OUTS ? (tq & ~1) + 4 * (tq & 1) : tq) : n0 + c00 + 2 * tq;
+                const int acol = GLU ? ((n0 + c00) >> 1) + tq : n0 + c00 + 2 * tq;
+                char* cp0 = reinterpret_cast<char*>(p.c) + (cbo + (long long)row0 * p.c_rs + col) * CES;
+                unsigned ao0 = ((unsigned)row0 * (unsigned)p.add_rs + (unsigned)acol) * (unsigned)aes;
+                const unsigned cs8 = 8u * (unsigned)p.c_rs * CES, as8 = 8u * (unsigned)p.add_rs * (unsigned)aes;     // bytes per 8 rows
+                auto cp = [&](int h, int rh) { return cp0 + (size_t)((2 * h + rh) * cs8); };
+                auto ao = [&](int h, int rh) { return ao0 + (unsigned)(2 * h + rh) * as8; };
+                const long long lo_delta = OUTS ? reinterpret_cast<char*>(p.c_lo) - reinterpret_cast<char*>(p.c) : 0;      // hi -> lo plane
+                const long long alo_delta = ADDS ? reinterpret_cast<const char*>(p.addend_lo) - reinterpret_cast<const char*>(p.addend) : 0;
+                constexpr int CSTEP = (GLU ? 32 : 64) * CES;                    // bytes per chunk stride (64 accumulator columns)
+                const int astep = (GLU ? 32 : 64) * aes;
+                for (int c0 = c00; c0 < n_rem; c0 += 64) {
+                    bool kok[2];
+                    float2 bv[2];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int n = n0 + c0 + 8 * k + 2 * tq;
+                        kok[k] = FULL || n < p.n;
+                        bv[k] = (p.bias && kok[k]) ? __ldg(reinterpret_cast<const float2*>(p.bias + n)) : make_float2(0.f, 0.f);
+                    }
+                    float v[2][8];
+                    __syncwarp();       // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+                    tmem_ld_16x256b_x2_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v[0]);
+                    tmem_ld_16x256b_x2_nowait(tmem_base + ((uint32_t)(q * 32 + 16) << 16) + (uint32_t)(acc * BN + c0), v[1]);
+                    // the U-Net skip tile (addend) comes from DRAM: all of this thread's addend values are requested BEFORE
+                    // waiting on the TMEM loads so their latency overlaps
+                    float2 ad[2][2][2];
+                    if (has_add) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) {
+                                    ad[h][rh][k] = make_float2(0.f, 0.f);
+                                    if (rok[h][rh] && kok[k]) {
+                                        const int ko = GLU ? 4 * k : 8 * k;                 // elements
+                                        if (ADDS) {     // hl16 addend: value = hi + lo
+                                            const char* ah = abase + ao(h, rh) + ko * 2;
+                                            if (GLU) ad[h][rh][k].x = __half2float(*reinterpret_cast<const __half*>(ah)) +
+                                                                      __half2float(*reinterpret_cast<const __half*>(ah + alo_delta));
+                                            else {
+                                                const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(ah));
+                                                const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(ah + alo_delta));
+                                                ad[h][rh][k] = make_float2(fh.x + fl.x, fh.y + fl.y);
+                                            }
+                                        } else if (OUT16) {
+                                            const char* a16 = abase + ao(h, rh) + ko * 2;
+                                            if (GLU) ad[h][rh][k].x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(a16));
+                                            else ad[h][rh][k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a16));
+                                        } else if (GLU) ad[h][rh][k].x = __ldg(reinterpret_cast<const float*>(abase + ao(h, rh) + ko * 4));
+                                        else ad[h][rh][k] = __ldg(reinterpret_cast<const float2*>(abase + ao(h, rh) + ko * 4));
+                                    }
+                                }
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
 #pragma unroll
                         for (int rh = 0; rh < 2; ++rh) {
-                            const int row = m0 + q * 32 + h * 16 + rh * 8 + tr;
-                            const float* arow = ab + (long long)row * p.add_rs;
-                            const __nv_bfloat16* arow16 = reinterpret_cast<const __nv_bfloat16*>(ab) + (long long)row * p.add_rs;
+                            if constexpr (OUTS && GLU) {
+                                // hl16 GLU output: every lane computes its two gated values, neighbouring lanes swap one so that each
+                                // stores ONE packed pair (even lane: the columns of k = 0, odd lane: k = 1) to the hi and the lo plane.
+                                // No early exit before the shuffle: all 32 lanes take part
+                                float o[2];
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) {
+                                    const float x0 = fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x);
+                                    const float x1 = fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y);
+                                    o[k] = x0 * tc_gate<EPI>(p.epi, x1);
+                                    if (has_add) o[k] += ad[h][rh][k].x;
+                                }
+                                const bool odd = tq & 1;
+                                const float got = __shfl_xor_sync(0xffffffffu, odd ? o[0] : o[1], 1);
+                                const float p0 = odd ? got : o[0], p1 = odd ? o[1] : got;
+                                if (rok[h][rh] && (FULL || n0 + c0 + 8 * (int)odd < p.n)) {
+                                    const uint32_t hi2 = cvt_f16x2_sat(p0, p1);
+                                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+                                    const uint32_t lo2 = cvt_f16x2_sat(p0 - hf.x, p1 - hf.y);
+                                    *reinterpret_cast<uint32_t*>(cp(h, rh)) = hi2;
+                                    *reinterpret_cast<uint32_t*>(cp(h, rh) + lo_delta) = lo2;
+                                }
+                                continue;
+                            }
+                            if (!rok[h][rh]) continue;
 #pragma unroll
                             for (int k = 0; k < 2; ++k) {
-                                const int n = n0 + c0 + 8 * k + 2 * tq;
-                                ad[h][rh][k] = make_float2(0.f, 0.f);
-                                if (row < p.m && n < p.n) {
-                                    if (ADDS) {     // hl16 addend: value = hi + lo
-                                        const __half* ah = reinterpret_cast<const __half*>(ab) + (long long)row * p.add_rs;
-                                        const __half* alr = al + (long long)row * p.add_rs;
-                                        if (GLU) ad[h][rh][k].x = __half2float(ah[n >> 1]) + __half2float(alr[n >> 1]);
-                                        else {
-                                            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(ah + n));
-                                            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(alr + n));
-                                            ad[h][rh][k] = make_float2(fh.x + fl.x, fh.y + fl.y);
-                                        }
+                                if (!kok[k]) break;
+                                char* const dst = cp(h, rh) + (GLU ? 4 * k : 8 * k) * CES;
+                                const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
+                                const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
+                                if (EPI == TC_EPI_ATOMIC_ADD) {
+                                    atomicAdd(reinterpret_cast<float*>(dst), x0);
+                                    atomicAdd(reinterpret_cast<float*>(dst) + 1, x1);
+                                } else if (GLU) {
+                                    float o = x0 * tc_gate<EPI>(p.epi, x1);
+                                    if (has_add) o += ad[h][rh][k].x;
+                                    if (OUT16) *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(o);
+                                    else *reinterpret_cast<float*>(dst) = o;
+                                } else {
+                                    float2 o = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
+                                    if (has_add) { o.x += ad[h][rh][k].x; o.y += ad[h][rh][k].y; }
+                                    if (OUTS) {
+                                        const uint32_t hi2 = cvt_f16x2_sat(o.x, o.y);
+                                        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+                                        const uint32_t lo2 = cvt_f16x2_sat(o.x - hf.x, o.y - hf.y);
+                                        *reinterpret_cast<uint32_t*>(dst) = hi2;
+                                        *reinterpret_cast<uint32_t*>(dst + lo_delta) = lo2;
                                     } else if (OUT16) {
-                                        if (GLU) ad[h][rh][k].x = __bfloat162float(arow16[n >> 1]);
-                                        else ad[h][rh][k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(arow16 + n));
-                                    } else if (GLU) ad[h][rh][k].x = __ldg(arow + (n >> 1));
-                                    else ad[h][rh][k] = __ldg(reinterpret_cast<const float2*>(arow + n));
+                                        *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o.x, o.y);
+                                    } else {
+                                        *reinterpret_cast<float2*>(dst) = o;
+                                    }
                                 }
                             }
                         }
-                }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                    for (int rh = 0; rh < 2; ++rh) {
-                        const int row = m0 + q * 32 + h * 16 + rh * 8 + tr;
-                        if constexpr (OUTS && GLU) {
-                            // hl16 GLU output: every lane computes its two gated values, neighbouring lanes swap one so that each
-                            // stores ONE packed pair (even lane: columns of k = 0, odd lane: k = 1) to the hi and the lo plane.
-                            // No early exit before the shuffle: all 32 lanes take part
-                            float o[2];
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) {
-                                const float x0 = fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x);
-                                const float x1 = fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y);
-                                o[k] = x0 * tc_gate<EPI>(p.epi, x1);
-                                if (ab) o[k] += ad[h][rh][k].x;
-                            }
-                            const bool odd = tq & 1;
-                            const float got = __shfl_xor_sync(0xffffffffu, odd ? o[0] : o[1], 1);
-                            const float p0 = odd ? got : o[0], p1 = odd ? o[1] : got;
-                            const int kk = odd ? 1 : 0;
-                            const int col = ((n0 + c0) >> 1) + 4 * kk + (tq & ~1);
-                            if (row < p.m && n0 + c0 + 8 * kk < p.n) {
-                                const uint32_t hi2 = cvt_f16x2_sat(p0, p1);
-                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
-                                const uint32_t lo2 = cvt_f16x2_sat(p0 - hf.x, p1 - hf.y);
-                                *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(cb) + (long long)row * p.c_rs + col) = hi2;
-                                *reinterpret_cast<uint32_t*>(cl + (long long)row * p.c_rs + col) = lo2;
-                            }
-                            continue;
-                        }
-                        if (row >= p.m) continue;
-                        float* crow = cb + (long long)row * p.c_rs;
-                        __nv_bfloat16* crow16 = reinterpret_cast<__nv_bfloat16*>(cb) + (long long)row * p.c_rs;
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int n = n0 + c0 + 8 * k + 2 * tq;
-                            if (n >= p.n) break;
-                            const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
-                            const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
-                            if (EPI == TC_EPI_ATOMIC_ADD) {
-                                atomicAdd(crow + n, x0);
-                                atomicAdd(crow + n + 1, x1);
-                            } else if (GLU) {
-                                float o = x0 * tc_gate<EPI>(p.epi, x1);
-                                if (ab) o += ad[h][rh][k].x;
-                                if (OUT16) crow16[n >> 1] = __float2bfloat16_rn(o);
-                                else crow[n >> 1] = o;
-                            } else {
-                                float2 o = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
-                                if (ab) { o.x += ad[h][rh][k].x; o.y += ad[h][rh][k].y; }
-                                if (OUTS) {
-                                    const uint32_t hi2 = cvt_f16x2_sat(o.x, o.y);
-                                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
-                                    const uint32_t lo2 = cvt_f16x2_sat(o.x - hf.x, o.y - hf.y);
-                                    *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(cb) + (long long)row * p.c_rs + n) = hi2;
-                                    *reinterpret_cast<uint32_t*>(cl + (long long)row * p.c_rs + n) = lo2;
-                                } else
-                                if (OUT16) *reinterpret_cast<__nv_bfloat162*>(crow16 + n) = __floats2bfloat162_rn(o.x, o.y);
-                                else *reinterpret_cast<float2*>(crow + n) = o;
-                            }
-                        }
                     }
+                    cp0 += CSTEP;
+                    ao0 += (unsigned)astep;
                 }
-            }
+            };
+            if (m0 + TC_BM <= p.m && n0 + BN <= p.n) run(std::true_type{}); else run(std::false_type{});
             tc_fence_before();
             if (CTA2) {
                 __syncwarp();
@@ -1082,6 +1112,9 @@ int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
 
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.a_row_stride >= d.k || d.a_rows == 1, "gemm_tc: a_row_stride < k");
+    CUM_REQUIRE((long long)d.m * d.c_row_stride < (1ll << 31) && (!d.addend || (long long)d.m * d.add_row_stride < (1ll << 29)),
+                "gemm_tc: one batch plane of the output / addend must span fewer than 2^31 elements (m=%d, c_row_stride=%lld)",
+                d.m, (long long)d.c_row_stride);
     const bool narrow = d.n <= 128;
     if (d.math == CUM_MATH_TF32X3) {
         CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: TF32X3 needs w_lo (see cum_split_tf32)");
