@@ -270,6 +270,59 @@ def run_train(args, net, dev, rank, world, dist):
         dist.destroy_process_group()
 
 
+def run_sweep(args, net, eng, dev):
+    """BASELINE.json configs[4]: long-clip / batch sweep of the offline forward on one GPU -- throughput plus the per-kernel
+    times of the scan and of the conv stack (tap-GEMMs) for every (batch, clip length)."""
+    points = [(8, 10.0), (64, 10.0), (256, 10.0), (21, 30.0), (85, 30.0), (10, 60.0), (42, 60.0)]
+    rows = []
+
+    def tokens(T):
+        n = net.valid_length(T)
+        for _ in range(net.encoder_n_layers):
+            n = (n - 4) // 2 + 1
+        return n
+
+    for B, sec in points:
+        T = int(sec * SR)
+        x_dev = synth_noisy(B, sec, 99).to(dev)
+        work = torch.empty_like(x_dev)
+
+        def step():
+            work.copy_(x_dev)
+            with torch.no_grad():
+                return net(work)
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        eng.prof, eng.launches = [], 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        prof = eng.profile_summary()
+        eng.prof = None
+        k = {n: round(v["ms"] / 3, 3) for n, v in prof.items()}
+        scan = prof.get("selective_scan")
+        rows.append({"batch": B, "clip_seconds": sec, "bottleneck_tokens": tokens(T), "ms_per_step": round(ms, 3),
+                     "audio_s_per_s": round(B * sec / (ms / 1e3), 1), "gemm_ms": round(k.get("gemm", 0) + k.get("gemm_tap2", 0), 3),
+                     "scan_ms": k.get("selective_scan"),
+                     "scan_state_updates_per_s": round(scan["flops"] / (scan["ms"] / 1e3)) if scan else None,
+                     "scan_GBps": round(scan["bytes"] / (scan["ms"] / 1e3) / 1e9, 1) if scan else None,
+                     "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)})
+        print("# sweep", rows[-1], file=sys.stderr, flush=True)
+        del x_dev, work
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+    print(json.dumps({"metric": METRIC + " [clip-length / batch sweep]", "unit": UNIT, "n_gpus": 1, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "CleanUMamba E8 full offline forward, math=%s: batch x clip-length sweep (3 timed steps "
+                                             "after 2 warm-ups per point, CUDA events)" % args.math},
+                      "sweep": rows}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -286,7 +339,7 @@ def main():
                          "full-scale amplitude); fp32 = exact CUDA-core FFMA")
     ap.add_argument("--no-variants", action="store_true", help="skip the short tf32x3 / fp32 comparison runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="offline", choices=["offline", "stream", "train"],
+    ap.add_argument("--mode", default="offline", choices=["offline", "stream", "train", "sweep"],
                     help="offline = headline (configs[1]); stream = configs[2]: carried-state chunked inference; "
                          "train = configs[3]: fwd + L1/MR-STFT loss + bwd + Adam, data-parallel gradient all-reduce")
     ap.add_argument("--streams", type=int, default=4096, help="[stream] concurrent streams per GPU")
@@ -318,6 +371,9 @@ def main():
         return
     if args.mode == "train":
         run_train(args, net, dev, rank, world, dist)
+        return
+    if args.mode == "sweep":
+        run_sweep(args, net, eng, dev)
         return
     B, T = args.batch, int(args.seconds * SR)
     host_in = synth_noisy(B, args.seconds, 1234 + rank).pin_memory()

@@ -1067,6 +1067,9 @@ static WgradPlan plan_wgrad(const cum_wgrad_desc& d) {
 long long wgrad_tc_workspace_bytes(const cum_wgrad_desc& d) { return (long long)plan_wgrad(d).ws_bytes; }
 
 template <int BN> static int launch_wgrad_gemm(const cum_gemm_desc& g, cudaStream_t st) {
+    if constexpr (BN == 256) {      // CTA pairs (half a W^T tile per CTA) when the output has more than one 128-row tile
+        if (cta2_policy() >= 0 && g.m > TC_BM && (sm_count() & 1) == 0) return launch_tc<TC_TF32X3, BN, TC_EPI_ATOMIC_ADD, 0, true>(g, st);
+    }
     return launch_tc<TC_TF32X3, BN, TC_EPI_ATOMIC_ADD, 0>(g, st);
 }
 
