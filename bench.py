@@ -6,7 +6,7 @@
 
 Workload (BASELINE.json configs[1]): CleanUMamba E8 full (41.37 M params, seeded random init -- the full checkpoints are
 not shipped), batch 64 x 10 s of 16 kHz synthetic noisy speech per GPU, offline forward, fp32 storage and
-fp32-tolerance arithmetic (default math mode tf32x3; --math fp32 = exact FFMA).  A "step" is
+fp32-tolerance arithmetic (default math mode f16x3; --math fp32 = exact FFMA).  A "step" is
 one forward pass over one batch.  Metric: audio-seconds denoised per wall-second, aggregate over all GPUs (utterance
 sharding, no data-path collective -> weak scaling).
 
@@ -461,7 +461,7 @@ def main():
     roofline = {"kernel": "tap-GEMM (conv/convT/1x1/projection contractions, %s)" % args.math, "bound": "tensor",
                 "achieved": round(achieved, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic,
-                "traffic_note": "bytes per STEP over the 44 launches of this kernel family (ncu dram__bytes, profiles/r01_ncu_gemm_all44_f16x3.md); "
+                "traffic_note": "bytes per STEP over the 44 launches of this kernel family (ncu dram__bytes, profiles/r01_final_launches_f16x3.md); "
                                 "algorithmic activation traffic is 64-66 GB, i.e. no re-reads" if traffic else None,
                 "peak_source": pk["src"] + " bf16 sustained",
                 "share_of_step": round(gem["ms"] / total_kernel_ms, 4) if total_kernel_ms else None,
@@ -472,8 +472,11 @@ def main():
                          "kind::tf32 MMAs per product (TF32 pipe = 1/2 of the bf16 peak used as denominator), so the pipe-level "
                          "rate is 3x achieved; ncu sm__pipe_tensor_cycles_active = 70-76 % on the K>=1024 layers "
                          "(profiles/r01_ncu_full_gemm_tf32x3.md)") if args.math == "tf32x3" else
-                        ("achieved = ALGORITHMIC flops / CUDA-event kernel time; bf16x3 issues 3 kind::f16 (bf16) MMAs per product, "
-                         "so the tensor-pipe rate is 3x achieved (K>=1024 layers: ~1.25 PFLOP/s of 16-bit MMA work)") if args.math in ("bf16x3", "f16x3") else None}
+                        ("achieved = ALGORITHMIC flops / CUDA-event kernel time; the split modes issue 3 kind::f16 MMAs per product, so the "
+                         "tensor-pipe work rate is 3x achieved (mma_work_tflops); ncu: K>=1024 layers 81-94 % tensor-pipe active, "
+                         "the 64/128-channel layers are bound by store wavefronts / HBM (profiles/r01_final_launches_f16x3.md)")
+                        if args.math in ("bf16x3", "f16x3") else None,
+                "mma_work_tflops": round(achieved * (3 if args.math in ("tf32x3", "bf16x3", "f16x3") else 1), 1)}
     scan = prof.get("selective_scan")
     scan_roof = None
     if scan:

@@ -12,6 +12,9 @@ timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --sectio
     $BENCH --batch 64 > gpurun_out/ncu_all44.log 2>&1; echo "ncu gemm all44 rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:selective_scan -s 12 -c 1 -f -o gpurun_out/prof_scan \
     $BENCH --batch $B > gpurun_out/ncu_full_scan.log 2>&1; echo "ncu scan rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s $((57*4)) -c 57 --csv --log-file gpurun_out/launches_$MATH.csv \
-    $BENCH > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+# launch list of one whole forward (our kernels only): time, DRAM bytes, tensor-pipe activity per launch -> tools/launch_table.py
+timeout 900 ncu -k regex:"gemm_tc_kernel|selective_scan|conv_in|convt_out|ln_residual|dwconv|wave_normalize" \
+    --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
+    --clock-control none -c 500 --csv --log-file gpurun_out/launches_$MATH.csv \
+    python -u bench.py --steps 1 --warmup 3 --math $MATH --no-cpu-baseline --no-variants > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 ls -la gpurun_out/*.ncu-rep; du -sh gpurun_out
