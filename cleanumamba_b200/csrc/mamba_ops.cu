@@ -301,7 +301,37 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
     // per-thread constants and carried state
     float2 a2p[NS / 2], h2[NS / 2];          // (state 2j, state 2j+1) pairs
     const bool state_vec = (p.n_state % 4 == 0) && (slice * NS + NS <= p.n_state) && c_ok;   // float4 path (64 B / thread)
-    if (state_vec) {
+    // Carried state (streaming): the (CH x NP) state block of this CTA is ONE contiguous 16 KB run of h0 / h_out.  Per-thread
+    // float4 accesses touch it with 16 bytes per 256-byte-strided lane (32 LSU wavefronts per instruction, x4 instructions, x2 for
+    // load + store: at one token per call that WAS the kernel).  Instead the block moves through shared memory (aliasing ypart,
+    // 16-byte chunks XOR-swizzled by the channel) with fully coalesced global accesses.
+    static_assert(NS <= TC, "the state staging tile aliases ypart");
+    float* const hs = &sm.ypart[0][0][0];
+    const bool state_tile = (p.n_state == NP) && (c0 + CH <= p.d) &&
+                            (!p.h0 || ((uintptr_t)p.h0 & 15) == 0) && (!p.h_out || ((uintptr_t)p.h_out & 15) == 0);
+    auto hs_chunk = [&](int chn, int chunk) { return hs + chn * NP + ((chunk ^ (chn & (NP / 4 - 1))) << 2); };
+    if (state_tile) {
+#pragma unroll
+        for (int q = 0; q < NS / 4; ++q) {
+            const float4 av = __ldg(reinterpret_cast<const float4*>(p.a2 + (long long)c * p.n_state + slice * NS) + q);
+            a2p[2 * q] = make_float2(av.x, av.y); a2p[2 * q + 1] = make_float2(av.z, av.w);
+            h2[2 * q] = make_float2(0.f, 0.f); h2[2 * q + 1] = make_float2(0.f, 0.f);
+        }
+        if (p.h0) {
+            const float4* src = reinterpret_cast<const float4*>(p.h0 + ((long long)b * p.d + c0) * NP);
+            for (int i = tid; i < CH * NP / 4; i += NT) {
+                const int chn = i / (NP / 4), chunk = i - chn * (NP / 4);
+                *reinterpret_cast<float4*>(hs_chunk(chn, chunk)) = src[i];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < NS / 4; ++q) {
+                const float4 hv = *reinterpret_cast<const float4*>(hs_chunk(ch, slice * (NS / 4) + q));
+                h2[2 * q] = make_float2(hv.x, hv.y); h2[2 * q + 1] = make_float2(hv.z, hv.w);
+            }
+            // (the chunk loop synchronises twice before ypart is written)
+        }
+    } else if (state_vec) {
 #pragma unroll
         for (int q = 0; q < NS / 4; ++q) {
             const float4 av = __ldg(reinterpret_cast<const float4*>(p.a2 + (long long)c * p.n_state + slice * NS) + q);
@@ -388,7 +418,18 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
         }
     }
     if (p.h_out) {
-        if (state_vec) {
+        if (state_tile) {
+            __syncthreads();          // the last combine phase has read ypart
+#pragma unroll
+            for (int q = 0; q < NS / 4; ++q)
+                *reinterpret_cast<float4*>(hs_chunk(ch, slice * (NS / 4) + q)) = make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
+            __syncthreads();
+            float4* dst = reinterpret_cast<float4*>(p.h_out + ((long long)b * p.d + c0) * NP);
+            for (int i = tid; i < CH * NP / 4; i += NT) {
+                const int chn = i / (NP / 4), chunk = i - chn * (NP / 4);
+                dst[i] = *reinterpret_cast<const float4*>(hs_chunk(chn, chunk));
+            }
+        } else if (state_vec) {
 #pragma unroll
             for (int q = 0; q < NS / 4; ++q)
                 *(reinterpret_cast<float4*>(p.h_out + ((long long)b * p.d + c) * p.n_state + slice * NS) + q) =
@@ -401,6 +442,64 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// selective_scan, few tokens per call with carried state (streaming: 1-2 tokens per stream per feed(); the reference's
+// Mamba.step / selective_state_update).  The work is then the 2 x 512 KB of state per (stream, layer) that must be read and
+// written, not the recurrence: one thread owns 4 states of one channel (16 lanes = one channel's 256-byte state row, fully
+// coalesced), loops over the tokens, and the 16 lanes reduce <h, C_t> with shuffles.  No shared memory, 11 registers of
+// state: occupancy hides the latency that bounded the chunked kernel (2.0 ms per layer at 4096 streams x 1 token).
+// ---------------------------------------------------------------------------------------------------------
+template <int T>      // tokens per call (compile-time: every token's inputs are requested before the dependent recurrence starts)
+__global__ void __launch_bounds__(256) selective_scan_step_kernel(const cum_scan_desc p) {
+    const int b = blockIdx.y;
+    const int g = threadIdx.x & 15;
+    const int c = blockIdx.x * 16 + (threadIdx.x >> 4);         // d % 16 == 0 (host check): whole 16-lane groups stay or leave
+    if (c >= p.d) return;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.a2 + (long long)c * 64) + g);
+    const long long hoff = ((long long)b * p.d + c) * 64;
+    float4 h = p.h0 ? *(reinterpret_cast<const float4*>(p.h0 + hoff) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float bias = p.delta_bias ? __ldg(p.delta_bias + c) : 0.f;
+    const float dk = p.Dskip ? __ldg(p.Dskip + c) : 0.f;
+    const float* ub = p.u + (long long)b * p.u_bs + c;
+    const float* db = p.delta + (long long)b * p.dl_bs + c;
+    const float* zb = p.z ? p.z + (long long)b * p.z_bs + c : nullptr;
+    const float* Bb = p.Bm + (long long)b * p.B_bs + 4 * g;
+    const float* Cb = p.Cm + (long long)b * p.C_bs + 4 * g;
+    float dlv[T], uv[T], zv[T];
+    float4 bvv[T], cvv[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        dlv[t] = db[(long long)t * p.dl_rs];
+        uv[t] = ub[(long long)t * p.u_rs];
+        zv[t] = zb ? zb[(long long)t * p.z_rs] : 0.f;
+        bvv[t] = *reinterpret_cast<const float4*>(Bb + (long long)t * p.B_rs);
+        cvv[t] = *reinterpret_cast<const float4*>(Cb + (long long)t * p.C_rs);
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        float dl = dlv[t] + bias;
+        if (p.delta_softplus) dl = softplusf_(dl);
+        const float u = uv[t];
+        const float du = dl * u;
+        const float4 bv = bvv[t], cv = cvv[t];
+        h.x = fmaf(ex2_approx(dl * a.x), h.x, du * bv.x);
+        h.y = fmaf(ex2_approx(dl * a.y), h.y, du * bv.y);
+        h.z = fmaf(ex2_approx(dl * a.z), h.z, du * bv.z);
+        h.w = fmaf(ex2_approx(dl * a.w), h.w, du * bv.w);
+        float part = fmaf(h.x, cv.x, fmaf(h.y, cv.y, fmaf(h.z, cv.z, h.w * cv.w)));
+        part += __shfl_xor_sync(0xffffffffu, part, 8);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        if (g == 0) {
+            float yv = fmaf(dk, u, part);
+            if (zb) yv *= __fdividef(zv[t], 1.0f + __expf(-zv[t]));
+            p.y[(long long)b * p.y_bs + (long long)t * p.y_rs + c] = yv;
+        }
+    }
+    if (p.h_out) *(reinterpret_cast<float4*>(p.h_out + hoff) + g) = h;
 }
 
 template <int NS, int SL, int CH, int TC>
@@ -423,6 +522,16 @@ int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.u && d.delta && d.Bm && d.Cm && d.y && d.a2, "selective_scan: null pointer");
     CUM_REQUIRE(d.batch > 0 && d.batch <= 65535 && d.len > 0 && d.d > 0 && d.n_state > 0, "selective_scan: bad shape");
     CUM_REQUIRE(d.n_state <= 64, "selective_scan: n_state=%d > 64 not supported", d.n_state);
+    const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    // measured at 4096 streams (3 layers): 1 token 2.5 ms vs 6.0 ms chunked, 2 tokens 4.1 vs 6.2, 4 tokens 7.3 vs 6.4 -> up to 2 tokens
+    if (d.len <= 2 && d.n_state == 64 && d.d % 16 == 0 && (d.h0 || d.h_out) && !d.h_ckpt && al16(d.a2) && al16(d.Bm) && al16(d.Cm) &&
+        (!d.h0 || al16(d.h0)) && (!d.h_out || al16(d.h_out)) && (d.B_rs | d.C_rs | d.B_bs | d.C_bs) % 4 == 0) {
+        dim3 grid((unsigned)(d.d / 16), (unsigned)d.batch);
+        if (d.len == 1) selective_scan_step_kernel<1><<<grid, 256, 0, st>>>(d);
+        else selective_scan_step_kernel<2><<<grid, 256, 0, st>>>(d);
+        CUM_LAUNCH_CHECK("selective_scan_step_kernel");
+        return CUM_OK;
+    }
     if (d.n_state > 32) return launch_scan<16, 4, 64, 16>(d, st);
     if (d.n_state > 16) return launch_scan<16, 2, 64, 16>(d, st);
     if (d.n_state > 8)  return launch_scan<16, 1, 64, 16>(d, st);

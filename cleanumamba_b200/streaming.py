@@ -28,6 +28,8 @@ from ._lib import EPI_GLU, EPI_RELU, ptr
 
 
 class StreamSession:
+    BATCH_MODE_ROWS = 128     # rows per stream from which a level runs one GEMM batch item per stream (in-place operands)
+
     def __init__(self, model, batch: int = 1):
         self.model = model
         self.eng = model.engine()
@@ -126,6 +128,15 @@ class StreamSession:
                 eng._call("conv_in", lib.cum_conv_in_fwd, X.data_ptr() + 4 * off, X.shape[1], B, n_use - off,
                           pk["enc0.w"].data_ptr(), pk["enc0.b"].data_ptr(), y.data_ptr(), rows_new, e["Hc_p"], 4, 2,
                           ptr(scale), per_frame, row_off, st())
+            elif rows_new >= self.BATCH_MODE_ROWS:
+                # enough rows per stream for full 128-row tiles: one GEMM batch item per stream, operands addressed IN PLACE
+                # (the input window inside the previous level's FIFO, the output slot inside this level's FIFO): no staging copies
+                P = rows_new
+                src, cp = self.enc_buf[i - 1], e["Cin_p"]
+                lo = 2 * c_old - self.enc_base[i - 1]
+                y = torch.empty(B * P, e["Hc_p"], dtype=torch.float32, device=dev)
+                eng.gemm(src, lo * cp, src.stride(0), 2 * cp, (src.shape[1] - lo) // 2, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
+                         y, 0, P * e["Hc_p"], e["Hc_p"], P, e["Hc_p"], B, EPI_RELU, taps=2, shifts=(0, 1))
             else:
                 P = rows_new + 1
                 src, cp = self.enc_buf[i - 1], e["Cin_p"]
@@ -134,14 +145,19 @@ class StreamSession:
                 y = torch.empty(B * P, e["Hc_p"], dtype=torch.float32, device=dev)
                 eng.gemm(cin, 0, 0, 2 * cp, B * P, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
                          y, 0, 0, e["Hc_p"], B * P, e["Hc_p"], 1, EPI_RELU, taps=2, shifts=(0, 1))
-            newc = eng.dense(y, B * P, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act)
             # output FIFO of this level: [columns the decoder has not consumed yet | new columns]
             keep = c_old - self.enc_base[i]
             buf = torch.empty(B, keep + rows_new, e["Ho_p"], dtype=torch.float32, device=dev)
             if keep:
                 old = self.enc_buf[i]
                 buf[:, :keep].copy_(old[:, old.shape[1] - keep:])
-            buf[:, keep:].copy_(newc.view(B, P, e["Ho_p"])[:, :rows_new])
+            if rows_new >= self.BATCH_MODE_ROWS:       # batch mode: the GLU GEMM writes straight into the FIFO slot
+                ho = e["Ho_p"]
+                eng.gemm(y, 0, P * e["Hc_p"], e["Hc_p"], P, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"],
+                         buf, keep * ho, (keep + rows_new) * ho, ho, rows_new, 2 * ho, B, act)
+            else:
+                newc = eng.dense(y, B * P, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act)
+                buf[:, keep:].copy_(newc.view(B, P, e["Ho_p"])[:, :rows_new])
             self.enc_buf[i] = buf
             self.enc_count[i] = c_new
             avail_in = c_new
@@ -161,12 +177,29 @@ class StreamSession:
         out = None
         for j, dd in enumerate(meta["dec"]):
             hg = dd["Hg_p"]
-            gnew = eng.dense(xcur, B * d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * hg, epi=act)
+            batch_mode = d_cols >= self.BATCH_MODE_ROWS
             G = torch.empty(B, d_cols + 1, hg, dtype=torch.float32, device=dev)
             G[:, 0].copy_(self.dec_carry[j])                    # carried g[-1]: replaces the overlap-add tail (:476-484)
-            G[:, 1:].copy_(gnew.view(B, d_cols, hg))
+            if batch_mode:      # one batch item per stream: the GLU output lands in G[:, 1:] directly
+                eng.gemm(xcur, 0, d_cols * dd["Cin_p"], dd["Cin_p"], d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"],
+                         G, hg, (d_cols + 1) * hg, hg, d_cols, 2 * hg, B, act)
+            else:
+                gnew = eng.dense(xcur, B * d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * hg, epi=act)
+                G[:, 1:].copy_(gnew.view(B, d_cols, hg))
             self.dec_carry[j] = G[:, d_cols].clone()
-            if j < D - 1:
+            if j < D - 1 and batch_mode:
+                co = dd["Co_p"]
+                lvl = D - 2 - j
+                skip = self.enc_buf[lvl]
+                nxt = torch.empty(B * d_cols, 2 * co, dtype=torch.float32, device=dev)
+                # row p of stream b = Wa . G[b, p+1] + Wb . G[b, p] + skip columns (2p, 2p+1), read in place from the encoder FIFO
+                eng.gemm(G, 0, (d_cols + 1) * hg, hg, d_cols + 1, hg, f"dec{j}.w", pk[f"dec{j}.b"], nxt, 0, d_cols * 2 * co, 2 * co,
+                         d_cols, 2 * co, B, EPI_RELU, taps=2, shifts=(1, 0), addend=skip, add_bs=skip.stride(0), add_rs=2 * co)
+                self.enc_base[lvl] += 2 * d_cols
+                self.enc_buf[lvl] = skip[:, 2 * d_cols:]
+                xcur = nxt                                       # (B, d_cols, 2 co) == (B * 2 d_cols, co)
+                d_cols = 2 * d_cols
+            elif j < D - 1:
                 co = dd["Co_p"]
                 lvl = D - 2 - j
                 skip = self.enc_buf[lvl]
