@@ -212,6 +212,7 @@ class Engine:
         self.pk16 = {k: t.to(torch.bfloat16) for k, t in items.items() if t.dim() >= 2} if self.bf16_io else {}
         self.lib = _lib.init(dev)
         self.pk_hi, self.pk_lo, self.w_scale_inv, self.w_lo_zero = {}, {}, {}, set()
+        self.key_math = {}
         if self.math == _lib.MATH_TF32X3:      # hi/lo copies of the whole packed buffer (only GEMM weights use them)
             hi, lo = torch.empty_like(flat), torch.empty_like(flat)
             check(self.lib.cum_split_tf32(flat.data_ptr(), hi.data_ptr(), lo.data_ptr(), flat.numel(),
@@ -274,7 +275,7 @@ class Engine:
         d.taps = taps
         d.tap_shift[0], d.tap_shift[1] = shifts
         wt = self.pk[w]
-        d.math = self.math if math is None else math
+        d.math = (self.key_math.get(w, self.math) if math is None else math)      # per-weight override (TrainEngine: dgrad weights)
         d.out_bf16 = 1 if c.dtype == torch.bfloat16 else 0
         if a.dtype == torch.bfloat16:          # reduced-precision variant: bf16 activations x bf16 weights, one MMA pass
             d.math = _lib.MATH_BF16

@@ -10,6 +10,7 @@ packed-weight layout and unpacked into parameter shapes at the end (``unpack_gra
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List
 
 import torch
@@ -22,13 +23,16 @@ from .engine import Engine
 class TrainEngine(Engine):
     """Engine with transposed weight copies (for dgrad) and a gradient buffer.
 
-    Training never uses the fp16 split ("f16x3"): back-propagated gradients routinely fall below fp16's 6e-5 normal
-    range, so that mode is mapped to "tf32x3" (same 22-bit products, fp32 exponent range)."""
+    Under "f16x3" the FORWARD GEMMs of a training step use the fp16 split (same kernels and accuracy as inference, 2x the
+    TF32 tensor rate); the data-gradient GEMMs never do: back-propagated gradients routinely fall below fp16's 6e-5 normal
+    range, so the transposed weights carry TF32 hi/lo halves and run as "tf32x3" (same 22-bit products, fp32 exponent
+    range), as do the weight gradients.  "bf16" (inference-only storage variant) maps to "tf32x3" entirely."""
 
     tc_wgrad = True      # tensor-core weight gradients (tests may switch to the fp32 CUDA-core kernel)
+    f16_forward = os.environ.get("CUM_TRAIN_F16_FWD", "1") != "0"     # f16x3 models: forward GEMMs in f16x3 (A/B switch)
 
     def _pack(self):
-        if getattr(self.model, "math_mode", None) in ("f16x3", "bf16"):
+        if getattr(self.model, "math_mode", None) == "bf16" or not self.f16_forward and getattr(self.model, "math_mode", None) == "f16x3":
             self.model_math_override = "tf32x3"
         super()._pack()
 
@@ -42,6 +46,23 @@ class TrainEngine(Engine):
         return extra
 
     def _post_pack(self, items, offs, total):
+        if self.math == _lib.MATH_F16X3:
+            # transposed (dgrad) weights: TF32 hi/lo halves instead of the fp16 split the base class prepared for every GEMM weight
+            tkeys = [k for k in items if k.endswith("T")]
+            lo0 = min(offs[k] for k in tkeys)
+            hi0 = max(offs[k] + (items[k].numel() + 63) // 64 * 64 for k in tkeys)
+            thi = torch.empty(hi0 - lo0, dtype=torch.float32, device=self.device)
+            tlo = torch.empty_like(thi)
+            check(self.lib.cum_split_tf32(self._flat.data_ptr() + 4 * lo0, thi.data_ptr(), tlo.data_ptr(), hi0 - lo0, _lib.stream_ptr()),
+                  "cum_split_tf32")
+            for k in tkeys:
+                o = offs[k] - lo0
+                self.pk_hi[k] = thi[o: o + items[k].numel()].view(items[k].shape)
+                self.pk_lo[k] = tlo[o: o + items[k].numel()].view(items[k].shape)
+                self.key_math[k] = _lib.MATH_TF32X3
+                self.w_scale_inv.pop(k, None)
+                self.w_lo_zero.discard(k)
+            self._t_split = (thi, tlo)
         # gradient buffer: same offsets as the packed weights for the base items (they precede the transposed copies),
         # followed by a slot for the scalar bias of the last transposed conv
         base = [k for k in items if not k.endswith("T")]

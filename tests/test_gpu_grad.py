@@ -168,7 +168,9 @@ def test_selective_scan_backward(b, d, l, n):
 
 @pytest.mark.parametrize("name,math,seconds", [("tiny_equalwidth_seed0", "fp32", 0.2), ("e6_pruned_200k", "fp32", 0.25),
                                                ("e8_pruned_500k", "fp32", 0.3), ("e8_pruned_500k", "tf32x3", 0.3),
-                                               ("e8_pruned_500k", "bf16x3", 0.3)])
+                                               ("e8_pruned_500k", "bf16x3", 0.3),
+                                               # default mode: forward GEMMs f16x3, data / weight gradients tf32x3
+                                               ("e8_pruned_500k", "f16x3", 0.3), ("mini_mamba_442k", "f16x3", 0.3)])
 def test_model_gradients_match_oracle_autograd(name, math, seconds):
     from cleanumamba_b200.network import Net
     fx = load_golden(name)

@@ -11,5 +11,5 @@ timeout 900 python -u bench.py --impl reference --steps 3 --warmup 1 > gpurun_ou
 for H in 1 4 16; do
   timeout 600 python -u bench.py --mode stream --model e6 --streams 4096 --hops $H --steps 5 --warmup 3 > gpurun_out/bench_stream_h$H.json 2> gpurun_out/bench_stream_h$H.err; echo "stream hops=$H rc=$?"; tail -c 1200 gpurun_out/bench_stream_h$H.json | cut -c1-1200
 done
-timeout 600 python -u bench.py --mode train --steps 3 --warmup 3 --math tf32x3 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err; echo "train rc=$?"; cut -c1-900 gpurun_out/bench_train.json
+timeout 600 python -u bench.py --mode train --steps 3 --warmup 3 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err; echo "train rc=$?"; cut -c1-900 gpurun_out/bench_train.json
 timeout 900 python -u bench.py --mode sweep > gpurun_out/bench_sweep.json 2> gpurun_out/bench_sweep.err; echo "sweep rc=$?"; grep "# sweep" gpurun_out/bench_sweep.err
