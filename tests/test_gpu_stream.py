@@ -71,6 +71,51 @@ def test_batched_streams_multi_hop_chunks():
         assert (got[b:b + 1] - want).abs().max().item() < TOL * (1 + b)
 
 
+def test_batched_streams_large_and_small_chunks_mix_gemm_modes():
+    """3 streams fed 40-hop chunks (>= 128 new rows per stream at the outer levels: one GEMM batch item per stream, operands read
+    and written in place inside the FIFOs), then 1- and 2-hop chunks (flattened streams, state-update scan kernel), then large
+    again: every transition between the two operand layouts, against offline forward on the fed signal."""
+    fx = load_golden("e6_pruned_200k")
+    net = build(fx, normalize_input=False, math_mode="f16x3")
+    g = torch.Generator().manual_seed(5)
+    B, hop = 3, 64
+    sizes = [190 + hop * 39, hop * 40, hop * 1, hop * 2, hop * 1, hop * 40, hop * 3, hop * 40]
+    x = torch.randn(B, sum(sizes), generator=g) * 0.1
+    sess = net.stream_session(batch=B)
+    outs, pos = [], 0
+    for n in sizes:
+        outs.append(sess.feed(x[:, pos:pos + n].cuda()))
+        pos += n
+    got = torch.cat(outs, 1).cpu()
+    off = orc.forward(fx["state_dict"], x, normalize_input=False)[:, 0]
+    assert got.shape[1] > 0.9 * x.shape[1]
+    assert (got - off[:, : got.shape[1]]).abs().max().item() < 1e-4      # f16x3 products (BASELINE tolerance)
+
+
+def test_single_hop_feeds_use_state_update_scan_d_state_64():
+    """d_state = 64 (the shipped full-size geometry): 1- and 2-hop feeds run the state-update scan kernel; streamed output
+    equals offline forward of the same weights (CPU oracle)."""
+    from cleanumamba_b200.network import Net
+    torch.manual_seed(3)
+    cfg = dict(channels_input=1, channels_output=1, channels_H=16, max_H=32, encoder_n_layers=3, kernel_size=4, stride=2,
+               tsfm_n_layers=2, tsfm_n_head=1, tsfm_d_model=64, tsfm_d_inner=64, normalize_input=False, math_mode="fp32")
+    net = Net("CleanUMamba", cfg).cuda().float().eval()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    B, hop = 2, 8
+    g = torch.Generator().manual_seed(9)
+    sizes = [net.frame_length] + [hop] * 9 + [2 * hop] * 4 + [hop * 5] + [hop] * 3
+    x = torch.randn(B, sum(sizes), generator=g) * 0.1
+    sess = net.stream_session(batch=B)
+    outs, pos = [], 0
+    for n in sizes:
+        outs.append(sess.feed(x[:, pos:pos + n].cuda()))
+        pos += n
+    got = torch.cat(outs, 1).cpu()
+    off = orc.forward(sd, x, normalize_input=False)[:, 0]
+    assert got.shape[1] >= x.shape[1] - net.frame_length
+    assert (got - off[:, : got.shape[1]]).abs().max().item() < TOL
+
+
 def test_module_feed_flush_api():
     """Same call pattern as the reference self-test (CleanUMamba.py:574-582): feed + flush ~= parallel forward."""
     fx = load_golden("mini_mamba_442k")
