@@ -161,8 +161,14 @@ def run_stream(args, net, eng, dev, rank, world, dist):
     for _ in range(args.warmup):
         out = sess.feed(chunk)
         assert out.shape == (S, n_chunk), out.shape
+    if args.graph:          # steady-state CUDA graph of feed(): one replay per step instead of ~260 launches + Python glue
+        eng.launches = 0
+        sess.capture_graph(n_chunk)
+        launches_per_replay = eng.launches // 2          # capture_graph runs the step twice (eager rehearsal + capture)
+        for _ in range(2):
+            sess.feed(chunk)
     barrier()
-    eng.prof, eng.launches = [], 0
+    eng.prof, eng.launches = (None if args.graph else []), 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -170,7 +176,7 @@ def run_stream(args, net, eng, dev, rank, world, dist):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches, prof = eng.launches, eng.profile_summary()
+    launches, prof = (launches_per_replay * args.steps if args.graph else eng.launches), eng.profile_summary()
     eng.prof = None
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dchunk = torch.empty_like(chunk)
@@ -194,7 +200,7 @@ def run_stream(args, net, eng, dev, rank, world, dist):
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"CleanUMamba {args.model.upper()} streaming, {S} streams per GPU, {H} hops "
                                                  f"({n_chunk} samples, {1e3 * n_chunk / SR:.0f} ms) per feed(), carried conv/SSM state, "
-                                                 f"math={args.math}", "real_time_factor_per_stream": round(n_chunk / SR / (ms / args.steps / 1e3), 2),
+                                                 f"math={args.math}" + (", CUDA-graph replay" if args.graph else ""), "real_time_factor_per_stream": round(n_chunk / SR / (ms / args.steps / 1e3), 2),
                                      "chunk_latency_ms": round(ms / args.steps, 3)},
                           "e2e": {"value": round(audio / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": S * n_chunk * 4,
                                   "d2h_bytes_per_step": S * n_chunk * 4},
@@ -344,6 +350,7 @@ def main():
                          "train = configs[3]: fwd + L1/MR-STFT loss + bwd + Adam, data-parallel gradient all-reduce")
     ap.add_argument("--streams", type=int, default=4096, help="[stream] concurrent streams per GPU")
     ap.add_argument("--hops", type=int, default=16, help="[stream] hops (2^D samples each) per feed() call")
+    ap.add_argument("--graph", action="store_true", help="[stream] replay a captured CUDA graph of the steady-state feed()")
     args = ap.parse_args()
     cfg = CONFIGS[args.model]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -104,6 +104,12 @@ int cum_stream_std_fwd(const float* x, long long x_stride, int batch, int frames
                           (cudaStream_t)stream);
 }
 
+int cum_stream_std_counter_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
+                               int* frames_counter, float* running, float* scale_out, cum_stream_t stream) {
+    CUM_REQUIRE(frames_counter, "stream_std: null frames_counter");
+    return stream_std_fwd(x, x_stride, batch, frames, frame_len, hop, 0, running, scale_out, (cudaStream_t)stream, frames_counter);
+}
+
 int cum_convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
                       const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
                       int kernel, int stride, cum_stream_t stream) {

@@ -72,7 +72,7 @@ int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const
                 float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
                 int row_offset, cudaStream_t st, int out_fmt = 0 /* 0 fp32, 1 bf16, 2 fp16 hi/lo planes */, void* y_lo = nullptr);
 int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
-                   int frames_before, float* running, float* scale_out, cudaStream_t st);
+                   int frames_before, float* running, float* scale_out, cudaStream_t st, int* frames_counter = nullptr);
 int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
                   const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
                   int kernel, int stride, cudaStream_t st, bool in_bf16 = false);

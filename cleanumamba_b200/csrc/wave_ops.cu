@@ -58,10 +58,11 @@ int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStre
 // scale_out[b, j] = the running value after frame j; running[b] is updated in place.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stream_std_kernel(const float* __restrict__ x, long long x_stride, int frames,
-                                                          int frame_len, int hop, int frames_before,
+                                                          int frame_len, int hop, int frames_before, const int* __restrict__ frames_counter,
                                                           float* __restrict__ running, float* __restrict__ scale_out) {
     __shared__ double red[32];
     const int b = blockIdx.x;
+    if (frames_counter) frames_before = *frames_counter;       // device-side frame count (CUDA-graph replays: no host argument changes)
     const float* xb = x + (long long)b * x_stride;
     float run = running[b];
     for (int j = 0; j < frames; ++j) {
@@ -83,12 +84,18 @@ __global__ void __launch_bounds__(256) stream_std_kernel(const float* __restrict
     if (threadIdx.x == 0) running[b] = run;
 }
 
+__global__ void add_int_kernel(int* counter, int v) { *counter += v; }
+
 int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
-                   int frames_before, float* running, float* scale_out, cudaStream_t st) {
+                   int frames_before, float* running, float* scale_out, cudaStream_t st, int* frames_counter) {
     CUM_REQUIRE(x && running && scale_out, "stream_std: null pointer");
     CUM_REQUIRE(batch > 0 && frames > 0 && frame_len > 0 && hop > 0 && frames_before >= 0, "stream_std: bad shape");
-    stream_std_kernel<<<batch, 256, 0, st>>>(x, x_stride, frames, frame_len, hop, frames_before, running, scale_out);
+    stream_std_kernel<<<batch, 256, 0, st>>>(x, x_stride, frames, frame_len, hop, frames_before, frames_counter, running, scale_out);
     CUM_LAUNCH_CHECK("stream_std_kernel");
+    if (frames_counter) {       // every block has read the counter: stream order
+        add_int_kernel<<<1, 1, 0, st>>>(frames_counter, frames);
+        CUM_LAUNCH_CHECK("add_int_kernel");
+    }
     return CUM_OK;
 }
 

@@ -48,6 +48,8 @@ class StreamSession:
         self.states = [(torch.zeros(batch, mm["W"] - 1, mm["di_p"], dtype=torch.float32, device=self.dev),
                         torch.zeros(batch, mm["di_p"], mm["N_p"], dtype=torch.float32, device=self.dev))
                        for mm in meta["mamba"]]
+        self.frames_dev = None               # device copy of `frames` (graph mode: the running-std kernel reads it there)
+        self._graph = None                   # (CUDAGraph, chunk_samples, static input, static output, static state, counter deltas)
         self._reset_conv_state()
 
     # ------------------------------------------------------------------------------------------------------
@@ -72,6 +74,13 @@ class StreamSession:
             raise ValueError(f"expected a (batch={self.B}, n) tensor, got {tuple(chunk.shape)}")
         if chunk.device != self.dev:
             raise RuntimeError(f"chunk is on {chunk.device}, model on {self.dev} (no CPU fallback)")
+        if self._graph is not None:
+            if chunk.shape[1] == self._graph["chunk"]:
+                return self._replay(chunk)
+            self.release_graph()             # a different chunk size: back to the eager path (state stays valid)
+        return self._feed_eager(chunk)
+
+    def _feed_eager(self, chunk: torch.Tensor) -> torch.Tensor:
         self.pending = torch.cat([self.pending, chunk.to(torch.float32)], dim=1)
         n = self.pending.shape[1]
         if n < self.frame_length:
@@ -82,9 +91,90 @@ class StreamSession:
         self.samples_base += F * self.hop
         return out
 
+    # ------------------------------------------------------------------------------------------------------
+    # Steady-state CUDA graph.  A streaming step is ~260 small launches plus Python glue: launch-bound for one or a few
+    # hundred streams (2.1 ms per hop eagerly, regardless of the stream count).  Once the session is in steady state for a
+    # fixed chunk size every shape, FIFO offset and operand address of a step is constant, so the whole feed() is captured
+    # once and replayed: the carried state lives in static tensors (the graph ends by copying the new FIFO tails / carries
+    # back into them), the frame count of the running std lives on the device (cum_stream_std_counter_fwd).
+    # ------------------------------------------------------------------------------------------------------
+    _COUNTERS = ("enc_base", "enc_count", "samples_base", "frames", "frames_since_reset")
+
+    def _snapshot(self):
+        return {k: (list(getattr(self, k)) if isinstance(getattr(self, k), list) else getattr(self, k)) for k in self._COUNTERS}
+
+    def _restore(self, snap):
+        for k, v in snap.items():
+            setattr(self, k, list(v) if isinstance(v, list) else v)
+
+    @torch.no_grad()
+    def capture_graph(self, chunk_samples: int) -> None:
+        """Capture feed() for chunks of exactly ``chunk_samples`` samples (a multiple of the hop).  Call after at least one
+        eager feed() has produced output (steady state); feeds of any other size transparently fall back to the eager path."""
+        if chunk_samples <= 0 or chunk_samples % self.hop:
+            raise ValueError(f"chunk_samples must be a positive multiple of the hop ({self.hop})")
+        if self.frames_since_reset == 0 or self.pending.shape[1] != self.frame_length - self.hop:
+            raise RuntimeError("capture_graph: the session is not in steady state (feed at least one full frame first, and "
+                               "feed whole hops so that pending holds frame_length - hop samples)")
+        self.release_graph()
+        if self.model.normalize_input and self.frames_dev is None:
+            self.frames_dev = torch.tensor([self.frames], dtype=torch.int32, device=self.dev)
+        # static state tensors
+        self.pending = self.pending.contiguous().clone()
+        self.enc_buf = [b.contiguous().clone() for b in self.enc_buf]
+        self.dec_carry = [c.contiguous().clone() for c in self.dec_carry]
+        static = dict(pending=self.pending, enc=list(self.enc_buf), carry=list(self.dec_carry))
+        gx = torch.zeros(self.B, chunk_samples, dtype=torch.float32, device=self.dev)
+        # one eager step on a copy of ALL state, so that every lazy initialisation of this exact launch sequence has happened
+        snap = self._snapshot()
+        saved = ([t.clone() for t in (static["pending"], *static["enc"], *static["carry"], self.running_std)],
+                 [(a.clone(), b.clone()) for a, b in self.states], None if self.frames_dev is None else self.frames_dev.clone())
+        self._feed_eager(gx)
+        shapes_after = [tuple(b.shape) for b in self.enc_buf]
+        after = self._snapshot()
+        for dst, src in zip((static["pending"], *static["enc"], *static["carry"], self.running_std), saved[0]):
+            dst.copy_(src)
+        for (a, b), (sa, sb) in zip(self.states, saved[1]):
+            a.copy_(sa); b.copy_(sb)
+        if self.frames_dev is not None:
+            self.frames_dev.copy_(saved[2])
+        if shapes_after != [tuple(b.shape) for b in static["enc"]]:
+            self.pending, self.enc_buf, self.dec_carry = static["pending"], list(static["enc"]), list(static["carry"])
+            self._restore(snap)
+            raise RuntimeError("capture_graph: FIFO shapes change from step to step (not in steady state for this chunk size)")
+        self.pending, self.enc_buf, self.dec_carry = static["pending"], list(static["enc"]), list(static["carry"])
+        self._restore(snap)
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._feed_eager(gx)
+            static["pending"].copy_(self.pending)
+            for dst, src in zip(static["enc"], self.enc_buf):
+                dst.copy_(src)
+            for dst, src in zip(static["carry"], self.dec_carry):
+                dst.copy_(src)
+        # capture records, it does not execute: the state is still the pre-capture one
+        self.pending, self.enc_buf, self.dec_carry = static["pending"], list(static["enc"]), list(static["carry"])
+        self._restore(snap)
+        delta = {k: ([x - y for x, y in zip(after[k], snap[k])] if isinstance(snap[k], list) else after[k] - snap[k]) for k in snap}
+        self._graph = dict(graph=graph, chunk=chunk_samples, x=gx, out=out, static=static, delta=delta)
+
+    def release_graph(self) -> None:
+        self._graph = None
+
+    def _replay(self, chunk: torch.Tensor) -> torch.Tensor:
+        g = self._graph
+        g["x"].copy_(chunk)
+        g["graph"].replay()
+        for k, d in g["delta"].items():
+            cur = getattr(self, k)
+            setattr(self, k, [c + x for c, x in zip(cur, d)] if isinstance(cur, list) else cur + d)
+        return g["out"].clone()
+
     @torch.no_grad()
     def flush(self) -> torch.Tensor:
         """:358-368 -- clear the conv caches, feed frame_length zeros, return the first len(pending) samples."""
+        self.release_graph()
         self._reset_conv_state()
         n = self.pending.shape[1]
         out = self.feed(torch.zeros(self.B, self.frame_length, dtype=torch.float32, device=self.dev))
@@ -104,8 +194,12 @@ class StreamSession:
         scale = None
         if m.normalize_input:
             scale = torch.empty(B, F, dtype=torch.float32, device=dev)
-            eng._call("stream_std", lib.cum_stream_std_fwd, X.data_ptr(), X.shape[1], B, F, self.frame_length, self.hop,
-                      self.frames, self.running_std.data_ptr(), scale.data_ptr(), st())
+            if self.frames_dev is not None:
+                eng._call("stream_std", lib.cum_stream_std_counter_fwd, X.data_ptr(), X.shape[1], B, F, self.frame_length, self.hop,
+                          self.frames_dev.data_ptr(), self.running_std.data_ptr(), scale.data_ptr(), st(), launches=2)
+            else:
+                eng._call("stream_std", lib.cum_stream_std_fwd, X.data_ptr(), X.shape[1], B, F, self.frame_length, self.hop,
+                          self.frames, self.running_std.data_ptr(), scale.data_ptr(), st())
 
         # ---------------- encoder: every level produces all columns its (frame-aligned) input allows.
         # All streams are flattened into the GEMM M dimension (full 128-row MMA tiles even when a stream contributes only

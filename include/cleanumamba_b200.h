@@ -83,6 +83,10 @@ int cum_conv_in_fwd(const float* x, long long x_stride, int batch, int length, c
  * x: (batch, >= (frames-1)*hop + frame_len) raw pending samples [row stride x_stride]. */
 int cum_stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
                        int frames_before, float* running, float* scale_out, cum_stream_t stream);
+/* Same, with the frame count kept on the device: frames_before = *frames_counter, and *frames_counter += frames afterwards
+ * (stream-ordered).  No host-side argument changes between calls, so a captured CUDA graph of a streaming step can be replayed. */
+int cum_stream_std_counter_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
+                               int* frames_counter, float* running, float* scale_out, cum_stream_t stream);
 
 /* Replaces decoder[-1][2] ConvTranspose1d(H,1,K,S) (CleanUMamba.py:124) + the crop and `* std` (:318-319; per hop
  * `out *= self.input_std` :406-407 when streaming).  g: (batch, rows_in, c_pad) channels-last; w: (K, c_pad);

@@ -116,6 +116,42 @@ def test_single_hop_feeds_use_state_update_scan_d_state_64():
     assert (got - off[:, : got.shape[1]]).abs().max().item() < TOL
 
 
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("batch,hops", [(1, 1), (3, 4), (2, 40)])
+def test_cuda_graph_replay_equals_eager_feed(batch, hops, normalize):
+    """capture_graph(): the steady-state feed() replayed from a CUDA graph (static state tensors, device-side frame counter)
+    gives bit-identical output to the eager path over many steps, survives a chunk-size change (falls back to eager, state
+    intact) and can be re-captured."""
+    fx = load_golden("e6_pruned_200k")
+    hop = 64
+    g = torch.Generator().manual_seed(21)
+    n = hops * hop
+    x = torch.randn(batch, 190 - hop + n * 9 + 3 * hop, generator=g) * 0.1
+    outs = {}
+    for mode in ("eager", "graph"):
+        net = build(fx, normalize_input=normalize, math_mode="f16x3")
+        sess = net.stream_session(batch=batch)
+        pos = 190 - hop
+        o = [sess.feed(x[:, :pos].cuda()), sess.feed(x[:, pos:pos + n].cuda())]
+        pos += n
+        if mode == "graph":
+            sess.capture_graph(n)
+        for _ in range(4):
+            o.append(sess.feed(x[:, pos:pos + n].cuda())); pos += n
+        o.append(sess.feed(x[:, pos:pos + 3 * hop].cuda())); pos += 3 * hop      # other size: eager fallback
+        if mode == "graph":
+            assert sess._graph is None
+        o.append(sess.feed(x[:, pos:pos + n].cuda())); pos += n
+        if mode == "graph":
+            sess.capture_graph(n)
+        for _ in range(3):
+            o.append(sess.feed(x[:, pos:pos + n].cuda())); pos += n
+        outs[mode] = torch.cat(o, 1).cpu()
+        assert pos == x.shape[1]
+    assert outs["graph"].shape == outs["eager"].shape and outs["graph"].shape[1] > 0
+    assert torch.equal(outs["graph"], outs["eager"])
+
+
 def test_module_feed_flush_api():
     """Same call pattern as the reference self-test (CleanUMamba.py:574-582): feed + flush ~= parallel forward."""
     fx = load_golden("mini_mamba_442k")
