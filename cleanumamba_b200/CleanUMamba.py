@@ -163,11 +163,12 @@ class CleanUMamba(nn.Module):
         return {i: self.allocate_inference_cache_layer(blk.mixer, batch_size, dtype=dtype)
                 for i, blk in enumerate(self.tsfm_Mamba_layers)}
 
-    def stream_session(self, batch=1, compat_skip_order_bug=False):
+    def stream_session(self, batch=1, compat_skip_order_bug=False, auto_graph=False):
         """New carried-state streaming session for ``batch`` independent streams (extension: the reference's
-        ``feed`` is batch 1 and keeps its state on the module)."""
+        ``feed`` is batch 1 and keeps its state on the module).  ``auto_graph``: capture the steady-state step as a CUDA
+        graph once the same whole-hop chunk size has been fed a few times (see StreamSession.capture_graph)."""
         from .streaming import StreamSession
-        return StreamSession(self, batch=batch)
+        return StreamSession(self, batch=batch, auto_graph=auto_graph)
 
     @torch.no_grad()
     def feed(self, noisy_input):
@@ -178,7 +179,7 @@ class CleanUMamba(nn.Module):
         if noisy_input.shape[0] != 1:
             raise ValueError(f"Expected 1 channel, got {noisy_input.shape[0]}")
         if self._stream is None:
-            self._stream = self.stream_session(batch=1)
+            self._stream = self.stream_session(batch=1, auto_graph=True)
         out = self._stream.feed(noisy_input)
         self.frames = self._stream.frames
         self.pending = self._stream.pending_view()
@@ -186,7 +187,7 @@ class CleanUMamba(nn.Module):
 
     def flush(self):
         if self._stream is None:
-            self._stream = self.stream_session(batch=1)
+            self._stream = self.stream_session(batch=1, auto_graph=True)
         out = self._stream.flush()
         self.frames = self._stream.frames
         self.pending = self._stream.pending_view()

@@ -29,8 +29,10 @@ from ._lib import EPI_GLU, EPI_RELU, ptr
 
 class StreamSession:
     BATCH_MODE_ROWS = 128     # rows per stream from which a level runs one GEMM batch item per stream (in-place operands)
+    AUTO_GRAPH_AFTER = 3      # auto_graph sessions: identical chunks seen before the step is captured as a CUDA graph
 
-    def __init__(self, model, batch: int = 1):
+    def __init__(self, model, batch: int = 1, auto_graph: bool = False):
+        self.auto_graph, self._same, self._last_n = auto_graph, 0, -1
         self.model = model
         self.eng = model.engine()
         self.eng.ensure_packed()
@@ -78,6 +80,19 @@ class StreamSession:
             if chunk.shape[1] == self._graph["chunk"]:
                 return self._replay(chunk)
             self.release_graph()             # a different chunk size: back to the eager path (state stays valid)
+        if self.auto_graph:
+            # the module-level feed() (one stream, the reference's real-time loop): after AUTO_GRAPH_AFTER identical whole-hop
+            # chunks in steady state the step is captured and replayed from then on (bit-identical, ~2.5x lower latency)
+            n = chunk.shape[1]
+            self._same = self._same + 1 if n == self._last_n else 1
+            self._last_n = n
+            if (self._same > self.AUTO_GRAPH_AFTER and n > 0 and n % self.hop == 0 and self.frames_since_reset > 0
+                    and self.pending.shape[1] == self.frame_length - self.hop):
+                try:
+                    self.capture_graph(n)
+                    return self._replay(chunk)
+                except RuntimeError:
+                    self.auto_graph = False  # not capturable in this state: stay eager
         return self._feed_eager(chunk)
 
     def _feed_eager(self, chunk: torch.Tensor) -> torch.Tensor:

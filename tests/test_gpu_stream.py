@@ -169,6 +169,28 @@ def test_module_feed_flush_api():
         net.feed(torch.zeros(2, 3, device="cuda"))
 
 
+def test_module_feed_hop_by_hop_auto_graph():
+    """The reference's real-time loop (examples/streaming_demo.py:118-172): net.feed() one hop at a time.  After a few identical
+    hops the step is replayed from a CUDA graph; the stream must equal offline forward and a plain eager session bit for bit."""
+    fx = load_golden("e6_pruned_200k")
+    net = build(fx, normalize_input=True, math_mode="f16x3")
+    hop = net.total_stride
+    x = (fx["noisy"][:1, 0, : net.frame_length - hop + 40 * hop] * 1.0).cuda()
+    first = net.frame_length - hop
+    outs = [net.feed(x[:, :first])]
+    for i in range(40):
+        outs.append(net.feed(x[:, first + i * hop: first + (i + 1) * hop]))
+        if i == 12:
+            assert net._stream._graph is not None           # captured by now
+    got = torch.cat(outs, 1)
+    ref_sess = net.stream_session(batch=1)                  # eager, no auto graph
+    want = torch.cat([ref_sess.feed(x[:, :first])] + [ref_sess.feed(x[:, first + i * hop: first + (i + 1) * hop]) for i in range(40)], 1)
+    assert got.shape == want.shape == (1, 40 * hop)
+    assert torch.equal(got, want)
+    tail = net.flush()                                       # releases the graph, clears the conv caches
+    assert net._stream._graph is None and tail.shape[1] == first
+
+
 def test_stream_edge_cases_empty_and_tiny_feeds():
     """feed() with fewer samples than a frame returns (B, 0); one sample at a time still converges to the same output."""
     fx = load_golden("tiny_equalwidth_seed0")
