@@ -61,6 +61,7 @@ class Engine:
         self._key = None
         self.pk: Dict[str, torch.Tensor] = {}
         self.meta: dict = {}
+        self._graphs: dict = {}    # (input shape, parameter versions) -> captured CUDA graph of the forward (small problems)
         self.launches = 0          # kernels launched through the C ABI (bench.py's gpu_launches)
         self.prof = None           # list of (kind, start_event, stop_event, flops, bytes) when profiling is on
 
@@ -94,6 +95,7 @@ class Engine:
     def ensure_packed(self):
         key = self._params_key()
         if key != self._key:
+            self._graphs.clear()       # captured graphs reference the previous packed weights
             self._pack()
             self._key = key
 
@@ -365,8 +367,46 @@ class Engine:
         return hn
 
     # ------------------------------------------------------------------------------------------------ forward
+    # Small problems (the pruned 200K-2M checkpoints at batch 1-8: ~285 launches in ~1.4 ms): after GRAPH_AFTER eager calls with
+    # the same input shape and the same parameter versions the whole forward is captured once as a CUDA graph and replayed
+    # (static input / activation buffers; bit-identical).  Measured gain is modest (E8-500K, 1 x 10 s: 1.42 -> 1.32 ms): the
+    # time is the start-up cost of 285 persistent kernels, not host launch latency -- the real fix for these tiny irregular
+    # layers is a fused multi-layer kernel.  Larger problems are GPU-bound and stay eager.
+    GRAPH_MAX_SAMPLES = int(os.environ.get("CUM_GRAPH_MAX_SAMPLES", 8 * 160000))     # batch x samples up to which graphs are used
+    GRAPH_AFTER = 2
+    GRAPH_CACHE = 4
+
     @torch.no_grad()
     def forward(self, noisy: torch.Tensor, return_skip_connections: bool = False):
+        self.ensure_packed()
+        if (return_skip_connections or self.prof is not None or noisy.dim() != 3 or noisy.numel() > self.GRAPH_MAX_SAMPLES
+                or noisy.device != self.device or torch.cuda.is_current_stream_capturing()):
+            return self._forward_eager(noisy, return_skip_connections)
+        key = (tuple(noisy.shape), self._key, self.model.normalize_input, self.model.glu_activation)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.GRAPH_CACHE:
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = self._graphs[key] = dict(seen=0, graph=None)
+        if ent["graph"] is None:
+            ent["seen"] += 1
+            if ent["seen"] <= self.GRAPH_AFTER:
+                return self._forward_eager(noisy, False)
+            x_static = torch.empty(noisy.shape, dtype=torch.float32, device=self.device)
+            x_static.copy_(noisy)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward_eager(x_static, False)
+            ent.update(graph=g, x=x_static, out=out)
+        ent["x"].copy_(noisy)
+        ent["graph"].replay()
+        if self.model.normalize_input:
+            noisy.copy_(ent["x"])            # the reference divides the caller's tensor in place (:262)
+        return ent["out"].clone()
+
+    @torch.no_grad()
+    def _forward_eager(self, noisy: torch.Tensor, return_skip_connections: bool = False):
         m = self.model
         self.ensure_packed()
         pk, meta, lib = self.pk, self.meta, self.lib

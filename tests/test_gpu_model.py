@@ -228,3 +228,41 @@ def test_bf16_storage_variant_reported_separately(name):
     assert rel < 2e-2 and d < 0.2
     with pytest.raises(NotImplementedError):
         net.stream_session(batch=1)
+
+
+def test_small_problem_forward_cuda_graph_equals_eager():
+    """Small problems replay the whole forward from a CUDA graph after two eager calls of the same shape (launch-latency
+    bound: 285 launches).  Bit-identical to the eager path for fresh inputs, across a shape change, and after a weight update
+    (which must invalidate the captured graph); the in-place input normalisation of the reference is preserved."""
+    import json as _json
+    from cleanumamba_b200.network import Net
+    fx = load_golden("e8_pruned_500k")
+    net = Net("CleanUMamba", {**_json.loads(fx["config"]), "math_mode": "f16x3"})
+    net.load_pruned_state_dict(fx["state_dict"])
+    net = net.cuda().float().eval()
+    eng = net.engine()
+    g = torch.Generator().manual_seed(2)
+    xs = [(torch.randn(2, 1, 9000, generator=g) * 0.1).cuda() for _ in range(5)]
+    with torch.no_grad():
+        want, want_in = [], []
+        for x in xs:
+            xi = x.clone()
+            want.append(eng._forward_eager(xi))
+            want_in.append(xi)
+        got = []
+        for i, x in enumerate(xs):
+            xi = x.clone()
+            got.append(net(xi))
+            assert torch.equal(xi, want_in[i])                      # normalised in place, like the reference
+        assert any(e["graph"] is not None for e in eng._graphs.values())
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+        y_other = net(torch.zeros(1, 1, 5000, device="cuda") + 0.01)    # another shape: eager again
+        assert y_other.shape == (1, 1, 5000)
+        first = next(net.parameters())
+        first.mul_(1.5)                                             # parameter version changes -> repack, graphs dropped
+        xi = xs[0].clone()
+        y_new = net(xi)
+        assert not eng._graphs or all(e["graph"] is None for e in eng._graphs.values())
+        assert not torch.equal(y_new, want[0])
+        assert torch.equal(y_new, eng._forward_eager(xs[0].clone()))
