@@ -12,7 +12,7 @@ import threading
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcleanumamba_sm100.so")
+LIB_PATH = os.environ.get("CUM_LIB_PATH") or os.path.join(_PKG, "libcleanumamba_sm100.so")    # override: A/B of two builds
 
 # enums (mirror include/cleanumamba_b200.h)
 EPI_NONE, EPI_RELU, EPI_SILU = 0, 1, 2

@@ -552,7 +552,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int rh = 0; rh < 2; ++rh) rok[h][rh] = FULL || row0 + h * 16 + rh * 8 < p.m;
-                const int col = GLU ? ((n0 + c00) >> 1) + (OUTS ? (tq & ~1) + 4 * (tq & 1) : tq) : n0 + c00 + 2 * tq;
+                // fp32 outputs (PAIR): neighbouring lanes swap one value (pair) so that each lane stores 8 (GLU) / 16 bytes of ONE k
+                // group -- a row's segment of the chunk leaves in one store instruction instead of two: half the LSU wavefronts,
+                // which bound the 64- / 128-channel layers.  Even lanes own the columns of k = 0, odd lanes those of k = 1
+                constexpr bool PAIR = (OUTF == 0) && EPI != TC_EPI_ATOMIC_ADD;
+                const int col = GLU ? ((n0 + c00) >> 1) + ((OUTS || PAIR) ? (tq & ~1) + 4 * (tq & 1) : tq)
+                                    : n0 + c00 + (PAIR ? ((tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq) : 2 * tq);
                 const int acol = GLU ? ((n0 + c00) >> 1) + tq : n0 + c00 + 2 * tq;
                 char* cp0 = reinterpret_cast<char*>(p.c) + (cbo + (long long)row0 * p.c_rs + col) * CES;
                 unsigned ao0 = ((unsigned)row0 * (unsigned)p.add_rs + (unsigned)acol) * (unsigned)aes;
@@ -633,6 +638,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     const uint32_t lo2 = cvt_f16x2_sat(p0 - hf.x, p1 - hf.y);
                                     *reinterpret_cast<uint32_t*>(cp(h, rh)) = hi2;
                                     *reinterpret_cast<uint32_t*>(cp(h, rh) + lo_delta) = lo2;
+                                }
+                                continue;
+                            }
+                            if constexpr (PAIR) {
+                                const bool odd = tq & 1;
+                                const bool ok = rok[h][rh] && (FULL || n0 + c0 + 8 * (int)odd < p.n);
+                                if constexpr (GLU) {
+                                    float o[2];
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k) {
+                                        const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
+                                        const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
+                                        o[k] = x0 * tc_gate<EPI>(p.epi, x1);
+                                        if (has_add) o[k] += ad[h][rh][k].x;
+                                    }
+                                    const float got = __shfl_xor_sync(0xffffffffu, odd ? o[0] : o[1], 1);
+                                    if (ok) *reinterpret_cast<float2*>(cp(h, rh)) = odd ? make_float2(got, o[1]) : make_float2(o[0], got);
+                                } else {
+                                    float2 o[2];
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k) {
+                                        const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
+                                        const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
+                                        o[k] = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
+                                        if (has_add) { o[k].x += ad[h][rh][k].x; o[k].y += ad[h][rh][k].y; }
+                                    }
+                                    const float2 snd = odd ? o[0] : o[1];
+                                    const float gx = __shfl_xor_sync(0xffffffffu, snd.x, 1), gy = __shfl_xor_sync(0xffffffffu, snd.y, 1);
+                                    if (ok) *reinterpret_cast<float4*>(cp(h, rh)) = odd ? make_float4(gx, gy, o[1].x, o[1].y) : make_float4(o[0].x, o[0].y, gx, gy);
                                 }
                                 continue;
                             }
@@ -1115,6 +1149,9 @@ int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
 
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.a_row_stride >= d.k || d.a_rows == 1, "gemm_tc: a_row_stride < k");
+    CUM_REQUIRE(d.out_bf16 || d.c_lo || (aligned16(d.c) && d.c_row_stride % 4 == 0 && (d.batch == 1 || d.c_batch_stride % 4 == 0)),
+                "gemm_tc: an fp32 output must be 16-byte aligned with row / batch strides that are multiples of 4 elements (c_row_stride=%lld)",
+                (long long)d.c_row_stride);
     CUM_REQUIRE((long long)d.m * d.c_row_stride < (1ll << 31) && (!d.addend || (long long)d.m * d.add_row_stride < (1ll << 29)),
                 "gemm_tc: one batch plane of the output / addend must span fewer than 2^31 elements (m=%d, c_row_stride=%lld)",
                 d.m, (long long)d.c_row_stride);
