@@ -555,7 +555,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // fp32 outputs (PAIR): neighbouring lanes swap one value (pair) so that each lane stores 8 (GLU) / 16 bytes of ONE k
                 // group -- a row's segment of the chunk leaves in one store instruction instead of two: half the LSU wavefronts,
                 // which bound the 64- / 128-channel layers.  Even lanes own the columns of k = 0, odd lanes those of k = 1
-                constexpr bool PAIR = (OUTF == 0) && EPI != TC_EPI_ATOMIC_ADD;
+                constexpr bool PAIR = ((OUTF == 0) || (OUTS && !GLU)) && EPI != TC_EPI_ATOMIC_ADD;
                 const int col = GLU ? ((n0 + c00) >> 1) + ((OUTS || PAIR) ? (tq & ~1) + 4 * (tq & 1) : tq)
                                     : n0 + c00 + (PAIR ? ((tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq) : 2 * tq);
                 const int acol = GLU ? ((n0 + c00) >> 1) + tq : n0 + c00 + 2 * tq;
@@ -666,7 +666,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     }
                                     const float2 snd = odd ? o[0] : o[1];
                                     const float gx = __shfl_xor_sync(0xffffffffu, snd.x, 1), gy = __shfl_xor_sync(0xffffffffu, snd.y, 1);
-                                    if (ok) *reinterpret_cast<float4*>(cp(h, rh)) = odd ? make_float4(gx, gy, o[1].x, o[1].y) : make_float4(o[0].x, o[0].y, gx, gy);
+                                    const float4 w = odd ? make_float4(gx, gy, o[1].x, o[1].y) : make_float4(o[0].x, o[0].y, gx, gy);
+                                    if constexpr (OUTS) {       // hl16 planes: 4 consecutive columns = 8 bytes per plane
+                                        const uint32_t h0 = cvt_f16x2_sat(w.x, w.y), h1 = cvt_f16x2_sat(w.z, w.w);
+                                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+                                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+                                        const uint32_t l0 = cvt_f16x2_sat(w.x - f0.x, w.y - f0.y), l1 = cvt_f16x2_sat(w.z - f1.x, w.w - f1.y);
+                                        if (ok) {
+                                            *reinterpret_cast<uint2*>(cp(h, rh)) = make_uint2(h0, h1);
+                                            *reinterpret_cast<uint2*>(cp(h, rh) + lo_delta) = make_uint2(l0, l1);
+                                        }
+                                    } else {
+                                        if (ok) *reinterpret_cast<float4*>(cp(h, rh)) = w;
+                                    }
                                 }
                                 continue;
                             }
@@ -1152,6 +1164,8 @@ int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.out_bf16 || d.c_lo || (aligned16(d.c) && d.c_row_stride % 4 == 0 && (d.batch == 1 || d.c_batch_stride % 4 == 0)),
                 "gemm_tc: an fp32 output must be 16-byte aligned with row / batch strides that are multiples of 4 elements (c_row_stride=%lld)",
                 (long long)d.c_row_stride);
+    CUM_REQUIRE(!d.c_lo || (aligned16(d.c) && aligned16(d.c_lo) && d.c_row_stride % 4 == 0 && (d.batch == 1 || d.c_batch_stride % 4 == 0)),
+                "gemm_tc: hi/lo output planes must be 16-byte aligned with strides that are multiples of 4 elements");
     CUM_REQUIRE((long long)d.m * d.c_row_stride < (1ll << 31) && (!d.addend || (long long)d.m * d.add_row_stride < (1ll << 29)),
                 "gemm_tc: one batch plane of the output / addend must span fewer than 2^31 elements (m=%d, c_row_stride=%lld)",
                 d.m, (long long)d.c_row_stride);
