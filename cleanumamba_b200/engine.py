@@ -55,6 +55,8 @@ def _interleave_glu(w: torch.Tensor, b: torch.Tensor, k_pad: int):
 class Engine:
     skip_zero_lo = True      # skip the a_hi*w_lo pass for weights whose low half is exactly zero (tests may turn it off)
     hl16 = os.environ.get("CUM_HL16", "1") != "0"    # f16x3: store the conv-stack activations as fp16 hi/lo planes (A/B switch)
+    HL16_MIN_CONSUMER_K = int(os.environ.get("CUM_HL16_CK", 512))     # thresholds of the per-tensor hl16 rule (see forward())
+    HL16_MIN_PRODUCER_K = int(os.environ.get("CUM_HL16_PK", 256))
 
     def __init__(self, model):
         self.model = model
@@ -439,7 +441,7 @@ class Engine:
         def fmt(consumer_k, producer_k):
             """Per tensor: hl16 pays when the consuming GEMM is compute-bound (it loses its splitter: -6..13 % at K >= 512) and
             the producing GEMM is not epilogue-bound (the split store costs it +3..5 % at K >= 256, +25 % on the 128-wide layers)"""
-            return torch.float16 if (hl16 and consumer_k >= 512 and producer_k >= 256) else adt
+            return torch.float16 if (hl16 and consumer_k >= self.HL16_MIN_CONSUMER_K and producer_k >= self.HL16_MIN_PRODUCER_K) else adt
         skips: List[torch.Tensor] = []
         prev = None
         for i, e in enumerate(meta["enc"]):
