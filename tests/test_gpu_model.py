@@ -266,3 +266,25 @@ def test_small_problem_forward_cuda_graph_equals_eager():
         assert not eng._graphs or all(e["graph"] is None for e in eng._graphs.values())
         assert not torch.equal(y_new, want[0])
         assert torch.equal(y_new, eng._forward_eager(xs[0].clone()))
+
+
+def test_host_pipeline_overlaps_copies_and_matches_direct_calls():
+    """HostPipeline (H2D / forward / D2H of consecutive batches on three streams) returns exactly what direct calls return."""
+    import json as _json
+    from cleanumamba_b200.network import Net
+    from cleanumamba_b200.pipeline import HostPipeline
+    fx = load_golden("e8_pruned_500k")
+    net = Net("CleanUMamba", {**_json.loads(fx["config"]), "math_mode": "f16x3"})
+    net.load_pruned_state_dict(fx["state_dict"])
+    net = net.cuda().float().eval()
+    g = torch.Generator().manual_seed(4)
+    ins = [(torch.randn(3, 1, 20000, generator=g) * 0.1).pin_memory() for _ in range(5)]
+    outs = [torch.empty(3, 1, 20000).pin_memory() for _ in range(5)]
+    pipe = HostPipeline(net)
+    for a, b in zip(ins, outs):
+        pipe.submit(a, b)
+    pipe.drain()
+    with torch.no_grad():
+        for a, b in zip(ins, outs):
+            want = net(a.cuda()).cpu()
+            assert torch.equal(b, want)
