@@ -99,3 +99,33 @@ def test_shape_helpers_and_api_surface():
         CleanUMamba(LSTM=True)
     with pytest.raises(ValueError):
         m.feed(torch.zeros(2, 3, 4))
+
+
+def test_struct_sizes_and_offsets_match_a_c_compiler(tmp_path):
+    """Compile the public header with plain gcc (it must be a C header: no CUDA / C++ needed) and compare sizeof / offsetof of
+    every descriptor with the ctypes mirror in cleanumamba_b200/_lib.py."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    from cleanumamba_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {"cum_gemm_desc": _lib.GemmDesc, "cum_scan_desc": _lib.ScanDesc, "cum_wgrad_desc": _lib.WgradDesc,
+             "cum_scan_bwd_desc": _lib.ScanBwdDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cleanumamba_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
