@@ -1,23 +1,27 @@
-// tcgen05 / TMEM / TMA tap-GEMM for sm_100a (CUM_MATH_TF32X3 and CUM_MATH_TF32).
+// tcgen05 / TMEM / TMA tap-GEMM for sm_100a (every CUM_MATH_* mode except the exact-fp32 SIMT kernel).
 //
 //   out[b, m, :] = EPI( bias + sum_{s<taps} W_s . a[b, m + shift_s, 0:k] ) (+ addend[b, m, :])
 //
-// One persistent CTA per SM, 128 x 256 (or 128 x 128) output tile (UMMA M=128, N runtime, K=8 for kind::tf32), accumulators in
-// TMEM (2 x 256 columns, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1), operands
-// staged by TMA into 128B-swizzled K-major shared-memory tiles.  The conv taps are extra K-blocks whose A-tile is the
-// same tensor map fetched at a shifted row coordinate; rows outside [0, a_rows) are zero-filled by TMA, which is
-// exactly the conv / transposed-conv boundary condition.
+// One persistent CTA per SM.  Tiles wider than 128 columns run on CTA PAIRS (cluster of 2 = the two SMs of a TPC,
+// tcgen05.mma.cta_group::2): a 256 x 256 tile, each CTA stages its own 128 rows of A and HALF of the W tile, the leader issues
+// the MMAs for both CTAs and multicasts the completion barriers.  Accumulators live in TMEM (2 x 256 columns, double-buffered
+// so the epilogue of tile i overlaps the main loop of tile i+1); operands are staged by TMA into swizzled K-major
+// shared-memory tiles (224 KB ring, 2-7 stages).  The conv taps are extra K-blocks whose A-tile is the same tensor map fetched
+// at a shifted row coordinate; rows outside [0, a_rows) are zero-filled by TMA, which is exactly the conv / transposed-conv
+// boundary condition.
 //
 // Warp roles (640 threads, 768 with the splitter):
 //   warp 0        TMA producer (one lane)
-//   warp 1        TMEM allocator + MMA issuer (one lane)
-//   warps 4..19   epilogue: tcgen05.ld (16x256b fragments) -> bias / ReLU / GLU / skip-add -> 32-byte-sector stores
-//   warps 20..23  (split modes) operand splitter: A tile -> hi = a & 0xffffe000 (in place), lo = a - hi
+//   warp 1        TMEM allocator + MMA issuer (one lane; in a pair only the leader's -- the peer's lane relays "A is split")
+//   warps 4..19   epilogue: tcgen05.ld (16x256b fragments) -> bias / ReLU / GLU / skip-add -> fp32, bf16 or fp16 hi/lo planes;
+//                 neighbouring lanes exchange one value so that each lane stores 8-16 contiguous bytes of one row
+//   warps 20..23  (modes with fp32 activations) operand splitter: the TMA-landed fp32 A tile is split into hi / lo halves in
+//                 place between TMA arrival and MMA issue
 //
-// TF32X3: fp32 activations cannot be fed to kind::tf32 directly within the 1e-4 waveform tolerance (10-bit mantissa,
-// 22 stacked layers), so every product is expanded a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (three MMAs, error
-// ~3*2^-22 per product).  W is split once at pack time (cum_split_tf32), A is split in shared memory by the
-// splitter warps between TMA arrival and MMA issue.
+// Split products: fp32 activations cannot be fed to one tensor-core pass within the 1e-4 waveform tolerance (10-11 mantissa
+// bits, 22 stacked layers), so every product is expanded a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (three MMAs, ~2^-21 per
+// product).  W is split once at pack time; A either by the splitter warps (F16X3 / BF16X3 / TF32X3) or -- TC_F16PS -- once by
+// the PRODUCING layer's epilogue, which writes fp16 hi / lo planes ("hl16") that the consumer feeds to the MMA straight from TMA.
 #include "common.cuh"
 
 #include <cuda.h>
