@@ -13,7 +13,7 @@ sharding, no data-path collective -> weak scaling).
 Own arm     : the product (cleanumamba_b200 -> libcleanumamba_sm100.so).  `value` = inputs resident in HBM, CUDA-event
               timed, max over ranks; `e2e` = same call with pinned HOST buffers, H2D + forward + D2H inside the timing.
 Reference arm (--impl reference): the reference's CPU path (oracle port of CleanUMamba.forward + selective_scan_ref,
-              oracle/cleanumamba_oracle.py) on all host cores, each step a bounded sample (1 clip) of the same workload.
+              oracle/cleanumamba_oracle.py) on all host cores, each step a bounded sample (2 clips) of the same workload.
 """
 import argparse
 import json
@@ -105,7 +105,20 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_pass(cfg, seconds, steps, warmup, threads):
+N_PARAMS_M = {"e8": 41.38, "e6": 27.21}       # README.md:61,121 of the reference (checked by tests/test_cpu_host.py against the constructor)
+
+
+def workload_name(args):
+    """config.workload of the headline bench -- shared by the product arm and the reference arm (same workload, the CPU arm
+    times a bounded sample of it per step)."""
+    return (f"CleanUMamba {args.model.upper()} full ({N_PARAMS_M[args.model]:.2f}M, seeded random init) offline forward, "
+            f"batch {args.batch} x {args.seconds:g} s @16 kHz per GPU")
+
+
+CPU_SAMPLE_CLIPS = 2      # clips per CPU step (selective_scan_ref materialises 0.67 GB per 10 s clip at E8)
+
+
+def cpu_reference_pass(cfg, seconds, steps, warmup, threads, clips=CPU_SAMPLE_CLIPS):
     """Times the oracle port of the reference's CPU path; returns (audio_s_per_s, ms_per_step, sample description)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cleanumamba_oracle as orc
@@ -113,27 +126,30 @@ def cpu_reference_pass(cfg, seconds, steps, warmup, threads):
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     sd = {k: v.clone() for k, v in Net("CleanUMamba", dict(cfg)).state_dict().items()}
-    x = synth_noisy(1, seconds, 1234)
-    for _ in range(warmup):
-        orc.forward(sd, x)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        orc.forward(sd, x)
-    dt = (time.perf_counter() - t0) / steps
-    return seconds / dt, dt * 1e3, f"1 clip x {seconds:g} s per step, {steps} steps after {warmup} warm-up, fp32, {threads} threads"
+    x = synth_noisy(clips, seconds, 1234)
+    with torch.no_grad():
+        for _ in range(warmup):
+            orc.forward(sd, x.clone())
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.forward(sd, x.clone())
+        dt = (time.perf_counter() - t0) / steps
+    return (clips * seconds / dt, dt * 1e3,
+            f"{clips} clips x {seconds:g} s per step (of the batch), {steps} steps after {warmup} warm-up, fp32, {threads} threads")
 
 
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))      # ~0.7 s per step: the run stays well under a minute
     val, ms, sample = cpu_reference_pass(cfg, args.seconds, steps, warmup, threads)
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"CleanUMamba {args.model.upper()} full offline forward, reference CPU path "
-                                   f"(oracle port of CleanUMamba.forward + selective_scan_ref), {sample}"},
+            "config": {"workload": workload_name(args), "sample": sample,
+                       "path": "reference CPU path: oracle port of CleanUMamba.forward + mamba_ssm selective_scan_ref "
+                               "(oracle/cleanumamba_oracle.py), all host cores"},
             "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -533,7 +549,7 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, _, sample = cpu_reference_pass(cfg, args.seconds, 3, 1, threads)
+        v, _, sample = cpu_reference_pass(cfg, args.seconds, 16, 1, threads)      # ~12 s of CPU work
         cpu = {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
 
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -549,9 +565,7 @@ def main():
                            "bf16": "REDUCED PRECISION variant (reported separately, outside the fp32 tolerance): bf16 activation storage and "
                                    "single-pass bf16 tensor-core products in the encoder / decoder stacks, fp32 accumulate",
                            "tf32": "single TF32 pass (outside the tolerance)"}[args.math],
-            "config": {"workload": f"CleanUMamba {args.model.upper()} full ({sum(p.numel() for p in net.parameters())/1e6:.2f}M, "
-                                   f"seeded random init) offline forward, batch {B} x {args.seconds:g} s @16 kHz per GPU, "
-                                   f"math={args.math}",
+            "config": {"workload": workload_name(args), "math": args.math,
                        "global_batch": world * B, "clip_seconds": args.seconds, "parallelism": f"utterance-sharded x{world}",
                        "l2": "inputs+activations per step (>25 GB) exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": B * T * 4,
