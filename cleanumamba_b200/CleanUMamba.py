@@ -146,8 +146,12 @@ class CleanUMamba(nn.Module):
 
     # ------------------------------------------------------------------ streaming (:326-490)
     def reset_time_per_frame(self):
+        """:326-328.  In the reference ``frames`` is also the denominator of the running input std (:399-401), so after a reset
+        the next frame restarts that running mean; the streaming session follows."""
         self.total_time = 0
         self.frames = 0
+        if self._stream is not None:
+            self._stream.reset_frames()
 
     @property
     def time_per_frame(self):
@@ -163,10 +167,14 @@ class CleanUMamba(nn.Module):
         return {i: self.allocate_inference_cache_layer(blk.mixer, batch_size, dtype=dtype)
                 for i, blk in enumerate(self.tsfm_Mamba_layers)}
 
-    def stream_session(self, batch=1, compat_skip_order_bug=False, auto_graph=False):
+    def stream_session(self, batch=1, auto_graph=False):
         """New carried-state streaming session for ``batch`` independent streams (extension: the reference's
         ``feed`` is batch 1 and keeps its state on the module).  ``auto_graph``: capture the steady-state step as a CUDA
-        graph once the same whole-hop chunk size has been fed a few times (see StreamSession.capture_graph)."""
+        graph once the same whole-hop chunk size has been fed a few times (see StreamSession.capture_graph).
+        The shipped skip-index slip (:474: ``skip_connections[i]`` without the reversal of :275) is NOT available as a mode:
+        it raises a channel-mismatch error on every shipped checkpoint and, where all widths happen to be equal, adds the
+        wrong level's skip; only the test oracle reproduces it (oracle ``compat_skip_order_bug``) to pin itself to the
+        reference's own ``feed`` output."""
         from .streaming import StreamSession
         return StreamSession(self, batch=batch, auto_graph=auto_graph)
 

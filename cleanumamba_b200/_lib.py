@@ -33,6 +33,20 @@ class GemmDesc(C.Structure):
                 ("a_lo", C.c_void_p), ("c_lo", C.c_void_p), ("addend_lo", C.c_void_p), ("cta_pair", C.c_int)]
 
 
+class Enc0BlockDesc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_stride", C.c_longlong), ("batch", C.c_int), ("length", C.c_int),
+                ("conv_w", C.c_void_p), ("conv_b", C.c_void_p), ("glu_w_hi", C.c_void_p), ("glu_w_lo", C.c_void_p),
+                ("glu_b", C.c_void_p), ("acc_scale", C.c_float), ("w_lo_is_zero", C.c_int),
+                ("out", C.c_void_p), ("rows_out", C.c_int), ("channels", C.c_int)]
+
+
+class DecLastBlockDesc(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("batch", C.c_int), ("rows_in", C.c_int),
+                ("glu_w_hi", C.c_void_p), ("glu_w_lo", C.c_void_p), ("glu_b", C.c_void_p), ("acc_scale", C.c_float),
+                ("w_lo_is_zero", C.c_int), ("convt_w", C.c_void_p), ("convt_bias", C.c_float), ("scale", C.c_void_p),
+                ("out", C.c_void_p), ("out_stride", C.c_longlong), ("out_length", C.c_int), ("channels", C.c_int)]
+
+
 class ScanDesc(C.Structure):
     _fields_ = [("u", C.c_void_p), ("u_bs", C.c_longlong), ("u_rs", C.c_longlong),
                 ("delta", C.c_void_p), ("dl_bs", C.c_longlong), ("dl_rs", C.c_longlong),
@@ -67,6 +81,7 @@ class ScanBwdDesc(C.Structure):
 EXPORTS = {
     "cum_abi_version": (C.c_int, []),
     "cum_init": (C.c_int, [C.c_int]),
+    "cum_shutdown": (C.c_int, []),
     "cum_last_error": (C.c_char_p, []),
     "cum_wave_normalize_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cum_conv_in_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -84,6 +99,8 @@ EXPORTS = {
     "cum_convt_out_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cum_gemm_bias_act_fwd": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "cum_enc0_block_fwd": (C.c_int, [C.POINTER(Enc0BlockDesc), C.c_void_p]),
+    "cum_dec_last_block_fwd": (C.c_int, [C.POINTER(DecLastBlockDesc), C.c_void_p]),
     "cum_split_tf32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "cum_split_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "cum_split_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),

@@ -30,7 +30,13 @@ class _CleanUMambaFn(torch.autograd.Function):
                     ctx.eng.gflat.mul_(scale)
             grads = ctx.eng.unpack_grads()
         ctx.saved = None
-        outs = [grads[n].to(dt) if need else None for n, need, dt in zip(ctx.names, ctx.needs, ctx.dtypes)]
+        lo = ctx.eng.gflat.data_ptr()
+        hi = lo + ctx.eng.gflat.numel() * 4
+
+        def own(g, dt):       # a gradient handed to autograd must never alias the persistent buffer (it may become param.grad)
+            g = g.to(dt)
+            return g.clone() if lo <= g.data_ptr() < hi else g
+        outs = [own(grads[n], dt) if need else None for n, need, dt in zip(ctx.names, ctx.needs, ctx.dtypes)]
         return (None, None, *outs)
 
 

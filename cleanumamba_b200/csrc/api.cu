@@ -3,10 +3,19 @@
 
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <set>
+#include <utility>
+
 namespace cum {
 
 static thread_local char g_err[512] = "";
-static int g_sm_count = 0;
+// per-device state: one process may drive several GPUs (teacher / student on two devices, DataParallel), from several threads
+constexpr int MAX_DEVICES = 64;
+static std::atomic<int> g_sm_count[MAX_DEVICES];
+static std::mutex g_attr_mu;
+static std::set<std::pair<const void*, int>> g_attr_done;      // (kernel, device) pairs whose dynamic-smem limit is raised
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -18,13 +27,34 @@ int cuda_fail(cudaError_t e, const char* what) {
     set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
     return CUM_ECUDA;
 }
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= MAX_DEVICES) ? 0 : dev;
+}
+// SM count of the CURRENT device of the calling thread
 int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    const int dev = current_device();
+    int v = g_sm_count[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        g_sm_count[dev].store(v, std::memory_order_relaxed);
     }
-    return g_sm_count;
+    return v;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: raise it once per (kernel, device)
+int ensure_dyn_smem(const void* kernel, int bytes, const char* what) {
+    const std::pair<const void*, int> key(kernel, current_device());
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    if (g_attr_done.count(key)) return CUM_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    g_attr_done.insert(key);
+    return CUM_OK;
+}
+void forget_func_attrs() {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    g_attr_done.clear();
 }
 
 static int validate_gemm(const cum_gemm_desc& d) {
@@ -54,17 +84,28 @@ int cum_abi_version(void) { return CUM_ABI_VERSION; }
 
 const char* cum_last_error(void) { return g_err; }
 
+// Checks that `device` can run this library.  Does NOT change the caller's current device: every entry point works on the
+// device that is current in the calling thread (the Python host wraps its calls in a device guard).
 int cum_init(int device) {
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
-    if (prop.major != 10) {
-        set_error("cum_init: device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", device, prop.major, prop.minor);
+    CUM_REQUIRE(device >= 0 && device < MAX_DEVICES, "cum_init: device %d out of range", device);
+    int major = 0, minor = 0, sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (major != 10) {
+        set_error("cum_init: device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", device, major, minor);
         return CUM_ENOTSUP;
     }
-    g_sm_count = prop.multiProcessorCount;
+    g_sm_count[device].store(sms, std::memory_order_relaxed);
+    return CUM_OK;
+}
+
+// Drops every process-wide cache of the library (tensor-map cache, per-device kernel attributes).  Stream-ordered work already
+// submitted is not affected; the library can be used again afterwards (caches refill lazily).
+int cum_shutdown(void) {
+    tensor_map_cache_clear();
+    forget_func_attrs();
     return CUM_OK;
 }
 
@@ -130,6 +171,16 @@ int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream) {
         case CUM_MATH_TF32: return gemm_tc_fwd(*desc, (cudaStream_t)stream);
         default: set_error("gemm: unknown math mode %d", desc->math); return CUM_EINVAL;
     }
+}
+
+int cum_enc0_block_fwd(const cum_enc0_block_desc* desc, cum_stream_t stream) {
+    if (!desc) { set_error("enc0_block: null descriptor"); return CUM_EINVAL; }
+    return enc0_block_fwd(*desc, (cudaStream_t)stream);
+}
+
+int cum_dec_last_block_fwd(const cum_dec_last_block_desc* desc, cum_stream_t stream) {
+    if (!desc) { set_error("dec_last_block: null descriptor"); return CUM_EINVAL; }
+    return dec_last_block_fwd(*desc, (cudaStream_t)stream);
 }
 
 int cum_split_tf32(const float* w, float* hi, float* lo, long long count, cum_stream_t stream) {

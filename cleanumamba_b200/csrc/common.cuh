@@ -78,6 +78,8 @@ int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float
                   int kernel, int stride, cudaStream_t st, bool in_bf16 = false);
 int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st);
+int enc0_block_fwd(const cum_enc0_block_desc& d, cudaStream_t st);
+int dec_last_block_fwd(const cum_dec_last_block_desc& d, cudaStream_t st);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t st);
 int split_bf16(const float* w, void* hi, void* lo, long long n, cudaStream_t st);
 int split_f16(const float* w, void* hi, void* lo, long long n, float scale, cudaStream_t st);
@@ -110,6 +112,9 @@ int selective_scan_bwd(const cum_scan_bwd_desc& d, cudaStream_t st);
 constexpr int CI_MAXK = 8;   // conv_in / conv_in_bwd
 constexpr int CT_MAXK = 8;   // convt_out / convt_out_bwd
 
-int  sm_count();
+int  sm_count();                                                          // of the calling thread's current device
+int  ensure_dyn_smem(const void* kernel, int bytes, const char* what);    // per (kernel, device), thread-safe
+void forget_func_attrs();
+void tensor_map_cache_clear();                                             // gemm_tc.cu
 
 }  // namespace cum

@@ -1,0 +1,387 @@
+// The two waveform-end blocks of the U-Net, each as ONE persistent tcgen05 kernel (f16x3 arithmetic, 64-channel geometry):
+//
+//   enc0_block      waveform -> [F.pad + Conv1d(1,64,4,2) + ReLU] -> [Conv1d(64,128,1) + GLU] -> skip0 (B, L1, 64)
+//                   (/root/reference/src/network/CleanUMamba.py:108-113, :263-269)
+//   dec_last_block  x (B, T, 64) -> [Conv1d(64,128,1) + GLU] -> [ConvTranspose1d(64,1,4,2)] -> crop to L, * std -> waveform
+//                   (:121-128, :313-319)
+//
+// Unfused, each block wrote its 64-channel intermediate (1.3 GB per 64 x 10 s batch) to HBM and read it back; both blocks are
+// HBM-bound (the 1x1 GEMM is 16 kFLOP per 256-byte row), so the round trip doubled their time.  Here the intermediate never
+// leaves the SM:
+//   * enc0: four "A generator" warps compute the Cin = 1 strided conv + ReLU on the CUDA cores straight from the waveform,
+//     split each value into fp16 hi / lo halves and write the two K-major 128-byte-swizzled MMA operand tiles; one thread
+//     issues the 12 tcgen05 MMAs of the 128 x 128 x 64 tile (a_hi w_hi + a_lo w_hi + a_hi w_lo) into TMEM; eight epilogue
+//     warps apply bias + GLU and stage the 128 x 64 fp32 tile in swizzled shared memory for a TMA store.
+//   * dec_last: the A generators load the fp32 input rows (coalesced 512-byte requests) and split them; the epilogue
+//     warps contract the 64 gated channels with the four transposed-conv taps in registers (thread = row), exchange the
+//     partial sums through shared memory, overlap-add neighbouring rows and write the cropped, re-scaled waveform.
+// A tile, TMEM accumulator and staging tile are double-buffered: generator, MMA and epilogue of consecutive tiles overlap.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <string.h>
+
+namespace cum {
+
+constexpr int FE_ROWS = 128;                    // rows per tile (MMA M)
+constexpr int FE_K = 64;                        // channels in (MMA K: one 128-byte swizzle row of fp16)
+constexpr int FE_N = 128;                       // GLU GEMM columns (interleaved a_c, b_c)
+constexpr int FE_THREADS = 512;                 // warp 0: MMA + TMEM; warp 1: weight TMA; warps 4-11: epilogue; warps 12-15: A generators
+constexpr uint32_t FE_W_BYTES = FE_N * FE_K * 2;          // 16 KB per weight half
+constexpr uint32_t FE_A_BYTES = FE_ROWS * FE_K * 2;       // 16 KB per activation half
+constexpr uint32_t FE_OUT_BYTES = FE_ROWS * 64 * 4;       // 32 KB fp32 staging tile (two 128-byte-swizzled halves of 32 channels)
+constexpr uint32_t FE_OFF_W = 0;
+constexpr uint32_t FE_OFF_A = 2 * FE_W_BYTES;                          // [buf][hi | lo]
+constexpr uint32_t FE_OFF_OUT = FE_OFF_A + 2 * 2 * FE_A_BYTES;         // [buf]
+constexpr uint32_t FE_OFF_SMALL = FE_OFF_OUT + 2 * FE_OUT_BYTES;       // bias (128 f) | taps (64 x float4) | b0 (64 f) | part (2 x 2 x 128 float4)
+constexpr uint32_t FE_SMALL_BYTES = 512 + 1024 + 256 + 2 * 2 * 128 * 16;
+constexpr uint32_t FE_OFF_BAR = FE_OFF_SMALL + FE_SMALL_BYTES;
+constexpr uint32_t FE_SMEM_BYTES = FE_OFF_BAR + 128 + 1024 /*align slack*/;
+constexpr uint32_t FE_TMEM_COLS = 256;          // 2 x 128 accumulator columns
+
+struct FusedEndParams {
+    // enc0: waveform in; dec_last: waveform out
+    const float* x; long long x_stride; int length;
+    int rows;                   // rows per clip: enc0 output rows L1; dec_last input rows T
+    int batch, tiles_per_clip, total_tiles;
+    const float* taps;          // (4, 64) taps-major: enc0 conv weights / dec_last transposed-conv weights
+    const float* b0;            // enc0: (64) conv bias
+    const float* bias;          // (128) interleaved GLU bias
+    float acc_scale;            // 2^-k undoing the fp16 weight pre-scale
+    int skip_wlo;               // low weight half is exactly zero: two MMA passes
+    const float* a;             // dec_last: (B, rows, 64) fp32 input
+    float out_bias; const float* scale; float* out; long long out_stride; int out_length;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// fp32 x8 -> fp16 hi (saturating) and lo halves, packed for one 16-byte chunk of a K-major operand row
+__device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        h[e] = cvt_f16x2_sat(f[2 * e], f[2 * e + 1]);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
+        l[e] = cvt_f16x2_sat(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// KIND 0 = enc0_block, 1 = dec_last_block
+template <int KIND>
+__global__ void __launch_bounds__(FE_THREADS, 1)
+fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                 const __grid_constant__ CUtensorMap tmOut, const FusedEndParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    float* bias_s = reinterpret_cast<float*>(smem_gen + FE_OFF_SMALL);
+    float4* taps_s = reinterpret_cast<float4*>(smem_gen + FE_OFF_SMALL + 512);
+    float* b0_s = reinterpret_cast<float*>(smem_gen + FE_OFF_SMALL + 512 + 1024);
+    float4* part_s = reinterpret_cast<float4*>(smem_gen + FE_OFF_SMALL + 512 + 1024 + 256);      // [buf][grp][row]
+    const uint32_t bar_base = smem_base + FE_OFF_BAR;
+    auto a_full = [&](int b) { return bar_base + 8u * b; };
+    auto a_empty = [&](int b) { return bar_base + 8u * (2 + b); };
+    auto acc_full = [&](int b) { return bar_base + 8u * (4 + b); };
+    auto acc_empty = [&](int b) { return bar_base + 8u * (6 + b); };
+    const uint32_t w_full = bar_base + 64;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + FE_OFF_BAR + 80);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(a_full(b), 128);
+            mbar_init(a_empty(b), 1);
+            mbar_init(acc_full(b), 1);
+            mbar_init(acc_empty(b), 8);
+        }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(FE_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // small operands: GLU bias, the four taps per channel as one float4, conv bias
+    for (int i = threadIdx.x; i < FE_N; i += FE_THREADS) bias_s[i] = __ldg(p.bias + i);
+    for (int i = threadIdx.x; i < 64; i += FE_THREADS) {
+        taps_s[i] = make_float4(__ldg(p.taps + i), __ldg(p.taps + 64 + i), __ldg(p.taps + 128 + i), __ldg(p.taps + 192 + i));
+        b0_s[i] = (KIND == 0) ? __ldg(p.b0 + i) : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (clip, first row).  dec_last tiles overlap by one row: row 0 of a tile only provides g[p-1] for row 1
+    constexpr int STEP = (KIND == 0) ? FE_ROWS : FE_ROWS - 1;
+    auto tile_coords = [&](int tile, int& b, int& m0) {
+        b = tile / p.tiles_per_clip;
+        m0 = (tile - b * p.tiles_per_clip) * STEP - (KIND == 0 ? 0 : 1);
+    };
+
+    if (warp == 1 && lane == 0) {
+        // ===================================================================== weights: once per CTA
+        tma_prefetch_desc(&tmWh);
+        mbar_arrive_expect_tx(w_full, p.skip_wlo ? FE_W_BYTES : 2 * FE_W_BYTES);
+        tma_load_3d(smem_base + FE_OFF_W, &tmWh, w_full, 0, 0, 0);
+        if (!p.skip_wlo) tma_load_3d(smem_base + FE_OFF_W + FE_W_BYTES, &tmWl, w_full, 0, 0, 0);
+    } else if (warp == 0 && lane == 0) {
+        // ===================================================================== MMA issuer
+        mbar_wait(w_full, 0);
+        // c = f32 (1 << 4); a / b = f16 (0); K-major both; N >> 3 at bit 17, M >> 4 at bit 24
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(FE_N >> 3) << 17) | ((uint32_t)(FE_ROWS >> 4) << 24);
+        const uint64_t whi = umma_desc_sw128(smem_base + FE_OFF_W), wlo = umma_desc_sw128(smem_base + FE_OFF_W + FE_W_BYTES);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait(acc_empty(buf), ph ^ 1u);
+            mbar_wait(a_full(buf), ph);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)buf * FE_N;
+            const uint64_t ahi = umma_desc_sw128(smem_base + FE_OFF_A + buf * 2 * FE_A_BYTES);
+            const uint64_t alo = umma_desc_sw128(smem_base + FE_OFF_A + buf * 2 * FE_A_BYTES + FE_A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < FE_K / 16; ++kk) {
+                const uint64_t koff = (uint64_t)(kk * 2);          // 32 bytes per k-step
+                umma_bf16(tmem_d, ahi + koff, whi + koff, idesc, kk != 0);
+                umma_bf16(tmem_d, alo + koff, whi + koff, idesc, 1u);
+                if (!p.skip_wlo) umma_bf16(tmem_d, ahi + koff, wlo + koff, idesc, 1u);
+            }
+            umma_commit(a_empty(buf));
+            umma_commit(acc_full(buf));
+        }
+    } else if (warp >= 12) {
+        // ===================================================================== A generators (128 threads)
+        const int t = threadIdx.x - 384;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            int b, m0;
+            tile_coords(tile, b, m0);
+            uint8_t* ahi = smem_gen + FE_OFF_A + buf * 2 * FE_A_BYTES;
+            uint8_t* alo = ahi + FE_A_BYTES;
+            if (KIND == 0) {
+                // thread = output row: y[c] = relu(b0[c] + sum_k w[k][c] x[2 row + k]); samples beyond the clip read as 0 (F.pad)
+                const long long s0 = 2ll * (m0 + t);
+                const float* xb = p.x + (long long)b * p.x_stride;
+                float xv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xv[k] = (s0 + k < p.length) ? __ldg(xb + s0 + k) : 0.f;
+                mbar_wait(a_empty(buf), ph ^ 1u);
+#pragma unroll 2
+                for (int j = 0; j < 8; ++j) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 w = taps_s[8 * j + e];
+                        float acc = b0_s[8 * j + e];
+                        acc = fmaf(w.x, xv[0], acc); acc = fmaf(w.y, xv[1], acc);
+                        acc = fmaf(w.z, xv[2], acc); acc = fmaf(w.w, xv[3], acc);
+                        f[e] = fmaxf(acc, 0.f);
+                    }
+                    uint4 hi, lo;
+                    split8(f, hi, lo);
+                    const uint32_t off = (uint32_t)t * 128u + (uint32_t)((j ^ (t & 7)) << 4);
+                    *reinterpret_cast<uint4*>(ahi + off) = hi;
+                    *reinterpret_cast<uint4*>(alo + off) = lo;
+                }
+            } else {
+                // 16 lanes = one 256-byte input row (float4 each), two rows per warp request; 16 requests per thread in two batches
+                const int j = t & 15, rsub = t >> 4;
+                const float* ab = p.a + (long long)b * p.rows * 64;
+                mbar_wait(a_empty(buf), ph ^ 1u);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = (half * 8 + i) * 8 + rsub;
+                        const int pr = m0 + r;
+                        v[i] = (pr >= 0 && pr < p.rows) ? __ldg(reinterpret_cast<const float4*>(ab + (long long)pr * 64) + j)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = (half * 8 + i) * 8 + rsub;
+                        const uint32_t h0 = cvt_f16x2_sat(v[i].x, v[i].y), h1 = cvt_f16x2_sat(v[i].z, v[i].w);
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+                        const uint32_t l0 = cvt_f16x2_sat(v[i].x - f0.x, v[i].y - f0.y), l1 = cvt_f16x2_sat(v[i].z - f1.x, v[i].w - f1.y);
+                        const uint32_t off = (uint32_t)r * 128u + (uint32_t)(((j >> 1) ^ (r & 7)) << 4) + (uint32_t)((j & 1) << 3);
+                        *reinterpret_cast<uint2*>(ahi + off) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(alo + off) = make_uint2(l0, l1);
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(a_full(buf));
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===================================================================== epilogue (8 warps): thread = tile row, 64 accumulator columns
+        const int q = warp & 3, grp = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const bool leader = (warp == 4 && lane == 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            int b, m0;
+            tile_coords(tile, b, m0);
+            mbar_wait(acc_full(buf), ph);
+            tc_fence_after();
+            float o[32];                    // gated outputs of this thread's 32 channels (enc0) / running tap sums (dec_last)
+            float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+                const int col0 = grp * 64 + half * 32;
+                __syncwarp();
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * FE_N + col0), v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float2 bv = *reinterpret_cast<const float2*>(bias_s + col0 + 2 * i);
+                    const float xa = fmaf(v[2 * i], p.acc_scale, bv.x), xb = fmaf(v[2 * i + 1], p.acc_scale, bv.y);
+                    const float g = xa * fast_sigmoid(xb);
+                    if (KIND == 0) {
+                        o[half * 16 + i] = g;
+                    } else {
+                        const float4 w = taps_s[grp * 32 + half * 16 + i];
+                        y0 = fmaf(g, w.x, y0); y1 = fmaf(g, w.y, y1); y2 = fmaf(g, w.z, y2); y3 = fmaf(g, w.w, y3);
+                    }
+                }
+            }
+            // the accumulator is in registers: hand the TMEM buffer back to the MMA thread
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(buf));
+            if (KIND == 0) {
+                // staging tile: two halves of 32 channels (128-byte rows, 128-byte swizzle like the tensor map of the store)
+                if (leader) bulk_wait_read<1>();        // the store issued two tiles ago has finished reading this buffer
+                epi_bar();
+                uint8_t* st = smem_gen + FE_OFF_OUT + buf * FE_OUT_BYTES + grp * (FE_OUT_BYTES / 2);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4*>(st + r * 128 + ((c ^ (r & 7)) << 4)) = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                fence_proxy_async();
+                epi_bar();
+                if (leader) {
+                    const uint32_t src = smem_base + FE_OFF_OUT + buf * FE_OUT_BYTES;
+                    tma_store_3d(&tmOut, src, 0, m0, b);
+                    tma_store_3d(&tmOut, src + FE_OUT_BYTES / 2, 32, m0, b);
+                    bulk_commit();
+                }
+            } else {
+                const int pr = m0 + r;
+                const bool valid = pr >= 0 && pr < p.rows;          // rows outside the clip contribute nothing (their A rows are zero, GLU(bias) is not)
+                float4* part = part_s + (buf * 2) * 128;
+                part[grp * 128 + r] = valid ? make_float4(y0, y1, y2, y3) : make_float4(0.f, 0.f, 0.f, 0.f);
+                epi_bar();
+                if (grp == 0 && r >= 1 && pr <= p.rows) {
+                    // out[2p + k] = bias + sum_c g[p][c] w[c][k] (k = 0, 1) + sum_c g[p-1][c] w[c][k + 2]
+                    const float4 c0 = part[r], c1 = part[128 + r], q0 = part[r - 1], q1 = part[128 + r - 1];
+                    const float sc = p.scale ? __ldg(p.scale + b) : 1.0f;
+                    const float e0 = (p.out_bias + (c0.x + c1.x) + (q0.z + q1.z)) * sc;
+                    const float e1 = (p.out_bias + (c0.y + c1.y) + (q0.w + q1.w)) * sc;
+                    const long long s = 2ll * pr;
+                    float* ob = p.out + (long long)b * p.out_stride;
+                    if (s + 1 < p.out_length && ((reinterpret_cast<uintptr_t>(ob + s) & 7u) == 0)) {
+                        *reinterpret_cast<float2*>(ob + s) = make_float2(e0, e1);
+                    } else {
+                        if (s < p.out_length) ob[s] = e0;
+                        if (s + 1 < p.out_length) ob[s + 1] = e1;
+                    }
+                }
+                // part[buf] is rewritten two tiles later: the barrier of the next tile orders that write after these reads
+            }
+        }
+        if (KIND == 0 && leader) bulk_wait_read<0>();
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(FE_TMEM_COLS));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <int KIND>
+static int launch_fused_end(const CUtensorMap& tmWh, const CUtensorMap& tmWl, const CUtensorMap& tmOut, const FusedEndParams& p,
+                            cudaStream_t st) {
+    auto kern = fused_end_kernel<KIND>;
+    const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)FE_SMEM_BYTES, "cudaFuncSetAttribute(fused_end_kernel)");
+    if (rc) return rc;
+    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    kern<<<grid, FE_THREADS, FE_SMEM_BYTES, st>>>(tmWh, tmWl, tmOut, p);
+    CUM_LAUNCH_CHECK("fused_end_kernel");
+    return CUM_OK;
+}
+
+static int weight_maps(const void* w_hi, const void* w_lo, CUtensorMap* tmWh, CUtensorMap* tmWl) {
+    CUM_REQUIRE(w_hi && aligned16(w_hi) && (!w_lo || aligned16(w_lo)), "fused block: weight halves must be 16-byte aligned");
+    int rc = make_tensor_map(tmWh, w_hi, FE_K, FE_N, 1, FE_K, (uint64_t)FE_K * FE_N, FE_K, FE_N, "W_hi", true, true);
+    if (rc) return rc;
+    if (w_lo) return make_tensor_map(tmWl, w_lo, FE_K, FE_N, 1, FE_K, (uint64_t)FE_K * FE_N, FE_K, FE_N, "W_lo", true, true);
+    *tmWl = *tmWh;
+    return CUM_OK;
+}
+
+int enc0_block_fwd(const cum_enc0_block_desc& d, cudaStream_t st) {
+    CUM_REQUIRE(d.x && d.conv_w && d.conv_b && d.glu_w_hi && d.glu_b && d.out, "enc0_block: null pointer");
+    CUM_REQUIRE(d.batch > 0 && d.length > 0 && d.rows_out > 0, "enc0_block: empty problem");
+    CUM_REQUIRE(d.channels == 64, "enc0_block: the fused kernel serves the 64-channel geometry (channels=%d): use conv_in + gemm", d.channels);
+    CUM_REQUIRE(d.glu_w_lo || d.w_lo_is_zero, "enc0_block: glu_w_lo missing");
+    CUM_REQUIRE(aligned16(d.out), "enc0_block: out must be 16-byte aligned");
+    CUM_REQUIRE(d.acc_scale > 0.f, "enc0_block: acc_scale = 1 / (weight scale passed to cum_split_f16)");
+    CUtensorMap tmWh, tmWl, tmOut;
+    int rc = weight_maps(d.glu_w_hi, d.w_lo_is_zero ? nullptr : d.glu_w_lo, &tmWh, &tmWl);
+    if (rc) return rc;
+    rc = make_tensor_map(&tmOut, d.out, 64, (uint64_t)d.rows_out, (uint64_t)d.batch, 64, (uint64_t)d.rows_out * 64, 32, FE_ROWS, "enc0 out");
+    if (rc) return rc;
+    FusedEndParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = d.x; p.x_stride = d.x_stride; p.length = d.length; p.rows = d.rows_out; p.batch = d.batch;
+    p.tiles_per_clip = (int)cdiv(d.rows_out, FE_ROWS);
+    const long long total = (long long)p.tiles_per_clip * d.batch;
+    CUM_REQUIRE(total < (1ll << 31), "enc0_block: too many tiles");
+    p.total_tiles = (int)total;
+    p.taps = d.conv_w; p.b0 = d.conv_b; p.bias = d.glu_b; p.acc_scale = d.acc_scale; p.skip_wlo = d.w_lo_is_zero ? 1 : 0;
+    return launch_fused_end<0>(tmWh, tmWl, tmOut, p, st);
+}
+
+int dec_last_block_fwd(const cum_dec_last_block_desc& d, cudaStream_t st) {
+    CUM_REQUIRE(d.a && d.glu_w_hi && d.glu_b && d.convt_w && d.out, "dec_last_block: null pointer");
+    CUM_REQUIRE(d.batch > 0 && d.rows_in > 0 && d.out_length > 0, "dec_last_block: empty problem");
+    CUM_REQUIRE(d.channels == 64, "dec_last_block: the fused kernel serves the 64-channel geometry (channels=%d): use gemm + convt_out", d.channels);
+    CUM_REQUIRE(d.glu_w_lo || d.w_lo_is_zero, "dec_last_block: glu_w_lo missing");
+    CUM_REQUIRE(aligned16(d.a), "dec_last_block: a must be 16-byte aligned");
+    CUM_REQUIRE(d.acc_scale > 0.f, "dec_last_block: acc_scale = 1 / (weight scale passed to cum_split_f16)");
+    CUM_REQUIRE(d.out_length <= 2 * d.rows_in + 2, "dec_last_block: out_length exceeds 2 rows_in + 2");
+    CUtensorMap tmWh, tmWl;
+    int rc = weight_maps(d.glu_w_hi, d.w_lo_is_zero ? nullptr : d.glu_w_lo, &tmWh, &tmWl);
+    if (rc) return rc;
+    FusedEndParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = d.a; p.rows = d.rows_in; p.batch = d.batch;
+    p.tiles_per_clip = (int)cdiv((long long)d.rows_in + 1, FE_ROWS - 1);
+    const long long total = (long long)p.tiles_per_clip * d.batch;
+    CUM_REQUIRE(total < (1ll << 31), "dec_last_block: too many tiles");
+    p.total_tiles = (int)total;
+    p.taps = d.convt_w; p.bias = d.glu_b; p.acc_scale = d.acc_scale; p.skip_wlo = d.w_lo_is_zero ? 1 : 0;
+    p.out_bias = d.convt_bias; p.scale = d.scale; p.out = d.out; p.out_stride = d.out_stride; p.out_length = d.out_length;
+    return launch_fused_end<1>(tmWh, tmWl, tmWh /* no output map: the waveform is written with plain stores */, p, st);
+}
+
+}  // namespace cum

@@ -23,6 +23,7 @@
 // product).  W is split once at pack time; A either by the splitter warps (F16X3 / BF16X3 / TF32X3) or -- TC_F16PS -- once by
 // the PRODUCING layer's epilogue, which writes fp16 hi / lo planes ("hl16") that the consumer feeds to the MMA straight from TMA.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -31,6 +32,9 @@
 #include <stdlib.h>
 #include <type_traits>
 #include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 namespace cum {
 
@@ -41,9 +45,6 @@ constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr uint32_t TC_TMEM_COLS = 512;
 constexpr int TC_EPI_WARPS = 16;              // warps 4..19: four per TMEM lane quarter, 32-column chunks interleaved.  The epilogue is
                                               // serial-issue-bound per warp (~0.25 IPC), so its speed scales with the warp count
-constexpr int TC_EPI_GENERIC_UNARY = -1;      // runtime-selected activation (SiLU ...)
-constexpr int TC_EPI_GENERIC_GLU = -2;        // runtime-selected GLU gate (ReLU / SiLU / GELU)
-constexpr int TC_EPI_ATOMIC_ADD = -3;         // wgrad split-K: accumulate the tile into C with atomics (no bias / activation)
 
 // MODE: 0 = single-pass TF32, 1 = TF32X3 (hi/lo fp32 tiles, 3 kind::tf32 MMAs), 2 / 3 = BF16X3 / F16X3 (hi/lo 16-bit tiles,
 // 3 kind::f16 MMAs at twice the TF32 rate; F16X3 keeps 22 mantissa bits, its weights carry a power-of-two scale undone in the epilogue)
@@ -95,240 +96,6 @@ struct TcParams {
     void* c_lo;               // OUTF == 2: low-half plane of the output (c is the high-half plane), fp16
     const void* addend_lo;    // OUTF == 2: low-half plane of the addend
 };
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    // K-major, 128B swizzle: 8-row core-matrix groups are 1024 B apart (SBO); LBO unused; version 1 (sm_100)
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(1024u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
-    // K-major, 64B swizzle (bf16 tiles with 32-element = 64-byte rows): 8-row groups are 512 B apart
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(512u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
-    return d;
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// ---- cta_group::2 (CTA pair) variants
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
-    return r;
-}
-// Remote arrive with the default .release.cta semantics (what CUTLASS' ClusterBarrier::arrive(cta_id) issues).  A
-// .release.cluster arrive compiles to ERRBAR (a full memory barrier, ~1 us) + SYNCS.ARRIVE and sat on the per-K-block critical
-// path; everything the leader consumes after this signal is shared memory already made visible to the async proxy by
-// fence.proxy.async + a cta-scope release/acquire inside the peer, or TMEM ordered by tcgen05.fence.
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// wait on a barrier of THIS CTA that peers arrive on remotely
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
-    }
-}
-// TMA load issued by either CTA of a pair; the bytes are accounted on `bar`, a shared::cluster barrier address (the leader's)
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-// completion of all MMAs issued so far by this thread -> one arrival on `bar` (same offset) in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-template <bool CTA2> __device__ __forceinline__ void umma_f16_any(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) {
-    if (CTA2) umma_bf16_2sm(d, a, b, i, acc); else umma_bf16(d, a, b, i, acc);
-}
-template <bool CTA2> __device__ __forceinline__ void umma_tf32_any(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) {
-    if (CTA2) umma_tf32_2sm(d, a, b, i, acc); else umma_tf32(d, a, b, i, acc);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// packed fp32 -> fp16x2 with saturation to +-65504 (first argument lands in the low half, like __floats2half2_rn)
-__device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo_elem, float hi_elem) {
-    uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
-    return r;
-}
-
-// 16 lanes x 64 columns: thread t gets rows (t/4, t/4+8) x columns 8k + 2(t%4) + {0,1}:
-//   r[4k+0], r[4k+1] -> row t/4 ; r[4k+2], r[4k+3] -> row t/4 + 8     (CuTe SM100_TMEM_LOAD_16dp256b8x layout)
-__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// 16 lanes x 32 columns: r[4k+0..1] -> row t/4, r[4k+2..3] -> row t/4 + 8, columns 8k + 2(t%4) + {0,1}, k = 0..3
-__device__ __forceinline__ void tmem_ld_16x256b_x4_nowait(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
-
-// 16 lanes x 16 columns: r[4k+0..1] -> row t/4, r[4k+2..3] -> row t/4 + 8, columns 8k + 2(t%4) + {0,1}, k = 0..1
-__device__ __forceinline__ void tmem_ld_16x256b_x2_nowait(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-}
-
-// epilogue math.  The tensor-core path uses the fast intrinsics (ex2.approx / rcp.approx, ~2 ulp): the gate error is
-// far below the TF32X3 product error; the exact-fp32 SIMT kernel keeps expf / IEEE division.
-// 1 / (1 + 2^(-v log2 e)) with bare ex2.approx / rcp.approx: +inf -> rcp -> 0 and flushed underflow -> 1 are the right limits, so the
-// range guards of __expf / __fdividef (3 more instructions per output) are not needed
-__device__ __forceinline__ float fast_sigmoid(float v) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return r;
-}
-template <int EPI>
-__device__ __forceinline__ float tc_gate(int epi, float g) {
-    if (EPI == CUM_EPI_GLU_SIGMOID) return fast_sigmoid(g);
-    switch (epi) {
-        case CUM_EPI_GLU_RELU: return fmaxf(g, 0.0f);
-        case CUM_EPI_GLU_SILU: return g * fast_sigmoid(g);
-        case CUM_EPI_GLU_GELU: return geluf_(g);
-        default:               return fast_sigmoid(g);
-    }
-}
-template <int EPI>
-__device__ __forceinline__ float tc_act(int epi, float v) {
-    if (EPI == CUM_EPI_NONE) return v;
-    if (EPI == CUM_EPI_RELU) return fmaxf(v, 0.0f);
-    switch (epi) {
-        case CUM_EPI_RELU: return fmaxf(v, 0.0f);
-        case CUM_EPI_SILU: return v * fast_sigmoid(v);
-        default:           return v;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------ kernel
 // OUTF: output (and addend) format -- 0 fp32, 1 bf16, 2 fp16 hi / lo planes ("hl16": what TC_F16PS consumes)
@@ -890,6 +657,55 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 static int make_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_elems,
                     uint64_t s2_elems, uint32_t box0, uint32_t box1, const char* what, bool bf16 = false, bool sw128_16 = false) {
+    return make_tensor_map(tm, base, d0, d1, d2, s1_elems, s2_elems, box0, box1, what, bf16, sw128_16);
+}
+
+static int encode_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_elems,
+                      uint64_t s2_elems, uint32_t box0, uint32_t box1, const char* what, bool bf16, bool sw128_16);
+
+// Tensor-map cache: a descriptor depends only on (base pointer, extents, strides, box, element type, swizzle), and a model
+// re-issues the same few hundred of them every forward (PyTorch's caching allocator hands the same activation buffers back), so
+// cuTensorMapEncodeTiled (a driver call, 3-4 per GEMM launch) runs once per distinct operand instead of once per launch.
+// Process-wide, mutex-protected, bounded; cum_shutdown() empties it.  The encoded bytes do not depend on the device.
+struct TmKey {
+    uint64_t v[8];
+    bool operator==(const TmKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmKeyHash {
+    size_t operator()(const TmKey& k) const {
+        uint64_t h = 0x9e3779b97f4a7c15ull;
+        for (int i = 0; i < 8; ++i) { h ^= k.v[i] + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); }
+        return (size_t)h;
+    }
+};
+static std::mutex g_tm_mu;
+static std::unordered_map<TmKey, CUtensorMap, TmKeyHash> g_tm_cache;
+constexpr size_t TM_CACHE_MAX = 8192;
+void tensor_map_cache_clear() {
+    std::lock_guard<std::mutex> lk(g_tm_mu);
+    g_tm_cache.clear();
+}
+
+int make_tensor_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_elems,
+                    uint64_t s2_elems, uint32_t box0, uint32_t box1, const char* what, bool bf16, bool sw128_16) {
+    TmKey key;
+    key.v[0] = reinterpret_cast<uint64_t>(base); key.v[1] = d0; key.v[2] = d1; key.v[3] = d2; key.v[4] = s1_elems; key.v[5] = s2_elems;
+    key.v[6] = ((uint64_t)box0 << 32) | box1; key.v[7] = (bf16 ? 1u : 0u) | (sw128_16 ? 2u : 0u);
+    {
+        std::lock_guard<std::mutex> lk(g_tm_mu);
+        auto it = g_tm_cache.find(key);
+        if (it != g_tm_cache.end()) { *tm = it->second; return CUM_OK; }
+    }
+    const int rc_enc = encode_map(tm, base, d0, d1, d2, s1_elems, s2_elems, box0, box1, what, bf16, sw128_16);
+    if (rc_enc) return rc_enc;
+    std::lock_guard<std::mutex> lk(g_tm_mu);
+    if (g_tm_cache.size() >= TM_CACHE_MAX) g_tm_cache.clear();
+    g_tm_cache.emplace(key, *tm);
+    return CUM_OK;
+}
+
+static int encode_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_elems,
+                      uint64_t s2_elems, uint32_t box0, uint32_t box1, const char* what, bool bf16, bool sw128_16) {
     auto enc = get_encode();
     if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return CUM_ECUDA; }
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -921,12 +737,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     constexpr bool P16 = Cfg::PLAIN16;
     constexpr bool PRES = Cfg::PRES;
     auto kern = gemm_tc_kernel<MODE, BN, EPI, OUTF, CTA2>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
-        attr_done = true;
-    }
+    { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)Cfg::SMEM_BYTES, "cudaFuncSetAttribute(gemm_tc_kernel)"); if (rc_attr) return rc_attr; }
     CUtensorMap tmA, tmAl, tmWh, tmWl;
     const uint64_t a_bs = (d.batch > 1 && !g_wgrad_kbs) ? (uint64_t)d.a_batch_stride : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
     int rc = make_map(&tmA, d.a, g_wgrad_kbs ? (uint64_t)d.a_row_stride : (uint64_t)d.k, (uint64_t)d.a_rows,
@@ -1006,7 +817,9 @@ static int dispatch_epi2(const cum_gemm_desc& d, cudaStream_t st) {
                 case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, 2, CTA2>(d, st);
                 case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, 2, CTA2>(d, st);
                 case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, 2, CTA2>(d, st);
-                default: set_error("gemm_tc: hi/lo output supports NONE / RELU / GLU_SIGMOID epilogues"); return CUM_ENOTSUP;
+                default:
+                    if (epi_is_glu(d.epilogue)) return launch_tc<MODE, BN, TC_EPI_GENERIC_GLU, 2, CTA2>(d, st);   // ReLU / SiLU / GELU gates
+                    set_error("gemm_tc: hi/lo output supports NONE / RELU / GLU_* epilogues"); return CUM_ENOTSUP;
             }
         } else {
             set_error("gemm_tc: hi/lo output planes are available for the F16X3 mode");
@@ -1019,7 +832,9 @@ static int dispatch_epi2(const cum_gemm_desc& d, cudaStream_t st) {
                 case CUM_EPI_NONE:        return launch_tc<MODE, BN, CUM_EPI_NONE, 1, CTA2>(d, st);
                 case CUM_EPI_RELU:        return launch_tc<MODE, BN, CUM_EPI_RELU, 1, CTA2>(d, st);
                 case CUM_EPI_GLU_SIGMOID: return launch_tc<MODE, BN, CUM_EPI_GLU_SIGMOID, 1, CTA2>(d, st);
-                default: set_error("gemm_tc: bf16 output supports NONE / RELU / GLU_SIGMOID epilogues"); return CUM_ENOTSUP;
+                default:
+                    if (epi_is_glu(d.epilogue)) return launch_tc<MODE, BN, TC_EPI_GENERIC_GLU, 1, CTA2>(d, st);
+                    set_error("gemm_tc: bf16 output supports NONE / RELU / GLU_* epilogues"); return CUM_ENOTSUP;
             }
         } else {
             set_error("gemm_tc: bf16 output is available for the BF16 and F16X3 modes");

@@ -506,12 +506,7 @@ template <int NS, int SL, int CH, int TC>
 static int launch_scan(const cum_scan_desc& d, cudaStream_t st) {
     auto kern = selective_scan_fwd_kernel<NS, SL, CH, TC>;
     const size_t smem = sizeof(ScanSmem<NS, SL, CH, TC>);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(selective_scan_fwd_kernel)");
-        attr_done = true;
-    }
+    { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem, "cudaFuncSetAttribute(selective_scan_fwd_kernel)"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)cdiv(d.d, CH), (unsigned)d.batch);
     kern<<<grid, CH * SL, smem, st>>>(d);
     CUM_LAUNCH_CHECK("selective_scan_fwd_kernel");

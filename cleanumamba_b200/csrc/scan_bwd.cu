@@ -268,12 +268,7 @@ template <int SL>
 static int launch_scan_bwd(const cum_scan_bwd_desc& d, cudaStream_t st) {
     auto kern = selective_scan_bwd_kernel<SL>;
     const size_t smem = sizeof(ScanBwdSmem<SL>);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(selective_scan_bwd_kernel)");
-        attr_done = true;
-    }
+    { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem, "cudaFuncSetAttribute(selective_scan_bwd_kernel)"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)cdiv(d.fwd.d, SB_CH), (unsigned)d.fwd.batch);
     kern<<<grid, 32 * SL, smem, st>>>(d);
     CUM_LAUNCH_CHECK("selective_scan_bwd_kernel");

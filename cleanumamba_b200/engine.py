@@ -10,7 +10,9 @@ Reference walk: /root/reference/src/network/CleanUMamba.py:252-324.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import functools
 import math
 import os
 from typing import Dict, List, Optional
@@ -52,11 +54,22 @@ def _interleave_glu(w: torch.Tensor, b: torch.Tensor, k_pad: int):
     return wp, bp, Hp
 
 
+def on_model_device(fn):
+    """Run a method with the model's GPU as the current device: the C ABI works on the calling thread's current device and
+    ``_lib.stream_ptr()`` is that device's current stream, so a model on cuda:1 works while cuda:0 is current."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with self.device_guard():
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 class Engine:
     skip_zero_lo = True      # skip the a_hi*w_lo pass for weights whose low half is exactly zero (tests may turn it off)
     hl16 = os.environ.get("CUM_HL16", "1") != "0"    # f16x3: store the conv-stack activations as fp16 hi/lo planes (A/B switch)
     HL16_MIN_CONSUMER_K = int(os.environ.get("CUM_HL16_CK", 512))     # thresholds of the per-tensor hl16 rule (see forward())
     HL16_MIN_PRODUCER_K = int(os.environ.get("CUM_HL16_PK", 256))
+    fused_ends = os.environ.get("CUM_FUSED_ENDS", "1") != "0"    # f16x3, 64-channel ends: first / last U-Net block as one kernel each
 
     def __init__(self, model):
         self.model = model
@@ -66,6 +79,12 @@ class Engine:
         self._graphs: dict = {}    # (input shape, parameter versions) -> captured CUDA graph of the forward (small problems)
         self.launches = 0          # kernels launched through the C ABI (bench.py's gpu_launches)
         self.prof = None           # list of (kind, start_event, stop_event, flops, bytes) when profiling is on
+
+    def device_guard(self):
+        dev = getattr(self, "device", None) or next(self.model.parameters()).device
+        if dev.type != "cuda" or dev.index is None or dev.index == torch.cuda.current_device():
+            return contextlib.nullcontext()
+        return torch.cuda.device(dev)
 
     def _call(self, kind, fn, *args, launches=1, flops=0, nbytes=0):
         """One C-ABI call on the current stream; optional CUDA-event bracket for per-kernel roofline numbers."""
@@ -94,12 +113,16 @@ class Engine:
     def _params_key(self):
         return tuple((id(p), p._version, p.data_ptr(), p.device, p.dtype) for p in self.model.parameters())
 
+    pack_generation = 0                # bumped by every repack: sessions holding captured graphs / packed pointers compare it
+
     def ensure_packed(self):
         key = self._params_key()
         if key != self._key:
             self._graphs.clear()       # captured graphs reference the previous packed weights
-            self._pack()
+            with self.device_guard():
+                self._pack()
             self._key = key
+            self.pack_generation += 1
 
     @torch.no_grad()
     def _pack(self):
@@ -379,6 +402,7 @@ class Engine:
     GRAPH_CACHE = 4
 
     @torch.no_grad()
+    @on_model_device
     def forward(self, noisy: torch.Tensor, return_skip_connections: bool = False):
         self.ensure_packed()
         if (return_skip_connections or self.prof is not None or noisy.dim() != 3 or noisy.numel() > self.GRAPH_MAX_SAMPLES
@@ -444,8 +468,26 @@ class Engine:
             return torch.float16 if (hl16 and consumer_k >= self.HL16_MIN_CONSUMER_K and producer_k >= self.HL16_MIN_PRODUCER_K) else adt
         skips: List[torch.Tensor] = []
         prev = None
+        fuse = (self.fused_ends and self.math == _lib.MATH_F16X3 and not self.bf16_io and m.glu_activation == "Sigmoid" and D > 1)
+        e0, dl = meta["enc"][0], meta["dec"][D - 1]
+        fuse_e0 = fuse and e0["Hc_p"] == 64 and e0["Ho_p"] == 64
+        fuse_dl = fuse and dl["Cin_p"] == 64 and dl["Hg_p"] == 64
         for i, e in enumerate(meta["enc"]):
             rows = B * Ls[i + 1]
+            if i == 0 and fuse_e0:
+                # whole first block in one kernel: the 64-channel conv output stays on the SM (fused_ends.cu)
+                prev = torch.empty(rows, 64, dtype=torch.float32, device=x.device)
+                d0 = _lib.Enc0BlockDesc()
+                d0.x, d0.x_stride, d0.batch, d0.length = x.data_ptr(), L, B, L
+                d0.conv_w, d0.conv_b = pk["enc0.w"].data_ptr(), pk["enc0.b"].data_ptr()
+                d0.glu_w_hi, d0.glu_w_lo, d0.glu_b = self.pk_hi["enc0.wg"].data_ptr(), self.pk_lo["enc0.wg"].data_ptr(), pk["enc0.bg"].data_ptr()
+                d0.acc_scale = self.w_scale_inv["enc0.wg"]
+                d0.w_lo_is_zero = 1 if (self.skip_zero_lo and "enc0.wg" in self.w_lo_zero) else 0
+                d0.out, d0.rows_out, d0.channels = prev.data_ptr(), Ls[1], 64
+                self._call("enc0_block", lib.cum_enc0_block_fwd, C.byref(d0), st(), flops=2 * rows * 128 * 64,
+                           nbytes=4 * B * (L + Ls[1] * e["Ho"]))
+                skips.append(prev)
+                continue
             y = self.act_buffer(rows, e["Hc_p"], fmt(e["Hc_p"], 2 * e["Cin_p"] if i else 0), x.device)
             if i == 0 and y.dtype == torch.float16:
                 self._call("conv_in", lib.cum_conv_in_hl16_fwd, x.data_ptr(), L, B, L, pk["enc0.w"].data_ptr(),
@@ -478,6 +520,20 @@ class Engine:
         Tj = T
         out = None
         for j, d in enumerate(meta["dec"]):
+            if j == D - 1 and fuse_dl and xcur.dtype == torch.float32:
+                # whole last block in one kernel: GLU GEMM + transposed conv to the waveform + crop + * std (fused_ends.cu)
+                length = L if m.normalize_input else Ls[0]
+                out = torch.empty(B, 1, length, dtype=torch.float32, device=x.device)
+                dd = _lib.DecLastBlockDesc()
+                dd.a, dd.batch, dd.rows_in = xcur.data_ptr(), B, Tj
+                dd.glu_w_hi, dd.glu_w_lo, dd.glu_b = self.pk_hi[f"dec{j}.wg"].data_ptr(), self.pk_lo[f"dec{j}.wg"].data_ptr(), pk[f"dec{j}.bg"].data_ptr()
+                dd.acc_scale = self.w_scale_inv[f"dec{j}.wg"]
+                dd.w_lo_is_zero = 1 if (self.skip_zero_lo and f"dec{j}.wg" in self.w_lo_zero) else 0
+                dd.convt_w, dd.convt_bias, dd.scale = pk[f"dec{j}.w"].data_ptr(), meta["out_bias"], ptr(std)
+                dd.out, dd.out_stride, dd.out_length, dd.channels = out.data_ptr(), length, length, 64
+                self._call("dec_last_block", lib.cum_dec_last_block_fwd, C.byref(dd), st(), flops=2 * B * Tj * 128 * 64,
+                           nbytes=4 * B * (Tj * d["Hg"] + length))
+                break
             # (the waveform-end kernel reads plain fp32 / bf16 rows: the last GLU output is never written as hi/lo planes)
             g = self.dense(xcur, B * Tj, d["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * d["Hg_p"], epi=act,
                            out_dtype=fmt(2 * d["Hg_p"], d["Cin_p"]) if j < D - 1 else adt)

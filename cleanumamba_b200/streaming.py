@@ -21,10 +21,20 @@ The reference's skip-index bug (:474) is NOT reproduced (it crashes on every shi
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 
 from . import _lib
 from ._lib import EPI_GLU, EPI_RELU, ptr
+
+
+def _on_device(fn):
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with self.eng.device_guard():
+            return fn(self, *args, **kwargs)
+    return wrapper
 
 
 class StreamSession:
@@ -36,6 +46,7 @@ class StreamSession:
         self.model = model
         self.eng = model.engine()
         self.eng.ensure_packed()
+        self._pack_gen = self.eng.pack_generation
         if self.eng.bf16_io:
             raise NotImplementedError("cleanumamba_b200: math_mode='bf16' (reduced-precision variant) is offline-forward only")
         self.B = batch
@@ -68,6 +79,21 @@ class StreamSession:
     def pending_view(self):
         return self.pending
 
+    def reset_frames(self):
+        """Restart the running mean of the per-frame input std (the reference's ``reset_time_per_frame`` zeroes ``frames``, its
+        denominator, :326-328 / :399-401)."""
+        self.frames = 0
+        if self.frames_dev is not None:
+            self.frames_dev.zero_()
+
+    def _sync_weights(self):
+        """Parameters may have changed since the last call (load_state_dict, an optimiser step, .half()/.float()): repack, and
+        drop a captured graph -- it has the previous packed-weight pointers baked in."""
+        self.eng.ensure_packed()
+        if self.eng.pack_generation != self._pack_gen:
+            self._pack_gen = self.eng.pack_generation
+            self.release_graph()
+
     # ------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def feed(self, chunk: torch.Tensor) -> torch.Tensor:
@@ -76,6 +102,11 @@ class StreamSession:
             raise ValueError(f"expected a (batch={self.B}, n) tensor, got {tuple(chunk.shape)}")
         if chunk.device != self.dev:
             raise RuntimeError(f"chunk is on {chunk.device}, model on {self.dev} (no CPU fallback)")
+        self._sync_weights()
+        with self.eng.device_guard():
+            return self._feed(chunk)
+
+    def _feed(self, chunk: torch.Tensor) -> torch.Tensor:
         if self._graph is not None:
             if chunk.shape[1] == self._graph["chunk"]:
                 return self._replay(chunk)
@@ -123,6 +154,7 @@ class StreamSession:
             setattr(self, k, list(v) if isinstance(v, list) else v)
 
     @torch.no_grad()
+    @_on_device
     def capture_graph(self, chunk_samples: int) -> None:
         """Capture feed() for chunks of exactly ``chunk_samples`` samples (a multiple of the hop).  Call after at least one
         eager feed() has produced output (steady state); feeds of any other size transparently fall back to the eager path."""
@@ -131,6 +163,7 @@ class StreamSession:
         if self.frames_since_reset == 0 or self.pending.shape[1] != self.frame_length - self.hop:
             raise RuntimeError("capture_graph: the session is not in steady state (feed at least one full frame first, and "
                                "feed whole hops so that pending holds frame_length - hop samples)")
+        self._sync_weights()
         self.release_graph()
         if self.model.normalize_input and self.frames_dev is None:
             self.frames_dev = torch.tensor([self.frames], dtype=torch.int32, device=self.dev)
@@ -187,6 +220,7 @@ class StreamSession:
         return g["out"].clone()
 
     @torch.no_grad()
+    @_on_device
     def flush(self) -> torch.Tensor:
         """:358-368 -- clear the conv caches, feed frame_length zeros, return the first len(pending) samples."""
         self.release_graph()

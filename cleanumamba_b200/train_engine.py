@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import EPI_NONE, EPI_RELU, ScanBwdDesc, ScanDesc, WgradDesc, check, ptr
-from .engine import Engine
+from .engine import Engine, on_model_device
 
 
 class TrainEngine(Engine):
@@ -107,6 +107,7 @@ class TrainEngine(Engine):
         return c
 
     # ---------------------------------------------------------------------------------------------- forward
+    @on_model_device
     def forward_train(self, noisy: torch.Tensor):
         m = self.model
         self.ensure_packed()
@@ -205,6 +206,7 @@ class TrainEngine(Engine):
         return out, S
 
     # ---------------------------------------------------------------------------------------------- backward
+    @on_model_device
     def backward(self, S: dict, dout: torch.Tensor, sync=None) -> Dict[str, torch.Tensor]:
         """dout: (B, 1, length) -> flat gradient views ``self.gk`` (packed layout), also returned.  ``sync`` (a
         distributed.GradSync) starts an asynchronous all-reduce of each gradient bucket as soon as it is complete."""
@@ -353,7 +355,7 @@ class TrainEngine(Engine):
         for i, e in enumerate(meta["enc"]):
             Hc = e["Hc"]
             if i == 0:
-                out["encoder.0.0.weight"] = gk["enc0.w"][:, :Hc].t()[:, None, :].contiguous()
+                out["encoder.0.0.weight"] = gk["enc0.w"][:, :Hc].t()[:, None, :].clone()
             else:
                 cp = e["Cin_p"]
                 Cin = m.encoder[i][0].weight.shape[1]
@@ -365,17 +367,19 @@ class TrainEngine(Engine):
                 out[f"encoder.{i}.0.weight"] = w
             out[f"encoder.{i}.0.bias"] = gk[f"enc{i}.b"][:Hc].clone()
             w, b = deinterleave(gk[f"enc{i}.wg"], gk[f"enc{i}.bg"], e["Ho"], Hc)
-            out[f"encoder.{i}.2.weight"], out[f"encoder.{i}.2.bias"] = w[:, :, None].contiguous(), b
+            out[f"encoder.{i}.2.weight"], out[f"encoder.{i}.2.bias"] = w[:, :, None], b          # torch.cat results: fresh storage
         dm = meta["dm"]
         C_b = meta["enc"][-1]["Ho"]
-        out["tsfm_conv1.weight"] = gk["t1.w"][:dm, :C_b, None].contiguous()
+        # .clone(), never .contiguous(): when no padding is cut away (dm % 8 == 0, every full-size model) .contiguous() is a VIEW of
+        # the persistent gradient buffer, autograd would adopt it as param.grad and the next backward would overwrite / double it
+        out["tsfm_conv1.weight"] = gk["t1.w"][:dm, :C_b, None].clone()
         out["tsfm_conv1.bias"] = gk["t1.b"][:dm].clone()
         for l, mm in enumerate(meta["mamba"]):
             di, di_p, N, N_p, R, R_p = mm["di"], mm["di_p"], mm["N"], mm["N_p"], mm["R"], mm["R_p"]
             p = f"tsfm_Mamba_layers.{l}."
             gin = gk[f"m{l}.in"]
             out[p + "mixer.in_proj.weight"] = torch.cat([gin[:di, :dm], gin[di_p: di_p + di, :dm]], 0)
-            out[p + "mixer.conv1d.weight"] = gk[f"m{l}.cw"][:, :di].t()[:, None, :].contiguous()
+            out[p + "mixer.conv1d.weight"] = gk[f"m{l}.cw"][:, :di].t()[:, None, :].clone()
             out[p + "mixer.conv1d.bias"] = gk[f"m{l}.cb"][:di].clone()
             gx = gk[f"m{l}.xp"]
             out[p + "mixer.x_proj.weight"] = torch.cat([gx[:R, :di], gx[R_p: R_p + N, :di], gx[R_p + N_p: R_p + N_p + N, :di]], 0)
@@ -386,15 +390,15 @@ class TrainEngine(Engine):
             out[p + "mixer.out_proj.weight"] = gk[f"m{l}.out"][:dm, :di].clone()
             out[p + "norm.weight"], out[p + "norm.bias"] = gk[f"m{l}.g"][:dm].clone(), gk[f"m{l}.be"][:dm].clone()
         out["norm_f.weight"], out["norm_f.bias"] = gk["nf.g"][:dm].clone(), gk["nf.be"][:dm].clone()
-        out["tsfm_conv2.weight"] = gk["t2.w"][:C_b, :dm, None].contiguous()
+        out["tsfm_conv2.weight"] = gk["t2.w"][:C_b, :dm, None].clone()
         out["tsfm_conv2.bias"] = gk["t2.b"][:C_b].clone()
         for j, d in enumerate(meta["dec"]):
             Cin = m.decoder[j][0].weight.shape[1]
             w, b = deinterleave(gk[f"dec{j}.wg"], gk[f"dec{j}.bg"], d["Hg"], Cin)
-            out[f"decoder.{j}.0.weight"], out[f"decoder.{j}.0.bias"] = w[:, :, None].contiguous(), b
+            out[f"decoder.{j}.0.weight"], out[f"decoder.{j}.0.bias"] = w[:, :, None], b
             Hg, Co, Co_p = d["Hg"], d["Co"], d["Co_p"]
             if j == D - 1:
-                out[f"decoder.{j}.2.weight"] = gk[f"dec{j}.w"][:, :Hg].t()[:, None, :].contiguous()
+                out[f"decoder.{j}.2.weight"] = gk[f"dec{j}.w"][:, :Hg].t()[:, None, :].clone()
                 out[f"decoder.{j}.2.bias"] = gk["out_bias"][:1].clone()
             else:
                 g = gk[f"dec{j}.w"]

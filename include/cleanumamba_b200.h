@@ -12,7 +12,11 @@
  *     so the header needs no CUDA include);
  *   - return 0 on success, a negative CUM_E* code otherwise; never throws; cum_last_error() returns a
  *     thread-local message for the most recent failure on the calling thread;
- *   - callable from any host thread (the device is taken from cum_init / the current context).
+ *   - callable from any host thread; every call works on the device that is CURRENT in the calling thread
+ *     (cudaSetDevice / torch.cuda.device guard) -- the library never changes the current device.  Per-device
+ *     state (SM count, raised shared-memory limits) is keyed by device ordinal, so one process may drive
+ *     several GPUs; the only process-wide mutable state is the tensor-map cache and that attribute set,
+ *     both behind a mutex and emptied by cum_shutdown().
  *
  * DATA LAYOUT.  Activations are channels-last: a (batch, time, channels) fp32 array whose channel
  * count is padded to a multiple of 8 (pad lanes are kept at 0 by zero-padded packed weights).  The
@@ -25,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CUM_ABI_VERSION 1
+#define CUM_ABI_VERSION 2
 
 /* error codes */
 #define CUM_OK            0
@@ -58,7 +62,9 @@ typedef void* cum_stream_t;    /* cudaStream_t */
 
 /* ---- library ------------------------------------------------------------------------------- */
 int         cum_abi_version(void);
-int         cum_init(int device);              /* selects + probes the device; fails unless it is sm_100 */
+int         cum_init(int device);              /* probes `device` (fails unless it is sm_100); does not make it current */
+int         cum_shutdown(void);                /* drops the library's caches (TMA descriptor cache, per-device kernel
+                                                  attributes); the library stays usable, caches refill lazily */
 const char* cum_last_error(void);
 
 /* ---- waveform ends -------------------------------------------------------------------------- */
@@ -164,6 +170,44 @@ int cum_split_bf16(const float* w, void* hi, void* lo, long long count, cum_stre
 /* fp16 hi/lo split of scale*w for CUM_MATH_F16X3 (scale = a power of two, typically 2^floor(log2(8/max|w|))); pass
  * acc_scale = 1/scale in the descriptor. */
 int cum_split_f16(const float* w, void* hi, void* lo, long long count, float scale, cum_stream_t stream);
+
+/* ---- fused U-Net blocks (CUM_MATH_F16X3 arithmetic) --------------------------------------------------------------- */
+/* First encoder block as ONE kernel (CleanUMamba.py:108-113 for i = 0, with F.pad of :263):
+ *   y[t,c]   = relu(conv_b[c] + sum_k conv_w[k,c] x[b, 2t+k])            Conv1d(1, 64, 4, 2) + ReLU, x read as 0 beyond `length`
+ *   out[t,:] = GLU(glu_b + W y[t,:])                                       Conv1d(64, 128, 1) + layers.Activation("Sigmoid")
+ * The 64-channel intermediate never reaches HBM (it was a 2 x 1.3 GB round trip per 64 x 10 s batch).  Same products and
+ * accumulation order as cum_conv_in_fwd followed by cum_gemm_bias_act_fwd(CUM_MATH_F16X3, CUM_EPI_GLU_SIGMOID).
+ * channels must be 64 (conv outputs == GLU outputs == 64: the shipped channels_H); otherwise CUM_EINVAL -- use the two calls. */
+typedef struct cum_enc0_block_desc {
+    const float* x; long long x_stride; int batch; int length;   /* (batch, length) waveform, already normalised */
+    const float* conv_w;     /* (4, 64) taps-major */
+    const float* conv_b;     /* (64) */
+    const void* glu_w_hi;    /* (128, 64) fp16, rows interleaved (a_c, b_c), scaled: cum_split_f16 */
+    const void* glu_w_lo;    /* low halves (may be NULL when w_lo_is_zero) */
+    const float* glu_b;      /* (128) interleaved */
+    float acc_scale;         /* 1 / weight scale */
+    int w_lo_is_zero;
+    float* out;              /* (batch, rows_out, 64) fp32 channels-last: the level-0 skip */
+    int rows_out;            /* (padded_length - 4) / 2 + 1 */
+    int channels;            /* 64 */
+} cum_enc0_block_desc;
+int cum_enc0_block_fwd(const cum_enc0_block_desc* desc, cum_stream_t stream);
+
+/* Last decoder block as ONE kernel (CleanUMamba.py:121-128 for the last level, crop + de-normalisation of :318-319):
+ *   g[p,:]      = GLU(glu_b + W a[b,p,:])                                  Conv1d(64, 128, 1) + layers.Activation("Sigmoid")
+ *   out[b,2p+k] = (convt_bias + <g[p], convt_w[k]> + <g[p-1], convt_w[k+2]>) * scale[b]     ConvTranspose1d(64, 1, 4, 2), k = 0, 1
+ * for 0 <= 2p+k < out_length (<= 2 rows_in + 2).  Replaces cum_gemm_bias_act_fwd + cum_convt_out_fwd; the gated 64-channel
+ * tensor never reaches HBM. */
+typedef struct cum_dec_last_block_desc {
+    const float* a; int batch; int rows_in;   /* (batch, rows_in, 64) fp32 channels-last (skip already added) */
+    const void* glu_w_hi; const void* glu_w_lo; const float* glu_b; float acc_scale; int w_lo_is_zero;
+    const float* convt_w;    /* (4, 64) taps-major */
+    float convt_bias;
+    const float* scale;      /* (batch) per-clip std, or NULL */
+    float* out; long long out_stride; int out_length;
+    int channels;            /* 64 */
+} cum_dec_last_block_desc;
+int cum_dec_last_block_fwd(const cum_dec_last_block_desc* desc, cum_stream_t stream);
 
 /* ---- Mamba block operators ------------------------------------------------------------------- */
 /* Replaces Block.forward's `residual = h + residual; h = LayerNorm(residual)` (mamba_ssm Block, non-fused

@@ -203,3 +203,71 @@ def test_model_gradients_match_oracle_autograd(name, math, seconds):
             worst = max(worst, err / scale)
             assert err / scale < (2e-3 if math == "fp32" else 5e-3), f"{k}: rel {err / scale:.3e}"
     print(f"\n[{name} {math}] worst per-tensor relative gradient error {worst:.3e}")
+
+
+@pytest.mark.parametrize("math", ["f16x3", "fp32"])
+def test_e8_full_gradients_match_oracle_autograd(math):
+    """gradient parity of the FULL E8 model (41.4 M parameters, seeded random init == reference
+    constructor), B = 1 x 1 s, against autograd through the CPU oracle.  Tolerance: per-tensor max-abs error relative to the
+    tensor's largest gradient entry <= 2e-3 (fp32 kernels) / 5e-3 (f16x3 forward + tf32x3 gradients)."""
+    import os
+    from cleanumamba_b200.network import Net
+    sums = json.load(open(os.path.join(__import__("conftest").GOLDEN, "full_init_seed0_sums.json")))["DNS-CleanUMamba-3N-E8"]
+    torch.manual_seed(0)
+    net = Net("CleanUMamba", dict(sums["config"], math_mode=math))
+    sd = {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items()}
+    net = net.cuda().train()
+    clean, noisy = orc.synth_batch(1, 1.0, seed=41)
+    out_ref = orc.forward(sd, noisy, differentiable=True)
+    loss_ref = F.l1_loss(out_ref, clean) + (out_ref ** 2).mean()
+    loss_ref.backward()
+    out = net(noisy.clone().cuda())
+    loss = F.l1_loss(out, clean.cuda()) + (out ** 2).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
+    worst, worst_k = 0.0, None
+    for k, p in net.named_parameters():
+        gr = sd[k].grad
+        assert p.grad is not None and p.grad.shape == gr.shape, k
+        scale = gr.abs().max().item()
+        if scale > 1e-12:
+            e = (p.grad.cpu() - gr).abs().max().item() / scale
+            if e > worst:
+                worst, worst_k = e, k
+    print(f"\n[E8-full grad {math}] worst per-tensor relative gradient error {worst:.3e} ({worst_k})")
+    assert worst < (2e-3 if math == "fp32" else 5e-3), worst_k
+
+
+def test_gradients_accumulate_over_two_backwards_without_zero_grad():
+    """Gradient accumulation (the reference's pruning loop, src/training/pruning.py:124-127) and ``zero_grad(set_to_none=False)``:
+    no gradient handed to autograd may alias the engine's persistent flat gradient buffer.  Uses a model whose d_model and
+    channel counts are multiples of 8 (no padding is cut away: the case where a ``.contiguous()`` would be a view)."""
+    from cleanumamba_b200.network import Net
+    cfg = dict(channels_input=1, channels_output=1, channels_H=16, max_H=64, encoder_n_layers=3, kernel_size=4, stride=2,
+               tsfm_n_layers=2, tsfm_n_head=4, tsfm_d_model=64, tsfm_d_inner=128, math_mode="fp32")
+    torch.manual_seed(1)
+    net = Net("CleanUMamba", cfg)
+    sd = {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items()}
+    net = net.cuda().train()
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(2, 1, 3000, generator=g) * 0.1, torch.randn(2, 1, 3000, generator=g) * 0.3]
+    for x in xs:            # oracle: two backward passes accumulate into .grad
+        (orc.forward(sd, x, differentiable=True) ** 2).mean().backward()
+    for x in xs:
+        (net(x.clone().cuda()) ** 2).mean().backward()
+    for k, p in net.named_parameters():
+        gr = sd[k].grad
+        scale = gr.abs().max().item()
+        if scale > 1e-12:
+            assert (p.grad.cpu() - gr).abs().max().item() / scale < 2e-3, k
+    # set_to_none=False keeps the .grad tensors: the next backward must add to zeros, not to the engine's buffer
+    net.zero_grad(set_to_none=False)
+    for v in sd.values():
+        v.grad = None
+    (orc.forward(sd, xs[0], differentiable=True) ** 2).mean().backward()
+    (net(xs[0].clone().cuda()) ** 2).mean().backward()
+    for k, p in net.named_parameters():
+        gr = sd[k].grad
+        scale = gr.abs().max().item()
+        if scale > 1e-12:
+            assert (p.grad.cpu() - gr).abs().max().item() / scale < 2e-3, k

@@ -304,3 +304,112 @@ def test_conv_in_hl16_matches_fp32_kernel():
         _lib.check(lib.cum_conv_in_hl16_fwd(x.data_ptr(), L, B, L, w.data_ptr(), bias.data_ptr(), yh[0].data_ptr(), yh[1].data_ptr(),
                                             rows, H, 4, 2, _lib.stream_ptr()), "conv_in_hl16")
         assert torch.equal(yh, ops.split_hl16(y))
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3", "f16x3", "tf32"])
+@pytest.mark.parametrize("gate", ["ReLU", "SiLU", "GELU"])
+def test_gemm_generic_glu_gates_and_unary_silu(gate, math):
+    """CUM_EPI_GLU_{RELU,SILU,GELU} (layers.py:17-24) and the unary CUM_EPI_SILU epilogue against PyTorch in every math mode."""
+    from cleanumamba_b200 import _lib, ops
+    b, cin, cout, l = 2, 96, 144, 333
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(b, cin, l, generator=g)
+    w, bias = torch.randn(cout, cin, generator=g) / cin ** 0.5, torch.randn(cout, generator=g)
+    ref = F.conv1d(x, w[:, :, None], bias)
+    H = cout // 2
+    wi = torch.stack([w[:H], w[H:]], 1).reshape(cout, cin)
+    bi = torch.stack([bias[:H], bias[H:]], 1).reshape(cout)
+    add = torch.randn(b, l, H, generator=g)
+    yg = ops.gemm_bias_act(_cl(x), wi[None].contiguous().to(dev()), bi.to(dev()), _lib.EPI_GLU[gate], addend=add.to(dev()), math=math)
+    refg = orc.glu(ref, gate) + add.permute(0, 2, 1)
+    assert rel_err(yg.permute(0, 2, 1), refg) < GEMM_TOL[math]
+    ys = ops.gemm_bias_act(_cl(x), w[None].contiguous().to(dev()), bias.to(dev()), _lib.EPI_SILU, math=math)
+    assert rel_err(ys.permute(0, 2, 1), F.silu(ref)) < GEMM_TOL[math]
+
+
+def test_library_caches_survive_shutdown():
+    """cum_shutdown() drops the tensor-map cache / per-device kernel attributes; the library keeps working afterwards."""
+    from cleanumamba_b200 import _lib, ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 64, 200, generator=g)
+    w = torch.randn(128, 64, generator=g) / 8
+    want = F.conv1d(x, w[:, :, None])
+    for _ in range(2):
+        y = ops.gemm_bias_act(_cl(x), w[None].contiguous().to(dev()), None, _lib.EPI_NONE, math="f16x3")
+        assert rel_err(y.permute(0, 2, 1), want) < GEMM_TOL["f16x3"]
+        assert _lib.load().cum_shutdown() == 0
+
+
+def _split_f16(w_dev):
+    """fp16 hi / lo halves of 2^k w (k so that max|2^k w| is in [8, 16)) like engine._pack; returns hi, lo, 1 / 2^k."""
+    import math
+    from cleanumamba_b200 import _lib
+    lib = _lib.init(torch.device(dev()))
+    a = w_dev.abs().max().item()
+    e = max(-14, min(14, int(math.floor(math.log2(8.0 / a))))) if a > 0 else 0
+    hi, lo = torch.empty_like(w_dev, dtype=torch.float16), torch.empty_like(w_dev, dtype=torch.float16)
+    _lib.check(lib.cum_split_f16(w_dev.data_ptr(), hi.data_ptr(), lo.data_ptr(), w_dev.numel(), float(2.0 ** e), _lib.stream_ptr()), "split")
+    return hi, lo, float(2.0 ** -e)
+
+
+@pytest.mark.parametrize("b,length", [(1, 200), (2, 4099), (3, 33000), (1, 6)])
+def test_fused_enc0_block(b, length):
+    """cum_enc0_block_fwd == F.pad + Conv1d(1,64,4,2) + ReLU + Conv1d(64,128,1) + GLU (CleanUMamba.py:108-113), ragged lengths."""
+    import ctypes as C
+    from cleanumamba_b200 import _lib
+    lib = _lib.init(torch.device(dev()))
+    g = torch.Generator().manual_seed(length)
+    x = torch.randn(b, 1, length, generator=g)
+    w0, b0 = torch.randn(64, 1, 4, generator=g) * 0.5, torch.randn(64, generator=g) * 0.1
+    w1, b1 = torch.randn(128, 64, generator=g) / 8, torch.randn(128, generator=g) * 0.1
+    padded = max(length, 4) + (max(length, 4) % 2)
+    rows = (padded - 4) // 2 + 1
+    ref = orc.glu(F.conv1d(F.relu(F.conv1d(F.pad(x, (0, padded - length)), w0, b0, stride=2)), w1[:, :, None], b1))      # (b, 64, rows)
+    wi = torch.stack([w1[:64], w1[64:]], 1).reshape(128, 64).contiguous().to(dev())
+    bi = torch.stack([b1[:64], b1[64:]], 1).reshape(128).contiguous().to(dev())
+    hi, lo, inv = _split_f16(wi)
+    xd = x[:, 0].contiguous().to(dev())
+    cw, cb = w0[:, 0, :].t().contiguous().to(dev()), b0.to(dev())
+    out = torch.full((b, rows, 64), float("nan"), device=dev())
+    d = _lib.Enc0BlockDesc()
+    d.x, d.x_stride, d.batch, d.length = xd.data_ptr(), length, b, length
+    d.conv_w, d.conv_b, d.glu_w_hi, d.glu_w_lo, d.glu_b = cw.data_ptr(), cb.data_ptr(), hi.data_ptr(), lo.data_ptr(), bi.data_ptr()
+    d.acc_scale, d.w_lo_is_zero, d.out, d.rows_out, d.channels = inv, 0, out.data_ptr(), rows, 64
+    _lib.check(lib.cum_enc0_block_fwd(C.byref(d), _lib.stream_ptr()), "enc0_block")
+    torch.cuda.synchronize()
+    assert rel_err(out.permute(0, 2, 1), ref) < GEMM_TOL["f16x3"]
+    d.channels = 56
+    assert lib.cum_enc0_block_fwd(C.byref(d), _lib.stream_ptr()) != 0      # only the 64-channel geometry is served
+
+
+@pytest.mark.parametrize("b,rows,crop", [(1, 100, 0), (2, 2047, 130), (3, 16500, 0), (1, 1, 1)])
+def test_fused_dec_last_block(b, rows, crop):
+    """cum_dec_last_block_fwd == Conv1d(64,128,1) + GLU + ConvTranspose1d(64,1,4,2) + crop + * std (CleanUMamba.py:121-128, :318-319)."""
+    import ctypes as C
+    from cleanumamba_b200 import _lib
+    lib = _lib.init(torch.device(dev()))
+    g = torch.Generator().manual_seed(rows)
+    a = torch.randn(b, 64, rows, generator=g)
+    w1, b1 = torch.randn(128, 64, generator=g) / 8, torch.randn(128, generator=g) * 0.1
+    wt, bt = torch.randn(64, 1, 4, generator=g) / 8, torch.randn(1, generator=g) * 0.1
+    std = torch.rand(b, generator=g) + 0.5
+    full = F.conv_transpose1d(orc.glu(F.conv1d(a, w1[:, :, None], b1)), wt, bt, stride=2)      # (b, 1, 2 rows + 2)
+    length = 2 * rows + 2 - crop
+    ref = full[:, :, :length] * std[:, None, None]
+    wi = torch.stack([w1[:64], w1[64:]], 1).reshape(128, 64).contiguous().to(dev())
+    bi = torch.stack([b1[:64], b1[64:]], 1).reshape(128).contiguous().to(dev())
+    hi, lo, inv = _split_f16(wi)
+    acl = _cl(a)
+    tw = wt[:, 0, :].t().contiguous().to(dev())
+    out = torch.full((b, 1, length), float("nan"), device=dev())
+    d = _lib.DecLastBlockDesc()
+    d.a, d.batch, d.rows_in = acl.data_ptr(), b, rows
+    d.glu_w_hi, d.glu_w_lo, d.glu_b, d.acc_scale, d.w_lo_is_zero = hi.data_ptr(), lo.data_ptr(), bi.data_ptr(), inv, 0
+    d.convt_w, d.convt_bias, d.scale = tw.data_ptr(), float(bt[0]), std.to(dev()).data_ptr()
+    sd = std.to(dev())
+    d.scale = sd.data_ptr()
+    d.out, d.out_stride, d.out_length, d.channels = out.data_ptr(), length, length, 64
+    _lib.check(lib.cum_dec_last_block_fwd(C.byref(d), _lib.stream_ptr()), "dec_last_block")
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    assert rel_err(out, ref) < GEMM_TOL["f16x3"]

@@ -208,3 +208,67 @@ def test_stream_edge_cases_empty_and_tiny_feeds():
         sess.feed(torch.zeros(2, 5, device="cuda"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         sess.feed(torch.zeros(1, 5))
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("math", ["f16x3", "fp32"])
+def test_e6_high_full_size_streaming_matches_stream_oracle(math, normalize):
+    """BASELINE configs[2]'s model -- E6 high FULL size (27.2 M, d_inner 2048, d_state 64; seeded random init == reference
+    constructor) -- 2 streams, multi-hop chunks (batch-mode GEMMs with >= 128 rows per stream, chunked scan) and single-hop
+    chunks (flattened GEMMs, state-update scan at d = 2048), against one StreamOracle per stream in both std modes."""
+    from cleanumamba_b200.network import Net
+    import os
+    sums = json.load(open(os.path.join(__import__("conftest").GOLDEN, "full_init_seed0_sums.json")))["DNS-CleanUMamba-3N-E6"]
+    torch.manual_seed(0)
+    net = Net("CleanUMamba", dict(sums["config"], math_mode=math, normalize_input=normalize))
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda().eval()
+    B, hop = 2, net.total_stride
+    assert hop == 64 and net.frame_length == 190
+    sizes = [190 + hop * 39, hop] + [hop] * 5 + [hop * 4, hop * 40, hop, hop * 2, 37, hop - 37]
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(B, sum(sizes), generator=g) * 0.1 * (1 + torch.arange(B)[:, None])
+    sess = net.stream_session(batch=B)
+    outs, pos = [], 0
+    for n in sizes:
+        outs.append(sess.feed(x[:, pos:pos + n].cuda()))
+        pos += n
+    outs.append(sess.flush())
+    got = torch.cat(outs, 1).cpu()
+    worst = 0.0
+    for b in range(B):
+        so = orc.StreamOracle(sd, normalize_input=normalize)
+        want = torch.cat([so.feed(x[b:b + 1]), so.flush()], 1)
+        assert got[b:b + 1].shape == want.shape
+        worst = max(worst, (got[b:b + 1] - want).abs().max().item())
+    print(f"\n[E6-high full streaming {math} normalize={normalize}] max-abs vs StreamOracle {worst:.3e}")
+    assert worst <= 1e-4
+
+
+def test_stream_session_follows_weight_updates_and_frame_reset():
+    """A session that already streamed (and captured a graph) must see new parameter values (load_state_dict / optimiser step
+    repack the weights: stale graphs are dropped), and ``reset_time_per_frame`` restarts the running input std like the
+    reference (:326-328, :399-401)."""
+    fx = load_golden("e6_pruned_200k")
+    net = build(fx, normalize_input=True)
+    hop = 64
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(1, 190 + hop * 12, generator=g) * 0.1
+    net.feed(x[:, :190].cuda())
+    for k in range(6):          # identical whole-hop chunks: auto graph capture kicks in
+        net.feed(x[:, 190 + hop * k: 190 + hop * (k + 1)].cuda())
+    assert net._stream._graph is not None
+    sd2 = {k: (v * 1.01 if v.dtype.is_floating_point else v) for k, v in fx["state_dict"].items()}
+    net.load_state_dict(sd2)
+    net.reset_time_per_frame()
+    assert net._stream.frames == 0
+    got = net.feed(x[:, 190 + hop * 6: 190 + hop * 7].cuda()).cpu()
+    assert net._stream._graph is None or net._stream._pack_gen == net.engine().pack_generation
+    # oracle: same history with the old weights, then the new weights + restarted running std for the last hop
+    so = orc.StreamOracle(fx["state_dict"], normalize_input=True)
+    so.feed(x[:, : 190 + hop * 6])
+    so.sd = {k: v.float() for k, v in sd2.items()}
+    so.frames = 0
+    want = so.feed(x[:, 190 + hop * 6: 190 + hop * 7])
+    assert got.shape == want.shape == (1, hop)
+    assert (got - want).abs().max().item() < TOL
