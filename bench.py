@@ -12,8 +12,14 @@ sharding, no data-path collective -> weak scaling).
 
 Own arm     : the product (cleanumamba_b200 -> libcleanumamba_sm100.so).  `value` = inputs resident in HBM, CUDA-event
               timed, max over ranks; `e2e` = same call with pinned HOST buffers, H2D + forward + D2H inside the timing.
-Reference arm (--impl reference): the reference's CPU path (oracle port of CleanUMamba.forward + selective_scan_ref,
-              oracle/cleanumamba_oracle.py) on all host cores, each step a bounded sample (2 clips) of the same workload.
+Reference arm (--impl reference): the reference's own CPU implementation of the path on all host cores, each step a bounded
+              sample (1 clip) of the same workload: the UNMODIFIED reference files (src/network/CleanUMamba.py ... staged
+              byte-for-byte into the git-ignored baseline/_ref/ by build(), imported through oracle/ref_loader.py on the
+              mamba_ssm stand-in oracle/ref_shim: selective_scan_ref) -> kind "reference"; the oracle port
+              (oracle/cleanumamba_oracle.py) is timed beside it (`port`) and is the fallback when baseline/_ref is absent.
+Extras      : the default line also carries `train` (configs[3]: DP training step, NCCL gradient all-reduce at N > 1, exposed
+              all-reduce time) and `stream` (configs[2]: 4096 streams in total, sharded over the ranks) sub-records, so the
+              driver's 1/2/4/8-GPU scaling run measures the collective path too (--no-extras skips them).
 """
 import argparse
 import json
@@ -115,52 +121,93 @@ def workload_name(args):
             f"batch {args.batch} x {args.seconds:g} s @16 kHz per GPU")
 
 
-CPU_SAMPLE_CLIPS = 2      # clips per CPU step (selective_scan_ref materialises 0.67 GB per 10 s clip at E8)
+CPU_SAMPLE_CLIPS = 1      # clips per CPU step (the reference's selective_scan_ref materialises 0.67 GB per 10 s clip at E8)
 
 
-def cpu_reference_pass(cfg, seconds, steps, warmup, threads, clips=CPU_SAMPLE_CLIPS):
-    """Times the oracle port of the reference's CPU path; returns (audio_s_per_s, ms_per_step, sample description)."""
+def shared_config(args, world):
+    """`config` of the bench line -- identical for the product arm and the reference arm (same workload; the CPU arm times a
+    bounded sample of it per step, described in its cpu_baseline.sample)."""
+    return {"workload": workload_name(args), "math": args.math, "global_batch": world * args.batch, "clip_seconds": args.seconds,
+            "parallelism": f"utterance-sharded x{world}",
+            "l2": "inputs+activations per step (>25 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+def _reference_net(cfg):
+    """The UNMODIFIED reference module (staged copy under baseline/_ref or the /root/reference mount) on the mamba_ssm shim, or
+    None when neither is present.  Checker / baseline only: nothing of the product imports this."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import cleanumamba_oracle as orc
-    from cleanumamba_b200.network import Net
+    try:
+        import ref_loader
+        if not ref_loader.reference_available():
+            return None
+        refnet = ref_loader.import_reference()
+        torch.manual_seed(0)
+        return refnet.Net("CleanUMamba", dict(cfg)).float().eval()
+    except Exception as exc:      # noqa: BLE001 -- the port remains as the baseline; say why
+        print(f"# unmodified reference unavailable: {exc!r}", file=sys.stderr)
+        return None
+
+
+def cpu_reference_pass(cfg, seconds, steps, warmup, threads, clips=CPU_SAMPLE_CLIPS, impl="port"):
+    """Times the reference's CPU path on `clips` clips per step; impl = "reference" (unmodified reference files through
+    selective_scan_ref) or "port" (oracle/cleanumamba_oracle.py).  Returns (audio_s_per_s, ms_per_step, sample) or None."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    sd = {k: v.clone() for k, v in Net("CleanUMamba", dict(cfg)).state_dict().items()}
     x = synth_noisy(clips, seconds, 1234)
+    if impl == "reference":
+        net = _reference_net(cfg)
+        if net is None:
+            return None
+        fwd = lambda: net(x.clone())          # noqa: E731  (the reference normalises its input in place)
+    else:
+        import cleanumamba_oracle as orc
+        from cleanumamba_b200.network import Net
+        torch.manual_seed(0)
+        sd = {k: v.clone() for k, v in Net("CleanUMamba", dict(cfg)).state_dict().items()}
+        fwd = lambda: orc.forward(sd, x.clone())          # noqa: E731
     with torch.no_grad():
         for _ in range(warmup):
-            orc.forward(sd, x.clone())
+            fwd()
         t0 = time.perf_counter()
         for _ in range(steps):
-            orc.forward(sd, x.clone())
+            fwd()
         dt = (time.perf_counter() - t0) / steps
     return (clips * seconds / dt, dt * 1e3,
-            f"{clips} clips x {seconds:g} s per step (of the batch), {steps} steps after {warmup} warm-up, fp32, {threads} threads")
+            f"{clips} clip(s) x {seconds:g} s per step (of the batch), {steps} steps after {warmup} warm-up, fp32, {threads} threads")
 
 
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))      # ~0.7 s per step: the run stays well under a minute
-    val, ms, sample = cpu_reference_pass(cfg, args.seconds, steps, warmup, threads)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)       # same K / W as the product arm; one clip per step keeps it to minutes
+    kind, res = "reference", cpu_reference_pass(cfg, args.seconds, steps, warmup, threads, impl="reference")
+    port = cpu_reference_pass(cfg, args.seconds, min(steps, 5), 1, threads, impl="port")
+    if res is None:
+        kind, res = "port", cpu_reference_pass(cfg, args.seconds, steps, warmup, threads, impl="port")
+    val, ms, sample = res
+    path = ("the reference's own files (src/network/CleanUMamba.py, layers.py, network.py, src/util/util.py: staged unmodified in "
+            "baseline/_ref) on CPU through mamba_ssm's selective_scan_ref path (oracle/ref_shim stand-in for the absent wheel), all host cores"
+            if kind == "reference" else
+            "oracle port of CleanUMamba.forward + mamba_ssm selective_scan_ref (oracle/cleanumamba_oracle.py), all host cores "
+            "(baseline/_ref not staged on this box)")
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "sample": sample,
-                       "path": "reference CPU path: oracle port of CleanUMamba.forward + mamba_ssm selective_scan_ref "
-                               "(oracle/cleanumamba_oracle.py), all host cores"},
-            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": shared_config(args, max(1, args.gpus)),
+            "reference_path": path,
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                             "port": {"value": round(port[0], 3), "unit": UNIT, "sample": port[2]} if port else None},
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def run_stream(args, net, eng, dev, rank, world, dist):
-    """configs[2]: `streams` concurrent streams per GPU, `hops` hops per feed() call, carried conv/SSM state.
-    A step = one feed() call over all streams; value = streamed audio-seconds per wall-second."""
-    S, H, hop = args.streams, args.hops, net.total_stride
+def measure_stream(net, eng, dev, rank, world, dist, S, H, steps, warmup, graph=False, math="f16x3", model="e6", total=None):
+    """configs[2]: S concurrent streams on this GPU, H hops per feed() call, carried conv/SSM state.  A step = one feed() call
+    over all streams; value = streamed audio-seconds per wall-second over all ranks.  Returns the record (every rank)."""
+    hop = net.total_stride
     g = torch.Generator().manual_seed(4321 + rank)
     n_chunk = H * hop
     host_chunk = (torch.randn(S, n_chunk, generator=g) * 0.1).pin_memory()
@@ -174,71 +221,88 @@ def run_stream(args, net, eng, dev, rank, world, dist):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         out = sess.feed(chunk)
         assert out.shape == (S, n_chunk), out.shape
-    if args.graph:          # steady-state CUDA graph of feed(): one replay per step instead of ~260 launches + Python glue
+    launches_per_replay = 0
+    if graph:          # steady-state CUDA graph of feed(): one replay per step instead of ~260 launches + Python glue
         eng.launches = 0
         sess.capture_graph(n_chunk)
         launches_per_replay = eng.launches // 2          # capture_graph runs the step twice (eager rehearsal + capture)
         for _ in range(2):
             sess.feed(chunk)
     barrier()
-    eng.prof, eng.launches = (None if args.graph else []), 0
+    eng.prof, eng.launches = (None if graph else []), 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         sess.feed(chunk)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches, prof = (launches_per_replay * args.steps if args.graph else eng.launches), eng.profile_summary()
+    launches, prof = (launches_per_replay * steps if graph else eng.launches), eng.profile_summary()
     eng.prof = None
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dchunk = torch.empty_like(chunk)
     f0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         dchunk.copy_(host_chunk, non_blocking=True)
         host_out.copy_(sess.feed(dchunk), non_blocking=True)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    n_streams = S
     if dist is not None:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+        from cleanumamba_b200.shard import max_over_ranks
+        ms, ms_e2e = max_over_ranks(ms, dev), max_over_ranks(ms_e2e, dev)
+        t = torch.tensor([S], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        n_streams = int(t.item())
+    audio = n_streams * n_chunk / SR * steps
+    kernels = {k: {"ms_per_step": round(v["ms"] / steps, 3), "launches_per_step": v["launches"] // steps}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    del sess
+    return {"metric": METRIC + " [streaming]", "value": round(audio / (ms / 1e3), 1), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 3),
+            "higher_is_better": True, "scaling": "strong" if total else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"CleanUMamba {model.upper()} streaming, {n_streams} streams in total ({S} on rank 0), {H} hops "
+                                   f"({n_chunk} samples, {1e3 * n_chunk / SR:.0f} ms) per feed(), carried conv/SSM state, "
+                                   f"math={math}" + (", CUDA-graph replay" if graph else ""),
+                       "streams_total": n_streams, "streams_per_gpu": S,
+                       "real_time_factor_per_stream": round(n_chunk / SR / (ms / steps / 1e3), 2),
+                       "chunk_latency_ms": round(ms / steps, 3)},
+            "e2e": {"value": round(audio / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": S * n_chunk * 4,
+                    "d2h_bytes_per_step": S * n_chunk * 4},
+            "gpu_launches": launches, "kernels": kernels}
+
+
+def run_stream(args, net, eng, dev, rank, world, dist):
+    from cleanumamba_b200.shard import shard_bounds
+    S = args.streams
+    if args.streams_total:          # configs[2] as specified: a FIXED total, sharded over the ranks (strong scaling)
+        lo, hi = shard_bounds(args.streams_total, rank, world)
+        S = hi - lo
+    rec = measure_stream(net, eng, dev, rank, world, dist, S, args.hops, args.steps, args.warmup, graph=args.graph, math=args.math,
+                         model=args.model, total=args.streams_total)
     if rank == 0:
-        audio = world * S * n_chunk / SR * args.steps
-        kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] // args.steps}
-                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-        print(json.dumps({"metric": METRIC + " [streaming]", "value": round(audio / (ms / 1e3), 1), "unit": UNIT, "n_gpus": world,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": f"CleanUMamba {args.model.upper()} streaming, {S} streams per GPU, {H} hops "
-                                                 f"({n_chunk} samples, {1e3 * n_chunk / SR:.0f} ms) per feed(), carried conv/SSM state, "
-                                                 f"math={args.math}" + (", CUDA-graph replay" if args.graph else ""), "real_time_factor_per_stream": round(n_chunk / SR / (ms / args.steps / 1e3), 2),
-                                     "chunk_latency_ms": round(ms / args.steps, 3)},
-                          "e2e": {"value": round(audio / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": S * n_chunk * 4,
-                                  "d2h_bytes_per_step": S * n_chunk * 4},
-                          "gpu_launches": launches, "kernels": kernels}), flush=True)
+        print(json.dumps(rec), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def run_train(args, net, dev, rank, world, dist):
+def measure_train(net, dev, rank, world, dist, B, seconds, steps, warmup, math="f16x3", model="e8"):
     """configs[3]: E8-full training step (fwd + L1 + multi-resolution STFT loss + bwd + fused Adam), per-GPU batch fixed
-    (weak scaling), gradients averaged with the bucketed NCCL all-reduce overlapped with the backward."""
+    (weak scaling), gradients averaged with the bucketed NCCL all-reduce overlapped with the backward.  At N > 1 the step is
+    also timed WITHOUT the all-reduce and the compute stream's stall on NCCL is measured with CUDA events (exposed time)."""
     from cleanumamba_b200.distributed import apply_gradient_allreduce
     from cleanumamba_b200.loss import DEFAULT_STFT_CONFIG, MultiResolutionSTFTLoss, loss_fn
-    B = args.batch if args.batch != 64 else 16
-    T = int(args.seconds * SR)
     net.train()
     if dist is not None:
         apply_gradient_allreduce(net)
     opt = torch.optim.Adam(net.parameters(), lr=2e-4, fused=True)
     mr = MultiResolutionSTFTLoss(**DEFAULT_STFT_CONFIG).to(dev)
-    noisy = synth_noisy(B, args.seconds, 1234 + rank).to(dev)
-    clean = synth_noisy(B, args.seconds, 99 + rank).to(dev) * 0.5
+    noisy = synth_noisy(B, seconds, 1234 + rank).to(dev)
+    clean = synth_noisy(B, seconds, 99 + rank).to(dev) * 0.5
     work = torch.empty_like(noisy)
     eng = net.train_engine()
 
@@ -255,39 +319,66 @@ def run_train(args, net, dev, rank, world, dist):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    def timed(n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss = step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            from cleanumamba_b200.shard import max_over_ranks
+            ms = max_over_ranks(ms, dev)
+        return ms, loss
+
+    for _ in range(warmup):
         loss = step()
-    barrier()
+    sync = getattr(net, "_grad_sync", None)
+    if sync is not None:
+        torch.cuda.synchronize()
+        sync.exposed_ms()
     eng.prof, eng.launches = [], 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, loss = timed(steps)
     launches, prof = eng.launches, eng.profile_summary()
     eng.prof = None
-    if dist is not None:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+    allreduce = None
+    if sync is not None:
+        exposed = sync.exposed_ms()
+        buckets = list(sync.bucket_bytes)
+        net._grad_sync = None                      # same step, no collective: what the all-reduce costs end to end
+        ms_local, _ = timed(max(2, steps // 2))
+        ms_local /= max(2, steps // 2)
+        net._grad_sync = sync
+        allreduce = {"bytes": sum(buckets), "buckets": dict(zip(("decoder", "bottleneck", "encoder"), buckets)), "overlapped": True,
+                     "ms_per_step_without_allreduce": round(ms_local, 3),
+                     "exposed_ms_per_step": round(ms / steps - ms_local, 3),
+                     "stream_stall_on_nccl_ms_per_step": round(exposed, 3),
+                     "limiting_bucket": "encoder (the last one the backward completes: nothing is left to hide it behind)"}
+    kernels = {k: {"ms_per_step": round(v["ms"] / steps, 3), "launches_per_step": v["launches"] // steps,
+                   "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] and v["ms"] else None}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    kernel_ms = sum(v["ms"] for v in prof.values()) / steps
+    rec = {"metric": METRIC.replace("denoised", "trained on") + " [training step]",
+           "value": round(world * B * seconds * steps / (ms / 1e3), 1), "unit": UNIT, "n_gpus": world,
+           "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"CleanUMamba {model.upper()} full training step: fwd + L1 + MR-STFT loss "
+                                  f"+ bwd + fused Adam (PyTorch), batch {B} x {seconds:g} s per GPU, math={math}",
+                      "global_batch": world * B, "parallelism": f"dp{world}",
+                      "grad_allreduce": allreduce,
+                      "our_kernels_ms_per_step": round(kernel_ms, 3), "final_loss": round(float(loss), 5)},
+           "gpu_launches": launches, "kernels": kernels}
+    del opt, mr, noisy, clean, work
+    return rec
+
+
+def run_train(args, net, dev, rank, world, dist):
+    B = args.batch if args.batch != 64 else 16
+    rec = measure_train(net, dev, rank, world, dist, B, args.seconds, args.steps, args.warmup, math=args.math, model=args.model)
     if rank == 0:
-        kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] // args.steps,
-                       "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] and v["ms"] else None}
-                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-        kernel_ms = sum(v["ms"] for v in prof.values()) / args.steps
-        grad_bytes = sum(p.numel() for p in net.parameters()) * 4
-        print(json.dumps({"metric": METRIC.replace("denoised", "trained on") + " [training step]",
-                          "value": round(world * B * args.seconds * args.steps / (ms / 1e3), 1), "unit": UNIT, "n_gpus": world,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": f"CleanUMamba {args.model.upper()} full training step: fwd + L1 + MR-STFT loss (PyTorch) "
-                                                 f"+ bwd + fused Adam (PyTorch), batch {B} x {args.seconds:g} s per GPU, math={args.math}",
-                                     "global_batch": world * B, "parallelism": f"dp{world}",
-                                     "grad_allreduce": {"bytes": grad_bytes, "buckets": 3, "overlapped": True} if world > 1 else None,
-                                     "our_kernels_ms_per_step": round(kernel_ms, 3), "final_loss": round(float(loss), 5)},
-                          "gpu_launches": launches, "kernels": kernels}), flush=True)
+        print(json.dumps(rec), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -367,6 +458,8 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="[stream] concurrent streams per GPU")
     ap.add_argument("--hops", type=int, default=16, help="[stream] hops (2^D samples each) per feed() call")
     ap.add_argument("--graph", action="store_true", help="[stream] replay a captured CUDA graph of the steady-state feed()")
+    ap.add_argument("--streams-total", type=int, default=0, help="[stream] total streams, sharded over the ranks (overrides --streams)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `train` / `stream` sub-records of the default line")
     args = ap.parse_args()
     cfg = CONFIGS[args.model]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -459,6 +552,32 @@ def main():
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
+    # ---- extras (every rank takes part): the collective path and the streaming configuration under the same clock ----------
+    extras = {}
+    if not args.no_extras and args.model == "e8" and args.math == "f16x3":
+        del pipe, work
+        eng._graphs.clear()
+        torch.cuda.empty_cache()
+        from cleanumamba_b200.shard import shard_bounds
+        try:
+            torch.manual_seed(0)
+            net_t = Net("CleanUMamba", dict(cfg, math_mode=args.math)).to(dev)
+            extras["train"] = measure_train(net_t, dev, rank, world, dist, 16, args.seconds, max(3, min(args.steps, 10)), 3, math=args.math)
+            del net_t
+        except Exception as exc:      # noqa: BLE001 -- the headline line must still be printed; the failure is reported in place
+            extras["train"] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+        try:
+            torch.manual_seed(0)
+            net_s = Net("CleanUMamba", dict(CONFIGS["e6"], math_mode=args.math)).to(dev).eval()
+            lo, hi = shard_bounds(4096, rank, world)
+            extras["stream"] = {f"hops{h}": measure_stream(net_s, net_s.engine(), dev, rank, world, dist, hi - lo, h,
+                                                            max(3, min(args.steps, 10)), 3, math=args.math, total=4096)
+                                for h in (16, 1)}
+            del net_s
+        except Exception as exc:      # noqa: BLE001
+            extras["stream"] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -472,21 +591,25 @@ def main():
     # roofline of the dominant kernel family (the tap-GEMM: all convs + projections), timed with CUDA events inside
     # the timed region; `peak` is the measured dense bf16 tensor throughput (sustained: timed inside a long step)
     gem = {"ms": 0.0, "launches": 0, "flops": 0}
-    for k in ("gemm", "gemm_tap2"):
+    for k in ("gemm", "gemm_tap2", "enc0_block", "dec_last_block", "enc_block", "dec_block"):
         if k in prof:
             for f in gem:
                 gem[f] += prof[k][f]
     total_kernel_ms = sum(v["ms"] for v in prof.values())
     achieved = gem["flops"] / (gem["ms"] / 1e3) / 1e12 if gem["ms"] else 0.0
-    traffic = None       # dram__bytes of the 44 GEMM launches of one step, from the committed ncu capture of this workload
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic_f16x3.json")
+    # dram__bytes of the tensor-core launches of one step: from the committed ncu capture of THIS workload and kernel set
+    # (profiles/r02_gemm_traffic_f16x3.json, written by tools/launch_table.py from the ncu launch list), null for any other config
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic_f16x3.json")
     if os.path.exists(tpath) and args.math == "f16x3" and B == 64 and args.seconds == 10.0 and args.model == "e8":
-        traffic = json.load(open(tpath))["dram_bytes_per_step_gemm_launches"]
+        tj = json.load(open(tpath))
+        if tj.get("launches_per_step") == gem["launches"] // max(1, args.steps):
+            traffic = tj["dram_bytes_per_step_gemm_launches"]
+            traffic_note = tj.get("note")
     roofline = {"kernel": "tap-GEMM (conv/convT/1x1/projection contractions, %s)" % args.math, "bound": "tensor",
                 "achieved": round(achieved, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic,
-                "traffic_note": "bytes per STEP over the 44 launches of this kernel family (ncu dram__bytes, profiles/r01_final_launches_f16x3.md); "
-                                "algorithmic activation traffic is 64-66 GB, i.e. no re-reads" if traffic else None,
+                "traffic_note": traffic_note,
                 "peak_source": pk["src"] + " bf16 sustained",
                 "share_of_step": round(gem["ms"] / total_kernel_ms, 4) if total_kernel_ms else None,
                 "launches_per_step": gem["launches"] // args.steps,
@@ -497,8 +620,7 @@ def main():
                          "rate is 3x achieved; ncu sm__pipe_tensor_cycles_active = 70-76 % on the K>=1024 layers "
                          "(profiles/r01_ncu_full_gemm_tf32x3.md)") if args.math == "tf32x3" else
                         ("achieved = ALGORITHMIC flops / CUDA-event kernel time; the split modes issue 3 kind::f16 MMAs per product, so the "
-                         "tensor-pipe work rate is 3x achieved (mma_work_tflops); ncu: K>=1024 layers 81-94 % tensor-pipe active, "
-                         "the 64/128-channel layers are bound by store wavefronts / HBM (profiles/r01_final_launches_f16x3.md)")
+                         "tensor-pipe work rate is 3x achieved (mma_work_tflops); per-launch ncu numbers: profiles/r02_launches_f16x3.md")
                         if args.math in ("bf16x3", "f16x3") else None,
                 "mma_work_tflops": round(achieved * (3 if args.math in ("tf32x3", "bf16x3", "f16x3") else 1), 1)}
     scan = prof.get("selective_scan")
@@ -549,8 +671,12 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, _, sample = cpu_reference_pass(cfg, args.seconds, 16, 1, threads)      # ~12 s of CPU work
-        cpu = {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        # ~10-20 s of CPU work: the unmodified reference (staged in baseline/_ref) when present, the oracle port beside it
+        ref = cpu_reference_pass(cfg, args.seconds, 5, 1, threads, impl="reference")
+        port = cpu_reference_pass(cfg, args.seconds, 8, 1, threads, impl="port")
+        v, _, sample = ref if ref else port
+        cpu = {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "reference" if ref else "port", "sample": sample,
+               "port": {"value": round(port[0], 3), "unit": UNIT, "sample": port[2]}}
 
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
@@ -565,9 +691,7 @@ def main():
                            "bf16": "REDUCED PRECISION variant (reported separately, outside the fp32 tolerance): bf16 activation storage and "
                                    "single-pass bf16 tensor-core products in the encoder / decoder stacks, fp32 accumulate",
                            "tf32": "single TF32 pass (outside the tolerance)"}[args.math],
-            "config": {"workload": workload_name(args), "math": args.math,
-                       "global_batch": world * B, "clip_seconds": args.seconds, "parallelism": f"utterance-sharded x{world}",
-                       "l2": "inputs+activations per step (>25 GB) exceed the 126 MB L2; no explicit flush"},
+            "config": shared_config(args, world),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": B * T * 4,
                     "d2h_bytes_per_step": B * T * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "scan_roofline": scan_roof,
@@ -576,6 +700,7 @@ def main():
         line["variants"] = variants
     if cpu:
         line["cpu_baseline"] = cpu
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

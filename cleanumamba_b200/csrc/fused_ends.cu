@@ -26,15 +26,19 @@ namespace cum {
 constexpr int FE_ROWS = 128;                    // rows per tile (MMA M)
 constexpr int FE_K = 64;                        // channels in (MMA K: one 128-byte swizzle row of fp16)
 constexpr int FE_N = 128;                       // GLU GEMM columns (interleaved a_c, b_c)
-constexpr int FE_THREADS = 512;                 // warp 0: MMA + TMEM; warp 1: weight TMA; warps 4-11: epilogue; warps 12-15: A generators
+// warp 0: MMA + TMEM; warp 1: TMA (weights, dec_last input tiles); warps 4-7 / 8-11: epilogue set 0 / 1 (alternating tiles);
+// warps 12-19: A generators.  Every stage of a tile is latency-bound on its own (TMEM load -> gate -> staging -> store), so
+// the throughput comes from running two epilogue sets and a double-buffered generator concurrently, not from wider warps.
+constexpr int FE_THREADS = 640;
+constexpr int FE_GEN_WARP0 = 12, FE_GEN_THREADS = 256;
 constexpr uint32_t FE_W_BYTES = FE_N * FE_K * 2;          // 16 KB per weight half
 constexpr uint32_t FE_A_BYTES = FE_ROWS * FE_K * 2;       // 16 KB per activation half
-constexpr uint32_t FE_OUT_BYTES = FE_ROWS * 64 * 4;       // 32 KB fp32 staging tile (two 128-byte-swizzled halves of 32 channels)
+constexpr uint32_t FE_OUT_BYTES = FE_ROWS * 64 * 4;       // 32 KB fp32 tile: enc0 staging per epilogue set / dec_last raw input per buffer
 constexpr uint32_t FE_OFF_W = 0;
 constexpr uint32_t FE_OFF_A = 2 * FE_W_BYTES;                          // [buf][hi | lo]
 constexpr uint32_t FE_OFF_OUT = FE_OFF_A + 2 * 2 * FE_A_BYTES;         // [buf]
-constexpr uint32_t FE_OFF_SMALL = FE_OFF_OUT + 2 * FE_OUT_BYTES;       // bias (128 f) | taps (64 x float4) | b0 (64 f) | part (2 x 2 x 128 float4)
-constexpr uint32_t FE_SMALL_BYTES = 512 + 1024 + 256 + 2 * 2 * 128 * 16;
+constexpr uint32_t FE_OFF_SMALL = FE_OFF_OUT + 2 * FE_OUT_BYTES;       // bias (128 f) | taps (64 x float4) | b0 (64 f) | part (2 x 128 float4)
+constexpr uint32_t FE_SMALL_BYTES = 512 + 1024 + 256 + 2 * 128 * 16;
 constexpr uint32_t FE_OFF_BAR = FE_OFF_SMALL + FE_SMALL_BYTES;
 constexpr uint32_t FE_SMEM_BYTES = FE_OFF_BAR + 128 + 1024 /*align slack*/;
 constexpr uint32_t FE_TMEM_COLS = 256;          // 2 x 128 accumulator columns
@@ -49,7 +53,6 @@ struct FusedEndParams {
     const float* bias;          // (128) interleaved GLU bias
     float acc_scale;            // 2^-k undoing the fp16 weight pre-scale
     int skip_wlo;               // low weight half is exactly zero: two MMA passes
-    const float* a;             // dec_last: (B, rows, 64) fp32 input
     float out_bias; const float* scale; float* out; long long out_stride; int out_length;
 };
 
@@ -59,7 +62,21 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void set_bar(int set) { asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory"); }
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // fp32 x8 -> fp16 hi (saturating) and lo halves, packed for one 16-byte chunk of a K-major operand row
 __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
@@ -78,29 +95,33 @@ __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
 template <int KIND>
 __global__ void __launch_bounds__(FE_THREADS, 1)
 fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
-                 const __grid_constant__ CUtensorMap tmOut, const FusedEndParams p) {
+                 const __grid_constant__ CUtensorMap tmIO, const FusedEndParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     float* bias_s = reinterpret_cast<float*>(smem_gen + FE_OFF_SMALL);
     float4* taps_s = reinterpret_cast<float4*>(smem_gen + FE_OFF_SMALL + 512);
     float* b0_s = reinterpret_cast<float*>(smem_gen + FE_OFF_SMALL + 512 + 1024);
-    float4* part_s = reinterpret_cast<float4*>(smem_gen + FE_OFF_SMALL + 512 + 1024 + 256);      // [buf][grp][row]
+    float4* part_s = reinterpret_cast<float4*>(smem_gen + FE_OFF_SMALL + 512 + 1024 + 256);      // [set][row]
     const uint32_t bar_base = smem_base + FE_OFF_BAR;
     auto a_full = [&](int b) { return bar_base + 8u * b; };
     auto a_empty = [&](int b) { return bar_base + 8u * (2 + b); };
     auto acc_full = [&](int b) { return bar_base + 8u * (4 + b); };
     auto acc_empty = [&](int b) { return bar_base + 8u * (6 + b); };
-    const uint32_t w_full = bar_base + 64;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + FE_OFF_BAR + 80);
+    auto raw_full = [&](int b) { return bar_base + 8u * (8 + b); };
+    auto raw_empty = [&](int b) { return bar_base + 8u * (10 + b); };
+    const uint32_t w_full = bar_base + 96;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + FE_OFF_BAR + 112);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) {
-            mbar_init(a_full(b), 128);
+            mbar_init(a_full(b), FE_GEN_THREADS);
             mbar_init(a_empty(b), 1);
             mbar_init(acc_full(b), 1);
-            mbar_init(acc_empty(b), 8);
+            mbar_init(acc_empty(b), 4);
+            mbar_init(raw_full(b), 1);
+            mbar_init(raw_empty(b), FE_GEN_THREADS);
         }
         mbar_init(w_full, 1);
         fence_barrier_init();
@@ -128,11 +149,26 @@ fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
     };
 
     if (warp == 1 && lane == 0) {
-        // ===================================================================== weights: once per CTA
+        // ===================================================================== TMA: weights once, dec_last input tiles two ahead
         tma_prefetch_desc(&tmWh);
         mbar_arrive_expect_tx(w_full, p.skip_wlo ? FE_W_BYTES : 2 * FE_W_BYTES);
         tma_load_3d(smem_base + FE_OFF_W, &tmWh, w_full, 0, 0, 0);
         if (!p.skip_wlo) tma_load_3d(smem_base + FE_OFF_W + FE_W_BYTES, &tmWl, w_full, 0, 0, 0);
+        if (KIND == 1) {
+            tma_prefetch_desc(&tmIO);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                int b, m0;
+                tile_coords(tile, b, m0);
+                mbar_wait(raw_empty(buf), ((it >> 1) & 1) ^ 1u);
+                mbar_arrive_expect_tx(raw_full(buf), FE_OUT_BYTES);
+                // two boxes of 32 channels x 128 rows (128-byte swizzle); rows outside [0, rows) arrive as zeros
+                const uint32_t dst = smem_base + FE_OFF_OUT + buf * FE_OUT_BYTES;
+                tma_load_3d(dst, &tmIO, raw_full(buf), 0, m0, b);
+                tma_load_3d(dst + FE_OUT_BYTES / 2, &tmIO, raw_full(buf), 32, m0, b);
+            }
+        }
     } else if (warp == 0 && lane == 0) {
         // ===================================================================== MMA issuer
         mbar_wait(w_full, 0);
@@ -159,139 +195,170 @@ fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
             umma_commit(a_empty(buf));
             umma_commit(acc_full(buf));
         }
-    } else if (warp >= 12) {
-        // ===================================================================== A generators (128 threads)
-        const int t = threadIdx.x - 384;
+    } else if (warp >= FE_GEN_WARP0) {
+        // ===================================================================== A generators (8 warps)
+        const int t = threadIdx.x - FE_GEN_WARP0 * 32;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            int b, m0;
-            tile_coords(tile, b, m0);
-            uint8_t* ahi = smem_gen + FE_OFF_A + buf * 2 * FE_A_BYTES;
-            uint8_t* alo = ahi + FE_A_BYTES;
-            if (KIND == 0) {
-                // thread = output row: y[c] = relu(b0[c] + sum_k w[k][c] x[2 row + k]); samples beyond the clip read as 0 (F.pad)
-                const long long s0 = 2ll * (m0 + t);
-                const float* xb = p.x + (long long)b * p.x_stride;
-                float xv[4];
+        if (KIND == 0) {
+            // warp = one 8-channel chunk of the operand row (its 32 conv weights + 8 biases live in REGISTERS: the kernel is bound
+            // by shared-memory bandwidth -- MMA operand reads + staging -- so the generator must not add broadcast loads), lane = rows
+            // l, l+32, l+64, l+96 of the tile.  y[c] = relu(b0[c] + sum_k w[k][c] x[2 row + k]); samples beyond the clip read as 0 (F.pad)
+            const int j = t >> 5;
+            float4 wr[8];
+            float br[8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) xv[k] = (s0 + k < p.length) ? __ldg(xb + s0 + k) : 0.f;
+            for (int e = 0; e < 8; ++e) { wr[e] = taps_s[8 * j + e]; br[e] = b0_s[8 * j + e]; }
+            float xn[4][4];
+            auto fetch_x = [&](int tile) {          // the NEXT tile's samples are requested before this tile's arithmetic
+                int b, m0;
+                tile_coords(tile, b, m0);
+                const float* xb = p.x + (long long)b * p.x_stride;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const long long s0 = 2ll * (m0 + lane + 32 * rr);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) xn[rr][k] = (s0 + k < p.length) ? __ldg(xb + s0 + k) : 0.f;
+                }
+            };
+            if ((int)blockIdx.x < p.total_tiles) fetch_x(blockIdx.x);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                uint8_t* ahi = smem_gen + FE_OFF_A + buf * 2 * FE_A_BYTES;
+                uint8_t* alo = ahi + FE_A_BYTES;
+                float xv[4][4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) xv[rr][k] = xn[rr][k];
+                if (tile + (int)gridDim.x < p.total_tiles) fetch_x(tile + gridDim.x);
                 mbar_wait(a_empty(buf), ph ^ 1u);
-#pragma unroll 2
-                for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int row = lane + 32 * rr;
                     float f[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const float4 w = taps_s[8 * j + e];
-                        float acc = b0_s[8 * j + e];
-                        acc = fmaf(w.x, xv[0], acc); acc = fmaf(w.y, xv[1], acc);
-                        acc = fmaf(w.z, xv[2], acc); acc = fmaf(w.w, xv[3], acc);
+                        float acc = br[e];
+                        acc = fmaf(wr[e].x, xv[rr][0], acc); acc = fmaf(wr[e].y, xv[rr][1], acc);
+                        acc = fmaf(wr[e].z, xv[rr][2], acc); acc = fmaf(wr[e].w, xv[rr][3], acc);
                         f[e] = fmaxf(acc, 0.f);
                     }
                     uint4 hi, lo;
                     split8(f, hi, lo);
-                    const uint32_t off = (uint32_t)t * 128u + (uint32_t)((j ^ (t & 7)) << 4);
+                    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
                     *reinterpret_cast<uint4*>(ahi + off) = hi;
                     *reinterpret_cast<uint4*>(alo + off) = lo;
                 }
-            } else {
-                // 16 lanes = one 256-byte input row (float4 each), two rows per warp request; 16 requests per thread in two batches
-                const int j = t & 15, rsub = t >> 4;
-                const float* ab = p.a + (long long)b * p.rows * 64;
+                fence_proxy_async();
+                mbar_arrive(a_full(buf));
+            }
+        } else {
+            // thread = (row, half of the channels): raw fp32 tile (TMA, two 128-byte-swizzled halves of 32 channels) -> fp16 hi / lo tiles
+            const int row = t & 127, ch = t >> 7;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                uint8_t* ahi = smem_gen + FE_OFF_A + buf * 2 * FE_A_BYTES;
+                uint8_t* alo = ahi + FE_A_BYTES;
+                const uint8_t* raw = smem_gen + FE_OFF_OUT + buf * FE_OUT_BYTES + ch * (FE_OUT_BYTES / 2) + row * 128;
+                mbar_wait(raw_full(buf), ph);
+                float4 v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(raw + ((c ^ (row & 7)) << 4));
+                mbar_arrive(raw_empty(buf));                     // the raw tile is in registers: the TMA may refill it
                 mbar_wait(a_empty(buf), ph ^ 1u);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float4 v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = (half * 8 + i) * 8 + rsub;
-                        const int pr = m0 + r;
-                        v[i] = (pr >= 0 && pr < p.rows) ? __ldg(reinterpret_cast<const float4*>(ab + (long long)pr * 64) + j)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = (half * 8 + i) * 8 + rsub;
-                        const uint32_t h0 = cvt_f16x2_sat(v[i].x, v[i].y), h1 = cvt_f16x2_sat(v[i].z, v[i].w);
-                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
-                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
-                        const uint32_t l0 = cvt_f16x2_sat(v[i].x - f0.x, v[i].y - f0.y), l1 = cvt_f16x2_sat(v[i].z - f1.x, v[i].w - f1.y);
-                        const uint32_t off = (uint32_t)r * 128u + (uint32_t)(((j >> 1) ^ (r & 7)) << 4) + (uint32_t)((j & 1) << 3);
-                        *reinterpret_cast<uint2*>(ahi + off) = make_uint2(h0, h1);
-                        *reinterpret_cast<uint2*>(alo + off) = make_uint2(l0, l1);
-                    }
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * ch + jj;
+                    const float f[8] = {v[2 * jj].x, v[2 * jj].y, v[2 * jj].z, v[2 * jj].w, v[2 * jj + 1].x, v[2 * jj + 1].y, v[2 * jj + 1].z, v[2 * jj + 1].w};
+                    uint4 hi, lo;
+                    split8(f, hi, lo);
+                    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(ahi + off) = hi;
+                    *reinterpret_cast<uint4*>(alo + off) = lo;
                 }
+                fence_proxy_async();
+                mbar_arrive(a_full(buf));
             }
-            fence_proxy_async();
-            mbar_arrive(a_full(buf));
         }
     } else if (warp >= 4 && warp < 12) {
-        // ===================================================================== epilogue (8 warps): thread = tile row, 64 accumulator columns
-        const int q = warp & 3, grp = (warp - 4) >> 2;
+        // ===================================================================== epilogue: set = tile parity, thread = tile row, all 128 columns
+        const int q = warp & 3, set = (warp - 4) >> 2;
         const int r = q * 32 + lane;
-        const bool leader = (warp == 4 && lane == 0);
+        const bool leader = (q == 0 && lane == 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
+            if ((it & 1) != set) continue;
+            const int buf = set;
             const uint32_t ph = (it >> 1) & 1;
             int b, m0;
             tile_coords(tile, b, m0);
             mbar_wait(acc_full(buf), ph);
             tc_fence_after();
-            float o[32];                    // gated outputs of this thread's 32 channels (enc0) / running tap sums (dec_last)
+            const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * FE_N);
+            uint8_t* st = smem_gen + FE_OFF_OUT + buf * FE_OUT_BYTES;
             float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+            float va[32], vb[32];
+            __syncwarp();
+            tmem_ld32_nowait(tsrc, va);
+            if (KIND == 0) {
+                if (leader) bulk_wait_read<0>();        // this set's previous store has finished reading the staging tile
+                set_bar(set);
+            }
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float v[32];
-                const int col0 = grp * 64 + half * 32;
-                __syncwarp();
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * FE_N + col0), v);
+            for (int c = 0; c < 4; ++c) {
+                float* v = (c & 1) ? vb : va;
+                tmem_ld_wait();
+                if (c < 3) tmem_ld32_nowait(tsrc + 32 * (c + 1), (c & 1) ? va : vb);
+                if (c == 3) {           // the accumulator is in registers: hand the TMEM buffer back to the MMA thread
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(buf));
+                }
+                float o[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float2 bv = *reinterpret_cast<const float2*>(bias_s + col0 + 2 * i);
+                    float4 bq;
+                    if ((i & 1) == 0) bq = *reinterpret_cast<const float4*>(bias_s + 32 * c + 2 * i);       // two column pairs per load
+                    const float2 bv = (i & 1) ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y);
                     const float xa = fmaf(v[2 * i], p.acc_scale, bv.x), xb = fmaf(v[2 * i + 1], p.acc_scale, bv.y);
-                    const float g = xa * fast_sigmoid(xb);
-                    if (KIND == 0) {
-                        o[half * 16 + i] = g;
-                    } else {
-                        const float4 w = taps_s[grp * 32 + half * 16 + i];
-                        y0 = fmaf(g, w.x, y0); y1 = fmaf(g, w.y, y1); y2 = fmaf(g, w.z, y2); y3 = fmaf(g, w.w, y3);
+                    o[i] = xa * fast_sigmoid(xb);
+                    if (KIND == 1) {
+                        const float4 w = taps_s[16 * c + i];
+                        y0 = fmaf(o[i], w.x, y0); y1 = fmaf(o[i], w.y, y1); y2 = fmaf(o[i], w.z, y2); y3 = fmaf(o[i], w.w, y3);
                     }
                 }
-            }
-            // the accumulator is in registers: hand the TMEM buffer back to the MMA thread
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(buf));
-            if (KIND == 0) {
-                // staging tile: two halves of 32 channels (128-byte rows, 128-byte swizzle like the tensor map of the store)
-                if (leader) bulk_wait_read<1>();        // the store issued two tiles ago has finished reading this buffer
-                epi_bar();
-                uint8_t* st = smem_gen + FE_OFF_OUT + buf * FE_OUT_BYTES + grp * (FE_OUT_BYTES / 2);
+                if (KIND == 0) {
+                    // staging tile: two halves of 32 channels (128-byte rows, 128-byte swizzle like the tensor map of the store)
+                    uint8_t* half = st + (c >> 1) * (FE_OUT_BYTES / 2) + r * 128;
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    *reinterpret_cast<float4*>(st + r * 128 + ((c ^ (r & 7)) << 4)) = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                    for (int k = 0; k < 4; ++k)
+                        *reinterpret_cast<float4*>(half + ((((c & 1) * 4 + k) ^ (r & 7)) << 4)) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+                }
+            }
+            if (KIND == 0) {
                 fence_proxy_async();
-                epi_bar();
+                set_bar(set);
                 if (leader) {
                     const uint32_t src = smem_base + FE_OFF_OUT + buf * FE_OUT_BYTES;
-                    tma_store_3d(&tmOut, src, 0, m0, b);
-                    tma_store_3d(&tmOut, src + FE_OUT_BYTES / 2, 32, m0, b);
+                    tma_store_3d(&tmIO, src, 0, m0, b);
+                    tma_store_3d(&tmIO, src + FE_OUT_BYTES / 2, 32, m0, b);
                     bulk_commit();
                 }
             } else {
                 const int pr = m0 + r;
                 const bool valid = pr >= 0 && pr < p.rows;          // rows outside the clip contribute nothing (their A rows are zero, GLU(bias) is not)
-                float4* part = part_s + (buf * 2) * 128;
-                part[grp * 128 + r] = valid ? make_float4(y0, y1, y2, y3) : make_float4(0.f, 0.f, 0.f, 0.f);
-                epi_bar();
-                if (grp == 0 && r >= 1 && pr <= p.rows) {
-                    // out[2p + k] = bias + sum_c g[p][c] w[c][k] (k = 0, 1) + sum_c g[p-1][c] w[c][k + 2]
-                    const float4 c0 = part[r], c1 = part[128 + r], q0 = part[r - 1], q1 = part[128 + r - 1];
+                float4* part = part_s + set * 128;
+                set_bar(set);                                       // the previous tile of this set has been read
+                part[r] = valid ? make_float4(y0, y1, y2, y3) : make_float4(0.f, 0.f, 0.f, 0.f);
+                set_bar(set);
+                if (r >= 1 && pr <= p.rows) {
+                    // out[2p + k] = bias + <g[p], w[k]> (k = 0, 1) + <g[p-1], w[k + 2]>
+                    const float4 cur = part[r], prv = part[r - 1];
                     const float sc = p.scale ? __ldg(p.scale + b) : 1.0f;
-                    const float e0 = (p.out_bias + (c0.x + c1.x) + (q0.z + q1.z)) * sc;
-                    const float e1 = (p.out_bias + (c0.y + c1.y) + (q0.w + q1.w)) * sc;
+                    const float e0 = (p.out_bias + cur.x + prv.z) * sc;
+                    const float e1 = (p.out_bias + cur.y + prv.w) * sc;
                     const long long s = 2ll * pr;
                     float* ob = p.out + (long long)b * p.out_stride;
                     if (s + 1 < p.out_length && ((reinterpret_cast<uintptr_t>(ob + s) & 7u) == 0)) {
@@ -301,7 +368,6 @@ fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                         if (s + 1 < p.out_length) ob[s + 1] = e1;
                     }
                 }
-                // part[buf] is rewritten two tiles later: the barrier of the next tile orders that write after these reads
             }
         }
         if (KIND == 0 && leader) bulk_wait_read<0>();
@@ -374,14 +440,17 @@ int dec_last_block_fwd(const cum_dec_last_block_desc& d, cudaStream_t st) {
     if (rc) return rc;
     FusedEndParams p;
     memset(&p, 0, sizeof(p));
-    p.a = d.a; p.rows = d.rows_in; p.batch = d.batch;
+    CUtensorMap tmIn;
+    rc = make_tensor_map(&tmIn, d.a, 64, (uint64_t)d.rows_in, (uint64_t)d.batch, 64, (uint64_t)d.rows_in * 64, 32, FE_ROWS, "dec_last in");
+    if (rc) return rc;
+    p.rows = d.rows_in; p.batch = d.batch;
     p.tiles_per_clip = (int)cdiv((long long)d.rows_in + 1, FE_ROWS - 1);
     const long long total = (long long)p.tiles_per_clip * d.batch;
     CUM_REQUIRE(total < (1ll << 31), "dec_last_block: too many tiles");
     p.total_tiles = (int)total;
     p.taps = d.convt_w; p.bias = d.glu_b; p.acc_scale = d.acc_scale; p.skip_wlo = d.w_lo_is_zero ? 1 : 0;
     p.out_bias = d.convt_bias; p.scale = d.scale; p.out = d.out; p.out_stride = d.out_stride; p.out_length = d.out_length;
-    return launch_fused_end<1>(tmWh, tmWl, tmWh /* no output map: the waveform is written with plain stores */, p, st);
+    return launch_fused_end<1>(tmWh, tmWl, tmIn, p, st);
 }
 
 }  // namespace cum

@@ -24,21 +24,43 @@ class GradSync:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.works: List = []
         self.bytes_reduced = 0
+        self.bucket_bytes: List[int] = []       # bytes of each bucket of the most recent backward, in issue order
+        self._stall: List = []                  # (event before the waits, event after): the compute stream's stall on NCCL
 
     def reduce(self, flat_slice: torch.Tensor) -> None:
         """Start reducing ``flat_slice`` (a contiguous view of the gradient buffer); returns immediately."""
         if self.world == 1 or flat_slice.numel() == 0:
             return
         assert flat_slice.is_contiguous()
+        if not self.works:
+            self.bucket_bytes = []
         self.bytes_reduced += flat_slice.numel() * flat_slice.element_size()
+        self.bucket_bytes.append(flat_slice.numel() * flat_slice.element_size())
         self.works.append(dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def finish(self) -> float:
         """Wait for every bucket (stream-ordered on CUDA) and return the averaging factor 1 / world."""
+        timed = bool(self.works) and torch.cuda.is_available() and dist.get_backend(self.group) == "nccl"
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         for w in self.works:
             w.wait()
+        if timed:
+            e1.record()
+            self._stall.append((e0, e1))
+            del self._stall[:-64]
         self.works.clear()
         return 1.0 / self.world
+
+    def exposed_ms(self) -> float:
+        """Mean time per backward the compute stream spent waiting for the all-reduces (CUDA events around the waits of
+        ``finish``: the part of the collective NOT hidden behind the backward kernels).  Call after a synchronize; resets."""
+        if not self._stall:
+            return 0.0
+        ms = sum(a.elapsed_time(b) for a, b in self._stall) / len(self._stall)
+        self._stall.clear()
+        return ms
 
 
 def apply_gradient_allreduce(module, group=None):

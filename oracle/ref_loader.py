@@ -4,15 +4,18 @@ The reference's hot-path module (/root/reference/src/network/CleanUMamba.py) can
   * it needs ``mamba_ssm`` (CleanUMamba.py:12,14) and ``torchinfo`` (:15) -> provided by ``oracle/ref_shim``;
   * ``src/util/util.py:220-227`` evaluates ``.cuda()`` in a default argument at import time -> on a GPU-less
     host ``nn.Module.cuda`` is made an identity for the duration of the import.
-Nothing under /root/reference is copied; it is imported where it lies.  The GPU box has no /root/reference, so
-only ``oracle/make_golden.py`` and the ``not gpu`` pinning tests (which skip when the mount is absent) use this.
+In the build container the reference is imported where it lies.  The GPU box has no /root/reference: there the loader falls
+back to the byte-for-byte staged copy under the git-ignored ``baseline/_ref/`` (``oracle/stage_reference.py``, made by
+``__graft_entry__.build()``), which only ``bench.py``'s CPU legs use (the reference arm / ``cpu_baseline``).
 """
 import os
 import sys
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("CLEANUMAMBA_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REFERENCE_ROOT = os.environ.get("CLEANUMAMBA_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/src/network/CleanUMamba.py") else _STAGED)
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shim")
 
 
