@@ -555,7 +555,7 @@ def main():
     # ---- extras (every rank takes part): the collective path and the streaming configuration under the same clock ----------
     extras = {}
     if not args.no_extras and args.model == "e8" and args.math == "f16x3":
-        del pipe, work
+        del pipe
         eng._graphs.clear()
         torch.cuda.empty_cache()
         from cleanumamba_b200.shard import shard_bounds

@@ -57,7 +57,7 @@ class ScanDesc(C.Structure):
                 ("a2", C.c_void_p), ("Dskip", C.c_void_p), ("delta_bias", C.c_void_p),
                 ("h0", C.c_void_p), ("h_out", C.c_void_p),
                 ("batch", C.c_int), ("len", C.c_int), ("d", C.c_int), ("n_state", C.c_int),
-                ("delta_softplus", C.c_int), ("h_ckpt", C.c_void_p)]
+                ("delta_softplus", C.c_int), ("h_ckpt", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
 
 
 class WgradDesc(C.Structure):
@@ -109,6 +109,7 @@ EXPORTS = {
     "cum_dwconv_silu_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cum_selective_scan_fwd": (C.c_int, [C.POINTER(ScanDesc), C.c_void_p]),
+    "cum_selective_scan_workspace_bytes": (C.c_longlong, [C.POINTER(ScanDesc)]),
     "cum_glu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "cum_glu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "cum_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
@@ -126,6 +127,8 @@ EXPORTS = {
     "cum_convt_out_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cum_selective_scan_bwd": (C.c_int, [C.POINTER(ScanBwdDesc), C.c_void_p]),
+    "cum_channel_importance_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -213,6 +213,10 @@ int cum_selective_scan_fwd(const cum_scan_desc* desc, cum_stream_t stream) {
     return selective_scan_fwd(*desc, (cudaStream_t)stream);
 }
 
+long long cum_selective_scan_workspace_bytes(const cum_scan_desc* desc) {
+    return desc ? selective_scan_workspace_bytes(*desc) : 0;
+}
+
 int cum_glu_fwd(const float* z, const float* addend, float* out, long long rows, int h_pad, cum_stream_t stream) {
     return glu_fwd(z, addend, out, rows, h_pad, (cudaStream_t)stream);
 }
@@ -257,6 +261,10 @@ int cum_convt_out_bwd(const float* g, int batch, int rows_in, int c_pad, const f
                       int kernel, int stride, cum_stream_t stream) {
     return convt_out_bwd(g, batch, rows_in, c_pad, w, scale, dout, dout_stride, length, dg, dw, dbias, kernel, stride,
                          (cudaStream_t)stream);
+}
+int cum_channel_importance_fwd(const float* w, const float* g, int rows, int cols, long long ldw, long long ldg, float* out_rows,
+                               float* out_cols, cum_stream_t stream) {
+    return channel_importance_fwd(w, g, rows, cols, ldw, ldg, out_rows, out_cols, (cudaStream_t)stream);
 }
 int cum_selective_scan_bwd(const cum_scan_bwd_desc* desc, cum_stream_t stream) {
     if (!desc) { set_error("selective_scan_bwd: null descriptor"); return CUM_EINVAL; }

@@ -90,6 +90,7 @@ int dwconv_silu_fwd(const float* x, long long x_bs, long long x_rs, const float*
                     const float* conv_state, float* conv_state_out, int batch, int len, int d_pad, int width,
                     cudaStream_t st);
 int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st);
+long long selective_scan_workspace_bytes(const cum_scan_desc& d);
 
 int glu_fwd(const float* z, const float* addend, float* out, long long rows, int h_pad, cudaStream_t st);
 int rowblock_bwd(int mode, const float* z, const float* dout, float* dz, float* dbias, long long rows, int cols, cudaStream_t st);
@@ -108,6 +109,8 @@ int convt_out_bwd(const float* g, int batch, int rows_in, int c_pad, const float
                   const float* dout, long long dout_stride, int length, float* dg, float* dw, float* dbias, int kernel,
                   int stride, cudaStream_t st);
 int selective_scan_bwd(const cum_scan_bwd_desc& d, cudaStream_t st);
+int channel_importance_fwd(const float* w, const float* g, int rows, int cols, long long ldw, long long ldg, float* out_rows,
+                           float* out_cols, cudaStream_t st);
 
 constexpr int CI_MAXK = 8;   // conv_in / conv_in_bwd
 constexpr int CT_MAXK = 8;   // convt_out / convt_out_bwd

@@ -229,26 +229,39 @@ struct ScanSmem {
     float ypart[SL][TC][CH];
 };
 
+// Kernel parameters: the public descriptor plus the SEGMENT-PARALLEL mode used for small batches (selective_scan_fwd below).
+// nseg > 1: blockIdx.y = item * nseg + segment; a segment covers rows [segment * seg_len, ...) of its item; carried states
+// (h0 / h_out) are indexed by blockIdx.y (one state block per segment); seg_sum receives sum_t softplus(delta_t + bias) of the
+// segment per channel (its total decay is exp2(a2 * seg_sum)).
+struct ScanK : cum_scan_desc {
+    int nseg, seg_len;
+    float* seg_sum;
+};
+
 template <int NS, int SL, int CH, int TC>
-__global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_scan_fwd_kernel(const cum_scan_desc p) {
+__global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_scan_fwd_kernel(const ScanK p) {
     constexpr int NP = NS * SL;
     constexpr int NT = CH * SL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScanSmem<NS, SL, CH, TC>& sm = *reinterpret_cast<ScanSmem<NS, SL, CH, TC>*>(smem_raw);
 
-    const int b = blockIdx.y;
+    const int bb = blockIdx.y;                                   // state block (h0 / h_out / seg_sum) index
+    const int seg = p.nseg > 1 ? bb % p.nseg : 0;
+    const int b = p.nseg > 1 ? bb / p.nseg : bb;                 // batch item
+    const int row0 = seg * p.seg_len;                            // first row of this CTA's segment
+    const int len = p.nseg > 1 ? min(p.seg_len, p.len - row0) : p.len;
     const int c0 = blockIdx.x * CH;
     const int tid = threadIdx.x;
     const int ch = tid % CH, slice = tid / CH;
     const int c = c0 + ch;
     const bool c_ok = c < p.d;
-    const int nchunks = (p.len + TC - 1) / TC;
+    const int nchunks = (len + TC - 1) / TC;
 
-    const float* ub = p.u + (long long)b * p.u_bs;
-    const float* db = p.delta + (long long)b * p.dl_bs;
-    const float* Bb = p.Bm + (long long)b * p.B_bs;
-    const float* Cb = p.Cm + (long long)b * p.C_bs;
-    const float* zb = p.z ? p.z + (long long)b * p.z_bs : nullptr;
+    const float* ub = p.u + (long long)b * p.u_bs + (long long)row0 * p.u_rs;
+    const float* db = p.delta + (long long)b * p.dl_bs + (long long)row0 * p.dl_rs;
+    const float* Bb = p.Bm + (long long)b * p.B_bs + (long long)row0 * p.B_rs;
+    const float* Cb = p.Cm + (long long)b * p.C_bs + (long long)row0 * p.C_rs;
+    const float* zb = (p.z && p.y) ? p.z + (long long)b * p.z_bs + (long long)row0 * p.z_rs : nullptr;
     const bool vec_ok = ((p.u_rs | p.dl_rs | p.B_rs | p.C_rs | p.u_bs | p.dl_bs | p.B_bs | p.C_bs) % 4 == 0) &&
                         (!p.z || ((p.z_rs | p.z_bs) % 4 == 0 && ((uintptr_t)p.z & 15) == 0)) &&
                         ((((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.Bm | (uintptr_t)p.Cm) & 15) == 0) &&
@@ -263,14 +276,14 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
             float* su = &sm.u[buf][t][q * 4];
             float* sd = &sm.dl[buf][t][q * 4];
             float* sz = &sm.z[buf][t][q * 4];
-            if (tt < p.len && cc + 3 < p.d && vec_ok) {
+            if (tt < len && cc + 3 < p.d && vec_ok) {
                 cp_async16(su, ub + (long long)tt * p.u_rs + cc);
                 cp_async16(sd, db + (long long)tt * p.dl_rs + cc);
                 if (zb) cp_async16(sz, zb + (long long)tt * p.z_rs + cc);
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const bool ok = tt < p.len && cc + e < p.d;
+                    const bool ok = tt < len && cc + e < p.d;
                     su[e] = ok ? ub[(long long)tt * p.u_rs + cc + e] : 0.f;
                     sd[e] = ok ? db[(long long)tt * p.dl_rs + cc + e] : 0.f;
                     if (zb) sz[e] = ok ? zb[(long long)tt * p.z_rs + cc + e] : 0.f;
@@ -283,13 +296,13 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
             const int tt = t0 + t, nn = q * 4;
             float* sb = &sm.Bm[buf][t][nn];
             float* sc = &sm.Cm[buf][t][nn];
-            if (tt < p.len && nn + 3 < p.n_state && vec_ok) {
+            if (tt < len && nn + 3 < p.n_state && vec_ok) {
                 cp_async16(sb, Bb + (long long)tt * p.B_rs + nn);
                 cp_async16(sc, Cb + (long long)tt * p.C_rs + nn);
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const bool ok = tt < p.len && nn + e < p.n_state;
+                    const bool ok = tt < len && nn + e < p.n_state;
                     sb[e] = ok ? Bb[(long long)tt * p.B_rs + nn + e] : 0.f;
                     sc[e] = ok ? Cb[(long long)tt * p.C_rs + nn + e] : 0.f;
                 }
@@ -318,7 +331,7 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
             h2[2 * q] = make_float2(0.f, 0.f); h2[2 * q + 1] = make_float2(0.f, 0.f);
         }
         if (p.h0) {
-            const float4* src = reinterpret_cast<const float4*>(p.h0 + ((long long)b * p.d + c0) * NP);
+            const float4* src = reinterpret_cast<const float4*>(p.h0 + ((long long)bb * p.d + c0) * NP);
             for (int i = tid; i < CH * NP / 4; i += NT) {
                 const int chn = i / (NP / 4), chunk = i - chn * (NP / 4);
                 *reinterpret_cast<float4*>(hs_chunk(chn, chunk)) = src[i];
@@ -337,7 +350,7 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
             const float4 av = __ldg(reinterpret_cast<const float4*>(p.a2 + (long long)c * p.n_state + slice * NS) + q);
             a2p[2 * q] = make_float2(av.x, av.y); a2p[2 * q + 1] = make_float2(av.z, av.w);
             float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.h0) hv = *(reinterpret_cast<const float4*>(p.h0 + ((long long)b * p.d + c) * p.n_state + slice * NS) + q);
+            if (p.h0) hv = *(reinterpret_cast<const float4*>(p.h0 + ((long long)bb * p.d + c) * p.n_state + slice * NS) + q);
             h2[2 * q] = make_float2(hv.x, hv.y); h2[2 * q + 1] = make_float2(hv.z, hv.w);
         }
     } else {
@@ -346,16 +359,17 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
             const int n = slice * NS + i;
             const bool ok = c_ok && n < p.n_state;
             const float av = ok ? p.a2[(long long)c * p.n_state + n] : 0.f;
-            const float hv = (ok && p.h0) ? p.h0[((long long)b * p.d + c) * p.n_state + n] : 0.f;
+            const float hv = (ok && p.h0) ? p.h0[((long long)bb * p.d + c) * p.n_state + n] : 0.f;
             if (i & 1) { a2p[i >> 1].y = av; h2[i >> 1].y = hv; } else { a2p[i >> 1].x = av; h2[i >> 1].x = hv; }
         }
     }
 
+    float seg_dl = 0.f;          // sum of the discretised steps of this segment (segment-parallel mode)
     stage(0, 0);
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int buf = chunk & 1;
         const int t0 = chunk * TC;
-        const int tn = min(TC, p.len - t0);
+        const int tn = min(TC, len - t0);
         if (p.h_ckpt) {   // training: state at the start of this chunk, for the reverse scan
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
@@ -381,6 +395,7 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
 #pragma unroll kScanUnroll
         for (int t = 0; t < tn; ++t) {
             const float dl = sm.dl[buf][t][ch];
+            seg_dl += dl;
             const float du = dl * sm.u[buf][t][ch];
             const float2 dl2 = make_float2(dl, dl), du2 = make_float2(du, du);
             const float4* bq = reinterpret_cast<const float4*>(&sm.Bm[buf][t][slice * NS]);
@@ -401,7 +416,8 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
             sm.ypart[slice][t][ch] = a.x + a.y;
         }
         __syncthreads();  // (C)
-        // combine + gate + store
+        // combine + gate + store (skipped by the first pass of the segment-parallel mode: only the end state is wanted)
+        if (p.y)
         for (int i = tid; i < tn * CH; i += NT) {
             const int t = i / CH, cc = i - t * CH;
             const int cg = c0 + cc;
@@ -414,9 +430,10 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
                 const float zz = sm.z[buf][t][cc];
                 yv *= __fdividef(zz, 1.0f + __expf(-zz));
             }
-            p.y[(long long)b * p.y_bs + (long long)(t0 + t) * p.y_rs + cg] = yv;
+            p.y[(long long)b * p.y_bs + (long long)(row0 + t0 + t) * p.y_rs + cg] = yv;
         }
     }
+    if (p.seg_sum && slice == 0 && c_ok) p.seg_sum[(long long)bb * p.d + c] = seg_dl;
     if (p.h_out) {
         if (state_tile) {
             __syncthreads();          // the last combine phase has read ypart
@@ -424,7 +441,7 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
             for (int q = 0; q < NS / 4; ++q)
                 *reinterpret_cast<float4*>(hs_chunk(ch, slice * (NS / 4) + q)) = make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
             __syncthreads();
-            float4* dst = reinterpret_cast<float4*>(p.h_out + ((long long)b * p.d + c0) * NP);
+            float4* dst = reinterpret_cast<float4*>(p.h_out + ((long long)bb * p.d + c0) * NP);
             for (int i = tid; i < CH * NP / 4; i += NT) {
                 const int chn = i / (NP / 4), chunk = i - chn * (NP / 4);
                 dst[i] = *reinterpret_cast<const float4*>(hs_chunk(chn, chunk));
@@ -432,13 +449,13 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
         } else if (state_vec) {
 #pragma unroll
             for (int q = 0; q < NS / 4; ++q)
-                *(reinterpret_cast<float4*>(p.h_out + ((long long)b * p.d + c) * p.n_state + slice * NS) + q) =
+                *(reinterpret_cast<float4*>(p.h_out + ((long long)bb * p.d + c) * p.n_state + slice * NS) + q) =
                     make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
         } else {
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
                 const int n = slice * NS + i;
-                if (c_ok && n < p.n_state) p.h_out[((long long)b * p.d + c) * p.n_state + n] = (i & 1) ? h2[i >> 1].y : h2[i >> 1].x;
+                if (c_ok && n < p.n_state) p.h_out[((long long)bb * p.d + c) * p.n_state + n] = (i & 1) ? h2[i >> 1].y : h2[i >> 1].x;
             }
         }
     }
@@ -503,14 +520,72 @@ __global__ void __launch_bounds__(256) selective_scan_step_kernel(const cum_scan
 }
 
 template <int NS, int SL, int CH, int TC>
-static int launch_scan(const cum_scan_desc& d, cudaStream_t st) {
+static int launch_scan(const ScanK& d, cudaStream_t st) {
     auto kern = selective_scan_fwd_kernel<NS, SL, CH, TC>;
     const size_t smem = sizeof(ScanSmem<NS, SL, CH, TC>);
     { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem, "cudaFuncSetAttribute(selective_scan_fwd_kernel)"); if (rc_attr) return rc_attr; }
-    dim3 grid((unsigned)cdiv(d.d, CH), (unsigned)d.batch);
+    dim3 grid((unsigned)cdiv(d.d, CH), (unsigned)(d.batch * (d.nseg > 1 ? d.nseg : 1)));
     kern<<<grid, CH * SL, smem, st>>>(d);
     CUM_LAUNCH_CHECK("selective_scan_fwd_kernel");
     return CUM_OK;
+}
+
+static int launch_scan_any(const ScanK& k, cudaStream_t st) {
+    if (k.n_state > 32) return launch_scan<16, 4, 64, 16>(k, st);
+    if (k.n_state > 16) return launch_scan<16, 2, 64, 16>(k, st);
+    if (k.n_state > 8)  return launch_scan<16, 1, 64, 16>(k, st);
+    return launch_scan<8, 1, 64, 16>(k, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Segment-parallel scan for SMALL batches (a single long clip: batch 1 x 60 s is 32 CTAs on 148 SMs with the plain kernel).
+// The recurrence h_t = dA_t h_{t-1} + x_t is linear in h, so a clip is cut into `nseg` time segments that run concurrently:
+//   pass 1  every segment scans from h = 0: its local end state E_s and sum_t dl_t (total decay P_s = exp2(a2 * sum dl))
+//   pass 2  carry: H_0 = h0, H_{s+1} = P_s * H_s + E_s                      (tiny: nseg steps per (item, channel, state))
+//   pass 3  every segment scans again from its true start state H_s and writes y
+// Twice the arithmetic, nseg-fold parallelism: pays when cdiv(d, 64) * batch CTAs leave most SMs idle.
+// ---------------------------------------------------------------------------------------------------------
+struct SegPlan { int nseg, seg_len; size_t state_elems, sum_elems; };
+
+static SegPlan plan_segments(const cum_scan_desc& d) {
+    SegPlan s{1, d.len, 0, 0};
+    const long long ctas = cdiv(d.d, 64) * d.batch;
+    if (d.h_ckpt || d.len < 256 || 2 * ctas > sm_count()) return s;
+    long long n = (2LL * sm_count() + ctas - 1) / ctas;
+    if (n > d.len / 64) n = d.len / 64;
+    if (n > 64) n = 64;
+    if (n < 2) return s;
+    s.seg_len = (int)(cdiv(cdiv(d.len, n), 16) * 16);
+    s.nseg = (int)cdiv(d.len, s.seg_len);
+    if (s.nseg < 2 || (long long)d.batch * s.nseg > 65535) { s.nseg = 1; s.seg_len = d.len; return s; }
+    s.state_elems = (size_t)d.batch * s.nseg * d.d * d.n_state;
+    s.sum_elems = ((size_t)d.batch * s.nseg * d.d + 3) / 4 * 4;
+    return s;
+}
+
+long long selective_scan_workspace_bytes(const cum_scan_desc& d) {
+    if (d.batch <= 0 || d.len <= 0 || d.d <= 0 || d.n_state <= 0) return 0;
+    const SegPlan s = plan_segments(d);
+    return s.nseg > 1 ? (long long)((2 * s.state_elems + s.sum_elems) * sizeof(float)) : 0;
+}
+
+// H_0 = h0 (or 0); H_{s+1} = exp2(a2 * sum_s) * H_s + E_s; h_start[s] = H_s; h_out = H_nseg
+__global__ void __launch_bounds__(256) scan_carry_kernel(const float* __restrict__ e, const float* __restrict__ sum, const float* __restrict__ a2,
+                                                          const float* __restrict__ h0, float* __restrict__ h_start, float* __restrict__ h_out,
+                                                          int batch, int nseg, int d, int n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (item, channel, state)
+    if (i >= (long long)batch * d * n) return;
+    const int st = (int)(i % n);
+    const int c = (int)((i / n) % d);
+    const int b = (int)(i / ((long long)n * d));
+    const float a = a2[(long long)c * n + st];
+    float h = h0 ? h0[i] : 0.f;
+    for (int s = 0; s < nseg; ++s) {
+        const long long o = (((long long)b * nseg + s) * d + c) * n + st;
+        h_start[o] = h;
+        h = fmaf(ex2_approx(a * sum[((long long)b * nseg + s) * d + c]), h, e[o]);
+    }
+    if (h_out) h_out[i] = h;
 }
 
 int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st) {
@@ -527,10 +602,32 @@ int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st) {
         CUM_LAUNCH_CHECK("selective_scan_step_kernel");
         return CUM_OK;
     }
-    if (d.n_state > 32) return launch_scan<16, 4, 64, 16>(d, st);
-    if (d.n_state > 16) return launch_scan<16, 2, 64, 16>(d, st);
-    if (d.n_state > 8)  return launch_scan<16, 1, 64, 16>(d, st);
-    return launch_scan<8, 1, 64, 16>(d, st);
+    ScanK k;
+    static_cast<cum_scan_desc&>(k) = d;
+    k.nseg = 1; k.seg_len = d.len; k.seg_sum = nullptr;
+    const SegPlan sp = plan_segments(d);
+    if (sp.nseg > 1 && d.workspace && al16(d.workspace) &&
+        d.workspace_bytes >= (long long)((2 * sp.state_elems + sp.sum_elems) * sizeof(float))) {
+        float* e = reinterpret_cast<float*>(d.workspace);
+        float* sum = e + sp.state_elems;
+        float* hstart = sum + sp.sum_elems;
+        // pass 1: local end states + per-segment decay sums (no y, no gate)
+        ScanK a = k;
+        a.nseg = sp.nseg; a.seg_len = sp.seg_len; a.seg_sum = sum;
+        a.y = nullptr; a.h0 = nullptr; a.h_out = e; a.h_ckpt = nullptr;
+        int rc = launch_scan_any(a, st);
+        if (rc) return rc;
+        // pass 2: carry across segments
+        const long long n = (long long)d.batch * d.d * d.n_state;
+        scan_carry_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(e, sum, d.a2, d.h0, hstart, d.h_out, d.batch, sp.nseg, d.d, d.n_state);
+        CUM_LAUNCH_CHECK("scan_carry_kernel");
+        // pass 3: every segment from its true start state
+        ScanK c = k;
+        c.nseg = sp.nseg; c.seg_len = sp.seg_len; c.seg_sum = nullptr;
+        c.h0 = hstart; c.h_out = nullptr; c.h_ckpt = nullptr;
+        return launch_scan_any(c, st);
+    }
+    return launch_scan_any(k, st);
 }
 
 }  // namespace cum

@@ -358,9 +358,14 @@ class Engine:
     def scan(self, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None, h_ckpt=None):
         s = ScanDesc()
         self.fill_scan(s, u, dt, xz, xdbl, y, l, mm, B, T, h0, h_out, h_ckpt)
+        ws = None
+        if h_ckpt is None and T >= 256:        # small batches of long clips: segment-parallel scan (scratch from the caching allocator)
+            from .ops import scan_workspace
+            ws = scan_workspace(self.lib, s, u.device)
         # algorithmic bytes: read u, delta, z + B, C, write y -- real (unpadded) widths
         self._call("selective_scan", self.lib.cum_selective_scan_fwd, C.byref(s), _lib.stream_ptr(),
-                   nbytes=4 * B * T * (4 * mm["di"] + 2 * mm["N"]), flops=B * T * mm["di"] * mm["N"])
+                   nbytes=4 * B * T * (4 * mm["di"] + 2 * mm["N"]), flops=B * T * mm["di"] * mm["N"], launches=1 if ws is None else 3)
+        del ws
 
     def mamba_layers(self, h, B, T, states=None):
         """h: (B*T, dm_p) output of tsfm_conv1 -> normed (B*T, dm_p) after norm_f.  ``states``: optional list of

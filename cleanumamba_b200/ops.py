@@ -31,8 +31,19 @@ def _cl(t):
 
 
 @torch.no_grad()
+def scan_workspace(lib, desc, device):
+    """Scratch for the segment-parallel scan of small batches (None when the problem runs time-sequentially); sets the
+    descriptor's workspace fields.  The caller keeps the returned tensor alive until the call has been issued."""
+    nbytes = lib.cum_selective_scan_workspace_bytes(C.byref(desc))
+    if nbytes <= 0:
+        return None
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+    desc.workspace, desc.workspace_bytes = ws.data_ptr(), nbytes
+    return ws
+
+
 def selective_scan_fn(u, delta, A, B, C_, D=None, z=None, delta_bias=None, delta_softplus=False,
-                      return_last_state=False, initial_state=None):
+                      return_last_state=False, initial_state=None, segment_parallel=True):
     """u, delta, z: (b, d, l); A: (d, n); B, C: (b, n, l).  Returns y (b, d, l) [, last_state (b, d, n)].
     ``initial_state`` (b, d, n) is an extension (the dependency's kernel always starts from h = 0)."""
     _need_cuda(u, delta, A, B, C_, D, z, delta_bias, initial_state)
@@ -56,6 +67,7 @@ def selective_scan_fn(u, delta, A, B, C_, D=None, z=None, delta_bias=None, delta
     s.y, s.y_bs, s.y_rs = y.data_ptr(), l * d, d
     s.a2, s.Dskip, s.delta_bias, s.h0, s.h_out = a2.data_ptr(), ptr(Df), ptr(bias), ptr(h0), ptr(h_out)
     s.batch, s.len, s.d, s.n_state, s.delta_softplus = b, l, d, n, int(bool(delta_softplus))
+    ws = scan_workspace(lib, s, u.device) if segment_parallel else None
     check(lib.cum_selective_scan_fwd(C.byref(s), _lib.stream_ptr()), "cum_selective_scan_fwd")
     out = y.permute(0, 2, 1).to(u.dtype)
     return (out, h_out) if return_last_state else out

@@ -246,8 +246,16 @@ typedef struct cum_scan_desc {
     int delta_softplus;
     float* h_ckpt;      /* optional (training): (batch, ceil(len/16), d, n_state) -- h at the start of every 16-step chunk,
                            consumed by cum_selective_scan_bwd */
+    void* workspace;    /* optional scratch (16-byte aligned) of cum_selective_scan_workspace_bytes(desc) bytes: with it, SMALL
+                           batches (fewer than SM-count/2 CTAs of 64 channels, len >= 256) run segment-parallel -- the clip is cut
+                           into time segments scanned concurrently from h = 0, a carry pass chains their end states
+                           (h is linear in its start state), a second pass writes y from the true start states: 2x the
+                           arithmetic, up to 64-fold parallelism.  NULL: always the time-sequential kernel */
+    long long workspace_bytes;
 } cum_scan_desc;
 int cum_selective_scan_fwd(const cum_scan_desc* desc, cum_stream_t stream);
+/* 0 when the problem would not run segment-parallel (large batch, short sequence, training checkpoints requested) */
+long long cum_selective_scan_workspace_bytes(const cum_scan_desc* desc);
 
 /* ---- backward (training; autograd of CleanUMamba.forward, src/training/train.py:278-285) ------------------- */
 /* In training the GLU gate and the skip add run as separate kernels so the pre-activation is saved once:
@@ -318,6 +326,17 @@ typedef struct cum_scan_bwd_desc {
     float* dA_log; float* dD; float* ddelta_bias;
 } cum_scan_bwd_desc;
 int cum_selective_scan_bwd(const cum_scan_bwd_desc* desc, cum_stream_t stream);
+
+/* ---- pruning support ---------------------------------------------------------------------------- */
+/* Channel-importance statistics of a weight matrix w (rows, cols; row strides ldw / ldg) and its gradient g, the inputs of the
+ * reference's pruning criteria (src/pruning/pruninggroup.py:160-226 `channel_importances`, importance.py:39): for every row and
+ * every column, in ONE pass over w and g,
+ *   [0] sum w^2 ("weight")   [1] sum g^2 ("grad")   [2] sum |w g| ("taylor_individual")
+ *   [3] sum (w g)^2 ("taylor_squared_individual")   [4] sum w g (|.| of it = "taylor_group")
+ * out_rows: (5, rows) or NULL; out_cols: (5, cols) or NULL (zeroed by the call).  The caller regroups rows / columns into
+ * channels (n_heads consecutive rows per channel, K taps per input channel of a conv weight). */
+int cum_channel_importance_fwd(const float* w, const float* g, int rows, int cols, long long ldw, long long ldg,
+                               float* out_rows, float* out_cols, cum_stream_t stream);
 
 #ifdef __cplusplus
 }

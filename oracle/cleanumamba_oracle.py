@@ -301,6 +301,40 @@ class StreamOracle:
 
 
 # --------------------------------------------------------------------------------------------------------------
+# pruning: channel importances  (src/pruning/pruninggroup.py:160-226)
+# --------------------------------------------------------------------------------------------------------------
+def channel_importances(weight: Tensor, grad: Optional[Tensor], dim: int = 0, channel_offset: int = 0,
+                        n_channels: Optional[int] = None, n_heads: int = 1) -> dict:
+    """Restatement of ``PruningModule.channel_importances`` (pruninggroup.py:160-226) without the module bookkeeping:
+    transpose for dim 1 (:178-181), flatten the trailing dims (:189-196), cut the group's rows out at ``channel_offset``
+    (:199-204), fold ``n_heads`` rows into one channel, then the five sums (:213-221)."""
+    w = weight.detach().to("cpu", torch.float32)
+    g = None if grad is None else grad.detach().to("cpu", torch.float32)
+    if dim == 1:
+        w = w.transpose(1, 0)
+        g = None if g is None else g.transpose(1, 0)
+    if w.dim() > 2:
+        w = w.flatten(1)
+        g = None if g is None else g.flatten(1)
+    elif w.dim() == 1:
+        w = w.unsqueeze(1)
+        g = None if g is None else g.unsqueeze(1)
+    if n_channels is None:
+        n_channels = (w.shape[0] - channel_offset) // n_heads
+    rows = slice(channel_offset, channel_offset + n_channels * n_heads)
+    w = w[rows].reshape(n_channels, -1)
+    out = {"weight": w.abs().pow(2).sum(1), "grad": None, "taylor_individual": None, "taylor_squared_individual": None,
+           "taylor_group": None, "n_parameters": w.shape[1], "act_var": None}
+    if g is not None:
+        g = g[rows].reshape(n_channels, -1)
+        out["grad"] = g.abs().pow(2).sum(1)
+        out["taylor_individual"] = (w * g).abs().sum(1)
+        out["taylor_squared_individual"] = (w * g).pow(2).sum(1)
+        out["taylor_group"] = (w * g).sum(1).abs()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
 # metrics used by the parity tests and the bench
 # --------------------------------------------------------------------------------------------------------------
 def si_sdr(estimate: Tensor, target: Tensor) -> Tensor:

@@ -166,3 +166,34 @@ def test_loss_restatement_matches_live_reference():
         b = RefLoss(**cfg)(x, y)
         assert torch.allclose(a[0], b[0], rtol=1e-5) and torch.allclose(a[1], b[1], rtol=1e-5), band
     del sys
+
+
+def test_channel_importances_restatement_matches_live_reference():
+    """oracle.channel_importances == the reference's PruningModule.channel_importances (pruninggroup.py:160-226) on conv / linear /
+    vector parameters, both dims, with a channel offset and several heads.  (src.pruning.util needs absent packages: only the
+    one symbol pruninggroup imports from it is stubbed.)"""
+    import sys
+    import types
+    import ref_loader
+    if not os.path.isdir(os.path.join("/root/reference", "src", "pruning")):
+        pytest.skip("reference tree not mounted")
+    ref_loader.import_reference()
+    if "src.pruning.util" not in sys.modules:
+        stub = types.ModuleType("src.pruning.util")
+        stub.prune_parameter_and_grad = lambda *a, **k: None
+        sys.modules["src.pruning.util"] = stub
+    from src.pruning.pruninggroup import PruningModule
+    g = torch.Generator().manual_seed(0)
+    cases = [(torch.nn.Conv1d(12, 16, 4), 0, 0, 16, 1), (torch.nn.Conv1d(12, 16, 4), 1, 0, 12, 1), (torch.nn.Linear(10, 24), 0, 8, 4, 4),
+             (torch.nn.Linear(10, 24), 1, 2, 8, 1), (torch.nn.LayerNorm(14), 0, 0, 14, 1)]
+    for mod, dim, off, n_ch, heads in cases:
+        mod.weight.grad = torch.randn(mod.weight.shape, generator=g)
+        pm = PruningModule(mod, dim=dim, n_heads=heads, channel_offset=off, statistics=False)
+        pm.group = types.SimpleNamespace(n_channels=n_ch)
+        if off or n_ch * heads != mod.weight.shape[dim]:        # the rest of the matrix belongs to a following module
+            pm.next_module_to_offset = types.SimpleNamespace(channel_offset=off + n_ch * heads, module=mod)
+        want = pm.channel_importances()
+        got = orc.channel_importances(mod.weight, mod.weight.grad, dim, off, n_ch, heads)
+        for k in ("weight", "grad", "taylor_individual", "taylor_squared_individual", "taylor_group"):
+            assert torch.allclose(got[k], want[k], rtol=1e-5, atol=1e-7), (type(mod).__name__, dim, k)
+        assert got["n_parameters"] == want["n_parameters"]

@@ -48,6 +48,33 @@ def test_selective_scan_matches_oracle(b, d, l, n, with_z, with_h0):
     assert rel_err(h, h_ref) < 2e-5
 
 
+@pytest.mark.parametrize("b,d,l,n,with_h0", [(1, 256, 2000, 64, True), (2, 128, 999, 16, False), (1, 64, 1300, 8, True), (1, 320, 257, 24, False)])
+def test_selective_scan_segment_parallel_small_batch(b, d, l, n, with_h0):
+    """Small batch x long sequence: the scan runs segment-parallel (local scans from h = 0, carry pass, second scan from the
+    true start states) -- same y / last state as the oracle and as the time-sequential kernel."""
+    import ctypes as C
+    from cleanumamba_b200 import _lib, ops
+    g = torch.Generator().manual_seed(b * 1000 + d + l + n)
+    u = torch.randn(b, d, l, generator=g)
+    delta = torch.randn(b, d, l, generator=g) * 0.5
+    A = -torch.exp(torch.randn(d, n, generator=g) * 0.5 + 0.5)
+    Bm, Cm = torch.randn(b, n, l, generator=g), torch.randn(b, n, l, generator=g)
+    D, z = torch.randn(d, generator=g), torch.randn(b, d, l, generator=g)
+    bias = torch.randn(d, generator=g) * 0.5 - 2.0
+    h0 = torch.randn(b, d, n, generator=g) if with_h0 else None
+    y_ref, h_ref = orc.selective_scan(u, delta, A, Bm, Cm, D, z, bias, True, h0=h0, return_last_state=True)
+    cu = lambda t: None if t is None else t.to(dev())  # noqa: E731
+    args = (cu(u), cu(delta), cu(A), cu(Bm), cu(Cm), cu(D), cu(z), cu(bias), True)
+    # the library must actually choose the segmented path for this shape
+    s = _lib.ScanDesc()
+    s.batch, s.len, s.d, s.n_state = b, l, d, n
+    assert _lib.init(torch.device(dev())).cum_selective_scan_workspace_bytes(C.byref(s)) > 0
+    y, h = ops.selective_scan_fn(*args, return_last_state=True, initial_state=cu(h0))
+    y1, h1 = ops.selective_scan_fn(*args, return_last_state=True, initial_state=cu(h0), segment_parallel=False)
+    assert rel_err(y, y_ref) < 3e-5 and rel_err(h, h_ref) < 3e-5
+    assert rel_err(y, y1) < 2e-5 and rel_err(h, h1) < 2e-5
+
+
 def test_selective_scan_chunk_carry_equals_one_shot():
     """Carried state: scanning two halves with h_out -> h0 equals one pass (streaming contract)."""
     from cleanumamba_b200 import ops
@@ -413,3 +440,23 @@ def test_fused_dec_last_block(b, rows, crop):
     torch.cuda.synchronize()
     assert not torch.isnan(out).any()
     assert rel_err(out, ref) < GEMM_TOL["f16x3"]
+
+
+@pytest.mark.parametrize("shape,dim,off,n_ch,heads", [((16, 12, 4), 0, 0, 16, 1), ((16, 12, 4), 1, 0, 12, 1), ((4096, 512), 0, 2048, 512, 4),
+                                                      ((160, 2048), 1, 5, 2000, 1), ((768,), 0, 0, 768, 1), ((53, 111, 4), 1, 3, 50, 2),
+                                                      ((2048, 64), 1, 0, 64, 1)])
+def test_channel_importance_kernel_matches_oracle(shape, dim, off, n_ch, heads):
+    """cum_channel_importance_fwd + importance.channel_importances == the reference's PruningModule.channel_importances
+    (pruninggroup.py:160-226; restated in the oracle, which is pinned to the live reference on CPU)."""
+    from cleanumamba_b200 import importance
+    g = torch.Generator().manual_seed(sum(shape) + dim)
+    w, gr = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g) * 1e-3
+    want = orc.channel_importances(w, gr, dim, off, n_ch, heads)
+    got = importance.channel_importances(w.to(dev()), gr.to(dev()), dim, off, n_ch, heads)
+    for k in ("weight", "grad", "taylor_individual", "taylor_squared_individual"):
+        assert rel_err(got[k], want[k]) < 1e-5, k
+    # |sum w g| cancels: bound the error by the un-cancelled magnitude
+    assert ((got["taylor_group"].cpu() - want["taylor_group"]).abs() <= 1e-5 * want["taylor_individual"] + 1e-12).all()
+    assert got["n_parameters"] == want["n_parameters"]
+    only_w = importance.channel_importances(w.to(dev()), None, dim, off, n_ch, heads)
+    assert only_w["grad"] is None and rel_err(only_w["weight"], want["weight"]) < 1e-5
