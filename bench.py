@@ -574,6 +574,9 @@ def main():
             extras["stream"] = {f"hops{h}": measure_stream(net_s, net_s.engine(), dev, rank, world, dist, hi - lo, h,
                                                             max(3, min(args.steps, 10)), 3, math=args.math, total=4096)
                                 for h in (16, 1)}
+            # the reference's real-time use -- ONE stream fed hop by hop (module-level feed(): CUDA-graph replay)
+            extras["stream"]["single_stream_hop1_graph"] = measure_stream(net_s, net_s.engine(), dev, rank, world, dist, 1, 1, 50, 5,
+                                                                            graph=True, math=args.math)
             del net_s
         except Exception as exc:      # noqa: BLE001
             extras["stream"] = {"error": repr(exc)}
