@@ -290,7 +290,7 @@ def run_stream(args, net, eng, dev, rank, world, dist):
         dist.destroy_process_group()
 
 
-def measure_train(net, dev, rank, world, dist, B, seconds, steps, warmup, math="f16x3", model="e8"):
+def measure_train(net, dev, rank, world, dist, B, seconds, steps, warmup, math="f16x3", model="e8", fused_loss=True):
     """configs[3]: E8-full training step (fwd + L1 + multi-resolution STFT loss + bwd + fused Adam), per-GPU batch fixed
     (weak scaling), gradients averaged with the bucketed NCCL all-reduce overlapped with the backward.  At N > 1 the step is
     also timed WITHOUT the all-reduce and the compute stream's stall on NCCL is measured with CUDA events (exposed time)."""
@@ -300,7 +300,11 @@ def measure_train(net, dev, rank, world, dist, B, seconds, steps, warmup, math="
     if dist is not None:
         apply_gradient_allreduce(net)
     opt = torch.optim.Adam(net.parameters(), lr=2e-4, fused=True)
-    mr = MultiResolutionSTFTLoss(**DEFAULT_STFT_CONFIG).to(dev)
+    if fused_loss:      # windowed DFT as a tcgen05 GEMM + fused reductions + own backward (cleanumamba_b200/fused_loss.py)
+        from cleanumamba_b200.fused_loss import FusedMultiResolutionSTFTLoss
+        mr = FusedMultiResolutionSTFTLoss(**DEFAULT_STFT_CONFIG)
+    else:               # the PyTorch restatement of the reference loss (torch.stft / cuFFT): the checker
+        mr = MultiResolutionSTFTLoss(**DEFAULT_STFT_CONFIG).to(dev)
     noisy = synth_noisy(B, seconds, 1234 + rank).to(dev)
     clean = synth_noisy(B, seconds, 99 + rank).to(dev) * 0.5
     work = torch.empty_like(noisy)
@@ -366,6 +370,8 @@ def measure_train(net, dev, rank, world, dist, B, seconds, steps, warmup, math="
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"CleanUMamba {model.upper()} full training step: fwd + L1 + MR-STFT loss "
                                   f"+ bwd + fused Adam (PyTorch), batch {B} x {seconds:g} s per GPU, math={math}",
+                      "loss": "L1 (PyTorch) + fused MR-STFT loss (DFT as tcgen05 GEMM, own backward)" if fused_loss
+                              else "L1 + MR-STFT loss in PyTorch (torch.stft / cuFFT)",
                       "global_batch": world * B, "parallelism": f"dp{world}",
                       "grad_allreduce": allreduce,
                       "our_kernels_ms_per_step": round(kernel_ms, 3), "final_loss": round(float(loss), 5)},
@@ -376,7 +382,8 @@ def measure_train(net, dev, rank, world, dist, B, seconds, steps, warmup, math="
 
 def run_train(args, net, dev, rank, world, dist):
     B = args.batch if args.batch != 64 else 16
-    rec = measure_train(net, dev, rank, world, dist, B, args.seconds, args.steps, args.warmup, math=args.math, model=args.model)
+    rec = measure_train(net, dev, rank, world, dist, B, args.seconds, args.steps, args.warmup, math=args.math, model=args.model,
+                        fused_loss=args.loss == "fused")
     if rank == 0:
         print(json.dumps(rec), flush=True)
     if dist is not None:
@@ -459,6 +466,7 @@ def main():
     ap.add_argument("--hops", type=int, default=16, help="[stream] hops (2^D samples each) per feed() call")
     ap.add_argument("--graph", action="store_true", help="[stream] replay a captured CUDA graph of the steady-state feed()")
     ap.add_argument("--streams-total", type=int, default=0, help="[stream] total streams, sharded over the ranks (overrides --streams)")
+    ap.add_argument("--loss", default="fused", choices=["fused", "pytorch"], help="[train] MR-STFT loss implementation")
     ap.add_argument("--no-extras", action="store_true", help="skip the `train` / `stream` sub-records of the default line")
     args = ap.parse_args()
     cfg = CONFIGS[args.model]

@@ -262,6 +262,21 @@ int cum_convt_out_bwd(const float* g, int batch, int rows_in, int c_pad, const f
     return convt_out_bwd(g, batch, rows_in, c_pad, w, scale, dout, dout_stride, length, dg, dw, dbias, kernel, stride,
                          (cudaStream_t)stream);
 }
+int cum_stft_frames_fwd(const float* x, const float* y, long long sig_stride, int length, int batch, int n_frames, int hop, int win,
+                        int n_fft, float* frames, cum_stream_t stream) {
+    return stft_frames_fwd(x, y, sig_stride, length, batch, n_frames, hop, win, n_fft, frames, (cudaStream_t)stream);
+}
+int cum_stft_loss_reduce_fwd(const float* sx, const float* sy, long long rows, int bins, int ld, double* sums, cum_stream_t stream) {
+    return stft_loss_reduce_fwd(sx, sy, rows, bins, ld, sums, (cudaStream_t)stream);
+}
+int cum_stft_loss_bwd(const float* sx, const float* sy, long long rows, int bins, int ld, const float* coef, float* dsx,
+                      cum_stream_t stream) {
+    return stft_loss_bwd(sx, sy, rows, bins, ld, coef, dsx, (cudaStream_t)stream);
+}
+int cum_stft_overlap_add(const float* dframes, int length, int batch, int n_frames, int hop, int win, int n_fft, float* dx,
+                         long long dx_stride, cum_stream_t stream) {
+    return stft_overlap_add(dframes, length, batch, n_frames, hop, win, n_fft, dx, dx_stride, (cudaStream_t)stream);
+}
 int cum_channel_importance_fwd(const float* w, const float* g, int rows, int cols, long long ldw, long long ldg, float* out_rows,
                                float* out_cols, cum_stream_t stream) {
     return channel_importance_fwd(w, g, rows, cols, ldw, ldg, out_rows, out_cols, (cudaStream_t)stream);

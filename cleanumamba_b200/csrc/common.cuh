@@ -109,6 +109,12 @@ int convt_out_bwd(const float* g, int batch, int rows_in, int c_pad, const float
                   const float* dout, long long dout_stride, int length, float* dg, float* dw, float* dbias, int kernel,
                   int stride, cudaStream_t st);
 int selective_scan_bwd(const cum_scan_bwd_desc& d, cudaStream_t st);
+int stft_frames_fwd(const float* x, const float* y, long long sig_stride, int length, int batch, int n_frames, int hop, int win,
+                    int n_fft, float* frames, cudaStream_t st);
+int stft_loss_reduce_fwd(const float* sx, const float* sy, long long rows, int bins, int ld, double* sums, cudaStream_t st);
+int stft_loss_bwd(const float* sx, const float* sy, long long rows, int bins, int ld, const float* coef, float* dsx, cudaStream_t st);
+int stft_overlap_add(const float* dframes, int length, int batch, int n_frames, int hop, int win, int n_fft, float* dx,
+                     long long dx_stride, cudaStream_t st);
 int channel_importance_fwd(const float* w, const float* g, int rows, int cols, long long ldw, long long ldg, float* out_rows,
                            float* out_cols, cudaStream_t st);
 

@@ -327,6 +327,25 @@ typedef struct cum_scan_bwd_desc {
 } cum_scan_bwd_desc;
 int cum_selective_scan_bwd(const cum_scan_bwd_desc* desc, cum_stream_t stream);
 
+/* ---- multi-resolution STFT loss (src/util/stft_loss.py:16-184, util.py:322) --------------------------------- */
+/* One resolution of the loss = a windowed DFT run as a tap-GEMM on the tensor cores (cum_gemm_bias_act_fwd with the hann window
+ * folded into a (2F, win_length) cos / -sin basis, re / im interleaved) between the kernels below.
+ * frames[(s, b, fr), k] = sig_s[b, reflect(fr hop + k + (n_fft - win)/2 - n_fft/2)]: torch.stft's center=True reflect padding by index
+ * arithmetic; s = 0 predicted (x), 1 target (y; NULL = one signal); frames: ((1|2) batch n_frames, win) fp32. */
+int cum_stft_frames_fwd(const float* x, const float* y, long long sig_stride, int length, int batch, int n_frames, int hop, int win,
+                        int n_fft, float* frames, cum_stream_t stream);
+/* sums[0..2] += sum (ym - xm)^2, sum ym^2, sum |log ym - log xm| over rows x bins, m = sqrt(max(re^2 + im^2, 1e-7)) (stft_loss.py:35,
+ * :57, :80).  sx / sy: (rows, ld) spectrograms, (re, im) of bin f at columns 2f, 2f+1.  sums: 3 doubles, zeroed by the caller. */
+int cum_stft_loss_reduce_fwd(const float* sx, const float* sy, long long rows, int bins, int ld, double* sums, cum_stream_t stream);
+/* dsx = coef[0] d(sum (ym-xm)^2 / 2)/dsx ... : gradient of the two loss terms w.r.t. the predicted spectrogram,
+ * dxm = -coef[0] (ym - xm) - coef[1] sign(log ym - log xm) / xm, d(re, im) = dxm (re, im) / xm (0 under the floor); coef: 2 floats on
+ * the device (coef[0] = k_sc / (sqrt(A) sqrt(B)), coef[1] = k_mag / count).  dsx may alias sx.  Pad columns are zeroed. */
+int cum_stft_loss_bwd(const float* sx, const float* sy, long long rows, int bins, int ld, const float* coef, float* dsx,
+                      cum_stream_t stream);
+/* dx[b, reflect(...)] += dframes[(b, fr), k]: transpose of cum_stft_frames_fwd for the predicted signal (atomic accumulation). */
+int cum_stft_overlap_add(const float* dframes, int length, int batch, int n_frames, int hop, int win, int n_fft, float* dx,
+                         long long dx_stride, cum_stream_t stream);
+
 /* ---- pruning support ---------------------------------------------------------------------------- */
 /* Channel-importance statistics of a weight matrix w (rows, cols; row strides ldw / ldg) and its gradient g, the inputs of the
  * reference's pruning criteria (src/pruning/pruninggroup.py:160-226 `channel_importances`, importance.py:39): for every row and

@@ -460,3 +460,25 @@ def test_channel_importance_kernel_matches_oracle(shape, dim, off, n_ch, heads):
     assert got["n_parameters"] == want["n_parameters"]
     only_w = importance.channel_importances(w.to(dev()), None, dim, off, n_ch, heads)
     assert only_w["grad"] is None and rel_err(only_w["weight"], want["weight"]) < 1e-5
+
+
+@pytest.mark.parametrize("b,t", [(2, 16000), (3, 5003), (1, 1025)])
+def test_fused_mr_stft_loss_matches_pytorch_restatement(b, t):
+    """FusedMultiResolutionSTFTLoss (DFT as tcgen05 GEMM + fused reductions, own backward) against loss.MultiResolutionSTFTLoss
+    -- the PyTorch restatement that tests/test_cpu_* pin to the reference's stft_loss.py run live -- values and d/dx."""
+    from cleanumamba_b200.fused_loss import FusedMultiResolutionSTFTLoss
+    from cleanumamba_b200.loss import DEFAULT_STFT_CONFIG, MultiResolutionSTFTLoss
+    g = torch.Generator().manual_seed(t)
+    clean = torch.randn(b, t, generator=g) * 0.1
+    pred = (clean + torch.randn(b, t, generator=g) * 0.03).requires_grad_()
+    sc_ref, mag_ref = MultiResolutionSTFTLoss(**DEFAULT_STFT_CONFIG)(pred, clean)
+    (2.0 * sc_ref + 0.7 * mag_ref).backward()
+    pd = pred.detach().to(dev()).requires_grad_()
+    sc, mag = FusedMultiResolutionSTFTLoss(**DEFAULT_STFT_CONFIG)(pd, clean.to(dev()))
+    (2.0 * sc + 0.7 * mag).backward()
+    assert abs(sc.item() - sc_ref.item()) < 1e-5 * abs(sc_ref.item()) + 1e-7
+    assert abs(mag.item() - mag_ref.item()) < 1e-5 * abs(mag_ref.item()) + 1e-7
+    scale = pred.grad.abs().max().item()
+    err = (pd.grad.cpu() - pred.grad).abs().max().item()
+    print(f"\n[fused MR-STFT loss b={b} t={t}] sc {sc.item():.6f} mag {mag.item():.6f} grad max-abs err / scale {err / scale:.2e}")
+    assert err / scale < 1e-3
