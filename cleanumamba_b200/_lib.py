@@ -37,14 +37,15 @@ class Enc0BlockDesc(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_stride", C.c_longlong), ("batch", C.c_int), ("length", C.c_int),
                 ("conv_w", C.c_void_p), ("conv_b", C.c_void_p), ("glu_w_hi", C.c_void_p), ("glu_w_lo", C.c_void_p),
                 ("glu_b", C.c_void_p), ("acc_scale", C.c_float), ("w_lo_is_zero", C.c_int),
-                ("out", C.c_void_p), ("rows_out", C.c_int), ("channels", C.c_int)]
+                ("out", C.c_void_p), ("rows_out", C.c_int), ("channels", C.c_int), ("channels_out", C.c_int)]
 
 
 class DecLastBlockDesc(C.Structure):
     _fields_ = [("a", C.c_void_p), ("batch", C.c_int), ("rows_in", C.c_int),
                 ("glu_w_hi", C.c_void_p), ("glu_w_lo", C.c_void_p), ("glu_b", C.c_void_p), ("acc_scale", C.c_float),
                 ("w_lo_is_zero", C.c_int), ("convt_w", C.c_void_p), ("convt_bias", C.c_float), ("scale", C.c_void_p),
-                ("out", C.c_void_p), ("out_stride", C.c_longlong), ("out_length", C.c_int), ("channels", C.c_int)]
+                ("out", C.c_void_p), ("out_stride", C.c_longlong), ("out_length", C.c_int), ("channels", C.c_int),
+                ("channels_gated", C.c_int)]
 
 
 class ScanDesc(C.Structure):

@@ -53,6 +53,7 @@ struct FusedEndParams {
     const float* bias;          // (128) interleaved GLU bias
     float acc_scale;            // 2^-k undoing the fp16 weight pre-scale
     int skip_wlo;               // low weight half is exactly zero: two MMA passes
+    int c_in, n_out;            // padded channel counts actually present (<= 64 / <= 128): the rest of the 64 x 128 tile is zero
     float out_bias; const float* scale; float* out; long long out_stride; int out_length;
 };
 
@@ -131,10 +132,15 @@ fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // small operands: GLU bias, the four taps per channel as one float4, conv bias
-    for (int i = threadIdx.x; i < FE_N; i += FE_THREADS) bias_s[i] = __ldg(p.bias + i);
-    for (int i = threadIdx.x; i < 64; i += FE_THREADS) {
-        taps_s[i] = make_float4(__ldg(p.taps + i), __ldg(p.taps + 64 + i), __ldg(p.taps + 128 + i), __ldg(p.taps + 192 + i));
-        b0_s[i] = (KIND == 0) ? __ldg(p.b0 + i) : 0.f;
+    // (narrower layers -- pruned checkpoints -- are zero-padded to the 64 x 128 tile: zero taps / biases here, zero-filled TMA boxes)
+    for (int i = threadIdx.x; i < FE_N; i += FE_THREADS) bias_s[i] = i < p.n_out ? __ldg(p.bias + i) : 0.f;
+    {
+        const int ct = (KIND == 0) ? p.c_in : p.n_out / 2;          // channels the taps apply to: conv outputs / gated channels
+        for (int i = threadIdx.x; i < 64; i += FE_THREADS) {
+            taps_s[i] = i < ct ? make_float4(__ldg(p.taps + i), __ldg(p.taps + ct + i), __ldg(p.taps + 2 * ct + i), __ldg(p.taps + 3 * ct + i))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            b0_s[i] = (KIND == 0 && i < ct) ? __ldg(p.b0 + i) : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -395,11 +401,12 @@ static int launch_fused_end(const CUtensorMap& tmWh, const CUtensorMap& tmWl, co
     return CUM_OK;
 }
 
-static int weight_maps(const void* w_hi, const void* w_lo, CUtensorMap* tmWh, CUtensorMap* tmWl) {
+// (n_out, c_in) fp16 weight halves seen through a 64 x 128 box: rows / columns beyond the real extents arrive as zeros
+static int weight_maps(const void* w_hi, const void* w_lo, int c_in, int n_out, CUtensorMap* tmWh, CUtensorMap* tmWl) {
     CUM_REQUIRE(w_hi && aligned16(w_hi) && (!w_lo || aligned16(w_lo)), "fused block: weight halves must be 16-byte aligned");
-    int rc = make_tensor_map(tmWh, w_hi, FE_K, FE_N, 1, FE_K, (uint64_t)FE_K * FE_N, FE_K, FE_N, "W_hi", true, true);
+    int rc = make_tensor_map(tmWh, w_hi, (uint64_t)c_in, (uint64_t)n_out, 1, (uint64_t)c_in, (uint64_t)c_in * n_out, FE_K, FE_N, "W_hi", true, true);
     if (rc) return rc;
-    if (w_lo) return make_tensor_map(tmWl, w_lo, FE_K, FE_N, 1, FE_K, (uint64_t)FE_K * FE_N, FE_K, FE_N, "W_lo", true, true);
+    if (w_lo) return make_tensor_map(tmWl, w_lo, (uint64_t)c_in, (uint64_t)n_out, 1, (uint64_t)c_in, (uint64_t)c_in * n_out, FE_K, FE_N, "W_lo", true, true);
     *tmWl = *tmWh;
     return CUM_OK;
 }
@@ -407,14 +414,17 @@ static int weight_maps(const void* w_hi, const void* w_lo, CUtensorMap* tmWh, CU
 int enc0_block_fwd(const cum_enc0_block_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.x && d.conv_w && d.conv_b && d.glu_w_hi && d.glu_b && d.out, "enc0_block: null pointer");
     CUM_REQUIRE(d.batch > 0 && d.length > 0 && d.rows_out > 0, "enc0_block: empty problem");
-    CUM_REQUIRE(d.channels == 64, "enc0_block: the fused kernel serves the 64-channel geometry (channels=%d): use conv_in + gemm", d.channels);
+    CUM_REQUIRE(d.channels > 0 && d.channels <= 64 && d.channels % 8 == 0 && d.channels_out > 0 && d.channels_out <= 64 && d.channels_out % 8 == 0,
+                "enc0_block: the fused kernel serves up to 64 channels, multiples of 8 (channels=%d, channels_out=%d): use conv_in + gemm",
+                d.channels, d.channels_out);
     CUM_REQUIRE(d.glu_w_lo || d.w_lo_is_zero, "enc0_block: glu_w_lo missing");
     CUM_REQUIRE(aligned16(d.out), "enc0_block: out must be 16-byte aligned");
     CUM_REQUIRE(d.acc_scale > 0.f, "enc0_block: acc_scale = 1 / (weight scale passed to cum_split_f16)");
     CUtensorMap tmWh, tmWl, tmOut;
-    int rc = weight_maps(d.glu_w_hi, d.w_lo_is_zero ? nullptr : d.glu_w_lo, &tmWh, &tmWl);
+    int rc = weight_maps(d.glu_w_hi, d.w_lo_is_zero ? nullptr : d.glu_w_lo, d.channels, 2 * d.channels_out, &tmWh, &tmWl);
     if (rc) return rc;
-    rc = make_tensor_map(&tmOut, d.out, 64, (uint64_t)d.rows_out, (uint64_t)d.batch, 64, (uint64_t)d.rows_out * 64, 32, FE_ROWS, "enc0 out");
+    const uint64_t co = (uint64_t)d.channels_out;
+    rc = make_tensor_map(&tmOut, d.out, co, (uint64_t)d.rows_out, (uint64_t)d.batch, co, (uint64_t)d.rows_out * co, 32, FE_ROWS, "enc0 out");
     if (rc) return rc;
     FusedEndParams p;
     memset(&p, 0, sizeof(p));
@@ -424,24 +434,28 @@ int enc0_block_fwd(const cum_enc0_block_desc& d, cudaStream_t st) {
     CUM_REQUIRE(total < (1ll << 31), "enc0_block: too many tiles");
     p.total_tiles = (int)total;
     p.taps = d.conv_w; p.b0 = d.conv_b; p.bias = d.glu_b; p.acc_scale = d.acc_scale; p.skip_wlo = d.w_lo_is_zero ? 1 : 0;
+    p.c_in = d.channels; p.n_out = 2 * d.channels_out;
     return launch_fused_end<0>(tmWh, tmWl, tmOut, p, st);
 }
 
 int dec_last_block_fwd(const cum_dec_last_block_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.a && d.glu_w_hi && d.glu_b && d.convt_w && d.out, "dec_last_block: null pointer");
     CUM_REQUIRE(d.batch > 0 && d.rows_in > 0 && d.out_length > 0, "dec_last_block: empty problem");
-    CUM_REQUIRE(d.channels == 64, "dec_last_block: the fused kernel serves the 64-channel geometry (channels=%d): use gemm + convt_out", d.channels);
+    CUM_REQUIRE(d.channels > 0 && d.channels <= 64 && d.channels % 8 == 0 && d.channels_gated > 0 && d.channels_gated <= 64 && d.channels_gated % 8 == 0,
+                "dec_last_block: the fused kernel serves up to 64 channels, multiples of 8 (channels=%d, channels_gated=%d): use gemm + convt_out",
+                d.channels, d.channels_gated);
     CUM_REQUIRE(d.glu_w_lo || d.w_lo_is_zero, "dec_last_block: glu_w_lo missing");
     CUM_REQUIRE(aligned16(d.a), "dec_last_block: a must be 16-byte aligned");
     CUM_REQUIRE(d.acc_scale > 0.f, "dec_last_block: acc_scale = 1 / (weight scale passed to cum_split_f16)");
     CUM_REQUIRE(d.out_length <= 2 * d.rows_in + 2, "dec_last_block: out_length exceeds 2 rows_in + 2");
     CUtensorMap tmWh, tmWl;
-    int rc = weight_maps(d.glu_w_hi, d.w_lo_is_zero ? nullptr : d.glu_w_lo, &tmWh, &tmWl);
+    int rc = weight_maps(d.glu_w_hi, d.w_lo_is_zero ? nullptr : d.glu_w_lo, d.channels, 2 * d.channels_gated, &tmWh, &tmWl);
     if (rc) return rc;
     FusedEndParams p;
     memset(&p, 0, sizeof(p));
     CUtensorMap tmIn;
-    rc = make_tensor_map(&tmIn, d.a, 64, (uint64_t)d.rows_in, (uint64_t)d.batch, 64, (uint64_t)d.rows_in * 64, 32, FE_ROWS, "dec_last in");
+    const uint64_t ci = (uint64_t)d.channels;
+    rc = make_tensor_map(&tmIn, d.a, ci, (uint64_t)d.rows_in, (uint64_t)d.batch, ci, (uint64_t)d.rows_in * ci, 32, FE_ROWS, "dec_last in");
     if (rc) return rc;
     p.rows = d.rows_in; p.batch = d.batch;
     p.tiles_per_clip = (int)cdiv((long long)d.rows_in + 1, FE_ROWS - 1);
@@ -449,6 +463,7 @@ int dec_last_block_fwd(const cum_dec_last_block_desc& d, cudaStream_t st) {
     CUM_REQUIRE(total < (1ll << 31), "dec_last_block: too many tiles");
     p.total_tiles = (int)total;
     p.taps = d.convt_w; p.bias = d.glu_b; p.acc_scale = d.acc_scale; p.skip_wlo = d.w_lo_is_zero ? 1 : 0;
+    p.c_in = d.channels; p.n_out = 2 * d.channels_gated;
     p.out_bias = d.convt_bias; p.scale = d.scale; p.out = d.out; p.out_stride = d.out_stride; p.out_length = d.out_length;
     return launch_fused_end<1>(tmWh, tmWl, tmIn, p, st);
 }

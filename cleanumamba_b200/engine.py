@@ -475,21 +475,21 @@ class Engine:
         prev = None
         fuse = (self.fused_ends and self.math == _lib.MATH_F16X3 and not self.bf16_io and m.glu_activation == "Sigmoid" and D > 1)
         e0, dl = meta["enc"][0], meta["dec"][D - 1]
-        fuse_e0 = fuse and e0["Hc_p"] == 64 and e0["Ho_p"] == 64
-        fuse_dl = fuse and dl["Cin_p"] == 64 and dl["Hg_p"] == 64
+        fuse_e0 = fuse and e0["Hc_p"] <= 64 and e0["Ho_p"] <= 64          # narrower (pruned) layers run zero-padded in the 64 x 128 tile
+        fuse_dl = fuse and dl["Cin_p"] <= 64 and dl["Hg_p"] <= 64
         for i, e in enumerate(meta["enc"]):
             rows = B * Ls[i + 1]
             if i == 0 and fuse_e0:
                 # whole first block in one kernel: the 64-channel conv output stays on the SM (fused_ends.cu)
-                prev = torch.empty(rows, 64, dtype=torch.float32, device=x.device)
+                prev = torch.empty(rows, e["Ho_p"], dtype=torch.float32, device=x.device)
                 d0 = _lib.Enc0BlockDesc()
                 d0.x, d0.x_stride, d0.batch, d0.length = x.data_ptr(), L, B, L
                 d0.conv_w, d0.conv_b = pk["enc0.w"].data_ptr(), pk["enc0.b"].data_ptr()
                 d0.glu_w_hi, d0.glu_w_lo, d0.glu_b = self.pk_hi["enc0.wg"].data_ptr(), self.pk_lo["enc0.wg"].data_ptr(), pk["enc0.bg"].data_ptr()
                 d0.acc_scale = self.w_scale_inv["enc0.wg"]
                 d0.w_lo_is_zero = 1 if (self.skip_zero_lo and "enc0.wg" in self.w_lo_zero) else 0
-                d0.out, d0.rows_out, d0.channels = prev.data_ptr(), Ls[1], 64
-                self._call("enc0_block", lib.cum_enc0_block_fwd, C.byref(d0), st(), flops=2 * rows * 128 * 64,
+                d0.out, d0.rows_out, d0.channels, d0.channels_out = prev.data_ptr(), Ls[1], e["Hc_p"], e["Ho_p"]
+                self._call("enc0_block", lib.cum_enc0_block_fwd, C.byref(d0), st(), flops=2 * rows * 2 * e["Ho_p"] * e["Hc_p"],
                            nbytes=4 * B * (L + Ls[1] * e["Ho"]))
                 skips.append(prev)
                 continue
@@ -535,8 +535,8 @@ class Engine:
                 dd.acc_scale = self.w_scale_inv[f"dec{j}.wg"]
                 dd.w_lo_is_zero = 1 if (self.skip_zero_lo and f"dec{j}.wg" in self.w_lo_zero) else 0
                 dd.convt_w, dd.convt_bias, dd.scale = pk[f"dec{j}.w"].data_ptr(), meta["out_bias"], ptr(std)
-                dd.out, dd.out_stride, dd.out_length, dd.channels = out.data_ptr(), length, length, 64
-                self._call("dec_last_block", lib.cum_dec_last_block_fwd, C.byref(dd), st(), flops=2 * B * Tj * 128 * 64,
+                dd.out, dd.out_stride, dd.out_length, dd.channels, dd.channels_gated = out.data_ptr(), length, length, d["Cin_p"], d["Hg_p"]
+                self._call("dec_last_block", lib.cum_dec_last_block_fwd, C.byref(dd), st(), flops=2 * B * Tj * 2 * d["Hg_p"] * d["Cin_p"],
                            nbytes=4 * B * (Tj * d["Hg"] + length))
                 break
             # (the waveform-end kernel reads plain fp32 / bf16 rows: the last GLU output is never written as hi/lo planes)

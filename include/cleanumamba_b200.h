@@ -177,19 +177,22 @@ int cum_split_f16(const float* w, void* hi, void* lo, long long count, float sca
  *   out[t,:] = GLU(glu_b + W y[t,:])                                       Conv1d(64, 128, 1) + layers.Activation("Sigmoid")
  * The 64-channel intermediate never reaches HBM (it was a 2 x 1.3 GB round trip per 64 x 10 s batch).  Same products and
  * accumulation order as cum_conv_in_fwd followed by cum_gemm_bias_act_fwd(CUM_MATH_F16X3, CUM_EPI_GLU_SIGMOID).
- * channels must be 64 (conv outputs == GLU outputs == 64: the shipped channels_H); otherwise CUM_EINVAL -- use the two calls. */
+ * channels (conv outputs) and channels_out (GLU outputs) are padded counts <= 64, multiples of 8 (64 / 64 for the shipped
+ * channels_H; pruned checkpoints are narrower): the kernel works on a zero-padded 64 x 128 tile.  Wider: CUM_EINVAL -- use the
+ * two calls. */
 typedef struct cum_enc0_block_desc {
     const float* x; long long x_stride; int batch; int length;   /* (batch, length) waveform, already normalised */
-    const float* conv_w;     /* (4, 64) taps-major */
-    const float* conv_b;     /* (64) */
-    const void* glu_w_hi;    /* (128, 64) fp16, rows interleaved (a_c, b_c), scaled: cum_split_f16 */
+    const float* conv_w;     /* (4, channels) taps-major */
+    const float* conv_b;     /* (channels) */
+    const void* glu_w_hi;    /* (2 channels_out, channels) fp16, rows interleaved (a_c, b_c), scaled: cum_split_f16 */
     const void* glu_w_lo;    /* low halves (may be NULL when w_lo_is_zero) */
-    const float* glu_b;      /* (128) interleaved */
+    const float* glu_b;      /* (2 channels_out) interleaved */
     float acc_scale;         /* 1 / weight scale */
     int w_lo_is_zero;
-    float* out;              /* (batch, rows_out, 64) fp32 channels-last: the level-0 skip */
+    float* out;              /* (batch, rows_out, channels_out) fp32 channels-last: the level-0 skip */
     int rows_out;            /* (padded_length - 4) / 2 + 1 */
-    int channels;            /* 64 */
+    int channels;            /* conv output channels, padded (<= 64, multiple of 8) */
+    int channels_out;        /* GLU output channels, padded (<= 64, multiple of 8) */
 } cum_enc0_block_desc;
 int cum_enc0_block_fwd(const cum_enc0_block_desc* desc, cum_stream_t stream);
 
@@ -199,13 +202,14 @@ int cum_enc0_block_fwd(const cum_enc0_block_desc* desc, cum_stream_t stream);
  * for 0 <= 2p+k < out_length (<= 2 rows_in + 2).  Replaces cum_gemm_bias_act_fwd + cum_convt_out_fwd; the gated 64-channel
  * tensor never reaches HBM. */
 typedef struct cum_dec_last_block_desc {
-    const float* a; int batch; int rows_in;   /* (batch, rows_in, 64) fp32 channels-last (skip already added) */
-    const void* glu_w_hi; const void* glu_w_lo; const float* glu_b; float acc_scale; int w_lo_is_zero;
-    const float* convt_w;    /* (4, 64) taps-major */
+    const float* a; int batch; int rows_in;   /* (batch, rows_in, channels) fp32 channels-last (skip already added) */
+    const void* glu_w_hi; const void* glu_w_lo; const float* glu_b; float acc_scale; int w_lo_is_zero;   /* (2 channels_gated, channels) */
+    const float* convt_w;    /* (4, channels_gated) taps-major */
     float convt_bias;
     const float* scale;      /* (batch) per-clip std, or NULL */
     float* out; long long out_stride; int out_length;
-    int channels;            /* 64 */
+    int channels;            /* input channels, padded (<= 64, multiple of 8) */
+    int channels_gated;      /* GLU output channels, padded (<= 64, multiple of 8) */
 } cum_dec_last_block_desc;
 int cum_dec_last_block_fwd(const cum_dec_last_block_desc* desc, cum_stream_t stream);
 

@@ -379,63 +379,66 @@ def _split_f16(w_dev):
     return hi, lo, float(2.0 ** -e)
 
 
+@pytest.mark.parametrize("hc,ho", [(64, 64), (56, 56), (32, 32), (24, 40)])
 @pytest.mark.parametrize("b,length", [(1, 200), (2, 4099), (3, 33000), (1, 6)])
-def test_fused_enc0_block(b, length):
-    """cum_enc0_block_fwd == F.pad + Conv1d(1,64,4,2) + ReLU + Conv1d(64,128,1) + GLU (CleanUMamba.py:108-113), ragged lengths."""
+def test_fused_enc0_block(b, length, hc, ho):
+    """cum_enc0_block_fwd == F.pad + Conv1d(1,Hc,4,2) + ReLU + Conv1d(Hc,2 Ho,1) + GLU (CleanUMamba.py:108-113), ragged lengths,
+    the shipped 64-channel geometry and narrower (pruned) widths that run zero-padded inside the 64 x 128 tile."""
     import ctypes as C
     from cleanumamba_b200 import _lib
     lib = _lib.init(torch.device(dev()))
-    g = torch.Generator().manual_seed(length)
+    g = torch.Generator().manual_seed(length + hc)
     x = torch.randn(b, 1, length, generator=g)
-    w0, b0 = torch.randn(64, 1, 4, generator=g) * 0.5, torch.randn(64, generator=g) * 0.1
-    w1, b1 = torch.randn(128, 64, generator=g) / 8, torch.randn(128, generator=g) * 0.1
+    w0, b0 = torch.randn(hc, 1, 4, generator=g) * 0.5, torch.randn(hc, generator=g) * 0.1
+    w1, b1 = torch.randn(2 * ho, hc, generator=g) / 8, torch.randn(2 * ho, generator=g) * 0.1
     padded = max(length, 4) + (max(length, 4) % 2)
     rows = (padded - 4) // 2 + 1
-    ref = orc.glu(F.conv1d(F.relu(F.conv1d(F.pad(x, (0, padded - length)), w0, b0, stride=2)), w1[:, :, None], b1))      # (b, 64, rows)
-    wi = torch.stack([w1[:64], w1[64:]], 1).reshape(128, 64).contiguous().to(dev())
-    bi = torch.stack([b1[:64], b1[64:]], 1).reshape(128).contiguous().to(dev())
+    ref = orc.glu(F.conv1d(F.relu(F.conv1d(F.pad(x, (0, padded - length)), w0, b0, stride=2)), w1[:, :, None], b1))      # (b, ho, rows)
+    wi = torch.stack([w1[:ho], w1[ho:]], 1).reshape(2 * ho, hc).contiguous().to(dev())
+    bi = torch.stack([b1[:ho], b1[ho:]], 1).reshape(2 * ho).contiguous().to(dev())
     hi, lo, inv = _split_f16(wi)
     xd = x[:, 0].contiguous().to(dev())
     cw, cb = w0[:, 0, :].t().contiguous().to(dev()), b0.to(dev())
-    out = torch.full((b, rows, 64), float("nan"), device=dev())
+    out = torch.full((b, rows, ho), float("nan"), device=dev())
     d = _lib.Enc0BlockDesc()
     d.x, d.x_stride, d.batch, d.length = xd.data_ptr(), length, b, length
     d.conv_w, d.conv_b, d.glu_w_hi, d.glu_w_lo, d.glu_b = cw.data_ptr(), cb.data_ptr(), hi.data_ptr(), lo.data_ptr(), bi.data_ptr()
-    d.acc_scale, d.w_lo_is_zero, d.out, d.rows_out, d.channels = inv, 0, out.data_ptr(), rows, 64
+    d.acc_scale, d.w_lo_is_zero, d.out, d.rows_out, d.channels, d.channels_out = inv, 0, out.data_ptr(), rows, hc, ho
     _lib.check(lib.cum_enc0_block_fwd(C.byref(d), _lib.stream_ptr()), "enc0_block")
     torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
     assert rel_err(out.permute(0, 2, 1), ref) < GEMM_TOL["f16x3"]
-    d.channels = 56
-    assert lib.cum_enc0_block_fwd(C.byref(d), _lib.stream_ptr()) != 0      # only the 64-channel geometry is served
+    d.channels = 72
+    assert lib.cum_enc0_block_fwd(C.byref(d), _lib.stream_ptr()) != 0      # wider than the 64-channel tile: not served
 
 
+@pytest.mark.parametrize("cin,hg", [(64, 64), (56, 64), (32, 32), (40, 24)])
 @pytest.mark.parametrize("b,rows,crop", [(1, 100, 0), (2, 2047, 130), (3, 16500, 0), (1, 1, 1)])
-def test_fused_dec_last_block(b, rows, crop):
-    """cum_dec_last_block_fwd == Conv1d(64,128,1) + GLU + ConvTranspose1d(64,1,4,2) + crop + * std (CleanUMamba.py:121-128, :318-319)."""
+def test_fused_dec_last_block(b, rows, crop, cin, hg):
+    """cum_dec_last_block_fwd == Conv1d(Cin,2 Hg,1) + GLU + ConvTranspose1d(Hg,1,4,2) + crop + * std (CleanUMamba.py:121-128, :318-319)."""
     import ctypes as C
     from cleanumamba_b200 import _lib
     lib = _lib.init(torch.device(dev()))
-    g = torch.Generator().manual_seed(rows)
-    a = torch.randn(b, 64, rows, generator=g)
-    w1, b1 = torch.randn(128, 64, generator=g) / 8, torch.randn(128, generator=g) * 0.1
-    wt, bt = torch.randn(64, 1, 4, generator=g) / 8, torch.randn(1, generator=g) * 0.1
+    g = torch.Generator().manual_seed(rows + cin)
+    a = torch.randn(b, cin, rows, generator=g)
+    w1, b1 = torch.randn(2 * hg, cin, generator=g) / 8, torch.randn(2 * hg, generator=g) * 0.1
+    wt, bt = torch.randn(hg, 1, 4, generator=g) / 8, torch.randn(1, generator=g) * 0.1
     std = torch.rand(b, generator=g) + 0.5
     full = F.conv_transpose1d(orc.glu(F.conv1d(a, w1[:, :, None], b1)), wt, bt, stride=2)      # (b, 1, 2 rows + 2)
     length = 2 * rows + 2 - crop
     ref = full[:, :, :length] * std[:, None, None]
-    wi = torch.stack([w1[:64], w1[64:]], 1).reshape(128, 64).contiguous().to(dev())
-    bi = torch.stack([b1[:64], b1[64:]], 1).reshape(128).contiguous().to(dev())
+    wi = torch.stack([w1[:hg], w1[hg:]], 1).reshape(2 * hg, cin).contiguous().to(dev())
+    bi = torch.stack([b1[:hg], b1[hg:]], 1).reshape(2 * hg).contiguous().to(dev())
     hi, lo, inv = _split_f16(wi)
     acl = _cl(a)
     tw = wt[:, 0, :].t().contiguous().to(dev())
+    sd = std.to(dev())
     out = torch.full((b, 1, length), float("nan"), device=dev())
     d = _lib.DecLastBlockDesc()
     d.a, d.batch, d.rows_in = acl.data_ptr(), b, rows
     d.glu_w_hi, d.glu_w_lo, d.glu_b, d.acc_scale, d.w_lo_is_zero = hi.data_ptr(), lo.data_ptr(), bi.data_ptr(), inv, 0
-    d.convt_w, d.convt_bias, d.scale = tw.data_ptr(), float(bt[0]), std.to(dev()).data_ptr()
-    sd = std.to(dev())
-    d.scale = sd.data_ptr()
-    d.out, d.out_stride, d.out_length, d.channels = out.data_ptr(), length, length, 64
+    d.convt_w, d.convt_bias, d.scale = tw.data_ptr(), float(bt[0]), sd.data_ptr()
+    d.out, d.out_stride, d.out_length, d.channels, d.channels_gated = out.data_ptr(), length, length, cin, hg
     _lib.check(lib.cum_dec_last_block_fwd(C.byref(d), _lib.stream_ptr()), "dec_last_block")
     torch.cuda.synchronize()
     assert not torch.isnan(out).any()
