@@ -93,17 +93,25 @@ struct TcParams {
     int skip_wlo;             // split modes: the low half of the weights is exactly zero -> skip its load and its MMA pass
     int w_k_batch_stride;     // wgrad (split-K over rows): W k-coordinate += batch * this + w_k_off
     int w_k_off;
+    int mn_splits;            // MN-major wgrad: splits per clip ("batch" = clip * mn_splits + split, k_blocks K-blocks of 32 rows per split)
+    const float* acc_scale_ptr;   // optional device-side acc_scale (overrides acc_scale): scales that are computed on the device
     void* c_lo;               // OUTF == 2: low-half plane of the output (c is the high-half plane), fp16
     const void* addend_lo;    // OUTF == 2: low-half plane of the addend
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
 // OUTF: output (and addend) format -- 0 fp32, 1 bf16, 2 fp16 hi / lo planes ("hl16": what TC_F16PS consumes)
-template <int MODE, int BN, int EPI, int OUTF, bool CTA2>
+// MNM (weight gradients, MODE = TC_F16PS): both operands are MN-major -- C[n, k] = sum_rows dZ[row, n] A[row + shift, k] contracts
+// over the ROW dimension, along which neither dZ nor A is contiguous.  Instead of transposing both into K-major copies first, the
+// TMA boxes (64 channels x 32 rows of an fp16 plane, 128-byte swizzle) land in shared memory exactly as the canonical MN-major
+// UMMA layout (128-byte rows along M / N, 8-row groups 1024 B apart, 64-channel slabs 4 KB apart) and the instruction descriptor
+// marks A and B as transposed.
+template <int MODE, int BN, int EPI, int OUTF, bool CTA2, int MNM = 0>
 __global__ void __launch_bounds__(TcCfg<MODE, BN, CTA2>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const TcParams p) {
     using Cfg = TcCfg<MODE, BN, CTA2>;
+    static_assert(!MNM || MODE == TC_F16PS, "MN-major operands: pre-split fp16 planes only");
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool X3 = Cfg::PASS3;              // three MMA passes, W_lo exists
     constexpr bool SPL = Cfg::SPLIT;             // splitter warps between TMA and MMA
@@ -200,7 +208,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // bytes this stage will receive: A + W_hi (+ W_lo unless it is skipped); non-split modes have no W_lo at all
                 const uint32_t tx = (X3 && !load_lo) ? Cfg::TX_BYTES - Cfg::W_BYTES : Cfg::TX_BYTES;
                 const int wk = kb * Cfg::BK + b * p.w_k_batch_stride + p.w_k_off;
-                if (CTA2 && !SPL) {
+                if constexpr (MNM != 0) {
+                    // split `sp` of clip `clip`: rows [r, r + 32) of both operands (the activation side shifted by the conv tap);
+                    // rows / channels outside the tensors arrive as zeros
+                    const int clip = b / p.mn_splits, sp = b - clip * p.mn_splits;
+                    const int r = (sp * p.k_blocks + kb) * 32;
+                    const uint32_t bar = CTA2 ? mapa_rank(full_bar(s), 0) : full_bar(s);
+                    if (!CTA2 || rank == 0) mbar_arrive_expect_tx(full_bar(s), (CTA2 ? 2 : 1) * tx);
+                    auto ld = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+                        if (CTA2) tma_load_3d_2sm(dst, m, bar, c0, c1, clip); else tma_load_3d(dst, m, bar, c0, c1, clip);
+                    };
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        ld(smem_base + ahi_off(s) + i * 4096, &tmA, m0 + 64 * i, r);
+                        ld(smem_base + alo_off(s) + i * 4096, &tmAl, m0 + 64 * i, r);
+                    }
+#pragma unroll
+                    for (int i = 0; i < Cfg::W_ROWS / 64; ++i) {
+                        ld(smem_base + w_off(s) + i * 4096, &tmWh, wn + 64 * i, r + shift);
+                        if (load_lo) ld(smem_base + wlo_off(s) + i * 4096, &tmWl, wn + 64 * i, r + shift);
+                    }
+                } else if (CTA2 && !SPL) {
                     // no splitter in between: the leader's MMA thread waits for the bytes of BOTH CTAs on its own barrier
                     const uint32_t lbar = mapa_rank(full_bar(s), 0);
                     if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * tx);
@@ -234,20 +262,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // c=f32 (1<<4); a/b format 2 = tf32, 1 = bf16 (bits 7, 10); K-major both; N>>3 at bit 17, M>>4 at bit 24
             const uint32_t fmt = F16 ? 0u : ((BF || P16) ? 1u : 2u);       // 0 = f16, 1 = bf16, 2 = tf32
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((umma_n >> 3) << 17) |
-                                   ((uint32_t)((CTA2 ? 2 * TC_BM : TC_BM) >> 4) << 24);
+                                   ((uint32_t)((CTA2 ? 2 * TC_BM : TC_BM) >> 4) << 24) |
+                                   (MNM ? ((1u << 15) | (1u << 16)) : 0u);           // a_major / b_major = MN
             const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
             if (CTA2) mbar_wait_cluster(tempty_bar(acc), acc_ph ^ 1u); else mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
             tc_fence_after();
             for (int it = 0; it < k_iters; ++it) {
                 if (CTA2) mbar_wait_cluster(SPL ? split_bar(s) : full_bar(s), ph); else mbar_wait(SPL ? split_bar(s) : full_bar(s), ph);
                 tc_fence_after();
-                const uint64_t adesc = BF ? umma_desc_sw64(smem_base + ahi_off(s)) : umma_desc_sw128(smem_base + ahi_off(s));
-                const uint64_t bdesc = BF ? umma_desc_sw64(smem_base + w_off(s)) : umma_desc_sw128(smem_base + w_off(s));
-                const uint64_t alo = BF ? umma_desc_sw64(smem_base + alo_off(s)) : umma_desc_sw128(smem_base + alo_off(s));
-                const uint64_t blo = BF ? umma_desc_sw64(smem_base + wlo_off(s)) : umma_desc_sw128(smem_base + wlo_off(s));
+                const uint64_t adesc = MNM ? umma_desc_mn_sw128(smem_base + ahi_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + ahi_off(s)) : umma_desc_sw128(smem_base + ahi_off(s));
+                const uint64_t bdesc = MNM ? umma_desc_mn_sw128(smem_base + w_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + w_off(s)) : umma_desc_sw128(smem_base + w_off(s));
+                const uint64_t alo = MNM ? umma_desc_mn_sw128(smem_base + alo_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + alo_off(s)) : umma_desc_sw128(smem_base + alo_off(s));
+                const uint64_t blo = MNM ? umma_desc_mn_sw128(smem_base + wlo_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + wlo_off(s)) : umma_desc_sw128(smem_base + wlo_off(s));
 #pragma unroll
                 for (int kk = 0; kk < Cfg::BK / Cfg::UMMA_K; ++kk) {
-                    const uint64_t koff = (uint64_t)(kk * 2);          // 32 bytes per k-step in both element types
+                    // K-major: 32 bytes per k-step in both element types; MN-major: 16 rows of 128 bytes = two 1024-byte row groups
+                    const uint64_t koff = MNM ? (uint64_t)(kk * 128) : (uint64_t)(kk * 2);
                     if (P16) {
                         umma_f16_any<CTA2>(tmem_d, adesc + koff, bdesc + koff, idesc, (it | kk) != 0);
                     } else if (BF) {
@@ -287,6 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================================================================== epilogue (16 warps)
         const int q = warp & 3;                 // TMEM lane quarter this warp may touch
         const int sub = (warp - 4) >> 2;        // which of every four 32-column chunks
+        const float acc_scale = p.acc_scale_ptr ? __ldg(p.acc_scale_ptr) : p.acc_scale;
         const int tq = lane & 3, tr = lane >> 2;
         int tcount = 0;
         const uint32_t tempty_leader = CTA2 ? mapa_rank(tempty_bar(0), 0) : 0u;
@@ -395,8 +426,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 float o[2];
 #pragma unroll
                                 for (int k = 0; k < 2; ++k) {
-                                    const float x0 = fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x);
-                                    const float x1 = fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y);
+                                    const float x0 = fmaf(v[h][4 * k + 2 * rh + 0], acc_scale, bv[k].x);
+                                    const float x1 = fmaf(v[h][4 * k + 2 * rh + 1], acc_scale, bv[k].y);
                                     o[k] = x0 * tc_gate<EPI>(p.epi, x1);
                                     if (has_add) o[k] += ad[h][rh][k].x;
                                 }
@@ -419,8 +450,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     float o[2];
 #pragma unroll
                                     for (int k = 0; k < 2; ++k) {
-                                        const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
-                                        const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
+                                        const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
+                                        const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
                                         o[k] = x0 * tc_gate<EPI>(p.epi, x1);
                                         if (has_add) o[k] += ad[h][rh][k].x;
                                     }
@@ -430,8 +461,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     float2 o[2];
 #pragma unroll
                                     for (int k = 0; k < 2; ++k) {
-                                        const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
-                                        const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
+                                        const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
+                                        const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
                                         o[k] = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
                                         if (has_add) { o[k].x += ad[h][rh][k].x; o[k].y += ad[h][rh][k].y; }
                                     }
@@ -458,8 +489,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int k = 0; k < 2; ++k) {
                                 if (!kok[k]) break;
                                 char* const dst = cp(h, rh) + (GLU ? 4 * k : 8 * k) * CES;
-                                const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], p.acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
-                                const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], p.acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
+                                const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
+                                const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
                                 if (EPI == TC_EPI_ATOMIC_ADD) {
                                     atomicAdd(reinterpret_cast<float*>(dst), x0);
                                     atomicAdd(reinterpret_cast<float*>(dst) + 1, x1);
@@ -770,6 +801,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.c_lo = d.c_lo; p.addend_lo = d.addend_lo;
     p.skip_wlo = (X3 && d.w_lo_is_zero) ? 1 : 0;
     p.w_k_batch_stride = g_wgrad_kbs; p.w_k_off = g_wgrad_koff;
+    p.mn_splits = 0; p.acc_scale_ptr = nullptr;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
     CUM_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
     if (CTA2) {
@@ -929,7 +961,12 @@ static WgradPlan plan_wgrad(const cum_wgrad_desc& d) {
     return w;
 }
 
-long long wgrad_tc_workspace_bytes(const cum_wgrad_desc& d) { return (long long)plan_wgrad(d).ws_bytes; }
+struct WgradMnPlan { int clips; long long rows_z, rows_a; size_t z_elems, a_elems, ws_bytes; };
+static WgradMnPlan plan_wgrad_mn(const cum_wgrad_desc& d);
+long long wgrad_tc_workspace_bytes(const cum_wgrad_desc& d) {       // either path fits
+    const size_t a = plan_wgrad(d).ws_bytes, b = plan_wgrad_mn(d).ws_bytes;
+    return (long long)(a > b ? a : b);
+}
 
 template <int BN> static int launch_wgrad_gemm(const cum_gemm_desc& g, cudaStream_t st) {
     if constexpr (BN == 256) {      // CTA pairs (half a W^T tile per CTA) when the output has more than one 128-row tile
@@ -938,10 +975,185 @@ template <int BN> static int launch_wgrad_gemm(const cum_gemm_desc& g, cudaStrea
     return launch_tc<TC_TF32X3, BN, TC_EPI_ATOMIC_ADD, 0>(g, st);
 }
 
+// ------------------------------------------------------------------------------------------------ MN-major weight gradients
+// dW_s[n, k] = sum_{b, r} dZ[b, r, n] A[b, r + shift_s, k] on the tensor cores WITHOUT transposing either operand (the K-major path
+// above spends ~40 % of its time in the two transposing pre-passes) and at the fp16 tensor rate:
+//   1. amax(dZ) -> a power-of-two scale computed ON THE DEVICE that lifts the gradients into fp16's range (back-propagated values
+//      are ~1e-6: unscaled they underflow; the reciprocal reaches the GEMM epilogue through TcParams::acc_scale_ptr)
+//   2. elementwise split of scale * dZ and of A into fp16 hi / lo planes, row-major as they are
+//   3. per tap one split-K GEMM (splits = (clip, row range)) whose TMA boxes are MN-major operand slabs (gemm_tc_kernel<..., MNM>),
+//      three fp16 MMA passes, atomic accumulation into the zero-initialised gradient.
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long bs, long long rs, int batch, int rows, int cols4,
+                                                    unsigned* __restrict__ amax_bits) {
+    const long long total = (long long)batch * rows * cols4;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols4);
+        const long long br = i / cols4;
+        const int r = (int)(br % rows), b = (int)(br / rows);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (long long)b * bs + (long long)r * rs) + c);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));      // non-negative floats order like their bits
+}
+
+// hi = fp16(s x) (saturating), lo = fp16(s x - hi); s = 2^(15 - e) with amax = f 2^e, f in [0.5, 1) (1 when no amax is given);
+// compact (batch, rows, cols) planes.  inv_scale_out[0] = 1 / s.
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long bs, long long rs, int batch, int rows, int cols4,
+                                                            __half* __restrict__ hi, __half* __restrict__ lo,
+                                                            const unsigned* __restrict__ amax_bits, float* __restrict__ inv_scale_out) {
+    float s = 1.f;
+    if (amax_bits) {
+        const float am = __uint_as_float(*amax_bits);
+        if (am > 0.f) {
+            int e;
+            frexpf(am, &e);
+            s = ldexpf(1.f, 15 - e);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale_out[0] = 1.f / s;
+    }
+    const long long total = (long long)batch * rows * cols4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols4);
+        const long long br = i / cols4;
+        const int r = (int)(br % rows), b = (int)(br / rows);
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + (long long)b * bs + (long long)r * rs) + c);
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        const uint32_t h0 = cvt_f16x2_sat(v.x, v.y), h1 = cvt_f16x2_sat(v.z, v.w);
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+        const uint32_t l0 = cvt_f16x2_sat(v.x - f0.x, v.y - f0.y), l1 = cvt_f16x2_sat(v.z - f1.x, v.w - f1.y);
+        reinterpret_cast<uint2*>(hi)[i] = make_uint2(h0, h1);
+        reinterpret_cast<uint2*>(lo)[i] = make_uint2(l0, l1);
+    }
+}
+
+static int wgrad_mn_policy() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CUM_WGRAD_MN");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
+static WgradMnPlan plan_wgrad_mn(const cum_wgrad_desc& d) {
+    WgradMnPlan w;
+    const bool flat = d.taps == 1;                 // 1x1 layers: all clips are one run of rows (no tap can cross a clip boundary)
+    w.clips = flat ? 1 : d.batch;
+    w.rows_z = flat ? (long long)d.batch * d.m : d.m;
+    w.rows_a = flat ? (long long)d.batch * d.m : d.a_rows;
+    w.z_elems = (size_t)w.clips * w.rows_z * d.n;
+    w.a_elems = (size_t)w.clips * w.rows_a * d.k;
+    w.ws_bytes = 256 + 4 * (((w.z_elems + 127) / 128) * 128 + ((w.a_elems + 127) / 128) * 128);      // two fp16 planes each
+    return w;
+}
+
+template <int BN, bool CTA2>
+static int launch_wgrad_mn(const __half* z_hi, const __half* z_lo, const __half* a_hi, const __half* a_lo, const WgradMnPlan& w,
+                           const cum_wgrad_desc& d, int tap, const float* inv_scale, cudaStream_t st) {
+    using Cfg = TcCfg<TC_F16PS, BN, CTA2>;
+    auto kern = gemm_tc_kernel<TC_F16PS, BN, TC_EPI_ATOMIC_ADD, 0, CTA2, 1>;
+    { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)Cfg::SMEM_BYTES, "cudaFuncSetAttribute(gemm_tc_kernel MN)"); if (rc_attr) return rc_attr; }
+    CUtensorMap tmA, tmAl, tmWh, tmWl;
+    int rc = make_map(&tmA, z_hi, (uint64_t)d.n, (uint64_t)w.rows_z, (uint64_t)w.clips, (uint64_t)d.n, (uint64_t)w.rows_z * d.n, 64, 32, "dZ_hi", true, true);
+    if (rc) return rc;
+    rc = make_map(&tmAl, z_lo, (uint64_t)d.n, (uint64_t)w.rows_z, (uint64_t)w.clips, (uint64_t)d.n, (uint64_t)w.rows_z * d.n, 64, 32, "dZ_lo", true, true);
+    if (rc) return rc;
+    rc = make_map(&tmWh, a_hi, (uint64_t)d.k, (uint64_t)w.rows_a, (uint64_t)w.clips, (uint64_t)d.k, (uint64_t)w.rows_a * d.k, 64, 32, "A_hi", true, true);
+    if (rc) return rc;
+    rc = make_map(&tmWl, a_lo, (uint64_t)d.k, (uint64_t)w.rows_a, (uint64_t)w.clips, (uint64_t)d.k, (uint64_t)w.rows_a * d.k, 64, 32, "A_lo", true, true);
+    if (rc) return rc;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.m = d.n; p.n = d.k; p.k = 32; p.taps = 1; p.shift0 = d.tap_shift[tap]; p.shift1 = 0; p.epi = CUM_EPI_NONE;
+    p.m_tiles = (int)cdiv(d.n, CTA2 ? 2 * TC_BM : TC_BM); p.n_tiles = (int)cdiv(d.k, BN);
+    // split-K: ~3 waves of CTAs, at least 8 K-blocks (256 rows) per split
+    const long long kb_clip = cdiv(w.rows_z, 32);
+    const long long tiles = (long long)p.m_tiles * p.n_tiles;
+    const long long units = CTA2 ? sm_count() / 2 : sm_count();
+    long long want = cdiv(cdiv(3 * units, tiles), w.clips);
+    const long long max_s = kb_clip / 8 > 0 ? kb_clip / 8 : 1;
+    if (want > max_s) want = max_s;
+    if (want < 1) want = 1;
+    p.k_blocks = (int)cdiv(kb_clip, want);
+    p.mn_splits = (int)cdiv(kb_clip, p.k_blocks);
+    const long long batch = (long long)w.clips * p.mn_splits;
+    CUM_REQUIRE(batch * tiles < (1ll << 31), "wgrad: too many tiles");
+    p.batch = (int)batch;
+    p.bias = nullptr; p.c = d.dw + (size_t)tap * d.n * d.ldw; p.c_bs = 0; p.c_rs = d.ldw;
+    p.addend = nullptr; p.acc_scale = 1.0f; p.acc_scale_ptr = inv_scale; p.skip_wlo = 0;
+    const long long total = batch * tiles;
+    if (CTA2) {
+        const int pairs = sm_count() / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs)));
+        cfg.blockDim = dim3(Cfg::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmAl, tmWh, tmWl, p);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tc_kernel MN, cluster 2)");
+        return CUM_OK;
+    }
+    const int grid = (int)(total < sm_count() ? total : sm_count());
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmAl, tmWh, tmWl, p);
+    CUM_LAUNCH_CHECK("gemm_tc_kernel (MN-major wgrad)");
+    return CUM_OK;
+}
+
+static bool wgrad_mn_ok(const cum_wgrad_desc& d) {
+    const auto s4 = [](long long v) { return v % 4 == 0; };
+    return wgrad_mn_policy() && d.n % 8 == 0 && d.k % 8 == 0 && aligned16(d.dz) && aligned16(d.a) && s4(d.dz_row_stride) && s4(d.a_row_stride) &&
+           s4(d.dz_batch_stride) && s4(d.a_batch_stride) &&
+           (d.taps != 1 || d.batch == 1 || (d.dz_batch_stride == (long long)d.m * d.dz_row_stride && d.a_batch_stride == (long long)d.m * d.a_row_stride));
+}
+
+static int wgrad_mn_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
+    const WgradMnPlan w = plan_wgrad_mn(d);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(d.workspace);
+    unsigned* amax_bits = reinterpret_cast<unsigned*>(ws);
+    float* inv_scale = reinterpret_cast<float*>(ws + 16);
+    const size_t zpl = ((w.z_elems + 127) / 128) * 128, apl = ((w.a_elems + 127) / 128) * 128;
+    __half* z_hi = reinterpret_cast<__half*>(ws + 256);
+    __half* z_lo = z_hi + zpl;
+    __half* a_hi = z_lo + zpl;
+    __half* a_lo = a_hi + apl;
+    cudaError_t e = cudaMemsetAsync(ws, 0, 32, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(wgrad amax)");
+    const bool flat = d.taps == 1;
+    const int zb = flat ? 1 : d.batch;
+    const long long z_bs = flat ? 0 : d.dz_batch_stride, a_bs = flat ? 0 : d.a_batch_stride;
+    const int grid = 8 * sm_count();
+    amax_kernel<<<grid, 256, 0, st>>>(d.dz, z_bs, d.dz_row_stride, zb, (int)w.rows_z, d.n / 4, amax_bits);
+    CUM_LAUNCH_CHECK("amax_kernel");
+    split_planes_kernel<<<grid, 256, 0, st>>>(d.dz, z_bs, d.dz_row_stride, zb, (int)w.rows_z, d.n / 4, z_hi, z_lo, amax_bits, inv_scale);
+    CUM_LAUNCH_CHECK("split_planes_kernel(dz)");
+    split_planes_kernel<<<grid, 256, 0, st>>>(d.a, a_bs, d.a_row_stride, zb, (int)w.rows_a, d.k / 4, a_hi, a_lo, nullptr, nullptr);
+    CUM_LAUNCH_CHECK("split_planes_kernel(a)");
+    const bool pair = cta2_policy() >= 0 && d.n > TC_BM && (sm_count() & 1) == 0;
+    for (int s = 0; s < d.taps; ++s) {
+        int rc;
+        if (d.k <= 128) rc = pair ? launch_wgrad_mn<128, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, inv_scale, st)
+                                  : launch_wgrad_mn<128, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, inv_scale, st);
+        else rc = pair ? launch_wgrad_mn<256, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, inv_scale, st)
+                       : launch_wgrad_mn<256, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, inv_scale, st);
+        if (rc) return rc;
+    }
+    return CUM_OK;
+}
+
 int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.workspace, "wgrad: tensor-core mode needs a workspace (cum_gemm_wgrad_workspace_bytes)");
     CUM_REQUIRE(aligned16(d.workspace), "wgrad: workspace must be 16-byte aligned");
     CUM_REQUIRE(d.n % 8 == 0 && d.k % 8 == 0, "wgrad: n and k must be multiples of 8");
+    if (wgrad_mn_ok(d)) return wgrad_mn_fwd(d, st);
     const WgradPlan w = plan_wgrad(d);
     float* zt = reinterpret_cast<float*>(d.workspace);            // dZ^T   (n, r_pad)
     float* at_hi = zt + (size_t)d.n * w.r_pad;                     // A^T hi (k, r_pad)

@@ -64,6 +64,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    // MN-major, 128B swizzle (canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)) in elements, T = elements per 16 bytes): rows of
+    // 128 bytes run along M / N, consecutive K-rows are 128 B apart, 8-row groups 1024 B apart (SBO), the next 128-byte slab along
+    // M / N is lbo_bytes away (LBO); version 1 (sm_100)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
     // K-major, 64B swizzle (bf16 tiles with 32-element = 64-byte rows): 8-row groups are 512 B apart
     uint64_t d = 0;
