@@ -30,7 +30,7 @@ class GemmDesc(C.Structure):
                 ("m", C.c_int), ("n", C.c_int), ("batch", C.c_int), ("epilogue", C.c_int),
                 ("addend", C.c_void_p), ("add_batch_stride", C.c_longlong), ("add_row_stride", C.c_longlong),
                 ("math", C.c_int), ("w_lo", C.c_void_p), ("acc_scale", C.c_float), ("out_bf16", C.c_int), ("w_lo_is_zero", C.c_int),
-                ("a_lo", C.c_void_p), ("c_lo", C.c_void_p), ("addend_lo", C.c_void_p), ("cta_pair", C.c_int)]
+                ("a_lo", C.c_void_p), ("c_lo", C.c_void_p), ("addend_lo", C.c_void_p), ("a_scale_dev", C.c_void_p), ("cta_pair", C.c_int)]
 
 
 class Enc0BlockDesc(C.Structure):
@@ -65,7 +65,7 @@ class WgradDesc(C.Structure):
     _fields_ = [("dz", C.c_void_p), ("dz_batch_stride", C.c_longlong), ("dz_row_stride", C.c_longlong),
                 ("a", C.c_void_p), ("a_batch_stride", C.c_longlong), ("a_row_stride", C.c_longlong), ("a_rows", C.c_int),
                 ("dw", C.c_void_p), ("ldw", C.c_int), ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("taps", C.c_int),
-                ("tap_shift", C.c_int * 2), ("batch", C.c_int), ("math", C.c_int), ("workspace", C.c_void_p)]
+                ("tap_shift", C.c_int * 2), ("batch", C.c_int), ("math", C.c_int), ("workspace", C.c_void_p), ("dz_scale_dev", C.c_void_p)]
 
 
 class ScanBwdDesc(C.Structure):
@@ -117,6 +117,7 @@ EXPORTS = {
     "cum_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "cum_add_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "cum_gemm_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "cum_grad_scale_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cum_gemm_wgrad_workspace_bytes": (C.c_longlong, [C.POINTER(WgradDesc)]),
     "cum_ln_residual_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_float, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),

@@ -237,6 +237,10 @@ int cum_gemm_wgrad(const cum_wgrad_desc* desc, cum_stream_t stream) {
     if (desc->math == CUM_MATH_FP32) return wgrad_fwd(*desc, (cudaStream_t)stream);
     return wgrad_tc_fwd(*desc, (cudaStream_t)stream);
 }
+int cum_grad_scale_fwd(const float* x, long long batch_stride, long long row_stride, int batch, int rows, int cols, float* scale4,
+                       cum_stream_t stream) {
+    return grad_scale_fwd(x, batch_stride, row_stride, batch, rows, cols, scale4, (cudaStream_t)stream);
+}
 long long cum_gemm_wgrad_workspace_bytes(const cum_wgrad_desc* desc) {
     if (!desc || desc->math == CUM_MATH_FP32) return 0;
     return wgrad_tc_workspace_bytes(*desc);

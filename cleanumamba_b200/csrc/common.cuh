@@ -98,6 +98,7 @@ int add_fwd(const float* a, const float* b, float* out, long long count, cudaStr
 int wgrad_fwd(const cum_wgrad_desc& d, cudaStream_t st);
 int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st);
 long long wgrad_tc_workspace_bytes(const cum_wgrad_desc& d);
+int grad_scale_fwd(const float* x, long long bs, long long rs, int batch, int rows, int cols, float* scale4, cudaStream_t st);
 int ln_bwd(const float* x, const float* dy, const float* dres_in, const float* gamma, float* dx, float* dgamma,
            float* dbeta, float eps, long long rows, int c, int c_pad, cudaStream_t st);
 int dwconv_silu_bwd(const float* x, long long x_bs, long long x_rs, const float* w, const float* bias, const float* dy,

@@ -94,7 +94,8 @@ struct TcParams {
     int w_k_batch_stride;     // wgrad (split-K over rows): W k-coordinate += batch * this + w_k_off
     int w_k_off;
     int mn_splits;            // MN-major wgrad: splits per clip ("batch" = clip * mn_splits + split, k_blocks K-blocks of 32 rows per split)
-    const float* acc_scale_ptr;   // optional device-side acc_scale (overrides acc_scale): scales that are computed on the device
+    const float* acc_scale_ptr;   // optional device-side factor multiplied into acc_scale (1 / gradient scale computed on the device)
+    const float* a_scale_ptr;     // optional device-side factor applied to A by the fp16 operand splitter (gradient scale)
     void* c_lo;               // OUTF == 2: low-half plane of the output (c is the high-half plane), fp16
     const void* addend_lo;    // OUTF == 2: low-half plane of the addend
 };
@@ -317,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================================================================== epilogue (16 warps)
         const int q = warp & 3;                 // TMEM lane quarter this warp may touch
         const int sub = (warp - 4) >> 2;        // which of every four 32-column chunks
-        const float acc_scale = p.acc_scale_ptr ? __ldg(p.acc_scale_ptr) : p.acc_scale;
+        const float acc_scale = p.acc_scale_ptr ? p.acc_scale * __ldg(p.acc_scale_ptr) : p.acc_scale;
         const int tq = lane & 3, tr = lane >> 2;
         int tcount = 0;
         const uint32_t tempty_leader = CTA2 ? mapa_rank(tempty_bar(0), 0) : 0u;
@@ -533,6 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (SPL && warp >= 4 + TC_EPI_WARPS) {
         // ===================================================================== operand splitter (A tile)
         const int t = threadIdx.x - (4 + TC_EPI_WARPS) * 32;
+        const float asc = (F16 && p.a_scale_ptr) ? __ldg(p.a_scale_ptr) : 1.0f;     // power-of-two gradient scale (dgrad in f16x3)
         int s = 0;
         uint32_t ph = 0;
         for (int tile = tile0; tile < total_tiles; tile += tstep) {
@@ -558,7 +560,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int i = t + 128 * j;
                         const int r = i >> 2, co = i & 3;
                         const float4 v0 = va[j], v1 = vb[j];
-                        const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                        const float f[8] = {v0.x * asc, v0.y * asc, v0.z * asc, v0.w * asc, v1.x * asc, v1.y * asc, v1.z * asc, v1.w * asc};
                         uint32_t h[4], l[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -801,7 +803,9 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.c_lo = d.c_lo; p.addend_lo = d.addend_lo;
     p.skip_wlo = (X3 && d.w_lo_is_zero) ? 1 : 0;
     p.w_k_batch_stride = g_wgrad_kbs; p.w_k_off = g_wgrad_koff;
-    p.mn_splits = 0; p.acc_scale_ptr = nullptr;
+    p.mn_splits = 0;
+    p.a_scale_ptr = (MODE == TC_F16X3) ? d.a_scale_dev : nullptr;
+    p.acc_scale_ptr = (MODE == TC_F16X3 && d.a_scale_dev) ? d.a_scale_dev + 1 : nullptr;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
     CUM_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
     if (CTA2) {
@@ -983,43 +987,75 @@ template <int BN> static int launch_wgrad_gemm(const cum_gemm_desc& g, cudaStrea
 //   2. elementwise split of scale * dZ and of A into fp16 hi / lo planes, row-major as they are
 //   3. per tap one split-K GEMM (splits = (clip, row range)) whose TMA boxes are MN-major operand slabs (gemm_tc_kernel<..., MNM>),
 //      three fp16 MMA passes, atomic accumulation into the zero-initialised gradient.
+// row-major (batch, rows, cols) with strides; `contig`: the whole tensor is one flat run (no index arithmetic per element)
+__device__ __forceinline__ const float4* elem4(const float* x, long long bs, long long rs, int rows, int cols4, bool contig, long long i) {
+    if (contig) return reinterpret_cast<const float4*>(x) + i;
+    const unsigned c = (unsigned)(i % (unsigned)cols4);
+    const long long br = i / (unsigned)cols4;
+    const unsigned r = (unsigned)(br % (unsigned)rows);
+    const long long b = br / (unsigned)rows;
+    return reinterpret_cast<const float4*>(x + b * bs + (long long)r * rs) + c;
+}
+
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long bs, long long rs, int batch, int rows, int cols4,
                                                     unsigned* __restrict__ amax_bits) {
     const long long total = (long long)batch * rows * cols4;
-    float m = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cols4);
-        const long long br = i / cols4;
-        const int r = (int)(br % rows), b = (int)(br / rows);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (long long)b * bs + (long long)r * rs) + c);
-        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    const bool contig = rs == 4ll * cols4 && (batch == 1 || bs == (long long)rows * rs);
+    float m0 = 0.f, m1 = 0.f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < total; i += 2 * stride) {          // two independent loads in flight per thread
+        const float4 v = __ldg(elem4(x, bs, rs, rows, cols4, contig, i)), u = __ldg(elem4(x, bs, rs, rows, cols4, contig, i + stride));
+        m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        m1 = fmaxf(m1, fmaxf(fmaxf(fabsf(u.x), fabsf(u.y)), fmaxf(fabsf(u.z), fabsf(u.w))));
     }
+    if (i < total) {
+        const float4 v = __ldg(elem4(x, bs, rs, rows, cols4, contig, i));
+        m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    float m = fmaxf(m0, m1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));      // non-negative floats order like their bits
 }
 
-// hi = fp16(s x) (saturating), lo = fp16(s x - hi); s = 2^(15 - e) with amax = f 2^e, f in [0.5, 1) (1 when no amax is given);
-// compact (batch, rows, cols) planes.  inv_scale_out[0] = 1 / s.
+// scale4 = {s, 1 / s, amax bits, -}: s = 2^(15 - e) with amax = f 2^e, f in [0.5, 1); 1 for an all-zero tensor
+__global__ void grad_scale_finalize_kernel(float* __restrict__ scale4) {
+    const float am = __uint_as_float(reinterpret_cast<const unsigned*>(scale4)[2]);
+    float s = 1.f;
+    if (am > 0.f) {
+        int e;
+        frexpf(am, &e);
+        s = ldexpf(1.f, 15 - e);
+    }
+    scale4[0] = s;
+    scale4[1] = 1.f / s;
+}
+
+int grad_scale_fwd(const float* x, long long bs, long long rs, int batch, int rows, int cols, float* scale4, cudaStream_t st) {
+    CUM_REQUIRE(x && scale4 && batch > 0 && rows > 0 && cols > 0 && cols % 4 == 0 && aligned16(x) && bs % 4 == 0 && rs % 4 == 0,
+                "grad_scale: bad arguments (cols and strides must be multiples of 4, x 16-byte aligned)");
+    cudaError_t e = cudaMemsetAsync(scale4, 0, 16, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_scale)");
+    const long long total = (long long)batch * rows * (cols / 4);
+    const long long want = cdiv(total, 256);
+    const int grid = (int)(want < 8LL * sm_count() ? want : 8LL * sm_count());
+    amax_kernel<<<grid, 256, 0, st>>>(x, bs, rs, batch, rows, cols / 4, reinterpret_cast<unsigned*>(scale4) + 2);
+    CUM_LAUNCH_CHECK("amax_kernel");
+    grad_scale_finalize_kernel<<<1, 1, 0, st>>>(scale4);
+    CUM_LAUNCH_CHECK("grad_scale_finalize_kernel");
+    return CUM_OK;
+}
+
+// hi = fp16(s x) (saturating), lo = fp16(s x - hi), s read from the device (1 when `scale` is NULL); compact (batch, rows, cols) planes
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long bs, long long rs, int batch, int rows, int cols4,
                                                             __half* __restrict__ hi, __half* __restrict__ lo,
-                                                            const unsigned* __restrict__ amax_bits, float* __restrict__ inv_scale_out) {
-    float s = 1.f;
-    if (amax_bits) {
-        const float am = __uint_as_float(*amax_bits);
-        if (am > 0.f) {
-            int e;
-            frexpf(am, &e);
-            s = ldexpf(1.f, 15 - e);
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale_out[0] = 1.f / s;
-    }
+                                                            const float* __restrict__ scale) {
+    const float s = scale ? __ldg(scale) : 1.f;
     const long long total = (long long)batch * rows * cols4;
+    const bool contig = rs == 4ll * cols4 && (batch == 1 || bs == (long long)rows * rs);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cols4);
-        const long long br = i / cols4;
-        const int r = (int)(br % rows), b = (int)(br / rows);
-        float4 v = __ldg(reinterpret_cast<const float4*>(x + (long long)b * bs + (long long)r * rs) + c);
+        float4 v = __ldg(elem4(x, bs, rs, rows, cols4, contig, i));
         v.x *= s; v.y *= s; v.z *= s; v.w *= s;
         const uint32_t h0 = cvt_f16x2_sat(v.x, v.y), h1 = cvt_f16x2_sat(v.z, v.w);
         const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
@@ -1083,7 +1119,7 @@ static int launch_wgrad_mn(const __half* z_hi, const __half* z_lo, const __half*
     CUM_REQUIRE(batch * tiles < (1ll << 31), "wgrad: too many tiles");
     p.batch = (int)batch;
     p.bias = nullptr; p.c = d.dw + (size_t)tap * d.n * d.ldw; p.c_bs = 0; p.c_rs = d.ldw;
-    p.addend = nullptr; p.acc_scale = 1.0f; p.acc_scale_ptr = inv_scale; p.skip_wlo = 0;
+    p.addend = nullptr; p.acc_scale = 1.0f; p.acc_scale_ptr = inv_scale; p.a_scale_ptr = nullptr; p.skip_wlo = 0;
     const long long total = batch * tiles;
     if (CTA2) {
         const int pairs = sm_count() / 2;
@@ -1118,32 +1154,33 @@ static bool wgrad_mn_ok(const cum_wgrad_desc& d) {
 static int wgrad_mn_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
     const WgradMnPlan w = plan_wgrad_mn(d);
     uint8_t* ws = reinterpret_cast<uint8_t*>(d.workspace);
-    unsigned* amax_bits = reinterpret_cast<unsigned*>(ws);
-    float* inv_scale = reinterpret_cast<float*>(ws + 16);
+    float* own_scale = reinterpret_cast<float*>(ws);                 // {s, 1/s, amax bits, -} when the caller brings no scale
     const size_t zpl = ((w.z_elems + 127) / 128) * 128, apl = ((w.a_elems + 127) / 128) * 128;
     __half* z_hi = reinterpret_cast<__half*>(ws + 256);
     __half* z_lo = z_hi + zpl;
     __half* a_hi = z_lo + zpl;
     __half* a_lo = a_hi + apl;
-    cudaError_t e = cudaMemsetAsync(ws, 0, 32, st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(wgrad amax)");
     const bool flat = d.taps == 1;
     const int zb = flat ? 1 : d.batch;
     const long long z_bs = flat ? 0 : d.dz_batch_stride, a_bs = flat ? 0 : d.a_batch_stride;
+    const float* scale = d.dz_scale_dev;
+    if (!scale) {
+        const int rc = grad_scale_fwd(d.dz, z_bs, d.dz_row_stride, zb, (int)w.rows_z, d.n, own_scale, st);
+        if (rc) return rc;
+        scale = own_scale;
+    }
     const int grid = 8 * sm_count();
-    amax_kernel<<<grid, 256, 0, st>>>(d.dz, z_bs, d.dz_row_stride, zb, (int)w.rows_z, d.n / 4, amax_bits);
-    CUM_LAUNCH_CHECK("amax_kernel");
-    split_planes_kernel<<<grid, 256, 0, st>>>(d.dz, z_bs, d.dz_row_stride, zb, (int)w.rows_z, d.n / 4, z_hi, z_lo, amax_bits, inv_scale);
+    split_planes_kernel<<<grid, 256, 0, st>>>(d.dz, z_bs, d.dz_row_stride, zb, (int)w.rows_z, d.n / 4, z_hi, z_lo, scale);
     CUM_LAUNCH_CHECK("split_planes_kernel(dz)");
-    split_planes_kernel<<<grid, 256, 0, st>>>(d.a, a_bs, d.a_row_stride, zb, (int)w.rows_a, d.k / 4, a_hi, a_lo, nullptr, nullptr);
+    split_planes_kernel<<<grid, 256, 0, st>>>(d.a, a_bs, d.a_row_stride, zb, (int)w.rows_a, d.k / 4, a_hi, a_lo, nullptr);
     CUM_LAUNCH_CHECK("split_planes_kernel(a)");
     const bool pair = cta2_policy() >= 0 && d.n > TC_BM && (sm_count() & 1) == 0;
     for (int s = 0; s < d.taps; ++s) {
         int rc;
-        if (d.k <= 128) rc = pair ? launch_wgrad_mn<128, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, inv_scale, st)
-                                  : launch_wgrad_mn<128, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, inv_scale, st);
-        else rc = pair ? launch_wgrad_mn<256, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, inv_scale, st)
-                       : launch_wgrad_mn<256, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, inv_scale, st);
+        if (d.k <= 128) rc = pair ? launch_wgrad_mn<128, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale + 1, st)
+                                  : launch_wgrad_mn<128, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale + 1, st);
+        else rc = pair ? launch_wgrad_mn<256, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale + 1, st)
+                       : launch_wgrad_mn<256, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale + 1, st);
         if (rc) return rc;
     }
     return CUM_OK;
@@ -1192,6 +1229,7 @@ int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
 
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.a_row_stride >= d.k || d.a_rows == 1, "gemm_tc: a_row_stride < k");
+    CUM_REQUIRE(!d.a_scale_dev || (d.math == CUM_MATH_F16X3 && !d.a_lo), "gemm_tc: a_scale_dev needs CUM_MATH_F16X3 with fp32 activations");
     CUM_REQUIRE(d.out_bf16 || d.c_lo || (aligned16(d.c) && d.c_row_stride % 4 == 0 && (d.batch == 1 || d.c_batch_stride % 4 == 0)),
                 "gemm_tc: an fp32 output must be 16-byte aligned with row / batch strides that are multiples of 4 elements (c_row_stride=%lld)",
                 (long long)d.c_row_stride);

@@ -23,12 +23,18 @@ from .engine import Engine, on_model_device
 class TrainEngine(Engine):
     """Engine with transposed weight copies (for dgrad) and a gradient buffer.
 
-    Under "f16x3" the FORWARD GEMMs of a training step use the fp16 split (same kernels and accuracy as inference, 2x the
-    TF32 tensor rate); the data-gradient GEMMs never do: back-propagated gradients routinely fall below fp16's 6e-5 normal
-    range, so the transposed weights carry TF32 hi/lo halves and run as "tf32x3" (same 22-bit products, fp32 exponent
-    range), as do the weight gradients.  "bf16" (inference-only storage variant) maps to "tf32x3" entirely."""
+    Under "f16x3" every GEMM of a training step uses the fp16 split (2x the TF32 tensor rate).  Back-propagated gradients
+    routinely fall below fp16's 6e-5 normal range, so each gradient tensor that feeds a GEMM is scaled by a power of two
+    computed on the device from its max (``grad_scale``): the data-gradient GEMM's operand splitter multiplies by it and the
+    epilogue divides it out, the weight-gradient GEMM (MN-major operands, no transposes) shares it.  ``CUM_TRAIN_F16_BWD=0``
+    restores the round-1 arithmetic (transposed weights as TF32 halves, "tf32x3" data gradients).  "bf16" (inference-only
+    storage variant) maps to "tf32x3" entirely."""
 
     tc_wgrad = True      # tensor-core weight gradients (tests may switch to the fp32 CUDA-core kernel)
+    # f16x3 models: the data-gradient GEMMs run in f16x3 as well (twice the TF32 tensor rate).  Back-propagated gradients (~1e-6)
+    # underflow fp16, so every gradient tensor that feeds a GEMM gets a power-of-two scale computed ON THE DEVICE from its max
+    # (cum_grad_scale_fwd): the operand splitter multiplies by it, the epilogue divides it out, the weight-gradient GEMM shares it.
+    f16_backward = os.environ.get("CUM_TRAIN_F16_BWD", "1") != "0"
     f16_forward = os.environ.get("CUM_TRAIN_F16_FWD", "1") != "0"     # f16x3 models: forward GEMMs in f16x3 (A/B switch)
 
     def _pack(self):
@@ -46,7 +52,9 @@ class TrainEngine(Engine):
         return extra
 
     def _post_pack(self, items, offs, total):
-        if self.math == _lib.MATH_F16X3:
+        self._scale_pool = torch.zeros(128, 4, dtype=torch.float32, device=self.device)
+        self._scale_next = 0
+        if self.math == _lib.MATH_F16X3 and not self.f16_backward:
             # transposed (dgrad) weights: TF32 hi/lo halves instead of the fp16 split the base class prepared for every GEMM weight
             tkeys = [k for k in items if k.endswith("T")]
             lo0 = min(offs[k] for k in tkeys)
@@ -81,7 +89,18 @@ class TrainEngine(Engine):
     def zeros(self, *shape):
         return torch.zeros(*shape, dtype=torch.float32, device=self.device)
 
-    def wgrad(self, dz, dz_bs, dz_rs, a, a_off, a_bs, a_rs, a_rows, key, m, n, k, batch, taps=1, shifts=(0, 0)):
+    def grad_scale(self, t, rows, cols):
+        """{s, 1/s} (device, 4 floats) of the contiguous (rows, cols) gradient tensor ``t``: s = the power of two that lifts max|t| to
+        [2^14, 2^15).  None outside f16x3 (the other modes keep fp32 range)."""
+        if self.math != _lib.MATH_F16X3 or not self.f16_backward:
+            return None
+        sc = self._scale_pool[self._scale_next % self._scale_pool.shape[0]]
+        self._scale_next += 1
+        self._call("grad_scale", self.lib.cum_grad_scale_fwd, t.data_ptr(), 0, cols, 1, rows, cols, sc.data_ptr(), _lib.stream_ptr(),
+                   launches=2, nbytes=4 * rows * cols)
+        return sc
+
+    def wgrad(self, dz, dz_bs, dz_rs, a, a_off, a_bs, a_rs, a_rows, key, m, n, k, batch, taps=1, shifts=(0, 0), scale=None):
         d = WgradDesc()
         d.dz, d.dz_batch_stride, d.dz_row_stride = dz.data_ptr(), dz_bs, dz_rs
         d.a, d.a_batch_stride, d.a_row_stride, d.a_rows = a.data_ptr() + 4 * a_off, a_bs, a_rs, a_rows
@@ -90,20 +109,22 @@ class TrainEngine(Engine):
         d.m, d.n, d.k, d.taps, d.batch = m, n, k, taps, batch
         d.tap_shift[0], d.tap_shift[1] = shifts
         d.math = _lib.MATH_FP32 if (self.math == _lib.MATH_FP32 or not self.tc_wgrad) else _lib.MATH_TF32X3
+        if scale is not None:
+            d.dz_scale_dev = scale.data_ptr()
         ws = None
         if d.math != _lib.MATH_FP32:
             nbytes = self.lib.cum_gemm_wgrad_workspace_bytes(C.byref(d))
             ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
             d.workspace = ws.data_ptr()
         self._call("wgrad", self.lib.cum_gemm_wgrad, C.byref(d), _lib.stream_ptr(), flops=2 * batch * m * n * k * taps,
-                   launches=1 if ws is None else 1 + 2 * taps)
+                   launches=1 if ws is None else 2 + taps + (0 if scale is not None else 3))
 
-    def dense_T(self, dz, rows, n_fwd, key, k_fwd, addend=None, out=None, c_rs=None):
+    def dense_T(self, dz, rows, n_fwd, key, k_fwd, addend=None, out=None, c_rs=None, scale=None):
         """Data gradient of a flat dense layer: (rows, n_fwd) x W (n_fwd, k_fwd) -> (rows, k_fwd)."""
         c = out if out is not None else self.new(rows, k_fwd)
         crs = k_fwd if c_rs is None else c_rs
         self.gemm(dz, 0, 0, n_fwd, rows, n_fwd, key + "T", None, c, 0, 0, crs, rows, k_fwd, 1, EPI_NONE,
-                  addend=addend, add_bs=0, add_rs=crs)
+                  addend=addend, add_bs=0, add_rs=crs, a_scale=scale)
         return c
 
     # ---------------------------------------------------------------------------------------------- forward
@@ -237,8 +258,9 @@ class TrainEngine(Engine):
             Zd, hg, cin = S["Zd"][j], d["Hg_p"], d["Cin_p"]
             self._call("glu_bwd", lib.cum_glu_bwd, Zd.data_ptr(), dg.data_ptr(), Zd.data_ptr(), gk[f"dec{j}.bg"].data_ptr(),
                        rows, hg, st())                                        # dZ in place
-            self.wgrad(Zd, 0, 2 * hg, S["xin"][j], 0, 0, cin, rows, f"dec{j}.wg", rows, 2 * hg, cin, 1)
-            dx = self.dense_T(Zd, rows, 2 * hg, f"dec{j}.wg", cin)           # gradient of this level's input
+            sc = self.grad_scale(Zd, rows, 2 * hg)
+            self.wgrad(Zd, 0, 2 * hg, S["xin"][j], 0, 0, cin, rows, f"dec{j}.wg", rows, 2 * hg, cin, 1, scale=sc)
+            dx = self.dense_T(Zd, rows, 2 * hg, f"dec{j}.wg", cin, scale=sc)           # gradient of this level's input
             if j > 0:
                 lvl = D - 1 - j                                               # x_in = relu-convT(prev) + skip[lvl]
                 dskip[lvl] = dx
@@ -247,11 +269,12 @@ class TrainEngine(Engine):
                 r = S["r"][j - 1]
                 self._call("relu_bwd", lib.cum_relu_bwd, r.data_ptr(), dx.data_ptr(), r.data_ptr(), gk[f"dec{j-1}.b"].data_ptr(),
                            B * (Tp + 1), 2 * co, st())                        # dZ (B, Tp+1, 2co) in place of r
+                sc = self.grad_scale(r, B * (Tp + 1), 2 * co)
                 self.wgrad(r, (Tp + 1) * 2 * co, 2 * co, S["g"][j - 1], 0, Tp * hgp, hgp, Tp, f"dec{j-1}.w", Tp + 1, 2 * co,
-                           hgp, B, taps=2, shifts=(0, -1))
+                           hgp, B, taps=2, shifts=(0, -1), scale=sc)
                 dg = self.new(B * Tp, hgp)
                 self.gemm(r, 0, (Tp + 1) * 2 * co, 2 * co, Tp + 1, 2 * co, f"dec{j-1}.wT", None, dg, 0, Tp * hgp, hgp, Tp, hgp, B,
-                          EPI_NONE, taps=2, shifts=(0, 1))
+                          EPI_NONE, taps=2, shifts=(0, 1), a_scale=sc)
                 Tj = Tp
             else:
                 dskip[D - 1] = dx                                             # x_in = tsfm_conv2(hn_f) + skip[D-1]
@@ -262,8 +285,9 @@ class TrainEngine(Engine):
         dm, dm_p, cb_p = meta["dm"], meta["dm_p"], meta["enc"][-1]["Ho_p"]
         dx0 = dskip[D - 1]
         self._call("colsum", lib.cum_colsum, dx0.data_ptr(), gk["t2.b"].data_ptr(), rows, cb_p, st())
-        self.wgrad(dx0, 0, cb_p, S["hn_f"], 0, 0, dm_p, rows, "t2.w", rows, cb_p, dm_p, 1)
-        dhn = self.dense_T(dx0, rows, cb_p, "t2.w", dm_p)
+        sc = self.grad_scale(dx0, rows, cb_p)
+        self.wgrad(dx0, 0, cb_p, S["hn_f"], 0, 0, dm_p, rows, "t2.w", rows, cb_p, dm_p, 1, scale=sc)
+        dhn = self.dense_T(dx0, rows, cb_p, "t2.w", dm_p, scale=sc)
         # ---- final norm, Mamba layers in reverse
         dres = self.new(rows, dm_p)
         self._call("ln_bwd", lib.cum_ln_residual_bwd, S["res_f"].data_ptr(), dhn.data_ptr(), 0, pk["nf.g"].data_ptr(),
@@ -273,8 +297,9 @@ class TrainEngine(Engine):
             di_p, N_p, R_p = mm["di_p"], mm["N_p"], mm["R_p"]
             ld = R_p + 2 * N_p
             dh = dres                                                          # grad of the mixer output == grad of res_{l+1}
-            self.wgrad(dh, 0, dm_p, sv["y"], 0, 0, di_p, rows, f"m{l}.out", rows, dm_p, di_p, 1)
-            dy = self.dense_T(dh, rows, dm_p, f"m{l}.out", di_p)
+            sc = self.grad_scale(dh, rows, dm_p)
+            self.wgrad(dh, 0, dm_p, sv["y"], 0, 0, di_p, rows, f"m{l}.out", rows, dm_p, di_p, 1, scale=sc)
+            dy = self.dense_T(dh, rows, dm_p, f"m{l}.out", di_p, scale=sc)
             dxz = self.new(rows, 2 * di_p)
             dxdbl = self.zeros(rows, ld)
             du, ddt = self.new(rows, di_p), self.new(rows, di_p)
@@ -290,18 +315,21 @@ class TrainEngine(Engine):
             sb.dA_log, sb.dD, sb.ddelta_bias = gk[f"m{l}.a2"].data_ptr(), gk[f"m{l}.D"].data_ptr(), gk[f"m{l}.dtb"].data_ptr()
             self._call("selective_scan_bwd", lib.cum_selective_scan_bwd, C.byref(sb), st())
             # dt_proj: delta = x_dbl[:, :R] @ W_dt^T
-            self.wgrad(ddt, 0, di_p, sv["xdbl"], 0, 0, ld, rows, f"m{l}.dtw", rows, di_p, R_p, 1)
-            self.dense_T(ddt, rows, di_p, f"m{l}.dtw", R_p, out=dxdbl, c_rs=ld)
+            sc = self.grad_scale(ddt, rows, di_p)
+            self.wgrad(ddt, 0, di_p, sv["xdbl"], 0, 0, ld, rows, f"m{l}.dtw", rows, di_p, R_p, 1, scale=sc)
+            self.dense_T(ddt, rows, di_p, f"m{l}.dtw", R_p, out=dxdbl, c_rs=ld, scale=sc)
             # x_proj
-            self.wgrad(dxdbl, 0, ld, sv["xc"], 0, 0, di_p, rows, f"m{l}.xp", rows, ld, di_p, 1)
-            dxc = self.dense_T(dxdbl, rows, ld, f"m{l}.xp", di_p, addend=du)
+            sc = self.grad_scale(dxdbl, rows, ld)
+            self.wgrad(dxdbl, 0, ld, sv["xc"], 0, 0, di_p, rows, f"m{l}.xp", rows, ld, di_p, 1, scale=sc)
+            dxc = self.dense_T(dxdbl, rows, ld, f"m{l}.xp", di_p, addend=du, scale=sc)
             # depthwise conv + SiLU (x half of xz)
             self._call("dwconv_silu_bwd", lib.cum_dwconv_silu_bwd, sv["xz"].data_ptr(), T * 2 * di_p, 2 * di_p,
                        pk[f"m{l}.cw"].data_ptr(), pk[f"m{l}.cb"].data_ptr(), dxc.data_ptr(), dxz.data_ptr(), T * 2 * di_p,
                        2 * di_p, gk[f"m{l}.cw"].data_ptr(), gk[f"m{l}.cb"].data_ptr(), B, T, di_p, mm["W"], st())
             # in_proj
-            self.wgrad(dxz, 0, 2 * di_p, sv["hn"], 0, 0, dm_p, rows, f"m{l}.in", rows, 2 * di_p, dm_p, 1)
-            dhn = self.dense_T(dxz, rows, 2 * di_p, f"m{l}.in", dm_p)
+            sc = self.grad_scale(dxz, rows, 2 * di_p)
+            self.wgrad(dxz, 0, 2 * di_p, sv["hn"], 0, 0, dm_p, rows, f"m{l}.in", rows, 2 * di_p, dm_p, 1, scale=sc)
+            dhn = self.dense_T(dxz, rows, 2 * di_p, f"m{l}.in", dm_p, scale=sc)
             # pre-norm + residual stream
             dres_new = self.new(rows, dm_p)
             self._call("ln_bwd", lib.cum_ln_residual_bwd, sv["res"].data_ptr(), dhn.data_ptr(), dres.data_ptr(),
@@ -310,8 +338,9 @@ class TrainEngine(Engine):
             dres = dres_new
         # ---- tsfm_conv1 (its output is res_0)
         self._call("colsum", lib.cum_colsum, dres.data_ptr(), gk["t1.b"].data_ptr(), rows, dm_p, st())
-        self.wgrad(dres, 0, dm_p, S["skip"][D - 1], 0, 0, cb_p, rows, "t1.w", rows, dm_p, cb_p, 1)
-        dskip[D - 1] = self.dense_T(dres, rows, dm_p, "t1.w", cb_p, addend=dskip[D - 1])
+        sc = self.grad_scale(dres, rows, dm_p)
+        self.wgrad(dres, 0, dm_p, S["skip"][D - 1], 0, 0, cb_p, rows, "t1.w", rows, dm_p, cb_p, 1, scale=sc)
+        dskip[D - 1] = self.dense_T(dres, rows, dm_p, "t1.w", cb_p, addend=dskip[D - 1], scale=sc)
         bucket_done("bottleneck")
         # ---- encoder levels in reverse
         for i in range(D - 1, -1, -1):
@@ -320,19 +349,21 @@ class TrainEngine(Engine):
             Z, ho, hc = S["Z"][i], e["Ho_p"], e["Hc_p"]
             self._call("glu_bwd", lib.cum_glu_bwd, Z.data_ptr(), dskip[i].data_ptr(), Z.data_ptr(), gk[f"enc{i}.bg"].data_ptr(),
                        rows, ho, st())
-            self.wgrad(Z, 0, 2 * ho, S["y"][i], 0, 0, hc, rows, f"enc{i}.wg", rows, 2 * ho, hc, 1)
-            dy = self.dense_T(Z, rows, 2 * ho, f"enc{i}.wg", hc)
+            sc = self.grad_scale(Z, rows, 2 * ho)
+            self.wgrad(Z, 0, 2 * ho, S["y"][i], 0, 0, hc, rows, f"enc{i}.wg", rows, 2 * ho, hc, 1, scale=sc)
+            dy = self.dense_T(Z, rows, 2 * ho, f"enc{i}.wg", hc, scale=sc)
             y = S["y"][i]
             if i > 0:
                 cp = e["Cin_p"]
                 self._call("relu_bwd", lib.cum_relu_bwd, y.data_ptr(), dy.data_ptr(), y.data_ptr(), gk[f"enc{i}.b"].data_ptr(),
                            rows, hc, st())                                    # dZ in place of y
                 src = S["skip"][i - 1]
+                sc = self.grad_scale(y, rows, hc)
                 self.wgrad(y, Ls[i + 1] * hc, hc, src, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2, f"enc{i}.w", Ls[i + 1], hc, 2 * cp, B,
-                           taps=2, shifts=(0, 1))
+                           taps=2, shifts=(0, 1), scale=sc)
                 dprev = self.new(B * Ls[i], cp)
                 self.gemm(y, 0, Ls[i + 1] * hc, hc, Ls[i + 1], hc, f"enc{i}.wT", None, dprev, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2,
-                          2 * cp, B, EPI_NONE, taps=2, shifts=(0, -1), addend=dskip[i - 1], add_bs=Ls[i] * cp, add_rs=2 * cp)
+                          2 * cp, B, EPI_NONE, taps=2, shifts=(0, -1), addend=dskip[i - 1], add_bs=Ls[i] * cp, add_rs=2 * cp, a_scale=sc)
                 dskip[i - 1] = dprev
             else:
                 self._call("conv_in_bwd", lib.cum_conv_in_bwd, S["x"].data_ptr(), L, B, L, y.data_ptr(), dy.data_ptr(),

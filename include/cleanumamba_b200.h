@@ -155,6 +155,9 @@ typedef struct cum_gemm_desc {
     const void* a_lo;        /* NULL, or the low-half plane of `a` (then `a` is the high-half plane, both fp16) */
     void* c_lo;              /* NULL, or the low-half plane of `c` (then `c` is the high-half plane, both fp16) */
     const void* addend_lo;   /* NULL, or the low-half plane of `addend` (then `addend` is the high-half plane, both fp16) */
+    const float* a_scale_dev;/* CUM_MATH_F16X3 with fp32 `a` only: NULL, or a DEVICE pointer to {s, 1/s} (cum_grad_scale_fwd): `a` is multiplied
+                                by s while it is split into fp16 halves and the accumulator by 1/s -- back-propagated gradients
+                                (~1e-6) are lifted into fp16's range by a power of two computed on the device, no host sync */
     int cta_pair;            /* tiles wider than 128 columns can run on CTA pairs (tcgen05 cta_group::2: 256-row tiles, each CTA
                                 stages half of the weight tile).  0 = automatic (pairs whenever a problem has more than 128 rows),
                                 1 = same, -1 = never.  Same products, same accumulation order: bit-identical results */
@@ -285,10 +288,17 @@ typedef struct cum_wgrad_desc {
     int tap_shift[2];
     int batch;
     int math;            /* CUM_MATH_FP32: CUDA-core FFMA (no workspace).  Any tensor-core mode: tcgen05 split-K GEMM over the
-                            rows in TF32X3 arithmetic (gradients need the fp32 exponent range) */
+                            rows: MN-major fp16 hi / lo operands of the device-scaled gradient (no transposes, f16 tensor rate);
+                            CUM_WGRAD_MN=0 selects the previous transposing TF32X3 path */
     void* workspace;     /* tensor-core mode: >= cum_gemm_wgrad_workspace_bytes(desc) bytes of device scratch */
+    const float* dz_scale_dev;   /* optional DEVICE pointer to {s, 1/s} of dz from cum_grad_scale_fwd (saves the call its own amax pass) */
 } cum_wgrad_desc;
 int       cum_gemm_wgrad(const cum_wgrad_desc* desc, cum_stream_t stream);
+/* scale4[0] = s = 2^(15 - e) with max|x| = f 2^e, f in [0.5, 1) (1 when x is all zero), scale4[1] = 1 / s; scale4[2..3] scratch.
+ * x: (batch, rows, cols) with the given strides, cols % 4 == 0, rows 16-byte aligned.  The power-of-two "loss scale" of ONE
+ * gradient tensor, left on the device for cum_gemm_desc.a_scale_dev / cum_wgrad_desc.dz_scale_dev. */
+int cum_grad_scale_fwd(const float* x, long long batch_stride, long long row_stride, int batch, int rows, int cols, float* scale4,
+                       cum_stream_t stream);
 long long cum_gemm_wgrad_workspace_bytes(const cum_wgrad_desc* desc);
 
 /* LayerNorm backward + residual-stream add: x = saved LN input (rows, c_pad); dy = grad of the normalised output;
