@@ -220,11 +220,13 @@ long long cum_selective_scan_workspace_bytes(const cum_scan_desc* desc) {
 int cum_glu_fwd(const float* z, const float* addend, float* out, long long rows, int h_pad, cum_stream_t stream) {
     return glu_fwd(z, addend, out, rows, h_pad, (cudaStream_t)stream);
 }
-int cum_glu_bwd(const float* z, const float* dout, float* dz, float* dbias, long long rows, int h_pad, cum_stream_t stream) {
-    return rowblock_bwd(0, z, dout, dz, dbias, rows, 2 * h_pad, (cudaStream_t)stream);
+int cum_glu_bwd(const float* z, const float* dout, float* dz, float* dbias, long long rows, int h_pad, float* dz_scale4,
+                cum_stream_t stream) {
+    return rowblock_bwd(0, z, dout, dz, dbias, rows, 2 * h_pad, (cudaStream_t)stream, dz_scale4);
 }
-int cum_relu_bwd(const float* y, const float* dy, float* dz, float* dbias, long long rows, int cols, cum_stream_t stream) {
-    return rowblock_bwd(1, y, dy, dz, dbias, rows, cols, (cudaStream_t)stream);
+int cum_relu_bwd(const float* y, const float* dy, float* dz, float* dbias, long long rows, int cols, float* dz_scale4,
+                 cum_stream_t stream) {
+    return rowblock_bwd(1, y, dy, dz, dbias, rows, cols, (cudaStream_t)stream, dz_scale4);
 }
 int cum_colsum(const float* d, float* dbias, long long rows, int cols, cum_stream_t stream) {
     return rowblock_bwd(2, nullptr, d, nullptr, dbias, rows, cols, (cudaStream_t)stream);

@@ -50,7 +50,8 @@ constexpr int RB_ROWS = 128;      // minimum rows per CTA; large problems use mo
 template <int MODE>
 __global__ void __launch_bounds__(256) rowblock_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dout,
                                                             float* __restrict__ dz, float* __restrict__ dbias,
-                                                            long long rows, int cols /* of dz / z */, int rows_per_cta) {
+                                                            long long rows, int cols /* of dz / z */, int rows_per_cta,
+                                                            unsigned* __restrict__ amax_bits /* optional: max |dz| for the gradient scale */) {
     const int groups = cols >> 2;                       // float4 groups per row
     const int gpr = groups < 256 ? groups : 256;        // groups handled per pass
     const int slots = 256 / gpr;                        // row slots per pass
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(256) rowblock_bwd_kernel(const float* __restri
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
     const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
     if (ts >= slots) return;
+    float amax = 0.f;
     for (int g = tg; g < groups; g += gpr) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (long long r = r0 + ts; r < r1; r += slots) {
@@ -76,26 +78,38 @@ __global__ void __launch_bounds__(256) rowblock_bwd_kernel(const float* __restri
             }
             if (MODE != 2) reinterpret_cast<float4*>(dz + r * cols)[g] = d;
             acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
         }
         if (dbias) {
             atomicAdd(dbias + 4 * g + 0, acc.x); atomicAdd(dbias + 4 * g + 1, acc.y);
             atomicAdd(dbias + 4 * g + 2, acc.z); atomicAdd(dbias + 4 * g + 3, acc.w);
         }
     }
+    if (amax_bits) {            // one atomic per warp (non-negative floats order like their bits)
+        const unsigned act = __activemask();
+        const unsigned m = __reduce_max_sync(act, __float_as_uint(amax));
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1) && m != 0u) atomicMax(amax_bits, m);
+    }
 }
 
 int rowblock_bwd(int mode, const float* z, const float* dout, float* dz, float* dbias, long long rows, int cols,
-                 cudaStream_t st) {
+                 cudaStream_t st, float* scale4) {
     CUM_REQUIRE(dout && rows > 0 && cols > 0 && cols % 4 == 0, "rowblock_bwd: bad arguments");
     CUM_REQUIRE(mode == 2 || (z && dz), "rowblock_bwd: z/dz required");
     CUM_REQUIRE(mode != 0 || cols % 8 == 0, "glu_bwd: cols must be a multiple of 8");
     long long rpc = cdiv(rows, 8LL * sm_count());      // ~8 CTAs per SM at most -> few thousand atomics per column
     if (rpc < RB_ROWS) rpc = RB_ROWS;
     const unsigned grid = (unsigned)cdiv(rows, rpc);
-    if (mode == 0) rowblock_bwd_kernel<0><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols, (int)rpc);
-    else if (mode == 1) rowblock_bwd_kernel<1><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols, (int)rpc);
-    else rowblock_bwd_kernel<2><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols, (int)rpc);
+    unsigned* amax_bits = scale4 ? reinterpret_cast<unsigned*>(scale4) + 2 : nullptr;
+    if (scale4) {
+        cudaError_t e = cudaMemsetAsync(scale4, 0, 16, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(rowblock_bwd scale)");
+    }
+    if (mode == 0) rowblock_bwd_kernel<0><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols, (int)rpc, amax_bits);
+    else if (mode == 1) rowblock_bwd_kernel<1><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols, (int)rpc, amax_bits);
+    else rowblock_bwd_kernel<2><<<grid, 256, 0, st>>>(z, dout, dz, dbias, rows, cols, (int)rpc, amax_bits);
     CUM_LAUNCH_CHECK("rowblock_bwd_kernel");
+    if (scale4) return grad_scale_finalize(scale4, st);      // {s, 1/s} of dz for the f16x3 gradient GEMMs: no separate amax pass
     return CUM_OK;
 }
 

@@ -93,7 +93,9 @@ int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st);
 long long selective_scan_workspace_bytes(const cum_scan_desc& d);
 
 int glu_fwd(const float* z, const float* addend, float* out, long long rows, int h_pad, cudaStream_t st);
-int rowblock_bwd(int mode, const float* z, const float* dout, float* dz, float* dbias, long long rows, int cols, cudaStream_t st);
+int rowblock_bwd(int mode, const float* z, const float* dout, float* dz, float* dbias, long long rows, int cols, cudaStream_t st,
+                 float* scale4 = nullptr);
+int grad_scale_finalize(float* scale4, cudaStream_t st);
 int add_fwd(const float* a, const float* b, float* out, long long count, cudaStream_t st);
 int wgrad_fwd(const cum_wgrad_desc& d, cudaStream_t st);
 int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st);

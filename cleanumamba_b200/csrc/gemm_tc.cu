@@ -1032,6 +1032,12 @@ __global__ void grad_scale_finalize_kernel(float* __restrict__ scale4) {
     scale4[1] = 1.f / s;
 }
 
+int grad_scale_finalize(float* scale4, cudaStream_t st) {
+    grad_scale_finalize_kernel<<<1, 1, 0, st>>>(scale4);
+    CUM_LAUNCH_CHECK("grad_scale_finalize_kernel");
+    return CUM_OK;
+}
+
 int grad_scale_fwd(const float* x, long long bs, long long rs, int batch, int rows, int cols, float* scale4, cudaStream_t st) {
     CUM_REQUIRE(x && scale4 && batch > 0 && rows > 0 && cols > 0 && cols % 4 == 0 && aligned16(x) && bs % 4 == 0 && rs % 4 == 0,
                 "grad_scale: bad arguments (cols and strides must be multiples of 4, x 16-byte aligned)");

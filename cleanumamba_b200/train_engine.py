@@ -89,6 +89,14 @@ class TrainEngine(Engine):
     def zeros(self, *shape):
         return torch.zeros(*shape, dtype=torch.float32, device=self.device)
 
+    def scale_slot(self):
+        """A free {s, 1/s, -, -} slot for a kernel that computes the scale of the gradient it produces (glu_bwd / relu_bwd)."""
+        if self.math != _lib.MATH_F16X3 or not self.f16_backward:
+            return None
+        sc = self._scale_pool[self._scale_next % self._scale_pool.shape[0]]
+        self._scale_next += 1
+        return sc
+
     def grad_scale(self, t, rows, cols):
         """{s, 1/s} (device, 4 floats) of the contiguous (rows, cols) gradient tensor ``t``: s = the power of two that lifts max|t| to
         [2^14, 2^15).  None outside f16x3 (the other modes keep fp32 range)."""
@@ -256,9 +264,9 @@ class TrainEngine(Engine):
             d = meta["dec"][j]
             rows = B * Tj
             Zd, hg, cin = S["Zd"][j], d["Hg_p"], d["Cin_p"]
+            sc = self.scale_slot()
             self._call("glu_bwd", lib.cum_glu_bwd, Zd.data_ptr(), dg.data_ptr(), Zd.data_ptr(), gk[f"dec{j}.bg"].data_ptr(),
-                       rows, hg, st())                                        # dZ in place
-            sc = self.grad_scale(Zd, rows, 2 * hg)
+                       rows, hg, ptr(sc), st(), launches=1 if sc is None else 2)                 # dZ in place (+ its scale)
             self.wgrad(Zd, 0, 2 * hg, S["xin"][j], 0, 0, cin, rows, f"dec{j}.wg", rows, 2 * hg, cin, 1, scale=sc)
             dx = self.dense_T(Zd, rows, 2 * hg, f"dec{j}.wg", cin, scale=sc)           # gradient of this level's input
             if j > 0:
@@ -267,9 +275,9 @@ class TrainEngine(Engine):
                 dp = meta["dec"][j - 1]
                 co, hgp, Tp = dp["Co_p"], dp["Hg_p"], (Tj - 2) // 2
                 r = S["r"][j - 1]
+                sc = self.scale_slot()
                 self._call("relu_bwd", lib.cum_relu_bwd, r.data_ptr(), dx.data_ptr(), r.data_ptr(), gk[f"dec{j-1}.b"].data_ptr(),
-                           B * (Tp + 1), 2 * co, st())                        # dZ (B, Tp+1, 2co) in place of r
-                sc = self.grad_scale(r, B * (Tp + 1), 2 * co)
+                           B * (Tp + 1), 2 * co, ptr(sc), st(), launches=1 if sc is None else 2)     # dZ (B, Tp+1, 2co) in place of r
                 self.wgrad(r, (Tp + 1) * 2 * co, 2 * co, S["g"][j - 1], 0, Tp * hgp, hgp, Tp, f"dec{j-1}.w", Tp + 1, 2 * co,
                            hgp, B, taps=2, shifts=(0, -1), scale=sc)
                 dg = self.new(B * Tp, hgp)
@@ -347,18 +355,18 @@ class TrainEngine(Engine):
             e = meta["enc"][i]
             rows = B * Ls[i + 1]
             Z, ho, hc = S["Z"][i], e["Ho_p"], e["Hc_p"]
+            sc = self.scale_slot()
             self._call("glu_bwd", lib.cum_glu_bwd, Z.data_ptr(), dskip[i].data_ptr(), Z.data_ptr(), gk[f"enc{i}.bg"].data_ptr(),
-                       rows, ho, st())
-            sc = self.grad_scale(Z, rows, 2 * ho)
+                       rows, ho, ptr(sc), st(), launches=1 if sc is None else 2)
             self.wgrad(Z, 0, 2 * ho, S["y"][i], 0, 0, hc, rows, f"enc{i}.wg", rows, 2 * ho, hc, 1, scale=sc)
             dy = self.dense_T(Z, rows, 2 * ho, f"enc{i}.wg", hc, scale=sc)
             y = S["y"][i]
             if i > 0:
                 cp = e["Cin_p"]
+                sc = self.scale_slot()
                 self._call("relu_bwd", lib.cum_relu_bwd, y.data_ptr(), dy.data_ptr(), y.data_ptr(), gk[f"enc{i}.b"].data_ptr(),
-                           rows, hc, st())                                    # dZ in place of y
+                           rows, hc, ptr(sc), st(), launches=1 if sc is None else 2)             # dZ in place of y
                 src = S["skip"][i - 1]
-                sc = self.grad_scale(y, rows, hc)
                 self.wgrad(y, Ls[i + 1] * hc, hc, src, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2, f"enc{i}.w", Ls[i + 1], hc, 2 * cp, B,
                            taps=2, shifts=(0, 1), scale=sc)
                 dprev = self.new(B * Ls[i], cp)

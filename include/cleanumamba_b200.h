@@ -271,8 +271,12 @@ long long cum_selective_scan_workspace_bytes(const cum_scan_desc* desc);
  *   relu_bwd: dz = dy * (y > 0); dbias (cols) += column sums.     colsum: dbias += column sums of d.
  *   add     : out = a + b (count elements, multiple of 4). */
 int cum_glu_fwd(const float* z, const float* addend, float* out, long long rows, int h_pad, cum_stream_t stream);
-int cum_glu_bwd(const float* z, const float* dout, float* dz, float* dbias, long long rows, int h_pad, cum_stream_t stream);
-int cum_relu_bwd(const float* y, const float* dy, float* dz, float* dbias, long long rows, int cols, cum_stream_t stream);
+/* dz_scale4: NULL, or 4 floats on the device that receive {s, 1/s, -, -} of dz like cum_grad_scale_fwd (the max is taken while dz is
+ * produced: no separate pass before the f16x3 gradient GEMMs). */
+int cum_glu_bwd(const float* z, const float* dout, float* dz, float* dbias, long long rows, int h_pad, float* dz_scale4,
+                cum_stream_t stream);
+int cum_relu_bwd(const float* y, const float* dy, float* dz, float* dbias, long long rows, int cols, float* dz_scale4,
+                 cum_stream_t stream);
 int cum_colsum(const float* d, float* dbias, long long rows, int cols, cum_stream_t stream);
 int cum_add_fwd(const float* a, const float* b, float* out, long long count, cum_stream_t stream);
 

@@ -63,14 +63,22 @@ def test_elementwise_backward_and_colsum():
     _lib.check(lib.cum_glu_fwd(zd.data_ptr(), addd.data_ptr(), out.data_ptr(), rows, H, _lib.stream_ptr()), "glu_fwd")
     assert rel(out, out_ref) < 1e-6
     dz, db = torch.empty(rows, 2 * H, device=DEV), torch.zeros(2 * H, device=DEV)
-    _lib.check(lib.cum_glu_bwd(zd.data_ptr(), doutd.data_ptr(), dz.data_ptr(), db.data_ptr(), rows, H, _lib.stream_ptr()), "glu_bwd")
+    sc4 = torch.full((4,), -1.0, device=DEV)
+    _lib.check(lib.cum_glu_bwd(zd.data_ptr(), doutd.data_ptr(), dz.data_ptr(), db.data_ptr(), rows, H, sc4.data_ptr(), _lib.stream_ptr()), "glu_bwd")
     assert rel(dz, z.grad) < 1e-5 and rel(db, z.grad.sum(0)) < 1e-5
+    # the fused gradient scale: the power of two lifting max|dz| into [2^14, 2^15), and its reciprocal; == cum_grad_scale_fwd
+    s, inv = sc4[0].item(), sc4[1].item()
+    amax = z.grad.abs().max().item()
+    assert s * inv == 1.0 and 2.0 ** 14 <= s * amax * (1 + 1e-6) and s * amax < 2.0 ** 15 * (1 + 1e-6)
+    sc5 = torch.zeros(4, device=DEV)
+    _lib.check(lib.cum_grad_scale_fwd(dz.data_ptr(), 0, 2 * H, 1, rows, 2 * H, sc5.data_ptr(), _lib.stream_ptr()), "grad_scale")
+    assert sc5[0].item() == s and sc5[1].item() == inv
     # relu_bwd + colsum, wide rows (> 256 float4 groups)
     y = torch.relu(torch.randn(70, 1536, generator=g))
     dy = torch.randn(70, 1536, generator=g)
     yd, dyd = y.to(DEV), dy.to(DEV)
     dzr, dbr, cs = torch.empty(70, 1536, device=DEV), torch.zeros(1536, device=DEV), torch.zeros(1536, device=DEV)
-    _lib.check(lib.cum_relu_bwd(yd.data_ptr(), dyd.data_ptr(), dzr.data_ptr(), dbr.data_ptr(), 70, 1536, _lib.stream_ptr()), "relu_bwd")
+    _lib.check(lib.cum_relu_bwd(yd.data_ptr(), dyd.data_ptr(), dzr.data_ptr(), dbr.data_ptr(), 70, 1536, 0, _lib.stream_ptr()), "relu_bwd")
     _lib.check(lib.cum_colsum(dyd.data_ptr(), cs.data_ptr(), 70, 1536, _lib.stream_ptr()), "colsum")
     want = dy * (y > 0)
     assert torch.equal(dzr.cpu(), want) and rel(dbr, want.sum(0)) < 1e-5 and rel(cs, dy.sum(0)) < 1e-5
