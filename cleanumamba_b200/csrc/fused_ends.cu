@@ -77,7 +77,18 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers are only valid after tcgen05.wait::ld.  The wait carries the 32 registers as
+// in/out operands so that the compiler cannot schedule any use of them (or a copy) above it -- a plain `asm volatile` wait orders only
+// against other volatile asm statements, not against the arithmetic that consumes the registers.
+__device__ __forceinline__ void tmem_ld_wait(float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
 
 // fp32 x8 -> fp16 hi (saturating) and lo halves, packed for one 16-byte chunk of a K-major operand row
 __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
@@ -272,7 +283,6 @@ fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 float4 v[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(raw + ((c ^ (row & 7)) << 4));
-                mbar_arrive(raw_empty(buf));                     // the raw tile is in registers: the TMA may refill it
                 mbar_wait(a_empty(buf), ph ^ 1u);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
@@ -284,6 +294,10 @@ fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                     *reinterpret_cast<uint4*>(ahi + off) = hi;
                     *reinterpret_cast<uint4*>(alo + off) = lo;
                 }
+                // The raw tile is handed back to the TMA only now: an arrive issued right behind the loads does not wait for their data
+                // (shared-memory loads complete asynchronously), and the async-proxy refill overtook them -- whole tiles computed from the
+                // NEXT tile's input at three or more tiles per CTA.  Here every loaded value has been consumed by the conversion above.
+                mbar_arrive(raw_empty(buf));
                 fence_proxy_async();
                 mbar_arrive(a_full(buf));
             }
@@ -315,7 +329,7 @@ fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float* v = (c & 1) ? vb : va;
-                tmem_ld_wait();
+                tmem_ld_wait(v);
                 if (c < 3) tmem_ld32_nowait(tsrc + 32 * (c + 1), (c & 1) ? va : vb);
                 if (c == 3) {           // the accumulator is in registers: hand the TMEM buffer back to the MMA thread
                     tc_fence_before();

@@ -415,7 +415,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     }
                                 }
                     }
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    {   // the wait carries the 16 destination registers of the two loads as in/out operands: no use of them (or copy)
+                        // may be scheduled above it (a bare volatile asm orders only against other volatile asm statements)
+                        uint32_t* r0 = reinterpret_cast<uint32_t*>(v[0]);
+                        uint32_t* r1 = reinterpret_cast<uint32_t*>(v[1]);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                                     : "+r"(r0[0]), "+r"(r0[1]), "+r"(r0[2]), "+r"(r0[3]), "+r"(r0[4]), "+r"(r0[5]), "+r"(r0[6]), "+r"(r0[7]),
+                                       "+r"(r1[0]), "+r"(r1[1]), "+r"(r1[2]), "+r"(r1[3]), "+r"(r1[4]), "+r"(r1[5]), "+r"(r1[6]), "+r"(r1[7])
+                                     :: "memory");
+                    }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
 #pragma unroll

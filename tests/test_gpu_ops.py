@@ -380,7 +380,7 @@ def _split_f16(w_dev):
 
 
 @pytest.mark.parametrize("hc,ho", [(64, 64), (56, 56), (32, 32), (24, 40)])
-@pytest.mark.parametrize("b,length", [(1, 200), (2, 4099), (3, 33000), (1, 6)])
+@pytest.mark.parametrize("b,length", [(1, 200), (2, 4099), (3, 33000), (1, 6), (4, 160000)])       # last: > 16 tiles per CTA
 def test_fused_enc0_block(b, length, hc, ho):
     """cum_enc0_block_fwd == F.pad + Conv1d(1,Hc,4,2) + ReLU + Conv1d(Hc,2 Ho,1) + GLU (CleanUMamba.py:108-113), ragged lengths,
     the shipped 64-channel geometry and narrower (pruned) widths that run zero-padded inside the 64 x 128 tile."""
@@ -413,7 +413,7 @@ def test_fused_enc0_block(b, length, hc, ho):
 
 
 @pytest.mark.parametrize("cin,hg", [(64, 64), (56, 64), (32, 32), (40, 24)])
-@pytest.mark.parametrize("b,rows,crop", [(1, 100, 0), (2, 2047, 130), (3, 16500, 0), (1, 1, 1)])
+@pytest.mark.parametrize("b,rows,crop", [(1, 100, 0), (2, 2047, 130), (3, 16500, 0), (1, 1, 1), (4, 80126, 254)])   # last: > 16 tiles per CTA
 def test_fused_dec_last_block(b, rows, crop, cin, hg):
     """cum_dec_last_block_fwd == Conv1d(Cin,2 Hg,1) + GLU + ConvTranspose1d(Hg,1,4,2) + crop + * std (CleanUMamba.py:121-128, :318-319)."""
     import ctypes as C
