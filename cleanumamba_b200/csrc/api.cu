@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <string.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -51,6 +52,14 @@ int ensure_dyn_smem(const void* kernel, int bytes, const char* what) {
     if (e != cudaSuccess) return cuda_fail(e, what);
     g_attr_done.insert(key);
     return CUM_OK;
+}
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CUM_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 void forget_func_attrs() {
     std::lock_guard<std::mutex> lk(g_attr_mu);

@@ -27,6 +27,27 @@ int  cuda_fail(cudaError_t e, const char* what);
         if (e__ != cudaSuccess) return ::cum::cuda_fail(e__, what);     \
     } while (0)
 
+// ---- programmatic dependent launch (PDL): a kernel of the forward path is launched with "programmatic stream serialization", so
+// its CTAs may start -- barrier / TMEM / tensor-map set-up, no global-memory access -- while the previous kernel of the stream is
+// still draining; pdl_wait() (griddepcontrol.wait) blocks until that kernel has completed and its writes are visible, and must
+// precede the first global access.  pdl_trigger() lets the NEXT kernel launch as soon as every CTA of this one has started.
+// The forward of a pruned checkpoint (57 launches of ~10 us) and a streaming step (260 launches) are bound by launch gaps.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();       // CUM_PDL=0 disables (api.cu)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 

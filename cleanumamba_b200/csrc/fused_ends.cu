@@ -142,7 +142,8 @@ fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(FE_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // small operands: GLU bias, the four taps per channel as one float4, conv bias
+    pdl_trigger();
+    // small operands: GLU bias, the four taps per channel as one float4, conv bias (parameters: never written by a kernel of the step)
     // (narrower layers -- pruned checkpoints -- are zero-padded to the 64 x 128 tile: zero taps / biases here, zero-filled TMA boxes)
     for (int i = threadIdx.x; i < FE_N; i += FE_THREADS) bias_s[i] = i < p.n_out ? __ldg(p.bias + i) : 0.f;
     {
@@ -157,6 +158,7 @@ fused_end_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // the previous kernel's output (the waveform / the decoder activations) is read from here on
 
     // tile -> (clip, first row).  dec_last tiles overlap by one row: row 0 of a tile only provides g[p-1] for row 1
     constexpr int STEP = (KIND == 0) ? FE_ROWS : FE_ROWS - 1;
@@ -410,8 +412,8 @@ static int launch_fused_end(const CUtensorMap& tmWh, const CUtensorMap& tmWl, co
     const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)FE_SMEM_BYTES, "cudaFuncSetAttribute(fused_end_kernel)");
     if (rc) return rc;
     const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    kern<<<grid, FE_THREADS, FE_SMEM_BYTES, st>>>(tmWh, tmWl, tmOut, p);
-    CUM_LAUNCH_CHECK("fused_end_kernel");
+    cudaError_t e = launch_kernel(kern, dim3(grid), dim3(FE_THREADS), FE_SMEM_BYTES, st, tmWh, tmWl, tmOut, p);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(fused_end_kernel)");
     return CUM_OK;
 }
 

@@ -173,10 +173,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
     }
+    pdl_trigger();
     tc_fence_before();
     if (CTA2) cluster_sync_all(); else __syncthreads();     // CTA2: the peer's barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // set-up above overlapped the previous kernel's tail; from here on its results are read
 
     auto tile_coords = [&](int tile, int& b, int& m0, int& n0) {
         const int nb = tile % p.n_tiles;
@@ -825,18 +827,20 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
         cfg.blockDim = dim3(Cfg::THREADS);
         cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmAl, tmWh, tmWl, p);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tc_kernel, cluster 2)");
         return CUM_OK;
     }
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmAl, tmWh, tmWl, p);
-    CUM_LAUNCH_CHECK("gemm_tc_kernel");
+    cudaError_t e = launch_kernel(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmA, tmAl, tmWh, tmWl, p);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tc_kernel)");
     return CUM_OK;
 }
 

@@ -20,6 +20,9 @@ __global__ void __launch_bounds__(256) ln_residual_kernel(const float* __restric
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps, long long rows,
                                                            int c, int c_pad) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -78,11 +81,12 @@ int ln_residual_fwd(const float* h, const float* rin, float* rout, float* normed
                 "ln_residual: pointers must be 16-byte aligned");
     const unsigned grid = (unsigned)cdiv(rows, 8);
     const int c4n = c_pad / 4;
-    if (c4n <= 32)        ln_residual_kernel<1><<<grid, 256, 0, st>>>(h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
-    else if (c4n <= 64)   ln_residual_kernel<2><<<grid, 256, 0, st>>>(h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
-    else if (c4n <= 128)  ln_residual_kernel<4><<<grid, 256, 0, st>>>(h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
-    else                  ln_residual_kernel<8><<<grid, 256, 0, st>>>(h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
-    CUM_LAUNCH_CHECK("ln_residual_kernel");
+    cudaError_t e;
+    if (c4n <= 32)        e = launch_kernel(ln_residual_kernel<1>, dim3(grid), dim3(256), 0, st, h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
+    else if (c4n <= 64)   e = launch_kernel(ln_residual_kernel<2>, dim3(grid), dim3(256), 0, st, h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
+    else if (c4n <= 128)  e = launch_kernel(ln_residual_kernel<4>, dim3(grid), dim3(256), 0, st, h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
+    else                  e = launch_kernel(ln_residual_kernel<8>, dim3(grid), dim3(256), 0, st, h, rin, rout, normed, gamma, beta, eps, rows, c, c_pad);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(ln_residual_kernel)");
     return CUM_OK;
 }
 
@@ -103,6 +107,9 @@ __global__ void __launch_bounds__(128) dwconv_silu_kernel(const float* __restric
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            float* __restrict__ y, const float* __restrict__ state,
                                                            int len, int d_pad, int width) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
     if (c4 >= (d_pad >> 2)) return;
     const int b = blockIdx.z;
@@ -144,6 +151,9 @@ __global__ void __launch_bounds__(128) dwconv_silu_kernel(const float* __restric
 __global__ void dwconv_state_kernel(const float* __restrict__ x, long long x_bs, long long x_rs,
                                     const float* __restrict__ state, float* __restrict__ state_out, int len, int d_pad,
                                     int width) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d_pad) return;
     const int b = blockIdx.y;
@@ -173,11 +183,13 @@ int dwconv_silu_fwd(const float* x, long long x_bs, long long x_rs, const float*
     CUM_REQUIRE(batch <= 65535, "dwconv_silu: batch too large");
     dim3 grid((unsigned)cdiv(d_pad / 4, 128), (unsigned)cdiv(len, DW_T), (unsigned)batch);
     CUM_REQUIRE(width == DW_MAXW, "dwconv_silu: only width 4 is instantiated (d_conv=4, CleanUMamba.py:143)");
-    dwconv_silu_kernel<<<grid, 128, 0, st>>>(x, x_bs, x_rs, w, bias, y, conv_state, len, d_pad, width);
+    cudaError_t e = launch_kernel(dwconv_silu_kernel, grid, dim3(128), 0, st, x, x_bs, x_rs, w, bias, y, conv_state, len, d_pad, width);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(dwconv_silu_kernel)");
     CUM_LAUNCH_CHECK("dwconv_silu_kernel");
     if (conv_state_out) {
         dim3 g2((unsigned)cdiv(d_pad, 128), (unsigned)batch);
-        dwconv_state_kernel<<<g2, 128, 0, st>>>(x, x_bs, x_rs, conv_state, conv_state_out, len, d_pad, width);
+        e = launch_kernel(dwconv_state_kernel, g2, dim3(128), 0, st, x, x_bs, x_rs, conv_state, conv_state_out, len, d_pad, width);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(dwconv_state_kernel)");
         CUM_LAUNCH_CHECK("dwconv_state_kernel");
     }
     return CUM_OK;
@@ -240,6 +252,9 @@ struct ScanK : cum_scan_desc {
 
 template <int NS, int SL, int CH, int TC>
 __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_scan_fwd_kernel(const ScanK p) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     constexpr int NP = NS * SL;
     constexpr int NT = CH * SL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -470,6 +485,9 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
 // ---------------------------------------------------------------------------------------------------------
 template <int T>      // tokens per call (compile-time: every token's inputs are requested before the dependent recurrence starts)
 __global__ void __launch_bounds__(256) selective_scan_step_kernel(const cum_scan_desc p) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     const int b = blockIdx.y;
     const int g = threadIdx.x & 15;
     const int c = blockIdx.x * 16 + (threadIdx.x >> 4);         // d % 16 == 0 (host check): whole 16-lane groups stay or leave
@@ -525,8 +543,8 @@ static int launch_scan(const ScanK& d, cudaStream_t st) {
     const size_t smem = sizeof(ScanSmem<NS, SL, CH, TC>);
     { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem, "cudaFuncSetAttribute(selective_scan_fwd_kernel)"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)cdiv(d.d, CH), (unsigned)(d.batch * (d.nseg > 1 ? d.nseg : 1)));
-    kern<<<grid, CH * SL, smem, st>>>(d);
-    CUM_LAUNCH_CHECK("selective_scan_fwd_kernel");
+    cudaError_t e = launch_kernel(kern, grid, dim3(CH * SL), smem, st, d);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_fwd_kernel)");
     return CUM_OK;
 }
 
@@ -573,6 +591,9 @@ long long selective_scan_workspace_bytes(const cum_scan_desc& d) {
 __global__ void __launch_bounds__(256) scan_carry_kernel(const float* __restrict__ e, const float* __restrict__ sum, const float* __restrict__ a2,
                                                           const float* __restrict__ h0, float* __restrict__ h_start, float* __restrict__ h_out,
                                                           int batch, int nseg, int d, int n) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (item, channel, state)
     if (i >= (long long)batch * d * n) return;
     const int st = (int)(i % n);
@@ -597,9 +618,9 @@ int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st) {
     if (d.len <= 2 && d.n_state == 64 && d.d % 16 == 0 && (d.h0 || d.h_out) && !d.h_ckpt && al16(d.a2) && al16(d.Bm) && al16(d.Cm) &&
         (!d.h0 || al16(d.h0)) && (!d.h_out || al16(d.h_out)) && (d.B_rs | d.C_rs | d.B_bs | d.C_bs) % 4 == 0) {
         dim3 grid((unsigned)(d.d / 16), (unsigned)d.batch);
-        if (d.len == 1) selective_scan_step_kernel<1><<<grid, 256, 0, st>>>(d);
-        else selective_scan_step_kernel<2><<<grid, 256, 0, st>>>(d);
-        CUM_LAUNCH_CHECK("selective_scan_step_kernel");
+        cudaError_t e = d.len == 1 ? launch_kernel(selective_scan_step_kernel<1>, grid, dim3(256), 0, st, d)
+                                   : launch_kernel(selective_scan_step_kernel<2>, grid, dim3(256), 0, st, d);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_step_kernel)");
         return CUM_OK;
     }
     ScanK k;
@@ -619,8 +640,8 @@ int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st) {
         if (rc) return rc;
         // pass 2: carry across segments
         const long long n = (long long)d.batch * d.d * d.n_state;
-        scan_carry_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(e, sum, d.a2, d.h0, hstart, d.h_out, d.batch, sp.nseg, d.d, d.n_state);
-        CUM_LAUNCH_CHECK("scan_carry_kernel");
+        cudaError_t ce = launch_kernel(scan_carry_kernel, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, st, (const float*)e, (const float*)sum, d.a2, d.h0, hstart, d.h_out, d.batch, sp.nseg, d.d, d.n_state);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaLaunchKernelEx(scan_carry_kernel)");
         // pass 3: every segment from its true start state
         ScanK c = k;
         c.nseg = sp.nseg; c.seg_len = sp.seg_len; c.seg_sum = nullptr;

@@ -28,6 +28,9 @@ __device__ double block_sum(double v, double* red) {
 
 __global__ void __launch_bounds__(1024) wave_normalize_kernel(float* __restrict__ x, float* __restrict__ std_out,
                                                                int length) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     __shared__ double red[32];
     float* row = x + (long long)blockIdx.x * length;
     double s = 0.0;
@@ -46,8 +49,8 @@ __global__ void __launch_bounds__(1024) wave_normalize_kernel(float* __restrict_
 
 int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStream_t st) {
     CUM_REQUIRE(x && std_out && batch > 0 && length > 0, "wave_normalize: bad arguments");
-    wave_normalize_kernel<<<batch, 1024, 0, st>>>(x, std_out, length);
-    CUM_LAUNCH_CHECK("wave_normalize_kernel");
+    cudaError_t e = launch_kernel(wave_normalize_kernel, dim3(batch), dim3(1024), 0, st, x, std_out, length);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(wave_normalize_kernel)");
     return CUM_OK;
 }
 
@@ -60,6 +63,9 @@ int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStre
 __global__ void __launch_bounds__(256) stream_std_kernel(const float* __restrict__ x, long long x_stride, int frames,
                                                           int frame_len, int hop, int frames_before, const int* __restrict__ frames_counter,
                                                           float* __restrict__ running, float* __restrict__ scale_out) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     __shared__ double red[32];
     const int b = blockIdx.x;
     if (frames_counter) frames_before = *frames_counter;       // device-side frame count (CUDA-graph replays: no host argument changes)
@@ -84,17 +90,21 @@ __global__ void __launch_bounds__(256) stream_std_kernel(const float* __restrict
     if (threadIdx.x == 0) running[b] = run;
 }
 
-__global__ void add_int_kernel(int* counter, int v) { *counter += v; }
+__global__ void add_int_kernel(int* counter, int v) {
+    pdl_wait();
+    *counter += v;
+}
 
 int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
                    int frames_before, float* running, float* scale_out, cudaStream_t st, int* frames_counter) {
     CUM_REQUIRE(x && running && scale_out, "stream_std: null pointer");
     CUM_REQUIRE(batch > 0 && frames > 0 && frame_len > 0 && hop > 0 && frames_before >= 0, "stream_std: bad shape");
-    stream_std_kernel<<<batch, 256, 0, st>>>(x, x_stride, frames, frame_len, hop, frames_before, frames_counter, running, scale_out);
-    CUM_LAUNCH_CHECK("stream_std_kernel");
+    cudaError_t e = launch_kernel(stream_std_kernel, dim3(batch), dim3(256), 0, st, x, x_stride, frames, frame_len, hop, frames_before,
+                                  (const int*)frames_counter, running, scale_out);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(stream_std_kernel)");
     if (frames_counter) {       // every block has read the counter: stream order
-        add_int_kernel<<<1, 1, 0, st>>>(frames_counter, frames);
-        CUM_LAUNCH_CHECK("add_int_kernel");
+        e = launch_kernel(add_int_kernel, dim3(1), dim3(1), 0, st, frames_counter, frames);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(add_int_kernel)");
     }
     return CUM_OK;
 }
@@ -136,6 +146,9 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                                                        float* __restrict__ y, void* __restrict__ y_lo, int rows_out, int c_pad, int kernel,
                                                        int stride, const float* __restrict__ in_scale, int scale_groups,
                                                        int group_rows, int row_offset) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     extern __shared__ float xs[];
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * CI_ROWS;
@@ -172,6 +185,9 @@ template <int OUTF>
 __global__ void __launch_bounds__(256) conv_in_c64_kernel(const float* __restrict__ x, long long x_stride, int length,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            float* __restrict__ y, void* __restrict__ y_lo, int rows_out) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     __shared__ __align__(16) float xs[CIF_ROWS * 2 + 4];
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * CIF_ROWS;
@@ -244,6 +260,9 @@ __global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict_
                                                          const float* __restrict__ scale, int scale_groups,
                                                          int scale_group, float* __restrict__ out, long long out_stride,
                                                          int first, int length, int kernel, int stride, int halo) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     extern __shared__ float dots[];  // [(CT_ROWS + halo)][kernel]
     const int b = blockIdx.y;
     const long long mbase = (long long)first + (long long)blockIdx.x * CT_ROWS * stride;  // first output of this CTA
@@ -315,6 +334,9 @@ __global__ void __launch_bounds__(256) convt_out_c64_kernel(const float* __restr
                                                              float bias, const float* __restrict__ scale, int scale_groups,
                                                              int scale_group, float* __restrict__ out, long long out_stride,
                                                              int first, int length) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
     __shared__ float dots[(CTF_ROWS + 2) * 4];
     const int b = blockIdx.y;
     const long long mbase = (long long)first + (long long)blockIdx.x * CTF_ROWS * 2;
