@@ -443,6 +443,84 @@ def run_sweep(args, net, eng, dev):
                       "sweep": rows}))
 
 
+def run_pruned(args, dev):
+    """BASELINE.json configs[0]: the shipped pruned checkpoint E8-pruned-500K (492 K parameters, trained, irregular widths),
+    batch 4 x 10 s -- the product on one GPU next to the reference's own CPU path (unmodified reference when staged) on the SAME
+    checkpoint and input.  The checkpoint comes from tests/golden/e8_pruned_500k.pt (state_dict + config of the reference's .pkl)."""
+    import json as _json
+    from cleanumamba_b200.network import Net
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "e8_pruned_500k.pt"), map_location="cpu", weights_only=True)
+    cfgp = _json.loads(fx["config"])
+    B, sec = (args.batch if args.batch != 64 else 4), args.seconds
+    x = synth_noisy(B, sec, 1234)
+    net = Net("CleanUMamba", dict(cfgp, math_mode=args.math))
+    net.load_pruned_state_dict(fx["state_dict"])
+    net = net.to(dev).float().eval()
+    host_in, host_out = x.pin_memory(), torch.empty(B, 1, int(sec * SR)).pin_memory()
+    x_dev, work = x.to(dev), torch.empty(B, 1, int(sec * SR), device=dev)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 5)):
+            work.copy_(x_dev); y = net(work)
+        torch.cuda.synchronize()
+        eng = net.engine()
+        eng.launches = 0
+        work.copy_(x_dev); eng._forward_eager(work)           # kernels per forward (the timed steps replay them from a CUDA graph)
+        per_forward = eng.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            work.copy_(x_dev); y = net(work)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            work.copy_(host_in, non_blocking=True)
+            host_out.copy_(net(work), non_blocking=True)
+        f1.record()
+        torch.cuda.synchronize()
+        ms_e2e = f0.elapsed_time(f1) / args.steps
+    # CPU arm on the same checkpoint: the unmodified reference when staged, else the oracle port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    kind, fwd = "port", None
+    try:
+        import ref_loader
+        if ref_loader.reference_available():
+            refnet = ref_loader.import_reference()
+            rn = refnet.Net("CleanUMamba", dict(cfgp))
+            rn.load_pruned_state_dict({k: v.clone() for k, v in fx["state_dict"].items()})
+            rn = rn.float().eval()
+            kind, fwd = "reference", (lambda: rn(x.clone()))
+    except Exception as exc:      # noqa: BLE001
+        print(f"# unmodified reference unavailable: {exc!r}", file=sys.stderr)
+    if fwd is None:
+        import cleanumamba_oracle as orc
+        fwd = lambda: orc.forward(fx["state_dict"], x.clone())      # noqa: E731
+    with torch.no_grad():
+        ref_out = fwd()
+        t0 = time.perf_counter()
+        n_cpu = 5
+        for _ in range(n_cpu):
+            fwd()
+        cpu_ms = (time.perf_counter() - t0) / n_cpu * 1e3
+    err = (y.cpu() - ref_out).abs().max().item()
+    print(_json.dumps({"metric": METRIC + " [pruned checkpoint]", "value": round(B * sec / (ms / 1e3), 1), "unit": UNIT, "n_gpus": 1,
+                       "steps": args.steps, "warmup": max(args.warmup, 5), "ms_per_step": round(ms, 4), "higher_is_better": True,
+                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                       "config": {"workload": f"CleanUMamba E8 pruned-500K (shipped checkpoint, 491 655 parameters), offline forward, batch {B} x "
+                                              f"{sec:g} s @16 kHz, math={args.math}; CUDA-graph replay of the forward", "global_batch": B},
+                       "e2e": {"value": round(B * sec / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": B * int(sec * SR) * 4,
+                               "d2h_bytes_per_step": B * int(sec * SR) * 4, "ms_per_step": round(ms_e2e, 4)},
+                       "gpu_launches": per_forward * args.steps,
+                       "parity_max_abs_vs_cpu_arm": err,
+                       "cpu_baseline": {"value": round(B * sec / (cpu_ms / 1e3), 2), "unit": UNIT, "cores": threads, "kind": kind,
+                                        "sample": f"the whole batch ({B} x {sec:g} s) per step, {n_cpu} steps after 1 warm-up, fp32, {threads} threads",
+                                        "ms_per_step": round(cpu_ms, 1)}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -459,7 +537,7 @@ def main():
                          "full-scale amplitude); fp32 = exact CUDA-core FFMA")
     ap.add_argument("--no-variants", action="store_true", help="skip the short tf32x3 / fp32 comparison runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="offline", choices=["offline", "stream", "train", "sweep"],
+    ap.add_argument("--mode", default="offline", choices=["offline", "stream", "train", "sweep", "pruned"],
                     help="offline = headline (configs[1]); stream = configs[2]: carried-state chunked inference; "
                          "train = configs[3]: fwd + L1/MR-STFT loss + bwd + Adam, data-parallel gradient all-reduce")
     ap.add_argument("--streams", type=int, default=4096, help="[stream] concurrent streams per GPU")
@@ -498,6 +576,10 @@ def main():
         return
     if args.mode == "sweep":
         run_sweep(args, net, eng, dev)
+        return
+    if args.mode == "pruned":
+        del net, eng
+        run_pruned(args, dev)
         return
     B, T = args.batch, int(args.seconds * SR)
     host_in = synth_noisy(B, args.seconds, 1234 + rank).pin_memory()
