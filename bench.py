@@ -721,12 +721,16 @@ def main():
     scan_roof = None
     if scan:
         gbs = scan["bytes"] / (scan["ms"] / 1e3) / 1e9
+        ups = scan["flops"] / (scan["ms"] / 1e3)
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        ceiling = 16 * 148 * mhz * 1e6            # 16 ex2 per clock and SM at the SM clock the box actually held during the timed region
         scan_roof = {"kernel": "selective_scan_fwd", "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"],
                      "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4), "traffic": None,
-                     "state_updates_per_s": round(scan["flops"] / (scan["ms"] / 1e3), 0),
+                     "state_updates_per_s": round(ups, 0),
+                     "mufu_ceiling_updates_per_s": round(ceiling, 0), "mufu_frac": round(ups / ceiling, 4), "sm_mhz": mhz,
                      "share_of_step": round(scan["ms"] / total_kernel_ms, 4),
-                     "note": "d_state=64: MUFU(ex2)/FMA-bound, not HBM-bound (SURVEY.md §7); 16 ex2/clk/SM ceiling = %.3g updates/s"
-                             % (16 * 148 * 1.9e9)}
+                     "note": "d_state=64: one MUFU ex2 per state update -- MUFU-bound, not HBM-bound (SURVEY.md §7); mufu_frac = state "
+                             "updates/s over the 16 ex2/clk/SM ceiling at the SM clock sampled during the timed region"}
     kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] // args.steps}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
