@@ -857,6 +857,15 @@ static int cta2_policy() {
     return v;
 }
 
+static bool narrow_pairs() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CUM_GEMM_CTA2_N128");
+        v = (e && e[0] == '0') ? 0 : 1;          // measured: 41.9-42.5 vs 42.5-42.7 ms per E8-full 64 x 10 s step
+    }
+    return v != 0;
+}
+
 template <int MODE, int BN, bool CTA2>
 static int dispatch_epi2(const cum_gemm_desc& d, cudaStream_t st) {
     if (d.c_lo) {           // fp16 hi / lo output planes (and addend): the activation format TC_F16PS consumes
@@ -901,10 +910,12 @@ static int dispatch_epi2(const cum_gemm_desc& d, cudaStream_t st) {
 
 template <int MODE, int BN>
 static int dispatch_epi(const cum_gemm_desc& d, cudaStream_t st) {
-    if constexpr (BN == 256) {
-        // a CTA pair per 256 x 256 tile when there are enough rows to fill whole pairs
+    {
+        // a CTA pair per 256 x BN tile when there are enough rows to fill whole pairs (BN = 128: the 128-channel layers are bound by
+        // the shared-memory datapath -- MMA operand reads + TMA writes -- and a pair stages only half of the weight tile per CTA;
+        // CUM_GEMM_CTA2_N128=0 restores single CTAs for them)
         const int pol = d.cta_pair != 0 ? d.cta_pair : cta2_policy();
-        const bool want = pol >= 0;
+        const bool want = pol >= 0 && (BN == 256 || narrow_pairs());
         if (want && d.m > TC_BM && (sm_count() & 1) == 0) return dispatch_epi2<MODE, BN, true>(d, st);
     }
     return dispatch_epi2<MODE, BN, false>(d, st);
