@@ -30,7 +30,8 @@ class GemmDesc(C.Structure):
                 ("m", C.c_int), ("n", C.c_int), ("batch", C.c_int), ("epilogue", C.c_int),
                 ("addend", C.c_void_p), ("add_batch_stride", C.c_longlong), ("add_row_stride", C.c_longlong),
                 ("math", C.c_int), ("w_lo", C.c_void_p), ("acc_scale", C.c_float), ("out_bf16", C.c_int), ("w_lo_is_zero", C.c_int),
-                ("a_lo", C.c_void_p), ("c_lo", C.c_void_p), ("addend_lo", C.c_void_p), ("a_scale_dev", C.c_void_p), ("cta_pair", C.c_int)]
+                ("a_lo", C.c_void_p), ("c_lo", C.c_void_p), ("addend_lo", C.c_void_p), ("a_scale_dev", C.c_void_p), ("aux", C.c_void_p), ("aux_batch_stride", C.c_longlong), ("aux_row_stride", C.c_longlong),
+                ("cta_pair", C.c_int)]
 
 
 class Enc0BlockDesc(C.Structure):

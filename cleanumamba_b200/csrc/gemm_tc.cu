@@ -96,6 +96,8 @@ struct TcParams {
     int mn_splits;            // MN-major wgrad: splits per clip ("batch" = clip * mn_splits + split, k_blocks K-blocks of 32 rows per split)
     const float* acc_scale_ptr;   // optional device-side factor multiplied into acc_scale (1 / gradient scale computed on the device)
     const float* a_scale_ptr;     // optional device-side factor applied to A by the fp16 operand splitter (gradient scale)
+    float* aux; long long aux_bs, aux_rs;   // optional second fp32 output (training): the value BEFORE the gate (GLU epilogues: the
+                                            // (rows, n) pre-activation) or before the addend (other epilogues: same shape as c)
     void* c_lo;               // OUTF == 2: low-half plane of the output (c is the high-half plane), fp16
     const void* addend_lo;    // OUTF == 2: low-half plane of the addend
 };
@@ -369,6 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const unsigned cs8 = 8u * (unsigned)p.c_rs * CES, as8 = 8u * (unsigned)p.add_rs * (unsigned)aes;     // bytes per 8 rows
                 auto cp = [&](int h, int rh) { return cp0 + (size_t)((2 * h + rh) * cs8); };
                 auto ao = [&](int h, int rh) { return ao0 + (unsigned)(2 * h + rh) * as8; };
+                float* const auxb = (OUTF == 0 && p.aux) ? p.aux + (long long)b * p.aux_bs : nullptr;
                 const long long lo_delta = OUTS ? reinterpret_cast<char*>(p.c_lo) - reinterpret_cast<char*>(p.c) : 0;      // hi -> lo plane
                 const long long alo_delta = ADDS ? reinterpret_cast<const char*>(p.addend_lo) - reinterpret_cast<const char*>(p.addend) : 0;
                 constexpr int CSTEP = (GLU ? 32 : 64) * CES;                    // bytes per chunk stride (64 accumulator columns)
@@ -465,6 +468,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
                                         o[k] = x0 * tc_gate<EPI>(p.epi, x1);
                                         if (has_add) o[k] += ad[h][rh][k].x;
+                                        if (OUTF == 0 && auxb && rok[h][rh] && kok[k])       // training: the pre-activation pair is saved for the GLU backward
+                                            *reinterpret_cast<float2*>(auxb + (long long)(row0 + (2 * h + rh) * 8) * p.aux_rs + (n0 + c0 + 8 * k + 2 * tq)) = make_float2(x0, x1);
                                     }
                                     const float got = __shfl_xor_sync(0xffffffffu, odd ? o[0] : o[1], 1);
                                     if (ok) *reinterpret_cast<float2*>(cp(h, rh)) = odd ? make_float2(got, o[1]) : make_float2(o[0], got);
@@ -475,6 +480,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         const float x0 = F16 ? fmaf(v[h][4 * k + 2 * rh + 0], acc_scale, bv[k].x) : v[h][4 * k + 2 * rh + 0] + bv[k].x;
                                         const float x1 = F16 ? fmaf(v[h][4 * k + 2 * rh + 1], acc_scale, bv[k].y) : v[h][4 * k + 2 * rh + 1] + bv[k].y;
                                         o[k] = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
+                                        if (OUTF == 0 && auxb && rok[h][rh] && kok[k])       // training: the value before the skip add (its sign is the ReLU mask)
+                                            *reinterpret_cast<float2*>(auxb + (long long)(row0 + (2 * h + rh) * 8) * p.aux_rs + (n0 + c0 + 8 * k + 2 * tq)) = o[k];
                                         if (has_add) { o[k].x += ad[h][rh][k].x; o[k].y += ad[h][rh][k].y; }
                                     }
                                     const float2 snd = odd ? o[0] : o[1];
@@ -814,6 +821,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.skip_wlo = (X3 && d.w_lo_is_zero) ? 1 : 0;
     p.w_k_batch_stride = g_wgrad_kbs; p.w_k_off = g_wgrad_koff;
     p.mn_splits = 0;
+    p.aux = (OUTF == 0) ? d.aux : nullptr; p.aux_bs = d.aux_batch_stride; p.aux_rs = d.aux_row_stride;
     p.a_scale_ptr = (MODE == TC_F16X3) ? d.a_scale_dev : nullptr;
     p.acc_scale_ptr = (MODE == TC_F16X3 && d.a_scale_dev) ? d.a_scale_dev + 1 : nullptr;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
@@ -1259,6 +1267,9 @@ int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.a_row_stride >= d.k || d.a_rows == 1, "gemm_tc: a_row_stride < k");
     CUM_REQUIRE(!d.a_scale_dev || (d.math == CUM_MATH_F16X3 && !d.a_lo), "gemm_tc: a_scale_dev needs CUM_MATH_F16X3 with fp32 activations");
+    CUM_REQUIRE(!d.aux || (!d.out_bf16 && !d.c_lo && aligned16(d.aux) && d.aux_row_stride % 2 == 0 && d.aux_batch_stride % 2 == 0 &&
+                           (d.epilogue == CUM_EPI_NONE || d.epilogue == CUM_EPI_RELU || epi_is_glu(d.epilogue))),
+                "gemm_tc: aux (second output) needs an fp32 output, even strides and a NONE / RELU / GLU epilogue");
     CUM_REQUIRE(d.out_bf16 || d.c_lo || (aligned16(d.c) && d.c_row_stride % 4 == 0 && (d.batch == 1 || d.c_batch_stride % 4 == 0)),
                 "gemm_tc: an fp32 output must be 16-byte aligned with row / batch strides that are multiples of 4 elements (c_row_stride=%lld)",
                 (long long)d.c_row_stride);

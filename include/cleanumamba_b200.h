@@ -158,6 +158,11 @@ typedef struct cum_gemm_desc {
     const float* a_scale_dev;/* CUM_MATH_F16X3 with fp32 `a` only: NULL, or a DEVICE pointer to {s, 1/s} (cum_grad_scale_fwd): `a` is multiplied
                                 by s while it is split into fp16 halves and the accumulator by 1/s -- back-propagated gradients
                                 (~1e-6) are lifted into fp16's range by a power of two computed on the device, no host sync */
+    float* aux; long long aux_batch_stride; long long aux_row_stride;
+                             /* optional SECOND fp32 output of a tensor-core call (training keeps what the backward needs without a
+                                separate elementwise kernel): with a GLU epilogue the (m, n) PRE-ACTIVATION (bias added, before the
+                                gate; row stride aux_row_stride >= n); with NONE / RELU the (m, n) value BEFORE the addend.  fp32
+                                output only; NULL = off */
     int cta_pair;            /* tiles wider than 128 columns can run on CTA pairs (tcgen05 cta_group::2: 256-row tiles, each CTA
                                 stages half of the weight tile).  0 = automatic (pairs whenever a problem has more than 128 rows),
                                 1 = same, -1 = never.  Same products, same accumulation order: bit-identical results */
