@@ -289,7 +289,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------ op wrappers
     def gemm(self, a, a_off, a_bs, a_rs, a_rows, k, w, bias, c, c_off, c_bs, c_rs, m, n, batch, epi,
-             taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None, a_scale=None):
+             taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None, a_scale=None, aux=None, aux_bs=0, aux_rs=0):
         d = GemmDesc()
         d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k = a.data_ptr() + a.element_size() * a_off, a_bs, a_rs, a_rows, k
         # "hl16" tensors (dtype float16, leading dimension 2 = [hi plane, lo plane], see cum_gemm_desc.a_lo): pre-split activations
@@ -319,16 +319,18 @@ class Engine:
         d.addend, d.add_batch_stride, d.add_row_stride = ptr(addend), add_bs, add_rs
         if a_scale is not None and d.math == _lib.MATH_F16X3 and a.dtype == torch.float32:
             d.a_scale_dev = a_scale.data_ptr()          # device-side power-of-two scale of a gradient operand (TrainEngine)
+        if aux is not None:         # training: second fp32 output (pre-gate / pre-addend value), see cum_gemm_desc.aux
+            d.aux, d.aux_batch_stride, d.aux_row_stride = aux.data_ptr(), aux_bs, aux_rs
         kind = "gemm_tap2" if taps == 2 else "gemm"
         self._call(kind, self.lib.cum_gemm_bias_act_fwd, C.byref(d), _lib.stream_ptr(),
                    flops=2 * batch * m * n * k * taps)
 
-    def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None, out_dtype=torch.float32):
-        """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers."""
+    def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None, out_dtype=torch.float32, aux=None):
+        """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers.  ``aux`` (rows, n): the pre-activation (training)."""
         n_out = n // 2 if epi >= 8 else n
         c = out if out is not None else self.act_buffer(rows, n_out, out_dtype, a.device)
         self.gemm(a, a_off, 0, k if a_rs is None else a_rs, rows, k, w, bias, c, 0, 0, n_out, rows, n, 1, epi,
-                  addend=addend, add_bs=0, add_rs=n_out)
+                  addend=addend, add_bs=0, add_rs=n_out, aux=aux, aux_rs=n)
         return c
 
     @staticmethod

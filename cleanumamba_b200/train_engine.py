@@ -16,7 +16,7 @@ from typing import Dict, List
 import torch
 
 from . import _lib
-from ._lib import EPI_NONE, EPI_RELU, ScanBwdDesc, ScanDesc, WgradDesc, check, ptr
+from ._lib import EPI_GLU, EPI_NONE, EPI_RELU, ScanBwdDesc, ScanDesc, WgradDesc, check, ptr
 from .engine import Engine, on_model_device
 
 
@@ -35,6 +35,9 @@ class TrainEngine(Engine):
     # underflow fp16, so every gradient tensor that feeds a GEMM gets a power-of-two scale computed ON THE DEVICE from its max
     # (cum_grad_scale_fwd): the operand splitter multiplies by it, the epilogue divides it out, the weight-gradient GEMM shares it.
     f16_backward = os.environ.get("CUM_TRAIN_F16_BWD", "1") != "0"
+    # tensor-core modes: the GLU gate and the decoder's skip add run in the GEMM epilogue, which ALSO stores what the backward needs
+    # (the pre-activation / the pre-add value: cum_gemm_desc.aux) -- no stand-alone glu_fwd / add kernels
+    fused_forward = os.environ.get("CUM_TRAIN_FUSED_FWD", "1") != "0"
     f16_forward = os.environ.get("CUM_TRAIN_F16_FWD", "1") != "0"     # f16x3 models: forward GEMMs in f16x3 (A/B switch)
 
     def _pack(self):
@@ -163,6 +166,7 @@ class TrainEngine(Engine):
         S["Ls"] = Ls
         S["y"], S["Z"], S["skip"] = [], [], []
         prev = None
+        fuse = self.fused_forward and self.math != _lib.MATH_FP32
         for i, e in enumerate(meta["enc"]):
             rows = B * Ls[i + 1]
             y = self.new(rows, e["Hc_p"])
@@ -173,9 +177,13 @@ class TrainEngine(Engine):
                 cp = e["Cin_p"]
                 self.gemm(prev, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
                           y, 0, Ls[i + 1] * e["Hc_p"], e["Hc_p"], Ls[i + 1], e["Hc_p"], B, EPI_RELU, taps=2, shifts=(0, 1))
-            Z = self.dense(y, rows, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"])
-            prev = self.new(rows, e["Ho_p"])
-            self._call("glu_fwd", lib.cum_glu_fwd, Z.data_ptr(), 0, prev.data_ptr(), rows, e["Ho_p"], st())
+            if fuse:        # gate in the epilogue, pre-activation saved through the second output
+                Z = self.new(rows, 2 * e["Ho_p"])
+                prev = self.dense(y, rows, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=EPI_GLU["Sigmoid"], aux=Z)
+            else:
+                Z = self.dense(y, rows, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"])
+                prev = self.new(rows, e["Ho_p"])
+                self._call("glu_fwd", lib.cum_glu_fwd, Z.data_ptr(), 0, prev.data_ptr(), rows, e["Ho_p"], st())
             S["y"].append(y); S["Z"].append(Z); S["skip"].append(prev)
 
         T = Ls[D]
@@ -212,18 +220,28 @@ class TrainEngine(Engine):
         out = None
         for j, d in enumerate(meta["dec"]):
             S["xin"].append(xcur)
-            Zd = self.dense(xcur, B * Tj, d["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * d["Hg_p"])
-            g = self.new(B * Tj, d["Hg_p"])
-            self._call("glu_fwd", lib.cum_glu_fwd, Zd.data_ptr(), 0, g.data_ptr(), B * Tj, d["Hg_p"], st())
+            if fuse:
+                Zd = self.new(B * Tj, 2 * d["Hg_p"])
+                g = self.dense(xcur, B * Tj, d["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * d["Hg_p"], epi=EPI_GLU["Sigmoid"], aux=Zd)
+            else:
+                Zd = self.dense(xcur, B * Tj, d["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * d["Hg_p"])
+                g = self.new(B * Tj, d["Hg_p"])
+                self._call("glu_fwd", lib.cum_glu_fwd, Zd.data_ptr(), 0, g.data_ptr(), B * Tj, d["Hg_p"], st())
             S["Zd"].append(Zd); S["g"].append(g)
             if j < D - 1:
                 co = d["Co_p"]
                 To = 2 * Tj + 2
                 r = self.new(B * To, co)
-                self.gemm(g, 0, Tj * d["Hg_p"], d["Hg_p"], Tj, d["Hg_p"], f"dec{j}.w", pk[f"dec{j}.b"],
-                          r, 0, To * co, 2 * co, Tj + 1, 2 * co, B, EPI_RELU, taps=2, shifts=(0, -1))
                 nxt = self.new(B * To, co)
-                self._call("add", lib.cum_add_fwd, r.data_ptr(), S["skip"][D - 2 - j].data_ptr(), nxt.data_ptr(), B * To * co, st())
+                if fuse:    # skip add in the epilogue; the pre-add ReLU output (the mask of the backward) leaves through the second output
+                    skip = S["skip"][D - 2 - j]
+                    self.gemm(g, 0, Tj * d["Hg_p"], d["Hg_p"], Tj, d["Hg_p"], f"dec{j}.w", pk[f"dec{j}.b"],
+                              nxt, 0, To * co, 2 * co, Tj + 1, 2 * co, B, EPI_RELU, taps=2, shifts=(0, -1),
+                              addend=skip, add_bs=To * co, add_rs=2 * co, aux=r, aux_bs=To * co, aux_rs=2 * co)
+                else:
+                    self.gemm(g, 0, Tj * d["Hg_p"], d["Hg_p"], Tj, d["Hg_p"], f"dec{j}.w", pk[f"dec{j}.b"],
+                              r, 0, To * co, 2 * co, Tj + 1, 2 * co, B, EPI_RELU, taps=2, shifts=(0, -1))
+                    self._call("add", lib.cum_add_fwd, r.data_ptr(), S["skip"][D - 2 - j].data_ptr(), nxt.data_ptr(), B * To * co, st())
                 S["r"].append(r)
                 xcur, Tj = nxt, To
             else:
