@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(TcCfg<MODE, BN, CTA2>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const TcParams p) {
     using Cfg = TcCfg<MODE, BN, CTA2>;
-    static_assert(!MNM || MODE == TC_F16PS, "MN-major operands: pre-split fp16 planes only");
+    static_assert(!MNM || MODE == TC_F16PS || MODE == TC_F16X3, "MN-major operands: fp16 hi / lo tiles (pre-split planes, or fp32 A split in the kernel)");
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool X3 = Cfg::PASS3;              // three MMA passes, W_lo exists
     constexpr bool SPL = Cfg::SPLIT;             // splitter warps between TMA and MMA
@@ -218,15 +218,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // rows / channels outside the tensors arrive as zeros
                     const int clip = b / p.mn_splits, sp = b - clip * p.mn_splits;
                     const int r = (sp * p.k_blocks + kb) * 32;
-                    const uint32_t bar = CTA2 ? mapa_rank(full_bar(s), 0) : full_bar(s);
-                    if (!CTA2 || rank == 0) mbar_arrive_expect_tx(full_bar(s), (CTA2 ? 2 : 1) * tx);
+                    // with the in-kernel splitter every CTA's bytes are counted on its own barrier (the splitter relays "ready" to
+                    // the leader); without it the leader's MMA thread waits for the bytes of both CTAs directly
+                    const bool remote = CTA2 && !SPL;
+                    const uint32_t bar = remote ? mapa_rank(full_bar(s), 0) : full_bar(s);
+                    if (!remote || rank == 0) mbar_arrive_expect_tx(full_bar(s), (remote ? 2 : 1) * tx);
                     auto ld = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
-                        if (CTA2) tma_load_3d_2sm(dst, m, bar, c0, c1, clip); else tma_load_3d(dst, m, bar, c0, c1, clip);
+                        if (remote) tma_load_3d_2sm(dst, m, bar, c0, c1, clip); else tma_load_3d(dst, m, bar, c0, c1, clip);
                     };
+                    if (SPL) {          // raw fp32 gradient tile: four slabs of 32 channels x 32 rows (split in place by the splitter warps)
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        ld(smem_base + ahi_off(s) + i * 4096, &tmA, m0 + 64 * i, r);
-                        ld(smem_base + alo_off(s) + i * 4096, &tmAl, m0 + 64 * i, r);
+                        for (int i = 0; i < 4; ++i) ld(smem_base + a_off(s) + i * 4096, &tmA, m0 + 32 * i, r);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            ld(smem_base + ahi_off(s) + i * 4096, &tmA, m0 + 64 * i, r);
+                            ld(smem_base + alo_off(s) + i * 4096, &tmAl, m0 + 64 * i, r);
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < Cfg::W_ROWS / 64; ++i) {
@@ -557,7 +565,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tile = tile0; tile < total_tiles; tile += tstep) {
             for (int it = 0; it < k_iters; ++it) {
                 mbar_wait(full_bar(s), ph);
-                if (BF) {
+                if constexpr (MNM != 0) {
+                    // MN-major: raw = four slabs (32 channels x 32 rows, 128-byte rows of fp32, 128B swizzle) -> hi / lo = two slabs each
+                    // (64 channels x 32 rows, 128-byte rows of fp16, 128B swizzle).  Item = one 16-byte fp16 chunk = 8 channels of one row
+                    // = two raw 16-byte chunks; 512 items, four per thread, all reads before the writes (in-place overwrite).
+                    const uint8_t* raw = smem_gen + a_off(s);
+                    uint8_t* hi = smem_gen + ahi_off(s);
+                    uint8_t* lo = smem_gen + alo_off(s);
+                    float4 va[4], vb[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = t + 128 * j;
+                        const int r = i >> 4, qg = i & 15;              // row, fp16 chunk index over the 128 channels
+                        const uint8_t* src = raw + (qg >> 2) * 4096 + r * 128;
+                        va[j] = *reinterpret_cast<const float4*>(src + (((2 * (qg & 3)) ^ (r & 7)) << 4));
+                        vb[j] = *reinterpret_cast<const float4*>(src + (((2 * (qg & 3) + 1) ^ (r & 7)) << 4));
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");     // the four splitter warps only
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = t + 128 * j;
+                        const int r = i >> 4, qg = i & 15;
+                        const float4 v0 = va[j], v1 = vb[j];
+                        const float f[8] = {v0.x * asc, v0.y * asc, v0.z * asc, v0.w * asc, v1.x * asc, v1.y * asc, v1.z * asc, v1.w * asc};
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            h[e] = cvt_f16x2_sat(f[2 * e], f[2 * e + 1]);
+                            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
+                            l[e] = cvt_f16x2_sat(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+                        }
+                        const uint32_t off = (uint32_t)(qg >> 3) * 4096u + (uint32_t)r * 128u + (uint32_t)(((qg & 7) ^ (r & 7)) << 4);
+                        *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
+                } else if (BF) {
                     // fp32 tile (128 x 32, 128B-swizzled rows) -> bf16 hi / lo tiles (128 x 32, 64B-swizzled rows)
                     const uint8_t* raw = smem_gen + a_off(s);
                     uint8_t* hi = smem_gen + ahi_off(s);
@@ -1123,17 +1165,29 @@ static WgradMnPlan plan_wgrad_mn(const cum_wgrad_desc& d) {
     return w;
 }
 
-template <int BN, bool CTA2>
+// ZSPLIT: the gradient operand is read as fp32 straight from dz and split by the kernel's splitter warps (scaled by *scale);
+// otherwise z_hi / z_lo are pre-split fp16 planes
+template <int BN, bool CTA2, bool ZSPLIT>
 static int launch_wgrad_mn(const __half* z_hi, const __half* z_lo, const __half* a_hi, const __half* a_lo, const WgradMnPlan& w,
-                           const cum_wgrad_desc& d, int tap, const float* inv_scale, cudaStream_t st) {
-    using Cfg = TcCfg<TC_F16PS, BN, CTA2>;
-    auto kern = gemm_tc_kernel<TC_F16PS, BN, TC_EPI_ATOMIC_ADD, 0, CTA2, 1>;
+                           const cum_wgrad_desc& d, int tap, const float* scale, cudaStream_t st) {
+    constexpr int MODE = ZSPLIT ? TC_F16X3 : TC_F16PS;
+    using Cfg = TcCfg<MODE, BN, CTA2>;
+    auto kern = gemm_tc_kernel<MODE, BN, TC_EPI_ATOMIC_ADD, 0, CTA2, 1>;
+    const float* inv_scale = scale + 1;
     { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)Cfg::SMEM_BYTES, "cudaFuncSetAttribute(gemm_tc_kernel MN)"); if (rc_attr) return rc_attr; }
     CUtensorMap tmA, tmAl, tmWh, tmWl;
-    int rc = make_map(&tmA, z_hi, (uint64_t)d.n, (uint64_t)w.rows_z, (uint64_t)w.clips, (uint64_t)d.n, (uint64_t)w.rows_z * d.n, 64, 32, "dZ_hi", true, true);
-    if (rc) return rc;
-    rc = make_map(&tmAl, z_lo, (uint64_t)d.n, (uint64_t)w.rows_z, (uint64_t)w.clips, (uint64_t)d.n, (uint64_t)w.rows_z * d.n, 64, 32, "dZ_lo", true, true);
-    if (rc) return rc;
+    int rc;
+    if (ZSPLIT) {       // fp32 dz as it lies in memory: (n, rows, clips) with the caller's strides, boxes of 32 channels x 32 rows
+        const uint64_t zbs = w.clips > 1 ? (uint64_t)d.dz_batch_stride : (uint64_t)w.rows_z * (uint64_t)d.dz_row_stride;
+        rc = make_map(&tmA, d.dz, (uint64_t)d.n, (uint64_t)w.rows_z, (uint64_t)w.clips, (uint64_t)d.dz_row_stride, zbs, 32, 32, "dZ");
+        if (rc) return rc;
+        tmAl = tmA;
+    } else {
+        rc = make_map(&tmA, z_hi, (uint64_t)d.n, (uint64_t)w.rows_z, (uint64_t)w.clips, (uint64_t)d.n, (uint64_t)w.rows_z * d.n, 64, 32, "dZ_hi", true, true);
+        if (rc) return rc;
+        rc = make_map(&tmAl, z_lo, (uint64_t)d.n, (uint64_t)w.rows_z, (uint64_t)w.clips, (uint64_t)d.n, (uint64_t)w.rows_z * d.n, 64, 32, "dZ_lo", true, true);
+        if (rc) return rc;
+    }
     rc = make_map(&tmWh, a_hi, (uint64_t)d.k, (uint64_t)w.rows_a, (uint64_t)w.clips, (uint64_t)d.k, (uint64_t)w.rows_a * d.k, 64, 32, "A_hi", true, true);
     if (rc) return rc;
     rc = make_map(&tmWl, a_lo, (uint64_t)d.k, (uint64_t)w.rows_a, (uint64_t)w.clips, (uint64_t)d.k, (uint64_t)w.rows_a * d.k, 64, 32, "A_lo", true, true);
@@ -1156,7 +1210,7 @@ static int launch_wgrad_mn(const __half* z_hi, const __half* z_lo, const __half*
     CUM_REQUIRE(batch * tiles < (1ll << 31), "wgrad: too many tiles");
     p.batch = (int)batch;
     p.bias = nullptr; p.c = d.dw + (size_t)tap * d.n * d.ldw; p.c_bs = 0; p.c_rs = d.ldw;
-    p.addend = nullptr; p.acc_scale = 1.0f; p.acc_scale_ptr = inv_scale; p.a_scale_ptr = nullptr; p.skip_wlo = 0;
+    p.addend = nullptr; p.acc_scale = 1.0f; p.acc_scale_ptr = inv_scale; p.a_scale_ptr = ZSPLIT ? scale : nullptr; p.skip_wlo = 0;
     const long long total = batch * tiles;
     if (CTA2) {
         const int pairs = sm_count() / 2;
@@ -1207,17 +1261,28 @@ static int wgrad_mn_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
         scale = own_scale;
     }
     const int grid = 8 * sm_count();
-    split_planes_kernel<<<grid, 256, 0, st>>>(d.dz, z_bs, d.dz_row_stride, zb, (int)w.rows_z, d.n / 4, z_hi, z_lo, scale);
-    CUM_LAUNCH_CHECK("split_planes_kernel(dz)");
+    // the gradient is split by the GEMM's own splitter warps (read once, as fp32); CUM_WGRAD_ZSPLIT=0: a pre-pass writes fp16 planes
+    static const bool zsplit = !(getenv("CUM_WGRAD_ZSPLIT") && getenv("CUM_WGRAD_ZSPLIT")[0] == '0');
+    if (!zsplit) {
+        split_planes_kernel<<<grid, 256, 0, st>>>(d.dz, z_bs, d.dz_row_stride, zb, (int)w.rows_z, d.n / 4, z_hi, z_lo, scale);
+        CUM_LAUNCH_CHECK("split_planes_kernel(dz)");
+    }
     split_planes_kernel<<<grid, 256, 0, st>>>(d.a, a_bs, d.a_row_stride, zb, (int)w.rows_a, d.k / 4, a_hi, a_lo, nullptr);
     CUM_LAUNCH_CHECK("split_planes_kernel(a)");
     const bool pair = cta2_policy() >= 0 && d.n > TC_BM && (sm_count() & 1) == 0;
     for (int s = 0; s < d.taps; ++s) {
         int rc;
-        if (d.k <= 128) rc = pair ? launch_wgrad_mn<128, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale + 1, st)
-                                  : launch_wgrad_mn<128, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale + 1, st);
-        else rc = pair ? launch_wgrad_mn<256, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale + 1, st)
-                       : launch_wgrad_mn<256, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale + 1, st);
+        if (zsplit) {
+            if (d.k <= 128) rc = pair ? launch_wgrad_mn<128, true, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)
+                                      : launch_wgrad_mn<128, false, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st);
+            else rc = pair ? launch_wgrad_mn<256, true, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)
+                           : launch_wgrad_mn<256, false, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st);
+        } else {
+            if (d.k <= 128) rc = pair ? launch_wgrad_mn<128, true, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)
+                                      : launch_wgrad_mn<128, false, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st);
+            else rc = pair ? launch_wgrad_mn<256, true, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)
+                           : launch_wgrad_mn<256, false, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st);
+        }
         if (rc) return rc;
     }
     return CUM_OK;
