@@ -236,10 +236,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             ld(smem_base + alo_off(s) + i * 4096, &tmAl, m0 + 64 * i, r);
                         }
                     }
+                    if constexpr (MNM == 2) {   // raw fp32 activation tile: slabs of 32 channels x 32 rows, split in place by the splitter warps
 #pragma unroll
-                    for (int i = 0; i < Cfg::W_ROWS / 64; ++i) {
-                        ld(smem_base + w_off(s) + i * 4096, &tmWh, wn + 64 * i, r + shift);
-                        if (load_lo) ld(smem_base + wlo_off(s) + i * 4096, &tmWl, wn + 64 * i, r + shift);
+                        for (int i = 0; i < Cfg::W_ROWS / 32; ++i) ld(smem_base + w_off(s) + i * 4096, &tmWh, wn + 32 * i, r + shift);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < Cfg::W_ROWS / 64; ++i) {
+                            ld(smem_base + w_off(s) + i * 4096, &tmWh, wn + 64 * i, r + shift);
+                            if (load_lo) ld(smem_base + wlo_off(s) + i * 4096, &tmWl, wn + 64 * i, r + shift);
+                        }
                     }
                 } else if (CTA2 && !SPL) {
                     // no splitter in between: the leader's MMA thread waits for the bytes of BOTH CTAs on its own barrier
@@ -284,9 +289,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (CTA2) mbar_wait_cluster(SPL ? split_bar(s) : full_bar(s), ph); else mbar_wait(SPL ? split_bar(s) : full_bar(s), ph);
                 tc_fence_after();
                 const uint64_t adesc = MNM ? umma_desc_mn_sw128(smem_base + ahi_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + ahi_off(s)) : umma_desc_sw128(smem_base + ahi_off(s));
-                const uint64_t bdesc = MNM ? umma_desc_mn_sw128(smem_base + w_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + w_off(s)) : umma_desc_sw128(smem_base + w_off(s));
+                // MNM == 2: the in-kernel split leaves [hi | lo] per 64-channel group (8 KB): slabs of one half are 8 KB apart
+                const uint64_t bdesc = MNM == 2 ? umma_desc_mn_sw128(smem_base + w_off(s), 8192u) : MNM ? umma_desc_mn_sw128(smem_base + w_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + w_off(s)) : umma_desc_sw128(smem_base + w_off(s));
                 const uint64_t alo = MNM ? umma_desc_mn_sw128(smem_base + alo_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + alo_off(s)) : umma_desc_sw128(smem_base + alo_off(s));
-                const uint64_t blo = MNM ? umma_desc_mn_sw128(smem_base + wlo_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + wlo_off(s)) : umma_desc_sw128(smem_base + wlo_off(s));
+                const uint64_t blo = MNM == 2 ? umma_desc_mn_sw128(smem_base + w_off(s) + 4096u, 8192u) : MNM ? umma_desc_mn_sw128(smem_base + wlo_off(s), 4096u) : BF ? umma_desc_sw64(smem_base + wlo_off(s)) : umma_desc_sw128(smem_base + wlo_off(s));
 #pragma unroll
                 for (int kk = 0; kk < Cfg::BK / Cfg::UMMA_K; ++kk) {
                     // K-major: 32 bytes per k-step in both element types; MN-major: 16 rows of 128 bytes = two 1024-byte row groups
@@ -598,6 +604,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t off = (uint32_t)(qg >> 3) * 4096u + (uint32_t)r * 128u + (uint32_t)(((qg & 7) ^ (r & 7)) << 4);
                         *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
                         *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
+                    if constexpr (MNM == 2) {
+                        // the activation tile, 64 channels (two raw slabs = 8 KB) at a time -> [hi slab | lo slab] in the same 8 KB;
+                        // 256 items of 8 channels per group, two per thread, reads / barrier / writes
+                        uint8_t* wb = smem_gen + w_off(s);
+#pragma unroll 1
+                        for (int g = 0; g < Cfg::W_ROWS / 64; ++g) {
+                            float4 wa[2], wc[2];
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int i = t + 128 * j;
+                                const int r = i >> 3, q = i & 7;
+                                const uint8_t* src = wb + (2 * g + (q >> 2)) * 4096 + r * 128;
+                                wa[j] = *reinterpret_cast<const float4*>(src + (((2 * (q & 3)) ^ (r & 7)) << 4));
+                                wc[j] = *reinterpret_cast<const float4*>(src + (((2 * (q & 3) + 1) ^ (r & 7)) << 4));
+                            }
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int i = t + 128 * j;
+                                const int r = i >> 3, q = i & 7;
+                                const float f[8] = {wa[j].x, wa[j].y, wa[j].z, wa[j].w, wc[j].x, wc[j].y, wc[j].z, wc[j].w};
+                                uint32_t h[4], l[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    h[e] = cvt_f16x2_sat(f[2 * e], f[2 * e + 1]);
+                                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
+                                    l[e] = cvt_f16x2_sat(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+                                }
+                                uint8_t* dst = wb + g * 8192 + r * 128 + ((q ^ (r & 7)) << 4);
+                                *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+                                *reinterpret_cast<uint4*>(dst + 4096) = make_uint4(l[0], l[1], l[2], l[3]);
+                            }
+                        }
                     }
                 } else if (BF) {
                     // fp32 tile (128 x 32, 128B-swizzled rows) -> bf16 hi / lo tiles (128 x 32, 64B-swizzled rows)
@@ -1167,12 +1207,13 @@ static WgradMnPlan plan_wgrad_mn(const cum_wgrad_desc& d) {
 
 // ZSPLIT: the gradient operand is read as fp32 straight from dz and split by the kernel's splitter warps (scaled by *scale);
 // otherwise z_hi / z_lo are pre-split fp16 planes
-template <int BN, bool CTA2, bool ZSPLIT>
+// ZSPLIT == 2: the activation operand as well (fp32 straight from `a`, no planes, no workspace beyond the scale)
+template <int BN, bool CTA2, int ZSPLIT>
 static int launch_wgrad_mn(const __half* z_hi, const __half* z_lo, const __half* a_hi, const __half* a_lo, const WgradMnPlan& w,
                            const cum_wgrad_desc& d, int tap, const float* scale, cudaStream_t st) {
     constexpr int MODE = ZSPLIT ? TC_F16X3 : TC_F16PS;
     using Cfg = TcCfg<MODE, BN, CTA2>;
-    auto kern = gemm_tc_kernel<MODE, BN, TC_EPI_ATOMIC_ADD, 0, CTA2, 1>;
+    auto kern = gemm_tc_kernel<MODE, BN, TC_EPI_ATOMIC_ADD, 0, CTA2, (ZSPLIT == 2 ? 2 : 1)>;
     const float* inv_scale = scale + 1;
     { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)Cfg::SMEM_BYTES, "cudaFuncSetAttribute(gemm_tc_kernel MN)"); if (rc_attr) return rc_attr; }
     CUtensorMap tmA, tmAl, tmWh, tmWl;
@@ -1188,10 +1229,17 @@ static int launch_wgrad_mn(const __half* z_hi, const __half* z_lo, const __half*
         rc = make_map(&tmAl, z_lo, (uint64_t)d.n, (uint64_t)w.rows_z, (uint64_t)w.clips, (uint64_t)d.n, (uint64_t)w.rows_z * d.n, 64, 32, "dZ_lo", true, true);
         if (rc) return rc;
     }
-    rc = make_map(&tmWh, a_hi, (uint64_t)d.k, (uint64_t)w.rows_a, (uint64_t)w.clips, (uint64_t)d.k, (uint64_t)w.rows_a * d.k, 64, 32, "A_hi", true, true);
-    if (rc) return rc;
-    rc = make_map(&tmWl, a_lo, (uint64_t)d.k, (uint64_t)w.rows_a, (uint64_t)w.clips, (uint64_t)d.k, (uint64_t)w.rows_a * d.k, 64, 32, "A_lo", true, true);
-    if (rc) return rc;
+    if (ZSPLIT == 2) {
+        const uint64_t abs_ = w.clips > 1 ? (uint64_t)d.a_batch_stride : (uint64_t)w.rows_a * (uint64_t)d.a_row_stride;
+        rc = make_map(&tmWh, d.a, (uint64_t)d.k, (uint64_t)w.rows_a, (uint64_t)w.clips, (uint64_t)d.a_row_stride, abs_, 32, 32, "A");
+        if (rc) return rc;
+        tmWl = tmWh;
+    } else {
+        rc = make_map(&tmWh, a_hi, (uint64_t)d.k, (uint64_t)w.rows_a, (uint64_t)w.clips, (uint64_t)d.k, (uint64_t)w.rows_a * d.k, 64, 32, "A_hi", true, true);
+        if (rc) return rc;
+        rc = make_map(&tmWl, a_lo, (uint64_t)d.k, (uint64_t)w.rows_a, (uint64_t)w.clips, (uint64_t)d.k, (uint64_t)w.rows_a * d.k, 64, 32, "A_lo", true, true);
+        if (rc) return rc;
+    }
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.m = d.n; p.n = d.k; p.k = 32; p.taps = 1; p.shift0 = d.tap_shift[tap]; p.shift1 = 0; p.epi = CUM_EPI_NONE;
@@ -1262,27 +1310,28 @@ static int wgrad_mn_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
     }
     const int grid = 8 * sm_count();
     // the gradient is split by the GEMM's own splitter warps (read once, as fp32); CUM_WGRAD_ZSPLIT=0: a pre-pass writes fp16 planes
-    static const bool zsplit = !(getenv("CUM_WGRAD_ZSPLIT") && getenv("CUM_WGRAD_ZSPLIT")[0] == '0');
+    // CUM_WGRAD_ZSPLIT: 1 (default) the gradient is split in the kernel, the activation planes by an elementwise pre-pass; 2 both
+    // operands in the kernel (no pre-pass at all, but the splitter warps then sit on the critical path of every stage: measured
+    // 13.9-14.3 vs 13.4-13.7 ms); 0 both by pre-passes
+    static const int zsplit = getenv("CUM_WGRAD_ZSPLIT") ? atoi(getenv("CUM_WGRAD_ZSPLIT")) : 1;
     if (!zsplit) {
         split_planes_kernel<<<grid, 256, 0, st>>>(d.dz, z_bs, d.dz_row_stride, zb, (int)w.rows_z, d.n / 4, z_hi, z_lo, scale);
         CUM_LAUNCH_CHECK("split_planes_kernel(dz)");
     }
-    split_planes_kernel<<<grid, 256, 0, st>>>(d.a, a_bs, d.a_row_stride, zb, (int)w.rows_a, d.k / 4, a_hi, a_lo, nullptr);
-    CUM_LAUNCH_CHECK("split_planes_kernel(a)");
+    if (zsplit != 2) {
+        split_planes_kernel<<<grid, 256, 0, st>>>(d.a, a_bs, d.a_row_stride, zb, (int)w.rows_a, d.k / 4, a_hi, a_lo, nullptr);
+        CUM_LAUNCH_CHECK("split_planes_kernel(a)");
+    }
     const bool pair = cta2_policy() >= 0 && d.n > TC_BM && (sm_count() & 1) == 0;
     for (int s = 0; s < d.taps; ++s) {
         int rc;
-        if (zsplit) {
-            if (d.k <= 128) rc = pair ? launch_wgrad_mn<128, true, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)
-                                      : launch_wgrad_mn<128, false, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st);
-            else rc = pair ? launch_wgrad_mn<256, true, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)
-                           : launch_wgrad_mn<256, false, true>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st);
-        } else {
-            if (d.k <= 128) rc = pair ? launch_wgrad_mn<128, true, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)
-                                      : launch_wgrad_mn<128, false, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st);
-            else rc = pair ? launch_wgrad_mn<256, true, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)
-                           : launch_wgrad_mn<256, false, false>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st);
-        }
+#define WG_LAUNCH(Z)                                                                                                        \
+        (d.k <= 128 ? (pair ? launch_wgrad_mn<128, true, Z>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)                           \
+                            : launch_wgrad_mn<128, false, Z>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st))                         \
+                    : (pair ? launch_wgrad_mn<256, true, Z>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)                           \
+                            : launch_wgrad_mn<256, false, Z>(z_hi, z_lo, a_hi, a_lo, w, d, s, scale, st)))
+        rc = zsplit == 2 ? WG_LAUNCH(2) : zsplit == 1 ? WG_LAUNCH(1) : WG_LAUNCH(0);
+#undef WG_LAUNCH
         if (rc) return rc;
     }
     return CUM_OK;
