@@ -30,7 +30,7 @@ class GemmDesc(C.Structure):
                 ("m", C.c_int), ("n", C.c_int), ("batch", C.c_int), ("epilogue", C.c_int),
                 ("addend", C.c_void_p), ("add_batch_stride", C.c_longlong), ("add_row_stride", C.c_longlong),
                 ("math", C.c_int), ("w_lo", C.c_void_p), ("acc_scale", C.c_float), ("out_bf16", C.c_int), ("w_lo_is_zero", C.c_int),
-                ("a_lo", C.c_void_p), ("c_lo", C.c_void_p), ("addend_lo", C.c_void_p), ("a_scale_dev", C.c_void_p), ("aux", C.c_void_p), ("aux_batch_stride", C.c_longlong), ("aux_row_stride", C.c_longlong),
+                ("a_lo", C.c_void_p), ("c_lo", C.c_void_p), ("addend_lo", C.c_void_p), ("a_scale_dev", C.c_void_p), ("addend_is_mask", C.c_int), ("aux", C.c_void_p), ("aux_batch_stride", C.c_longlong), ("aux_row_stride", C.c_longlong),
                 ("cta_pair", C.c_int)]
 
 
@@ -115,7 +115,7 @@ EXPORTS = {
     "cum_glu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "cum_glu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "cum_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
-    "cum_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "cum_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "cum_add_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "cum_gemm_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
     "cum_grad_scale_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

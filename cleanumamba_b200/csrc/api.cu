@@ -237,8 +237,8 @@ int cum_relu_bwd(const float* y, const float* dy, float* dz, float* dbias, long 
                  cum_stream_t stream) {
     return rowblock_bwd(1, y, dy, dz, dbias, rows, cols, (cudaStream_t)stream, dz_scale4);
 }
-int cum_colsum(const float* d, float* dbias, long long rows, int cols, cum_stream_t stream) {
-    return rowblock_bwd(2, nullptr, d, nullptr, dbias, rows, cols, (cudaStream_t)stream);
+int cum_colsum(const float* d, float* dbias, long long rows, int cols, float* d_scale4, cum_stream_t stream) {
+    return rowblock_bwd(2, nullptr, d, nullptr, dbias, rows, cols, (cudaStream_t)stream, d_scale4);
 }
 int cum_add_fwd(const float* a, const float* b, float* out, long long count, cum_stream_t stream) {
     return add_fwd(a, b, out, count, (cudaStream_t)stream);

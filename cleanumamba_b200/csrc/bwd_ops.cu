@@ -47,6 +47,21 @@ int glu_fwd(const float* z, const float* addend, float* out, long long rows, int
 // ---------------------------------------------------------------------------------------------------------
 constexpr int RB_ROWS = 128;      // minimum rows per CTA; large problems use more so the column atomics stay ~1 per SM wave
 
+// Column partial sums of the `slots` row slots of a CTA meet in shared memory (red: 256 float4) so that ONE thread per column group
+// issues the atomics.  Must be called by every thread of the CTA; returns true for the threads (slot 0) that hold the CTA total.
+__device__ __forceinline__ bool cta_slot_reduce(float4& acc, float4* red, int slots, int gpr, int tg, int ts) {
+    if (slots <= 1) return ts == 0;
+    __syncthreads();                 // a previous use of `red` is over
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (ts != 0) return false;
+    for (int sl = 1; sl < slots; ++sl) {
+        const float4 o = red[sl * gpr + tg];
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    return true;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) rowblock_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dout,
                                                             float* __restrict__ dz, float* __restrict__ dbias,
@@ -58,34 +73,54 @@ __global__ void __launch_bounds__(256) rowblock_bwd_kernel(const float* __restri
     const int tg = threadIdx.x % gpr, ts = threadIdx.x / gpr;
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
     const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
-    if (ts >= slots) return;
+    // slots > 1 (fewer than 129 column groups): every column is summed by `slots` threads of the CTA.  Their partial sums meet in
+    // shared memory so that ONE atomic per column and CTA reaches the bias gradient -- with 16 slots x ~1200 CTAs the same 64
+    // addresses took 19 k serialised atomics each, a third of the kernel's time on the 64-channel levels.
+    __shared__ float4 red[256];
+    const bool active = ts < slots;
     float amax = 0.f;
     for (int g = tg; g < groups; g += gpr) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long r = r0 + ts; r < r1; r += slots) {
-            float4 d;
+        if (active) {
+        auto grad = [&](const float4& zv, const float4& dv) {
             if (MODE == 0) {
-                const float4 zv = reinterpret_cast<const float4*>(z + r * cols)[g];
-                const float2 dv = reinterpret_cast<const float2*>(dout + r * (cols >> 1))[g];
                 const float s0 = sigmoidf_(zv.y), s1 = sigmoidf_(zv.w);
-                d = make_float4(dv.x * s0, dv.x * zv.x * s0 * (1.f - s0), dv.y * s1, dv.y * zv.z * s1 * (1.f - s1));
+                return make_float4(dv.x * s0, dv.x * zv.x * s0 * (1.f - s0), dv.y * s1, dv.y * zv.z * s1 * (1.f - s1));
             } else if (MODE == 1) {
-                const float4 yv = reinterpret_cast<const float4*>(z + r * cols)[g];
-                const float4 dv = reinterpret_cast<const float4*>(dout + r * cols)[g];
-                d = make_float4(yv.x > 0.f ? dv.x : 0.f, yv.y > 0.f ? dv.y : 0.f, yv.z > 0.f ? dv.z : 0.f, yv.w > 0.f ? dv.w : 0.f);
-            } else {
-                d = reinterpret_cast<const float4*>(dout + r * cols)[g];
+                return make_float4(zv.x > 0.f ? dv.x : 0.f, zv.y > 0.f ? dv.y : 0.f, zv.z > 0.f ? dv.z : 0.f, zv.w > 0.f ? dv.w : 0.f);
             }
+            return dv;
+        };
+        auto load_z = [&](long long r) { return MODE == 2 ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(z + r * cols)[g]; };
+        auto load_d = [&](long long r) {
+            if (MODE == 0) { const float2 d2 = reinterpret_cast<const float2*>(dout + r * (cols >> 1))[g]; return make_float4(d2.x, d2.y, 0.f, 0.f); }
+            return reinterpret_cast<const float4*>(dout + r * cols)[g];
+        };
+        auto finish = [&](long long r, const float4& d) {
             if (MODE != 2) reinterpret_cast<float4*>(dz + r * cols)[g] = d;
             acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
+        };
+        // four rows per iteration, every load issued before the first use: the kernel is a pure stream (48-80 bytes per thread in
+        // flight instead of 16-24 -- one row at a time ran at 1.4 (colsum) to 3.5 TB/s (GLU backward))
+        constexpr int UNR = 4;
+        long long r = r0 + ts;
+        for (; r + (UNR - 1) * slots < r1; r += UNR * slots) {
+            float4 zv[UNR], dv[UNR];
+#pragma unroll
+            for (int i = 0; i < UNR; ++i) { zv[i] = load_z(r + i * slots); dv[i] = load_d(r + i * slots); }
+#pragma unroll
+            for (int i = 0; i < UNR; ++i) finish(r + i * slots, grad(zv[i], dv[i]));
         }
-        if (dbias) {
+        for (; r < r1; r += slots) finish(r, grad(load_z(r), load_d(r)));
+        }
+        if (!cta_slot_reduce(acc, red, slots, gpr, tg, ts)) continue;      // uniform call; the g loop has a single iteration when slots > 1
+        if (dbias && active) {
             atomicAdd(dbias + 4 * g + 0, acc.x); atomicAdd(dbias + 4 * g + 1, acc.y);
             atomicAdd(dbias + 4 * g + 2, acc.z); atomicAdd(dbias + 4 * g + 3, acc.w);
         }
     }
-    if (amax_bits) {            // one atomic per warp (non-negative floats order like their bits)
+    if (amax_bits && active) {            // one atomic per warp (non-negative floats order like their bits)
         const unsigned act = __activemask();
         const unsigned m = __reduce_max_sync(act, __float_as_uint(amax));
         if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1) && m != 0u) atomicMax(amax_bits, m);
@@ -480,14 +515,16 @@ __global__ void __launch_bounds__(256) conv_in_bwd_kernel(const float* __restric
     const int gpr = groups < 256 ? groups : 256;
     const int slots = 256 / gpr;
     const int tg = threadIdx.x % gpr, ts = threadIdx.x / gpr;
-    if (ts >= slots) return;
+    __shared__ float4 red[256];
+    const bool active = ts < slots;
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * rows_per_cta, t1 = min(rows_out, t0 + rows_per_cta);
     const float* xb = x + (long long)b * x_stride;
-    for (int g = tg; g < groups; g += gpr) {
+    for (int g = tg; g < groups; g += gpr) {          // (a single iteration whenever slots > 1)
         float4 acc[CI_MAXK], accb = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < CI_MAXK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active)
         for (int t = t0 + ts; t < t1; t += slots) {
             const long long off = ((long long)b * rows_out + t) * c_pad;
             const float4 yv = reinterpret_cast<const float4*>(y + off)[g];
@@ -504,15 +541,20 @@ __global__ void __launch_bounds__(256) conv_in_bwd_kernel(const float* __restric
                 }
             }
         }
+        // one atomic per column and CTA (the row slots' partial sums meet in shared memory first)
 #pragma unroll
         for (int k = 0; k < CI_MAXK; ++k) {
-            if (k < kernel) {
-                float* p = dw + (long long)k * c_pad + 4 * g;
-                atomicAdd(p + 0, acc[k].x); atomicAdd(p + 1, acc[k].y); atomicAdd(p + 2, acc[k].z); atomicAdd(p + 3, acc[k].w);
+            if (k < kernel) {       // uniform
+                if (cta_slot_reduce(acc[k], red, slots, gpr, tg, ts) && active) {
+                    float* p = dw + (long long)k * c_pad + 4 * g;
+                    atomicAdd(p + 0, acc[k].x); atomicAdd(p + 1, acc[k].y); atomicAdd(p + 2, acc[k].z); atomicAdd(p + 3, acc[k].w);
+                }
             }
         }
-        atomicAdd(db + 4 * g + 0, accb.x); atomicAdd(db + 4 * g + 1, accb.y);
-        atomicAdd(db + 4 * g + 2, accb.z); atomicAdd(db + 4 * g + 3, accb.w);
+        if (cta_slot_reduce(accb, red, slots, gpr, tg, ts) && active) {
+            atomicAdd(db + 4 * g + 0, accb.x); atomicAdd(db + 4 * g + 1, accb.y);
+            atomicAdd(db + 4 * g + 2, accb.z); atomicAdd(db + 4 * g + 3, accb.w);
+        }
     }
 }
 
@@ -589,12 +631,22 @@ __global__ void __launch_bounds__(256) convt_out_bwd_kernel(const float* __restr
             }
         }
     }
+    // CTA totals first (shared memory), then one atomic per address and CTA
+    __shared__ float4 red[256];
+    __shared__ float esum_w[8];
     esum = warp_sum(esum);
-    if ((threadIdx.x & 31) == 0 && dbias) atomicAdd(dbias, esum);
-    if (ts < slots && tg < groups) {
+    if ((threadIdx.x & 31) == 0) esum_w[threadIdx.x >> 5] = esum;
+    __syncthreads();
+    if (threadIdx.x == 0 && dbias) {
+        float e = 0.f;
+        for (int i = 0; i < 8; ++i) e += esum_w[i];
+        atomicAdd(dbias, e);
+    }
+    const bool active = ts < slots && tg < groups;
 #pragma unroll
-        for (int k = 0; k < CT_MAXK; ++k) {
-            if (k < kernel) {
+    for (int k = 0; k < CT_MAXK; ++k) {
+        if (k < kernel) {           // uniform
+            if (cta_slot_reduce(acc[k], red, slots, gpr, tg, ts) && active) {
                 float* p = dw + (long long)k * c_pad + 4 * tg;
                 atomicAdd(p + 0, acc[k].x); atomicAdd(p + 1, acc[k].y); atomicAdd(p + 2, acc[k].z); atomicAdd(p + 3, acc[k].w);
             }

@@ -96,6 +96,7 @@ struct TcParams {
     int mn_splits;            // MN-major wgrad: splits per clip ("batch" = clip * mn_splits + split, k_blocks K-blocks of 32 rows per split)
     const float* acc_scale_ptr;   // optional device-side factor multiplied into acc_scale (1 / gradient scale computed on the device)
     const float* a_scale_ptr;     // optional device-side factor applied to A by the fp16 operand splitter (gradient scale)
+    int add_mask;             // the addend is a ReLU MASK: out = addend > 0 ? value : 0 (ReLU backward in the data-gradient epilogue)
     float* aux; long long aux_bs, aux_rs;   // optional second fp32 output (training): the value BEFORE the gate (GLU epilogues: the
                                             // (rows, n) pre-activation) or before the addend (other epilogues: same shape as c)
     void* c_lo;               // OUTF == 2: low-half plane of the output (c is the high-half plane), fp16
@@ -496,7 +497,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         o[k] = make_float2(tc_act<EPI>(p.epi, x0), tc_act<EPI>(p.epi, x1));
                                         if (OUTF == 0 && auxb && rok[h][rh] && kok[k])       // training: the value before the skip add (its sign is the ReLU mask)
                                             *reinterpret_cast<float2*>(auxb + (long long)(row0 + (2 * h + rh) * 8) * p.aux_rs + (n0 + c0 + 8 * k + 2 * tq)) = o[k];
-                                        if (has_add) { o[k].x += ad[h][rh][k].x; o[k].y += ad[h][rh][k].y; }
+                                        if (has_add) {
+                                            if (p.add_mask) { o[k].x = ad[h][rh][k].x > 0.f ? o[k].x : 0.f; o[k].y = ad[h][rh][k].y > 0.f ? o[k].y : 0.f; }
+                                            else { o[k].x += ad[h][rh][k].x; o[k].y += ad[h][rh][k].y; }
+                                        }
                                     }
                                     const float2 snd = odd ? o[0] : o[1];
                                     const float gx = __shfl_xor_sync(0xffffffffu, snd.x, 1), gy = __shfl_xor_sync(0xffffffffu, snd.y, 1);
@@ -904,6 +908,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.w_k_batch_stride = g_wgrad_kbs; p.w_k_off = g_wgrad_koff;
     p.mn_splits = 0;
     p.aux = (OUTF == 0) ? d.aux : nullptr; p.aux_bs = d.aux_batch_stride; p.aux_rs = d.aux_row_stride;
+    p.add_mask = (OUTF == 0 && d.addend_is_mask) ? 1 : 0;
     p.a_scale_ptr = (MODE == TC_F16X3) ? d.a_scale_dev : nullptr;
     p.acc_scale_ptr = (MODE == TC_F16X3 && d.a_scale_dev) ? d.a_scale_dev + 1 : nullptr;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
@@ -1381,6 +1386,8 @@ int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.a_row_stride >= d.k || d.a_rows == 1, "gemm_tc: a_row_stride < k");
     CUM_REQUIRE(!d.a_scale_dev || (d.math == CUM_MATH_F16X3 && !d.a_lo), "gemm_tc: a_scale_dev needs CUM_MATH_F16X3 with fp32 activations");
+    CUM_REQUIRE(!d.addend_is_mask || (d.addend && !d.out_bf16 && !d.c_lo && !d.addend_lo && (d.epilogue == CUM_EPI_NONE || d.epilogue == CUM_EPI_RELU)),
+                "gemm_tc: addend_is_mask needs an fp32 addend / output and a NONE / RELU epilogue");
     CUM_REQUIRE(!d.aux || (!d.out_bf16 && !d.c_lo && aligned16(d.aux) && d.aux_row_stride % 2 == 0 && d.aux_batch_stride % 2 == 0 &&
                            (d.epilogue == CUM_EPI_NONE || d.epilogue == CUM_EPI_RELU || epi_is_glu(d.epilogue))),
                 "gemm_tc: aux (second output) needs an fp32 output, even strides and a NONE / RELU / GLU epilogue");

@@ -401,7 +401,8 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
             for (int i = 0; i < NS; ++i) {
                 const int n = slice * NS + i;
                 if (c_ok && n < p.n_state)
-                    p.h_ckpt[(((long long)b * nchunks + chunk) * p.d + c) * p.n_state + n] = (i & 1) ? h2[i >> 1].y : h2[i >> 1].x;
+                    // (batch, chunk, state, channel): the 32 lanes of a warp are 32 consecutive channels -> one 128-byte run per store
+                    p.h_ckpt[(((long long)b * nchunks + chunk) * p.n_state + n) * p.d + c] = (i & 1) ? h2[i >> 1].y : h2[i >> 1].x;
             }
         }
         cp_async_wait<0>();

@@ -57,12 +57,16 @@ __device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane) {
 template <int SL>
 struct ScanBwdSmem {
     static constexpr int NP = 4 * SL;
-    float u[SB_TC][SB_CH], dl[SB_TC][SB_CH], draw[SB_TC][SB_CH], z[SB_TC][SB_CH], dout[SB_TC][SB_CH], dy[SB_TC][SB_CH];
+    float u[SB_TC][SB_CH], dl[SB_TC][SB_CH], duv[SB_TC][SB_CH], draw[SB_TC][SB_CH], z[SB_TC][SB_CH], dout[SB_TC][SB_CH], dy[SB_TC][SB_CH];
     float Bm[SB_TC][NP], Cm[SB_TC][NP];
     float part0[SL][SB_TC][SB_CH];      // y partials, then sum_n g B partials
     float part1[SL][SB_TC][SB_CH];      // sum_n g h_prev A e partials
 };
 
+// The kernel is instruction-issue-bound (ncu round 2: 0.56 IPC per scheduler, MUFU 20 %, DRAM 5 %; 47 SASS instructions per state
+// update).  Every per-state operation therefore runs as PACKED 2-wide fp32 math (FMUL2 / FFMA2 of sm_100: one issue slot per state
+// PAIR), dl*u is discretised once per (t, channel) into shared memory, and the per-step address arithmetic of the dB / dC atomics is
+// hoisted (each lane's reduction role -- which of the warp's 8 totals it ends up holding -- is fixed for the whole kernel).
 template <int SL>
 __global__ void __launch_bounds__(32 * SL) selective_scan_bwd_kernel(const cum_scan_bwd_desc p) {
     constexpr int NP = 4 * SL;
@@ -77,23 +81,41 @@ __global__ void __launch_bounds__(32 * SL) selective_scan_bwd_kernel(const cum_s
     const bool c_ok = c < f.d;
     const int nchunks = (f.len + SB_TC - 1) / SB_TC;
 
-    float a2[4], Aln[4], G[4], dA[4];
+    float2 a2p[2], Alnp[2], G2[2], dA2[2];      // state pairs (4*slice + {0,1}) and (4*slice + {2,3})
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = slice * 4 + i;
-        const bool ok = c_ok && n < f.n_state;
-        a2[i] = ok ? f.a2[(long long)c * f.n_state + n] : 0.f;
-        Aln[i] = a2[i] * LN2F;           // A = a2 / log2(e)
-        G[i] = 0.f;
-        dA[i] = 0.f;
+    for (int j = 0; j < 2; ++j) {
+        float av[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int n = slice * 4 + 2 * j + e;
+            av[e] = (c_ok && n < f.n_state) ? f.a2[(long long)c * f.n_state + n] : 0.f;
+        }
+        a2p[j] = make_float2(av[0], av[1]);
+        Alnp[j] = make_float2(av[0] * LN2F, av[1] * LN2F);           // A = a2 / log2(e)
+        G2[j] = make_float2(0.f, 0.f);
+        dA2[j] = make_float2(0.f, 0.f);
     }
     float accD = 0.f, accBias = 0.f;     // per (tid & 31) channel partials of the combine threads
     const float Dv = (f.Dskip && c_ok) ? f.Dskip[c] : 0.f;
+
+    // d-reductions of dB / dC: after warp_sum8 lane L holds the warp total of value ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1)
+    // (values 0..3 = dC of this slice's 4 states, 4..7 = dB); one lane of every four adds it to global memory
+    const int ridx = ((ch >> 4) & 1) * 4 + ((ch >> 3) & 1) * 2 + ((ch >> 2) & 1);
+    const int rn = slice * 4 + (ridx & 3);
+    const bool red_lane = (ch & 3) == 0 && rn < f.n_state;
+    float* const red_base = (ridx < 4 ? p.dC + (long long)b * p.dC_bs : p.dB + (long long)b * p.dB_bs) + rn;
+    const long long red_rs = ridx < 4 ? p.dC_rs : p.dB_rs;
 
     // register prefetch buffers: every thread owns a fixed share of each tile
     constexpr int PF_E = (SB_TC * SB_CH + NT - 1) / NT;      // u / delta / z / dout elements per thread
     constexpr int PF_N = (SB_TC * NP + NT - 1) / NT;         // B / C elements per thread
     float pf_u[PF_E], pf_d[PF_E], pf_z[PF_E], pf_o[PF_E], pf_B[PF_N], pf_C[PF_N];
+    const float* const ub = f.u + (long long)b * f.u_bs;
+    const float* const db = f.delta + (long long)b * f.dl_bs;
+    const float* const zb = f.z ? f.z + (long long)b * f.z_bs : nullptr;
+    const float* const ob = p.dout + (long long)b * p.dout_bs;
+    const float* const Bb = f.Bm + (long long)b * f.B_bs;
+    const float* const Cb = f.Cm + (long long)b * f.C_bs;
     auto prefetch = [&](int chunk) {
         const int t0 = chunk * SB_TC;
         const int tn = min(SB_TC, f.len - t0);
@@ -102,17 +124,17 @@ __global__ void __launch_bounds__(32 * SL) selective_scan_bwd_kernel(const cum_s
             const int t = i >> 5, cc = i & 31;
             const int tt = t0 + t, cg = c0 + cc;
             const bool ok = t < tn && cg < f.d;
-            pf_u[e] = ok ? f.u[(long long)b * f.u_bs + (long long)tt * f.u_rs + cg] : 0.f;
-            pf_d[e] = ok ? f.delta[(long long)b * f.dl_bs + (long long)tt * f.dl_rs + cg] : 0.f;
-            pf_z[e] = (ok && f.z) ? f.z[(long long)b * f.z_bs + (long long)tt * f.z_rs + cg] : 0.f;
-            pf_o[e] = ok ? p.dout[(long long)b * p.dout_bs + (long long)tt * p.dout_rs + cg] : 0.f;
+            pf_u[e] = ok ? ub[(long long)tt * f.u_rs + cg] : 0.f;
+            pf_d[e] = ok ? db[(long long)tt * f.dl_rs + cg] : 0.f;
+            pf_z[e] = (ok && zb) ? zb[(long long)tt * f.z_rs + cg] : 0.f;
+            pf_o[e] = ok ? ob[(long long)tt * p.dout_rs + cg] : 0.f;
         }
         e = 0;
         for (int i = tid; i < SB_TC * NP; i += NT, ++e) {
             const int t = i / NP, n = i - t * NP;
             const bool ok = t < tn && n < f.n_state;
-            pf_B[e] = ok ? f.Bm[(long long)b * f.B_bs + (long long)(t0 + t) * f.B_rs + n] : 0.f;
-            pf_C[e] = ok ? f.Cm[(long long)b * f.C_bs + (long long)(t0 + t) * f.C_rs + n] : 0.f;
+            pf_B[e] = ok ? Bb[(long long)(t0 + t) * f.B_rs + n] : 0.f;
+            pf_C[e] = ok ? Cb[(long long)(t0 + t) * f.C_rs + n] : 0.f;
         }
     };
     prefetch(nchunks - 1);
@@ -128,9 +150,11 @@ __global__ void __launch_bounds__(32 * SL) selective_scan_bwd_kernel(const cum_s
                 const int cg = c0 + cc;
                 float dr = pf_d[e];
                 if (f.delta_bias && cg < f.d) dr += f.delta_bias[cg];
+                const float dlv = f.delta_softplus ? softplus_b(dr) : dr;
                 sm.u[t][cc] = pf_u[e];
                 sm.draw[t][cc] = dr;
-                sm.dl[t][cc] = f.delta_softplus ? softplus_b(dr) : dr;
+                sm.dl[t][cc] = dlv;
+                sm.duv[t][cc] = dlv * pf_u[e];
                 sm.z[t][cc] = pf_z[e];
                 sm.dout[t][cc] = pf_o[e];
             }
@@ -143,27 +167,34 @@ __global__ void __launch_bounds__(32 * SL) selective_scan_bwd_kernel(const cum_s
         }
         if (chunk > 0) prefetch(chunk - 1);       // global latency of the next (earlier) chunk overlaps this chunk's math
         __syncthreads();
-        // ---- forward recompute with history in registers
-        float hs[4], hist[SB_TC][4];
+        // ---- forward recompute with history in registers (checkpoints: (batch, chunk, state, channel), coalesced over the lanes)
+        float2 hs2[2], hist[SB_TC][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int n = slice * 4 + i;
-            hs[i] = (c_ok && n < f.n_state) ? p.h_ckpt[(((long long)b * nchunks + chunk) * f.d + c) * f.n_state + n] : 0.f;
+        for (int j = 0; j < 2; ++j) {
+            float hv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = slice * 4 + 2 * j + e;
+                hv[e] = (c_ok && n < f.n_state) ? p.h_ckpt[(((long long)b * nchunks + chunk) * f.n_state + n) * f.d + c] : 0.f;
+            }
+            hs2[j] = make_float2(hv[0], hv[1]);
         }
         {
-            float h[4] = {hs[0], hs[1], hs[2], hs[3]};
+            float2 h0 = hs2[0], h1 = hs2[1];
 #pragma unroll
             for (int t = 0; t < SB_TC; ++t) {
-                const float dlv = sm.dl[t][ch];
-                const float duv = dlv * sm.u[t][ch];
+                const float dlv = sm.dl[t][ch], duv = sm.duv[t][ch];
+                const float2 dl2 = make_float2(dlv, dlv), du2 = make_float2(duv, duv);
                 const float4 bv = *reinterpret_cast<const float4*>(&sm.Bm[t][slice * 4]);
                 const float4 cv = *reinterpret_cast<const float4*>(&sm.Cm[t][slice * 4]);
-                h[0] = fmaf(ex2_approx_b(dlv * a2[0]), h[0], duv * bv.x);
-                h[1] = fmaf(ex2_approx_b(dlv * a2[1]), h[1], duv * bv.y);
-                h[2] = fmaf(ex2_approx_b(dlv * a2[2]), h[2], duv * bv.z);
-                h[3] = fmaf(ex2_approx_b(dlv * a2[3]), h[3], duv * bv.w);
-                hist[t][0] = h[0]; hist[t][1] = h[1]; hist[t][2] = h[2]; hist[t][3] = h[3];
-                sm.part0[slice][t][ch] = (h[0] * cv.x + h[1] * cv.y) + (h[2] * cv.z + h[3] * cv.w);
+                float2 x0 = __fmul2_rn(dl2, a2p[0]), x1 = __fmul2_rn(dl2, a2p[1]);
+                x0.x = ex2_approx_b(x0.x); x0.y = ex2_approx_b(x0.y);
+                x1.x = ex2_approx_b(x1.x); x1.y = ex2_approx_b(x1.y);
+                h0 = __ffma2_rn(x0, h0, __fmul2_rn(du2, make_float2(bv.x, bv.y)));
+                h1 = __ffma2_rn(x1, h1, __fmul2_rn(du2, make_float2(bv.z, bv.w)));
+                hist[t][0] = h0; hist[t][1] = h1;
+                const float2 yp = __ffma2_rn(h1, make_float2(cv.z, cv.w), __fmul2_rn(h0, make_float2(cv.x, cv.y)));
+                sm.part0[slice][t][ch] = yp.x + yp.y;
             }
         }
         __syncthreads();
@@ -189,43 +220,39 @@ __global__ void __launch_bounds__(32 * SL) selective_scan_bwd_kernel(const cum_s
             if (t < tn) accD = fmaf(dyv, uv, accD);
         }
         __syncthreads();
-        // ---- reverse walk
+        // ---- reverse walk.  Steps beyond the sequence end (t >= tn, last chunk only -- the FIRST one walked, so G is still 0 there)
+        // have dy = 0: every product below is an exact 0 and nothing has to be masked except the atomics' row bound.
+        float* red_ptr = red_base + (long long)(t0 + SB_TC - 1) * red_rs;
 #pragma unroll
         for (int t = SB_TC - 1; t >= 0; --t) {
-            const float dyv = sm.dy[t][ch];
-            const float dlv = sm.dl[t][ch];
-            const float duv = dlv * sm.u[t][ch];
+            const float dyv = sm.dy[t][ch], dlv = sm.dl[t][ch], duv = sm.duv[t][ch];
+            const float2 dy2 = make_float2(dyv, dyv), dl2 = make_float2(dlv, dlv), du2 = make_float2(duv, duv);
             const float4 bv = *reinterpret_cast<const float4*>(&sm.Bm[t][slice * 4]);
             const float4 cv = *reinterpret_cast<const float4*>(&sm.Cm[t][slice * 4]);
-            const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, cc4[4] = {cv.x, cv.y, cv.z, cv.w};
-            float sgB = 0.f, sdl = 0.f, dCp[4], dBp[4];
+            const float2 b2[2] = {make_float2(bv.x, bv.y), make_float2(bv.z, bv.w)};
+            const float2 c2[2] = {make_float2(cv.x, cv.y), make_float2(cv.z, cv.w)};
+            float2 sg2 = make_float2(0.f, 0.f), sd2 = make_float2(0.f, 0.f), dC2[2], dB2[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float g = fmaf(dyv, cc4[i], G[i]);
-                dCp[i] = dyv * hist[t][i];
-                dBp[i] = g * duv;
-                sgB = fmaf(g, bb[i], sgB);
-                const float hprev = t > 0 ? hist[t > 0 ? t - 1 : 0][i] : hs[i];
-                const float e = ex2_approx_b(dlv * a2[i]);
-                const float de = g * hprev;
-                dA[i] = fmaf(de * dlv, e, dA[i]);
-                sdl = fmaf(de * e, Aln[i], sdl);
-                G[i] = t < tn ? g * e : G[i];        // steps beyond the sequence end carry nothing
+            for (int j = 0; j < 2; ++j) {
+                const float2 g = __ffma2_rn(dy2, c2[j], G2[j]);
+                dC2[j] = __fmul2_rn(dy2, hist[t][j]);
+                dB2[j] = __fmul2_rn(g, du2);
+                sg2 = __ffma2_rn(g, b2[j], sg2);
+                const float2 hprev = t > 0 ? hist[t > 0 ? t - 1 : 0][j] : hs2[j];
+                float2 e = __fmul2_rn(dl2, a2p[j]);
+                e.x = ex2_approx_b(e.x); e.y = ex2_approx_b(e.y);
+                const float2 q = __fmul2_rn(__fmul2_rn(g, hprev), e);
+                dA2[j] = __ffma2_rn(q, dl2, dA2[j]);
+                sd2 = __ffma2_rn(q, Alnp[j], sd2);
+                G2[j] = __fmul2_rn(g, e);
             }
-            sm.part0[slice][t][ch] = sgB;
-            sm.part1[slice][t][ch] = sdl;
+            sm.part0[slice][t][ch] = sg2.x + sg2.y;
+            sm.part1[slice][t][ch] = sd2.x + sd2.y;
             // d-reductions of dB / dC over the warp's 32 channels: 8 values, 9 shuffles (warp_sum8)
-            {
-                const float v8[8] = {dCp[0], dCp[1], dCp[2], dCp[3], dBp[0], dBp[1], dBp[2], dBp[3]};
-                const float tot = warp_sum8(v8, ch);
-                const int idx = ((ch >> 4) & 1) * 4 + ((ch >> 3) & 1) * 2 + ((ch >> 2) & 1);    // value this lane holds
-                const int n = slice * 4 + (idx & 3);
-                if ((ch & 3) == 0 && t < tn && n < f.n_state) {
-                    float* dst = idx < 4 ? p.dC + (long long)b * p.dC_bs + (long long)(t0 + t) * p.dC_rs
-                                         : p.dB + (long long)b * p.dB_bs + (long long)(t0 + t) * p.dB_rs;
-                    atomicAdd(dst + n, tot);
-                }
-            }
+            const float v8[8] = {dC2[0].x, dC2[0].y, dC2[1].x, dC2[1].y, dB2[0].x, dB2[0].y, dB2[1].x, dB2[1].y};
+            const float tot = warp_sum8(v8, ch);
+            if (red_lane && t < tn) atomicAdd(red_ptr, tot);
+            red_ptr -= red_rs;
         }
         __syncthreads();
         // ---- combine 2: du, ddelta, dbias
@@ -254,9 +281,13 @@ __global__ void __launch_bounds__(32 * SL) selective_scan_bwd_kernel(const cum_s
     }
     // ---- parameter gradients
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = slice * 4 + i;
-        if (c_ok && n < f.n_state && p.dA_log) atomicAdd(p.dA_log + (long long)c * f.n_state + n, dA[i] * Aln[i]);
+    for (int j = 0; j < 2; ++j) {
+        const float dv[2] = {dA2[j].x * Alnp[j].x, dA2[j].y * Alnp[j].y};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int n = slice * 4 + 2 * j + e;
+            if (c_ok && n < f.n_state && p.dA_log) atomicAdd(p.dA_log + (long long)c * f.n_state + n, dv[e]);
+        }
     }
     if (c_ok) {
         if (p.dD) atomicAdd(p.dD + c, accD);

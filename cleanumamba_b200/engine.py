@@ -289,7 +289,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------ op wrappers
     def gemm(self, a, a_off, a_bs, a_rs, a_rows, k, w, bias, c, c_off, c_bs, c_rs, m, n, batch, epi,
-             taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None, a_scale=None, aux=None, aux_bs=0, aux_rs=0):
+             taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None, a_scale=None, aux=None, aux_bs=0, aux_rs=0, addend_mask=False):
         d = GemmDesc()
         d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k = a.data_ptr() + a.element_size() * a_off, a_bs, a_rs, a_rows, k
         # "hl16" tensors (dtype float16, leading dimension 2 = [hi plane, lo plane], see cum_gemm_desc.a_lo): pre-split activations
@@ -317,6 +317,7 @@ class Engine:
         d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch = c.data_ptr() + c.element_size() * c_off, c_bs, c_rs, m, n, batch
         d.epilogue = epi
         d.addend, d.add_batch_stride, d.add_row_stride = ptr(addend), add_bs, add_rs
+        d.addend_is_mask = 1 if (addend_mask and addend is not None) else 0
         if a_scale is not None and d.math == _lib.MATH_F16X3 and a.dtype == torch.float32:
             d.a_scale_dev = a_scale.data_ptr()          # device-side power-of-two scale of a gradient operand (TrainEngine)
         if aux is not None:         # training: second fp32 output (pre-gate / pre-addend value), see cum_gemm_desc.aux

@@ -39,6 +39,10 @@ class TrainEngine(Engine):
     # (the pre-activation / the pre-add value: cum_gemm_desc.aux) -- no stand-alone glu_fwd / add kernels
     fused_forward = os.environ.get("CUM_TRAIN_FUSED_FWD", "1") != "0"
     f16_forward = os.environ.get("CUM_TRAIN_F16_FWD", "1") != "0"     # f16x3 models: forward GEMMs in f16x3 (A/B switch)
+    # ReLU backward as a mask in the epilogue of the data-gradient GEMM that produces its input gradient (cum_gemm_desc.addend_is_mask).
+    # Measured (same box, 16 x 10 s): 55.3 ms with it, 54.8 ms without -- the mask read + the separate column-sum pass cost more than
+    # the stand-alone relu_bwd kernel saves; off by default.
+    fused_relu_bwd = os.environ.get("CUM_TRAIN_FUSED_RELU_BWD", "0") != "0"
 
     def _pack(self):
         if getattr(self.model, "math_mode", None) == "bf16" or not self.f16_forward and getattr(self.model, "math_mode", None) == "f16x3":
@@ -130,13 +134,26 @@ class TrainEngine(Engine):
         self._call("wgrad", self.lib.cum_gemm_wgrad, C.byref(d), _lib.stream_ptr(), flops=2 * batch * m * n * k * taps,
                    launches=1 if ws is None else 2 + taps + (0 if scale is not None else 3))
 
-    def dense_T(self, dz, rows, n_fwd, key, k_fwd, addend=None, out=None, c_rs=None, scale=None):
-        """Data gradient of a flat dense layer: (rows, n_fwd) x W (n_fwd, k_fwd) -> (rows, k_fwd)."""
+    def dense_T(self, dz, rows, n_fwd, key, k_fwd, addend=None, out=None, c_rs=None, scale=None, relu_mask=None, unmasked=None):
+        """Data gradient of a flat dense layer: (rows, n_fwd) x W (n_fwd, k_fwd) -> (rows, k_fwd).  ``relu_mask`` (rows, k_fwd): the
+        forward's ReLU output -- the gradient is zeroed where it is not positive (ReLU backward in the epilogue), ``unmasked``
+        receives the gradient before the mask."""
         c = out if out is not None else self.new(rows, k_fwd)
         crs = k_fwd if c_rs is None else c_rs
-        self.gemm(dz, 0, 0, n_fwd, rows, n_fwd, key + "T", None, c, 0, 0, crs, rows, k_fwd, 1, EPI_NONE,
-                  addend=addend, add_bs=0, add_rs=crs, a_scale=scale)
+        if relu_mask is not None:
+            self.gemm(dz, 0, 0, n_fwd, rows, n_fwd, key + "T", None, c, 0, 0, crs, rows, k_fwd, 1, EPI_NONE,
+                      addend=relu_mask, add_bs=0, add_rs=crs, addend_mask=True, a_scale=scale, aux=unmasked, aux_rs=crs)
+        else:
+            self.gemm(dz, 0, 0, n_fwd, rows, n_fwd, key + "T", None, c, 0, 0, crs, rows, k_fwd, 1, EPI_NONE,
+                      addend=addend, add_bs=0, add_rs=crs, a_scale=scale)
         return c
+
+    def colsum_scale(self, t, bias_key, rows, cols):
+        """Bias gradient (column sums) of the gradient tensor ``t`` and, in the same pass, its device scale for the f16x3 GEMMs."""
+        sc = self.scale_slot()
+        self._call("colsum", self.lib.cum_colsum, t.data_ptr(), self.gk[bias_key].data_ptr(), rows, cols, ptr(sc), _lib.stream_ptr(),
+                   launches=1 if sc is None else 2)
+        return sc
 
     # ---------------------------------------------------------------------------------------------- forward
     @on_model_device
@@ -206,7 +223,7 @@ class TrainEngine(Engine):
             xdbl = self.dense(xc, rows, di_p, f"m{l}.xp", None, R_p + 2 * N_p)
             dt = self.dense(xdbl, rows, R_p, f"m{l}.dtw", None, di_p, a_rs=R_p + 2 * N_p)
             y = self.new(rows, di_p)
-            ck = self.new(B, nchunks, di_p, N_p)
+            ck = self.new(B, nchunks, N_p, di_p)          # chunk-start states, channel fastest (cum_scan_desc.h_ckpt)
             self.scan(xc, dt, xz, xdbl, y, l, mm, B, T, h_ckpt=ck)
             h = self.dense(y, rows, di_p, f"m{l}.out", None, dm_p)
             S["mamba"].append(dict(res=res, hn=hn, xz=xz, xc=xc, xdbl=xdbl, dt=dt, y=y, ck=ck))
@@ -286,16 +303,26 @@ class TrainEngine(Engine):
             self._call("glu_bwd", lib.cum_glu_bwd, Zd.data_ptr(), dg.data_ptr(), Zd.data_ptr(), gk[f"dec{j}.bg"].data_ptr(),
                        rows, hg, ptr(sc), st(), launches=1 if sc is None else 2)                 # dZ in place (+ its scale)
             self.wgrad(Zd, 0, 2 * hg, S["xin"][j], 0, 0, cin, rows, f"dec{j}.wg", rows, 2 * hg, cin, 1, scale=sc)
-            dx = self.dense_T(Zd, rows, 2 * hg, f"dec{j}.wg", cin, scale=sc)           # gradient of this level's input
+            fuse_relu = j > 0 and self.fused_relu_bwd and self.fused_forward and self.math != _lib.MATH_FP32
+            if fuse_relu:
+                # x_in = relu(convT(prev)) + skip: dskip = dx (unmasked, second output), d(convT output) = dx where r > 0, written over r
+                r = S["r"][j - 1]
+                dx = self.new(rows, cin)
+                self.dense_T(Zd, rows, 2 * hg, f"dec{j}.wg", cin, scale=sc, relu_mask=r, unmasked=dx, out=r)
+            else:
+                dx = self.dense_T(Zd, rows, 2 * hg, f"dec{j}.wg", cin, scale=sc)           # gradient of this level's input
             if j > 0:
                 lvl = D - 1 - j                                               # x_in = relu-convT(prev) + skip[lvl]
                 dskip[lvl] = dx
                 dp = meta["dec"][j - 1]
                 co, hgp, Tp = dp["Co_p"], dp["Hg_p"], (Tj - 2) // 2
                 r = S["r"][j - 1]
-                sc = self.scale_slot()
-                self._call("relu_bwd", lib.cum_relu_bwd, r.data_ptr(), dx.data_ptr(), r.data_ptr(), gk[f"dec{j-1}.b"].data_ptr(),
-                           B * (Tp + 1), 2 * co, ptr(sc), st(), launches=1 if sc is None else 2)     # dZ (B, Tp+1, 2co) in place of r
+                if fuse_relu:
+                    sc = self.colsum_scale(r, f"dec{j-1}.b", B * (Tp + 1), 2 * co)
+                else:
+                    sc = self.scale_slot()
+                    self._call("relu_bwd", lib.cum_relu_bwd, r.data_ptr(), dx.data_ptr(), r.data_ptr(), gk[f"dec{j-1}.b"].data_ptr(),
+                               B * (Tp + 1), 2 * co, ptr(sc), st(), launches=1 if sc is None else 2)     # dZ (B, Tp+1, 2co) in place of r
                 self.wgrad(r, (Tp + 1) * 2 * co, 2 * co, S["g"][j - 1], 0, Tp * hgp, hgp, Tp, f"dec{j-1}.w", Tp + 1, 2 * co,
                            hgp, B, taps=2, shifts=(0, -1), scale=sc)
                 dg = self.new(B * Tp, hgp)
@@ -310,8 +337,7 @@ class TrainEngine(Engine):
         rows = B * T
         dm, dm_p, cb_p = meta["dm"], meta["dm_p"], meta["enc"][-1]["Ho_p"]
         dx0 = dskip[D - 1]
-        self._call("colsum", lib.cum_colsum, dx0.data_ptr(), gk["t2.b"].data_ptr(), rows, cb_p, st())
-        sc = self.grad_scale(dx0, rows, cb_p)
+        sc = self.colsum_scale(dx0, "t2.b", rows, cb_p)
         self.wgrad(dx0, 0, cb_p, S["hn_f"], 0, 0, dm_p, rows, "t2.w", rows, cb_p, dm_p, 1, scale=sc)
         dhn = self.dense_T(dx0, rows, cb_p, "t2.w", dm_p, scale=sc)
         # ---- final norm, Mamba layers in reverse
@@ -363,8 +389,7 @@ class TrainEngine(Engine):
                        mm["eps"], rows, dm, dm_p, st())
             dres = dres_new
         # ---- tsfm_conv1 (its output is res_0)
-        self._call("colsum", lib.cum_colsum, dres.data_ptr(), gk["t1.b"].data_ptr(), rows, dm_p, st())
-        sc = self.grad_scale(dres, rows, dm_p)
+        sc = self.colsum_scale(dres, "t1.b", rows, dm_p)
         self.wgrad(dres, 0, dm_p, S["skip"][D - 1], 0, 0, cb_p, rows, "t1.w", rows, dm_p, cb_p, 1, scale=sc)
         dskip[D - 1] = self.dense_T(dres, rows, dm_p, "t1.w", cb_p, addend=dskip[D - 1], scale=sc)
         bucket_done("bottleneck")
@@ -377,13 +402,21 @@ class TrainEngine(Engine):
             self._call("glu_bwd", lib.cum_glu_bwd, Z.data_ptr(), dskip[i].data_ptr(), Z.data_ptr(), gk[f"enc{i}.bg"].data_ptr(),
                        rows, ho, ptr(sc), st(), launches=1 if sc is None else 2)
             self.wgrad(Z, 0, 2 * ho, S["y"][i], 0, 0, hc, rows, f"enc{i}.wg", rows, 2 * ho, hc, 1, scale=sc)
-            dy = self.dense_T(Z, rows, 2 * ho, f"enc{i}.wg", hc, scale=sc)
             y = S["y"][i]
+            fuse_relu = i > 0 and self.fused_relu_bwd and self.fused_forward and self.math != _lib.MATH_FP32
+            if fuse_relu:       # ReLU backward in the epilogue of the data-gradient GEMM: dZ = dy where y > 0, written over y
+                self.dense_T(Z, rows, 2 * ho, f"enc{i}.wg", hc, scale=sc, relu_mask=y, out=y)
+                dy = None
+            else:
+                dy = self.dense_T(Z, rows, 2 * ho, f"enc{i}.wg", hc, scale=sc)
             if i > 0:
                 cp = e["Cin_p"]
-                sc = self.scale_slot()
-                self._call("relu_bwd", lib.cum_relu_bwd, y.data_ptr(), dy.data_ptr(), y.data_ptr(), gk[f"enc{i}.b"].data_ptr(),
-                           rows, hc, ptr(sc), st(), launches=1 if sc is None else 2)             # dZ in place of y
+                if fuse_relu:
+                    sc = self.colsum_scale(y, f"enc{i}.b", rows, hc)
+                else:
+                    sc = self.scale_slot()
+                    self._call("relu_bwd", lib.cum_relu_bwd, y.data_ptr(), dy.data_ptr(), y.data_ptr(), gk[f"enc{i}.b"].data_ptr(),
+                               rows, hc, ptr(sc), st(), launches=1 if sc is None else 2)             # dZ in place of y
                 src = S["skip"][i - 1]
                 self.wgrad(y, Ls[i + 1] * hc, hc, src, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2, f"enc{i}.w", Ls[i + 1], hc, 2 * cp, B,
                            taps=2, shifts=(0, 1), scale=sc)

@@ -158,6 +158,8 @@ typedef struct cum_gemm_desc {
     const float* a_scale_dev;/* CUM_MATH_F16X3 with fp32 `a` only: NULL, or a DEVICE pointer to {s, 1/s} (cum_grad_scale_fwd): `a` is multiplied
                                 by s while it is split into fp16 halves and the accumulator by 1/s -- back-propagated gradients
                                 (~1e-6) are lifted into fp16's range by a power of two computed on the device, no host sync */
+    int addend_is_mask;      /* tensor-core modes, fp32 output: `addend` is a ReLU MASK instead -- out = addend > 0 ? value : 0 (the ReLU backward
+                                of a data-gradient GEMM; with `aux` the unmasked value is kept as well) */
     float* aux; long long aux_batch_stride; long long aux_row_stride;
                              /* optional SECOND fp32 output of a tensor-core call (training keeps what the backward needs without a
                                 separate elementwise kernel): with a GLU epilogue the (m, n) PRE-ACTIVATION (bias added, before the
@@ -256,7 +258,8 @@ typedef struct cum_scan_desc {
     const float* h0; float* h_out;
     int batch, len, d, n_state;
     int delta_softplus;
-    float* h_ckpt;      /* optional (training): (batch, ceil(len/16), d, n_state) -- h at the start of every 16-step chunk,
+    float* h_ckpt;      /* optional (training): (batch, ceil(len/16), n_state, d) -- h at the start of every 16-step chunk (channel
+                           fastest: a warp's 32 channels store / load one 128-byte run per state),
                            consumed by cum_selective_scan_bwd */
     void* workspace;    /* optional scratch (16-byte aligned) of cum_selective_scan_workspace_bytes(desc) bytes: with it, SMALL
                            batches (fewer than SM-count/2 CTAs of 64 channels, len >= 256) run segment-parallel -- the clip is cut
@@ -282,7 +285,7 @@ int cum_glu_bwd(const float* z, const float* dout, float* dz, float* dbias, long
                 cum_stream_t stream);
 int cum_relu_bwd(const float* y, const float* dy, float* dz, float* dbias, long long rows, int cols, float* dz_scale4,
                  cum_stream_t stream);
-int cum_colsum(const float* d, float* dbias, long long rows, int cols, cum_stream_t stream);
+int cum_colsum(const float* d, float* dbias, long long rows, int cols, float* d_scale4, cum_stream_t stream);
 int cum_add_fwd(const float* a, const float* b, float* out, long long count, cum_stream_t stream);
 
 /* Weight gradient of the tap-GEMM:  dw[s, n, k] += sum_{b, row < m} dz[b,row,n] * a[b, row + tap_shift[s], k]

@@ -79,7 +79,7 @@ def test_elementwise_backward_and_colsum():
     yd, dyd = y.to(DEV), dy.to(DEV)
     dzr, dbr, cs = torch.empty(70, 1536, device=DEV), torch.zeros(1536, device=DEV), torch.zeros(1536, device=DEV)
     _lib.check(lib.cum_relu_bwd(yd.data_ptr(), dyd.data_ptr(), dzr.data_ptr(), dbr.data_ptr(), 70, 1536, 0, _lib.stream_ptr()), "relu_bwd")
-    _lib.check(lib.cum_colsum(dyd.data_ptr(), cs.data_ptr(), 70, 1536, _lib.stream_ptr()), "colsum")
+    _lib.check(lib.cum_colsum(dyd.data_ptr(), cs.data_ptr(), 70, 1536, 0, _lib.stream_ptr()), "colsum")
     want = dy * (y > 0)
     assert torch.equal(dzr.cpu(), want) and rel(dbr, want.sum(0)) < 1e-5 and rel(cs, dy.sum(0)) < 1e-5
 
@@ -140,7 +140,7 @@ def test_selective_scan_backward(b, d, l, n):
     a2 = (-torch.exp(A_log.detach()) * 1.4426950408889634).contiguous().to(DEV)
     Dd, biasd = D.detach().to(DEV), bias.detach().to(DEV)
     nchunks = (l + 15) // 16
-    y, ck = torch.empty(b, l, d, device=DEV), torch.empty(b, nchunks, d, n, device=DEV)
+    y, ck = torch.empty(b, l, d, device=DEV), torch.empty(b, nchunks, n, d, device=DEV)
     s = _lib.ScanDesc()
     s.u, s.u_bs, s.u_rs = ucl.data_ptr(), l * d, d
     s.delta, s.dl_bs, s.dl_rs = dcl.data_ptr(), l * d, d
