@@ -582,7 +582,10 @@ static SegPlan plan_segments(const cum_scan_desc& d) {
     const long long ctas = cdiv(d.d, 64) * d.batch;
     if (d.h_ckpt || d.len < 256 || 2 * ctas > sm_count()) return s;
     long long n = (2LL * sm_count() + ctas - 1) / ctas;
-    if (n > d.len / 64) n = d.len / 64;
+    // segments of at least 64 steps -- except for the handful of CTAs of a pruned checkpoint (d_inner 8-48 at batch 1-4), whose scan is
+    // pure latency: 16-step segments (one staging chunk each) cut a 624-token pass from 21-31 us to one chunk's time
+    const long long min_seg = ctas <= 8 ? 16 : 64;
+    if (n > d.len / min_seg) n = d.len / min_seg;
     if (n > 64) n = 64;
     if (n < 2) return s;
     s.seg_len = (int)(cdiv(cdiv(d.len, n), 16) * 16);

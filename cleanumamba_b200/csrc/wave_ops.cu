@@ -1,6 +1,7 @@
 // Waveform-end kernels: input normalisation, first encoder conv (Cin = 1), last decoder transposed conv (Cout = 1).
 // All three are HBM-bound streaming kernels (a few FLOP per byte); see DESIGN.md "kernels".
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -8,8 +9,8 @@
 namespace cum {
 
 // ---------------------------------------------------------------------------------------------------------
-// std (unbiased) + 1e-3, in-place divide.  Reference: CleanUMamba.py:260-262.  One CTA per clip; two-pass
-// mean/variance in fp64 (torch's CPU std accumulates in double), then the divide.
+// std (unbiased) + 1e-3, in-place divide.  Reference: CleanUMamba.py:260-262.  Two-pass mean/variance in fp64 (torch's CPU std
+// accumulates in double), then the divide.
 // ---------------------------------------------------------------------------------------------------------
 __device__ double block_sum(double v, double* red) {
     v = warp_sum(v);
@@ -26,30 +27,61 @@ __device__ double block_sum(double v, double* red) {
     return red[0];
 }
 
-__global__ void __launch_bounds__(1024) wave_normalize_kernel(float* __restrict__ x, float* __restrict__ std_out,
-                                                               int length) {
+// A clip is shared by a CLUSTER of WN_CL CTAs (one CTA per clip walked 640 KB three times with 1024 threads: 96 us at batch 1 -- 13 %
+// of the whole forward of a pruned checkpoint -- and 64 CTAs on 148 SMs at batch 64).  Each CTA reduces its slice, the CTA totals meet
+// through distributed shared memory (every CTA adds the WN_CL partials in the same order, so all of them hold the same fp64 value).
+constexpr int WN_CL = 8, WN_THREADS = 512;
+
+__device__ __forceinline__ double cluster_sum(double v, double* red, double* part) {
+    const double t = block_sum(v, red);
+    if (threadIdx.x == 0) *part = t;
+    cluster_sync_all();                                  // release / acquire: every CTA's partial is visible cluster-wide
+    double tot = 0.0;
+#pragma unroll
+    for (int r = 0; r < WN_CL; ++r) {
+        double pv;
+        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(pv) : "r"(mapa_rank(smem_u32(part), (uint32_t)r)));
+        tot += pv;
+    }
+    return tot;
+}
+
+__global__ void __cluster_dims__(WN_CL, 1, 1) __launch_bounds__(WN_THREADS)
+wave_normalize_kernel(float* __restrict__ x, float* __restrict__ std_out, int length) {
     pdl_trigger();
     pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
 
     __shared__ double red[32];
-    float* row = x + (long long)blockIdx.x * length;
+    __shared__ double part[2];
+    const int clip = blockIdx.x / WN_CL;
+    const int rank = (int)cluster_ctarank();
+    float* row = x + (long long)clip * length;
+    const bool vec = (length % 4 == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    const int t = rank * WN_THREADS + threadIdx.x, nt = WN_CL * WN_THREADS;      // this thread among the clip's threads
+    const int n4 = vec ? length >> 2 : 0;
+    float4* row4 = reinterpret_cast<float4*>(row);
     double s = 0.0;
-    for (int i = threadIdx.x; i < length; i += blockDim.x) s += (double)row[i];
-    const double mean = block_sum(s, red) / (double)length;
+    if (vec) for (int i = t; i < n4; i += nt) { const float4 v = row4[i]; s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w); }
+    else for (int i = t; i < length; i += nt) s += (double)row[i];
+    const double mean = cluster_sum(s, red, &part[0]) / (double)length;
     double q = 0.0;
-    for (int i = threadIdx.x; i < length; i += blockDim.x) {
-        const double d = (double)row[i] - mean;
-        q += d * d;
+    if (vec) for (int i = t; i < n4; i += nt) {
+        const float4 v = row4[i];
+        const double d0 = (double)v.x - mean, d1 = (double)v.y - mean, d2 = (double)v.z - mean, d3 = (double)v.w - mean;
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
     }
-    const double var = block_sum(q, red) / (double)(length > 1 ? length - 1 : 1);
+    else for (int i = t; i < length; i += nt) { const double d = (double)row[i] - mean; q += d * d; }
+    const double var = cluster_sum(q, red, &part[1]) / (double)(length > 1 ? length - 1 : 1);
     const float sd = (float)sqrt(var) + 1e-3f;
-    if (threadIdx.x == 0) std_out[blockIdx.x] = sd;
-    for (int i = threadIdx.x; i < length; i += blockDim.x) row[i] = row[i] / sd;
+    if (t == 0) std_out[clip] = sd;
+    if (vec) for (int i = t; i < n4; i += nt) { float4 v = row4[i]; v.x = v.x / sd; v.y = v.y / sd; v.z = v.z / sd; v.w = v.w / sd; row4[i] = v; }
+    else for (int i = t; i < length; i += nt) row[i] = row[i] / sd;
+    cluster_sync_all();                                  // no CTA exits while a peer may still read its partials
 }
 
 int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStream_t st) {
     CUM_REQUIRE(x && std_out && batch > 0 && length > 0, "wave_normalize: bad arguments");
-    cudaError_t e = launch_kernel(wave_normalize_kernel, dim3(batch), dim3(1024), 0, st, x, std_out, length);
+    cudaError_t e = launch_kernel(wave_normalize_kernel, dim3((unsigned)batch * WN_CL), dim3(WN_THREADS), 0, st, x, std_out, length);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(wave_normalize_kernel)");
     return CUM_OK;
 }
