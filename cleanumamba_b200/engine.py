@@ -67,7 +67,7 @@ def on_model_device(fn):
 class Engine:
     skip_zero_lo = True      # skip the a_hi*w_lo pass for weights whose low half is exactly zero (tests may turn it off)
     hl16 = os.environ.get("CUM_HL16", "1") != "0"    # f16x3: store the conv-stack activations as fp16 hi/lo planes (A/B switch)
-    HL16_MIN_CONSUMER_K = int(os.environ.get("CUM_HL16_CK", 512))     # thresholds of the per-tensor hl16 rule (see forward())
+    HL16_MIN_CONSUMER_K = int(os.environ.get("CUM_HL16_CK", 256))     # thresholds of the per-tensor hl16 rule (see forward())
     HL16_MIN_PRODUCER_K = int(os.environ.get("CUM_HL16_PK", 256))
     fused_ends = os.environ.get("CUM_FUSED_ENDS", "1") != "0"    # f16x3, 64-channel ends: first / last U-Net block as one kernel each
 
