@@ -204,7 +204,8 @@ def run_reference(args, cfg, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def measure_stream(net, eng, dev, rank, world, dist, S, H, steps, warmup, graph=False, math="f16x3", model="e6", total=None):
+def measure_stream(net, eng, dev, rank, world, dist, S, H, steps, warmup, graph=False, math="f16x3", model="e6", total=None,
+                   layout="auto", state_f16=False):
     """configs[2]: S concurrent streams on this GPU, H hops per feed() call, carried conv/SSM state.  A step = one feed() call
     over all streams; value = streamed audio-seconds per wall-second over all ranks.  Returns the record (every rank)."""
     hop = net.total_stride
@@ -213,7 +214,8 @@ def measure_stream(net, eng, dev, rank, world, dist, S, H, steps, warmup, graph=
     host_chunk = (torch.randn(S, n_chunk, generator=g) * 0.1).pin_memory()
     host_out = torch.empty(S, n_chunk).pin_memory()
     chunk = host_chunk.to(dev)
-    sess = net.stream_session(batch=S)
+    sess = net.stream_session(batch=S, layout=layout, state_dtype=torch.float16 if state_f16 else torch.float32)
+    layout_used = "time_major" if type(sess).__name__ == "TimeMajorStreamSession" else "stream_major"
     sess.feed((torch.randn(S, net.frame_length - hop, generator=g) * 0.1).to(dev))   # prime: next feeds emit H hops each
 
     def barrier():
@@ -267,8 +269,10 @@ def measure_stream(net, eng, dev, rank, world, dist, S, H, steps, warmup, graph=
             "higher_is_better": True, "scaling": "strong" if total else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"CleanUMamba {model.upper()} streaming, {n_streams} streams in total ({S} on rank 0), {H} hops "
                                    f"({n_chunk} samples, {1e3 * n_chunk / SR:.0f} ms) per feed(), carried conv/SSM state, "
-                                   f"math={math}" + (", CUDA-graph replay" if graph else ""),
-                       "streams_total": n_streams, "streams_per_gpu": S,
+                                   f"math={math}" + (", CUDA-graph replay" if graph else "") +
+                                   (", REDUCED-PRECISION variant: SSM state stored as fp16" if state_f16 else ""),
+                       "streams_total": n_streams, "streams_per_gpu": S, "buffer_layout": layout_used,
+                       "ssm_state_dtype": "f16" if state_f16 else "f32",
                        "real_time_factor_per_stream": round(n_chunk / SR / (ms / steps / 1e3), 2),
                        "chunk_latency_ms": round(ms / steps, 3)},
             "e2e": {"value": round(audio / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": S * n_chunk * 4,
@@ -283,7 +287,7 @@ def run_stream(args, net, eng, dev, rank, world, dist):
         lo, hi = shard_bounds(args.streams_total, rank, world)
         S = hi - lo
     rec = measure_stream(net, eng, dev, rank, world, dist, S, args.hops, args.steps, args.warmup, graph=args.graph, math=args.math,
-                         model=args.model, total=args.streams_total)
+                         model=args.model, total=args.streams_total, layout=args.layout, state_f16=args.state_f16)
     if rank == 0:
         print(json.dumps(rec), flush=True)
     if dist is not None:
@@ -544,6 +548,8 @@ def main():
     ap.add_argument("--hops", type=int, default=16, help="[stream] hops (2^D samples each) per feed() call")
     ap.add_argument("--graph", action="store_true", help="[stream] replay a captured CUDA graph of the steady-state feed()")
     ap.add_argument("--streams-total", type=int, default=0, help="[stream] total streams, sharded over the ranks (overrides --streams)")
+    ap.add_argument("--layout", default="auto", choices=["auto", "stream_major", "time_major"], help="[stream] buffer layout of the session")
+    ap.add_argument("--state-f16", action="store_true", help="[stream] reduced-precision variant: SSM state stored as fp16 (time-major only)")
     ap.add_argument("--loss", default="fused", choices=["fused", "pytorch"], help="[train] MR-STFT loss implementation")
     ap.add_argument("--no-extras", action="store_true", help="skip the `train` / `stream` sub-records of the default line")
     args = ap.parse_args()
@@ -665,6 +671,10 @@ def main():
             extras["stream"] = {f"hops{h}": measure_stream(net_s, net_s.engine(), dev, rank, world, dist, hi - lo, h,
                                                             max(3, min(args.steps, 10)), 3, graph=(h == 1), math=args.math, total=4096)
                                 for h in (16, 1)}
+            # reduced-precision variant, reported separately: the carried SSM state (the HBM floor of a 1-hop call) stored as fp16
+            extras["stream"]["hops1_fp16_state_variant"] = measure_stream(net_s, net_s.engine(), dev, rank, world, dist, hi - lo, 1,
+                                                                            max(3, min(args.steps, 10)), 3, graph=True, math=args.math,
+                                                                            total=4096, state_f16=True)
             # the reference's real-time use -- ONE stream fed hop by hop (module-level feed(): CUDA-graph replay)
             extras["stream"]["single_stream_hop1_graph"] = measure_stream(net_s, net_s.engine(), dev, rank, world, dist, 1, 1, 50, 5,
                                                                             graph=True, math=args.math)

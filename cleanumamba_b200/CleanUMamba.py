@@ -167,15 +167,28 @@ class CleanUMamba(nn.Module):
         return {i: self.allocate_inference_cache_layer(blk.mixer, batch_size, dtype=dtype)
                 for i, blk in enumerate(self.tsfm_Mamba_layers)}
 
-    def stream_session(self, batch=1, auto_graph=False):
+    TIME_MAJOR_MIN_STREAMS = 64     # from this many concurrent streams the session keeps its buffers (column, stream, channel)
+
+    def stream_session(self, batch=1, auto_graph=False, layout="auto", state_dtype=torch.float32):
         """New carried-state streaming session for ``batch`` independent streams (extension: the reference's
         ``feed`` is batch 1 and keeps its state on the module).  ``auto_graph``: capture the steady-state step as a CUDA
         graph once the same whole-hop chunk size has been fed a few times (see StreamSession.capture_graph).
+        ``layout``: "auto" | "stream_major" | "time_major"; ``state_dtype=torch.float16`` (time-major only): reduced-precision
+        carried SSM state, a separately reported variant.
         The shipped skip-index slip (:474: ``skip_connections[i]`` without the reversal of :275) is NOT available as a mode:
         it raises a channel-mismatch error on every shipped checkpoint and, where all widths happen to be equal, adds the
         wrong level's skip; only the test oracle reproduces it (oracle ``compat_skip_order_bug``) to pin itself to the
         reference's own ``feed`` output."""
         from .streaming import StreamSession
+        from .stream_tm import TimeMajorStreamSession, time_major_supported
+        if layout not in ("auto", "stream_major", "time_major"):
+            raise ValueError("layout must be 'auto', 'stream_major' or 'time_major'")
+        # many streams: time-major buffers (stream_tm.py: all streams in the M dimension of every GEMM, FIFOs appended in place, no
+        # gather / scatter copies); one or a few streams: stream-major (rows of a stream contiguous).  Bit-identical outputs.
+        if layout == "time_major" or (layout == "auto" and batch >= self.TIME_MAJOR_MIN_STREAMS and time_major_supported(self)):
+            return TimeMajorStreamSession(self, batch=batch, auto_graph=auto_graph, state_dtype=state_dtype)
+        if state_dtype != torch.float32:
+            raise NotImplementedError("cleanumamba_b200: the reduced-precision SSM state is a feature of the time-major session")
         return StreamSession(self, batch=batch, auto_graph=auto_graph)
 
     @torch.no_grad()

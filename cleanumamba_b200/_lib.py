@@ -31,7 +31,8 @@ class GemmDesc(C.Structure):
                 ("addend", C.c_void_p), ("add_batch_stride", C.c_longlong), ("add_row_stride", C.c_longlong),
                 ("math", C.c_int), ("w_lo", C.c_void_p), ("acc_scale", C.c_float), ("out_bf16", C.c_int), ("w_lo_is_zero", C.c_int),
                 ("a_lo", C.c_void_p), ("c_lo", C.c_void_p), ("addend_lo", C.c_void_p), ("a_scale_dev", C.c_void_p), ("addend_is_mask", C.c_int), ("aux", C.c_void_p), ("aux_batch_stride", C.c_longlong), ("aux_row_stride", C.c_longlong),
-                ("cta_pair", C.c_int)]
+                ("cta_pair", C.c_int),
+                ("a_planes", C.c_int), ("a_plane_k", C.c_int), ("a_plane0", C.c_int), ("a_plane_step", C.c_int), ("n_half", C.c_int)]
 
 
 class Enc0BlockDesc(C.Structure):
@@ -59,7 +60,8 @@ class ScanDesc(C.Structure):
                 ("a2", C.c_void_p), ("Dskip", C.c_void_p), ("delta_bias", C.c_void_p),
                 ("h0", C.c_void_p), ("h_out", C.c_void_p),
                 ("batch", C.c_int), ("len", C.c_int), ("d", C.c_int), ("n_state", C.c_int),
-                ("delta_softplus", C.c_int), ("h_ckpt", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
+                ("delta_softplus", C.c_int), ("h_ckpt", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
+                ("state_f16", C.c_int)]
 
 
 class WgradDesc(C.Structure):
@@ -78,6 +80,11 @@ class ScanBwdDesc(C.Structure):
                 ("dB", C.c_void_p), ("dB_bs", C.c_longlong), ("dB_rs", C.c_longlong),
                 ("dC", C.c_void_p), ("dC_bs", C.c_longlong), ("dC_rs", C.c_longlong),
                 ("dA_log", C.c_void_p), ("dD", C.c_void_p), ("ddelta_bias", C.c_void_p)]
+
+
+class ShiftEntry(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("row_stride", C.c_longlong), ("src_off", C.c_longlong), ("count", C.c_longlong),
+                ("rows", C.c_int), ("reserved", C.c_int)]
 
 
 EXPORTS = {
@@ -100,6 +107,15 @@ EXPORTS = {
                                              C.c_void_p, C.c_void_p]),
     "cum_convt_out_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cum_conv_in_strided_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_void_p]),
+    "cum_convt_out_strided_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
+                                            C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cum_dwconv_silu_strided_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p]),
+    "cum_stream_shift_fwd": (C.c_int, [C.POINTER(ShiftEntry), C.c_int, C.c_void_p]),
     "cum_gemm_bias_act_fwd": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "cum_enc0_block_fwd": (C.c_int, [C.POINTER(Enc0BlockDesc), C.c_void_p]),
     "cum_dec_last_block_fwd": (C.c_int, [C.POINTER(DecLastBlockDesc), C.c_void_p]),

@@ -167,6 +167,37 @@ int cum_convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const f
                          stride, (cudaStream_t)stream);
 }
 
+// ---- ABI v3: strided variants for the time-major streaming session + its FIFO maintenance
+int cum_conv_in_strided_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
+                            float* y, long long y_batch_stride, long long y_row_stride, int rows_out, int c_pad, int kernel, int stride,
+                            const float* in_scale, int group_rows, int row_offset, cum_stream_t stream) {
+    CUM_REQUIRE(y_batch_stride > 0 && y_row_stride > 0, "conv_in_strided: strides must be positive");
+    return conv_in_fwd(x, x_stride, batch, length, w, bias, y, rows_out, c_pad, kernel, stride, in_scale, group_rows,
+                       row_offset, (cudaStream_t)stream, 0, nullptr, y_batch_stride, y_row_stride);
+}
+
+int cum_convt_out_strided_fwd(const float* g, long long g_batch_stride, long long g_row_stride, int batch, int rows_in, int c_pad,
+                              const float* w, float bias, const float* scale, int scale_group, float* out, long long out_stride,
+                              int first, int length, int kernel, int stride, cum_stream_t stream) {
+    CUM_REQUIRE(g_batch_stride > 0 && g_row_stride > 0, "convt_out_strided: strides must be positive");
+    return convt_out_fwd(g, batch, rows_in, c_pad, w, bias, scale, scale_group, out, out_stride, first, length, kernel,
+                         stride, (cudaStream_t)stream, false, g_batch_stride, g_row_stride);
+}
+
+int cum_dwconv_silu_strided_fwd(const float* x, long long x_batch_stride, long long x_row_stride, const float* w,
+                                const float* bias, float* y, long long y_batch_stride, long long y_row_stride,
+                                const float* conv_state, float* conv_state_out, int batch, int len, int d_pad, int width,
+                                cum_stream_t stream) {
+    CUM_REQUIRE(y_batch_stride > 0 && y_row_stride > 0, "dwconv_silu_strided: strides must be positive");
+    return dwconv_silu_fwd(x, x_batch_stride, x_row_stride, w, bias, y, conv_state, conv_state_out, batch, len, d_pad,
+                           width, (cudaStream_t)stream, y_batch_stride, y_row_stride);
+}
+
+int cum_stream_shift_fwd(const cum_shift_entry* entries, int n_entries, cum_stream_t stream) {
+    static_assert(sizeof(cum_shift_entry) == sizeof(StreamShiftEntry), "cum_shift_entry mirrors StreamShiftEntry");
+    return stream_shift_fwd(reinterpret_cast<const StreamShiftEntry*>(entries), n_entries, (cudaStream_t)stream);
+}
+
 int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream) {
     if (!desc) { set_error("gemm: null descriptor"); return CUM_EINVAL; }
     int rc = validate_gemm(*desc);

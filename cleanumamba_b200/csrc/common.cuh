@@ -91,12 +91,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 int wave_normalize_fwd(float* x, float* std_out, int batch, int length, cudaStream_t st);
 int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
                 float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
-                int row_offset, cudaStream_t st, int out_fmt = 0 /* 0 fp32, 1 bf16, 2 fp16 hi/lo planes */, void* y_lo = nullptr);
+                int row_offset, cudaStream_t st, int out_fmt = 0 /* 0 fp32, 1 bf16, 2 fp16 hi/lo planes */, void* y_lo = nullptr,
+                long long y_bs = 0, long long y_rs = 0 /* 0, 0 = contiguous (batch, rows_out, c_pad) */);
 int stream_std_fwd(const float* x, long long x_stride, int batch, int frames, int frame_len, int hop,
                    int frames_before, float* running, float* scale_out, cudaStream_t st, int* frames_counter = nullptr);
 int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
                   const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
-                  int kernel, int stride, cudaStream_t st, bool in_bf16 = false);
+                  int kernel, int stride, cudaStream_t st, bool in_bf16 = false, long long g_bs = 0, long long g_rs = 0);
 int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int enc0_block_fwd(const cum_enc0_block_desc& d, cudaStream_t st);
@@ -109,7 +110,9 @@ int ln_residual_fwd(const float* h, const float* residual_in, float* residual_ou
                     cudaStream_t st);
 int dwconv_silu_fwd(const float* x, long long x_bs, long long x_rs, const float* w, const float* bias, float* y,
                     const float* conv_state, float* conv_state_out, int batch, int len, int d_pad, int width,
-                    cudaStream_t st);
+                    cudaStream_t st, long long y_bs = 0, long long y_rs = 0);
+struct StreamShiftEntry { float* base; long long row_stride; long long src_off; long long count; int rows; int pad; };
+int stream_shift_fwd(const StreamShiftEntry* entries, int n_entries, cudaStream_t st);
 int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st);
 long long selective_scan_workspace_bytes(const cum_scan_desc& d);
 

@@ -18,6 +18,7 @@ struct SimtParams {
     const float* bias;
     float* c; long long c_bs, c_rs; int m, n, epi;
     const float* addend; long long add_bs, add_rs;
+    int a_planes, a_plane_k, a_plane0, a_plane_step, n_half;     // plane-major A (cum_gemm_desc.a_planes; 0 = off)
 };
 
 __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const SimtParams p) {
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const SimtParams 
     // tile element (row r, k-quad q): r = (tid >> 2) + 64*i, q = tid & 3
     const int lr = tid >> 2, lq = tid & 3;
     const float* ab = p.a + (long long)b * p.a_bs;
+    const int nh_off = (p.n_half && (b & 1)) ? p.n : 0;       // n_half: weight rows of this batch item's column half (the bias is shared)
 
     const int kblocks = (p.k + SG_BK - 1) / SG_BK;
     const int total = kblocks * p.taps;
@@ -49,16 +51,28 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(const SimtParams 
         const int tap = it / kblocks, kb = it - tap * kblocks;
         const int shift = tap == 0 ? p.shift0 : p.shift1;
         const int kk = kb * SG_BK + lq * 4;
+        // plane-major A: the tap shift and the upper part of K select the plane (see cum_gemm_desc.a_planes)
+        int ka = kk, rshift = shift;
+        const float* abase = ab;
+        bool plane_ok = true;
+        if (p.a_planes) {
+            const int kp = kk / p.a_plane_k;
+            const int pl = p.a_plane0 + p.a_plane_step * ((p.n_half ? b >> 1 : b) + shift) + kp;
+            ka = kk - kp * p.a_plane_k;
+            rshift = 0;
+            plane_ok = pl >= 0 && pl < p.a_planes;
+            abase = p.a + (long long)pl * p.a_bs;
+        }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int row = m0 + lr + 64 * i + shift;
+            const int row = m0 + lr + 64 * i + rshift;
             ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row >= 0 && row < p.a_rows && (m0 + lr + 64 * i) < p.m && kk < p.k)
-                ra[i] = __ldg(reinterpret_cast<const float4*>(ab + (long long)row * p.a_rs + kk));
+            if (plane_ok && row >= 0 && row < p.a_rows && (m0 + lr + 64 * i) < p.m && kk < p.k)
+                ra[i] = __ldg(reinterpret_cast<const float4*>(abase + (long long)row * p.a_rs + ka));
             const int nn = n0 + lr + 64 * i;
             rw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (nn < p.n && kk < p.k)
-                rw[i] = __ldg(reinterpret_cast<const float4*>(p.w + (long long)tap * p.w_tap_stride + (long long)nn * p.ldw + kk));
+                rw[i] = __ldg(reinterpret_cast<const float4*>(p.w + (long long)tap * p.w_tap_stride + (long long)(nn + nh_off) * p.ldw + kk));
         }
     };
     auto store_smem = [&](int buf) {
@@ -149,6 +163,13 @@ int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     p.w = d.w; p.ldw = d.ldw; p.w_tap_stride = (long long)d.n * d.ldw;
     p.bias = d.bias; p.c = d.c; p.c_bs = d.c_batch_stride; p.c_rs = d.c_row_stride; p.m = d.m; p.n = d.n;
     p.epi = d.epilogue; p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
+    p.a_planes = d.a_planes > 0 ? d.a_planes : 0; p.a_plane_k = d.a_plane_k; p.a_plane0 = d.a_plane0; p.a_plane_step = d.a_plane_step;
+    p.n_half = (d.a_planes > 0 && d.n_half) ? 1 : 0;
+    if (p.a_planes) {
+        CUM_REQUIRE(d.a_plane_k > 0 && d.a_plane_k % 4 == 0, "gemm: plane-major a needs a_plane_k %% 4 == 0");
+        CUM_REQUIRE(!p.n_half || !(d.epilogue >= CUM_EPI_GLU_SIGMOID), "gemm: n_half needs a non-GLU epilogue");
+        if (p.n_half) p.w_tap_stride = 2LL * d.n * d.ldw;
+    }
     dim3 grid((unsigned)cdiv(d.m, SG_BM), (unsigned)cdiv(d.n, SG_BN), (unsigned)d.batch);
     CUM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm: n=%d or batch=%d too large for the grid", d.n, d.batch);
     gemm_simt_kernel<<<grid, SG_THREADS, 0, st>>>(p);

@@ -101,6 +101,11 @@ struct TcParams {
                                             // (rows, n) pre-activation) or before the addend (other epilogues: same shape as c)
     void* c_lo;               // OUTF == 2: low-half plane of the output (c is the high-half plane), fp16
     const void* addend_lo;    // OUTF == 2: low-half plane of the addend
+    // plane-major A (time-major streaming FIFOs, cum_gemm_desc.a_planes): tensor-map dims are (a_plane_k, streams, planes); batch item b,
+    // tap shift s, K-offset ak read plane a_plane0 + a_plane_step * ((n_half ? b >> 1 : b) + s) + ak / a_plane_k at channels ak % a_plane_k
+    int a_plane_k;            // 0 = off
+    int a_plane0, a_plane_step;
+    int n_half;               // batch item b computes output-column half (b & 1): W rows (b & 1) * n ... (the bias is shared by both halves)
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -205,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int b, m0, n0;
             tile_coords(tile, b, m0, n0);
             // CTA2: this CTA stages the W rows of ITS half of the tile's columns (the MMA splits N across the pair)
-            const int wn = CTA2 ? n0 + (int)rank * (int)(tile_umma_n(n0) >> 1) : n0;
+            const int wn = (CTA2 ? n0 + (int)rank * (int)(tile_umma_n(n0) >> 1) : n0) + ((p.n_half && (b & 1)) ? p.n : 0);
             for (int it = 0; it < k_iters; ++it) {
                 const int tap = it / p.k_blocks, kb = it - tap * p.k_blocks;
                 const int shift = tap == 0 ? p.shift0 : p.shift1;
@@ -214,6 +219,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // bytes this stage will receive: A + W_hi (+ W_lo unless it is skipped); non-split modes have no W_lo at all
                 const uint32_t tx = (X3 && !load_lo) ? Cfg::TX_BYTES - Cfg::W_BYTES : Cfg::TX_BYTES;
                 const int wk = kb * Cfg::BK + b * p.w_k_batch_stride + p.w_k_off;
+                // A coordinates: (K offset, row, batch plane); plane-major A moves the tap shift and the upper part of K into the plane
+                int ak = kb * Cfg::BK, arow = m0 + shift, ab = b;
+                if (p.a_plane_k) {
+                    const int kp = ak / p.a_plane_k;
+                    ab = p.a_plane0 + p.a_plane_step * ((p.n_half ? b >> 1 : b) + shift) + kp;
+                    ak -= kp * p.a_plane_k;
+                    arow = m0;
+                }
                 if constexpr (MNM != 0) {
                     // split `sp` of clip `clip`: rows [r, r + 32) of both operands (the activation side shifted by the conv tap);
                     // rows / channels outside the tensors arrive as zeros
@@ -251,16 +264,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // no splitter in between: the leader's MMA thread waits for the bytes of BOTH CTAs on its own barrier
                     const uint32_t lbar = mapa_rank(full_bar(s), 0);
                     if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * tx);
-                    tma_load_3d_2sm(smem_base + a_off(s), &tmA, lbar, kb * Cfg::BK, m0 + shift, b);
-                    if (PRES) tma_load_3d_2sm(smem_base + alo_off(s), &tmAl, lbar, kb * Cfg::BK, m0 + shift, b);
+                    tma_load_3d_2sm(smem_base + a_off(s), &tmA, lbar, ak, arow, ab);
+                    if (PRES) tma_load_3d_2sm(smem_base + alo_off(s), &tmAl, lbar, ak, arow, ab);
                     tma_load_3d_2sm(smem_base + w_off(s), &tmWh, lbar, wk, wn, tap);
                     if (load_lo) tma_load_3d_2sm(smem_base + wlo_off(s), &tmWl, lbar, wk, wn, tap);
                 } else {
                     mbar_arrive_expect_tx(full_bar(s), tx);
                     // wgrad (split-K over rows): the split index selects a column range of ONE 2-D operand instead of a batch plane
                     if (p.w_k_batch_stride) tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK + b * p.w_k_batch_stride, m0, 0);
-                    else tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), kb * Cfg::BK, m0 + shift, b);
-                    if (PRES) tma_load_3d(smem_base + alo_off(s), &tmAl, full_bar(s), kb * Cfg::BK, m0 + shift, b);
+                    else tma_load_3d(smem_base + a_off(s), &tmA, full_bar(s), ak, arow, ab);
+                    if (PRES) tma_load_3d(smem_base + alo_off(s), &tmAl, full_bar(s), ak, arow, ab);
                     tma_load_3d(smem_base + w_off(s), &tmWh, full_bar(s), wk, wn, tap);
                     if (load_lo) tma_load_3d(smem_base + wlo_off(s), &tmWl, full_bar(s), wk, wn, tap);
                 }
@@ -875,23 +888,26 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     auto kern = gemm_tc_kernel<MODE, BN, EPI, OUTF, CTA2>;
     { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)Cfg::SMEM_BYTES, "cudaFuncSetAttribute(gemm_tc_kernel)"); if (rc_attr) return rc_attr; }
     CUtensorMap tmA, tmAl, tmWh, tmWl;
-    const uint64_t a_bs = (d.batch > 1 && !g_wgrad_kbs) ? (uint64_t)d.a_batch_stride : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
-    int rc = make_map(&tmA, d.a, g_wgrad_kbs ? (uint64_t)d.a_row_stride : (uint64_t)d.k, (uint64_t)d.a_rows,
-                      g_wgrad_kbs ? 1 : (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs, Cfg::BK, TC_BM, "A", P16 || PRES, P16);
+    const bool planes = d.a_planes > 0 && !g_wgrad_kbs;        // plane-major A: dims (a_plane_k, a_rows, a_planes)
+    const uint64_t a_bs = ((d.batch > 1 || planes) && !g_wgrad_kbs) ? (uint64_t)d.a_batch_stride : (uint64_t)d.a_rows * (uint64_t)d.a_row_stride;
+    const uint64_t a_d0 = planes ? (uint64_t)d.a_plane_k : (uint64_t)d.k, a_d2 = planes ? (uint64_t)d.a_planes : (uint64_t)d.batch;
+    int rc = make_map(&tmA, d.a, g_wgrad_kbs ? (uint64_t)d.a_row_stride : a_d0, (uint64_t)d.a_rows,
+                      g_wgrad_kbs ? 1 : a_d2, (uint64_t)d.a_row_stride, a_bs, Cfg::BK, TC_BM, "A", P16 || PRES, P16);
     if (rc) return rc;
     if (PRES) {     // low-half plane of the activations: same geometry
-        rc = make_map(&tmAl, d.a_lo, (uint64_t)d.k, (uint64_t)d.a_rows, (uint64_t)d.batch, (uint64_t)d.a_row_stride, a_bs, Cfg::BK, TC_BM,
+        rc = make_map(&tmAl, d.a_lo, a_d0, (uint64_t)d.a_rows, a_d2, (uint64_t)d.a_row_stride, a_bs, Cfg::BK, TC_BM,
                       "A_lo", true, false);
         if (rc) return rc;
     } else {
         tmAl = tmA;
     }
-    const uint64_t w_ts = (uint64_t)d.n * (uint64_t)d.ldw;
+    const int w_rows = (planes && d.n_half) ? 2 * d.n : d.n;        // n_half: the packed weight has 2 n rows per tap, one half per batch parity
+    const uint64_t w_ts = (uint64_t)w_rows * (uint64_t)d.ldw;
     const uint64_t w_k_extent = g_wgrad_kbs ? (uint64_t)d.ldw : (uint64_t)d.k;     // wgrad: W columns span every split
-    rc = make_map(&tmWh, d.w, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, Cfg::BK, Cfg::W_ROWS, "W", BF || P16, P16);
+    rc = make_map(&tmWh, d.w, w_k_extent, (uint64_t)w_rows, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, Cfg::BK, Cfg::W_ROWS, "W", BF || P16, P16);
     if (rc) return rc;
     if (X3) {
-        rc = make_map(&tmWl, d.w_lo, w_k_extent, (uint64_t)d.n, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, Cfg::W_ROWS, "W_lo", BF);
+        rc = make_map(&tmWl, d.w_lo, w_k_extent, (uint64_t)w_rows, (uint64_t)d.taps, (uint64_t)d.ldw, w_ts, TC_BK, Cfg::W_ROWS, "W_lo", BF);
         if (rc) return rc;
     } else {
         tmWl = tmWh;
@@ -909,6 +925,7 @@ static int launch_tc(const cum_gemm_desc& d, cudaStream_t st) {
     p.mn_splits = 0;
     p.aux = (OUTF == 0) ? d.aux : nullptr; p.aux_bs = d.aux_batch_stride; p.aux_rs = d.aux_row_stride;
     p.add_mask = (OUTF == 0 && d.addend_is_mask) ? 1 : 0;
+    p.a_plane_k = planes ? d.a_plane_k : 0; p.a_plane0 = d.a_plane0; p.a_plane_step = d.a_plane_step; p.n_half = (planes && d.n_half) ? 1 : 0;
     p.a_scale_ptr = (MODE == TC_F16X3) ? d.a_scale_dev : nullptr;
     p.acc_scale_ptr = (MODE == TC_F16X3 && d.a_scale_dev) ? d.a_scale_dev + 1 : nullptr;
     const long long total = (long long)p.batch * p.m_tiles * p.n_tiles;
@@ -1384,7 +1401,7 @@ int wgrad_tc_fwd(const cum_wgrad_desc& d, cudaStream_t st) {
 }
 
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
-    CUM_REQUIRE(d.a_row_stride >= d.k || d.a_rows == 1, "gemm_tc: a_row_stride < k");
+    CUM_REQUIRE(d.a_row_stride >= (d.a_planes > 0 ? d.a_plane_k : d.k) || d.a_rows == 1, "gemm_tc: a_row_stride < k");
     CUM_REQUIRE(!d.a_scale_dev || (d.math == CUM_MATH_F16X3 && !d.a_lo), "gemm_tc: a_scale_dev needs CUM_MATH_F16X3 with fp32 activations");
     CUM_REQUIRE(!d.addend_is_mask || (d.addend && !d.out_bf16 && !d.c_lo && !d.addend_lo && (d.epilogue == CUM_EPI_NONE || d.epilogue == CUM_EPI_RELU)),
                 "gemm_tc: addend_is_mask needs an fp32 addend / output and a NONE / RELU epilogue");
@@ -1399,6 +1416,11 @@ int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE((long long)d.m * d.c_row_stride < (1ll << 31) && (!d.addend || (long long)d.m * d.add_row_stride < (1ll << 29)),
                 "gemm_tc: one batch plane of the output / addend must span fewer than 2^31 elements (m=%d, c_row_stride=%lld)",
                 d.m, (long long)d.c_row_stride);
+    if (d.a_planes > 0) {
+        const int bk = d.math == CUM_MATH_BF16 ? 64 : TC_BK;
+        CUM_REQUIRE(d.a_plane_k > 0 && d.a_plane_k % bk == 0, "gemm_tc: plane-major a needs a_plane_k (= %d) to be a multiple of the K-block (%d elements)", d.a_plane_k, bk);
+        CUM_REQUIRE(!d.n_half || (d.n % 16 == 0 && !epi_is_glu(d.epilogue)), "gemm_tc: n_half needs n %% 16 == 0 and a non-GLU epilogue");
+    }
     const bool narrow = d.n <= 128;
     if (d.math == CUM_MATH_TF32X3) {
         CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: TF32X3 needs w_lo (see cum_split_tf32)");

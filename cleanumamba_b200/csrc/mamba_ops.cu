@@ -2,6 +2,9 @@
 // selective scan (fwd) with optional carried state.  All HBM / MUFU-bound CUDA-core kernels.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 #ifndef SCAN_T_UNROLL
 #define SCAN_T_UNROLL 1   // time-loop unroll of the scan recurrence (2 trades occupancy for ILP)
 #endif
@@ -105,7 +108,8 @@ __device__ __forceinline__ float4 f4_fma(float4 w, float4 x, float4 a) {
 
 __global__ void __launch_bounds__(128) dwconv_silu_kernel(const float* __restrict__ x, long long x_bs, long long x_rs,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
-                                                           float* __restrict__ y, const float* __restrict__ state,
+                                                           float* __restrict__ y, long long y_bs, long long y_rs,
+                                                           const float* __restrict__ state, float* __restrict__ state_out,
                                                            int len, int d_pad, int width) {
     pdl_trigger();
     pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
@@ -151,10 +155,17 @@ __global__ void __launch_bounds__(128) dwconv_silu_kernel(const float* __restric
                 acc = f4_fma(wv[k], win[k], acc);  // tap k multiplies x[t - (W-1) + k]
             }
             float4 o = make_float4(siluf_(acc.x), siluf_(acc.y), siluf_(acc.z), siluf_(acc.w));
-            *reinterpret_cast<float4*>(y + ((long long)b * len + tb + i) * d_pad + c4 * 4) = o;
+            *reinterpret_cast<float4*>(y + (long long)b * y_bs + (long long)(tb + i) * y_rs + c4 * 4) = o;
 #pragma unroll
             for (int j = 0; j < DW_MAXW - 1; ++j) win[j] = win[j + 1];
         }
+    }
+    // single-tile problems (streaming: a few tokens per call) update the carried state here: the window now holds the last
+    // W-1 inputs (older entries from the previous state when len < W-1); this thread is the only reader of these state entries
+    if (state_out) {
+#pragma unroll
+        for (int j = 0; j < DW_MAXW - 1; ++j)
+            *reinterpret_cast<float4*>(state_out + ((long long)b * (DW_MAXW - 1) + j) * d_pad + c4 * 4) = win[j];
     }
 }
 
@@ -185,7 +196,9 @@ __global__ void dwconv_state_kernel(const float* __restrict__ x, long long x_bs,
 
 int dwconv_silu_fwd(const float* x, long long x_bs, long long x_rs, const float* w, const float* bias, float* y,
                     const float* conv_state, float* conv_state_out, int batch, int len, int d_pad, int width,
-                    cudaStream_t st) {
+                    cudaStream_t st, long long y_bs, long long y_rs) {
+    if (y_bs == 0 && y_rs == 0) { y_bs = (long long)len * d_pad; y_rs = d_pad; }
+    CUM_REQUIRE(y_bs % 4 == 0 && y_rs % 4 == 0, "dwconv_silu: output strides must be multiples of 4 elements");
     CUM_REQUIRE(x && w && bias && y, "dwconv_silu: null pointer");
     CUM_REQUIRE(batch > 0 && len > 0 && d_pad > 0 && d_pad % 4 == 0, "dwconv_silu: bad shape");
     CUM_REQUIRE(width >= 1 && width <= DW_MAXW, "dwconv_silu: width=%d unsupported (1..4)", width);
@@ -194,10 +207,12 @@ int dwconv_silu_fwd(const float* x, long long x_bs, long long x_rs, const float*
     CUM_REQUIRE(batch <= 65535, "dwconv_silu: batch too large");
     dim3 grid((unsigned)cdiv(d_pad / 4, 128), (unsigned)cdiv(len, DW_T), (unsigned)batch);
     CUM_REQUIRE(width == DW_MAXW, "dwconv_silu: only width 4 is instantiated (d_conv=4, CleanUMamba.py:143)");
-    cudaError_t e = launch_kernel(dwconv_silu_kernel, grid, dim3(128), 0, st, x, x_bs, x_rs, w, bias, y, conv_state, len, d_pad, width);
+    const bool fused_state = conv_state_out && len <= DW_T;      // one time tile per (stream, channel): the kernel writes the new state itself
+    cudaError_t e = launch_kernel(dwconv_silu_kernel, grid, dim3(128), 0, st, x, x_bs, x_rs, w, bias, y, y_bs, y_rs, conv_state,
+                                  fused_state ? conv_state_out : (float*)nullptr, len, d_pad, width);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(dwconv_silu_kernel)");
     CUM_LAUNCH_CHECK("dwconv_silu_kernel");
-    if (conv_state_out) {
+    if (conv_state_out && !fused_state) {
         dim3 g2((unsigned)cdiv(d_pad, 128), (unsigned)batch);
         e = launch_kernel(dwconv_state_kernel, g2, dim3(128), 0, st, x, x_bs, x_rs, conv_state, conv_state_out, len, d_pad, width);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(dwconv_state_kernel)");
@@ -495,58 +510,103 @@ __global__ void __launch_bounds__(CH* SL, (CH * SL >= 256) ? 3 : 4) selective_sc
 // coalesced), loops over the tokens, and the 16 lanes reduce <h, C_t> with shuffles.  No shared memory, 11 registers of
 // state: occupancy hides the latency that bounded the chunked kernel (2.0 ms per layer at 4096 streams x 1 token).
 // ---------------------------------------------------------------------------------------------------------
-template <int T>      // tokens per call (compile-time: every token's inputs are requested before the dependent recurrence starts)
+// CPT channels per thread (independent 16-byte state loads in flight per thread: one load per thread left the kernel at 80 % of the
+// copy bandwidth); H16: the carried state is stored as fp16 (reduced-precision streaming state, half the traffic; recurrence in fp32)
+template <int T, int CPT, bool H16>      // tokens per call (compile-time: every token's inputs are requested before the dependent recurrence starts)
 __global__ void __launch_bounds__(256) selective_scan_step_kernel(const cum_scan_desc p) {
     pdl_trigger();
     pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
 
     const int b = blockIdx.y;
     const int g = threadIdx.x & 15;
-    const int c = blockIdx.x * 16 + (threadIdx.x >> 4);         // d % 16 == 0 (host check): whole 16-lane groups stay or leave
-    if (c >= p.d) return;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p.a2 + (long long)c * 64) + g);
-    const long long hoff = ((long long)b * p.d + c) * 64;
-    float4 h = p.h0 ? *(reinterpret_cast<const float4*>(p.h0 + hoff) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float bias = p.delta_bias ? __ldg(p.delta_bias + c) : 0.f;
-    const float dk = p.Dskip ? __ldg(p.Dskip + c) : 0.f;
-    const float* ub = p.u + (long long)b * p.u_bs + c;
-    const float* db = p.delta + (long long)b * p.dl_bs + c;
-    const float* zb = p.z ? p.z + (long long)b * p.z_bs + c : nullptr;
-    const float* Bb = p.Bm + (long long)b * p.B_bs + 4 * g;
-    const float* Cb = p.Cm + (long long)b * p.C_bs + 4 * g;
-    float dlv[T], uv[T], zv[T];
+    const int cbase = blockIdx.x * (16 * CPT) + (threadIdx.x >> 4);      // d % (16 CPT) == 0 (host check): whole 16-lane groups stay or leave
+    if (cbase >= p.d) return;
+    float4 a[CPT], h[CPT];
+    float bias[CPT], dk[CPT];
+    float dlv[CPT][T], uv[CPT][T], zv[CPT][T];
     float4 bvv[T], cvv[T];
 #pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+        const int c = cbase + 16 * q;
+        const long long hoff = ((long long)b * p.d + c) * 64;
+        if (!p.h0) h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        else if (H16) {
+            const uint2 raw = *(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.h0) + hoff) + g);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            h[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else h[q] = *(reinterpret_cast<const float4*>(p.h0 + hoff) + g);
+    }
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+        const int c = cbase + 16 * q;
+        a[q] = __ldg(reinterpret_cast<const float4*>(p.a2 + (long long)c * 64) + g);
+        bias[q] = p.delta_bias ? __ldg(p.delta_bias + c) : 0.f;
+        dk[q] = p.Dskip ? __ldg(p.Dskip + c) : 0.f;
+        const float* ub = p.u + (long long)b * p.u_bs + c;
+        const float* db = p.delta + (long long)b * p.dl_bs + c;
+        const float* zb = p.z ? p.z + (long long)b * p.z_bs + c : nullptr;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            dlv[q][t] = db[(long long)t * p.dl_rs];
+            uv[q][t] = ub[(long long)t * p.u_rs];
+            zv[q][t] = zb ? zb[(long long)t * p.z_rs] : 0.f;
+        }
+    }
+    const float* Bb = p.Bm + (long long)b * p.B_bs + 4 * g;
+    const float* Cb = p.Cm + (long long)b * p.C_bs + 4 * g;
+#pragma unroll
     for (int t = 0; t < T; ++t) {
-        dlv[t] = db[(long long)t * p.dl_rs];
-        uv[t] = ub[(long long)t * p.u_rs];
-        zv[t] = zb ? zb[(long long)t * p.z_rs] : 0.f;
         bvv[t] = *reinterpret_cast<const float4*>(Bb + (long long)t * p.B_rs);
         cvv[t] = *reinterpret_cast<const float4*>(Cb + (long long)t * p.C_rs);
     }
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-        float dl = dlv[t] + bias;
-        if (p.delta_softplus) dl = softplusf_(dl);
-        const float u = uv[t];
-        const float du = dl * u;
-        const float4 bv = bvv[t], cv = cvv[t];
-        h.x = fmaf(ex2_approx(dl * a.x), h.x, du * bv.x);
-        h.y = fmaf(ex2_approx(dl * a.y), h.y, du * bv.y);
-        h.z = fmaf(ex2_approx(dl * a.z), h.z, du * bv.z);
-        h.w = fmaf(ex2_approx(dl * a.w), h.w, du * bv.w);
-        float part = fmaf(h.x, cv.x, fmaf(h.y, cv.y, fmaf(h.z, cv.z, h.w * cv.w)));
-        part += __shfl_xor_sync(0xffffffffu, part, 8);
-        part += __shfl_xor_sync(0xffffffffu, part, 4);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        if (g == 0) {
-            float yv = fmaf(dk, u, part);
-            if (zb) yv *= __fdividef(zv[t], 1.0f + __expf(-zv[t]));
-            p.y[(long long)b * p.y_bs + (long long)t * p.y_rs + c] = yv;
+    for (int q = 0; q < CPT; ++q) {
+        const int c = cbase + 16 * q;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            float dl = dlv[q][t] + bias[q];
+            if (p.delta_softplus) dl = softplusf_(dl);
+            const float u = uv[q][t];
+            const float du = dl * u;
+            const float4 bv = bvv[t], cv = cvv[t];
+            h[q].x = fmaf(ex2_approx(dl * a[q].x), h[q].x, du * bv.x);
+            h[q].y = fmaf(ex2_approx(dl * a[q].y), h[q].y, du * bv.y);
+            h[q].z = fmaf(ex2_approx(dl * a[q].z), h[q].z, du * bv.z);
+            h[q].w = fmaf(ex2_approx(dl * a[q].w), h[q].w, du * bv.w);
+            float part = fmaf(h[q].x, cv.x, fmaf(h[q].y, cv.y, fmaf(h[q].z, cv.z, h[q].w * cv.w)));
+            part += __shfl_xor_sync(0xffffffffu, part, 8);
+            part += __shfl_xor_sync(0xffffffffu, part, 4);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            if (g == 0) {
+                float yv = fmaf(dk[q], u, part);
+                if (p.z) yv *= __fdividef(zv[q][t], 1.0f + __expf(-zv[q][t]));
+                p.y[(long long)b * p.y_bs + (long long)t * p.y_rs + c] = yv;
+            }
+        }
+        if (p.h_out) {
+            const long long hoff = ((long long)b * p.d + c) * 64;
+            if (H16) {
+                const __half2 lo = __floats2half2_rn(h[q].x, h[q].y), hi = __floats2half2_rn(h[q].z, h[q].w);
+                *(reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.h_out) + hoff) + g) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+            } else *(reinterpret_cast<float4*>(p.h_out + hoff) + g) = h[q];
         }
     }
-    if (p.h_out) *(reinterpret_cast<float4*>(p.h_out + hoff) + g) = h;
+}
+
+template <int T, bool H16>
+static cudaError_t launch_step(const cum_scan_desc& d, cudaStream_t st) {
+    // channels per thread = independent 16-byte (fp32 state) / 8-byte (fp16 state) loads in flight per thread.
+    // CUM_SCAN_STEP_CPT=1|2|4 overrides (A/B measurements); default 2, and 4 for the fp16 state (half the bytes per load)
+    static int cpt_env = -1;
+    if (cpt_env < 0) { const char* e = getenv("CUM_SCAN_STEP_CPT"); cpt_env = e ? atoi(e) : 0; }
+    int cpt = cpt_env > 0 ? cpt_env : (H16 ? 4 : 2);
+    while (cpt > 1 && d.d % (16 * cpt)) cpt >>= 1;
+    const dim3 grid((unsigned)(d.d / (16 * cpt)), (unsigned)d.batch);
+    if (cpt >= 4) return launch_kernel(selective_scan_step_kernel<T, 4, H16>, grid, dim3(256), 0, st, d);
+    if (cpt == 2) return launch_kernel(selective_scan_step_kernel<T, 2, H16>, grid, dim3(256), 0, st, d);
+    return launch_kernel(selective_scan_step_kernel<T, 1, H16>, grid, dim3(256), 0, st, d);
 }
 
 template <int NS, int SL, int CH, int TC>
@@ -630,11 +690,26 @@ int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.n_state <= 64, "selective_scan: n_state=%d > 64 not supported", d.n_state);
     const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     // measured at 4096 streams (3 layers): 1 token 2.5 ms vs 6.0 ms chunked, 2 tokens 4.1 vs 6.2, 4 tokens 7.3 vs 6.4 -> up to 2 tokens
-    if (d.len <= 2 && d.n_state == 64 && d.d % 16 == 0 && (d.h0 || d.h_out) && !d.h_ckpt && al16(d.a2) && al16(d.Bm) && al16(d.Cm) &&
-        (!d.h0 || al16(d.h0)) && (!d.h_out || al16(d.h_out)) && (d.B_rs | d.C_rs | d.B_bs | d.C_bs) % 4 == 0) {
-        dim3 grid((unsigned)(d.d / 16), (unsigned)d.batch);
-        cudaError_t e = d.len == 1 ? launch_kernel(selective_scan_step_kernel<1>, grid, dim3(256), 0, st, d)
-                                   : launch_kernel(selective_scan_step_kernel<2>, grid, dim3(256), 0, st, d);
+    const bool step_ok = d.n_state == 64 && d.d % 16 == 0 && (d.h0 || d.h_out) && !d.h_ckpt && al16(d.a2) && al16(d.Bm) && al16(d.Cm) &&
+                         (!d.h0 || al16(d.h0)) && (!d.h_out || al16(d.h_out)) && (d.B_rs | d.C_rs | d.B_bs | d.C_bs) % 4 == 0;
+    if (d.state_f16) {
+        // reduced-precision carried state (streaming variant, reported separately): fp16 storage, fp32 recurrence; only the step kernel
+        // reads / writes it, longer calls advance two tokens per launch
+        CUM_REQUIRE(step_ok && d.h0 && d.h_out, "selective_scan: state_f16 needs n_state = 64, d %% 16 == 0, aligned operands and both h0 and h_out");
+        cum_scan_desc s = d;
+        for (int t = 0; t < d.len; t += 2) {
+            const int n = d.len - t >= 2 ? 2 : 1;
+            s.len = n;
+            s.u = d.u + (long long)t * d.u_rs; s.delta = d.delta + (long long)t * d.dl_rs; s.z = d.z ? d.z + (long long)t * d.z_rs : nullptr;
+            s.Bm = d.Bm + (long long)t * d.B_rs; s.Cm = d.Cm + (long long)t * d.C_rs; s.y = d.y + (long long)t * d.y_rs;
+            if (t > 0) s.h0 = d.h_out;
+            cudaError_t e = n == 1 ? launch_step<1, true>(s, st) : launch_step<2, true>(s, st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_step_kernel, fp16 state)");
+        }
+        return CUM_OK;
+    }
+    if (d.len <= 2 && step_ok) {
+        cudaError_t e = d.len == 1 ? launch_step<1, false>(d, st) : launch_step<2, false>(d, st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_step_kernel)");
         return CUM_OK;
     }

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        float* __restrict__ y, void* __restrict__ y_lo, int rows_out, int c_pad, int kernel,
                                                        int stride, const float* __restrict__ in_scale, int scale_groups,
-                                                       int group_rows, int row_offset) {
+                                                       int group_rows, int row_offset, long long y_bs, long long y_rs) {
     pdl_trigger();
     pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
 
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
             acc.z = fmaf(wv.z, xv, acc.z); acc.w = fmaf(wv.w, xv, acc.w);
         }
         acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-        store4<OUTF>(y, y_lo, ((long long)b * rows_out + t0 + t) * c_pad + 4 * c4, acc);
+        store4<OUTF>(y, y_lo, (long long)b * y_bs + (long long)(t0 + t) * y_rs + 4 * c4, acc);
     }
 }
 
@@ -252,7 +252,10 @@ __global__ void __launch_bounds__(256) conv_in_c64_kernel(const float* __restric
 
 int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
                 float* y, int rows_out, int c_pad, int kernel, int stride, const float* in_scale, int group_rows,
-                int row_offset, cudaStream_t st, int out_fmt, void* y_lo) {
+                int row_offset, cudaStream_t st, int out_fmt, void* y_lo, long long y_bs, long long y_rs) {
+    const bool strided = y_bs != 0 || y_rs != 0;       // streaming (time-major): y[b, t, :] at y + b * y_bs + t * y_rs
+    if (!strided) { y_bs = (long long)rows_out * c_pad; y_rs = c_pad; }
+    CUM_REQUIRE(y_bs % 4 == 0 && y_rs % 4 == 0, "conv_in: output strides must be multiples of 4 elements");
     CUM_REQUIRE(out_fmt != 2 || (y_lo && aligned16(y_lo)), "conv_in: hi/lo output needs a 16-byte aligned y_lo");
     CUM_REQUIRE(x && w && bias && y, "conv_in: null pointer");
     CUM_REQUIRE(batch > 0 && length > 0 && rows_out > 0, "conv_in: empty problem");
@@ -260,7 +263,7 @@ int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const
     CUM_REQUIRE(kernel >= 1 && kernel <= CI_MAXK && stride >= 1 && stride <= kernel, "conv_in: kernel=%d stride=%d unsupported", kernel, stride);
     CUM_REQUIRE(aligned16(w) && aligned16(bias) && aligned16(y), "conv_in: w/bias/y must be 16-byte aligned");
     CUM_REQUIRE(!in_scale || group_rows > 0, "conv_in: group_rows must be positive when in_scale is given");
-    if (c_pad == 64 && kernel == 4 && stride == 2 && !in_scale && batch <= 65535) {
+    if (c_pad == 64 && kernel == 4 && stride == 2 && !in_scale && batch <= 65535 && !strided) {
         dim3 gridf((unsigned)cdiv(rows_out, CIF_ROWS), batch);
         if (out_fmt == 2) conv_in_c64_kernel<2><<<gridf, 256, 0, st>>>(x, x_stride, length, w, bias, y, y_lo, rows_out);
         else if (out_fmt == 1) conv_in_c64_kernel<1><<<gridf, 256, 0, st>>>(x, x_stride, length, w, bias, y, y_lo, rows_out);
@@ -271,10 +274,66 @@ int conv_in_fwd(const float* x, long long x_stride, int batch, int length, const
     dim3 grid((unsigned)cdiv(rows_out, CI_ROWS), batch);
     const size_t smem = (size_t)(CI_ROWS * stride + kernel) * sizeof(float);
     const int groups = in_scale ? (int)cdiv(max(1, rows_out + row_offset), group_rows) : 0;
-#define CI_LAUNCH(F) conv_in_kernel<F><<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, y_lo, rows_out, c_pad, kernel, stride, in_scale, groups, group_rows, row_offset)
+#define CI_LAUNCH(F) conv_in_kernel<F><<<grid, 256, smem, st>>>(x, x_stride, length, w, bias, y, y_lo, rows_out, c_pad, kernel, stride, in_scale, groups, group_rows, row_offset, y_bs, y_rs)
     if (out_fmt == 2) CI_LAUNCH(2); else if (out_fmt == 1) CI_LAUNCH(1); else CI_LAUNCH(0);
 #undef CI_LAUNCH
     CUM_LAUNCH_CHECK("conv_in_kernel");
+    return CUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stream_shift: end-of-call FIFO maintenance of the time-major streaming session -- every carried buffer (pending samples, the
+// encoder levels' unconsumed columns, the decoder levels' carried GLU column) moves its unconsumed tail to the front, ALL of them
+// in one launch (the round-1 session did this with ~30 torch copy / cat / clone kernels per call).  Entry: for every row r < rows,
+// base[r * row_stride + i] = base[r * row_stride + src_off + i], i < count.  Source and destination may overlap (src_off < count):
+// positions congruent modulo src_off form independent chains, one thread walks one chain front to back.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SHIFT_MAX_ENTRIES = 24;
+struct StreamShiftTable { StreamShiftEntry e[SHIFT_MAX_ENTRIES]; };
+
+template <typename V>
+__device__ __forceinline__ void shift_entry(const StreamShiftEntry& e, long long first, long long step) {
+    constexpr int W = sizeof(V) / 4;
+    const long long s = e.src_off / W, n = e.count / W;
+    const long long par = s < n ? s : n;                 // independent chains per row
+    const long long total = par * e.rows;
+    for (long long w = first; w < total; w += step) {
+        const long long r = w / par, j = w - r * par;
+        V* row = reinterpret_cast<V*>(e.base + r * e.row_stride);
+        for (long long i = j; i < n; i += s) row[i] = row[i + s];
+    }
+}
+
+__global__ void __launch_bounds__(256) stream_shift_kernel(const StreamShiftTable tab) {
+    pdl_trigger();
+    pdl_wait();
+    const StreamShiftEntry& e = tab.e[blockIdx.y];
+    if (e.count <= 0 || e.src_off <= 0) return;
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+    const bool v4 = ((e.src_off | e.count | e.row_stride) & 3) == 0 && (reinterpret_cast<uintptr_t>(e.base) & 15) == 0;
+    if (v4) shift_entry<float4>(e, first, step); else shift_entry<float>(e, first, step);
+}
+
+int stream_shift_fwd(const StreamShiftEntry* entries, int n_entries, cudaStream_t st) {
+    CUM_REQUIRE(entries && n_entries > 0 && n_entries <= SHIFT_MAX_ENTRIES, "stream_shift: 1..%d entries", SHIFT_MAX_ENTRIES);
+    StreamShiftTable tab;
+    memset(&tab, 0, sizeof(tab));
+    long long most = 0;
+    for (int i = 0; i < n_entries; ++i) {
+        const StreamShiftEntry& e = entries[i];
+        CUM_REQUIRE(e.count == 0 || (e.base && e.rows > 0 && e.src_off >= 0 && e.count > 0), "stream_shift: bad entry %d", i);
+        tab.e[i] = e;
+        const long long par = (e.src_off < e.count ? e.src_off : e.count) * (long long)e.rows;
+        if (par > most) most = par;
+    }
+    if (most == 0) return CUM_OK;
+    long long blocks = cdiv(cdiv(most, 4), 256);
+    const long long cap = 8LL * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    cudaError_t e = launch_kernel(stream_shift_kernel, dim3((unsigned)blocks, (unsigned)n_entries), dim3(256), 0, st, tab);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(stream_shift_kernel)");
+    CUM_LAUNCH_CHECK("stream_shift_kernel");
     return CUM_OK;
 }
 
@@ -291,7 +350,8 @@ __global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict_
                                                          const float* __restrict__ w, float bias,
                                                          const float* __restrict__ scale, int scale_groups,
                                                          int scale_group, float* __restrict__ out, long long out_stride,
-                                                         int first, int length, int kernel, int stride, int halo) {
+                                                         int first, int length, int kernel, int stride, int halo,
+                                                         long long g_bs, long long g_rs) {
     pdl_trigger();
     pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
 
@@ -311,8 +371,8 @@ __global__ void __launch_bounds__(256) convt_out_kernel(const float* __restrict_
 #pragma unroll
         for (int k = 0; k < CT_MAXK; ++k) acc[k] = 0.f;
         if (r < nrows && j >= 0 && j < rows_in) {
-            const float4* row = reinterpret_cast<const float4*>(g + ((long long)b * rows_in + j) * c_pad);
-            const uint2* row16 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g) + ((long long)b * rows_in + j) * c_pad);
+            const float4* row = reinterpret_cast<const float4*>(g + (long long)b * g_bs + (long long)j * g_rs);
+            const uint2* row16 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g) + (long long)b * g_bs + (long long)j * g_rs);
             for (int c4 = sub; c4 < c4n; c4 += LPR) {
                 float4 v;
                 if (IN16) {
@@ -365,7 +425,7 @@ template <bool IN16>
 __global__ void __launch_bounds__(256) convt_out_c64_kernel(const float* __restrict__ g, int rows_in, const float* __restrict__ w,
                                                              float bias, const float* __restrict__ scale, int scale_groups,
                                                              int scale_group, float* __restrict__ out, long long out_stride,
-                                                             int first, int length) {
+                                                             int first, int length, long long g_bs, long long g_rs) {
     pdl_trigger();
     pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
 
@@ -387,12 +447,12 @@ __global__ void __launch_bounds__(256) convt_out_c64_kernel(const float* __restr
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j >= 0 && j < rows_in) {
                 if (IN16) {
-                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g) + ((long long)b * rows_in + j) * 64) + sub);
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g) + (long long)b * g_bs + (long long)j * g_rs) + sub);
                     const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
                     const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
                     v[u] = make_float4(a.x, a.y, c.x, c.y);
                 } else {
-                    v[u] = __ldg(reinterpret_cast<const float4*>(g + ((long long)b * rows_in + j) * 64) + sub);
+                    v[u] = __ldg(reinterpret_cast<const float4*>(g + (long long)b * g_bs + (long long)j * g_rs) + sub);
                 }
             }
         }
@@ -429,7 +489,9 @@ __global__ void __launch_bounds__(256) convt_out_c64_kernel(const float* __restr
 
 int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float* w, float bias,
                   const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
-                  int kernel, int stride, cudaStream_t st, bool in_bf16) {
+                  int kernel, int stride, cudaStream_t st, bool in_bf16, long long g_bs, long long g_rs) {
+    if (g_bs == 0 && g_rs == 0) { g_bs = (long long)rows_in * c_pad; g_rs = c_pad; }    // streaming (time-major): g[b, j, :] at g + b * g_bs + j * g_rs
+    CUM_REQUIRE(g_bs % 4 == 0 && g_rs % 4 == 0, "convt_out: input strides must be multiples of 4 elements");
     CUM_REQUIRE(g && w && out, "convt_out: null pointer");
     CUM_REQUIRE(batch > 0 && batch <= 65535 && rows_in > 0 && length > 0 && first >= 0, "convt_out: empty problem");
     CUM_REQUIRE(c_pad > 0 && c_pad % 4 == 0, "convt_out: c_pad=%d must be a positive multiple of 4", c_pad);
@@ -443,14 +505,14 @@ int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float
     const int groups = scale ? (int)cdiv(length, scale_group) : 0;
     if (c_pad == 64 && kernel == 4 && stride == 2) {
         dim3 gridf((unsigned)cdiv(length, (long long)CTF_ROWS * 2), batch);
-        if (in_bf16) convt_out_c64_kernel<true><<<gridf, 256, 0, st>>>(g, rows_in, w, bias, scale, groups, scale_group, out, out_stride, first, length);
-        else convt_out_c64_kernel<false><<<gridf, 256, 0, st>>>(g, rows_in, w, bias, scale, groups, scale_group, out, out_stride, first, length);
+        if (in_bf16) convt_out_c64_kernel<true><<<gridf, 256, 0, st>>>(g, rows_in, w, bias, scale, groups, scale_group, out, out_stride, first, length, g_bs, g_rs);
+        else convt_out_c64_kernel<false><<<gridf, 256, 0, st>>>(g, rows_in, w, bias, scale, groups, scale_group, out, out_stride, first, length, g_bs, g_rs);
         CUM_LAUNCH_CHECK("convt_out_c64_kernel");
         return CUM_OK;
     }
     dim3 grid((unsigned)cdiv(length, (long long)CT_ROWS * stride), batch);
     const size_t smem = (size_t)(CT_ROWS + halo + 1) * kernel * sizeof(float);
-#define CT_LAUNCH(L, I) convt_out_kernel<L, I><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, groups, scale_group, out, out_stride, first, length, kernel, stride, halo)
+#define CT_LAUNCH(L, I) convt_out_kernel<L, I><<<grid, 256, smem, st>>>(g, rows_in, c_pad, w, bias, scale, groups, scale_group, out, out_stride, first, length, kernel, stride, halo, g_bs, g_rs)
     if (c_pad <= 64) { if (in_bf16) CT_LAUNCH(16, true); else CT_LAUNCH(16, false); }
     else             { if (in_bf16) CT_LAUNCH(32, true); else CT_LAUNCH(32, false); }
 #undef CT_LAUNCH

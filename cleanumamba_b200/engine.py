@@ -289,8 +289,13 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------ op wrappers
     def gemm(self, a, a_off, a_bs, a_rs, a_rows, k, w, bias, c, c_off, c_bs, c_rs, m, n, batch, epi,
-             taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None, a_scale=None, aux=None, aux_bs=0, aux_rs=0, addend_mask=False):
+             taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None, a_scale=None, aux=None, aux_bs=0, aux_rs=0, addend_mask=False,
+             planes=None, add_off=0):
+        """``planes`` = (a_planes, a_plane_k, a_plane0, a_plane_step, n_half): plane-major ``a`` (cum_gemm_desc.a_planes; the time-major
+        streaming session).  ``add_off``: element offset into ``addend``."""
         d = GemmDesc()
+        if planes is not None:
+            d.a_planes, d.a_plane_k, d.a_plane0, d.a_plane_step, d.n_half = planes
         d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k = a.data_ptr() + a.element_size() * a_off, a_bs, a_rs, a_rows, k
         # "hl16" tensors (dtype float16, leading dimension 2 = [hi plane, lo plane], see cum_gemm_desc.a_lo): pre-split activations
         if a.dtype == torch.float16:
@@ -317,6 +322,8 @@ class Engine:
         d.c, d.c_batch_stride, d.c_row_stride, d.m, d.n, d.batch = c.data_ptr() + c.element_size() * c_off, c_bs, c_rs, m, n, batch
         d.epilogue = epi
         d.addend, d.add_batch_stride, d.add_row_stride = ptr(addend), add_bs, add_rs
+        if addend is not None and add_off:
+            d.addend = addend.data_ptr() + addend.element_size() * add_off
         d.addend_is_mask = 1 if (addend_mask and addend is not None) else 0
         if a_scale is not None and d.math == _lib.MATH_F16X3 and a.dtype == torch.float32:
             d.a_scale_dev = a_scale.data_ptr()          # device-side power-of-two scale of a gradient operand (TrainEngine)
@@ -326,11 +333,11 @@ class Engine:
         self._call(kind, self.lib.cum_gemm_bias_act_fwd, C.byref(d), _lib.stream_ptr(),
                    flops=2 * batch * m * n * k * taps)
 
-    def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None, out_dtype=torch.float32, aux=None):
+    def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None, out_dtype=torch.float32, aux=None, out_off=0):
         """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers.  ``aux`` (rows, n): the pre-activation (training)."""
         n_out = n // 2 if epi >= 8 else n
         c = out if out is not None else self.act_buffer(rows, n_out, out_dtype, a.device)
-        self.gemm(a, a_off, 0, k if a_rs is None else a_rs, rows, k, w, bias, c, 0, 0, n_out, rows, n, 1, epi,
+        self.gemm(a, a_off, 0, k if a_rs is None else a_rs, rows, k, w, bias, c, out_off, 0, n_out, rows, n, 1, epi,
                   addend=addend, add_bs=0, add_rs=n_out, aux=aux, aux_rs=n)
         return c
 
@@ -346,23 +353,28 @@ class Engine:
                    ptr(be), eps, rows, c, c_p, _lib.stream_ptr(),
                    nbytes=4 * rows * c * (2 + (res_in is not None) + (res_out is not None)))
 
-    def fill_scan(self, s, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None, h_ckpt=None):
-        """Fill a cum_scan_desc for Mamba layer ``l`` operating on the engine's channels-last buffers."""
+    def fill_scan(self, s, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None, h_ckpt=None, tm=False):
+        """Fill a cum_scan_desc for Mamba layer ``l`` operating on the engine's channels-last buffers.  ``tm``: the rows are
+        time-major (token t of stream b is row t * B + b: the streaming session for many streams) instead of (b, t)."""
         di_p, N_p, R_p = mm["di_p"], mm["N_p"], mm["R_p"]
-        s.u, s.u_bs, s.u_rs = u.data_ptr(), T * di_p, di_p
-        s.delta, s.dl_bs, s.dl_rs = dt.data_ptr(), T * di_p, di_p
-        s.z, s.z_bs, s.z_rs = xz.data_ptr() + 4 * di_p, T * 2 * di_p, 2 * di_p
         ld = R_p + 2 * N_p
-        s.Bm, s.B_bs, s.B_rs = xdbl.data_ptr() + 4 * R_p, T * ld, ld
-        s.Cm, s.C_bs, s.C_rs = xdbl.data_ptr() + 4 * (R_p + N_p), T * ld, ld
-        s.y, s.y_bs, s.y_rs = ptr(y), T * di_p, di_p
+
+        def strides(width):            # (batch stride, row stride) of a (rows, width) array
+            return (width, B * width) if tm else (T * width, width)
+        s.u, (s.u_bs, s.u_rs) = u.data_ptr(), strides(di_p)
+        s.delta, (s.dl_bs, s.dl_rs) = dt.data_ptr(), strides(di_p)
+        s.z, (s.z_bs, s.z_rs) = xz.data_ptr() + 4 * di_p, strides(2 * di_p)
+        s.Bm, (s.B_bs, s.B_rs) = xdbl.data_ptr() + 4 * R_p, strides(ld)
+        s.Cm, (s.C_bs, s.C_rs) = xdbl.data_ptr() + 4 * (R_p + N_p), strides(ld)
+        s.y, (s.y_bs, s.y_rs) = ptr(y), strides(di_p)
         s.a2, s.Dskip, s.delta_bias = self.pk[f"m{l}.a2"].data_ptr(), self.pk[f"m{l}.D"].data_ptr(), self.pk[f"m{l}.dtb"].data_ptr()
         s.h0, s.h_out, s.h_ckpt = ptr(h0), ptr(h_out), ptr(h_ckpt)
+        s.state_f16 = 1 if (h0 is not None and h0.dtype == torch.float16) else 0
         s.batch, s.len, s.d, s.n_state, s.delta_softplus = B, T, di_p, N_p, 1
 
-    def scan(self, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None, h_ckpt=None):
+    def scan(self, u, dt, xz, xdbl, y, l, mm, B, T, h0=None, h_out=None, h_ckpt=None, tm=False):
         s = ScanDesc()
-        self.fill_scan(s, u, dt, xz, xdbl, y, l, mm, B, T, h0, h_out, h_ckpt)
+        self.fill_scan(s, u, dt, xz, xdbl, y, l, mm, B, T, h0, h_out, h_ckpt, tm=tm)
         ws = None
         if h_ckpt is None and T >= 256:        # small batches of long clips: segment-parallel scan (scratch from the caching allocator)
             from .ops import scan_workspace
@@ -372,9 +384,10 @@ class Engine:
                    nbytes=4 * B * T * (4 * mm["di"] + 2 * mm["N"]), flops=B * T * mm["di"] * mm["N"], launches=1 if ws is None else 3)
         del ws
 
-    def mamba_layers(self, h, B, T, states=None):
+    def mamba_layers(self, h, B, T, states=None, tm=False):
         """h: (B*T, dm_p) output of tsfm_conv1 -> normed (B*T, dm_p) after norm_f.  ``states``: optional list of
-        (conv_state (B, W-1, di_p), ssm_state (B, di_p, N_p)) carried in place (streaming)."""
+        (conv_state (B, W-1, di_p), ssm_state (B, di_p, N_p)) carried in place (streaming; an fp16 ssm_state selects the
+        reduced-precision state variant).  ``tm``: rows are time-major (t * B + b) instead of (b * T + t)."""
         pk, meta = self.pk, self.meta
         dm, dm_p = meta["dm"], meta["dm_p"]
         rows = B * T
@@ -389,14 +402,20 @@ class Engine:
             xz = self.dense(hn, rows, dm_p, f"m{l}.in", None, 2 * di_p)
             xc = torch.empty(rows, di_p, dtype=torch.float32, device=dev)
             cs = states[l][0] if states is not None else None
-            self._call("dwconv_silu", self.lib.cum_dwconv_silu_fwd, xz.data_ptr(), T * 2 * di_p, 2 * di_p,
-                       pk[f"m{l}.cw"].data_ptr(), pk[f"m{l}.cb"].data_ptr(), xc.data_ptr(), ptr(cs), ptr(cs), B, T, di_p,
-                       mm["W"], _lib.stream_ptr(), launches=1 + (cs is not None), nbytes=8 * rows * mm["di"])
+            n_l = 1 + (cs is not None and T > 16)      # up to 16 tokens the kernel writes the new conv state itself
+            if tm:
+                self._call("dwconv_silu", self.lib.cum_dwconv_silu_strided_fwd, xz.data_ptr(), 2 * di_p, B * 2 * di_p,
+                           pk[f"m{l}.cw"].data_ptr(), pk[f"m{l}.cb"].data_ptr(), xc.data_ptr(), di_p, B * di_p, ptr(cs), ptr(cs), B, T, di_p,
+                           mm["W"], _lib.stream_ptr(), launches=n_l, nbytes=8 * rows * mm["di"])
+            else:
+                self._call("dwconv_silu", self.lib.cum_dwconv_silu_fwd, xz.data_ptr(), T * 2 * di_p, 2 * di_p,
+                           pk[f"m{l}.cw"].data_ptr(), pk[f"m{l}.cb"].data_ptr(), xc.data_ptr(), ptr(cs), ptr(cs), B, T, di_p,
+                           mm["W"], _lib.stream_ptr(), launches=n_l, nbytes=8 * rows * mm["di"])
             xdbl = self.dense(xc, rows, di_p, f"m{l}.xp", None, R_p + 2 * N_p)
             dt = self.dense(xdbl, rows, R_p, f"m{l}.dtw", None, di_p, a_rs=R_p + 2 * N_p)
             y = torch.empty(rows, di_p, dtype=torch.float32, device=dev)
             hs = states[l][1] if states is not None else None
-            self.scan(xc, dt, xz, xdbl, y, l, mm, B, T, h0=hs, h_out=hs)
+            self.scan(xc, dt, xz, xdbl, y, l, mm, B, T, h0=hs, h_out=hs, tm=tm)
             h = self.dense(y, rows, di_p, f"m{l}.out", None, dm_p)
         self.ln(h, res, None, hn, pk["nf.g"], pk["nf.be"], meta["eps"], rows, dm, dm_p)
         return hn

@@ -147,17 +147,26 @@ def split_hl16(x):
 
 
 def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None, addend=None, math="fp32", cta_pair=0,
-                  out_hl16=False):
+                  out_hl16=False, plane_major=None):
     """Raw tap-GEMM on channels-last tensors (thin wrapper of cum_gemm_bias_act_fwd, used by tests / benchmarks).
     a: (batch, rows, K) fp32 contiguous, K % 4 == 0;  w: (taps, N, K), N % 8 == 0;  bias: (N);  addend: (batch, m, N_out).
     out[b, i, :] = EPI(bias + sum_s W_s . a[b, i + shifts[s], :]) + addend[b, i, :]   (rows outside a read as 0).
     f16x3 only: ``a`` may be an hl16 tensor (2, batch, rows, K) float16 (``split_hl16``); ``out_hl16`` returns the result in
-    that format, and the addend must then be hl16 as well."""
+    that format, and the addend must then be hl16 as well.
+    ``plane_major=dict(batch=, plane0=, step=, n_half=)``: ``a`` is a stack (planes, rows, plane_k) of planes (the time-major streaming
+    FIFOs, cum_gemm_desc.a_planes): batch item b, tap s, K offset kk read plane plane0 + step * (b' + shifts[s]) + kk // plane_k,
+    b' = b >> 1 with n_half (then w holds 2 n rows per tap, bias n entries, and item b uses rows (b & 1) n ...)."""
     _need_cuda(a, w, bias, addend)
     lib = _lib.init(a.device)
     a_planes = a if a.dtype == torch.float16 else None
     batch, rows, k = a.shape[-3:]
     taps, n, kw = w.shape
+    pm = plane_major
+    if pm is not None:
+        n_planes, plane_k = batch, k
+        batch, k = pm["batch"], kw
+        if pm.get("n_half"):
+            n //= 2
     assert kw == k and a.is_contiguous() and w.is_contiguous()
     m = rows if m is None else m
     n_out = n // 2 if epilogue >= 8 else n
@@ -165,6 +174,9 @@ def gemm_bias_act(a, w, bias=None, epilogue=_lib.EPI_NONE, shifts=(0, 0), m=None
            else torch.empty(batch, m, n_out, dtype=torch.float32, device=a.device))
     d = _lib.GemmDesc()
     d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k, d.taps = a.data_ptr(), rows * k, k, rows, k, taps
+    if pm is not None:
+        d.a_batch_stride, d.a_row_stride = rows * plane_k, plane_k
+        d.a_planes, d.a_plane_k, d.a_plane0, d.a_plane_step, d.n_half = n_planes, plane_k, pm.get("plane0", 0), pm.get("step", 1), int(bool(pm.get("n_half")))
     if a_planes is not None:
         d.a_lo = a_planes[1].data_ptr()
     if out_hl16:

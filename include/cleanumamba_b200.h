@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CUM_ABI_VERSION 2
+#define CUM_ABI_VERSION 3
 
 /* error codes */
 #define CUM_OK            0
@@ -118,6 +118,23 @@ int cum_conv_in_hl16_fwd(const float* x, long long x_stride, int batch, int leng
                          const float* bias, void* y_hi, void* y_lo, int rows_out, int c_pad, int kernel, int stride,
                          cum_stream_t stream);
 
+/* ---- ABI v3: the time-major streaming session (cleanumamba_b200/stream_tm.py) ------------------------------------
+ * feed() for MANY concurrent streams (CleanUMamba.py:371-490 once per stream and hop in the reference) keeps every carried
+ * buffer as (column, stream, channel): all streams of a hop sit in the M dimension of each GEMM (full 128-row tiles), a FIFO is
+ * appended / consumed by whole planes, and no per-call gather / scatter copies are left.  The kernels below are the strided
+ * forms of cum_conv_in_fwd / cum_convt_out_fwd / cum_dwconv_silu_fwd (element [b, t, :] of the channels-last side at
+ * base + b * batch_stride + t * row_stride) and the one FIFO-maintenance launch that ends a call. */
+int cum_conv_in_strided_fwd(const float* x, long long x_stride, int batch, int length, const float* w, const float* bias,
+                            float* y, long long y_batch_stride, long long y_row_stride, int rows_out, int c_pad, int kernel,
+                            int stride, const float* in_scale, int group_rows, int row_offset, cum_stream_t stream);
+int cum_convt_out_strided_fwd(const float* g, long long g_batch_stride, long long g_row_stride, int batch, int rows_in, int c_pad,
+                              const float* w, float bias, const float* scale, int scale_group, float* out, long long out_stride,
+                              int first, int length, int kernel, int stride, cum_stream_t stream);
+/* For every entry and row r < rows: base[r * row_stride + i] = base[r * row_stride + src_off + i], i < count (elements; the
+ * ranges may overlap) -- the unconsumed tail of a carried FIFO moves to its front.  Up to 24 entries per launch. */
+typedef struct cum_shift_entry { float* base; long long row_stride; long long src_off; long long count; int rows; int reserved; } cum_shift_entry;
+int cum_stream_shift_fwd(const cum_shift_entry* entries, int n_entries, cum_stream_t stream);
+
 /* ---- the tap-GEMM: every dense contraction of the path -------------------------------------- */
 /* out[b, m, :] = EPI( bias + sum_{s<taps} W_s . a[b, m + tap_shift[s], 0:k] ) (+ addend[b, m, :])
  * Rows of `a` outside [0, a_rows) read as zero.  One descriptor covers:
@@ -168,6 +185,17 @@ typedef struct cum_gemm_desc {
     int cta_pair;            /* tiles wider than 128 columns can run on CTA pairs (tcgen05 cta_group::2: 256-row tiles, each CTA
                                 stages half of the weight tile).  0 = automatic (pairs whenever a problem has more than 128 rows),
                                 1 = same, -1 = never.  Same products, same accumulation order: bit-identical results */
+    /* ABI v3 -- PLANE-MAJOR `a` (time-major streaming: the carried encoder / decoder FIFOs of feed(), CleanUMamba.py:432-442,476-484,
+     * are stored as (column, stream, channel) so that every GEMM of a hop has all streams in its M dimension and a FIFO is appended /
+     * consumed by whole contiguous planes).  a_planes > 0: `a` is a stack of a_planes planes of (a_rows, a_plane_k) values
+     * [plane stride a_batch_stride, row stride a_row_stride]; output row m of batch item b reads, for tap s and K offset kk < k,
+     *     plane  a_plane0 + a_plane_step * (b' + tap_shift[s]) + kk / a_plane_k,  row m,  channel kk % a_plane_k      (b' = b, or b >> 1 with n_half)
+     * (planes outside [0, a_planes) read as zero): the tap shifts move across PLANES instead of rows, and the 2C-wide input row of a
+     * strided conv (k = 2 a_plane_k, a_plane_step = 2) is two neighbouring planes.  a_plane_k must be a multiple of 32 (64 for CUM_MATH_BF16).
+     * n_half (plane mode, non-GLU epilogues): the packed weight holds 2 n rows per tap and batch item b uses rows
+     * (b & 1) * n .. + n, `bias` (n entries) is shared by both halves: a transposed conv writes its even / odd output columns as
+     * separate planes (c_batch_stride apart). */
+    int a_planes; int a_plane_k; int a_plane0; int a_plane_step; int n_half;
 } cum_gemm_desc;
 int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream);
 
@@ -238,6 +266,10 @@ int cum_ln_residual_fwd(const float* h, const float* residual_in, float* residua
 int cum_dwconv_silu_fwd(const float* x, long long x_batch_stride, long long x_row_stride, const float* w,
                         const float* bias, float* y, const float* conv_state, float* conv_state_out,
                         int batch, int len, int d_pad, int width, cum_stream_t stream);
+int cum_dwconv_silu_strided_fwd(const float* x, long long x_batch_stride, long long x_row_stride, const float* w,
+                                const float* bias, float* y, long long y_batch_stride, long long y_row_stride,
+                                const float* conv_state, float* conv_state_out, int batch, int len, int d_pad, int width,
+                                cum_stream_t stream);
 
 /* Replaces selective_scan_fn(u, delta, A, B, C, D, z, delta_bias, delta_softplus=True) (mamba_ssm; oracle =
  * selective_scan_ref) and, with h0/h_out, selective_state_update / Mamba.step's recurrence:
@@ -267,6 +299,9 @@ typedef struct cum_scan_desc {
                            (h is linear in its start state), a second pass writes y from the true start states: 2x the
                            arithmetic, up to 64-fold parallelism.  NULL: always the time-sequential kernel */
     long long workspace_bytes;
+    int state_f16;      /* ABI v3 -- streaming variant with a REDUCED-PRECISION carried state (reported separately): h0 / h_out point to
+                           fp16 arrays of the same shape (half the state traffic that bounds a 1-hop call); the recurrence itself
+                           stays fp32.  Needs n_state = 64, d % 16 == 0, both h0 and h_out */
 } cum_scan_desc;
 int cum_selective_scan_fwd(const cum_scan_desc* desc, cum_stream_t stream);
 /* 0 when the problem would not run segment-parallel (large batch, short sequence, training checkpoints requested) */

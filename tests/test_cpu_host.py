@@ -114,7 +114,7 @@ def test_struct_sizes_and_offsets_match_a_c_compiler(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pairs = {"cum_gemm_desc": _lib.GemmDesc, "cum_scan_desc": _lib.ScanDesc, "cum_wgrad_desc": _lib.WgradDesc,
              "cum_scan_bwd_desc": _lib.ScanBwdDesc, "cum_enc0_block_desc": _lib.Enc0BlockDesc,
-             "cum_dec_last_block_desc": _lib.DecLastBlockDesc}
+             "cum_dec_last_block_desc": _lib.DecLastBlockDesc, "cum_shift_entry": _lib.ShiftEntry}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cleanumamba_b200.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
