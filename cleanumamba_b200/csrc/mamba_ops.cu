@@ -1,6 +1,7 @@
 // Mamba-block operators in channels-last layout: residual add + LayerNorm, depthwise causal conv + SiLU,
 // selective scan (fwd) with optional carried state.  All HBM / MUFU-bound CUDA-core kernels.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -595,6 +596,227 @@ __global__ void __launch_bounds__(256) selective_scan_step_kernel(const cum_scan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA-staged state update (many streams: BASELINE configs[2], 4096 streams x 1 hop).  The per-thread-load kernel above is bound
+// by WARP LIFETIME, not by bytes: a warp issues one 16-byte state load per thread, waits ~1 us for DRAM, computes for ~0.2 us and
+// retires -- 64 resident warps x 512 B = 32 KB in flight per SM, 2.6 TB/s of reads whatever the state's element size (fp16 state:
+// the same 2.4 ms).  Here the state moves through shared memory: a persistent CTA owns ONE block of 64 channels (its A2 rows, D and
+// dt bias stay in registers) and walks over streams; per (stream, channel block) tile one elected thread requests the tile's
+// 64 x 64 state block as TMA tensor boxes (128-byte swizzle: conflict-free reads with compile-time register indices) and the
+// tile's 256-byte rows of delta, u, z, B_t, C_t as plain bulk copies onto one mbarrier, SB_NST stages deep; the 256 threads update
+// the state IN PLACE in shared memory (thread = 16 states of one channel: softplus 4x instead of 16x redundant, 2 shuffles
+// instead of 4, ~6 instructions per state instead of ~20) and TMA stores write the tile back.  In flight per SM: 3 CTAs x 2 tiles.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int SB_CH = 64;          // channels per tile
+constexpr int SB_NST = 3;          // stages
+template <int T, bool H16> struct StepBulkCfg {
+    static constexpr uint32_t STATE_BYTES = SB_CH * 64 * (H16 ? 2 : 4);   // fp32: two boxes of 64 rows x 128 B; fp16: one
+    static constexpr uint32_t ROW_BYTES = SB_CH * 4;                       // one token's delta / u / z / B / C row of the tile (64 floats)
+    static constexpr uint32_t STAGE_BYTES = (STATE_BYTES + 5 * T * ROW_BYTES + 1023u) & ~1023u;      // swizzle atoms are 1 KB aligned
+    static constexpr uint32_t SMEM_BYTES = SB_NST * STAGE_BYTES + 64 /*barriers*/ + 1024 /*alignment*/;
+};
+
+template <int T, bool H16>
+__global__ void __launch_bounds__(256, 3) selective_scan_step_bulk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
+                                                                            const cum_scan_desc p, int groups) {
+    using Cfg = StepBulkCfg<T, H16>;
+    extern __shared__ uint8_t sb_raw[];
+    const uint32_t base = (smem_u32(sb_raw) + 1023u) & ~1023u;
+    uint8_t* gen = sb_raw + (base - smem_u32(sb_raw));
+    const uint32_t bar0 = base + SB_NST * Cfg::STAGE_BYTES;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmIn);
+        tma_prefetch_desc(&tmOut);
+        for (int s = 0; s < SB_NST; ++s) mbar_init(bar0 + 8u * s, 1);
+        fence_barrier_init();
+    }
+    pdl_trigger();
+    __syncthreads();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+
+    const int c0 = blockIdx.x * SB_CH;
+    const int ch = tid >> 2, sub = tid & 3;
+    const int c = c0 + ch;
+    // This thread's 16 states as four 16-byte pieces i = 0..3 (compile-time register indices).
+    //   fp32: piece i = logical chunk 2 sub + (i & 1) of box (i >> 1): states 32 (i >> 1) + 8 sub + 4 (i & 1) + {0..3}
+    //   fp16: pieces (2 e, 2 e + 1) = the 8 halves of logical chunk 2 sub + e: states 16 sub + 8 e + {0..7}
+    // physical 16-byte chunk inside the 128-byte row of channel ch: logical ^ (ch & 7) -- a quarter-warp (2 channels x 4 subs) hits 8 banks groups
+    auto state0 = [&](int i) { return H16 ? 16 * sub + 4 * i : 32 * (i >> 1) + 8 * sub + 4 * (i & 1); };
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.a2 + (long long)c * 64 + state0(i)));
+        a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+    }
+    const float bias = p.delta_bias ? __ldg(p.delta_bias + c) : 0.f;
+    const float dk = p.Dskip ? __ldg(p.Dskip + c) : 0.f;
+    const uint32_t x7 = (uint32_t)(ch & 7);
+    uint32_t poff[H16 ? 2 : 4];              // byte offset of this thread's pieces inside the stage's state region
+    if (H16) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) poff[e] = (uint32_t)ch * 128u + (((uint32_t)(2 * sub + e)) ^ x7) * 16u;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) poff[i] = (uint32_t)(i >> 1) * 8192u + (uint32_t)ch * 128u + (((uint32_t)(2 * sub + (i & 1))) ^ x7) * 16u;
+    }
+
+    auto issue = [&](int b, int s) {            // one thread: every byte of tile (b, this channel block) onto the stage's barrier
+        const uint32_t st = base + (uint32_t)s * Cfg::STAGE_BYTES, bar = bar0 + 8u * s;
+        mbar_arrive_expect_tx(bar, Cfg::STATE_BYTES + (p.z ? 5 : 4) * T * Cfg::ROW_BYTES);
+        const int row = b * p.d + c0;
+        tma_load_3d(st, &tmIn, bar, 0, row, 0);
+        if (!H16) tma_load_3d(st + 8192u, &tmIn, bar, 32, row, 0);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const uint32_t r = st + Cfg::STATE_BYTES + (uint32_t)t * 5 * Cfg::ROW_BYTES;
+            bulk_load(r, p.delta + (long long)b * p.dl_bs + (long long)t * p.dl_rs + c0, Cfg::ROW_BYTES, bar);
+            bulk_load(r + Cfg::ROW_BYTES, p.u + (long long)b * p.u_bs + (long long)t * p.u_rs + c0, Cfg::ROW_BYTES, bar);
+            if (p.z) bulk_load(r + 2 * Cfg::ROW_BYTES, p.z + (long long)b * p.z_bs + (long long)t * p.z_rs + c0, Cfg::ROW_BYTES, bar);
+            bulk_load(r + 3 * Cfg::ROW_BYTES, p.Bm + (long long)b * p.B_bs + (long long)t * p.B_rs, Cfg::ROW_BYTES, bar);
+            bulk_load(r + 4 * Cfg::ROW_BYTES, p.Cm + (long long)b * p.C_bs + (long long)t * p.C_rs, Cfg::ROW_BYTES, bar);
+        }
+    };
+
+    const int b_first = blockIdx.y;
+    const int n_tiles = (p.batch - b_first + groups - 1) / groups;          // streams b_first, b_first + groups, ...
+    if (tid == 0) {
+        for (int i = 0; i < SB_NST - 1 && i < n_tiles; ++i) issue(b_first + i * groups, i);
+    }
+    for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % SB_NST;
+        const int b = b_first + it * groups;
+        mbar_wait(bar0 + 8u * s, (uint32_t)(it / SB_NST) & 1u);
+        uint8_t* stage = gen + (size_t)s * Cfg::STAGE_BYTES;
+        float h[16];
+        if (H16) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(stage + poff[e]);
+                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+                    h[8 * e + 2 * k] = f.x; h[8 * e + 2 * k + 1] = f.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(stage + poff[i]);
+                h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const float* row = reinterpret_cast<const float*>(stage + Cfg::STATE_BYTES) + t * 5 * SB_CH;
+            float dl = row[ch] + bias;
+            if (p.delta_softplus) dl = softplusf_(dl);
+            const float u = row[SB_CH + ch];
+            const float du = dl * u;
+            float part = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 bv = *reinterpret_cast<const float4*>(row + 3 * SB_CH + state0(i));
+                const float4 cv = *reinterpret_cast<const float4*>(row + 4 * SB_CH + state0(i));
+                h[4 * i] = fmaf(ex2_approx(dl * a[4 * i]), h[4 * i], du * bv.x);
+                h[4 * i + 1] = fmaf(ex2_approx(dl * a[4 * i + 1]), h[4 * i + 1], du * bv.y);
+                h[4 * i + 2] = fmaf(ex2_approx(dl * a[4 * i + 2]), h[4 * i + 2], du * bv.z);
+                h[4 * i + 3] = fmaf(ex2_approx(dl * a[4 * i + 3]), h[4 * i + 3], du * bv.w);
+                part = fmaf(h[4 * i], cv.x, fmaf(h[4 * i + 1], cv.y, fmaf(h[4 * i + 2], cv.z, fmaf(h[4 * i + 3], cv.w, part))));
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            if (sub == 0) {
+                float yv = fmaf(dk, u, part);
+                if (p.z) { const float zv = row[2 * SB_CH + ch]; yv *= __fdividef(zv, 1.0f + __expf(-zv)); }
+                p.y[(long long)b * p.y_bs + (long long)t * p.y_rs + c] = yv;
+            }
+        }
+        // new state back into the stage, in place
+        if (H16) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __half2 v = __floats2half2_rn(h[8 * e + 2 * k], h[8 * e + 2 * k + 1]);
+                    w[k] = *reinterpret_cast<const uint32_t*>(&v);
+                }
+                *reinterpret_cast<uint4*>(stage + poff[e]) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(stage + poff[i]) = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        }
+        fence_proxy_async();            // generic-proxy writes of the state -> visible to the TMA store (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t st = base + (uint32_t)s * Cfg::STAGE_BYTES;
+            const int row = b * p.d + c0;
+            tma_store_3d_(&tmOut, st, 0, row, 0);
+            if (!H16) tma_store_3d_(&tmOut, st + 8192u, 32, row, 0);
+            bulk_commit_group();
+            // refill the stage of the PREVIOUS iteration: its store (the group before the one just committed) has read it
+            const int nxt = it + SB_NST - 1;
+            if (nxt < n_tiles) {
+                bulk_wait_group_read<1>();
+                issue(b_first + nxt * groups, nxt % SB_NST);
+            }
+        }
+    }
+    if (tid == 0) bulk_wait_group<0>();     // the stores must have left shared memory before the CTA exits
+}
+
+template <int T, bool H16>
+static int launch_step_bulk(const cum_scan_desc& d, cudaStream_t st) {
+    using Cfg = StepBulkCfg<T, H16>;
+    auto kern = selective_scan_step_bulk_kernel<T, H16>;
+    { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)Cfg::SMEM_BYTES, "cudaFuncSetAttribute(selective_scan_step_bulk_kernel)"); if (rc_attr) return rc_attr; }
+    // the carried state as a 2-D tensor (batch * d rows of 64 states): boxes of 64 rows x 128 bytes, 128-byte swizzle.  The fp16 state
+    // uses the 2-byte tensor type of the map helper (raw copies: no conversion takes place)
+    CUtensorMap tmIn, tmOut;
+    const uint64_t rows = (uint64_t)d.batch * (uint64_t)d.d;
+    int rc = make_tensor_map(&tmIn, d.h0, 64, rows, 1, 64, rows * 64, H16 ? 64 : 32, SB_CH, "scan state in", H16, H16);
+    if (rc) return rc;
+    rc = make_tensor_map(&tmOut, d.h_out, 64, rows, 1, 64, rows * 64, H16 ? 64 : 32, SB_CH, "scan state out", H16, H16);
+    if (rc) return rc;
+    const int cblocks = d.d / SB_CH;
+    // 3 CTAs fit an SM: every CTA of the grid must be resident at once (one CTA more than 3 x SMs would run as a second wave and
+    // double the kernel's time), each walking over batch / groups streams
+    int groups = (3 * sm_count()) / cblocks;
+    if (groups < 1) groups = 1;
+    if (groups > d.batch) groups = d.batch;
+    if (groups > 65535) groups = 65535;
+    cudaError_t e = launch_kernel(kern, dim3((unsigned)cblocks, (unsigned)groups), dim3(256), Cfg::SMEM_BYTES, st, tmIn, tmOut, d, groups);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_step_bulk_kernel)");
+    return CUM_OK;
+}
+
+// many streams with whole 64-channel blocks and 16-byte aligned rows: the bulk-staged kernel (CUM_SCAN_STEP_BULK=0 disables: A/B)
+static bool step_bulk_ok(const cum_scan_desc& d) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("CUM_SCAN_STEP_BULK"); env = (e && e[0] == '0') ? 0 : 1; }
+    if (!env || d.d % SB_CH || d.n_state != 64 || !d.h0 || !d.h_out || d.len > 2) return false;
+    if ((long long)d.batch * (d.d / SB_CH) < 4LL * sm_count()) return false;        // few tiles: the per-thread kernel has more parallelism
+    const auto ok = [](const void* q, long long bs, long long rs) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0 && bs % 4 == 0 && rs % 4 == 0; };
+    return ok(d.u, d.u_bs, d.u_rs) && ok(d.delta, d.dl_bs, d.dl_rs) && (!d.z || ok(d.z, d.z_bs, d.z_rs)) && ok(d.Bm, d.B_bs, d.B_rs) &&
+           ok(d.Cm, d.C_bs, d.C_rs) && (reinterpret_cast<uintptr_t>(d.h0) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.h_out) & 15) == 0;
+}
+
 template <int T, bool H16>
 static cudaError_t launch_step(const cum_scan_desc& d, cudaStream_t st) {
     // channels per thread = independent 16-byte (fp32 state) / 8-byte (fp16 state) loads in flight per thread.
@@ -703,11 +925,17 @@ int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st) {
             s.u = d.u + (long long)t * d.u_rs; s.delta = d.delta + (long long)t * d.dl_rs; s.z = d.z ? d.z + (long long)t * d.z_rs : nullptr;
             s.Bm = d.Bm + (long long)t * d.B_rs; s.Cm = d.Cm + (long long)t * d.C_rs; s.y = d.y + (long long)t * d.y_rs;
             if (t > 0) s.h0 = d.h_out;
+            if (step_bulk_ok(s)) {
+                const int rc = n == 1 ? launch_step_bulk<1, true>(s, st) : launch_step_bulk<2, true>(s, st);
+                if (rc) return rc;
+                continue;
+            }
             cudaError_t e = n == 1 ? launch_step<1, true>(s, st) : launch_step<2, true>(s, st);
             if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_step_kernel, fp16 state)");
         }
         return CUM_OK;
     }
+    if (d.len <= 2 && step_ok && step_bulk_ok(d)) return d.len == 1 ? launch_step_bulk<1, false>(d, st) : launch_step_bulk<2, false>(d, st);
     if (d.len <= 2 && step_ok) {
         cudaError_t e = d.len == 1 ? launch_step<1, false>(d, st) : launch_step<2, false>(d, st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_step_kernel)");

@@ -27,7 +27,9 @@ def rel_err(a, b):
     (2, 64, 37, 64, True, False), (1, 2048, 130, 64, True, True), (3, 40, 50, 8, True, True),
     (2, 128, 33, 16, False, False), (2, 96, 20, 24, True, False), (1, 8, 5, 8, True, True), (2, 24, 624, 64, True, False),
     # few tokens + carried state: the streaming state-update kernel (selective_scan_step_kernel)
-    (2, 64, 2, 64, True, True), (1, 2048, 1, 64, True, True), (3, 48, 2, 64, False, True), (2, 32, 1, 64, True, False), (2, 64, 3, 64, True, True)])
+    (2, 64, 2, 64, True, True), (1, 2048, 1, 64, True, True), (3, 48, 2, 64, False, True), (2, 32, 1, 64, True, False), (2, 64, 3, 64, True, True),
+    # many streams x whole 64-channel blocks: the TMA-staged state-update kernel (selective_scan_step_bulk_kernel), 1 and 2 tokens
+    (48, 1024, 1, 64, True, True), (41, 1024, 2, 64, False, True), (300, 128, 2, 64, True, True)])
 def test_selective_scan_matches_oracle(b, d, l, n, with_z, with_h0):
     from cleanumamba_b200 import ops
     g = torch.Generator().manual_seed(b * 1000 + d + l + n)

@@ -156,7 +156,7 @@ def test_strided_wave_ends_and_dwconv_equal_contiguous_forms():
             assert torch.equal(s0, ref_state)
 
 
-@pytest.mark.parametrize("b,d,l", [(3, 64, 1), (2, 2048, 2), (5, 48, 1), (2, 96, 5)])
+@pytest.mark.parametrize("b,d,l", [(3, 64, 1), (2, 2048, 2), (5, 48, 1), (2, 96, 5), (48, 1024, 1), (41, 1024, 2), (300, 128, 5)])
 def test_step_scan_fp16_state_close_to_fp32_state(b, d, l):
     """Reduced-precision carried state (fp16 storage, fp32 recurrence): y of a call equals the fp32-state kernel's up to the
     rounding of the INPUT state (<= 2^-11 relative per element), the new state equals fp16(fp32 result)."""
@@ -187,8 +187,8 @@ def test_step_scan_fp16_state_close_to_fp32_state(b, d, l):
 
     y32 = run(h32, False)
     y16 = run(h16, True)
-    if l <= 2:      # one launch: the only difference is the rounding of the stored result
-        assert torch.equal(y16, y32)
+    if l <= 2:      # one launch: the only differences are the rounding of the stored result and the order of the <h, C> sum
+        assert rel_err(y16, y32) < 2e-6
         assert torch.equal(h16, h32.to(torch.float16))
     else:           # two tokens per launch, the state is rounded to fp16 between launches
         assert rel_err(y16, y32) < 2e-3 and rel_err(h16.float(), h32) < 2e-3
