@@ -621,21 +621,25 @@ template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatil
 
 constexpr int SB_CH = 64;          // channels per tile
 constexpr int SB_NST = 3;          // stages
-template <int T, bool H16> struct StepBulkCfg {
+constexpr int SB_MAXT = 8;         // tokens per call (runtime): the state is read and written once per call, whatever T.  Measured at 4096
+                                   // streams x 3 layers vs the per-thread / chunked kernels: 1 token 2.23 vs 2.44 ms, 2: 2.30 vs 3.76, 4: 3.85 vs
+                                   // 6.96, 8: 7.88 vs 8.77, 16: 15.1 vs 12.1 -> up to 8 tokens, the chunked kernel beyond
+template <bool H16> struct StepBulkCfg {
     static constexpr uint32_t STATE_BYTES = SB_CH * 64 * (H16 ? 2 : 4);   // fp32: two boxes of 64 rows x 128 B; fp16: one
     static constexpr uint32_t ROW_BYTES = SB_CH * 4;                       // one token's delta / u / z / B / C row of the tile (64 floats)
-    static constexpr uint32_t STAGE_BYTES = (STATE_BYTES + 5 * T * ROW_BYTES + 1023u) & ~1023u;      // swizzle atoms are 1 KB aligned
-    static constexpr uint32_t SMEM_BYTES = SB_NST * STAGE_BYTES + 64 /*barriers*/ + 1024 /*alignment*/;
+    static uint32_t stage_bytes(int T) { return (STATE_BYTES + 5u * (uint32_t)T * ROW_BYTES + 1023u) & ~1023u; }     // swizzle atoms are 1 KB aligned
+    static uint32_t smem_bytes(int T) { return SB_NST * stage_bytes(T) + 64 /*barriers*/ + 1024 /*alignment*/; }
 };
 
-template <int T, bool H16>
+template <bool H16>
 __global__ void __launch_bounds__(256, 3) selective_scan_step_bulk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
-                                                                            const cum_scan_desc p, int groups) {
-    using Cfg = StepBulkCfg<T, H16>;
+                                                                            const cum_scan_desc p, int groups, uint32_t stage_bytes) {
+    using Cfg = StepBulkCfg<H16>;
+    const int T = p.len;
     extern __shared__ uint8_t sb_raw[];
     const uint32_t base = (smem_u32(sb_raw) + 1023u) & ~1023u;
     uint8_t* gen = sb_raw + (base - smem_u32(sb_raw));
-    const uint32_t bar0 = base + SB_NST * Cfg::STAGE_BYTES;
+    const uint32_t bar0 = base + SB_NST * stage_bytes;
     const int tid = threadIdx.x;
     if (tid == 0) {
         tma_prefetch_desc(&tmIn);
@@ -674,12 +678,11 @@ __global__ void __launch_bounds__(256, 3) selective_scan_step_bulk_kernel(const 
     }
 
     auto issue = [&](int b, int s) {            // one thread: every byte of tile (b, this channel block) onto the stage's barrier
-        const uint32_t st = base + (uint32_t)s * Cfg::STAGE_BYTES, bar = bar0 + 8u * s;
-        mbar_arrive_expect_tx(bar, Cfg::STATE_BYTES + (p.z ? 5 : 4) * T * Cfg::ROW_BYTES);
+        const uint32_t st = base + (uint32_t)s * stage_bytes, bar = bar0 + 8u * s;
+        mbar_arrive_expect_tx(bar, Cfg::STATE_BYTES + (p.z ? 5u : 4u) * (uint32_t)T * Cfg::ROW_BYTES);
         const int row = b * p.d + c0;
         tma_load_3d(st, &tmIn, bar, 0, row, 0);
         if (!H16) tma_load_3d(st + 8192u, &tmIn, bar, 32, row, 0);
-#pragma unroll
         for (int t = 0; t < T; ++t) {
             const uint32_t r = st + Cfg::STATE_BYTES + (uint32_t)t * 5 * Cfg::ROW_BYTES;
             bulk_load(r, p.delta + (long long)b * p.dl_bs + (long long)t * p.dl_rs + c0, Cfg::ROW_BYTES, bar);
@@ -699,7 +702,7 @@ __global__ void __launch_bounds__(256, 3) selective_scan_step_bulk_kernel(const 
         const int s = it % SB_NST;
         const int b = b_first + it * groups;
         mbar_wait(bar0 + 8u * s, (uint32_t)(it / SB_NST) & 1u);
-        uint8_t* stage = gen + (size_t)s * Cfg::STAGE_BYTES;
+        uint8_t* stage = gen + (size_t)s * stage_bytes;
         float h[16];
         if (H16) {
 #pragma unroll
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(256, 3) selective_scan_step_bulk_kernel(const 
                 h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
             }
         }
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < T; ++t) {
             const float* row = reinterpret_cast<const float*>(stage + Cfg::STATE_BYTES) + t * 5 * SB_CH;
             float dl = row[ch] + bias;
@@ -765,7 +768,7 @@ __global__ void __launch_bounds__(256, 3) selective_scan_step_bulk_kernel(const 
         fence_proxy_async();            // generic-proxy writes of the state -> visible to the TMA store (async proxy)
         __syncthreads();
         if (tid == 0) {
-            const uint32_t st = base + (uint32_t)s * Cfg::STAGE_BYTES;
+            const uint32_t st = base + (uint32_t)s * stage_bytes;
             const int row = b * p.d + c0;
             tma_store_3d_(&tmOut, st, 0, row, 0);
             if (!H16) tma_store_3d_(&tmOut, st + 8192u, 32, row, 0);
@@ -781,11 +784,12 @@ __global__ void __launch_bounds__(256, 3) selective_scan_step_bulk_kernel(const 
     if (tid == 0) bulk_wait_group<0>();     // the stores must have left shared memory before the CTA exits
 }
 
-template <int T, bool H16>
+template <bool H16>
 static int launch_step_bulk(const cum_scan_desc& d, cudaStream_t st) {
-    using Cfg = StepBulkCfg<T, H16>;
-    auto kern = selective_scan_step_bulk_kernel<T, H16>;
-    { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)Cfg::SMEM_BYTES, "cudaFuncSetAttribute(selective_scan_step_bulk_kernel)"); if (rc_attr) return rc_attr; }
+    using Cfg = StepBulkCfg<H16>;
+    auto kern = selective_scan_step_bulk_kernel<H16>;
+    const uint32_t stage = Cfg::stage_bytes(d.len), smem = Cfg::smem_bytes(d.len);
+    { const int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)Cfg::smem_bytes(SB_MAXT), "cudaFuncSetAttribute(selective_scan_step_bulk_kernel)"); if (rc_attr) return rc_attr; }
     // the carried state as a 2-D tensor (batch * d rows of 64 states): boxes of 64 rows x 128 bytes, 128-byte swizzle.  The fp16 state
     // uses the 2-byte tensor type of the map helper (raw copies: no conversion takes place)
     CUtensorMap tmIn, tmOut;
@@ -795,13 +799,14 @@ static int launch_step_bulk(const cum_scan_desc& d, cudaStream_t st) {
     rc = make_tensor_map(&tmOut, d.h_out, 64, rows, 1, 64, rows * 64, H16 ? 64 : 32, SB_CH, "scan state out", H16, H16);
     if (rc) return rc;
     const int cblocks = d.d / SB_CH;
-    // 3 CTAs fit an SM: every CTA of the grid must be resident at once (one CTA more than 3 x SMs would run as a second wave and
-    // double the kernel's time), each walking over batch / groups streams
-    int groups = (3 * sm_count()) / cblocks;
+    // every CTA of the grid must be resident at once (one CTA more than fit would run as a second wave and double the kernel's
+    // time): 3 CTAs per SM up to 4 tokens per call (56-67 KB of shared memory each), 2 beyond; each walks over batch / groups streams
+    const int per_sm = (int)(232448u / (smem + 1024u)) >= 3 ? 3 : ((int)(232448u / (smem + 1024u)) >= 2 ? 2 : 1);
+    int groups = (per_sm * sm_count()) / cblocks;
     if (groups < 1) groups = 1;
     if (groups > d.batch) groups = d.batch;
     if (groups > 65535) groups = 65535;
-    cudaError_t e = launch_kernel(kern, dim3((unsigned)cblocks, (unsigned)groups), dim3(256), Cfg::SMEM_BYTES, st, tmIn, tmOut, d, groups);
+    cudaError_t e = launch_kernel(kern, dim3((unsigned)cblocks, (unsigned)groups), dim3(256), smem, st, tmIn, tmOut, d, groups, stage);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_step_bulk_kernel)");
     return CUM_OK;
 }
@@ -810,7 +815,7 @@ static int launch_step_bulk(const cum_scan_desc& d, cudaStream_t st) {
 static bool step_bulk_ok(const cum_scan_desc& d) {
     static int env = -1;
     if (env < 0) { const char* e = getenv("CUM_SCAN_STEP_BULK"); env = (e && e[0] == '0') ? 0 : 1; }
-    if (!env || d.d % SB_CH || d.n_state != 64 || !d.h0 || !d.h_out || d.len > 2) return false;
+    if (!env || d.d % SB_CH || d.n_state != 64 || !d.h0 || !d.h_out || d.len > SB_MAXT || d.h_ckpt) return false;
     if ((long long)d.batch * (d.d / SB_CH) < 4LL * sm_count()) return false;        // few tiles: the per-thread kernel has more parallelism
     const auto ok = [](const void* q, long long bs, long long rs) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0 && bs % 4 == 0 && rs % 4 == 0; };
     return ok(d.u, d.u_bs, d.u_rs) && ok(d.delta, d.dl_bs, d.dl_rs) && (!d.z || ok(d.z, d.z_bs, d.z_rs)) && ok(d.Bm, d.B_bs, d.B_rs) &&
@@ -915,27 +920,32 @@ int selective_scan_fwd(const cum_scan_desc& d, cudaStream_t st) {
     const bool step_ok = d.n_state == 64 && d.d % 16 == 0 && (d.h0 || d.h_out) && !d.h_ckpt && al16(d.a2) && al16(d.Bm) && al16(d.Cm) &&
                          (!d.h0 || al16(d.h0)) && (!d.h_out || al16(d.h_out)) && (d.B_rs | d.C_rs | d.B_bs | d.C_bs) % 4 == 0;
     if (d.state_f16) {
-        // reduced-precision carried state (streaming variant, reported separately): fp16 storage, fp32 recurrence; only the step kernel
-        // reads / writes it, longer calls advance two tokens per launch
+        // reduced-precision carried state (streaming variant, reported separately): fp16 storage, fp32 recurrence; only the state-update
+        // kernels read / write it, longer calls advance in pieces (8 tokens per launch TMA-staged, else 2)
         CUM_REQUIRE(step_ok && d.h0 && d.h_out, "selective_scan: state_f16 needs n_state = 64, d %% 16 == 0, aligned operands and both h0 and h_out");
         cum_scan_desc s = d;
-        for (int t = 0; t < d.len; t += 2) {
-            const int n = d.len - t >= 2 ? 2 : 1;
-            s.len = n;
+        for (int t = 0; t < d.len;) {
             s.u = d.u + (long long)t * d.u_rs; s.delta = d.delta + (long long)t * d.dl_rs; s.z = d.z ? d.z + (long long)t * d.z_rs : nullptr;
             s.Bm = d.Bm + (long long)t * d.B_rs; s.Cm = d.Cm + (long long)t * d.C_rs; s.y = d.y + (long long)t * d.y_rs;
             if (t > 0) s.h0 = d.h_out;
+            s.len = d.len - t < SB_MAXT ? d.len - t : SB_MAXT;
             if (step_bulk_ok(s)) {
-                const int rc = n == 1 ? launch_step_bulk<1, true>(s, st) : launch_step_bulk<2, true>(s, st);
+                const int rc = launch_step_bulk<true>(s, st);
                 if (rc) return rc;
+                t += s.len;
                 continue;
             }
+            const int n = d.len - t >= 2 ? 2 : 1;
+            s.len = n;
             cudaError_t e = n == 1 ? launch_step<1, true>(s, st) : launch_step<2, true>(s, st);
             if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_step_kernel, fp16 state)");
+            t += n;
         }
         return CUM_OK;
     }
-    if (d.len <= 2 && step_ok && step_bulk_ok(d)) return d.len == 1 ? launch_step_bulk<1, false>(d, st) : launch_step_bulk<2, false>(d, st);
+    // many streams, up to 8 tokens per call: the TMA-staged kernel (the state is read and written once per call; measured at 4096
+    // streams x 3 layers: 1 token 2.18 ms vs 2.42 per-thread loads, 2 tokens 2.24 vs 3.72)
+    if (step_bulk_ok(d)) return launch_step_bulk<false>(d, st);
     if (d.len <= 2 && step_ok) {
         cudaError_t e = d.len == 1 ? launch_step<1, false>(d, st) : launch_step<2, false>(d, st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(selective_scan_step_kernel)");

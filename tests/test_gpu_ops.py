@@ -29,7 +29,8 @@ def rel_err(a, b):
     # few tokens + carried state: the streaming state-update kernel (selective_scan_step_kernel)
     (2, 64, 2, 64, True, True), (1, 2048, 1, 64, True, True), (3, 48, 2, 64, False, True), (2, 32, 1, 64, True, False), (2, 64, 3, 64, True, True),
     # many streams x whole 64-channel blocks: the TMA-staged state-update kernel (selective_scan_step_bulk_kernel), 1 and 2 tokens
-    (48, 1024, 1, 64, True, True), (41, 1024, 2, 64, False, True), (300, 128, 2, 64, True, True)])
+    (48, 1024, 1, 64, True, True), (41, 1024, 2, 64, False, True), (300, 128, 2, 64, True, True),
+    (48, 1024, 5, 64, True, True), (40, 1024, 16, 64, True, True), (300, 128, 9, 64, False, True)])      # ... up to 16 tokens per call
 def test_selective_scan_matches_oracle(b, d, l, n, with_z, with_h0):
     from cleanumamba_b200 import ops
     g = torch.Generator().manual_seed(b * 1000 + d + l + n)
