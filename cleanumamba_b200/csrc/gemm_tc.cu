@@ -1421,14 +1421,17 @@ int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st) {
         CUM_REQUIRE(d.a_plane_k > 0 && d.a_plane_k % bk == 0, "gemm_tc: plane-major a needs a_plane_k (= %d) to be a multiple of the K-block (%d elements)", d.a_plane_k, bk);
         CUM_REQUIRE(!d.n_half || (d.n % 16 == 0 && !epi_is_glu(d.epilogue)), "gemm_tc: n_half needs n %% 16 == 0 and a non-GLU epilogue");
     }
-    // 128-wide tiles for narrow layers, and for problems whose 256-wide tiles would not even fill the SMs once (streaming / small
-    // batches: M = a few thousand rows, N <= 512 -- e.g. out_proj of 4096 streams x 1 hop is 64 tiles of K = 2048 on 148 SMs):
-    // twice the tiles, half the time per tile.  Same products and accumulation order per output element: bit-identical results.
-    // Measured (E6 streaming from the graph): single stream 0.87 -> 0.75 ms per hop, 512 streams 1.18 -> 1.10 ms; CUM_GEMM_FILL=0 disables
+    // Tile width.  128-wide tiles for narrow layers, and for problems whose 256-wide tiling would fill less than HALF of the SMs
+    // (streaming / small batches: e.g. out_proj of 4096 streams x 1 hop is 64 tiles of K = 2048 on 148 SMs): twice the tiles in the
+    // same single wave, half the time per tile.  Same products and accumulation order per output element: bit-identical results.
+    // Measured (E6 streaming from the graph): single stream 0.87 -> 0.75 ms per hop, 512 streams 1.18 -> 1.10 ms, 4096 streams
+    // unchanged.  Going further (128-wide whenever the wave-quantised time waves x width is smaller, e.g. 384 tiles in 3 waves
+    // instead of 192 in 2) measured SLOWER: 1.16 vs 1.01 ms for the GEMMs of a 4096-stream call -- a 128-wide tile re-reads its A
+    // rows for twice as many column tiles and runs at ~2/3 of the efficiency.  CUM_GEMM_FILL=0 disables
     static int split_env = -1;
     if (split_env < 0) { const char* e = getenv("CUM_GEMM_FILL"); split_env = (e && e[0] == '0') ? 0 : 1; }
     const long long tiles256 = cdiv(d.m, TC_BM) * (long long)d.batch * cdiv(d.n, 256);
-    const bool narrow = d.n <= 128 || (split_env && 2 * tiles256 <= sm_count());      // the doubled tile count still fits one wave
+    const bool narrow = d.n <= 128 || (split_env && 2 * tiles256 <= sm_count());
     if (d.math == CUM_MATH_TF32X3) {
         CUM_REQUIRE(d.w_lo && aligned16(d.w_lo), "gemm_tc: TF32X3 needs w_lo (see cum_split_tf32)");
         return narrow ? dispatch_epi<TC_TF32X3, 128>(d, st) : dispatch_epi<TC_TF32X3, 256>(d, st);
