@@ -70,6 +70,7 @@ class Engine:
     HL16_MIN_CONSUMER_K = int(os.environ.get("CUM_HL16_CK", 256))     # thresholds of the per-tensor hl16 rule (see forward())
     HL16_MIN_PRODUCER_K = int(os.environ.get("CUM_HL16_PK", 256))
     fused_ends = os.environ.get("CUM_FUSED_ENDS", "1") != "0"    # f16x3, 64-channel ends: first / last U-Net block as one kernel each
+    pack_stream_copies = True  # pack the pitch-32 copies of the conv weights the time-major streaming session uses for irregular widths
 
     def __init__(self, model):
         self.model = model
@@ -218,6 +219,28 @@ class Engine:
             meta["dec"].append(dict(Hg=Hg, Hg_p=Hg_p, Co=Co, Co_p=Co_p, Cin_p=c_prev_p))
             c_prev_p = Co_p
 
+        # Time-major streaming (stream_tm.py): a plane-major GEMM operand must be a whole number of 32-element K-blocks wide, so the
+        # carried FIFOs use the channel pitch q32(C) and, where that differs from C_pad (pruned checkpoints), the two convolutions get a
+        # second packed copy with every K segment padded to the pitch (and the transposed conv's column halves padded to 16)
+        q32 = lambda n: (n + 31) // 32 * 32          # noqa: E731
+        padded = self.pack_stream_copies
+        for i, e in enumerate(meta["enc"]):
+            e["Hoq"] = q32(e["Ho_p"])
+            if padded and i and q32(e["Cin_p"]) != e["Cin_p"]:
+                cp, cq, w = e["Cin_p"], q32(e["Cin_p"]), items[f"enc{i}.w"]
+                wq = w.new_zeros(2, w.shape[1], 2 * cq)
+                for j in range(2):
+                    wq[:, :, j * cq: j * cq + cp] = w[:, :, j * cp: (j + 1) * cp]
+                items[f"enc{i}.wq"] = wq
+        for j, dd in enumerate(meta["dec"]):
+            dd["Hgq"], dd["Coq"] = q32(dd["Hg_p"]), (dd["Co_p"] + 15) // 16 * 16
+            if padded and j < D - 1 and (dd["Hgq"] != dd["Hg_p"] or dd["Coq"] != dd["Co_p"]):
+                cp, cq, w, b = dd["Co_p"], dd["Coq"], items[f"dec{j}.w"], items[f"dec{j}.b"]
+                wq = w.new_zeros(2, 2 * cq, dd["Hgq"])
+                for par in range(2):
+                    wq[:, par * cq: par * cq + cp, : dd["Hg_p"]] = w[:, par * cp: (par + 1) * cp, :]
+                items[f"dec{j}.wq"] = wq
+                items[f"dec{j}.bq"] = _pad1(b[:cp], cq)
         items.update(self._extra_items(items))
         # one flat device buffer, every tensor 256-byte aligned
         offs, total = {}, 0
@@ -333,12 +356,14 @@ class Engine:
         self._call(kind, self.lib.cum_gemm_bias_act_fwd, C.byref(d), _lib.stream_ptr(),
                    flops=2 * batch * m * n * k * taps)
 
-    def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None, out_dtype=torch.float32, aux=None, out_off=0):
-        """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers.  ``aux`` (rows, n): the pre-activation (training)."""
+    def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None, out_dtype=torch.float32, aux=None, out_off=0,
+              out_rs=None, add_rs=None):
+        """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers.  ``aux`` (rows, n): the pre-activation (training).
+        ``a_rs`` / ``out_rs`` / ``add_rs``: row pitches of the operands when they are wider than their logical width."""
         n_out = n // 2 if epi >= 8 else n
         c = out if out is not None else self.act_buffer(rows, n_out, out_dtype, a.device)
-        self.gemm(a, a_off, 0, k if a_rs is None else a_rs, rows, k, w, bias, c, out_off, 0, n_out, rows, n, 1, epi,
-                  addend=addend, add_bs=0, add_rs=n_out, aux=aux, aux_rs=n)
+        self.gemm(a, a_off, 0, k if a_rs is None else a_rs, rows, k, w, bias, c, out_off, 0, n_out if out_rs is None else out_rs, rows, n, 1, epi,
+                  addend=addend, add_bs=0, add_rs=n_out if add_rs is None else add_rs, aux=aux, aux_rs=n)
         return c
 
     @staticmethod

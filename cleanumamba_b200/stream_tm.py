@@ -17,7 +17,8 @@ Here every carried buffer is **(column, stream, channel)** -- one contiguous *pl
   * the U-Net skip is read in place from the encoder FIFO as the GEMM's addend;
   * ONE ``cum_stream_shift_fwd`` launch at the end of the call moves every FIFO's unconsumed tail to its front.
 
-All buffers are static (grow-only) so a steady-state call allocates nothing that outlives it, touches only fixed addresses and
+Channel counts that are not multiples of 32 (pruned checkpoints) run on planes padded to a pitch of 32 with padded copies of the
+two convolutions' weights (``engine._pack``: ``enc{i}.wq`` / ``dec{j}.wq``).  All buffers are static (grow-only) so a steady-state call allocates nothing that outlives it, touches only fixed addresses and
 is captured as a CUDA graph without any copy-back epilogue.  The arithmetic per stream is the one of ``StreamSession``
 (same kernels, same products, same accumulation order): outputs are bit-identical to it.
 
@@ -36,24 +37,17 @@ from .streaming import StreamSession, _on_device
 
 
 def time_major_supported(model) -> bool:
-    """Plane-major GEMM operands need every contracted channel count to be a whole number of K-blocks (32 fp32 elements)."""
+    """Every fp32-storage math mode; the bf16-storage variant is offline-forward only."""
     eng = model.engine()
     eng.ensure_packed()
-    if eng.bf16_io:
-        return False
-    meta = eng.meta
-    return (all(e["Cin_p"] % 32 == 0 for e in meta["enc"][1:]) and all(d["Hg_p"] % 32 == 0 for d in meta["dec"][:-1])
-            and all(d["Co_p"] % 16 == 0 for d in meta["dec"][:-1]))
+    return not eng.bf16_io
 
 
 class TimeMajorStreamSession(StreamSession):
     def __init__(self, model, batch: int = 1, auto_graph: bool = False, state_dtype: torch.dtype = torch.float32):
         if state_dtype not in (torch.float32, torch.float16):
             raise ValueError("state_dtype must be torch.float32 or torch.float16")
-        if not time_major_supported(model):
-            raise NotImplementedError("cleanumamba_b200: the time-major streaming session needs channel counts that are multiples of 32 "
-                                      "(use StreamSession)")
-        super().__init__(model, batch=batch, auto_graph=auto_graph)
+        super().__init__(model, batch=batch, auto_graph=auto_graph)       # raises for the bf16-storage variant
         self.state_dtype = state_dtype
         if state_dtype == torch.float16:
             mm0 = self.eng.meta["mamba"]
@@ -70,9 +64,12 @@ class TimeMajorStreamSession(StreamSession):
         self.frames_since_reset = 0
         # encoder level i: planes [0, enc_count[i] - enc_base[i]) of enc_fifo[i] are the outputs the decoder has not consumed yet
         if not hasattr(self, "enc_fifo"):
-            self.enc_fifo = [torch.zeros(4, B, e["Ho_p"], dtype=torch.float32, device=dev) for e in meta["enc"]]
+            # channel pitch of a plane = q32(C): a plane-major GEMM operand is a whole number of 32-element K-blocks wide.  The pad lanes
+            # are zero-initialised and never written (the GEMMs that fill the FIFOs write C_pad columns), the padded weight copies
+            # (engine._pack: enc{i}.wq / dec{j}.wq) have zeros there as well
+            self.enc_fifo = [torch.zeros(4, B, e["Hoq"], dtype=torch.float32, device=dev) for e in meta["enc"]]
             # decoder level j: plane 0 = the carried GLU column g[-1] (replaces the overlap-add tail, :476-484), planes 1.. = this call's
-            self.dec_fifo = [torch.zeros(2, B, d["Hg_p"], dtype=torch.float32, device=dev) for d in meta["dec"]]
+            self.dec_fifo = [torch.zeros(2, B, d["Hgq"], dtype=torch.float32, device=dev) for d in meta["dec"]]
             self.x_buf = torch.zeros(B, max(4, self.frame_length), dtype=torch.float32, device=dev)
             self.n_pend = 0
         else:
@@ -274,47 +271,51 @@ class TimeMajorStreamSession(StreamSession):
                           pk["enc0.w"].data_ptr(), pk["enc0.b"].data_ptr(), y.data_ptr(), e["Hc_p"], B * e["Hc_p"], rows_new, e["Hc_p"], 4, 2,
                           ptr(scale), per_frame, row_off, st())
             else:
-                src, cp = self.enc_fifo[i - 1], e["Cin_p"]
+                src, cq = self.enc_fifo[i - 1], meta["enc"][i - 1]["Hoq"]
+                wkey = f"enc{i}.wq" if f"enc{i}.wq" in pk else f"enc{i}.w"
                 lo = 2 * c_old - self.enc_base[i - 1]                    # plane of the first input column this call needs
                 # output column t of every stream = W01 . [plane lo+2t | plane lo+2t+1] + W23 . [plane lo+2t+2 | lo+2t+3]
-                eng.gemm(src, 0, B * cp, cp, B, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"], y, 0, B * e["Hc_p"], e["Hc_p"], B, e["Hc_p"],
-                         rows_new, EPI_RELU, taps=2, shifts=(0, 1), planes=(fill[i - 1] + cols[i - 1], cp, lo, 2, 0))
-            ho = e["Ho_p"]
+                eng.gemm(src, 0, B * cq, cq, B, 2 * cq, wkey, pk[f"enc{i}.b"], y, 0, B * e["Hc_p"], e["Hc_p"], B, e["Hc_p"],
+                         rows_new, EPI_RELU, taps=2, shifts=(0, 1), planes=(fill[i - 1] + cols[i - 1], cq, lo, 2, 0))
+            ho, hoq = e["Ho_p"], e["Hoq"]
             self.enc_fifo[i] = self._grow_planes(self.enc_fifo[i], fill[i] + rows_new, fill[i])
             # the GLU 1x1 conv appends its planes to the level's FIFO directly
             eng.dense(y, rows_new * B, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * ho, epi=act, out=self.enc_fifo[i],
-                      out_off=fill[i] * B * ho)
+                      out_off=fill[i] * B * hoq, out_rs=hoq)
 
         # ---------------- bottleneck: F tokens per stream, time-major rows (t * B + b)
         last = self.enc_fifo[D - 1]
-        cbp = meta["enc"][-1]["Ho_p"]
+        cbp, cbq = meta["enc"][-1]["Ho_p"], meta["enc"][-1]["Hoq"]
         assert fill[D - 1] + cols[D - 1] == F, (fill[D - 1], cols[D - 1], F)
-        h = eng.dense(last, B * F, cbp, "t1.w", pk["t1.b"], meta["dm_p"])
+        h = eng.dense(last, B * F, cbp, "t1.w", pk["t1.b"], meta["dm_p"], a_rs=cbq)
         hn = eng.mamba_layers(h, B, F, states=self.states, tm=True)
-        xcur = eng.dense(hn, B * F, meta["dm_p"], "t2.w", pk["t2.b"], cbp, addend=last)
+        xcur = eng.dense(hn, B * F, meta["dm_p"], "t2.w", pk["t2.b"], cbp, addend=last, add_rs=cbq)
+        x_rs = cbp                                      # row pitch of xcur
 
         # ---------------- decoder
         d_cols = F
         out = None
         for j, dd in enumerate(meta["dec"]):
-            hg = dd["Hg_p"]
+            hg, hgq = dd["Hg_p"], dd["Hgq"]
             self.dec_fifo[j] = G = self._grow_planes(self.dec_fifo[j], d_cols + 1, 1)
-            eng.dense(xcur, B * d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * hg, epi=act, out=G, out_off=B * hg)
-            shifts.append((G, 0, d_cols * B * hg, B * hg, 1))            # the last column becomes the carried one
+            eng.dense(xcur, B * d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * hg, epi=act, out=G, out_off=B * hgq, out_rs=hgq,
+                      a_rs=x_rs)
+            shifts.append((G, 0, d_cols * B * hgq, B * hgq, 1))          # the last column becomes the carried one
             if j < D - 1:
-                co = dd["Co_p"]
+                coq = dd["Coq"]
                 lvl = D - 2 - j
-                skip = self.enc_fifo[lvl]
-                nxt = torch.empty(2 * d_cols, B, co, dtype=torch.float32, device=dev)
+                skip, skq = self.enc_fifo[lvl], meta["enc"][lvl]["Hoq"]
+                wkey, bkey = (f"dec{j}.wq", f"dec{j}.bq") if f"dec{j}.wq" in pk else (f"dec{j}.w", f"dec{j}.b")
+                nxt = torch.empty(2 * d_cols, B, coq, dtype=torch.float32, device=dev)
                 # output column 2p + par of every stream = Wa_par . G[p + 1] + Wb_par . G[p] + skip column 2p + par (read in place)
-                eng.gemm(G, 0, B * hg, hg, B, hg, f"dec{j}.w", pk[f"dec{j}.b"], nxt, 0, B * co, co, B, co, 2 * d_cols, EPI_RELU,
-                         taps=2, shifts=(1, 0), addend=skip, add_bs=B * co, add_rs=co, planes=(d_cols + 1, hg, 0, 1, 1))
-                xcur = nxt
+                eng.gemm(G, 0, B * hgq, hgq, B, hgq, wkey, pk[bkey], nxt, 0, B * coq, coq, B, coq, 2 * d_cols, EPI_RELU,
+                         taps=2, shifts=(1, 0), addend=skip, add_bs=B * skq, add_rs=skq, planes=(d_cols + 1, hgq, 0, 1, 1))
+                xcur, x_rs = nxt, coq
                 d_cols = 2 * d_cols
             else:
                 length = 2 * d_cols
                 out = torch.empty(B, length, dtype=torch.float32, device=dev)
-                eng._call("convt_out", lib.cum_convt_out_strided_fwd, G.data_ptr(), hg, B * hg, B, d_cols + 1, hg,
+                eng._call("convt_out", lib.cum_convt_out_strided_fwd, G.data_ptr(), hgq, B * hgq, B, d_cols + 1, hg,
                           pk[f"dec{j}.w"].data_ptr(), meta["out_bias"], ptr(scale), self.hop, out.data_ptr(), length, 2, length, 4, 2, st())
 
         # ---------------- FIFO maintenance: one launch
@@ -328,7 +329,7 @@ class TimeMajorStreamSession(StreamSession):
             left = fill[i] + cols[i] - consumed[i]
             assert left >= 0
             if left:
-                pe = B * e["Ho_p"]
+                pe = B * e["Hoq"]
                 shifts.append((self.enc_fifo[i], 0, consumed[i] * pe, left * pe, 1))
         left = n_total - F * self.hop
         if left:

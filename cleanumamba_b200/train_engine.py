@@ -49,6 +49,8 @@ class TrainEngine(Engine):
             self.model_math_override = "tf32x3"
         super()._pack()
 
+    pack_stream_copies = False     # training never streams
+
     def _extra_items(self, items: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         extra = {}
         for k, t in items.items():

@@ -242,12 +242,41 @@ def test_auto_layout_picks_time_major_for_many_streams_only():
     net = toy("f16x3", False)
     assert isinstance(net.stream_session(batch=64), TimeMajorStreamSession)
     assert not isinstance(net.stream_session(batch=8), TimeMajorStreamSession)
-    odd = toy("f16x3", False, channels_H=24, max_H=40)             # channel counts that are not whole K-blocks: stream-major
-    assert not isinstance(odd.stream_session(batch=64), TimeMajorStreamSession)
-    with pytest.raises(NotImplementedError):
-        odd.stream_session(batch=64, layout="time_major")
+    odd = toy("f16x3", False, channels_H=24, max_H=40)             # channel counts that are not whole K-blocks: planes padded to 32
+    assert isinstance(odd.stream_session(batch=64), TimeMajorStreamSession)
     with pytest.raises(NotImplementedError):
         net.stream_session(batch=4, state_dtype=torch.float16)
+    with pytest.raises(ValueError):
+        net.stream_session(batch=4, layout="columns")
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("name,math", [("e6_pruned_200k", "fp32"), ("e6_pruned_200k", "f16x3"), ("e8_pruned_500k", "f16x3"), ("e8_pruned_500k", "tf32x3"),
+                                       ("tiny_equalwidth_seed0", "fp32")])
+def test_time_major_session_on_pruned_checkpoints_matches_stream_oracle(name, math, normalize):
+    """The shipped pruned checkpoints (irregular channel counts: planes padded to a pitch of 32, padded weight copies) on the
+    time-major session: ragged chunks, 1-hop and multi-hop calls, flush -- against one StreamOracle per stream, and against the
+    stream-major session (same arithmetic up to the summation order of the zero-padded K-blocks)."""
+    from conftest import load_golden
+    from cleanumamba_b200.network import Net
+    fx = load_golden(name)
+    net = Net("CleanUMamba", {**json.loads(fx["config"]), "normalize_input": normalize, "math_mode": math})
+    net.load_pruned_state_dict(fx["state_dict"])
+    net = net.cuda().float().eval()
+    hop, fl = net.total_stride, net.frame_length
+    B = 3
+    sizes = [11, fl - 11, hop, hop, 2 * hop, 5, hop - 5, hop * 6, hop, hop * 9 + 3, hop - 3]
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, sum(sizes), generator=g) * 0.1 * (1 + torch.arange(B)[:, None])
+    tm = run_session(net.stream_session(batch=B, layout="time_major"), x, sizes)
+    sm = run_session(net.stream_session(batch=B, layout="stream_major"), x, sizes)
+    assert tm.shape == sm.shape == x.shape
+    assert (tm - sm).abs().max().item() < 2e-5
+    tol = 2e-5 if math == "fp32" else 1e-4
+    for b in range(B):
+        so = orc.StreamOracle(fx["state_dict"], normalize_input=normalize)
+        want = torch.cat([so.feed(x[b:b + 1]), so.flush()], 1)
+        assert (tm[b:b + 1] - want).abs().max().item() < tol
 
 
 @pytest.mark.parametrize("normalize", [False, True])
