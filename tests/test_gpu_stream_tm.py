@@ -241,11 +241,13 @@ def test_auto_layout_picks_time_major_for_many_streams_only():
     from cleanumamba_b200.stream_tm import TimeMajorStreamSession
     net = toy("f16x3", False)
     assert isinstance(net.stream_session(batch=64), TimeMajorStreamSession)
-    assert not isinstance(net.stream_session(batch=8), TimeMajorStreamSession)
+    assert isinstance(net.stream_session(batch=net.TIME_MAJOR_MIN_STREAMS), TimeMajorStreamSession)
+    assert not isinstance(net.stream_session(batch=net.TIME_MAJOR_MIN_STREAMS - 1), TimeMajorStreamSession)
+    assert not isinstance(net.stream_session(batch=1), TimeMajorStreamSession)
     odd = toy("f16x3", False, channels_H=24, max_H=40)             # channel counts that are not whole K-blocks: planes padded to 32
     assert isinstance(odd.stream_session(batch=64), TimeMajorStreamSession)
     with pytest.raises(NotImplementedError):
-        net.stream_session(batch=4, state_dtype=torch.float16)
+        net.stream_session(batch=2, state_dtype=torch.float16)
     with pytest.raises(ValueError):
         net.stream_session(batch=4, layout="columns")
 
