@@ -18,5 +18,9 @@ class Activation(nn.Module):
     def extra_repr(self) -> str:
         return f"glu={self.kind}, bypass_channels={self.bypass_channels}"
 
-    def forward(self, input):  # pragma: no cover - never on the product path
-        raise RuntimeError("cleanumamba_b200.Activation is fused into the GEMM epilogue; call the model's forward()")
+    def forward(self, input):
+        """Stand-alone call of the module (the model's forward never takes this path: the gate is a GEMM epilogue there)."""
+        if self.bypass_channels != 0:
+            raise NotImplementedError("cleanumamba_b200: bypass_channels != 0 is not on the shipped path")
+        from . import ops
+        return ops.glu_forward(input, self.kind)

@@ -130,12 +130,72 @@ def layer_norm_residual(h, residual, weight, bias, eps=1e-5):
     return no[:, :c].reshape(h.shape), ro[:, :c].reshape(h.shape)
 
 
+def _linear(x, weight, bias=None, math="f16x3"):
+    """(b, l, k) x (n, k)^T (+ bias) on the tap-GEMM; k and n padded to multiples of 8 with zeros."""
+    b, l, k = x.shape
+    n = weight.shape[0]
+    kp, np_ = (k + 7) // 8 * 8, (n + 7) // 8 * 8
+    a = x.detach().float()
+    if kp != k or not a.is_contiguous():
+        a = torch.nn.functional.pad(a, (0, kp - k)).contiguous()
+    w = torch.zeros(1, np_, kp, dtype=torch.float32, device=x.device)
+    w[0, :n, :k] = weight.detach().float()
+    bv = None
+    if bias is not None:
+        bv = torch.zeros(np_, dtype=torch.float32, device=x.device)
+        bv[:n] = bias.detach().float()
+    return gemm_bias_act(a, w, bv, _lib.EPI_NONE, math=math)[..., :n]
+
+
+@torch.no_grad()
 def mamba_mixer_forward(mixer, hidden_states, inference_params=None):
-    raise NotImplementedError("stand-alone Mamba.forward is served through CleanUMamba.forward / StreamSession")
+    """Stand-alone ``Mamba.forward`` (mamba_ssm 1.2.2 ``Mamba.forward`` slow path) on the library's kernels:
+    in_proj -> causal depthwise conv + SiLU -> x_proj -> dt_proj -> selective scan (softplus, D skip, SiLU(z) gate) -> out_proj.
+    hidden_states: (batch, len, d_model) on CUDA.  Inference only; inside ``CleanUMamba.forward`` the engine runs the same kernels on
+    its packed weights without the layout changes made here.  Step mode (``inference_params``) is served by ``stream_session``."""
+    if inference_params is not None:
+        raise NotImplementedError("cleanumamba_b200: stand-alone Mamba.step (inference_params) is served through stream_session()")
+    _need_cuda(hidden_states)
+    math = getattr(mixer, "math_mode", "f16x3")
+    di, n = mixer.A_log.shape
+    r = mixer.dt_proj.weight.shape[1]
+    xz = _linear(hidden_states, mixer.in_proj.weight, mixer.in_proj.bias, math)                 # (b, l, 2 di)
+    x, z = xz[..., :di].permute(0, 2, 1), xz[..., di:].permute(0, 2, 1)                          # (b, di, l)
+    x = causal_conv1d_fn(x, mixer.conv1d.weight[:, 0, :], mixer.conv1d.bias, "silu")
+    x_dbl = _linear(x.permute(0, 2, 1), mixer.x_proj.weight, None, math)                          # (b, l, r + 2 n)
+    dt = _linear(x_dbl[..., :r], mixer.dt_proj.weight, None, math).permute(0, 2, 1)               # (b, di, l); bias goes in as delta_bias
+    Bm, Cm = x_dbl[..., r: r + n].permute(0, 2, 1), x_dbl[..., r + n:].permute(0, 2, 1)          # (b, n, l)
+    y = selective_scan_fn(x, dt, -torch.exp(mixer.A_log.detach().float()), Bm, Cm, mixer.D.detach().float(), z,
+                          mixer.dt_proj.bias.detach().float(), True)
+    return _linear(y.permute(0, 2, 1), mixer.out_proj.weight, mixer.out_proj.bias, math).to(hidden_states.dtype)
 
 
+@torch.no_grad()
 def block_forward(block, hidden_states, residual=None, inference_params=None):
-    raise NotImplementedError("stand-alone Block.forward is served through CleanUMamba.forward / StreamSession")
+    """Stand-alone ``Block.forward`` (mamba_ssm ``Block``: residual add -> LayerNorm -> mixer; returns (hidden_states, residual))."""
+    _need_cuda(hidden_states, residual)
+    normed, res = layer_norm_residual(hidden_states, residual, block.norm.weight, block.norm.bias, block.norm.eps)
+    return block.mixer(normed.to(hidden_states.dtype), inference_params=inference_params), res.to(hidden_states.dtype)
+
+
+@torch.no_grad()
+def glu_forward(x, kind="Sigmoid"):
+    """Stand-alone GLU of layers.Activation (/root/reference/src/network/layers.py:26-33, bypass_channels = 0): (b, 2c, l) ->
+    a * sigmoid(b) on the library's gate kernel (the model's forward fuses the gate into the 1x1-conv GEMM epilogue instead)."""
+    if kind != "Sigmoid":
+        raise NotImplementedError("cleanumamba_b200: the stand-alone GLU kernel implements the Sigmoid gate (other gates: GEMM epilogues only)")
+    _need_cuda(x)
+    lib = _lib.init(x.device)
+    b, c2, l = x.shape
+    c = c2 // 2
+    cp = (c + 3) // 4 * 4
+    z = torch.zeros(b * l, 2 * cp, dtype=torch.float32, device=x.device)          # interleaved (a_c, b_c) rows, see cum_glu_fwd
+    xt = x.detach().float().permute(0, 2, 1).reshape(b * l, c2)
+    z[:, 0: 2 * c: 2] = xt[:, :c]
+    z[:, 1: 2 * c: 2] = xt[:, c:]
+    out = torch.empty(b * l, cp, dtype=torch.float32, device=x.device)
+    check(lib.cum_glu_fwd(z.data_ptr(), None, out.data_ptr(), b * l, cp, _lib.stream_ptr()), "cum_glu_fwd")
+    return out[:, :c].reshape(b, l, c).permute(0, 2, 1).to(x.dtype)
 
 
 @torch.no_grad()

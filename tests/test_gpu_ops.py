@@ -488,3 +488,37 @@ def test_fused_mr_stft_loss_matches_pytorch_restatement(b, t):
     err = (pd.grad.cpu() - pred.grad).abs().max().item()
     print(f"\n[fused MR-STFT loss b={b} t={t}] sc {sc.item():.6f} mag {mag.item():.6f} grad max-abs err / scale {err / scale:.2e}")
     assert err / scale < 1e-3
+
+
+@pytest.mark.parametrize("name", ["e8_pruned_500k", "mini_mamba_442k"])
+def test_standalone_submodule_forwards_match_oracle(name):
+    """The module tree's submodules are individually callable like the reference's (pruning / analysis code does that):
+    ``Block.forward`` / ``Mamba.forward`` (mamba_ssm slow path) and the GLU ``Activation`` on the library's kernels, against the
+    oracle's mixer / LayerNorm / GLU on a trained checkpoint."""
+    import json
+    from conftest import load_golden
+    from cleanumamba_b200.network import Net
+    fx = load_golden(name)
+    net = Net("CleanUMamba", json.loads(fx["config"]))
+    net.load_pruned_state_dict(fx["state_dict"])
+    net = net.cuda().float().eval()
+    sd = {k: v.float() for k, v in fx["state_dict"].items()}
+    dm = net.tsfm_conv1.weight.shape[0]
+    g = torch.Generator().manual_seed(5)
+    h = torch.randn(2, 37, dm, generator=g)
+    res = torch.randn(2, 37, dm, generator=g)
+    blk = net.tsfm_Mamba_layers[1]
+    p = "tsfm_Mamba_layers.1."
+    want_res = h + res
+    normed = F.layer_norm(want_res, (dm,), sd[p + "norm.weight"], sd[p + "norm.bias"], blk.norm.eps)
+    want = orc.mamba_mixer(normed, sd, p + "mixer.")
+    out, r = blk(h.cuda(), res.cuda())
+    assert out.shape == want.shape and torch.equal(r.cpu(), want_res)
+    assert rel_err(out, want) < 2e-4                       # f16x3 products through four GEMMs + the scan
+    out0 = blk.mixer(normed.cuda())
+    assert rel_err(out0, want) < 2e-4
+    with pytest.raises(NotImplementedError):
+        blk.mixer(normed.cuda(), inference_params=object())
+    x = torch.randn(2, 2 * 24, 50, generator=g)
+    y = net.encoder[0][3](x.cuda())                         # layers.Activation (GLU)
+    assert rel_err(y, orc.glu(x)) < 1e-6
