@@ -359,11 +359,12 @@ def measure_train(net, dev, rank, world, dist, B, seconds, steps, warmup, math="
         ms_local, _ = timed(max(2, steps // 2))
         ms_local /= max(2, steps // 2)
         net._grad_sync = sync
-        allreduce = {"bytes": sum(buckets), "buckets": dict(zip(("decoder", "bottleneck", "encoder"), buckets)), "overlapped": True,
+        allreduce = {"bytes": sum(buckets), "buckets": dict(zip(("decoder", "bottleneck", "encoder_deep", "encoder_outer"), buckets)), "overlapped": True,
                      "ms_per_step_without_allreduce": round(ms_local, 3),
                      "exposed_ms_per_step": round(ms / steps - ms_local, 3),
                      "stream_stall_on_nccl_ms_per_step": round(exposed, 3),
-                     "limiting_bucket": "encoder (the last one the backward completes: nothing is left to hide it behind)"}
+                     "limiting_bucket": "encoder_outer (the last one the backward completes: nothing is left to hide it behind; the deep encoder levels "
+                                        "-- almost all of the encoder's bytes -- are reduced under the backward of the outer levels)"}
     kernels = {k: {"ms_per_step": round(v["ms"] / steps, 3), "launches_per_step": v["launches"] // steps,
                    "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] and v["ms"] else None}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}

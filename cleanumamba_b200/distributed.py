@@ -5,10 +5,12 @@ from rank 0, then -- once the WHOLE backward has finished -- flattens every grad
 all-reduces it, divides by the world size and copies it back (no overlap with compute).
 
 Here the backward kernels already write into ONE flat fp32 buffer in packed-weight order (train_engine.TrainEngine.gflat),
-so there is no flatten / unflatten, and the buffer is reduced in three contiguous buckets as soon as each is complete --
-decoder, bottleneck, encoder: the order the backward produces them -- with ``async_op=True`` so NCCL (NVLink 5 /
-NVSwitch; NVLS in-switch reduction when available) runs on its own stream underneath the remaining backward kernels.
-Only the last (encoder) bucket is exposed.  The same object works over gloo for the CPU tests.
+so there is no flatten / unflatten, and the buffer is reduced in four contiguous buckets as soon as each is complete --
+decoder, bottleneck, the deep encoder levels, the outer encoder levels: the order the backward produces them -- with
+``async_op=True`` so NCCL (NVLink 5 / NVSwitch; NVLS in-switch reduction when available) runs on its own stream underneath
+the remaining backward kernels.  Only the last bucket is exposed, and it is the outer encoder levels' 1.3 MB: the deep levels
+(58 MB of the encoder's 59 MB) are reduced under the backward of the outer levels, whose activations are the largest of the
+model (compute-stream stall on NCCL at 2 GPUs: 0.68 -> 0.04 ms per step).  The same object works over gloo for the CPU tests.
 """
 from typing import List, Optional
 

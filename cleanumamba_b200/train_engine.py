@@ -87,9 +87,17 @@ class TrainEngine(Engine):
         self.gflat = torch.zeros(base_total + 64, dtype=torch.float32, device=self.device)
         self.gk = {k: self.gflat[offs[k]: offs[k] + items[k].numel()].view(items[k].shape) for k in base}
         self.gk["out_bias"] = self.gflat[base_total: base_total + 4]
-        # all-reduce buckets in the order the backward completes them: decoder (+ out bias), bottleneck, encoder
+        # all-reduce buckets in the order the backward completes them: decoder (+ out bias), bottleneck, the DEEP encoder levels (almost
+        # all of the encoder's bytes: their reduction hides behind the backward of the outer levels, whose activations are the largest
+        # of the model), and last the few outer levels (<= 2 MB: all that is left exposed)
+        D = self.meta["D"]
+        k_split = 1
+        while k_split < D - 1 and 4 * offs[f"enc{k_split + 1}.w"] <= (2 << 20):
+            k_split += 1
+        self.enc_split_level = k_split if D >= 2 else -1
+        cut = offs[f"enc{k_split}.w"] if D >= 2 else offs["t1.w"]
         self.buckets = dict(decoder=(offs["dec0.wg"], base_total + 64), bottleneck=(offs["t1.w"], offs["dec0.wg"]),
-                            encoder=(0, offs["t1.w"]))
+                            encoder_deep=(cut, offs["t1.w"]), encoder_outer=(0, cut))
 
     # ---------------------------------------------------------------------------------------------- helpers
     def new(self, *shape):
@@ -426,10 +434,12 @@ class TrainEngine(Engine):
                 self.gemm(y, 0, Ls[i + 1] * hc, hc, Ls[i + 1], hc, f"enc{i}.wT", None, dprev, 0, Ls[i] * cp, 2 * cp, Ls[i] // 2,
                           2 * cp, B, EPI_NONE, taps=2, shifts=(0, -1), addend=dskip[i - 1], add_bs=Ls[i] * cp, add_rs=2 * cp, a_scale=sc)
                 dskip[i - 1] = dprev
+                if i == self.enc_split_level:
+                    bucket_done("encoder_deep")
             else:
                 self._call("conv_in_bwd", lib.cum_conv_in_bwd, S["x"].data_ptr(), L, B, L, y.data_ptr(), dy.data_ptr(),
                            gk["enc0.w"].data_ptr(), gk["enc0.b"].data_ptr(), Ls[1], hc, 4, 2, st())
-        bucket_done("encoder")
+        bucket_done("encoder_outer")
         return gk
 
     # ---------------------------------------------------------------------------------------------- unpack

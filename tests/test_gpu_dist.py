@@ -78,4 +78,4 @@ def test_nccl_bucketed_allreduce_equals_single_rank_gradients():
     assert ret["w0"] == ret["w1"], "rank 1 did not receive rank 0's parameters"
     # mean-reduced loss over equal per-rank batches: average of rank gradients == gradient of the concatenated batch
     assert ret["worst"] < 1e-4, ret["worst"]
-    assert ret["bytes"] == ret["expect_bytes"]      # the three buckets tile the whole flat gradient buffer
+    assert ret["bytes"] == ret["expect_bytes"]      # the buckets tile the whole flat gradient buffer
