@@ -167,9 +167,10 @@ class CleanUMamba(nn.Module):
         return {i: self.allocate_inference_cache_layer(blk.mixer, batch_size, dtype=dtype)
                 for i, blk in enumerate(self.tsfm_Mamba_layers)}
 
-    TIME_MAJOR_MIN_STREAMS = 4      # from this many concurrent streams the session keeps its buffers (column, stream, channel).  Measured
-                                    # (E6 full, 1 hop per call from the graph): 4 streams 0.81 -> 0.73 ms, 64 streams 0.89 -> 0.79 ms, 4096
-                                    # streams 5.05 -> 3.99 ms; one stream 0.76 vs 0.74 ms: the module-level feed() keeps the stream-major session
+    TIME_MAJOR_MIN_STREAMS = 1      # from this many concurrent streams the session keeps its buffers (column, stream, channel).  Measured
+                                    # (E6 full, 1 hop per call from the graph): 1 stream 0.47 -> 0.41 ms, 2 streams 0.60 -> 0.46 ms, 64 streams
+                                    # 0.89 -> 0.79 ms, 4096 streams 5.05 -> 3.99 ms: time-major at every stream count; layout="stream_major"
+                                    # keeps the other session available
 
     def stream_session(self, batch=1, auto_graph=False, layout="auto", state_dtype=torch.float32):
         """New carried-state streaming session for ``batch`` independent streams (extension: the reference's

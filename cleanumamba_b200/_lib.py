@@ -32,7 +32,8 @@ class GemmDesc(C.Structure):
                 ("math", C.c_int), ("w_lo", C.c_void_p), ("acc_scale", C.c_float), ("out_bf16", C.c_int), ("w_lo_is_zero", C.c_int),
                 ("a_lo", C.c_void_p), ("c_lo", C.c_void_p), ("addend_lo", C.c_void_p), ("a_scale_dev", C.c_void_p), ("addend_is_mask", C.c_int), ("aux", C.c_void_p), ("aux_batch_stride", C.c_longlong), ("aux_row_stride", C.c_longlong),
                 ("cta_pair", C.c_int),
-                ("a_planes", C.c_int), ("a_plane_k", C.c_int), ("a_plane0", C.c_int), ("a_plane_step", C.c_int), ("n_half", C.c_int)]
+                ("a_planes", C.c_int), ("a_plane_k", C.c_int), ("a_plane0", C.c_int), ("a_plane_step", C.c_int), ("n_half", C.c_int),
+                ("small_m_path", C.c_int)]
 
 
 class Enc0BlockDesc(C.Structure):

@@ -202,6 +202,7 @@ int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream) {
     if (!desc) { set_error("gemm: null descriptor"); return CUM_EINVAL; }
     int rc = validate_gemm(*desc);
     if (rc != CUM_OK) return rc;
+    if (gemm_skinny_ok(*desc)) return gemm_skinny_fwd(*desc, (cudaStream_t)stream);
     switch (desc->math) {
         case CUM_MATH_FP32: return gemm_simt_fwd(*desc, (cudaStream_t)stream);
         case CUM_MATH_TF32X3:

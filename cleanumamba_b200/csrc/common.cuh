@@ -99,6 +99,8 @@ int convt_out_fwd(const float* g, int batch, int rows_in, int c_pad, const float
                   const float* scale, int scale_group, float* out, long long out_stride, int first, int length,
                   int kernel, int stride, cudaStream_t st, bool in_bf16 = false, long long g_bs = 0, long long g_rs = 0);
 int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st);
+bool gemm_skinny_ok(const cum_gemm_desc& d);        // a few output rows in total (single-stream streaming): CUDA-core path
+int gemm_skinny_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int gemm_tc_fwd(const cum_gemm_desc& d, cudaStream_t st);
 int enc0_block_fwd(const cum_enc0_block_desc& d, cudaStream_t st);
 int dec_last_block_fwd(const cum_dec_last_block_desc& d, cudaStream_t st);

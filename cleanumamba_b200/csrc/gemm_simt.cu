@@ -8,6 +8,10 @@
 // that every shared-memory read is a conflict-free float4, register-staged double buffering of the global loads.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 namespace cum {
 
 constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16, SG_THREADS = 256;
@@ -174,6 +178,155 @@ int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm: n=%d or batch=%d too large for the grid", d.n, d.batch);
     gemm_simt_kernel<<<grid, SG_THREADS, 0, st>>>(p);
     CUM_LAUNCH_CHECK("gemm_simt_kernel");
+    return CUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Skinny tap-GEMM: the whole problem has at most SK_MAX_ROWS output rows (one stream fed hop by hop -- the reference's real-time use,
+// CleanUMamba.py:371-418 / examples/streaming_demo.py -- or a handful of streams: every GEMM of a call is 1-33 rows).  The tcgen05
+// kernel is a persistent pipeline (TMEM allocation, barrier ring, tensor-map prefetch, 128-row tiles): ~14 us per launch whatever the
+// size, 36 launches per hop.  Here a warp owns TWO output columns (one GLU pair) for up to 8 rows, its lanes split K (coalesced
+// 16-byte weight loads, the few A rows come from L1), a butterfly reduction ends the K loop and lane r finishes row r (bias,
+// activation / gate, addend).  Products are exact fp32 FMAs on the full-precision weights (split modes: hi + lo halves), so this
+// path is at least as accurate as the tensor-core modes it stands in for.  Same descriptor semantics as the kernels above.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SK_MAX_ROWS = 64;     // m * batch up to which cum_gemm_bias_act_fwd takes this path
+constexpr int SK_M = 8;             // rows per warp pass
+constexpr int SK_WARPS = 4;
+
+// four consecutive weights w[k .. k+3] of one weight row; WF: 0 fp32, 1 fp32 hi + lo (TF32X3), 2 fp16 hi + lo (F16X3, scaled), 3 bf16 hi + lo
+template <int WF>
+__device__ __forceinline__ float4 sk_load_w(const void* w, const void* w_lo, long long off) {
+    if (WF == 0) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w) + off));
+    if (WF == 1) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w) + off));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w_lo) + off));
+        return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(w) + off));
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(w_lo) + off));
+    float2 h0, h1, l0, l1;
+    if (WF == 2) {
+        h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)); h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+        l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)); l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+    } else {
+        h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.x)); h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.y));
+        l0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.x)); l1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.y));
+    }
+    return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+}
+
+struct SkinnyParams { SimtParams s; const void* w_lo; float acc_scale; };
+
+template <int WF>
+__global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const SkinnyParams q) {
+    pdl_trigger();
+    pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
+    const SimtParams& p = q.s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int n = (blockIdx.x * SK_WARPS + warp) * 2;          // this warp's two output columns (weight rows n, n + 1)
+    if (n >= p.n) return;
+    const int nh_off = (p.n_half && (b & 1)) ? p.n : 0;
+    const bool glu = p.epi >= CUM_EPI_GLU_SIGMOID;
+    for (int m0 = 0; m0 < p.m; m0 += SK_M) {
+        float acc[SK_M][2];
+#pragma unroll
+        for (int r = 0; r < SK_M; ++r) acc[r][0] = acc[r][1] = 0.f;
+        for (int tap = 0; tap < p.taps; ++tap) {
+            const int shift = tap == 0 ? p.shift0 : p.shift1;
+            const long long wrow = (long long)tap * p.w_tap_stride + (long long)(n + nh_off) * p.ldw;
+#pragma unroll 2
+            for (int kk = lane * 4; kk < p.k; kk += 128) {
+                const float4 w0 = sk_load_w<WF>(p.w, q.w_lo, wrow + kk);
+                const float4 w1 = sk_load_w<WF>(p.w, q.w_lo, wrow + p.ldw + kk);
+                // A addressing as in gemm_simt_kernel (plane-major: the tap shift and the upper part of K select the plane)
+                int ka = kk, rshift = shift;
+                const float* abase = p.a + (long long)b * p.a_bs;
+                bool plane_ok = true;
+                if (p.a_planes) {
+                    const int kp = kk / p.a_plane_k;
+                    const int pl = p.a_plane0 + p.a_plane_step * ((p.n_half ? b >> 1 : b) + shift) + kp;
+                    ka = kk - kp * p.a_plane_k;
+                    rshift = 0;
+                    plane_ok = pl >= 0 && pl < p.a_planes;
+                    abase = p.a + (long long)pl * p.a_bs;
+                }
+#pragma unroll
+                for (int r = 0; r < SK_M; ++r) {
+                    const int row = m0 + r + rshift;
+                    if (plane_ok && m0 + r < p.m && row >= 0 && row < p.a_rows) {
+                        const float4 av = __ldg(reinterpret_cast<const float4*>(abase + (long long)row * p.a_rs + ka));
+                        acc[r][0] = fmaf(av.x, w0.x, fmaf(av.y, w0.y, fmaf(av.z, w0.z, fmaf(av.w, w0.w, acc[r][0]))));
+                        acc[r][1] = fmaf(av.x, w1.x, fmaf(av.y, w1.y, fmaf(av.z, w1.z, fmaf(av.w, w1.w, acc[r][1]))));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SK_M; ++r) { acc[r][0] = warp_sum(acc[r][0]); acc[r][1] = warp_sum(acc[r][1]); }
+        // lane r finishes row m0 + r (every lane holds every total after the butterfly)
+        float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < SK_M; ++r) if (lane == r) { v0 = acc[r][0]; v1 = acc[r][1]; }
+        const int m = m0 + lane;
+        if (lane < SK_M && m < p.m) {
+            v0 *= q.acc_scale; v1 *= q.acc_scale;
+            if (p.bias) { v0 += __ldg(p.bias + n); v1 += __ldg(p.bias + n + 1); }
+            float* crow = p.c + (long long)b * p.c_bs + (long long)m * p.c_rs;
+            const float* arow = p.addend ? p.addend + (long long)b * p.add_bs + (long long)m * p.add_rs : nullptr;
+            if (glu) {
+                float o = v0 * glu_gate(p.epi, v1);
+                if (arow) o += __ldg(arow + (n >> 1));
+                crow[n >> 1] = o;
+            } else {
+                float o0 = unary_act(p.epi, v0), o1 = unary_act(p.epi, v1);
+                if (arow) { o0 += __ldg(arow + n); o1 += __ldg(arow + n + 1); }
+                *reinterpret_cast<float2*>(crow + n) = make_float2(o0, o1);
+            }
+        }
+    }
+}
+
+bool gemm_skinny_ok(const cum_gemm_desc& d) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("CUM_GEMM_SKINNY"); env = (e && e[0] == '0') ? 0 : 1; }
+    if (!env || d.math == CUM_MATH_BF16 || d.math == CUM_MATH_TF32 || d.a_lo || d.c_lo || d.addend_lo || d.out_bf16 || d.aux || d.addend_is_mask ||
+        d.a_scale_dev || d.batch > 65535)
+        return false;
+    if ((d.math == CUM_MATH_TF32X3 || d.math == CUM_MATH_BF16X3 || d.math == CUM_MATH_F16X3) && !d.w_lo) return false;
+    if (d.math != CUM_MATH_FP32 && d.math != CUM_MATH_TF32X3 && d.ldw % 8) return false;       // 16-bit weight rows: 8-byte aligned quads
+    if (d.small_m_path) return d.small_m_path > 0;
+    return (long long)d.m * d.batch <= SK_MAX_ROWS;
+}
+
+int gemm_skinny_fwd(const cum_gemm_desc& d, cudaStream_t st) {
+    SkinnyParams q;
+    SimtParams& p = q.s;
+    p.a = d.a; p.a_bs = d.a_batch_stride; p.a_rs = d.a_row_stride; p.a_rows = d.a_rows; p.k = d.k; p.taps = d.taps;
+    p.shift0 = d.tap_shift[0]; p.shift1 = d.tap_shift[1];
+    p.w = d.w; p.ldw = d.ldw; p.w_tap_stride = (long long)d.n * d.ldw;
+    p.bias = d.bias; p.c = d.c; p.c_bs = d.c_batch_stride; p.c_rs = d.c_row_stride; p.m = d.m; p.n = d.n;
+    p.epi = d.epilogue; p.addend = d.addend; p.add_bs = d.add_batch_stride; p.add_rs = d.add_row_stride;
+    p.a_planes = d.a_planes > 0 ? d.a_planes : 0; p.a_plane_k = d.a_plane_k; p.a_plane0 = d.a_plane0; p.a_plane_step = d.a_plane_step;
+    p.n_half = (d.a_planes > 0 && d.n_half) ? 1 : 0;
+    if (p.a_planes) {
+        CUM_REQUIRE(d.a_plane_k > 0 && d.a_plane_k % 4 == 0, "gemm: plane-major a needs a_plane_k %% 4 == 0");
+        CUM_REQUIRE(!p.n_half || !(d.epilogue >= CUM_EPI_GLU_SIGMOID), "gemm: n_half needs a non-GLU epilogue");
+        if (p.n_half) p.w_tap_stride = 2LL * d.n * d.ldw;
+    }
+    q.w_lo = d.w_lo;
+    q.acc_scale = d.math == CUM_MATH_F16X3 ? d.acc_scale : 1.0f;
+    CUM_REQUIRE(d.math != CUM_MATH_F16X3 || d.acc_scale > 0.f, "gemm: F16X3 needs acc_scale = 1 / (weight scale passed to cum_split_f16)");
+    const dim3 grid((unsigned)cdiv(d.n / 2, SK_WARPS), (unsigned)d.batch);
+    cudaError_t e;
+    switch (d.math) {
+        case CUM_MATH_TF32X3: e = launch_kernel(gemm_skinny_kernel<1>, grid, dim3(SK_WARPS * 32), 0, st, q); break;
+        case CUM_MATH_F16X3:  e = launch_kernel(gemm_skinny_kernel<2>, grid, dim3(SK_WARPS * 32), 0, st, q); break;
+        case CUM_MATH_BF16X3: e = launch_kernel(gemm_skinny_kernel<3>, grid, dim3(SK_WARPS * 32), 0, st, q); break;
+        default:              e = launch_kernel(gemm_skinny_kernel<0>, grid, dim3(SK_WARPS * 32), 0, st, q); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_skinny_kernel)");
     return CUM_OK;
 }
 

@@ -313,10 +313,12 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ op wrappers
     def gemm(self, a, a_off, a_bs, a_rs, a_rows, k, w, bias, c, c_off, c_bs, c_rs, m, n, batch, epi,
              taps=1, shifts=(0, 0), addend=None, add_bs=0, add_rs=0, math=None, a_scale=None, aux=None, aux_bs=0, aux_rs=0, addend_mask=False,
-             planes=None, add_off=0):
+             planes=None, add_off=0, small=0):
         """``planes`` = (a_planes, a_plane_k, a_plane0, a_plane_step, n_half): plane-major ``a`` (cum_gemm_desc.a_planes; the time-major
-        streaming session).  ``add_off``: element offset into ``addend``."""
+        streaming session).  ``add_off``: element offset into ``addend``.  ``small``: cum_gemm_desc.small_m_path (the streaming sessions
+        decide per level from columns x streams, so that both buffer layouts run the same kernel for the same level)."""
         d = GemmDesc()
+        d.small_m_path = small
         if planes is not None:
             d.a_planes, d.a_plane_k, d.a_plane0, d.a_plane_step, d.n_half = planes
         d.a, d.a_batch_stride, d.a_row_stride, d.a_rows, d.k = a.data_ptr() + a.element_size() * a_off, a_bs, a_rs, a_rows, k
@@ -357,13 +359,13 @@ class Engine:
                    flops=2 * batch * m * n * k * taps)
 
     def dense(self, a, rows, k, w, bias, n, epi=EPI_NONE, a_rs=None, a_off=0, addend=None, out=None, out_dtype=torch.float32, aux=None, out_off=0,
-              out_rs=None, add_rs=None):
+              out_rs=None, add_rs=None, small=0):
         """Flat (rows, k) x W^T -> (rows, n or n/2): 1x1 convs and Linear layers.  ``aux`` (rows, n): the pre-activation (training).
         ``a_rs`` / ``out_rs`` / ``add_rs``: row pitches of the operands when they are wider than their logical width."""
         n_out = n // 2 if epi >= 8 else n
         c = out if out is not None else self.act_buffer(rows, n_out, out_dtype, a.device)
         self.gemm(a, a_off, 0, k if a_rs is None else a_rs, rows, k, w, bias, c, out_off, 0, n_out if out_rs is None else out_rs, rows, n, 1, epi,
-                  addend=addend, add_bs=0, add_rs=n_out if add_rs is None else add_rs, aux=aux, aux_rs=n)
+                  addend=addend, add_bs=0, add_rs=n_out if add_rs is None else add_rs, aux=aux, aux_rs=n, small=small)
         return c
 
     @staticmethod

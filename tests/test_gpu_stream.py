@@ -12,6 +12,17 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-5      # fp32, outputs are O(0.1); chunked vs frame-by-frame differ only by summation order
 
 
+@pytest.fixture(autouse=True, params=["time_major", "stream_major"])
+def default_session_layout(request):
+    """Every test of this file runs on both carried-state sessions: stream_session(layout="auto") -- and with it the module-level
+    feed() / flush() -- picks the time-major session from TIME_MAJOR_MIN_STREAMS streams (1: always) or the stream-major one."""
+    from cleanumamba_b200.CleanUMamba import CleanUMamba
+    old = CleanUMamba.TIME_MAJOR_MIN_STREAMS
+    CleanUMamba.TIME_MAJOR_MIN_STREAMS = 1 if request.param == "time_major" else 10 ** 9
+    yield request.param
+    CleanUMamba.TIME_MAJOR_MIN_STREAMS = old
+
+
 def build(fx, **kw):
     from cleanumamba_b200.network import Net
     net = Net("CleanUMamba", {**json.loads(fx["config"]), **kw})

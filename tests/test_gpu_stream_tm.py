@@ -72,10 +72,46 @@ def test_plane_major_gemm_as_strided_conv_and_transposed_conv(math, streams, cin
 
 def test_plane_major_gemm_rejects_unaligned_planes():
     from cleanumamba_b200 import _lib, ops
-    fifo = torch.zeros(4, 16, 40, device=dev())
+    fifo = torch.zeros(4, 200, 40, device=dev())       # 200 streams: the tensor-core path (a few rows would take the CUDA-core small-M path)
     w = torch.zeros(2, 16, 80, device=dev())
     with pytest.raises(RuntimeError, match="a_plane_k"):
         ops.gemm_bias_act(fifo, w, None, _lib.EPI_RELU, shifts=(0, 1), math="f16x3", plane_major=dict(batch=1, plane0=0, step=2))
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3", "f16x3"])
+@pytest.mark.parametrize("streams,cin,cout,cols", [(1, 64, 128, 7), (2, 768, 768, 1), (3, 40, 56, 5), (1, 256, 512, 33)])
+def test_small_m_gemm_path_matches_pytorch(math, streams, cin, cout, cols):
+    """A few output rows in total (one stream fed hop by hop): cum_gemm_desc.small_m_path -- CUDA-core kernel, exact fp32 FMAs on the
+    full-precision weights -- for the pointwise / GLU / strided-conv / transposed-conv forms, stream-major and plane-major."""
+    from cleanumamba_b200 import _lib, ops
+    g = torch.Generator().manual_seed(streams + cin + cout + cols)
+    tol = {"fp32": 2e-6, "tf32x3": 2e-6, "f16x3": 4e-6, "bf16x3": 6e-5}[math]       # weight precision of the mode: 24 / 24 / 22 / 16 bits
+    x = torch.randn(streams, cin, cols, generator=g)
+    w, bias = torch.randn(cout, cin, generator=g) / cin ** 0.5, torch.randn(cout, generator=g)
+    ref = F.conv1d(x, w[:, :, None], bias)
+    a = x.permute(0, 2, 1).contiguous().to(dev())
+    y = ops.gemm_bias_act(a, w[None].contiguous().to(dev()), bias.to(dev()), _lib.EPI_RELU, math=math)
+    assert rel_err(y.permute(0, 2, 1), F.relu(ref)) < tol
+    H = cout // 2
+    wi = torch.stack([w[:H], w[H:]], 1).reshape(cout, cin)
+    bi = torch.stack([bias[:H], bias[H:]], 1).reshape(cout)
+    add = torch.randn(streams, cols, H, generator=g)
+    yg = ops.gemm_bias_act(a, wi[None].contiguous().to(dev()), bi.to(dev()), _lib.EPI_GLU["Sigmoid"], addend=add.to(dev()), math=math)
+    assert rel_err(yg.permute(0, 2, 1), orc.glu(ref) + add.permute(0, 2, 1)) < tol
+    if cin % 32 or cols > 8:
+        return
+    # strided conv on a plane-major FIFO: (column, stream, channel), columns lo .. lo + 2 cols + 1
+    lo = 1
+    xf = torch.randn(streams, cin, lo + 2 * cols + 2, generator=g)
+    wc, bc = torch.randn(cout, cin, 4, generator=g) / (4 * cin) ** 0.5, torch.randn(cout, generator=g)
+    refc = F.relu(F.conv1d(xf[:, :, lo:], wc, bc, stride=2))[:, :, :cols]
+    wt = torch.zeros(2, cout, 2 * cin)
+    for s_ in range(2):
+        for j in range(2):
+            wt[s_, :, j * cin:(j + 1) * cin] = wc[:, :, 2 * s_ + j]
+    fifo = xf.permute(2, 0, 1).contiguous().to(dev())
+    yc = ops.gemm_bias_act(fifo, wt.to(dev()), bc.to(dev()), _lib.EPI_RELU, shifts=(0, 1), math=math, plane_major=dict(batch=cols, plane0=lo, step=2))
+    assert rel_err(yc.permute(1, 2, 0), refc) < tol
 
 
 def test_stream_shift_kernel_matches_torch():
@@ -242,12 +278,12 @@ def test_auto_layout_picks_time_major_for_many_streams_only():
     net = toy("f16x3", False)
     assert isinstance(net.stream_session(batch=64), TimeMajorStreamSession)
     assert isinstance(net.stream_session(batch=net.TIME_MAJOR_MIN_STREAMS), TimeMajorStreamSession)
-    assert not isinstance(net.stream_session(batch=net.TIME_MAJOR_MIN_STREAMS - 1), TimeMajorStreamSession)
-    assert not isinstance(net.stream_session(batch=1), TimeMajorStreamSession)
+    assert isinstance(net.stream_session(batch=1), TimeMajorStreamSession)
+    assert not isinstance(net.stream_session(batch=64, layout="stream_major"), TimeMajorStreamSession)
     odd = toy("f16x3", False, channels_H=24, max_H=40)             # channel counts that are not whole K-blocks: planes padded to 32
     assert isinstance(odd.stream_session(batch=64), TimeMajorStreamSession)
     with pytest.raises(NotImplementedError):
-        net.stream_session(batch=2, state_dtype=torch.float16)
+        net.stream_session(batch=2, layout="stream_major", state_dtype=torch.float16)
     with pytest.raises(ValueError):
         net.stream_session(batch=4, layout="columns")
 
