@@ -182,7 +182,7 @@ int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Skinny tap-GEMM: the whole problem has at most SK_MAX_ROWS output rows (one stream fed hop by hop -- the reference's real-time use,
+// Skinny tap-GEMM: the whole problem is a few output rows (one stream fed hop by hop -- the reference's real-time use,
 // CleanUMamba.py:371-418 / examples/streaming_demo.py -- or a handful of streams: every GEMM of a call is 1-33 rows).  The tcgen05
 // kernel is a persistent pipeline (TMEM allocation, barrier ring, tensor-map prefetch, 128-row tiles): ~14 us per launch whatever the
 // size, 36 launches per hop.  Here a warp owns TWO output columns (one GLU pair) for up to 8 rows, its lanes split K (coalesced
@@ -190,7 +190,12 @@ int gemm_simt_fwd(const cum_gemm_desc& d, cudaStream_t st) {
 // activation / gate, addend).  Products are exact fp32 FMAs on the full-precision weights (split modes: hi + lo halves), so this
 // path is at least as accurate as the tensor-core modes it stands in for.  Same descriptor semantics as the kernels above.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int SK_MAX_ROWS = 64;     // m * batch up to which cum_gemm_bias_act_fwd takes this path
+constexpr int SK_AUTO_ROWS = 4;                 // automatic choice: at most 4 output rows in total (m * batch) ...
+constexpr long long SK_MAX_MACS = 16000000;     // ... and at most 16 M multiply-adds.  The kernel runs at ~0.4 TMAC/s with ~4 us of fixed cost
+                                               // against ~14 us for the tensor-core launch, and it loses efficiency with the rows per pass.
+                                               // Measured (E6 full, 1 hop per call from the graph; every GEMM here vs none): 1 stream 0.40 vs
+                                               // 0.73 ms, 2 streams 0.45 vs 0.73, 4 streams 0.59 vs 0.73, 8 streams 0.83 vs 0.74, 16 streams
+                                               // 1.37 vs 0.75; mixed per-GEMM rules by bytes or work were worse than all-or-nothing from 8 streams
 constexpr int SK_M = 8;             // rows per warp pass
 constexpr int SK_WARPS = 4;
 
@@ -297,7 +302,7 @@ bool gemm_skinny_ok(const cum_gemm_desc& d) {
     if ((d.math == CUM_MATH_TF32X3 || d.math == CUM_MATH_BF16X3 || d.math == CUM_MATH_F16X3) && !d.w_lo) return false;
     if (d.math != CUM_MATH_FP32 && d.math != CUM_MATH_TF32X3 && d.ldw % 8) return false;       // 16-bit weight rows: 8-byte aligned quads
     if (d.small_m_path) return d.small_m_path > 0;
-    return (long long)d.m * d.batch <= SK_MAX_ROWS;
+    return (long long)d.batch * d.m <= SK_AUTO_ROWS && (long long)d.batch * d.m * d.n * d.k * d.taps <= SK_MAX_MACS;
 }
 
 int gemm_skinny_fwd(const cum_gemm_desc& d, cudaStream_t st) {

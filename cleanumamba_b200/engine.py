@@ -411,7 +411,7 @@ class Engine:
                    nbytes=4 * B * T * (4 * mm["di"] + 2 * mm["N"]), flops=B * T * mm["di"] * mm["N"], launches=1 if ws is None else 3)
         del ws
 
-    def mamba_layers(self, h, B, T, states=None, tm=False):
+    def mamba_layers(self, h, B, T, states=None, tm=False, small=0):
         """h: (B*T, dm_p) output of tsfm_conv1 -> normed (B*T, dm_p) after norm_f.  ``states``: optional list of
         (conv_state (B, W-1, di_p), ssm_state (B, di_p, N_p)) carried in place (streaming; an fp16 ssm_state selects the
         reduced-precision state variant).  ``tm``: rows are time-major (t * B + b) instead of (b * T + t)."""
@@ -426,7 +426,7 @@ class Engine:
             res_out = res if res is not None else torch.empty(rows, dm_p, dtype=torch.float32, device=dev)
             self.ln(h, res, res_out, hn, pk[f"m{l}.g"], pk[f"m{l}.be"], mm["eps"], rows, dm, dm_p)
             res = res_out
-            xz = self.dense(hn, rows, dm_p, f"m{l}.in", None, 2 * di_p)
+            xz = self.dense(hn, rows, dm_p, f"m{l}.in", None, 2 * di_p, small=small)
             xc = torch.empty(rows, di_p, dtype=torch.float32, device=dev)
             cs = states[l][0] if states is not None else None
             n_l = 1 + (cs is not None and T > 16)      # up to 16 tokens the kernel writes the new conv state itself
@@ -438,12 +438,12 @@ class Engine:
                 self._call("dwconv_silu", self.lib.cum_dwconv_silu_fwd, xz.data_ptr(), T * 2 * di_p, 2 * di_p,
                            pk[f"m{l}.cw"].data_ptr(), pk[f"m{l}.cb"].data_ptr(), xc.data_ptr(), ptr(cs), ptr(cs), B, T, di_p,
                            mm["W"], _lib.stream_ptr(), launches=n_l, nbytes=8 * rows * mm["di"])
-            xdbl = self.dense(xc, rows, di_p, f"m{l}.xp", None, R_p + 2 * N_p)
-            dt = self.dense(xdbl, rows, R_p, f"m{l}.dtw", None, di_p, a_rs=R_p + 2 * N_p)
+            xdbl = self.dense(xc, rows, di_p, f"m{l}.xp", None, R_p + 2 * N_p, small=small)
+            dt = self.dense(xdbl, rows, R_p, f"m{l}.dtw", None, di_p, a_rs=R_p + 2 * N_p, small=small)
             y = torch.empty(rows, di_p, dtype=torch.float32, device=dev)
             hs = states[l][1] if states is not None else None
             self.scan(xc, dt, xz, xdbl, y, l, mm, B, T, h0=hs, h_out=hs, tm=tm)
-            h = self.dense(y, rows, di_p, f"m{l}.out", None, dm_p)
+            h = self.dense(y, rows, di_p, f"m{l}.out", None, dm_p, small=small)
         self.ln(h, res, None, hn, pk["nf.g"], pk["nf.be"], meta["eps"], rows, dm, dm_p)
         return hn
 

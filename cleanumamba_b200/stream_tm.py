@@ -276,20 +276,20 @@ class TimeMajorStreamSession(StreamSession):
                 lo = 2 * c_old - self.enc_base[i - 1]                    # plane of the first input column this call needs
                 # output column t of every stream = W01 . [plane lo+2t | plane lo+2t+1] + W23 . [plane lo+2t+2 | lo+2t+3]
                 eng.gemm(src, 0, B * cq, cq, B, 2 * cq, wkey, pk[f"enc{i}.b"], y, 0, B * e["Hc_p"], e["Hc_p"], B, e["Hc_p"],
-                         rows_new, EPI_RELU, taps=2, shifts=(0, 1), planes=(fill[i - 1] + cols[i - 1], cq, lo, 2, 0), small=self._small(rows_new))
+                         rows_new, EPI_RELU, taps=2, shifts=(0, 1), planes=(fill[i - 1] + cols[i - 1], cq, lo, 2, 0), small=self._small(rows_new, f"enc{i}.w"))
             ho, hoq = e["Ho_p"], e["Hoq"]
             self.enc_fifo[i] = self._grow_planes(self.enc_fifo[i], fill[i] + rows_new, fill[i])
             # the GLU 1x1 conv appends its planes to the level's FIFO directly
             eng.dense(y, rows_new * B, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * ho, epi=act, out=self.enc_fifo[i],
-                      out_off=fill[i] * B * hoq, out_rs=hoq, small=self._small(rows_new))
+                      out_off=fill[i] * B * hoq, out_rs=hoq, small=self._small(rows_new, f"enc{i}.wg"))
 
         # ---------------- bottleneck: F tokens per stream, time-major rows (t * B + b)
         last = self.enc_fifo[D - 1]
         cbp, cbq = meta["enc"][-1]["Ho_p"], meta["enc"][-1]["Hoq"]
         assert fill[D - 1] + cols[D - 1] == F, (fill[D - 1], cols[D - 1], F)
-        h = eng.dense(last, B * F, cbp, "t1.w", pk["t1.b"], meta["dm_p"], a_rs=cbq, small=self._small(F))
-        hn = eng.mamba_layers(h, B, F, states=self.states, tm=True)
-        xcur = eng.dense(hn, B * F, meta["dm_p"], "t2.w", pk["t2.b"], cbp, addend=last, add_rs=cbq, small=self._small(F))
+        h = eng.dense(last, B * F, cbp, "t1.w", pk["t1.b"], meta["dm_p"], a_rs=cbq, small=self._small(F, "t1.w"))
+        hn = eng.mamba_layers(h, B, F, states=self.states, tm=True, small=self._small(F, "m0.in"))
+        xcur = eng.dense(hn, B * F, meta["dm_p"], "t2.w", pk["t2.b"], cbp, addend=last, add_rs=cbq, small=self._small(F, "t2.w"))
         x_rs = cbp                                      # row pitch of xcur
 
         # ---------------- decoder
@@ -299,7 +299,7 @@ class TimeMajorStreamSession(StreamSession):
             hg, hgq = dd["Hg_p"], dd["Hgq"]
             self.dec_fifo[j] = G = self._grow_planes(self.dec_fifo[j], d_cols + 1, 1)
             eng.dense(xcur, B * d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * hg, epi=act, out=G, out_off=B * hgq, out_rs=hgq,
-                      a_rs=x_rs, small=self._small(d_cols))
+                      a_rs=x_rs, small=self._small(d_cols, f"dec{j}.wg"))
             shifts.append((G, 0, d_cols * B * hgq, B * hgq, 1))          # the last column becomes the carried one
             if j < D - 1:
                 coq = dd["Coq"]
@@ -310,7 +310,7 @@ class TimeMajorStreamSession(StreamSession):
                 # output column 2p + par of every stream = Wa_par . G[p + 1] + Wb_par . G[p] + skip column 2p + par (read in place)
                 eng.gemm(G, 0, B * hgq, hgq, B, hgq, wkey, pk[bkey], nxt, 0, B * coq, coq, B, coq, 2 * d_cols, EPI_RELU,
                          taps=2, shifts=(1, 0), addend=skip, add_bs=B * skq, add_rs=skq, planes=(d_cols + 1, hgq, 0, 1, 1),
-                         small=self._small(2 * d_cols))
+                         small=self._small(2 * d_cols, f"dec{j}.w", half=True))
                 xcur, x_rs = nxt, coq
                 d_cols = 2 * d_cols
             else:

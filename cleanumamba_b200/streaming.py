@@ -22,6 +22,7 @@ The reference's skip-index bug (:474) is NOT reproduced (it crashes on every shi
 from __future__ import annotations
 
 import functools
+import os
 
 import torch
 
@@ -39,12 +40,21 @@ def _on_device(fn):
 
 class StreamSession:
     BATCH_MODE_ROWS = 128     # rows per stream from which a level runs one GEMM batch item per stream (in-place operands)
-    SMALL_ROWS = 64           # columns x streams of a level up to which its GEMMs take the CUDA-core small-M path (cum_gemm_desc.small_m_path);
-                              # decided from (columns, streams) so that the stream-major and the time-major session agree per level
-
-    def _small(self, cols: int) -> int:
-        return 1 if cols * self.B <= self.SMALL_ROWS else -1
     AUTO_GRAPH_AFTER = 3      # auto_graph sessions: identical chunks seen before the step is captured as a CUDA graph
+    SMALL_STREAMS = int(os.environ.get("CUM_STREAM_SMALL_STREAMS", 4))
+    SMALL_MACS = int(float(os.environ.get("CUM_STREAM_SMALL_MMAC", 16)) * 1e6)
+    # Sessions of up to SMALL_STREAMS streams run the GEMMs of a call on the CUDA-core small-M path (cum_gemm_desc.small_m_path: ~10 us
+    # less fixed cost per launch than the tensor-core pipeline, ~0.4 TMAC/s) as long as a GEMM stays under SMALL_MACS multiply-adds
+    # (multi-hop calls of a single stream go back to the tensor cores).  Decided from (columns, streams, weight shape) -- not from the
+    # GEMM's own m / batch, which differ between the two buffer layouts -- so that the stream-major and the time-major session run
+    # the same kernel for the same level.  Measured per 1-hop call from the graph, all GEMMs small-M vs none: 1 stream 0.40 vs
+    # 0.73 ms, 2 streams 0.45 vs 0.73, 4 streams 0.59 vs 0.73, 8 streams 0.83 vs 0.74
+
+    def _small(self, cols: int, w: str, half: bool = False) -> int:
+        if self.B > self.SMALL_STREAMS:
+            return -1
+        macs = cols * self.B * self.eng.pk[w].numel() // (2 if half else 1)
+        return 1 if macs <= self.SMALL_MACS else -1
 
     def __init__(self, model, batch: int = 1, auto_graph: bool = False):
         self.auto_graph, self._same, self._last_n = auto_graph, 0, -1
@@ -292,7 +302,7 @@ class StreamSession:
                 cin = src[:, lo: lo + 2 * P].contiguous()       # (B, 2P, cp) == B*P rows of 2*cp
                 y = torch.empty(B * P, e["Hc_p"], dtype=torch.float32, device=dev)
                 eng.gemm(cin, 0, 0, 2 * cp, B * P, 2 * cp, f"enc{i}.w", pk[f"enc{i}.b"],
-                         y, 0, 0, e["Hc_p"], B * P, e["Hc_p"], 1, EPI_RELU, taps=2, shifts=(0, 1), small=self._small(rows_new))
+                         y, 0, 0, e["Hc_p"], B * P, e["Hc_p"], 1, EPI_RELU, taps=2, shifts=(0, 1), small=self._small(rows_new, f"enc{i}.w"))
             # output FIFO of this level: [columns the decoder has not consumed yet | new columns]
             keep = c_old - self.enc_base[i]
             buf = torch.empty(B, keep + rows_new, e["Ho_p"], dtype=torch.float32, device=dev)
@@ -304,7 +314,7 @@ class StreamSession:
                 eng.gemm(y, 0, P * e["Hc_p"], e["Hc_p"], P, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"],
                          buf, keep * ho, (keep + rows_new) * ho, ho, rows_new, 2 * ho, B, act)
             else:
-                newc = eng.dense(y, B * P, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act, small=self._small(rows_new))
+                newc = eng.dense(y, B * P, e["Hc_p"], f"enc{i}.wg", pk[f"enc{i}.bg"], 2 * e["Ho_p"], epi=act, small=self._small(rows_new, f"enc{i}.wg"))
                 buf[:, keep:].copy_(newc.view(B, P, e["Ho_p"])[:, :rows_new])
             self.enc_buf[i] = buf
             self.enc_count[i] = c_new
@@ -314,9 +324,9 @@ class StreamSession:
         last = self.enc_buf[D - 1]
         cbp = meta["enc"][-1]["Ho_p"]
         assert last.shape[1] == F, (last.shape, F)
-        h = eng.dense(last, B * F, cbp, "t1.w", pk["t1.b"], meta["dm_p"], small=self._small(F))
-        hn = eng.mamba_layers(h, B, F, states=self.states)
-        xcur = eng.dense(hn, B * F, meta["dm_p"], "t2.w", pk["t2.b"], cbp, addend=last, small=self._small(F))
+        h = eng.dense(last, B * F, cbp, "t1.w", pk["t1.b"], meta["dm_p"], small=self._small(F, "t1.w"))
+        hn = eng.mamba_layers(h, B, F, states=self.states, small=self._small(F, "m0.in"))
+        xcur = eng.dense(hn, B * F, meta["dm_p"], "t2.w", pk["t2.b"], cbp, addend=last, small=self._small(F, "t2.w"))
         self.enc_base[D - 1] += F
         self.enc_buf[D - 1] = last[:, F:]
 
@@ -332,7 +342,7 @@ class StreamSession:
                 eng.gemm(xcur, 0, d_cols * dd["Cin_p"], dd["Cin_p"], d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"],
                          G, hg, (d_cols + 1) * hg, hg, d_cols, 2 * hg, B, act)
             else:
-                gnew = eng.dense(xcur, B * d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * hg, epi=act, small=self._small(d_cols))
+                gnew = eng.dense(xcur, B * d_cols, dd["Cin_p"], f"dec{j}.wg", pk[f"dec{j}.bg"], 2 * hg, epi=act, small=self._small(d_cols, f"dec{j}.wg"))
                 G[:, 1:].copy_(gnew.view(B, d_cols, hg))
             self.dec_carry[j] = G[:, d_cols].clone()
             if j < D - 1 and batch_mode:
@@ -357,7 +367,7 @@ class StreamSession:
                 nxt = torch.empty(B * Pd, 2 * co, dtype=torch.float32, device=dev)
                 # flat row b*Pd + p = Wa . G[b, p+1] + Wb . G[b, p]; p = d_cols is the junk row of stream b
                 eng.gemm(G, 0, 0, hg, B * Pd, hg, f"dec{j}.w", pk[f"dec{j}.b"], nxt, 0, 0, 2 * co, B * Pd, 2 * co, 1,
-                         EPI_RELU, taps=2, shifts=(1, 0), addend=skipc, add_bs=0, add_rs=2 * co, small=self._small(2 * d_cols))
+                         EPI_RELU, taps=2, shifts=(1, 0), addend=skipc, add_bs=0, add_rs=2 * co, small=self._small(2 * d_cols, f"dec{j}.w", half=True))
                 self.enc_base[lvl] += 2 * d_cols
                 self.enc_buf[lvl] = skip[:, 2 * d_cols:]
                 xcur = nxt.view(B, Pd, 2 * co)[:, :d_cols].reshape(B * 2 * d_cols, co)

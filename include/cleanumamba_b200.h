@@ -196,10 +196,11 @@ typedef struct cum_gemm_desc {
      * (b & 1) * n .. + n, `bias` (n entries) is shared by both halves: a transposed conv writes its even / odd output columns as
      * separate planes (c_batch_stride apart). */
     int a_planes; int a_plane_k; int a_plane0; int a_plane_step; int n_half;
-    int small_m_path;        /* problems of at most 64 output rows in total (m * batch; one or two streams fed hop by hop -- the reference's
-                                real-time use) run on a CUDA-core kernel instead of the persistent tensor-core pipeline, whose fixed cost
-                                (~14 us per launch) dominates there: exact fp32 FMAs on the full-precision weights (hi + lo halves in the
-                                split modes).  0 = automatic by size, 1 = force (any size), -1 = never.  Not for bf16 / hl16 operands */
+    int small_m_path;        /* problems of a few output rows in total (a handful of streams fed hop by hop -- the reference's real-time
+                                use) run on a CUDA-core kernel instead of the persistent tensor-core pipeline, whose fixed cost (~14 us
+                                per launch) dominates there: exact fp32 FMAs on the full-precision weights (hi + lo halves in the split
+                                modes).  0 = automatic: at most 4 output rows in total and 16 M multiply-adds;
+                                1 = force (any size), -1 = never.  Not for bf16 / hl16 operands */
 } cum_gemm_desc;
 int cum_gemm_bias_act_fwd(const cum_gemm_desc* desc, cum_stream_t stream);
 

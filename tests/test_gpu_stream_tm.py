@@ -72,14 +72,14 @@ def test_plane_major_gemm_as_strided_conv_and_transposed_conv(math, streams, cin
 
 def test_plane_major_gemm_rejects_unaligned_planes():
     from cleanumamba_b200 import _lib, ops
-    fifo = torch.zeros(4, 200, 40, device=dev())       # 200 streams: the tensor-core path (a few rows would take the CUDA-core small-M path)
+    fifo = torch.zeros(4, 200, 40, device=dev())       # 200 streams: the tensor-core path (up to 4 output rows take the CUDA-core small-M path)
     w = torch.zeros(2, 16, 80, device=dev())
     with pytest.raises(RuntimeError, match="a_plane_k"):
         ops.gemm_bias_act(fifo, w, None, _lib.EPI_RELU, shifts=(0, 1), math="f16x3", plane_major=dict(batch=1, plane0=0, step=2))
 
 
 @pytest.mark.parametrize("math", ["fp32", "tf32x3", "bf16x3", "f16x3"])
-@pytest.mark.parametrize("streams,cin,cout,cols", [(1, 64, 128, 7), (2, 768, 768, 1), (3, 40, 56, 5), (1, 256, 512, 33)])
+@pytest.mark.parametrize("streams,cin,cout,cols", [(1, 64, 128, 4), (2, 768, 768, 1), (2, 40, 56, 2), (1, 256, 512, 3)])
 def test_small_m_gemm_path_matches_pytorch(math, streams, cin, cout, cols):
     """A few output rows in total (one stream fed hop by hop): cum_gemm_desc.small_m_path -- CUDA-core kernel, exact fp32 FMAs on the
     full-precision weights -- for the pointwise / GLU / strided-conv / transposed-conv forms, stream-major and plane-major."""
@@ -98,7 +98,7 @@ def test_small_m_gemm_path_matches_pytorch(math, streams, cin, cout, cols):
     add = torch.randn(streams, cols, H, generator=g)
     yg = ops.gemm_bias_act(a, wi[None].contiguous().to(dev()), bi.to(dev()), _lib.EPI_GLU["Sigmoid"], addend=add.to(dev()), math=math)
     assert rel_err(yg.permute(0, 2, 1), orc.glu(ref) + add.permute(0, 2, 1)) < tol
-    if cin % 32 or cols > 8:
+    if cin % 32:
         return
     # strided conv on a plane-major FIFO: (column, stream, channel), columns lo .. lo + 2 cols + 1
     lo = 1
