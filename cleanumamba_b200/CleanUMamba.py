@@ -168,7 +168,7 @@ class CleanUMamba(nn.Module):
                 for i, blk in enumerate(self.tsfm_Mamba_layers)}
 
     TIME_MAJOR_MIN_STREAMS = 1      # from this many concurrent streams the session keeps its buffers (column, stream, channel).  Measured
-                                    # (E6 full, 1 hop per call from the graph): 1 stream 0.47 -> 0.41 ms, 2 streams 0.60 -> 0.46 ms, 64 streams
+                                    # (E6 full, 1 hop per call from the graph; small-M GEMM path of its first version): 1 stream 0.47 -> 0.41 ms, 2 streams 0.60 -> 0.46 ms, 64 streams
                                     # 0.89 -> 0.79 ms, 4096 streams 5.05 -> 3.99 ms: time-major at every stream count; layout="stream_major"
                                     # keeps the other session available
 

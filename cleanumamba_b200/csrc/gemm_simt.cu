@@ -223,8 +223,10 @@ __device__ __forceinline__ float4 sk_load_w(const void* w, const void* w_lo, lon
 
 struct SkinnyParams { SimtParams s; const void* w_lo; float acc_scale; };
 
-template <int WF>
+// RM: rows per pass (1, 2, 4 or 8: the few-row cases keep more weight loads in flight -- a lane's K loop is a chain of L2 round trips)
+template <int WF, int RM>
 __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const SkinnyParams q) {
+    constexpr int SK_M = RM;
     pdl_trigger();
     pdl_wait();          // PDL: nothing of the previous kernel is touched before this point
     const SimtParams& p = q.s;
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const Skinny
         for (int tap = 0; tap < p.taps; ++tap) {
             const int shift = tap == 0 ? p.shift0 : p.shift1;
             const long long wrow = (long long)tap * p.w_tap_stride + (long long)(n + nh_off) * p.ldw;
-#pragma unroll 2
+#pragma unroll (RM <= 2 ? 8 : (RM == 4 ? 4 : 2))
             for (int kk = lane * 4; kk < p.k; kk += 128) {
                 const float4 w0 = sk_load_w<WF>(p.w, q.w_lo, wrow + kk);
                 const float4 w1 = sk_load_w<WF>(p.w, q.w_lo, wrow + p.ldw + kk);
@@ -325,12 +327,18 @@ int gemm_skinny_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     CUM_REQUIRE(d.math != CUM_MATH_F16X3 || d.acc_scale > 0.f, "gemm: F16X3 needs acc_scale = 1 / (weight scale passed to cum_split_f16)");
     const dim3 grid((unsigned)cdiv(d.n / 2, SK_WARPS), (unsigned)d.batch);
     cudaError_t e;
-    switch (d.math) {
-        case CUM_MATH_TF32X3: e = launch_kernel(gemm_skinny_kernel<1>, grid, dim3(SK_WARPS * 32), 0, st, q); break;
-        case CUM_MATH_F16X3:  e = launch_kernel(gemm_skinny_kernel<2>, grid, dim3(SK_WARPS * 32), 0, st, q); break;
-        case CUM_MATH_BF16X3: e = launch_kernel(gemm_skinny_kernel<3>, grid, dim3(SK_WARPS * 32), 0, st, q); break;
-        default:              e = launch_kernel(gemm_skinny_kernel<0>, grid, dim3(SK_WARPS * 32), 0, st, q); break;
+    const int wf = d.math == CUM_MATH_TF32X3 ? 1 : d.math == CUM_MATH_F16X3 ? 2 : d.math == CUM_MATH_BF16X3 ? 3 : 0;
+    const int rm = d.m <= 1 ? 1 : d.m <= 2 ? 2 : d.m <= 4 ? 4 : 8;
+#define SK_LAUNCH(WF, RM) e = launch_kernel(gemm_skinny_kernel<WF, RM>, grid, dim3(SK_WARPS * 32), 0, st, q)
+#define SK_ROWS(WF) do { if (rm == 1) SK_LAUNCH(WF, 1); else if (rm == 2) SK_LAUNCH(WF, 2); else if (rm == 4) SK_LAUNCH(WF, 4); else SK_LAUNCH(WF, 8); } while (0)
+    switch (wf) {
+        case 1: SK_ROWS(1); break;
+        case 2: SK_ROWS(2); break;
+        case 3: SK_ROWS(3); break;
+        default: SK_ROWS(0); break;
     }
+#undef SK_ROWS
+#undef SK_LAUNCH
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_skinny_kernel)");
     return CUM_OK;
 }

@@ -47,8 +47,8 @@ class StreamSession:
     # less fixed cost per launch than the tensor-core pipeline, ~0.4 TMAC/s) as long as a GEMM stays under SMALL_MACS multiply-adds
     # (multi-hop calls of a single stream go back to the tensor cores).  Decided from (columns, streams, weight shape) -- not from the
     # GEMM's own m / batch, which differ between the two buffer layouts -- so that the stream-major and the time-major session run
-    # the same kernel for the same level.  Measured per 1-hop call from the graph, all GEMMs small-M vs none: 1 stream 0.40 vs
-    # 0.73 ms, 2 streams 0.45 vs 0.73, 4 streams 0.59 vs 0.73, 8 streams 0.83 vs 0.74
+    # the same kernel for the same level.  Measured per 1-hop call from the graph, all GEMMs small-M vs none: 1 stream 0.32 vs
+    # 0.73 ms, 2 streams 0.35 vs 0.73, 4 streams 0.49 vs 0.73, 8 streams 0.83 vs 0.74
 
     def _small(self, cols: int, w: str, half: bool = False) -> int:
         if self.B > self.SMALL_STREAMS:
