@@ -328,6 +328,8 @@ int gemm_skinny_fwd(const cum_gemm_desc& d, cudaStream_t st) {
     const dim3 grid((unsigned)cdiv(d.n / 2, SK_WARPS), (unsigned)d.batch);
     cudaError_t e;
     const int wf = d.math == CUM_MATH_TF32X3 ? 1 : d.math == CUM_MATH_F16X3 ? 2 : d.math == CUM_MATH_BF16X3 ? 3 : 0;
+    // rows per pass; m > 4 keeps 8 rows per pass (two 4-row passes measured slower: 0.96 vs 0.82 ms per call at 8 streams -- and both
+    // slower than the tensor-core path there, 0.74 ms: the sessions use this kernel up to 4 streams)
     const int rm = d.m <= 1 ? 1 : d.m <= 2 ? 2 : d.m <= 4 ? 4 : 8;
 #define SK_LAUNCH(WF, RM) e = launch_kernel(gemm_skinny_kernel<WF, RM>, grid, dim3(SK_WARPS * 32), 0, st, q)
 #define SK_ROWS(WF) do { if (rm == 1) SK_LAUNCH(WF, 1); else if (rm == 2) SK_LAUNCH(WF, 2); else if (rm == 4) SK_LAUNCH(WF, 4); else SK_LAUNCH(WF, 8); } while (0)
