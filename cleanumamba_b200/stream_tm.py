@@ -27,8 +27,6 @@ read + write is the HBM floor of a one-hop call, is stored as fp16 (recurrence s
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from . import _lib

@@ -3,9 +3,7 @@ under the tensor-bound GEMMs of another) vs one full-batch session.  E6 full, S 
 Measured on B200 (4096 streams): 1 hop 3.98 ms (one session) vs 4.51 (2 parts) / 4.14 (2 parts, second part started after the first
 part's encoder via an event inside _process) / 4.65 (4 parts); 2 hops 5.27 vs 5.64 / 5.49 / 5.84 -- SLOWER: a GEMM CTA needs a whole
 SM's shared memory and cannot co-reside with the state-update CTAs, and the part-batch GEMMs fill the machine worse.  Not adopted."""
-import json
 import sys
-import time
 
 import torch
 
