@@ -21,6 +21,14 @@
  * DATA LAYOUT.  Activations are channels-last: a (batch, time, channels) fp32 array whose channel
  * count is padded to a multiple of 8 (pad lanes are kept at 0 by zero-padded packed weights).  The
  * reference's NCL tensors only exist at the waveform ends, where C == 1 and both layouts coincide.
+ * The carried caches of feed() (CleanUMamba.py:432-442,476-484) are kept time-major, (column, stream, channel), by the
+ * streaming host (cleanumamba_b200/stream_tm.py): see "ABI v3" below.
+ *
+ * ABI HISTORY.  v1: offline forward, streaming, backward.  v2: cum_shutdown, fused first / last U-Net blocks, segment-parallel scan
+ * workspace, device-side gradient scales, fused MR-STFT loss kernels, channel importances.  v3: plane-major tap-GEMM operands
+ * (a_planes / n_half) and the small-M path (small_m_path) in cum_gemm_desc, fp16 carried state (state_f16) in cum_scan_desc, strided
+ * conv_in / convt_out / dwconv_silu, cum_stream_shift_fwd.  Descriptors only grow at their end; zero-initialised new fields select
+ * the previous behaviour.
  */
 #ifndef CLEANUMAMBA_B200_H_
 #define CLEANUMAMBA_B200_H_
